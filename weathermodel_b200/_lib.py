@@ -1,0 +1,90 @@
+"""ctypes binding of libwm_b200.so (the C ABI declared in include/wm_b200.h).
+
+The product path has NO fallback: if the shared library is missing this module raises at import of
+`lib()`; if a call returns non-zero, `check()` raises RuntimeError with the library's own message.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwm_b200.so")
+
+_vp, _i, _i64, _u64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
+
+
+class GemmEpilogue(C.Structure):
+    _fields_ = [
+        ("bias", _vp), ("relu", _i), ("dropout_p", _f), ("seed", _u64), ("stream_id", _u64),
+        ("gate_bf16", _vp), ("ld_gate", _i), ("gate_scale", _f), ("residual_bf16", _vp), ("ld_res", _i),
+    ]
+
+
+class EncoderConfig(C.Structure):
+    _fields_ = [
+        ("B", _i), ("S", _i), ("F", _i), ("D", _i), ("H", _i), ("L", _i), ("FF", _i), ("out_dim", _i),
+        ("dropout_p", _f), ("ln_eps", _f),
+    ]
+
+
+# name -> (restype, argtypes); kept in the order of include/wm_b200.h
+SIGNATURES = {
+    "wm_abi_version": (_i, []),
+    "wm_strerror": (C.c_char_p, [_i]),
+    "wm_device_error": (_i, []),
+    "wm_rand_grid_x": (_i, [_i64]),
+    "wm_mask_bert": (_i, [_u64, _u64, _i, _f, _i64, _vp, _vp, _vp]),
+    "wm_mask_former": (_i, [_u64, _u64, _i, _i, _i64, _i, _vp, _vp]),
+    "wm_embed_fwd": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "wm_gemm_tn": (_i, [_vp, _i, _vp, _i, _i, _i, _i, C.POINTER(GemmEpilogue), _vp, _i, _i, _i, _vp]),
+    "wm_gemm_wgrad_workspace_bytes": (_sz, [_i, _i, _i]),
+    "wm_gemm_wgrad": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "wm_umma_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "wm_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _u64, _u64, _vp]),
+    "wm_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _u64, _u64, _vp]),
+    "wm_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "wm_layernorm_bwd_workspace_bytes": (_sz, [_i, _i]),
+    "wm_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _u64, _u64, _vp, _vp]),
+    "wm_colsum_workspace_bytes": (_sz, [_i, _i]),
+    "wm_colsum": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "wm_loss_bert": (_i, [_vp, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp]),
+    "wm_loss_former": (_i, [_vp, _i, _vp, _vp, _i64, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "wm_adam_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp]),
+    "wm_encoder_param_count": (_i64, [C.POINTER(EncoderConfig)]),
+    "wm_encoder_param_layout": (_i, [C.POINTER(EncoderConfig), C.POINTER(_i64), _i]),
+    "wm_encoder_workspace_bytes": (_sz, [C.POINTER(EncoderConfig)]),
+    "wm_encoder_create": (_i, [C.POINTER(EncoderConfig), _vp, _sz, C.POINTER(_vp)]),
+    "wm_encoder_destroy": (_i, [_vp]),
+    "wm_encoder_refresh_weights": (_i, [_vp, _vp, _vp]),
+    "wm_encoder_forward": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i, _u64, _u64, _vp]),
+    "wm_encoder_backward_head": (_i, [_vp, _vp, _vp, _vp]),
+    "wm_encoder_backward_layers": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "wm_encoder_backward_embed": (_i, [_vp, _vp, _vp]),
+    "wm_encoder_activation": (_vp, [_vp, _i, _i]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raise loudly if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m weathermodel_b200.build` "
+                "(there is no CPU or PyTorch fallback for the hot path)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.wm_abi_version() != 1:
+            raise RuntimeError("libwm_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str = "libwm_b200"):
+    if code != 0:
+        msg = lib().wm_strerror(code).decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {code})")

@@ -1,0 +1,548 @@
+// wm_attn.cu -- fused multi-head self-attention forward / backward for S <= 384 on tcgen05 (sm_100a).
+//
+// Replaces F.scaled_dot_product_attention(q, k, v, None, dropout_p, False) as reached from
+// nn.TransformerEncoderLayer (torch/nn/functional.py:6666-6696; reference call site
+// src/pretraining/models/weatherbert.py:45-54,116-118). Head dims of this model family are 12/20/28/36:
+// Q/K/V rows are copied from the token-major [M, 3D] QKV activation into zero-padded, UNSWIZZLED
+// canonical core-matrix tiles in shared memory (8 rows x 16 B per core matrix), which one and the same
+// tile can feed to tcgen05.mma either K-major (contract over head dim) or MN-major (contract over rows).
+//
+// One CTA per (batch, head); thread t owns query row t of the current 128-row tile (TMEM lane t), so
+// row max / row sum / LSE / delta are plain per-thread scalars -- no shuffles, no atomics.
+//   fwd : pass 1 row max over 64-key score chunks, pass 2 exp2 + dropout + P(bf16)->smem, O += P V.
+//   bwd : per (kv tile j, q tile i): S = Q K^T, dP = dO V^T in TMEM; P, dS -> smem (bf16);
+//         dV_j += P^T dO, dK_j += dS^T Q, dQ_i += dS K; all five accumulators live in TMEM (<= 496 cols).
+// Dropout on P uses Philox4x32-10 keyed by (seed, stream, (bh*S + q)*ceil(S/16) + k/16), 8 bits / element
+// (keep iff byte >= thresh8), regenerated identically in backward.
+#include "wm_kernels.h"
+
+namespace wm {
+
+constexpr int kAttThreads = 128;
+constexpr int kSP = 384;  // key rows staged per head (S <= 384)
+
+// canonical unswizzled tile [rows, DHP]: elem(r, d) at (r/8)*RS + (d/8)*128 + (r%8)*16 + (d%8)*2
+template <int DHP>
+struct TileGeom {
+  static constexpr uint32_t RS = (DHP / 8) * 128;
+};
+
+// copy rows [0, S) of one head slice (row pitch ld elements, dh valid columns) into a canonical tile of
+// `rows_alloc` rows, zero-filling pad columns and pad rows.
+template <int DHP>
+WM_DEVICE void load_head_tile(uint8_t* tile, const __nv_bfloat16* __restrict__ src, int ld, int row0, int nrows_valid,
+                              int rows_alloc, int dh) {
+  constexpr uint32_t RS = TileGeom<DHP>::RS;
+  constexpr int PP = DHP / 4;  // 8-byte pieces per padded row
+  const int pv = dh / 4;
+  for (int i = threadIdx.x; i < rows_alloc * PP; i += blockDim.x) {
+    const int r = i / PP, p = i - r * PP;
+    uint2 val = make_uint2(0u, 0u);
+    if (r < nrows_valid && p < pv)
+      val = __ldg(reinterpret_cast<const uint2*>(src + static_cast<size_t>(row0 + r) * ld) + p);
+    const int d = p * 4;
+    *reinterpret_cast<uint2*>(tile + (r >> 3) * RS + (d >> 3) * 128 + (r & 7) * 16 + (d & 7) * 2) = val;
+  }
+}
+
+WM_DEVICE void keep16_from_philox(uint64_t seed, uint64_t stream, uint64_t grp, uint32_t thresh8, uint32_t& keep) {
+  const Philox4 r = philox4x32_10(seed, stream, grp);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  keep = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) keep |= (((w[i] >> (8 * b)) & 0xFFu) >= thresh8 ? 1u : 0u) << (i * 4 + b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int DHP>
+__global__ void __launch_bounds__(kAttThreads, 2)
+attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse_out,
+                int S, int H, int dh, float scale, uint32_t thresh8, float drop_scale, uint64_t seed,
+                uint64_t stream_id) {
+  constexpr uint32_t RS = TileGeom<DHP>::RS;
+  constexpr int KC = 64;                      // keys per score chunk
+  constexpr uint32_t RS_P = (KC / 8) * 128;   // P tile [128, 64]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 128 * DHP * 2;
+  uint8_t* sV = sK + kSP * DHP * 2;
+  uint8_t* sP = sV + kSP * DHP * 2;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int D = H * dh;
+  const int ld = 3 * D;
+  const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const __nv_bfloat16* qbase = qkv + static_cast<size_t>(b) * S * ld + h * dh;
+  const int nchunks = (S + KC - 1) / KC;
+  const int ntiles = (S + 127) / 128;
+  const int grp_per_row = (S + 15) / 16;
+
+  load_head_tile<DHP>(sK, qbase + D, ld, 0, S, kSP, dh);
+  load_head_tile<DHP>(sV, qbase + 2 * D, ld, 0, S, kSP, dh);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<128>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tS = tmem, tO = tmem + KC;
+  const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+  uint32_t phase = 0;
+  const uint32_t idesc_s = umma_idesc_bf16(128, KC, 0, 0);
+  const uint32_t idesc_o = umma_idesc_bf16(128, DHP, 0, 1);
+  const float c2 = scale * 1.4426950408889634f;
+
+  for (int it = 0; it < ntiles; ++it) {
+    const int q0 = it * 128;
+    const int q = q0 + tid;
+    const bool qvalid = q < S;
+    load_head_tile<DHP>(sQ, qbase, ld, q0, min(128, S - q0), 128, dh);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- pass 1: row max of the raw scores -------------------------------------------------
+    float mrow = -INFINITY;
+    for (int c = 0; c < nchunks; ++c) {
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DHP / 16; ++k) {
+          const uint64_t da = umma_smem_desc(smem_u32(sQ) + k * 256, 128, RS, UMMA_SWZ_NONE);
+          const uint64_t db = umma_smem_desc(smem_u32(sK) + (c * KC / 8) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
+          umma_ss(tS, da, db, idesc_s, k != 0);
+        }
+        umma_commit(&bar);
+      }
+      mbar_wait(&bar, phase, 41);
+      phase ^= 1u;
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_sel + half * 32, v);
+        tmem_ld_wait();
+        const int kbase = c * KC + half * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (kbase + j < S) mrow = fmaxf(mrow, __uint_as_float(v[j]));
+      }
+      tc_fence_before();
+      __syncthreads();
+    }
+    // ---- pass 2: P = exp2((s - m) * c2), O += P V -----------------------------------------------
+    float lsum = 0.0f;
+    const float mneg = -mrow * c2;
+    for (int c = 0; c < nchunks; ++c) {
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DHP / 16; ++k) {
+          const uint64_t da = umma_smem_desc(smem_u32(sQ) + k * 256, 128, RS, UMMA_SWZ_NONE);
+          const uint64_t db = umma_smem_desc(smem_u32(sK) + (c * KC / 8) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
+          umma_ss(tS, da, db, idesc_s, k != 0);
+        }
+        umma_commit(&bar);
+      }
+      mbar_wait(&bar, phase, 42);
+      phase ^= 1u;
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_sel + half * 32, v);
+        tmem_ld_wait();
+        const int kbase = c * KC + half * 32;
+#pragma unroll
+        for (int g16 = 0; g16 < 2; ++g16) {
+          uint32_t keep = 0xFFFFu;
+          if (thresh8) {
+            const uint64_t grp = (static_cast<uint64_t>(bh) * S + (qvalid ? q : 0)) * grp_per_row + ((kbase + g16 * 16) >> 4);
+            keep16_from_philox(seed, stream_id, grp, thresh8, keep);
+          }
+          float p[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int kk = kbase + g16 * 16 + j;
+            float e = 0.0f;
+            if (kk < S) e = exp2f(fmaf(__uint_as_float(v[g16 * 16 + j]), c2, mneg));
+            lsum += e;
+            p[j] = ((keep >> j) & 1u) ? e : 0.0f;
+          }
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            uint4 pk;
+            pk.x = pack_bf16x2(p[g8 * 8 + 0], p[g8 * 8 + 1]);
+            pk.y = pack_bf16x2(p[g8 * 8 + 2], p[g8 * 8 + 3]);
+            pk.z = pack_bf16x2(p[g8 * 8 + 4], p[g8 * 8 + 5]);
+            pk.w = pack_bf16x2(p[g8 * 8 + 6], p[g8 * 8 + 7]);
+            const int kc = half * 32 + g16 * 16 + g8 * 8;  // key column within the chunk
+            *reinterpret_cast<uint4*>(sP + (tid >> 3) * RS_P + (kc >> 3) * 128 + (tid & 7) * 16) = pk;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k) {
+          const uint64_t da = umma_smem_desc(smem_u32(sP) + k * 256, 128, RS_P, UMMA_SWZ_NONE);
+          // V as MN-major B: mn = head dim (SBO = 128 between 8-column groups), k = key rows (LBO = RS)
+          const uint64_t db = umma_smem_desc(smem_u32(sV) + ((c * KC + k * 16) / 8) * RS, RS, 128, UMMA_SWZ_NONE);
+          umma_ss(tO, da, db, idesc_o, (c | k) != 0);
+        }
+        umma_commit(&bar);
+      }
+      mbar_wait(&bar, phase, 43);  // P tile and S columns are free again after this
+      phase ^= 1u;
+      tc_fence_after();
+    }
+    // ---- epilogue: O / sum -> ctx, LSE -------------------------------------------------------------
+    {
+      const float inv = drop_scale / lsum;
+      __nv_bfloat16* orow = ctx + (static_cast<size_t>(b) * S + (qvalid ? q : 0)) * D + h * dh;
+#pragma unroll
+      for (int c0 = 0; c0 < DHP; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tO + lane_sel + c0, v);
+        tmem_ld_wait();
+        if (qvalid) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            if (c0 + j < dh) {  // dh % 4 == 0
+              uint2 pk;
+              pk.x = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+              pk.y = pack_bf16x2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+              *reinterpret_cast<uint2*>(orow + c0 + j) = pk;
+            }
+          }
+        }
+      }
+      if (qvalid && lse_out) lse_out[static_cast<size_t>(bh) * S + q] = mrow * scale + logf(lsum);
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<128>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+template <int DHP>
+__global__ void __launch_bounds__(kAttThreads, 1)
+attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ ctx,
+                const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
+                __nv_bfloat16* __restrict__ dqkv, int S, int H, int dh, float scale, uint32_t thresh8,
+                float drop_scale, uint64_t seed, uint64_t stream_id) {
+  constexpr uint32_t RS = TileGeom<DHP>::RS;
+  constexpr uint32_t RS_P = (128 / 8) * 128;  // P / dS tiles are [128 q, 128 keys]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kSP * DHP * 2;
+  uint8_t* sV = sK + kSP * DHP * 2;
+  uint8_t* sdO = sV + kSP * DHP * 2;
+  uint8_t* sP = sdO + kSP * DHP * 2;
+  uint8_t* sdS = sP + 128 * 128 * 2;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int D = H * dh;
+  const int ld = 3 * D;
+  const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const __nv_bfloat16* qbase = qkv + static_cast<size_t>(b) * S * ld + h * dh;
+  const __nv_bfloat16* obase = ctx + static_cast<size_t>(b) * S * D + h * dh;
+  const __nv_bfloat16* dobase = dctx + static_cast<size_t>(b) * S * D + h * dh;
+  const int ntiles = (S + 127) / 128;
+  const int grp_per_row = (S + 15) / 16;
+
+  load_head_tile<DHP>(sQ, qbase, ld, 0, S, kSP, dh);
+  load_head_tile<DHP>(sK, qbase + D, ld, 0, S, kSP, dh);
+  load_head_tile<DHP>(sV, qbase + 2 * D, ld, 0, S, kSP, dh);
+  load_head_tile<DHP>(sdO, dobase, D, 0, S, kSP, dh);
+  // per-thread row statistics for the (up to) three q tiles: LSE and delta = sum_d dO * O
+  float lse_r[3], delta_r[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int q = i * 128 + tid;
+    lse_r[i] = 0.0f;
+    delta_r[i] = 0.0f;
+    if (q < S) {
+      lse_r[i] = lse[static_cast<size_t>(bh) * S + q];
+      float acc = 0.0f;
+      const uint2* po = reinterpret_cast<const uint2*>(obase + static_cast<size_t>(q) * D);
+      const uint2* pd = reinterpret_cast<const uint2*>(dobase + static_cast<size_t>(q) * D);
+      for (int p = 0; p < dh / 4; ++p) {
+        const uint2 o = __ldg(po + p), d = __ldg(pd + p);
+        acc = fmaf(bf16_lo(o.x), bf16_lo(d.x), acc);
+        acc = fmaf(bf16_hi(o.x), bf16_hi(d.x), acc);
+        acc = fmaf(bf16_lo(o.y), bf16_lo(d.y), acc);
+        acc = fmaf(bf16_hi(o.y), bf16_hi(d.y), acc);
+      }
+      delta_r[i] = acc;
+    }
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 256 + DHP, tdQ = tmem + 256 + 2 * DHP;
+  const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+  uint32_t phase = 0;
+  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+  const uint32_t idesc_kv = umma_idesc_bf16(128, DHP, 1, 1);
+  const uint32_t idesc_q = umma_idesc_bf16(128, DHP, 0, 1);
+  const float c2 = scale * 1.4426950408889634f;
+  const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), adO = smem_u32(sdO);
+  const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
+
+  for (int j = 0; j < ntiles; ++j) {
+    for (int i = 0; i < ntiles; ++i) {
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DHP / 16; ++k) {
+          const uint64_t da = umma_smem_desc(aQ + (i * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
+          const uint64_t db = umma_smem_desc(aK + (j * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
+          umma_ss(tS, da, db, idesc_s, k != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < DHP / 16; ++k) {
+          const uint64_t da = umma_smem_desc(adO + (i * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
+          const uint64_t db = umma_smem_desc(aV + (j * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
+          umma_ss(tdP, da, db, idesc_s, k != 0);
+        }
+        umma_commit(&bar);
+      }
+      mbar_wait(&bar, phase, 51);
+      phase ^= 1u;
+      tc_fence_after();
+      const int q = i * 128 + tid;
+      const bool qvalid = q < S;
+      const float lneg = -lse_r[i] * 1.4426950408889634f;
+      const float dl = delta_r[i];
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t vs[32], vd[32];
+        tmem_ld32(tS + lane_sel + c0, vs);
+        tmem_ld32(tdP + lane_sel + c0, vd);
+        tmem_ld_wait();
+        const int kbase = j * 128 + c0;
+#pragma unroll
+        for (int g16 = 0; g16 < 2; ++g16) {
+          uint32_t keep = 0xFFFFu;
+          if (thresh8) {
+            const uint64_t grp = (static_cast<uint64_t>(bh) * S + (qvalid ? q : 0)) * grp_per_row + ((kbase + g16 * 16) >> 4);
+            keep16_from_philox(seed, stream_id, grp, thresh8, keep);
+          }
+          float pp[16], ds[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const int kk = kbase + g16 * 16 + jj;
+            float p = 0.0f;
+            if (qvalid && kk < S) p = exp2f(fmaf(__uint_as_float(vs[g16 * 16 + jj]), c2, lneg));
+            const float kp = ((keep >> jj) & 1u) ? drop_scale : 0.0f;
+            pp[jj] = p * kp;
+            ds[jj] = p * (__uint_as_float(vd[g16 * 16 + jj]) * kp - dl) * scale;
+          }
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            uint4 pk, dk;
+            pk.x = pack_bf16x2(pp[g8 * 8 + 0], pp[g8 * 8 + 1]);
+            pk.y = pack_bf16x2(pp[g8 * 8 + 2], pp[g8 * 8 + 3]);
+            pk.z = pack_bf16x2(pp[g8 * 8 + 4], pp[g8 * 8 + 5]);
+            pk.w = pack_bf16x2(pp[g8 * 8 + 6], pp[g8 * 8 + 7]);
+            dk.x = pack_bf16x2(ds[g8 * 8 + 0], ds[g8 * 8 + 1]);
+            dk.y = pack_bf16x2(ds[g8 * 8 + 2], ds[g8 * 8 + 3]);
+            dk.z = pack_bf16x2(ds[g8 * 8 + 4], ds[g8 * 8 + 5]);
+            dk.w = pack_bf16x2(ds[g8 * 8 + 6], ds[g8 * 8 + 7]);
+            const int kc = c0 + g16 * 16 + g8 * 8;
+            const uint32_t off = (tid >> 3) * RS_P + (kc >> 3) * 128 + (tid & 7) * 16;
+            *reinterpret_cast<uint4*>(sP + off) = pk;
+            *reinterpret_cast<uint4*>(sdS + off) = dk;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 128 / 16; ++k) {
+          // contraction over the 128 query rows of tile i: P / dS read MN-major (mn = keys: SBO = 128,
+          // k = q rows: LBO = RS_P); dO / Q read MN-major (mn = head dim: SBO = 128, k = rows: LBO = RS)
+          const uint64_t dpT = umma_smem_desc(aP + (k * 2) * RS_P, RS_P, 128, UMMA_SWZ_NONE);
+          const uint64_t dsT = umma_smem_desc(adS + (k * 2) * RS_P, RS_P, 128, UMMA_SWZ_NONE);
+          const uint64_t ddo = umma_smem_desc(adO + (i * 16 + k * 2) * RS, RS, 128, UMMA_SWZ_NONE);
+          const uint64_t dq = umma_smem_desc(aQ + (i * 16 + k * 2) * RS, RS, 128, UMMA_SWZ_NONE);
+          umma_ss(tdV, dpT, ddo, idesc_kv, (i | k) != 0);
+          umma_ss(tdK, dsT, dq, idesc_kv, (i | k) != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 128 / 16; ++k) {
+          // dQ_i += dS K_j: dS K-major over keys (LBO = 128, SBO = RS_P); K_j MN-major over key rows
+          const uint64_t da = umma_smem_desc(adS + k * 256, 128, RS_P, UMMA_SWZ_NONE);
+          const uint64_t db = umma_smem_desc(aK + (j * 16 + k * 2) * RS, RS, 128, UMMA_SWZ_NONE);
+          umma_ss(tdQ + i * DHP, da, db, idesc_q, (j | k) != 0);
+        }
+        umma_commit(&bar);
+      }
+      mbar_wait(&bar, phase, 52);
+      phase ^= 1u;
+      tc_fence_after();
+    }
+    // dK_j, dV_j complete: thread = key row
+    {
+      const int kr = j * 128 + tid;
+      const bool kvalid = kr < S;
+      __nv_bfloat16* drow = dqkv + (static_cast<size_t>(b) * S + (kvalid ? kr : 0)) * ld + h * dh;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t tsrc = which == 0 ? tdK : tdV;
+        __nv_bfloat16* dst = drow + (which == 0 ? D : 2 * D);
+#pragma unroll
+        for (int c0 = 0; c0 < DHP; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tsrc + lane_sel + c0, v);
+          tmem_ld_wait();
+          if (kvalid) {
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4) {
+              if (c0 + jj < dh) {
+                uint2 pk;
+                pk.x = pack_bf16x2(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]));
+                pk.y = pack_bf16x2(__uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
+                *reinterpret_cast<uint2*>(dst + c0 + jj) = pk;
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  for (int i = 0; i < ntiles; ++i) {
+    const int q = i * 128 + tid;
+    const bool qvalid = q < S;
+    __nv_bfloat16* dst = dqkv + (static_cast<size_t>(b) * S + (qvalid ? q : 0)) * ld + h * dh;
+#pragma unroll
+    for (int c0 = 0; c0 < DHP; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tdQ + i * DHP + lane_sel + c0, v);
+      tmem_ld_wait();
+      if (qvalid) {
+#pragma unroll
+        for (int jj = 0; jj < 16; jj += 4) {
+          if (c0 + jj < dh) {
+            uint2 pk;
+            pk.x = pack_bf16x2(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]));
+            pk.y = pack_bf16x2(__uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
+            *reinterpret_cast<uint2*>(dst + c0 + jj) = pk;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static int padded_dh(int dh) { return dh <= 16 ? 16 : dh <= 32 ? 32 : dh <= 48 ? 48 : 0; }
+
+template <int DHP>
+static int launch_fwd_t(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, int B, int S, int H, int dh,
+                        float scale, uint32_t thresh8, float dscale, uint64_t seed, uint64_t stream_id,
+                        cudaStream_t stream) {
+  const int smem = 128 * DHP * 2 + 2 * kSP * DHP * 2 + 128 * 64 * 2 + 256;
+  if (cudaFuncSetAttribute(attn_fwd_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return WM_ERR_CUDA;
+  attn_fwd_kernel<DHP><<<B * H, kAttThreads, smem, stream>>>(qkv, ctx, lse, S, H, dh, scale, thresh8, dscale, seed,
+                                                             stream_id);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+template <int DHP>
+static int launch_bwd_t(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __nv_bfloat16* dctx,
+                        const float* lse, __nv_bfloat16* dqkv, int B, int S, int H, int dh, float scale,
+                        uint32_t thresh8, float dscale, uint64_t seed, uint64_t stream_id, cudaStream_t stream) {
+  const int smem = 4 * kSP * DHP * 2 + 2 * 128 * 128 * 2 + 256;
+  if (cudaFuncSetAttribute(attn_bwd_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return WM_ERR_CUDA;
+  attn_bwd_kernel<DHP><<<B * H, kAttThreads, smem, stream>>>(qkv, ctx, dctx, lse, dqkv, S, H, dh, scale, thresh8,
+                                                             dscale, seed, stream_id);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// drop_thresh is the 16-bit threshold used everywhere else (round(p*65536)); attention rounds it to 8 bits
+static void attn_drop_params(uint32_t drop_thresh16, uint32_t* thresh8, float* scale) {
+  *thresh8 = (drop_thresh16 + 128u) >> 8;
+  *scale = *thresh8 ? 256.0f / static_cast<float>(256u - *thresh8) : 1.0f;
+}
+
+int launch_attn_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, int B, int S, int H, int dh,
+                    uint32_t drop_thresh, float drop_scale, uint64_t seed, uint64_t stream_id, cudaStream_t stream) {
+  (void)drop_scale;
+  if (B <= 0 || H <= 0 || S <= 0 || S > kSP || (dh & 3)) return WM_ERR_SHAPE;
+  const int dhp = padded_dh(dh);
+  if (!dhp) return WM_ERR_SHAPE;
+  uint32_t t8;
+  float ds;
+  attn_drop_params(drop_thresh, &t8, &ds);
+  const float scale = 1.0f / sqrtf(static_cast<float>(dh));
+  switch (dhp) {
+    case 16: return launch_fwd_t<16>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
+    case 32: return launch_fwd_t<32>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
+    default: return launch_fwd_t<48>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
+  }
+}
+
+int launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __nv_bfloat16* dctx, const float* lse,
+                    __nv_bfloat16* dqkv, int B, int S, int H, int dh, uint32_t drop_thresh, float drop_scale,
+                    uint64_t seed, uint64_t stream_id, cudaStream_t stream) {
+  (void)drop_scale;
+  if (B <= 0 || H <= 0 || S <= 0 || S > kSP || (dh & 3)) return WM_ERR_SHAPE;
+  const int dhp = padded_dh(dh);
+  if (!dhp) return WM_ERR_SHAPE;
+  uint32_t t8;
+  float ds;
+  attn_drop_params(drop_thresh, &t8, &ds);
+  const float scale = 1.0f / sqrtf(static_cast<float>(dh));
+  switch (dhp) {
+    case 16: return launch_bwd_t<16>(qkv, ctx, dctx, lse, dqkv, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
+    case 32: return launch_bwd_t<32>(qkv, ctx, dctx, lse, dqkv, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
+    default: return launch_bwd_t<48>(qkv, ctx, dctx, lse, dqkv, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
+  }
+}
+
+}  // namespace wm

@@ -1,0 +1,275 @@
+// wm_common.cuh -- sm_100a device primitives shared by every kernel of the WeatherModel hot path.
+//
+// Thin inline-PTX wrappers (mbarrier, TMA, tcgen05/TMEM), the UMMA descriptor encoders, a
+// counter-based Philox4x32-10 (bit-compatible with curand, which ATen uses for torch.rand on
+// CUDA: torch/include/ATen/native/cuda/DistributionTemplates.h:66-89) and small math helpers.
+// Nothing here allocates or holds global state except the device-side error word g_wm_dev_error.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wm {
+
+// ---------------------------------------------------------------------------------------------
+// device-side error word: a bounded mbarrier wait that times out records a code here instead of
+// hanging the GPU (a hang on the shared box is a strike). Host reads it via wm_device_error().
+// ---------------------------------------------------------------------------------------------
+// (the library is built as ONE translation unit -- wm_lib.cu -- so this is the single definition)
+__device__ unsigned int g_wm_dev_error = 0;
+
+#define WM_DEVICE __device__ __forceinline__
+
+WM_DEVICE uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+WM_DEVICE uint32_t lane_id() { return threadIdx.x & 31u; }
+
+WM_DEVICE bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 %%rx;\n\t"
+      ".reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, %%px;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier
+// ---------------------------------------------------------------------------------------------
+WM_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+WM_DEVICE void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+// generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)
+WM_DEVICE void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+WM_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+WM_DEVICE void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+WM_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: ~seconds at most, then flag + fall through (results are garbage, GPU survives).
+WM_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t code = 1) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0) {
+      // ~0.25 s at 1.9 GHz for the first waiter; everyone else bails as soon as the flag is up
+      if (*reinterpret_cast<volatile unsigned int*>(&g_wm_dev_error) != 0) break;
+      if (clock64() - t0 > 500000000LL) {
+        atomicCAS(&g_wm_dev_error, 0u, code);
+        break;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor) -- 2D tiled loads into 128B-swizzled smem, completion on an mbarrier
+// ---------------------------------------------------------------------------------------------
+WM_DEVICE void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+WM_DEVICE void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 / TMEM
+// ---------------------------------------------------------------------------------------------
+template <uint32_t kCols>
+WM_DEVICE void tmem_alloc(uint32_t* smem_slot) {  // whole warp, .sync.aligned
+  static_assert(kCols >= 32 && kCols <= 512 && (kCols & (kCols - 1)) == 0, "TMEM cols: pow2 in [32,512]");
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                   smem_u32(smem_slot)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+template <uint32_t kCols>
+WM_DEVICE void tmem_dealloc(uint32_t taddr) {  // same warp that allocated
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "n"(kCols)
+               : "memory");
+}
+WM_DEVICE void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+WM_DEVICE void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread for the whole CTA.
+WM_DEVICE void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+// (implies tcgen05.fence::before_thread_sync)
+WM_DEVICE void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+// TMEM -> registers: lane t of the warp receives 32 / 16 consecutive fp32 columns of TMEM lane
+// (lane_base + t); lane_base must be 32*(warp_id % 4).
+WM_DEVICE void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+WM_DEVICE void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+WM_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// UMMA descriptors (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor / InstrDescriptor)
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t { UMMA_SWZ_NONE = 0, UMMA_SWZ_128B = 2, UMMA_SWZ_64B = 4, UMMA_SWZ_32B = 6 };
+
+WM_DEVICE uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                  uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);          // [0,14)  start address
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;     // [16,30) leading byte offset
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;     // [32,46) stride byte offset
+  d |= static_cast<uint64_t>(1) << 46;                              // [46,48) version = 1 (sm_100)
+  d |= static_cast<uint64_t>(layout_type & 7u) << 61;               // [61,64) swizzle mode
+  return d;
+}
+// kind::f16, bf16 x bf16 -> fp32; a_mn / b_mn = 1 selects an MN-major (transposed) operand.
+__host__ __device__ inline uint32_t umma_idesc_bf16(uint32_t m, uint32_t n, uint32_t a_mn,
+                                                    uint32_t b_mn) {
+  uint32_t d = 0;
+  d |= 1u << 4;            // c_format = F32
+  d |= 1u << 7;            // a_format = BF16
+  d |= 1u << 10;           // b_format = BF16
+  d |= (a_mn & 1u) << 15;  // a_major
+  d |= (b_mn & 1u) << 16;  // b_major
+  d |= ((n >> 3) & 0x3Fu) << 17;
+  d |= ((m >> 4) & 0x1Fu) << 24;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10, curand-compatible. counter = {offset_lo, offset_hi, subseq_lo, subseq_hi}
+// (curand_init(seed, subsequence, offset) with offset counted in 128-bit blocks here).
+// ---------------------------------------------------------------------------------------------
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+__host__ __device__ inline Philox4 philox4x32_10(uint64_t seed, uint64_t subsequence,
+                                                 uint64_t block_offset) {
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  uint32_t c0 = static_cast<uint32_t>(block_offset), c1 = static_cast<uint32_t>(block_offset >> 32);
+  uint32_t c2 = static_cast<uint32_t>(subsequence), c3 = static_cast<uint32_t>(subsequence >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#else
+    uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0, p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+    uint32_t hi0 = static_cast<uint32_t>(p0 >> 32), lo0 = static_cast<uint32_t>(p0);
+    uint32_t hi1 = static_cast<uint32_t>(p1 >> 32), lo1 = static_cast<uint32_t>(p1);
+#endif
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+// curand_uniform: (0,1]
+__host__ __device__ inline float curand_uniform_from_u32(uint32_t x) {
+  return static_cast<float>(x) * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+}
+
+// Dropout keep decision for 8 consecutive elements out of one Philox block: 16-bit lanes,
+// keep iff lane >= thresh16 where thresh16 = round(p * 65536).
+WM_DEVICE uint32_t dropout_keep8(uint64_t seed, uint64_t stream, uint64_t group_index,
+                                 uint32_t thresh16) {
+  Philox4 r = philox4x32_10(seed, stream, group_index);
+  uint32_t m = 0;
+  m |= ((r.x & 0xFFFFu) >= thresh16) << 0;
+  m |= ((r.x >> 16) >= thresh16) << 1;
+  m |= ((r.y & 0xFFFFu) >= thresh16) << 2;
+  m |= ((r.y >> 16) >= thresh16) << 3;
+  m |= ((r.z & 0xFFFFu) >= thresh16) << 4;
+  m |= ((r.z >> 16) >= thresh16) << 5;
+  m |= ((r.w & 0xFFFFu) >= thresh16) << 6;
+  m |= ((r.w >> 16) >= thresh16) << 7;
+  return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// misc
+// ---------------------------------------------------------------------------------------------
+WM_DEVICE float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+WM_DEVICE float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+WM_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+WM_DEVICE float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+WM_DEVICE float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+}  // namespace wm

@@ -1,0 +1,748 @@
+// wm_elementwise.cu -- the HBM-bound kernels of the WeatherModel training step (sm_100a).
+//
+//   mask_bert / mask_former : bit-exact replay of torch.rand on the CUDA generator
+//                             (reference: src/pretraining/dataloader/pretraining_dataloader.py:56-84;
+//                              torch/include/ATen/native/cuda/DistributionTemplates.h:50-89)
+//   embed_fwd               : normalise + mask + Linear(34->D) + sinusoidal PE, one pass
+//                             (reference: src/pretraining/models/weatherbert.py:101-115,
+//                              src/utils/utils.py:63-74, src/base_models/vanilla_pos_encoding.py:57)
+//   layernorm_fwd / bwd     : post-LN of nn.TransformerEncoderLayer (torch/nn/modules/transformer.py:951-957)
+//   loss_bert / loss_former : fused loss + dLoss/dY (reference: src/pretraining/trainers/
+//                             weatherbert_trainer.py:55-60, weatherformer_trainer.py:68-111,
+//                             src/utils/losses.py:10-47, src/pretraining/models/weatherformer.py:87-92)
+//   adam                    : torch.optim.Adam single step over a flat parameter bucket
+//                             (reference: src/base_trainer/base_trainer.py:337)
+#include "wm_kernels.h"
+
+namespace wm {
+
+// ------------------------------------------------------------------------------------------------
+// torch.rand replay. ATen launches grid_x blocks of 256 threads; thread idx draws Philox blocks
+// (seed, subsequence = idx, offset/4 + iter) and writes component ii to element
+// idx + iter*4*T + ii*T with T = 256*grid_x.
+// ------------------------------------------------------------------------------------------------
+WM_DEVICE float torch_rand_element(uint64_t seed, uint64_t offset_blocks, int64_t T, int64_t li) {
+  const int64_t iter = li / (4 * T);
+  const int64_t rem = li - iter * 4 * T;
+  const int ii = static_cast<int>(rem / T);
+  const int64_t idx = rem - static_cast<int64_t>(ii) * T;
+  const Philox4 r = philox4x32_10(seed, static_cast<uint64_t>(idx), offset_blocks + static_cast<uint64_t>(iter));
+  const uint32_t u = ii == 0 ? r.x : ii == 1 ? r.y : ii == 2 ? r.z : r.w;
+  const float v = curand_uniform_from_u32(u);
+  return v == 1.0f ? 0.0f : v;  // ATen reverses (0,1] -> [0,1)
+}
+
+__global__ void __launch_bounds__(256)
+mask_bert_kernel(uint64_t seed, uint64_t offset_blocks, float p, int64_t numel, uint8_t* __restrict__ mask,
+                 float* __restrict__ rand_out) {
+  const int64_t T = static_cast<int64_t>(gridDim.x) * 256;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  uint64_t iter = 0;
+  for (int64_t base = idx; base < numel; base += 4 * T, ++iter) {
+    const Philox4 r = philox4x32_10(seed, static_cast<uint64_t>(idx), offset_blocks + iter);
+    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const int64_t li = base + T * ii;
+      if (li < numel) {
+        float v = curand_uniform_from_u32(u[ii]);
+        v = v == 1.0f ? 0.0f : v;
+        mask[li] = v < p ? 1 : 0;
+        if (rand_out) rand_out[li] = v;
+      }
+    }
+  }
+}
+
+int launch_mask_bert(uint64_t seed, uint64_t philox_offset, int grid_x, float p, int64_t numel,
+                     uint8_t* mask, float* rand_out, cudaStream_t stream) {
+  if (numel <= 0) return WM_OK;
+  if (grid_x <= 0 || (philox_offset & 3)) return WM_ERR_ARG;
+  mask_bert_kernel<<<grid_x, 256, 0, stream>>>(seed, philox_offset / 4, p, numel, mask, rand_out);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// one warp per sample: lane i holds v_i = rand[b, i]; mask[b, rank(v_i)] = (i < n_masked)
+__global__ void __launch_bounds__(256)
+mask_former_kernel(uint64_t seed, uint64_t offset_blocks, int64_t T, int n_masked, int64_t n_samples,
+                   int F, uint8_t* __restrict__ mask) {
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= n_samples) return;
+  float v = 2.0f;
+  if (lane < F) v = torch_rand_element(seed, offset_blocks, T, b * F + lane);
+  int rank = 0;
+  for (int k = 0; k < F; ++k) {
+    const float vk = __shfl_sync(0xffffffffu, v, k);
+    rank += (vk < v) || (vk == v && k < lane);  // stable sort tie order
+  }
+  // position `rank` holds original index `lane`; argsort(...) < n  <=>  lane < n
+  if (lane < F) mask[b * F + rank] = lane < n_masked ? 1 : 0;
+}
+
+int launch_mask_former(uint64_t seed, uint64_t philox_offset, int grid_x, int n_masked, int64_t n_samples,
+                       int n_features, uint8_t* mask, cudaStream_t stream) {
+  if (n_samples <= 0) return WM_OK;
+  if (grid_x <= 0 || (philox_offset & 3) || n_features > 32 || n_features <= 0) return WM_ERR_ARG;
+  const int blocks = static_cast<int>((n_samples + 7) / 8);
+  mask_former_kernel<<<blocks, 256, 0, stream>>>(seed, philox_offset / 4, static_cast<int64_t>(grid_x) * 256,
+                                                  n_masked, n_samples, n_features, mask);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------
+// embed_fwd. CTA = 32 tokens x all D; W_in^T staged in smem as [Fin][D] fp32.
+// ------------------------------------------------------------------------------------------------
+constexpr int kEmbTok = 32;
+constexpr int kXinLd = 64;  // padded bf16 copy of the 34-channel input row (wgrad operand)
+
+__global__ void __launch_bounds__(256)
+embed_fwd_kernel(const float* __restrict__ weather, const uint8_t* __restrict__ mask, int64_t msb, int64_t mss,
+                 const float* __restrict__ year, const float* __restrict__ coords,
+                 const float* __restrict__ w_in, const float* __restrict__ b_in, const float* __restrict__ pe,
+                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ xin, int B, int S, int F, int D) {
+  extern __shared__ float smf[];
+  const int Fin = F + 3;
+  const int FinP = (Fin + 3) & ~3;
+  float* sW = smf;                 // [Fin][D]
+  float* sX = smf + Fin * D;       // [kEmbTok][FinP]
+  const int64_t M = static_cast<int64_t>(B) * S;
+  const int64_t t0 = static_cast<int64_t>(blockIdx.x) * kEmbTok;
+  for (int i = threadIdx.x; i < Fin * D; i += blockDim.x) {
+    const int d = i / Fin, c = i - d * Fin;  // w_in is [D][Fin]
+    sW[c * D + d] = w_in[i];
+  }
+  for (int i = threadIdx.x; i < kEmbTok * FinP; i += blockDim.x) {
+    const int tt = i / FinP, c = i - tt * FinP;
+    const int64_t t = t0 + tt;
+    float v = 0.0f;
+    if (t < M && c < Fin) {
+      const int64_t b = t / S, s = t - b * S;
+      if (c < F) {
+        const float w = weather[t * F + c];
+        const uint8_t m = mask[b * msb + s * mss + c];
+        v = m ? w * 0.0f : w;  // weather * (~mask): keeps NaN/Inf semantics of the multiply
+      } else if (c == F) {
+        v = (year[t] - 1970.0f) / 100.0f;
+      } else if (c == F + 1) {
+        v = coords[b * 2] / 360.0f;
+      } else {
+        v = coords[b * 2 + 1] / 180.0f;
+      }
+    }
+    sX[i] = v;
+  }
+  __syncthreads();
+  if (xin) {
+    for (int i = threadIdx.x; i < kEmbTok * kXinLd; i += blockDim.x) {
+      const int tt = i / kXinLd, c = i - tt * kXinLd;
+      const int64_t t = t0 + tt;
+      if (t < M) xin[t * kXinLd + c] = __float2bfloat16(c < Fin ? sX[tt * FinP + c] : 0.0f);
+    }
+  }
+  for (int d = threadIdx.x * 2; d < D; d += blockDim.x * 2) {
+    float w0[40], w1[40];
+#pragma unroll
+    for (int c = 0; c < 40; ++c) {
+      w0[c] = c < Fin ? sW[c * D + d] : 0.0f;
+      w1[c] = c < Fin ? sW[c * D + d + 1] : 0.0f;
+    }
+    const float bias0 = b_in[d], bias1 = b_in[d + 1];
+    for (int tt = 0; tt < kEmbTok; ++tt) {
+      const int64_t t = t0 + tt;
+      if (t >= M) break;
+      const int s = static_cast<int>(t % S);
+      float a0 = 0.0f, a1 = 0.0f;
+      const float4* xr = reinterpret_cast<const float4*>(sX + tt * FinP);
+#pragma unroll
+      for (int c4 = 0; c4 < 10; ++c4) {
+        if (c4 * 4 < FinP) {
+          const float4 x = xr[c4];
+          a0 = fmaf(x.x, w0[c4 * 4], a0); a1 = fmaf(x.x, w1[c4 * 4], a1);
+          a0 = fmaf(x.y, w0[c4 * 4 + 1], a0); a1 = fmaf(x.y, w1[c4 * 4 + 1], a1);
+          a0 = fmaf(x.z, w0[c4 * 4 + 2], a0); a1 = fmaf(x.z, w1[c4 * 4 + 2], a1);
+          a0 = fmaf(x.w, w0[c4 * 4 + 3], a0); a1 = fmaf(x.w, w1[c4 * 4 + 3], a1);
+        }
+      }
+      a0 = (a0 + bias0) + pe[static_cast<size_t>(s) * D + d];
+      a1 = (a1 + bias1) + pe[static_cast<size_t>(s) * D + d + 1];
+      *reinterpret_cast<uint32_t*>(out + t * D + d) = pack_bf16x2(a0, a1);
+    }
+  }
+}
+
+int launch_embed_fwd(const float* weather, const uint8_t* mask, int64_t msb, int64_t mss, const float* year,
+                     const float* coords, const float* w_in, const float* b_in, const float* pe,
+                     __nv_bfloat16* out, __nv_bfloat16* xin, int B, int S, int F, int D, cudaStream_t stream) {
+  if (B <= 0 || S <= 0 || F <= 0 || F + 3 > 40 || (D & 1)) return WM_ERR_SHAPE;
+  const int64_t M = static_cast<int64_t>(B) * S;
+  const int Fin = F + 3, FinP = (Fin + 3) & ~3;
+  const int smem = (Fin * D + kEmbTok * FinP) * 4;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return WM_ERR_CUDA;
+  const int blocks = static_cast<int>((M + kEmbTok - 1) / kEmbTok);
+  embed_fwd_kernel<<<blocks, 256, smem, stream>>>(weather, mask, msb, mss, year, coords, w_in, b_in, pe, out,
+                                                  xin, B, S, F, D);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row; lane owns 8-element chunks c = lane + 32*i (D % 8 == 0, D <= 768).
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnMaxChunks = 3;
+
+WM_DEVICE void ln_load_row(const __nv_bfloat16* row, int nchunks, int lane, float (&v)[kLnMaxChunks][8]) {
+#pragma unroll
+  for (int i = 0; i < kLnMaxChunks; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(row) + c);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[i][2 * j] = bf16_lo(aw[j]);
+        v[i][2 * j + 1] = bf16_hi(aw[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.0f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int M, int D, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int nchunks = D >> 3;
+  float v[kLnMaxChunks][8];
+  ln_load_row(x + static_cast<size_t>(row) * D, nchunks, lane, v);
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxChunks; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[i][j];
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxChunks; ++i) {
+    if (lane + 32 * i < nchunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < kLnMaxChunks; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + 1);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, g[j], b[j]);
+      uint4 pk;
+      pk.x = pack_bf16x2(o[0], o[1]);
+      pk.y = pack_bf16x2(o[2], o[3]);
+      pk.z = pack_bf16x2(o[4], o[5]);
+      pk.w = pack_bf16x2(o[6], o[7]);
+      reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * D)[c] = pk;
+    }
+  }
+}
+
+int launch_layernorm_fwd(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y,
+                         float* mean, float* rstd, int M, int D, float eps, cudaStream_t stream) {
+  if (M <= 0 || D <= 0 || (D & 7) || D > kLnMaxChunks * 256) return WM_ERR_SHAPE;
+  layernorm_fwd_kernel<<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, mean, rstd, M, D, eps);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// LayerNorm backward. Each warp walks rows (grid-stride) keeping per-column partial sums of
+// dgamma, dbeta and the bias gradient of the producing linear in registers; CTA partials go to a
+// workspace and a second kernel folds them in a fixed order (deterministic).
+constexpr int kLnBwdCtas = 148 * 4;
+
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, __nv_bfloat16* __restrict__ dx,
+                     __nv_bfloat16* __restrict__ dx_drop, int M, int D, uint32_t drop_thresh, float drop_scale,
+                     uint64_t seed, uint64_t stream_id, float* __restrict__ partial) {
+  extern __shared__ float sred[];  // [8 warps][3][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = D >> 3;
+  float g[kLnMaxChunks][8];
+  float ag[kLnMaxChunks][8], ab[kLnMaxChunks][8], ad[kLnMaxChunks][8];
+#pragma unroll
+  for (int i = 0; i < kLnMaxChunks; ++i) {
+    const int c = lane + 32 * i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      g[i][j] = c < nchunks ? gamma[c * 8 + j] : 0.0f;
+      ag[i][j] = 0.0f; ab[i][j] = 0.0f; ad[i][j] = 0.0f;
+    }
+  }
+  const float invD = 1.0f / static_cast<float>(D);
+  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+    float xv[kLnMaxChunks][8], dv[kLnMaxChunks][8];
+    ln_load_row(x + static_cast<size_t>(row) * D, nchunks, lane, xv);
+    ln_load_row(dy + static_cast<size_t>(row) * D, nchunks, lane, dv);
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxChunks; ++i) {
+      if (lane + 32 * i < nchunks) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[i][j] - mu) * rs;
+          const float gd = dv[i][j] * g[i][j];
+          s1 += gd;
+          s2 = fmaf(gd, xh, s2);
+          ag[i][j] = fmaf(dv[i][j], xh, ag[i][j]);
+          ab[i][j] += dv[i][j];
+          xv[i][j] = xh;
+        }
+      }
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+#pragma unroll
+    for (int i = 0; i < kLnMaxChunks; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (dv[i][j] * g[i][j] - s1 - xv[i][j] * s2);
+        uint4 pk;
+        pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
+        pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+        reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * D)[c] = pk;
+        if (drop_thresh) {
+          const uint64_t grp = (static_cast<uint64_t>(row) * static_cast<uint64_t>(D) + c * 8) >> 3;
+          const uint32_t keep = dropout_keep8(seed, stream_id, grp, drop_thresh);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = ((keep >> j) & 1u) ? o[j] * drop_scale : 0.0f;
+          pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
+          pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+          reinterpret_cast<uint4*>(dx_drop + static_cast<size_t>(row) * D)[c] = pk;
+        }
+        // bias gradient of the producing linear sums what that linear's output actually received;
+        // use the bf16-rounded values so it matches the wgrad operand exactly
+        const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ad[i][2 * j] += bf16_lo(pw[j]);
+          ad[i][2 * j + 1] += bf16_hi(pw[j]);
+        }
+      }
+    }
+  }
+  // CTA reduce: warp w writes its registers, then 256 threads fold 8 warps per column
+#pragma unroll
+  for (int i = 0; i < kLnMaxChunks; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sred[(warp * 3 + 0) * D + c * 8 + j] = ag[i][j];
+        sred[(warp * 3 + 1) * D + c * 8 + j] = ab[i][j];
+        sred[(warp * 3 + 2) * D + c * 8 + j] = ad[i][j];
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sred[w * 3 * D + i];
+    partial[static_cast<size_t>(blockIdx.x) * 3 * D + i] = s;
+  }
+}
+
+// out_k[c] (+)= sum_{cta} partial[cta][k][c]
+__global__ void ln_bwd_finalize_kernel(const float* __restrict__ partial, int ncta, int D, float* dgamma,
+                                       float* dbeta, float* dbias) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * D) return;
+  float s = 0.0f;
+  for (int c = 0; c < ncta; ++c) s += partial[static_cast<size_t>(c) * 3 * D + i];
+  const int k = i / D, col = i - k * D;
+  float* dst = k == 0 ? dgamma : k == 1 ? dbeta : dbias;
+  if (dst) dst[col] = s;
+}
+
+size_t layernorm_bwd_workspace_bytes(int M, int D) {
+  (void)M;
+  return static_cast<size_t>(kLnBwdCtas) * 3 * D * sizeof(float);
+}
+
+int launch_layernorm_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const float* gamma, const float* mean,
+                         const float* rstd, __nv_bfloat16* dx, __nv_bfloat16* dx_drop, float* dgamma,
+                         float* dbeta, float* dbias, int M, int D, uint32_t drop_thresh, float drop_scale,
+                         uint64_t seed, uint64_t stream_id, float* workspace, cudaStream_t stream) {
+  if (M <= 0 || D <= 0 || (D & 7) || D > kLnMaxChunks * 256) return WM_ERR_SHAPE;
+  if (drop_thresh && !dx_drop) return WM_ERR_ARG;
+  int ctas = (M + 7) / 8;
+  if (ctas > kLnBwdCtas) ctas = kLnBwdCtas;
+  const int smem = 8 * 3 * D * 4;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return WM_ERR_CUDA;
+  layernorm_bwd_kernel<<<ctas, 256, smem, stream>>>(dy, x, gamma, mean, rstd, dx, dx_drop, M, D, drop_thresh,
+                                                    drop_scale, seed, stream_id, workspace);
+  if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
+  ln_bwd_finalize_kernel<<<(3 * D + 255) / 256, 256, 0, stream>>>(workspace, ctas, D, dgamma, dbeta, dbias);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------
+// colsum: out[n] = sum_m x[m, n] (bias gradients). blockDim (32, 8); each x-thread owns 8 columns.
+// ------------------------------------------------------------------------------------------------
+constexpr int kColsumSlabs = 296;
+
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, int ld, int M, int N, float* __restrict__ partial) {
+  __shared__ float sred[8][32][9];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;  // 8-column chunk index
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c * 8 < N) {
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * ld) + c);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += bf16_lo(aw[j]);
+        acc[2 * j + 1] += bf16_hi(aw[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sred[ty][tx][j] = acc[j];
+  __syncthreads();
+  if (ty == 0 && c * 8 < N) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += sred[w][tx][j];
+      partial[static_cast<size_t>(blockIdx.y) * N + c * 8 + j] = s;
+    }
+  }
+}
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int slabs, int N, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float s = 0.0f;
+  for (int k = 0; k < slabs; ++k) s += partial[static_cast<size_t>(k) * N + i];
+  out[i] = s;
+}
+static int colsum_slabs(int M, int N) {
+  const int gx = (N / 8 + 31) / 32;
+  int slabs = (kColsumSlabs * 4 + gx - 1) / gx;
+  if (slabs > (M + 7) / 8) slabs = (M + 7) / 8;
+  return slabs < 1 ? 1 : slabs;
+}
+size_t colsum_workspace_bytes(int M, int N) { return static_cast<size_t>(colsum_slabs(M, N)) * N * sizeof(float); }
+
+int launch_colsum(const __nv_bfloat16* x, int ld, int M, int N, float* out, float* workspace, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || (N & 7) || (ld & 7)) return WM_ERR_SHAPE;
+  const int slabs = colsum_slabs(M, N);
+  dim3 grid((N / 8 + 31) / 32, slabs);
+  colsum_kernel<<<grid, 256, 0, stream>>>(x, ld, M, N, workspace);
+  if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
+  colsum_finalize_kernel<<<(N + 255) / 256, 256, 0, stream>>>(workspace, slabs, N, out);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Loss heads. Phase 1: per-CTA partial sums -> scratch; phase 2: every CTA folds the partials in a
+// fixed order (deterministic), CTA 0 publishes the scalars, all CTAs write dY (bf16, padded ld).
+// scratch layout: [kLossCtas][4] floats.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLossCtas = 592;
+
+WM_DEVICE void block_reduce4(float (&v)[4], float* sbuf /* [8][4] */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sbuf[warp * 4 + k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float s = 0.0f;
+    for (int w = 0; w < 8; ++w) s += sbuf[w * 4 + k];
+    v[k] = s;
+  }
+  __syncthreads();
+}
+// every thread folds the CTA partials in the same fixed order
+WM_DEVICE void fold_partials(const float* scratch, int nctas, float (&tot)[4], float* sbuf) {
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < nctas; i += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] += scratch[i * 4 + k];
+  }
+  block_reduce4(v, sbuf);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) tot[k] = v[k];
+}
+
+__global__ void __launch_bounds__(256)
+loss_bert_partial_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ weather,
+                         const uint8_t* __restrict__ mask, int64_t M, int F, float* __restrict__ scratch) {
+  __shared__ float sbuf[32];
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t n = M * F;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (mask[i]) {
+      const int64_t t = i / F;
+      const int f = static_cast<int>(i - t * F);
+      const float d = weather[i] - y[t * ldy + f];
+      v[0] = fmaf(d, d, v[0]);
+      v[1] += 1.0f;
+    }
+  }
+  block_reduce4(v, sbuf);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) scratch[blockIdx.x * 4 + k] = v[k];
+  }
+}
+__global__ void __launch_bounds__(256)
+loss_bert_grad_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ weather,
+                      const uint8_t* __restrict__ mask, int64_t M, int F, const float* __restrict__ scratch,
+                      int nctas, float* __restrict__ loss_out, __nv_bfloat16* __restrict__ dy, int lddy) {
+  __shared__ float sbuf[32];
+  float tot[4];
+  fold_partials(scratch, nctas, tot, sbuf);
+  const float inv = 1.0f / tot[1];  // NaN/Inf if nothing is masked, exactly as the reference's mean over []
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    loss_out[0] = tot[0] * inv;
+    loss_out[1] = tot[1];
+  }
+  if (!dy) return;
+  const int64_t n = M * lddy;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t t = i / lddy;
+    const int f = static_cast<int>(i - t * lddy);
+    float gval = 0.0f;
+    if (f < F && mask[t * F + f]) gval = 2.0f * (y[t * ldy + f] - weather[t * F + f]) * inv;
+    dy[i] = __float2bfloat16(gval);
+  }
+}
+
+int launch_loss_bert(const float* y, int ldy, const float* weather, const uint8_t* mask, int64_t M, int F,
+                     float* scratch, float* loss_out, __nv_bfloat16* dy, int lddy, cudaStream_t stream) {
+  if (M <= 0 || F <= 0) return WM_ERR_SHAPE;
+  int ctas = static_cast<int>((M * F + 255) / 256);
+  if (ctas > kLossCtas) ctas = kLossCtas;
+  loss_bert_partial_kernel<<<ctas, 256, 0, stream>>>(y, ldy, weather, mask, M, F, scratch);
+  if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
+  loss_bert_grad_kernel<<<kLossCtas, 256, 0, stream>>>(y, ldy, weather, mask, M, F, scratch, ctas, loss_out, dy, lddy);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// WeatherFormer ELBO. y[t, 0:F] = mu, y[t, F:2F] = log-variance.
+struct FormerTerms {
+  float nll, kl, dmu_r, dmu_k, dl_r, dl_k;
+};
+WM_DEVICE FormerTerms former_terms(float x, float mu, float lv) {
+  const float e = expf(lv);
+  const float v = fminf(fmaxf(e, 1e-6f), 1.0f);
+  const float d = x - mu;
+  FormerTerms t;
+  t.nll = 0.5f * logf(2.0f * 3.14159265358979323846f * v) + 0.5f * d * d / v;
+  t.kl = 0.5f * (logf(1.0f / v) + v + mu * mu - 1.0f);
+  const float gate = (e >= 1e-6f && e <= 1.0f) ? e : 0.0f;  // d clamp(exp(l)) / dl
+  t.dmu_r = -d / v;
+  t.dmu_k = mu;
+  t.dl_r = (0.5f / v - 0.5f * d * d / (v * v)) * gate;
+  t.dl_k = 0.5f * (1.0f - 1.0f / v) * gate;
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+loss_former_partial_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ weather,
+                           const uint8_t* __restrict__ mask, int64_t msb, int64_t mss, int B, int S, int F,
+                           float* __restrict__ scratch, float* __restrict__ mu_out, float* __restrict__ var_out) {
+  __shared__ float sbuf[32];
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t n = static_cast<int64_t>(B) * S * F;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t t = i / F;
+    const int f = static_cast<int>(i - t * F);
+    const int64_t b = t / S, s = t - b * S;
+    const float mu = y[t * ldy + f], lv = y[t * ldy + F + f];
+    if (mu_out) {
+      mu_out[i] = mu;
+      var_out[i] = fminf(fmaxf(expf(lv), 1e-6f), 1.0f);
+    }
+    if (mask[b * msb + s * mss + f]) {
+      const FormerTerms tm = former_terms(weather[i], mu, lv);
+      v[0] += tm.nll;
+      v[1] += tm.kl;
+      v[2] += 1.0f;
+    }
+  }
+  block_reduce4(v, sbuf);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) scratch[blockIdx.x * 4 + k] = v[k];
+  }
+}
+__global__ void __launch_bounds__(256)
+loss_former_grad_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ weather,
+                        const uint8_t* __restrict__ mask, int64_t msb, int64_t mss, int B, int S, int F,
+                        float beta, const float* __restrict__ scratch, int nctas, float* __restrict__ loss_out,
+                        __nv_bfloat16* __restrict__ dy, int lddy) {
+  __shared__ float sbuf[32];
+  float tot[4];
+  fold_partials(scratch, nctas, tot, sbuf);
+  // n_bar = tot[2] / B ; recon = (1/B) sum_b nll_b / n_bar = tot[0] / tot[2] ; kl likewise * beta
+  const float inv = 1.0f / tot[2];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const float recon = tot[0] * inv, kl = beta * tot[1] * inv;
+    loss_out[0] = recon + kl;
+    loss_out[1] = recon;
+    loss_out[2] = kl;
+    loss_out[3] = tot[2];
+  }
+  if (!dy) return;
+  const int64_t M = static_cast<int64_t>(B) * S;
+  const int64_t n = M * F;
+  // zero the padding columns [2F, lddy)
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < M * (lddy - 2 * F);
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t t = i / (lddy - 2 * F);
+    dy[t * lddy + 2 * F + (i - t * (lddy - 2 * F))] = __float2bfloat16(0.0f);
+  }
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t t = i / F;
+    const int f = static_cast<int>(i - t * F);
+    const int64_t b = t / S, s = t - b * S;
+    float gm = 0.0f, gl = 0.0f;
+    if (mask[b * msb + s * mss + f]) {
+      const FormerTerms tm = former_terms(weather[i], y[t * ldy + f], y[t * ldy + F + f]);
+      gm = (tm.dmu_r + beta * tm.dmu_k) * inv;
+      gl = (tm.dl_r + beta * tm.dl_k) * inv;
+    }
+    dy[t * lddy + f] = __float2bfloat16(gm);
+    dy[t * lddy + F + f] = __float2bfloat16(gl);
+  }
+}
+
+int launch_loss_former(const float* y, int ldy, const float* weather, const uint8_t* mask, int64_t msb,
+                       int64_t mss, int B, int S, int F, float beta, float* scratch, float* loss_out,
+                       __nv_bfloat16* dy, int lddy, float* mu_out, float* var_out, cudaStream_t stream) {
+  if (B <= 0 || S <= 0 || F <= 0 || (dy && lddy < 2 * F)) return WM_ERR_SHAPE;
+  const int64_t n = static_cast<int64_t>(B) * S * F;
+  int ctas = static_cast<int>((n + 255) / 256);
+  if (ctas > kLossCtas) ctas = kLossCtas;
+  loss_former_partial_kernel<<<ctas, 256, 0, stream>>>(y, ldy, weather, mask, msb, mss, B, S, F, scratch, mu_out, var_out);
+  if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
+  loss_former_grad_kernel<<<kLossCtas, 256, 0, stream>>>(y, ldy, weather, mask, msb, mss, B, S, F, beta, scratch,
+                                                         ctas, loss_out, dy, lddy);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam, amsgrad=False, maximize=False). Also refreshes the bf16 shadow weights.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            __nv_bfloat16* __restrict__ shadow, int64_t n, float lr, float beta1, float beta2, float eps,
+            float weight_decay, float bc1, float bc2_sqrt, float grad_scale) {
+  const float step_size = lr / bc1;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    float pi = p[i];
+    if (weight_decay != 0.0f) gi = fmaf(weight_decay, pi, gi);
+    float mi = m[i], vi = v[i];
+    mi = mi + (1.0f - beta1) * (gi - mi);            // exp_avg.lerp_(grad, 1 - beta1), weight < 0.5
+    vi = vi * beta2 + (1.0f - beta2) * gi * gi;      // mul_(beta2).addcmul_(g, g, 1 - beta2)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi = pi - step_size * (mi / denom);              // addcdiv_(exp_avg, denom, value=-step_size)
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (shadow) shadow[i] = __float2bfloat16(pi);
+  }
+}
+
+int launch_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, __nv_bfloat16* shadow,
+                int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                float grad_scale, cudaStream_t stream) {
+  if (n <= 0) return WM_OK;
+  if (step < 1) return WM_ERR_ARG;
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_kernel<<<blocks, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, shadow, n, lr, beta1, beta2, eps,
+                                          weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
+                                          grad_scale);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// wt[c, r] = bf16(w[r, c]); wt row pitch ld_out >= rows, pad columns zeroed by the caller (memset once)
+__global__ void __launch_bounds__(256)
+cast_transpose_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt, int rows, int cols, int ld_out) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    tile[j][tx] = (r < rows && c < cols) ? w[static_cast<size_t>(r) * cols + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (c < cols && r < rows) wt[static_cast<size_t>(c) * ld_out + r] = __float2bfloat16(tile[tx][j]);
+  }
+}
+int launch_cast_transpose(const float* w, __nv_bfloat16* wt, int rows, int cols, int ld_out, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0 || ld_out < rows) return WM_ERR_SHAPE;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  cast_transpose_kernel<<<grid, 256, 0, stream>>>(w, wt, rows, cols, ld_out);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+int launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return WM_OK;
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cast_bf16_kernel<<<blocks, 256, 0, stream>>>(src, dst, n);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+}  // namespace wm

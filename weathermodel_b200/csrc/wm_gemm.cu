@@ -1,0 +1,589 @@
+// wm_gemm.cu -- tcgen05 / TMEM / TMA GEMMs for the encoder's dense layers (sm_100a only).
+//
+// Replaces the cuBLAS SGEMMs the reference reaches through nn.Linear / F.multi_head_attention_forward
+// (reference: src/pretraining/models/weatherbert.py:34,45-56; torch/nn/modules/transformer.py:944-982)
+//
+//   gemm_tn   : C[M,N] = epilogue( A[M,K] . B[N,K]^T )   A,B bf16 row-major (K contiguous), fp32 acc.
+//               Persistent, warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (one thread),
+//               warps2-5 = epilogue (TMEM -> regs -> fused bias/ReLU/dropout/residual -> global).
+//               TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of i+1.
+//               Used for forward linears and for dgrad (with a transposed bf16 weight copy as B).
+//   gemm_wgrad: P[s][Nout,Kout] = A[Mtok,Nout]^T . B[Mtok,Kout] over token slice s (split-K),
+//               both operands MN-major straight from the token-major activations (no transposes),
+//               fp32 partials reduced deterministically by wgrad_reduce.
+#include "wm_kernels.h"
+
+namespace wm {
+
+// ------------------------------------------------------------------------------------------------
+// host: TMA descriptor encode through the driver entry point (no -lcuda link dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2D bf16 row-major tensor [rows, cols] with row pitch ld (elements); box = {box_cols, box_rows};
+// 128B swizzle (box_cols must be 64 bf16 = 128 B). Out-of-bounds elements read as zero.
+int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                   uint32_t box_cols, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return WM_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((ld * 2) & 15u)) return WM_ERR_ALIGN;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? WM_OK : WM_ERR_DRIVER;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gemm_tn
+// ------------------------------------------------------------------------------------------------
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kMaxStages = 8;
+constexpr int kGemmThreads = 192;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kAccStride = 256;
+
+struct GemmSmemTail {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int NC, typename OutT>
+WM_DEVICE void epilogue_chunk(uint32_t taddr, const GemmEpilogue& ep, int row, int n0, int M, int N) {
+  uint32_t v[NC];
+  if constexpr (NC == 32) {
+    tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(v));
+  } else {
+    tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(v));
+  }
+  tmem_ld_wait();
+  if (row >= M) return;
+#pragma unroll
+  for (int g = 0; g < NC / 8; ++g) {
+    const int n = n0 + g * 8;
+    if (n >= N) break;  // N is a multiple of 8 at every call site (checked on the host)
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+    if (ep.bias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
+      f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+      f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+    }
+    if (ep.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
+    }
+    if (ep.drop_thresh) {
+      const uint64_t grp = (static_cast<uint64_t>(row) * static_cast<uint64_t>(N) + n) >> 3;
+      const uint32_t keep = dropout_keep8(ep.seed, ep.stream, grp, ep.drop_thresh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1u) ? f[j] * ep.drop_scale : 0.0f;
+    }
+    if (ep.gate) {  // multiplicative ReLU/dropout gate for dgrad through dropout(relu(.)): aux > 0
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(ep.gate + static_cast<size_t>(row) * ep.ld_gate + n));
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f[2 * j] = bf16_lo(aw[j]) > 0.0f ? f[2 * j] * ep.gate_scale : 0.0f;
+        f[2 * j + 1] = bf16_hi(aw[j]) > 0.0f ? f[2 * j + 1] * ep.gate_scale : 0.0f;
+      }
+    }
+    if (ep.residual) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(row) * ep.ld_res + n));
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f[2 * j] += bf16_lo(aw[j]);
+        f[2 * j + 1] += bf16_hi(aw[j]);
+      }
+    }
+    if constexpr (sizeof(OutT) == 2) {
+      uint4 o;
+      o.x = pack_bf16x2(f[0], f[1]);
+      o.y = pack_bf16x2(f[2], f[3]);
+      o.z = pack_bf16x2(f[4], f[5]);
+      o.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(row) * ep.ld_out + n) = o;
+    } else {
+      float* o = reinterpret_cast<float*>(ep.out) + static_cast<size_t>(row) * ep.ld_out + n;
+      *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               int M, int N, int K, int BN, int stages, GemmEpilogue ep) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024B-align the tile ring (SWIZZLE_128B atoms)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = kBM * kBK * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(BN) * kBK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(smem + static_cast<size_t>(stages) * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + kBM - 1) / kBM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&tail->full[s], 1);
+      mbar_init(&tail->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tail->acc_full[s], 1);
+      mbar_init(&tail->acc_empty[s], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(&tail->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&tail->empty[s], ph ^ 1u, 11);
+          uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
+          mbar_arrive_expect_tx(&tail->full[s], stage_bytes);
+          tma_load_2d(sa, &tmA, &tail->full[s], kb * kBK, m_blk * kBM);
+          tma_load_2d(sa + a_bytes, &tmB, &tail->full[s], kb * kBK, n_blk * BN);
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kBM, static_cast<uint32_t>(BN), 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1u;
+        mbar_wait(&tail->acc_empty[as], aph ^ 1u, 12);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&tail->full[s], ph, 13);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * 32, 16, 1024, UMMA_SWZ_128B);
+            const uint64_t db = umma_smem_desc(sb + k * 32, 16, 1024, UMMA_SWZ_128B);
+            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&tail->empty[s]);
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(&tail->acc_full[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1u;
+      mbar_wait(&tail->acc_full[as], aph, 14);
+      tc_fence_after();
+      const int row = m_blk * kBM + q * 32 + lane;
+      const uint32_t tbase = tmem_base + as * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      int c0 = 0;
+      for (; c0 + 32 <= BN; c0 += 32)
+        epilogue_chunk<32, OutT>(tbase + c0, ep, row, n_blk * BN + c0, M, N);
+      if (c0 < BN) epilogue_chunk<16, OutT>(tbase + c0, ep, row, n_blk * BN + c0, M, N);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->acc_empty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+static int pick_bn(int N) {
+  const int nt = (N + 255) / 256;
+  int bn = (N + nt - 1) / nt;
+  bn = (bn + 15) / 16 * 16;
+  if (bn < 16) bn = 16;
+  return bn;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+static int launch_gemm_tn_impl(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int b_rows,
+                               const GemmEpilogue& ep, int out_fp32, int bn_override, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || b_rows <= 0 || b_rows > N) return WM_ERR_SHAPE;
+  if ((N & 7) || (K & 7) || (lda & 7) || (ldb & 7) || (ep.ld_out & 7)) return WM_ERR_ALIGN;
+  const int BN = bn_override > 0 ? bn_override : pick_bn(N);
+  if (BN & 15 || BN > 256) return WM_ERR_SHAPE;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16(&tmA, A, M, K, lda, kBK, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, B, b_rows, K, ldb, kBK, BN);
+  if (rc) return rc;
+  const int stage_bytes = (kBM + BN) * kBK * 2;
+  int stages = (227 * 1024 - 2048 - static_cast<int>(sizeof(GemmSmemTail))) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  const int smem = stages * stage_bytes + static_cast<int>(sizeof(GemmSmemTail)) + 1024;
+  const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + BN - 1) / BN;
+  const int grid = min(m_tiles * n_tiles, num_sms());
+  cudaError_t e;
+  if (out_fp32) {
+    e = cudaFuncSetAttribute(gemm_tn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return WM_ERR_CUDA;
+    gemm_tn_kernel<float><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, BN, stages, ep);
+  } else {
+    e = cudaFuncSetAttribute(gemm_tn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return WM_ERR_CUDA;
+    gemm_tn_kernel<__nv_bfloat16><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, BN, stages, ep);
+  }
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
+                   const GemmEpilogue& ep, int out_fp32, int bn_override, cudaStream_t stream) {
+  return launch_gemm_tn_impl(A, lda, B, ldb, M, N, K, N, ep, out_fp32, bn_override, stream);
+}
+// B has only b_rows (< N) real rows; the rest of the N tile is TMA zero-fill (padded output heads)
+int launch_gemm_tn_rows(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int b_rows,
+                        const GemmEpilogue& ep, int out_fp32, cudaStream_t stream) {
+  return launch_gemm_tn_impl(A, lda, B, ldb, M, N, K, b_rows, ep, out_fp32, 0, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// gemm_wgrad: P[split][Nout, Kout] = sum_{t in slice} A[t, Nout]^T B[t, Kout]   (both MN-major)
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgStages = 4;
+struct WgSmemTail {
+  uint64_t full[kWgStages];
+  uint64_t empty[kWgStages];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  int Mtok, int Nout, int Kout, int BN, int tok_per_split, float* __restrict__ partial) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = kBM * kBK * 2;                             // 2 boxes of 64 tok x 64 n
+  const uint32_t b_bytes = static_cast<uint32_t>(BN) * kBK * 2;       // BN/64 boxes
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  WgSmemTail* tail = reinterpret_cast<WgSmemTail*>(smem + static_cast<size_t>(kWgStages) * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x;  // tile over Nout (UMMA M side)
+  const int k_blk = blockIdx.y;  // tile over Kout (UMMA N side)
+  const int split = blockIdx.z;
+  const int tok0 = split * tok_per_split;
+  const int tok1 = min(Mtok, tok0 + tok_per_split);
+  const int num_kb = (tok1 - tok0 + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(&tail->full[s], 1);
+      mbar_init(&tail->empty[s], 1);
+    }
+    mbar_init(&tail->acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(&tail->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&tail->empty[s], ph ^ 1u, 21);
+        uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
+        mbar_arrive_expect_tx(&tail->full[s], stage_bytes);
+        const int t = tok0 + kb * kBK;
+        // NOTE: token rows past tok1 but < Mtok would belong to the next split; tok_per_split is a
+        // multiple of 64 so a box never straddles a split boundary; rows >= Mtok are zero-filled.
+        for (int c = 0; c < kBM / 64; ++c)
+          tma_load_2d(sa + c * 8192, &tmA, &tail->full[s], n_blk * kBM + c * 64, t);
+        for (int c = 0; c < BN / 64; ++c)
+          tma_load_2d(sa + a_bytes + c * 8192, &tmB, &tail->full[s], k_blk * BN + c * 64, t);
+        if (++s == kWgStages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kBM, static_cast<uint32_t>(BN), 1, 1);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&tail->full[s], ph, 23);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+        const uint32_t sb = sa + a_bytes;
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // MN-major SW128: 64-wide MN chunks LBO=8192 B apart, 8-token groups SBO=1024 B apart
+          const uint64_t da = umma_smem_desc(sa + k * 2048, 8192, 1024, UMMA_SWZ_128B);
+          const uint64_t db = umma_smem_desc(sb + k * 2048, 8192, 1024, UMMA_SWZ_128B);
+          umma_ss(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&tail->empty[s]);
+        if (++s == kWgStages) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(&tail->acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    float* out = partial + static_cast<size_t>(split) * Nout * Kout;
+    const int row = n_blk * kBM + q * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(&tail->acc_full, 0, 24);
+      tc_fence_after();
+    }
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      if (num_kb > 0) {
+        tmem_ld32(tmem_base + c0 + (static_cast<uint32_t>(q * 32) << 16), v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (row < Nout) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int n = k_blk * BN + c0 + g * 4;
+          if (n < Kout)  // Kout % 4 == 0 (host-checked)
+            *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * Kout + n) =
+                make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
+                            __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+// out[r, c] = (accumulate ? out[r, c] : 0) + sum_s partial[s][r, c] for r < rows_valid, c < cols_valid
+// (fixed summation order -> deterministic); out row pitch ld_out, partial tiles are [Nout, Kout].
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int Nout, int Kout,
+                                    int rows_valid, int cols_valid, int ld_out, int splits, int accumulate) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(rows_valid) * cols_valid) return;
+  const int r = static_cast<int>(i / cols_valid), c = static_cast<int>(i - static_cast<int64_t>(r) * cols_valid);
+  const size_t n = static_cast<size_t>(Nout) * Kout;
+  const size_t src = static_cast<size_t>(r) * Kout + c;
+  float acc = accumulate ? out[static_cast<size_t>(r) * ld_out + c] : 0.0f;
+  for (int s = 0; s < splits; ++s) acc += __ldg(partial + s * n + src);
+  out[static_cast<size_t>(r) * ld_out + c] = acc;
+}
+
+int wgrad_plan(int Mtok, int Nout, int Kout, int* BN, int* splits, int* tok_per_split) {
+  int bn;
+  if (Kout <= 64) bn = 64;
+  else if (Kout <= 128) bn = 128;
+  else if (Kout % 192 == 0 || (Kout > 128 && Kout <= 192)) bn = 192;
+  else bn = 256;
+  const int tiles = ((Nout + kBM - 1) / kBM) * ((Kout + bn - 1) / bn);
+  int sp = (2 * num_sms() + tiles - 1) / tiles;  // ~2 waves of work items
+  const int kb_total = (Mtok + kBK - 1) / kBK;
+  if (sp > kb_total) sp = kb_total;
+  if (sp < 1) sp = 1;
+  int kb_per = (kb_total + sp - 1) / sp;
+  sp = (kb_total + kb_per - 1) / kb_per;
+  *BN = bn;
+  *splits = sp;
+  *tok_per_split = kb_per * kBK;
+  return tiles;
+}
+
+size_t wgrad_workspace_bytes(int Mtok, int Nout, int Kout) {
+  int bn, sp, tps;
+  wgrad_plan(Mtok, Nout, Kout, &bn, &sp, &tps);
+  return static_cast<size_t>(sp) * Nout * Kout * sizeof(float);
+}
+
+static int launch_gemm_wgrad_impl(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout,
+                                  float* dW, int rows_valid, int cols_valid, int ld_dw, int accumulate,
+                                  float* workspace, cudaStream_t stream) {
+  if (Mtok <= 0 || Nout <= 0 || Kout <= 0) return WM_ERR_SHAPE;
+  if (rows_valid > Nout || cols_valid > Kout || ld_dw < cols_valid) return WM_ERR_SHAPE;
+  if ((Nout & 7) || (Kout & 7) || (lda & 7) || (ldb & 7)) return WM_ERR_ALIGN;
+  int BN, splits, tps;
+  wgrad_plan(Mtok, Nout, Kout, &BN, &splits, &tps);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16(&tmA, A, Mtok, Nout, lda, 64, kBK);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, B, Mtok, Kout, ldb, 64, kBK);
+  if (rc) return rc;
+  const int stage_bytes = (kBM + BN) * kBK * 2;
+  const int smem = kWgStages * stage_bytes + static_cast<int>(sizeof(WgSmemTail)) + 1024;
+  if (cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return WM_ERR_CUDA;
+  dim3 grid((Nout + kBM - 1) / kBM, (Kout + BN - 1) / BN, splits);
+  gemm_wgrad_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, Mtok, Nout, Kout, BN, tps, workspace);
+  if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
+  const int64_t n = static_cast<int64_t>(rows_valid) * cols_valid;
+  const int threads = 256;
+  const int blocks = static_cast<int>((n + threads - 1) / threads);
+  wgrad_reduce_kernel<<<blocks, threads, 0, stream>>>(workspace, dW, Nout, Kout, rows_valid, cols_valid, ld_dw,
+                                                      splits, accumulate);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+int launch_gemm_wgrad(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout, float* dW,
+                      int accumulate, float* workspace, cudaStream_t stream) {
+  return launch_gemm_wgrad_impl(A, lda, B, ldb, Mtok, Nout, Kout, dW, Nout, Kout, Kout, accumulate, workspace, stream);
+}
+// only the top-left [rows_valid, cols_valid] block of the product is written, with row pitch ld_dw
+int launch_gemm_wgrad_ex(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout, float* dW,
+                         int rows_valid, int cols_valid, int ld_dw, float* workspace, cudaStream_t stream) {
+  return launch_gemm_wgrad_impl(A, lda, B, ldb, Mtok, Nout, Kout, dW, rows_valid, cols_valid, ld_dw, 0, workspace,
+                                stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// umma_probe: one CTA, one 128 x N x K product with operands staged by hand into the UNSWIZZLED
+// canonical core-matrix layouts the attention kernels use. Validates descriptor semantics
+// (K-major / MN-major, LBO / SBO) on hardware independently of TMA.
+//   A: [128, K] bf16 row-major in global, B: [N, K] bf16 row-major, D: [128, N] fp32.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
+                  float* __restrict__ D, int N, int K, int a_mn, int b_mn) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int kg = K / 8;  // core matrices along K
+  // K-major : elem(r,k) at (r/8)*SBO + (k/8)*LBO + (r%8)*16 + (k%8)*2,  LBO=128, SBO=kg*128
+  // MN-major: elem(r,k) at (r/8)*SBO + (k/8)*LBO + (k%8)*16 + (r%8)*2,  SBO=128, LBO=(rows/8)*128
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * K * 2;
+  const uint32_t a_lbo = a_mn ? (128 / 8) * 128 : 128, a_sbo = a_mn ? 128 : kg * 128;
+  const uint32_t b_lbo = b_mn ? (N / 8) * 128 : 128, b_sbo = b_mn ? 128 : kg * 128;
+  for (int i = threadIdx.x; i < 128 * K; i += blockDim.x) {
+    const int r = i / K, k = i % K;
+    const uint32_t off = (r / 8) * a_sbo + (k / 8) * a_lbo + (a_mn ? (k % 8) * 16 + (r % 8) * 2 : (r % 8) * 16 + (k % 8) * 2);
+    *reinterpret_cast<__nv_bfloat16*>(sA + off) = A[i];
+  }
+  for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
+    const int r = i / K, k = i % K;
+    const uint32_t off = (r / 8) * b_sbo + (k / 8) * b_lbo + (b_mn ? (k % 8) * 16 + (r % 8) * 2 : (r % 8) * 16 + (k % 8) * 2);
+    *reinterpret_cast<__nv_bfloat16*>(sB + off) = B[i];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<256>(&tmem_slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(N), a_mn, b_mn);
+    for (int k = 0; k < K / 16; ++k) {
+      // one UMMA covers 16 k = two core matrices along K
+      const uint64_t da = umma_smem_desc(smem_u32(sA) + k * 2 * a_lbo, a_lbo, a_sbo, UMMA_SWZ_NONE);
+      const uint64_t db = umma_smem_desc(smem_u32(sB) + k * 2 * b_lbo, b_lbo, b_sbo, UMMA_SWZ_NONE);
+      umma_ss(tmem_base, da, db, idesc, k != 0);
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0, 31);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem_base + c0 + (static_cast<uint32_t>(warp * 32) << 16), v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[static_cast<size_t>(row) * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+int launch_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_mn, int b_mn,
+                      cudaStream_t stream) {
+  if (N % 16 || N > 256 || K % 16 || K > 256) return WM_ERR_SHAPE;
+  const int smem = (128 + N) * K * 2 + 1024;
+  if (cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return WM_ERR_CUDA;
+  umma_probe_kernel<<<1, 128, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(A),
+                                              reinterpret_cast<const __nv_bfloat16*>(B), D, N, K, a_mn, b_mn);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+}  // namespace wm

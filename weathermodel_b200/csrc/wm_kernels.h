@@ -1,0 +1,90 @@
+// wm_kernels.h -- internal (C++) launcher declarations shared by the .cu translation units.
+// The public C-ABI lives in include/wm_b200.h; wm_api.cu maps one onto the other.
+#pragma once
+
+#include "wm_common.cuh"
+#include <stddef.h>
+
+#define WM_OK 0
+#define WM_ERR_SHAPE 1
+#define WM_ERR_ALIGN 2
+#define WM_ERR_CUDA 3
+#define WM_ERR_DRIVER 4
+#define WM_ERR_ARG 5
+#define WM_ERR_DEVICE 6
+
+namespace wm {
+
+// Fused GEMM epilogue: v = acc (+bias) -> [relu] -> [dropout] -> [gate: aux>0 ? v*s : 0] -> (+residual)
+struct GemmEpilogue {
+  const float* bias = nullptr;           // [N] fp32
+  int relu = 0;
+  uint32_t drop_thresh = 0;              // round(p * 65536); 0 = no dropout
+  float drop_scale = 1.0f;               // 1 / (1 - p)
+  uint64_t seed = 0;                     // Philox key
+  uint64_t stream = 0;                   // Philox subsequence: (step, layer, site)
+  const __nv_bfloat16* gate = nullptr;   // [M, ld_gate] saved post-activation (dgrad through ReLU+dropout)
+  int ld_gate = 0;
+  float gate_scale = 1.0f;
+  const __nv_bfloat16* residual = nullptr;  // [M, ld_res]
+  int ld_res = 0;
+  void* out = nullptr;                   // [M, ld_out] bf16 or fp32
+  int ld_out = 0;
+};
+
+int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                   uint32_t box_cols, uint32_t box_rows);
+
+int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
+                   const GemmEpilogue& ep, int out_fp32, int bn_override, cudaStream_t stream);
+int launch_gemm_tn_rows(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int b_rows,
+                        const GemmEpilogue& ep, int out_fp32, cudaStream_t stream);
+int launch_gemm_wgrad_ex(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout, float* dW,
+                         int rows_valid, int cols_valid, int ld_dw, float* workspace, cudaStream_t stream);
+size_t wgrad_workspace_bytes(int Mtok, int Nout, int Kout);
+int launch_gemm_wgrad(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout,
+                      float* dW, int accumulate, float* workspace, cudaStream_t stream);
+int launch_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_mn, int b_mn,
+                      cudaStream_t stream);
+
+// ---- memory-bound kernels (wm_elementwise.cu) ------------------------------------------------
+int launch_mask_bert(uint64_t seed, uint64_t philox_offset, int grid_x, float p, int64_t numel,
+                     uint8_t* mask, float* rand_out, cudaStream_t stream);
+int launch_mask_former(uint64_t seed, uint64_t philox_offset, int grid_x, int n_masked, int64_t n_samples,
+                       int n_features, uint8_t* mask, cudaStream_t stream);
+int launch_embed_fwd(const float* weather, const uint8_t* mask, int64_t mask_stride_b, int64_t mask_stride_s,
+                     const float* year, const float* coords, const float* w_in, const float* b_in,
+                     const float* pe, __nv_bfloat16* out, __nv_bfloat16* xin, int B, int S, int F, int D,
+                     cudaStream_t stream);
+int launch_layernorm_fwd(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y,
+                         float* mean, float* rstd, int M, int D, float eps, cudaStream_t stream);
+size_t layernorm_bwd_workspace_bytes(int M, int D);
+int launch_layernorm_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const float* gamma,
+                         const float* mean, const float* rstd, __nv_bfloat16* dx, __nv_bfloat16* dx_drop,
+                         float* dgamma, float* dbeta, float* dbias, int M, int D, uint32_t drop_thresh,
+                         float drop_scale, uint64_t seed, uint64_t stream_id, float* workspace,
+                         cudaStream_t stream);
+size_t colsum_workspace_bytes(int M, int N);
+int launch_colsum(const __nv_bfloat16* x, int ld, int M, int N, float* out, float* workspace,
+                  cudaStream_t stream);
+int launch_loss_bert(const float* y, int ldy, const float* weather, const uint8_t* mask, int64_t M, int F,
+                     float* scratch, float* loss_out, __nv_bfloat16* dy, int lddy, cudaStream_t stream);
+int launch_loss_former(const float* y, int ldy, const float* weather, const uint8_t* mask,
+                       int64_t mask_stride_b, int64_t mask_stride_s, int B, int S, int F, float beta,
+                       float* scratch, float* loss_out, __nv_bfloat16* dy, int lddy, float* mu_out,
+                       float* var_out, cudaStream_t stream);
+int launch_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, __nv_bfloat16* shadow,
+                int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                float grad_scale, cudaStream_t stream);
+int launch_cast_transpose(const float* w, __nv_bfloat16* wt, int rows, int cols, int ld_out, cudaStream_t stream);
+int launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream);
+
+// ---- attention (wm_attn.cu) --------------------------------------------------------------------
+int launch_attn_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, int B, int S, int H, int dh,
+                    uint32_t drop_thresh, float drop_scale, uint64_t seed, uint64_t stream_id,
+                    cudaStream_t stream);
+int launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __nv_bfloat16* dctx,
+                    const float* lse, __nv_bfloat16* dqkv, int B, int S, int H, int dh, uint32_t drop_thresh,
+                    float drop_scale, uint64_t seed, uint64_t stream_id, cudaStream_t stream);
+
+}  // namespace wm

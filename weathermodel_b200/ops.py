@@ -1,0 +1,241 @@
+"""Torch-tensor front end of the per-kernel C ABI (include/wm_b200.h).
+
+PyTorch is used for device memory and streams only: every function here takes CUDA tensors, passes
+their `data_ptr()` and the current stream handle to libwm_b200.so and returns torch tensors that it
+allocated with `torch.empty`. Nothing is computed in PyTorch; a missing library or a non-zero status
+raises (see `_lib.check`).
+"""
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and (not t.is_cuda):
+            raise RuntimeError("weathermodel_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def device_error() -> int:
+    return lib().wm_device_error()
+
+
+# ---------------------------------------------------------------------------------------------
+# masks
+# ---------------------------------------------------------------------------------------------
+def _consume_generator(numel: int, device) -> Tuple[int, int, int]:
+    """Reserve the Philox range torch.rand(numel) would use on `device`'s default generator and
+    return (seed, philox_offset, grid_x) -- mirrors calc_execution_policy + philox_cuda_state
+    (torch/include/ATen/native/cuda/DistributionTemplates.h:50-63)."""
+    gen = torch.cuda.default_generators[torch.device(device).index or 0]
+    grid_x = lib().wm_rand_grid_x(numel)
+    counter_offset = ((numel - 1) // (256 * grid_x * 4) + 1) * 4
+    seed = gen.initial_seed()
+    offset = gen.get_offset()
+    gen.set_offset(offset + counter_offset)
+    return seed, offset, grid_x
+
+
+def mask_bert(seq_len: int, n_features: int, batch_size: int, masking_prob: float, device="cuda",
+              return_rand: bool = False):
+    """== (torch.rand(batch, seq, feat, device=cuda) < p), bit-exact, advancing the default CUDA
+    generator exactly as torch.rand would (pretraining_dataloader.py:56-66)."""
+    numel = batch_size * seq_len * n_features
+    with torch.cuda.device(device):
+        seed, offset, grid_x = _consume_generator(numel, device)
+        mask = torch.empty((batch_size, seq_len, n_features), dtype=torch.bool, device=device)
+        rnd = torch.empty((batch_size, seq_len, n_features), dtype=torch.float32, device=device) if return_rand else None
+        check(lib().wm_mask_bert(seed, offset, grid_x, masking_prob, numel, _p(mask), _p(rnd), _stream()), "wm_mask_bert")
+    return (mask, rnd) if return_rand else mask
+
+
+def mask_former(seq_len: int, n_features: int, batch_size: int, n_masked_features: int, device="cuda"):
+    """== (argsort(rand(batch, feat)) < n).unsqueeze(1).expand(-1, seq, -1), bit-exact
+    (pretraining_dataloader.py:68-84). Returns the stride-0 expanded view like the reference."""
+    numel = batch_size * n_features
+    with torch.cuda.device(device):
+        seed, offset, grid_x = _consume_generator(numel, device)
+        fmask = torch.empty((batch_size, n_features), dtype=torch.bool, device=device)
+        check(lib().wm_mask_former(seed, offset, grid_x, n_masked_features, batch_size, n_features, _p(fmask),
+                                   _stream()), "wm_mask_former")
+    return fmask.unsqueeze(1).expand(-1, seq_len, -1)
+
+
+def mask_strides(mask: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
+    """uint8 view + (batch, seq) strides of a [B,S,F] bool mask whose feature stride is 1 (dense or the
+    stride-0 expand of a [B,F] feature mask); anything else is made contiguous."""
+    if mask.dtype != torch.bool:
+        mask = mask != 0
+    if mask.dim() != 3:
+        raise ValueError("weather_feature_mask must be [batch, seq, features]")
+    if mask.stride(2) != 1 and mask.shape[2] != 1:
+        mask = mask.contiguous()
+    return mask, mask.stride(0), mask.stride(1)
+
+
+# ---------------------------------------------------------------------------------------------
+# embedding
+# ---------------------------------------------------------------------------------------------
+def embed_fwd(weather, mask, year, coords, w_in, b_in, pos_encoding, want_xin=False):
+    _cuda(weather, mask, year, coords, w_in, b_in, pos_encoding)
+    B, S, F = weather.shape
+    D = w_in.shape[0]
+    mask, msb, mss = mask_strides(mask)
+    out = torch.empty((B * S, D), dtype=BF16, device=weather.device)
+    xin = torch.empty((B * S, 64), dtype=BF16, device=weather.device) if want_xin else None
+    check(lib().wm_embed_fwd(_p(weather.contiguous()), _p(mask), msb, mss, _p(year.contiguous()),
+                             _p(coords.contiguous()), _p(w_in.contiguous()), _p(b_in.contiguous()),
+                             _p(pos_encoding.contiguous()), _p(out), _p(xin), B, S, F, D, _stream()), "wm_embed_fwd")
+    return (out, xin) if want_xin else out
+
+
+# ---------------------------------------------------------------------------------------------
+# GEMMs
+# ---------------------------------------------------------------------------------------------
+def gemm_tn(a, b, bias=None, relu=False, dropout_p=0.0, seed=0, stream_id=0, gate=None, gate_scale=1.0,
+            residual=None, out_fp32=False, tile_n=0):
+    """out[M,N] = epilogue(a[M,K] @ b[N,K]^T); a, b bf16 row-major."""
+    _cuda(a, b, bias, gate, residual)
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32 if out_fp32 else BF16, device=a.device)
+    ep = _lib.GemmEpilogue(_p(bias), int(relu), float(dropout_p), int(seed), int(stream_id), _p(gate),
+                           gate.stride(0) if gate is not None else 0, float(gate_scale), _p(residual),
+                           residual.stride(0) if residual is not None else 0)
+    check(lib().wm_gemm_tn(_p(a), a.stride(0), _p(b), b.stride(0), M, N, K, C.byref(ep), _p(out), out.stride(0),
+                           int(out_fp32), int(tile_n), _stream()), "wm_gemm_tn")
+    return out
+
+
+def gemm_wgrad(a, b, accumulate_into=None):
+    """dW[Nout,Kout] = a[Mtok,Nout]^T @ b[Mtok,Kout] (fp32 out, deterministic split-K)."""
+    _cuda(a, b)
+    Mtok, Nout = a.shape
+    Kout = b.shape[1]
+    ws = torch.empty(lib().wm_gemm_wgrad_workspace_bytes(Mtok, Nout, Kout) // 4, dtype=torch.float32, device=a.device)
+    out = accumulate_into if accumulate_into is not None else torch.empty((Nout, Kout), dtype=torch.float32, device=a.device)
+    check(lib().wm_gemm_wgrad(_p(a), a.stride(0), _p(b), b.stride(0), Mtok, Nout, Kout, _p(out),
+                              int(accumulate_into is not None), _p(ws), _stream()), "wm_gemm_wgrad")
+    return out
+
+
+def umma_probe(a, b, a_mn=False, b_mn=False):
+    _cuda(a, b)
+    N, K = b.shape
+    d = torch.empty((128, N), dtype=torch.float32, device=a.device)
+    check(lib().wm_umma_probe(_p(a), _p(b), _p(d), N, K, int(a_mn), int(b_mn), _stream()), "wm_umma_probe")
+    return d
+
+
+# ---------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------
+def attn_fwd(qkv, B, S, H, dh, dropout_p=0.0, seed=0, stream_id=0):
+    _cuda(qkv)
+    ctx = torch.empty((B * S, H * dh), dtype=BF16, device=qkv.device)
+    lse = torch.empty((B * H, S), dtype=torch.float32, device=qkv.device)
+    check(lib().wm_attn_fwd(_p(qkv), _p(ctx), _p(lse), B, S, H, dh, float(dropout_p), int(seed), int(stream_id),
+                            _stream()), "wm_attn_fwd")
+    return ctx, lse
+
+
+def attn_bwd(qkv, ctx, dctx, lse, B, S, H, dh, dropout_p=0.0, seed=0, stream_id=0):
+    _cuda(qkv, ctx, dctx, lse)
+    dqkv = torch.empty_like(qkv)
+    check(lib().wm_attn_bwd(_p(qkv), _p(ctx), _p(dctx), _p(lse), _p(dqkv), B, S, H, dh, float(dropout_p), int(seed),
+                            int(stream_id), _stream()), "wm_attn_bwd")
+    return dqkv
+
+
+# ---------------------------------------------------------------------------------------------
+# LayerNorm, column sums
+# ---------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps=1e-5):
+    _cuda(x, gamma, beta)
+    M, D = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(M, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+    check(lib().wm_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), M, D, float(eps), _stream()),
+          "wm_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dropout_p=0.0, seed=0, stream_id=0):
+    _cuda(dy, x, gamma, mean, rstd)
+    M, D = x.shape
+    dx = torch.empty_like(x)
+    dxd = torch.empty_like(x) if dropout_p > 0 else None
+    dg = torch.empty(D, dtype=torch.float32, device=x.device)
+    db = torch.empty(D, dtype=torch.float32, device=x.device)
+    dbias = torch.empty(D, dtype=torch.float32, device=x.device)
+    ws = torch.empty(lib().wm_layernorm_bwd_workspace_bytes(M, D) // 4, dtype=torch.float32, device=x.device)
+    check(lib().wm_layernorm_bwd(_p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dxd), _p(dg), _p(db),
+                                 _p(dbias), M, D, float(dropout_p), int(seed), int(stream_id), _p(ws), _stream()),
+          "wm_layernorm_bwd")
+    return dx, dxd, dg, db, dbias
+
+
+def colsum(x):
+    _cuda(x)
+    M, N = x.shape
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    ws = torch.empty(lib().wm_colsum_workspace_bytes(M, N) // 4, dtype=torch.float32, device=x.device)
+    check(lib().wm_colsum(_p(x), x.stride(0), M, N, _p(out), _p(ws), _stream()), "wm_colsum")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# loss heads, Adam
+# ---------------------------------------------------------------------------------------------
+LOSS_SCRATCH_FLOATS = 4 * 592
+
+
+def loss_bert(y, weather, mask, want_grad=True, ld_grad=32):
+    """y: fp32 [M, ldy>=F]; weather fp32 [M,F]; mask bool [M,F] dense. Returns (loss[2], dy bf16 [M, ld_grad])."""
+    _cuda(y, weather, mask)
+    M, F = weather.shape
+    scratch = torch.empty(LOSS_SCRATCH_FLOATS, dtype=torch.float32, device=y.device)
+    out = torch.empty(2, dtype=torch.float32, device=y.device)
+    dy = torch.empty((M, ld_grad), dtype=BF16, device=y.device) if want_grad else None
+    check(lib().wm_loss_bert(_p(y), y.stride(0), _p(weather), _p(mask), M, F, _p(scratch), _p(out), _p(dy), ld_grad,
+                             _stream()), "wm_loss_bert")
+    return out, dy
+
+
+def loss_former(y, weather, mask, beta, want_grad=True, ld_grad=64, want_mu_var=False):
+    """y: fp32 [B*S, ldy>=2F]; weather fp32 [B,S,F]; mask bool [B,S,F] (dense or stride-0 expand).
+    Returns (loss[4] = total, recon, kl, sum_mask; dy bf16 [B*S, ld_grad]; mu; var)."""
+    _cuda(y, weather, mask)
+    B, S, F = weather.shape
+    mask, msb, mss = mask_strides(mask)
+    scratch = torch.empty(LOSS_SCRATCH_FLOATS, dtype=torch.float32, device=y.device)
+    out = torch.empty(4, dtype=torch.float32, device=y.device)
+    dy = torch.empty((B * S, ld_grad), dtype=BF16, device=y.device) if want_grad else None
+    mu = torch.empty((B, S, F), dtype=torch.float32, device=y.device) if want_mu_var else None
+    var = torch.empty((B, S, F), dtype=torch.float32, device=y.device) if want_mu_var else None
+    check(lib().wm_loss_former(_p(y), y.stride(0), _p(weather.contiguous()), _p(mask), msb, mss, B, S, F, float(beta),
+                               _p(scratch), _p(out), _p(dy), ld_grad, _p(mu), _p(var), _stream()), "wm_loss_former")
+    return out, dy, mu, var
+
+
+def adam_fused(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+               shadow=None, grad_scale=1.0):
+    _cuda(param, grad, exp_avg, exp_avg_sq, shadow)
+    check(lib().wm_adam_fused(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(shadow), param.numel(), float(lr),
+                              float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                              float(grad_scale), _stream()), "wm_adam_fused")
