@@ -1,0 +1,169 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference from /root/reference (torch CPU, fp32).
+
+Run in the build container only (the GPU box has no /root/reference):
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+Recipe follows SURVEY.md 8(c): model built right after torch.manual_seed(1234); inputs from
+torch.Generator().manual_seed(0); mask from the reference's own masking function right after a fresh
+torch.manual_seed(1234); dropout neutralised without leaving train() mode. The script asserts the
+known-answer values recorded in SURVEY.md 8(c) before writing anything.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+os.chdir("/tmp")
+
+from src.pretraining.dataloader.pretraining_dataloader import StreamingDataset  # noqa: E402
+from src.pretraining.models.weatherbert import WeatherBERT  # noqa: E402
+from src.pretraining.models.weatherformer import WeatherFormer  # noqa: E402
+from src.utils.losses import compute_gaussian_kl_divergence, gaussian_log_likelihood  # noqa: E402
+from src.utils.utils import get_model_params, get_scheduler  # noqa: E402
+
+
+def neutralise_dropout(model):
+    for mod in model.modules():
+        if isinstance(mod, nn.Dropout):
+            mod.p = 0.0
+        if isinstance(mod, nn.MultiheadAttention):
+            mod.dropout = 0.0
+
+
+def inputs(batch):
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(batch, 365, 31, generator=g)
+    lat = torch.rand(batch, generator=g) * 120 - 60
+    lon = torch.rand(batch, generator=g) * 360 - 180
+    idx = torch.randint(0, 2, (batch,), generator=g)
+    t = torch.arange(365, dtype=torch.float32)
+    year = 1984.0 + ((idx[:, None].float() * 365 + t[None]) * 7.0) / 365
+    interval = torch.full((batch, 1), 7.0)
+    return w, torch.stack([lat, lon], 1), year, interval, idx
+
+
+def dataset(kind, p=0.15, n=10):
+    return StreamingDataset([], masking_function=kind, masking_prob=p, n_masked_features=n)
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def model_case(kind, size, batch, beta=0.5):
+    torch.manual_seed(1234)
+    cls = WeatherBERT if kind == "weatherbert" else WeatherFormer
+    model = cls(weather_dim=31, output_dim=31, device=torch.device("cpu"), **get_model_params(size))
+    model.train()
+    neutralise_dropout(model)
+    w, coords, year, interval, idx = inputs(batch)
+    torch.manual_seed(1234)
+    if kind == "weatherbert":
+        mask = dataset("weatherbert", p=0.15).masking_function(365, 31, batch)
+    else:
+        mask = dataset("weatherformer", n=10).masking_function(365, 31, batch)
+    out = model(w, coords, year, interval, weather_feature_mask=mask)
+    rec = {}
+    if kind == "weatherbert":
+        loss = nn.MSELoss(reduction="mean")(w[mask], out[mask])
+        y = out
+        rec["loss"] = np.array([loss.item()], dtype=np.float64)
+    else:
+        mu, var = out
+        nm = mask.sum(dim=(1, 2)).float().mean()
+        recon = (-gaussian_log_likelihood(w, mu, var, mask) / nm).mean()
+        kl = beta * compute_gaussian_kl_divergence(mask, mu, var, torch.zeros_like(mu), torch.ones_like(var)).mean() / nm
+        loss = recon + kl
+        rec["loss"] = np.array([loss.item(), recon.item(), kl.item()], dtype=np.float64)
+        rec["mu"] = mu.detach().numpy()
+        rec["var"] = var.detach().numpy()
+        y = None
+    loss.backward()
+    if y is not None:
+        rec["y"] = y.detach().numpy()
+    rec.update(weather=w.numpy(), coords=coords.numpy(), year=year.numpy(), interval=interval.numpy(),
+               mask=mask.contiguous().numpy(), beta=np.array([beta]), num_heads=np.array([get_model_params(size)["num_heads"]]))
+    for k, v in model.state_dict().items():
+        rec["param/" + k] = v.detach().numpy().copy()
+    for k, v in model.named_parameters():
+        rec["grad/" + k] = v.grad.detach().numpy().copy()
+    # one Adam step on these gradients (lr 5e-4) for the optimiser oracle
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    opt.step()
+    rec["adam/in_proj.weight"] = model.in_proj.weight.detach().numpy()
+    rec["adam/out_proj.bias"] = model.out_proj.bias.detach().numpy()
+    return rec, model, mask, loss
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    # ---- masks on the CPU generator (config 1), SURVEY.md 8(c) golden values
+    masks = {}
+    for name, kind, kw, want_sum, want_sha, want_idx in [
+        ("bert_p15", "weatherbert", dict(p=0.15), 108421, "9b5a0f934533c16f", [0, 4, 6]),
+        ("bert_p30", "weatherbert", dict(p=0.30), 217284, "25e3b2039b038155", [0, 2, 4, 6, 14, 16, 18, 22, 29]),
+        ("former_n10", "weatherformer", dict(n=10), 233600, "8186b49a39436e1f", [0, 1, 2, 6, 10, 11, 12, 14, 21, 23]),
+        ("former_n1", "weatherformer", dict(n=1), 23360, "996391d64bc927d0", [0]),
+    ]:
+        torch.manual_seed(1234)
+        m = dataset(kind, **kw).masking_function(365, 31, 64).contiguous().numpy()
+        assert int(m.sum()) == want_sum, (name, int(m.sum()))
+        assert sha16(m) == want_sha, (name, sha16(m))
+        assert np.nonzero(m[0, 0])[0].tolist() == want_idx, name
+        masks[name + "_sum"] = np.array([m.sum()])
+        masks[name + "_sha16"] = np.frombuffer(want_sha.encode(), dtype=np.uint8)
+        masks[name + "_row00"] = m[0, 0]
+        masks[name + "_packed"] = np.packbits(m if kind == "weatherbert" else m[:, 0, :])
+    torch.manual_seed(1234)
+    r5 = torch.rand(5).numpy()
+    assert np.allclose(r5, [0.028979241847991943, 0.4018985629081726, 0.25984418392181396, 0.3666413426399231,
+                            0.05830073356628418], atol=0, rtol=0)
+    masks["rand5_seed1234"] = r5
+    np.savez_compressed(os.path.join(OUT, "masks_cpu.npz"), **masks)
+
+    # ---- model cases
+    rec, model, mask, loss = model_case("weatherbert", "mini", 8)
+    assert int(mask.sum()) == 13435
+    assert abs(loss.item() - 1.33503056) < 2e-6, loss.item()
+    assert abs(model.in_proj.weight.grad.norm().item() - 0.08772561) < 1e-6
+    assert abs(model.out_proj.weight.grad.norm().item() - 0.65765929) < 1e-6
+    np.savez_compressed(os.path.join(OUT, "weatherbert_mini_b8.npz"), **rec)
+    rec, model, mask, loss = model_case("weatherformer", "mini", 8)
+    assert abs(rec["loss"][0] - 1.75079405) < 2e-6 and abs(rec["loss"][1] - 1.66437364) < 2e-6
+    assert abs(rec["loss"][2] - 0.08642045) < 1e-6
+    assert abs(model.in_proj.weight.grad.norm().item() - 0.07980558) < 1e-6
+    assert abs(model.out_proj.weight.grad.norm().item() - 0.70168072) < 1e-6
+    np.savez_compressed(os.path.join(OUT, "weatherformer_mini_b8.npz"), **rec)
+
+    # ---- scheduler + sizes
+    sched = {}
+    for nm, warm, total, decay in [("exp", 10.0, 100, 0.99), ("cos", 5, 50, None), ("nowarm", 0, 20, 0.9)]:
+        p = nn.Parameter(torch.zeros(1))
+        opt = torch.optim.Adam([p], lr=5e-4)
+        s = get_scheduler(opt, warm, total, decay)
+        lrs = []
+        for _ in range(total):
+            lrs.append(opt.param_groups[0]["lr"])
+            opt.step()
+            s.step()
+        sched[nm] = np.array(lrs)
+    for size in ["mini", "small", "medium", "large"]:
+        for kind, cls in [("weatherbert", WeatherBERT), ("weatherformer", WeatherFormer)]:
+            m = cls(weather_dim=31, output_dim=31, device=torch.device("cpu"), **get_model_params(size))
+            sched[f"params_{kind}_{size}"] = np.array([m.total_params()])
+            if size == "mini" and kind == "weatherbert":
+                sched["pe_mini"] = m.positional_encoding.pos_encoding.numpy()
+    np.savez_compressed(os.path.join(OUT, "schedules.npz"), **sched)
+    print("golden vectors written to", OUT)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

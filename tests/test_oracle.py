@@ -1,0 +1,142 @@
+"""Pin the CPU oracle (oracle/wm_oracle.py) against golden vectors produced by the unmodified reference
+(oracle/make_golden.py, run in the build container) and against published known answers. CPU only."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import wm_oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _load(name):
+    return dict(np.load(os.path.join(GOLD, name)))
+
+
+def _sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def test_cpu_generator_rand_known_answer():
+    g = _load("masks_cpu.npz")
+    assert np.array_equal(O.torch_cpu_rand(1234, 5), g["rand5_seed1234"])
+
+
+@pytest.mark.parametrize("name,kind,arg", [("bert_p15", "bert", 0.15), ("bert_p30", "bert", 0.30),
+                                           ("former_n10", "former", 10), ("former_n1", "former", 1)])
+def test_cpu_masks_match_reference(name, kind, arg):
+    """SURVEY.md 8(c) golden vectors: torch.manual_seed(1234); masking_function(365, 31, 64) on CPU."""
+    g = _load("masks_cpu.npz")
+    if kind == "bert":
+        m = O.weatherbert_mask(O.torch_cpu_rand(1234, 64 * 365 * 31).reshape(64, 365, 31), arg)
+        packed = np.packbits(m)
+    else:
+        m = O.weatherformer_mask(O.torch_cpu_rand(1234, 64 * 31).reshape(64, 31), arg, 365)
+        packed = np.packbits(m[:, 0, :])
+    assert int(m.sum()) == int(g[name + "_sum"][0])
+    assert _sha16(np.ascontiguousarray(m)) == bytes(g[name + "_sha16"]).decode()
+    assert np.array_equal(m[0, 0], g[name + "_row00"])
+    assert np.array_equal(packed, g[name + "_packed"])
+
+
+def test_philox_known_answer():
+    """Random123 philox4x32-10 KATs (counter, key) -> output."""
+    r = O.philox4x32_10(0, np.array([0], dtype=np.uint64), np.array([0], dtype=np.uint64))[0]
+    assert [hex(int(x)) for x in r] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    # counter = ffffffff x4, key = ffffffff x2
+    r = O.philox4x32_10(0xFFFFFFFFFFFFFFFF, np.array([0xFFFFFFFFFFFFFFFF], dtype=np.uint64),
+                        np.array([0xFFFFFFFFFFFFFFFF], dtype=np.uint64))[0]
+    assert [hex(int(x)) for x in r] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+
+
+def test_cuda_rand_structure():
+    """Without a GPU only structural properties can be checked here (bit-exactness vs torch.rand on the
+    CUDA generator is a -m gpu test): range, determinism, offset bookkeeping."""
+    n = 64 * 31
+    gx = O.rand_grid_x(n)
+    a = O.torch_cuda_rand(1234, 0, gx, n)
+    assert a.dtype == np.float32 and (a >= 0).all() and (a < 1).all()
+    assert np.array_equal(a, O.torch_cuda_rand(1234, 0, gx, n))
+    assert not np.array_equal(a, O.torch_cuda_rand(1234, 4, gx, n))
+    assert O.rand_offset_increment(n, gx) == 4
+    big = 4096 * 365 * 31
+    assert O.rand_grid_x(big) == 1184 and O.rand_offset_increment(big, 1184) == ((big - 1) // (256 * 1184 * 4) + 1) * 4
+
+
+@pytest.mark.parametrize("fname,model", [("weatherbert_mini_b8.npz", "weatherbert"),
+                                         ("weatherformer_mini_b8.npz", "weatherformer")])
+def test_encoder_loss_and_grads_match_reference(fname, model):
+    g = _load(fname)
+    state = {k[len("param/"):]: v for k, v in g.items() if k.startswith("param/")}
+    losses, Y, grads = O.train_step_grads(state, int(g["num_heads"][0]), model, g["weather"], g["coords"], g["year"],
+                                          g["interval"], g["mask"], beta=float(g["beta"][0]))
+    if model == "weatherbert":
+        assert np.allclose(Y, g["y"], rtol=1e-4, atol=2e-5)
+        assert abs(losses["total_loss"] - g["loss"][0]) < 1e-5 * abs(g["loss"][0])
+    else:
+        mu, var = O.weatherformer_head(Y, 31)
+        assert np.allclose(mu, g["mu"], rtol=1e-4, atol=2e-5)
+        assert np.allclose(var, g["var"], rtol=1e-4, atol=2e-6)
+        for got, ref in zip([losses["total_loss"], losses["reconstruction"], losses["kl_term"]], g["loss"]):
+            assert abs(got - ref) < 1e-5 * abs(ref)
+    for k, v in g.items():
+        if not k.startswith("grad/"):
+            continue
+        got = grads[k[len("grad/"):]]
+        rel = np.linalg.norm(got - v) / (np.linalg.norm(v) + 1e-30)
+        assert rel < 1e-3, f"{k}: relative error {rel}"  # fp32 reference vs fp64 oracle noise floor is ~4e-4
+
+
+def test_known_answers_from_survey():
+    """loss and gradient norms of the reference (CPU fp32) for the mini models."""
+    g = _load("weatherbert_mini_b8.npz")
+    assert int(g["mask"].sum()) == 13435
+    state = {k[len("param/"):]: v for k, v in g.items() if k.startswith("param/")}
+    losses, _, grads = O.train_step_grads(state, 4, "weatherbert", g["weather"], g["coords"], g["year"], g["interval"], g["mask"])
+    assert abs(losses["total_loss"] - 1.33503056) < 2e-5
+    assert abs(np.linalg.norm(grads["in_proj.weight"]) - 0.08772561) < 5e-6
+    assert abs(np.linalg.norm(grads["out_proj.weight"]) - 0.65765929) < 1e-5
+    g = _load("weatherformer_mini_b8.npz")
+    state = {k[len("param/"):]: v for k, v in g.items() if k.startswith("param/")}
+    losses, _, grads = O.train_step_grads(state, 4, "weatherformer", g["weather"], g["coords"], g["year"], g["interval"],
+                                          g["mask"], beta=0.5)
+    assert abs(losses["total_loss"] - 1.75079405) < 2e-5
+    assert abs(losses["reconstruction"] - 1.66437364) < 2e-5
+    assert abs(losses["kl_term"] - 0.08642045) < 2e-6
+    assert abs(np.linalg.norm(grads["in_proj.weight"]) - 0.07980558) < 5e-6
+    assert abs(np.linalg.norm(grads["out_proj.weight"]) - 0.70168072) < 1e-5
+
+
+def test_adam_matches_reference_step():
+    g = _load("weatherbert_mini_b8.npz")
+    for name in ["in_proj.weight", "out_proj.bias"]:
+        p0, gr = g["param/" + name], g["grad/" + name]
+        p1, _, _ = O.adam_step(p0, gr, np.zeros_like(p0), np.zeros_like(p0), 1, 5e-4)
+        assert np.allclose(p1, g["adam/" + name], rtol=1e-6, atol=1e-9)
+
+
+def test_schedules_sizes_and_pe():
+    g = _load("schedules.npz")
+    for nm, warm, total, decay in [("exp", 10.0, 100, 0.99), ("cos", 5, 50, None), ("nowarm", 0, 20, 0.9)]:
+        lrs = np.array([5e-4 * O.lr_lambda(e, warm, total, decay) for e in range(total)])
+        assert np.allclose(lrs, g[nm], rtol=1e-12, atol=0)
+    assert g["exp"][0] == 0.0  # lr is 0 during epoch 0 when warm-up > 0
+    assert np.allclose(O.positional_encoding(365, 48), g["pe_mini"], rtol=0, atol=5e-5)  # fp32 sin/exp differ by ulps between numpy and torch
+    assert [O.n_masked_features_schedule(e, 10) for e in (None, 0, 4, 5, 37, 99)] == [10, 10, 10, 12, 24, 25]
+    with pytest.raises(ValueError):
+        O.get_model_params("huge")
+    assert int(g["params_weatherformer_large"][0]) == 31966334 and int(g["params_weatherbert_mini"][0]) == 59743
+
+
+def test_years_and_normalisation():
+    idx = np.array([0.0, 1.0], dtype=np.float32)
+    yrs = O.years_from_index(idx, np.array([7.0, 7.0], dtype=np.float32), 365)
+    assert yrs.dtype == np.float32 and yrs[0, 0] == 1984.0
+    assert abs(float(yrs[1, 364]) - (1984 + ((365 + 364) * 7) / 365)) < 1e-3 and yrs.max() < 2002.0
+    y, i, c = O.normalize_year_interval_coords(yrs.astype(np.float64), np.array([[7.0], [7.0]]), np.array([[36.0, -90.0], [10.0, 20.0]]))
+    assert np.allclose(c, [[0.1, -0.5], [10 / 360, 20 / 180]]) and np.allclose(i, 7 / 30) and np.allclose(y[0, 0], 0.14)
