@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- pretrain sequences/sec of the WeatherModel hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload large|medium|small|mini] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One step = mask -> forward -> loss -> backward -> (bucketed NCCL gradient all-reduce) -> Adam on one
+synthetic batch of 365-day x 31-feature sequences, dropout 0.1 live as in the reference. Default workload:
+WeatherFormer large (D=576, H=16, L=8), beta-KL ELBO, 512 sequences per GPU (BASELINE.json configs[3], weak
+scaling). Rank 0 prints ONE JSON line. `--impl reference` times the reference's CPU PyTorch path (torch-CPU
+port in oracle/torch_port.py; the reference is pure Python over torch and cannot be installed) on the host
+cores with a bounded batch of the same model.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model kind, size, per-GPU batch, reference CPU sample batch)
+    "large": ("weatherformer", "large", 512, 4),
+    "medium": ("weatherbert", "medium", 256, 8),
+    "small": ("weatherformer", "small", 128, 16),
+    "mini": ("weatherbert", "mini", 64, 64),
+}
+SIZES = {"mini": (4, 2, 12), "small": (10, 4, 20), "medium": (12, 6, 28), "large": (16, 8, 36)}
+S, F = 365, 31
+
+
+def train_flops_per_seq(size, out):
+    h, l, f = SIZES[size]
+    d = h * f
+    return 3 * S * (l * (24 * d * d + 4 * S * d) + 2 * 34 * d + 2 * d * out)
+
+
+def size_params(size):
+    h, l, f = SIZES[size]
+    return {"num_heads": h, "num_layers": l, "hidden_dim_factor": f}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port
+
+    kind, size, _, ref_batch = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    times, loss = torch_port.time_port_steps(kind, size_params(size), ref_batch, args.steps, args.warmup, threads)
+    sec = sum(times) / len(times)
+    value = ref_batch / sec
+    line = {
+        "impl": "reference", "metric": "pretrain sequences/sec (365d x 31 feat)", "value": value, "unit": "sequences/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{kind}-{size} pretraining step (reference CPU PyTorch path, dropout 0.1 on)",
+                   "sample": f"{ref_batch} sequences per step", "seq_len": S, "features": F},
+        "cpu_baseline": {"value": value, "unit": "sequences/s", "cores": threads, "kind": "port",
+                         "sample": f"{kind}-{size}, {ref_batch} sequences/step, {args.steps} steps, torch {torch.__version__} CPU fp32"},
+        "e2e": {"value": value, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "loss": loss,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from weathermodel_b200 import engine, ops
+    from weathermodel_b200._lib import lib
+    from weathermodel_b200.data_parallel import BucketedDataParallel
+    from weathermodel_b200.optim import FusedAdam
+    from weathermodel_b200.pretraining.models.weatherbert import WeatherBERT
+    from weathermodel_b200.pretraining.models.weatherformer import WeatherFormer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA sm_100a device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    kind, size, B, ref_batch = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    torch.manual_seed(1234)
+    cls = WeatherFormer if kind == "weatherformer" else WeatherBERT
+    model = cls(weather_dim=F, output_dim=F, device=dev, **size_params(size)).to(dev).train()
+    net = model
+    if world > 1:
+        model = BucketedDataParallel(model)
+    opt = FusedAdam(model.parameters(), lr=5e-4, runtime=net.runtime)
+
+    # synthetic data: a ring of host batches in pinned memory + device-resident copies
+    g = torch.Generator().manual_seed(rank)
+    n_ring = 2
+    host = []
+    for _ in range(n_ring):
+        w = torch.randn(B, S, F, generator=g).pin_memory()
+        c = torch.stack([torch.rand(B, generator=g) * 120 - 60, torch.rand(B, generator=g) * 360 - 180], 1).pin_memory()
+        idx = torch.randint(0, 2, (B,), generator=g).float()
+        y = (1984.0 + ((idx[:, None] * 365 + torch.arange(S, dtype=torch.float32)[None]) * 7.0) / 365).pin_memory()
+        iv = torch.full((B, 1), 7.0).pin_memory()
+        host.append((w, c, y, iv))
+    resident = [tuple(t.to(dev) for t in hb) for hb in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    torch.cuda.manual_seed(1234 + rank)
+
+    def step(batch):
+        w, c, y, iv = batch
+        if kind == "weatherformer":
+            mask = ops.mask_former(S, F, B, 10, device=dev)
+        else:
+            mask = ops.mask_bert(S, F, B, 0.15, device=dev)
+        opt.zero_grad()
+        y_pad = net.forward_raw(w, c, y, iv, mask)
+        if kind == "weatherformer":
+            loss = engine.former_elbo(y_pad, w, mask, 0.5)["total_loss"]
+        else:
+            loss = engine.bert_masked_mse(y_pad, w, mask)
+        loss.backward()
+        if world > 1:
+            model.finish_gradient_sync()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, from_host):
+        barrier()
+        l0 = lib().wm_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        last = None
+        ev0.record()
+        for i in range(n_steps):
+            if from_host:
+                batch = tuple(t.to(dev, non_blocking=True) for t in host[i % n_ring])
+                last = step(batch).item()  # device -> host read of the step's loss
+            else:
+                last = step(resident[i % n_ring])
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        launches = lib().wm_launch_count() - l0
+        return t.item(), launches, (last if from_host else last.item())
+
+    for i in range(args.warmup):
+        step(resident[i % n_ring])
+    with ClockSampler(local_rank) as clocks:
+        ms_total, launches, loss_val = timed(args.steps, from_host=False)
+        ms_e2e, _, loss_e2e = timed(args.steps, from_host=True)
+    code = ops.device_error()
+    if code:
+        raise SystemExit(f"device-side mbarrier timeout (site {code}) during the benchmark: numbers invalid")
+
+    pk = peaks()
+    seqs = B * world * args.steps
+    value = seqs / (ms_total * 1e-3)
+    e2e = seqs / (ms_e2e * 1e-3)
+    flops_seq = train_flops_per_seq(size, 62 if kind == "weatherformer" else 31)
+
+    # ---- roofline of the dominant kernel (gemm_tn: FFN linear1 shape), timed alone with CUDA events
+    roof = None
+    also = {}
+    if rank == 0:
+        h, l, f = SIZES[size]
+        D, FF, M = h * f, 4 * h * f, B * S
+        a = (torch.randn(M, D, device=dev) * 0.5).to(torch.bfloat16)
+        bmat = (torch.randn(FF, D, device=dev) * D ** -0.5).to(torch.bfloat16)
+        bias = torch.zeros(FF, device=dev)
+        for _ in range(3):
+            ops.gemm_tn(a, bmat, bias=bias, relu=True)
+        reps = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            ops.gemm_tn(a, bmat, bias=bias, relu=True)
+        e1.record()
+        torch.cuda.synchronize()
+        gemm_ms = e0.elapsed_time(e1) / reps
+        achieved = 2.0 * M * FF * D / (gemm_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tn_kernel<bf16> (linear1: M x 4D x D, bias+ReLU epilogue)",
+                "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
+                "traffic": None, "peak_source": pk["source"] + " burst (kernel timed alone)",
+                "launch_ms": gemm_ms, "shape": [M, FF, D]}
+        also["step_tensor_frac_of_sustained"] = (value / world) * flops_seq / (pk["tf_sustained"] * 1e12)
+        also["algorithmic_gflop_per_seq"] = flops_seq / 1e9
+        del a, bmat
+
+    # ---- CPU baseline (rank 0, N == 1 only): reference CPU PyTorch path, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import torch_port
+
+        threads = os.cpu_count() or 1
+        times, _ = torch_port.time_port_steps(kind, size_params(size), ref_batch, 2, 1, threads)
+        sec = sum(times) / len(times)
+        cpu = {"value": ref_batch / sec, "unit": "sequences/s", "cores": threads, "kind": "port",
+               "sample": f"{kind}-{size}, {ref_batch} sequences/step x 2 steps (+1 warm-up), torch CPU fp32, dropout on"}
+
+    if rank == 0:
+        line = {
+            "metric": "pretrain sequences/sec (365d x 31 feat)", "value": value, "unit": "sequences/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{kind}-{size} pretraining step, {B} sequences/GPU, seq 365 x 31 features, "
+                                   f"dropout 0.1, {'beta-KL ELBO' if kind == 'weatherformer' else 'masked MSE'}, Adam",
+                       "global_batch": B * world, "seq_len": S, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (activations) >> 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "loss": loss_val, "loss_e2e": loss_e2e,
+        }
+        line.update(also)
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,8 @@ const char* wm_strerror(int code);
 /* Reads and clears the device-side error word (non-zero = a bounded mbarrier wait timed out inside a
  * tcgen05 kernel; the code identifies the wait site). Synchronises the device. */
 int wm_device_error(void);
+/* number of kernels this library has launched so far in this process (host-side counter) */
+long long wm_launch_count(void);
 /* torch.rand grid size for `numel` elements on the current device
  * (torch:include/ATen/native/cuda/DistributionTemplates.h:50-63 calc_execution_policy). */
 int wm_rand_grid_x(int64_t numel);

@@ -1,0 +1,232 @@
+"""Whole-path parity on a real B200, through the drop-in classes (which bind the C ABI via ctypes):
+WeatherBERT / WeatherFormer forward + fused loss + backward + FusedAdam against
+  (1) the committed golden vectors produced by the unmodified reference (tests/golden, oracle/make_golden.py)
+  (2) the numpy oracle (oracle/wm_oracle.py) on freshly seeded inputs at a second size.
+
+Tolerances (north_star: losses and gradients within 1e-3 relative with fp32 accumulation; the product path
+keeps activations and GEMM operands in bf16, 2^-9 per rounding):
+  loss            |got - ref| / |ref| <= 1e-3
+  gradient norms  | ||g|| - ||g_ref|| | / ||g_ref|| <= 5e-3 per parameter tensor, 1e-3 for the global norm
+  gradient field  ||g - g_ref||_F / ||g_ref||_F <= 3e-2 per tensor (bf16 operand rounding noise, unbiased)
+  outputs         ||y - y_ref||_F / ||y_ref||_F <= 1e-2
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import wm_oracle as O  # noqa: E402
+
+from src.pretraining.models.weatherbert import WeatherBERT  # noqa: E402
+from src.pretraining.models.weatherformer import WeatherFormer  # noqa: E402
+from weathermodel_b200 import engine  # noqa: E402
+from weathermodel_b200.optim import FusedAdam  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+DEV = "cuda"
+
+
+def _neutralise_dropout(model):
+    for m in model.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, nn.MultiheadAttention):
+            m.dropout = 0.0
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def _check_grads(model, ref_grads, tag):
+    tot_g, tot_r = 0.0, 0.0
+    worst = (0.0, "")
+    for name, p in model.named_parameters():
+        assert p.grad is not None, f"{tag}: {name} has no gradient"
+        g = p.grad.detach().float().cpu().numpy().astype(np.float64)
+        r = np.asarray(ref_grads[name], dtype=np.float64)
+        assert np.isfinite(g).all(), f"{tag}: {name} gradient not finite"
+        ng, nr = np.linalg.norm(g), np.linalg.norm(r)
+        tot_g += ng ** 2
+        tot_r += nr ** 2
+        assert abs(ng - nr) <= 5e-3 * nr + 1e-9, f"{tag}: ||grad {name}|| {ng:.6g} vs {nr:.6g}"
+        rel = _rel(g, r)
+        worst = max(worst, (rel, name))
+        assert rel <= 3e-2, f"{tag}: grad {name} rel fro err {rel:.4g}"
+    assert abs(np.sqrt(tot_g) - np.sqrt(tot_r)) <= 1e-3 * np.sqrt(tot_r), f"{tag}: global grad norm"
+    return worst
+
+
+def _load_golden(fname, cls):
+    g = dict(np.load(os.path.join(GOLD, fname)))
+    torch.manual_seed(1234)
+    model = cls(weather_dim=31, output_dim=31, device=torch.device(DEV), **O.get_model_params("mini")).to(DEV)
+    state = {k[len("param/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param/")}
+    # our constructor consumes the RNG exactly like the reference: same initial weights bit for bit
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), state[k]), f"initial weight {k} differs from the reference's for seed 1234"
+    model.load_state_dict(state)
+    model.train()
+    _neutralise_dropout(model)
+    t = lambda k, dt=torch.float32: torch.from_numpy(g[k]).to(DEV).to(dt)  # noqa: E731
+    batch = (t("weather"), t("coords"), t("year"), t("interval"), torch.from_numpy(g["mask"]).to(DEV))
+    grads = {k[len("grad/"):]: v for k, v in g.items() if k.startswith("grad/")}
+    return g, model, batch, grads
+
+
+def test_weatherbert_matches_reference_golden():
+    g, model, (w, c, yr, iv, mask), ref_grads = _load_golden("weatherbert_mini_b8.npz", WeatherBERT)
+    y_pad = model.forward_raw(w, c, yr, iv, mask)
+    loss = engine.bert_masked_mse(y_pad, w, mask)
+    loss.backward()
+    assert _rel(y_pad[..., :31].detach().cpu().numpy(), g["y"]) <= 1e-2
+    assert abs(loss.item() - g["loss"][0]) <= 1e-3 * abs(g["loss"][0]), (loss.item(), g["loss"][0])
+    worst = _check_grads(model, ref_grads, "bert")
+    print("bert mini: loss", loss.item(), "ref", g["loss"][0], "worst grad rel", worst)
+    # the public forward (sliced view) gives the same numbers and supports autograd through torch ops
+    model.zero_grad()
+    out = model(w, c, yr, iv, weather_feature_mask=mask)
+    assert out.shape == (8, 365, 31)
+    loss2 = nn.functional.mse_loss(w[mask], out[mask])
+    loss2.backward()
+    assert abs(loss2.item() - loss.item()) <= 1e-5 * abs(loss.item())
+    _check_grads(model, ref_grads, "bert/torch-loss")
+
+
+def test_weatherformer_matches_reference_golden():
+    g, model, (w, c, yr, iv, mask), ref_grads = _load_golden("weatherformer_mini_b8.npz", WeatherFormer)
+    mask = mask[:, :1, :].expand(-1, 365, -1)  # stride-0 feature mask, as the reference loader produces
+    mu, var = model(w, c, yr, iv, weather_feature_mask=mask)
+    assert _rel(mu.detach().cpu().numpy(), g["mu"]) <= 1e-2
+    assert _rel(var.detach().cpu().numpy(), g["var"]) <= 1e-2
+    losses = engine.former_elbo(mu._wm_raw, w, mask, float(g["beta"][0]))
+    losses["total_loss"].backward()
+    for key, ref in zip(("total_loss", "reconstruction", "kl_term"), g["loss"]):
+        assert abs(losses[key].item() - ref) <= 1e-3 * abs(ref), (key, losses[key].item(), ref)
+    worst = _check_grads(model, ref_grads, "former")
+    print("former mini: losses", {k: v.item() for k, v in losses.items()}, "ref", g["loss"], "worst", worst)
+
+
+@pytest.mark.parametrize("kind,size,B,S", [("weatherformer", "small", 3, 365), ("weatherbert", "medium", 2, 364),
+                                           ("weatherformer", "large", 2, 365)])
+def test_model_matches_numpy_oracle(kind, size, B, S):
+    torch.manual_seed(7)
+    cls = WeatherBERT if kind == "weatherbert" else WeatherFormer
+    hp = O.get_model_params(size)
+    model = cls(weather_dim=31, output_dim=31, device=torch.device(DEV), **hp).to(DEV).train()
+    _neutralise_dropout(model)
+    with torch.no_grad():  # de-generate the all-equal layers and zero biases a little
+        for p in model.parameters():
+            p.add_(torch.randn_like(p) * 0.02)
+    state = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    weather, coords, year, interval = O.synthetic_batch(B, S, seed=3)
+    rs = np.random.RandomState(5)
+    if kind == "weatherbert":
+        mask = rs.rand(B, S, 31) < 0.3
+    else:
+        mask = np.ascontiguousarray(O.weatherformer_mask(rs.rand(B, 31).astype(np.float32), 10, S))
+    losses_ref, y_ref, grads_ref = O.train_step_grads(state, hp["num_heads"], kind, weather, coords, year, interval,
+                                                      mask, beta=0.5)
+    tw, tc, ty, ti = (torch.from_numpy(a).to(DEV) for a in (weather, coords, year, interval))
+    tm = torch.from_numpy(mask).to(DEV)
+    y_pad = model.forward_raw(tw, tc, ty, ti, tm)
+    if kind == "weatherbert":
+        losses = {"total_loss": engine.bert_masked_mse(y_pad, tw, tm)}
+    else:
+        losses = engine.former_elbo(y_pad, tw, tm, 0.5)
+    losses["total_loss"].backward()
+    assert _rel(y_pad[..., : y_ref.shape[-1]].detach().cpu().numpy(), y_ref) <= 1e-2
+    for k, ref in losses_ref.items():
+        assert abs(losses[k].item() - ref) <= 1e-3 * abs(ref), (k, losses[k].item(), ref)
+    worst = _check_grads(model, grads_ref, f"{kind}-{size}")
+    print(kind, size, "loss", losses["total_loss"].item(), "oracle", losses_ref["total_loss"], "worst grad", worst)
+
+
+def test_fused_adam_training_reduces_loss_and_matches_torch_adam():
+    torch.manual_seed(11)
+    hp = O.get_model_params("mini")
+    model = WeatherFormer(31, 31, torch.device(DEV), **hp).to(DEV).train()
+    _neutralise_dropout(model)
+    weather, coords, year, interval = (torch.from_numpy(a).to(DEV) for a in O.synthetic_batch(16, 365, seed=1))
+    mask = (torch.rand(16, 31, device=DEV) < 0.3).unsqueeze(1).expand(-1, 365, -1)
+    opt = FusedAdam(model.parameters(), lr=1e-3, runtime=model.runtime)
+    # shadow: torch.optim.Adam on a copy of the parameters fed the SAME gradients
+    shadow = [p.detach().clone().requires_grad_(True) for p in model.parameters()]
+    ref_opt = torch.optim.Adam(shadow, lr=1e-3)
+    first = last = None
+    for step in range(6):
+        opt.zero_grad()
+        mu, var = model(weather, coords, year, interval, weather_feature_mask=mask)
+        loss = engine.former_elbo(mu._wm_raw, weather, mask, 0.5)["total_loss"]
+        loss.backward()
+        for s, p in zip(shadow, model.parameters()):
+            s.grad = p.grad.detach().clone()
+        opt.step()
+        ref_opt.step()
+        first = loss.item() if first is None else first
+        last = loss.item()
+    assert np.isfinite(last) and last < first, (first, last)
+    for s, (n, p) in zip(shadow, model.named_parameters()):
+        assert torch.allclose(p.detach(), s.detach(), rtol=1e-5, atol=1e-7), f"FusedAdam diverged from torch Adam on {n}"
+    sd = opt.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 6.0
+
+
+def test_dropout_training_mode_runs_and_is_replayable():
+    torch.manual_seed(3)
+    model = WeatherBERT(31, 31, torch.device(DEV), **O.get_model_params("small")).to(DEV).train()
+    weather, coords, year, interval = (torch.from_numpy(a).to(DEV) for a in O.synthetic_batch(4, 365, seed=2))
+    mask = torch.rand(4, 365, 31, device=DEV) < 0.15
+    rt = model.runtime
+    assert abs(rt.dropout_p - 0.1) < 1e-9
+    y1 = model.forward_raw(weather, coords, year, interval, mask)
+    l1 = engine.bert_masked_mse(y1, weather, mask)
+    l1.backward()
+    g1 = model.in_proj.weight.grad.clone()
+    rt.step_counter -= 1  # replay the same dropout stream
+    model.zero_grad()
+    y2 = model.forward_raw(weather, coords, year, interval, mask)
+    engine.bert_masked_mse(y2, weather, mask).backward()
+    assert torch.equal(y1, y2) and torch.equal(g1, model.in_proj.weight.grad)
+    y3 = model.forward_raw(weather, coords, year, interval, mask)  # next step: different masks
+    assert not torch.equal(y1, y3)
+    model.eval()
+    with torch.no_grad():
+        e1 = model(weather, coords, year, interval, weather_feature_mask=mask)
+        e2 = model(weather, coords, year, interval, weather_feature_mask=mask)
+    assert torch.equal(e1, e2) and torch.isfinite(e1).all()
+
+
+def test_checkpoint_roundtrip_and_load_pretrained(tmp_path):
+    torch.manual_seed(5)
+    hp = O.get_model_params("mini")
+    bert = WeatherBERT(31, 31, torch.device(DEV), **hp).to(DEV)
+    weather, coords, year, interval = (torch.from_numpy(a).to(DEV) for a in O.synthetic_batch(2, 365, seed=4))
+    mask = torch.rand(2, 365, 31, device=DEV) < 0.15
+    bert.eval()
+    with torch.no_grad():
+        ref = bert(weather, coords, year, interval, weather_feature_mask=mask)
+    path = tmp_path / "weatherbert_59.7k_latest.pth"
+    torch.save(bert, path)  # whole pickled module, as BaseTrainer.save_checkpoint does
+    again = torch.load(path, weights_only=False).to(DEV).eval()
+    assert type(again).__module__.endswith("pretraining.models.weatherbert")
+    with torch.no_grad():
+        assert torch.equal(again(weather, coords, year, interval, weather_feature_mask=mask), ref)
+    former = WeatherFormer(31, 31, torch.device(DEV), **hp).to(DEV).eval()
+    former.load_pretrained(again)  # BERT -> Former keeps Former's own wider head
+    assert former.out_proj.out_features == 62
+    assert torch.equal(former.in_proj.weight, again.in_proj.weight)
+    with torch.no_grad():
+        mu, var = former(weather, coords, year, interval, weather_feature_mask=mask)
+    assert mu.shape == (2, 365, 31) and (var > 0).all() and (var <= 1).all()
+    with pytest.raises(ValueError):
+        WeatherBERT(30, 30, torch.device(DEV), **hp).to(DEV).load_pretrained(again)

@@ -38,6 +38,8 @@ int wm_device_error(void) {
   return static_cast<int>(v);
 }
 
+long long wm_launch_count(void) { return g_wm_launches; }
+
 int wm_rand_grid_x(int64_t numel) {
   int dev = 0, sms = 0, tpm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;

@@ -490,6 +490,7 @@ static int launch_fwd_t(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse
     return WM_ERR_CUDA;
   attn_fwd_kernel<DHP><<<B * H, kAttThreads, smem, stream>>>(qkv, ctx, lse, S, H, dh, scale, thresh8, dscale, seed,
                                                              stream_id);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 template <int DHP>
@@ -501,6 +502,7 @@ static int launch_bwd_t(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, cons
     return WM_ERR_CUDA;
   attn_bwd_kernel<DHP><<<B * H, kAttThreads, smem, stream>>>(qkv, ctx, dctx, lse, dqkv, S, H, dh, scale, thresh8,
                                                              dscale, seed, stream_id);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 

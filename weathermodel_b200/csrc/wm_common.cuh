@@ -20,6 +20,10 @@ namespace wm {
 // (the library is built as ONE translation unit -- wm_lib.cu -- so this is the single definition)
 __device__ unsigned int g_wm_dev_error = 0;
 
+// host-side count of kernel launches issued by this library (bench.py reports it as gpu_launches)
+static long long g_wm_launches = 0;
+#define WM_COUNT_LAUNCH() (++::wm::g_wm_launches)
+
 #define WM_DEVICE __device__ __forceinline__
 
 WM_DEVICE uint32_t smem_u32(const void* p) {

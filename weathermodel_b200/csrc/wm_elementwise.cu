@@ -59,6 +59,7 @@ int launch_mask_bert(uint64_t seed, uint64_t philox_offset, int grid_x, float p,
   if (numel <= 0) return WM_OK;
   if (grid_x <= 0 || (philox_offset & 3)) return WM_ERR_ARG;
   mask_bert_kernel<<<grid_x, 256, 0, stream>>>(seed, philox_offset / 4, p, numel, mask, rand_out);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
@@ -87,6 +88,7 @@ int launch_mask_former(uint64_t seed, uint64_t philox_offset, int grid_x, int n_
   const int blocks = static_cast<int>((n_samples + 7) / 8);
   mask_former_kernel<<<blocks, 256, 0, stream>>>(seed, philox_offset / 4, static_cast<int64_t>(grid_x) * 256,
                                                   n_masked, n_samples, n_features, mask);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
@@ -184,6 +186,7 @@ int launch_embed_fwd(const float* weather, const uint8_t* mask, int64_t msb, int
   const int blocks = static_cast<int>((M + kEmbTok - 1) / kEmbTok);
   embed_fwd_kernel<<<blocks, 256, smem, stream>>>(weather, mask, msb, mss, year, coords, w_in, b_in, pe, out,
                                                   xin, B, S, F, D);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
@@ -270,6 +273,7 @@ int launch_layernorm_fwd(const __nv_bfloat16* x, const float* gamma, const float
                          float* mean, float* rstd, int M, int D, float eps, cudaStream_t stream) {
   if (M <= 0 || D <= 0 || (D & 7) || D > kLnMaxChunks * 256) return WM_ERR_SHAPE;
   layernorm_fwd_kernel<<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, mean, rstd, M, D, eps);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
@@ -406,8 +410,10 @@ int launch_layernorm_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const 
     return WM_ERR_CUDA;
   layernorm_bwd_kernel<<<ctas, 256, smem, stream>>>(dy, x, gamma, mean, rstd, dx, dx_drop, M, D, drop_thresh,
                                                     drop_scale, seed, stream_id, workspace);
+  WM_COUNT_LAUNCH();
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
   ln_bwd_finalize_kernel<<<(3 * D + 255) / 256, 256, 0, stream>>>(workspace, ctas, D, dgamma, dbeta, dbias);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
@@ -468,8 +474,10 @@ int launch_colsum(const __nv_bfloat16* x, int ld, int M, int N, float* out, floa
   const int slabs = colsum_slabs(M, N);
   dim3 grid((N / 8 + 31) / 32, slabs);
   colsum_kernel<<<grid, 256, 0, stream>>>(x, ld, M, N, workspace);
+  WM_COUNT_LAUNCH();
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
   colsum_finalize_kernel<<<(N + 255) / 256, 256, 0, stream>>>(workspace, slabs, N, out);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
@@ -561,8 +569,10 @@ int launch_loss_bert(const float* y, int ldy, const float* weather, const uint8_
   int ctas = static_cast<int>((M * F + 255) / 256);
   if (ctas > kLossCtas) ctas = kLossCtas;
   loss_bert_partial_kernel<<<ctas, 256, 0, stream>>>(y, ldy, weather, mask, M, F, scratch);
+  WM_COUNT_LAUNCH();
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
   loss_bert_grad_kernel<<<kLossCtas, 256, 0, stream>>>(y, ldy, weather, mask, M, F, scratch, ctas, loss_out, dy, lddy);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
@@ -665,9 +675,11 @@ int launch_loss_former(const float* y, int ldy, const float* weather, const uint
   int ctas = static_cast<int>((n + 255) / 256);
   if (ctas > kLossCtas) ctas = kLossCtas;
   loss_former_partial_kernel<<<ctas, 256, 0, stream>>>(y, ldy, weather, mask, msb, mss, B, S, F, scratch, mu_out, var_out);
+  WM_COUNT_LAUNCH();
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
   loss_former_grad_kernel<<<kLossCtas, 256, 0, stream>>>(y, ldy, weather, mask, msb, mss, B, S, F, beta, scratch,
                                                          ctas, loss_out, dy, lddy);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
@@ -706,6 +718,7 @@ int launch_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_
   adam_kernel<<<blocks, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, shadow, n, lr, beta1, beta2, eps,
                                           weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
                                           grad_scale);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
@@ -729,6 +742,7 @@ int launch_cast_transpose(const float* w, __nv_bfloat16* wt, int rows, int cols,
   if (rows <= 0 || cols <= 0 || ld_out < rows) return WM_ERR_SHAPE;
   dim3 grid((cols + 31) / 32, (rows + 31) / 32);
   cast_transpose_kernel<<<grid, 256, 0, stream>>>(w, wt, rows, cols, ld_out);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
@@ -742,6 +756,7 @@ int launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream
   int blocks = static_cast<int>((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   cast_bf16_kernel<<<blocks, 256, 0, stream>>>(src, dst, n);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 

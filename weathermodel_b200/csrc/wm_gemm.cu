@@ -289,10 +289,12 @@ static int launch_gemm_tn_impl(const void* A, int lda, const void* B, int ldb, i
     e = cudaFuncSetAttribute(gemm_tn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return WM_ERR_CUDA;
     gemm_tn_kernel<float><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, BN, stages, ep);
+    WM_COUNT_LAUNCH();
   } else {
     e = cudaFuncSetAttribute(gemm_tn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return WM_ERR_CUDA;
     gemm_tn_kernel<__nv_bfloat16><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, BN, stages, ep);
+    WM_COUNT_LAUNCH();
   }
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
@@ -488,12 +490,14 @@ static int launch_gemm_wgrad_impl(const void* A, int lda, const void* B, int ldb
     return WM_ERR_CUDA;
   dim3 grid((Nout + kBM - 1) / kBM, (Kout + BN - 1) / BN, splits);
   gemm_wgrad_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, Mtok, Nout, Kout, BN, tps, workspace);
+  WM_COUNT_LAUNCH();
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
   const int64_t n = static_cast<int64_t>(rows_valid) * cols_valid;
   const int threads = 256;
   const int blocks = static_cast<int>((n + threads - 1) / threads);
   wgrad_reduce_kernel<<<blocks, threads, 0, stream>>>(workspace, dW, Nout, Kout, rows_valid, cols_valid, ld_dw,
                                                       splits, accumulate);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 int launch_gemm_wgrad(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout, float* dW,
@@ -583,6 +587,7 @@ int launch_umma_probe(const void* A, const void* B, float* D, int N, int K, int 
     return WM_ERR_CUDA;
   umma_probe_kernel<<<1, 128, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(A),
                                               reinterpret_cast<const __nv_bfloat16*>(B), D, N, K, a_mn, b_mn);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 

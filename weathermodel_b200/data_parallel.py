@@ -1,0 +1,80 @@
+"""BucketedDataParallel: the data-parallel wrapper that replaces torch DDP for this path
+(reference: src/base_trainer/base_trainer.py:311-315).
+
+Semantics kept from DDP: parameters broadcast from rank 0 at wrap time, gradients AVERAGED over ranks
+(of per-rank mean losses -- not re-normalised globally), `.module` gives the wrapped model.
+Mechanism: the encoder's backward publishes gradients straight into one flat fp32 buffer; as soon as the
+kernels producing a bucket (one or more encoder layers, top first) are enqueued, that slice is all-reduced
+with NCCL on its own stream (async_op) while the next layers' backward kernels run; all handles are waited
+once before the optimiser step. No per-parameter hooks, no gradient copies.
+"""
+from typing import List
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+class BucketedDataParallel(nn.Module):
+    def __init__(self, module: nn.Module, process_group=None, bucket_cap_mb: float = 25.0):
+        super().__init__()
+        self.module = module
+        self.process_group = process_group
+        self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self._pending: List = []
+        self._runtimes = [m.runtime for m in module.modules() if hasattr(m, "runtime")]
+        if not self._runtimes:
+            raise ValueError("BucketedDataParallel wraps models built on weathermodel_b200's encoder")
+        dev = next(module.parameters()).device
+        for rt in self._runtimes:
+            rt.ensure_flat(dev)
+            # bucket = as many whole layers as fit the cap (DDP default 25 MiB)
+            per_layer = (rt.offsets[14] - rt.offsets[2]) * 4 if len(rt.offsets) > 14 else rt.flat_params.numel() * 4
+            rt.layers_per_bucket = max(1, int(bucket_cap_mb * 2 ** 20 // max(1, per_layer)))
+            rt.grad_ready_hook = self._make_hook(rt)
+        self._broadcast_parameters()
+        self._backend = dist.get_backend(process_group) if dist.is_initialized() else "none"
+
+    def _broadcast_parameters(self):
+        if self.world_size == 1:
+            return
+        for rt in self._runtimes:
+            dist.broadcast(rt.flat_params, src=0, group=self.process_group)
+            rt.mark_weights_dirty()
+        flat_ids = {id(p) for rt in self._runtimes for _, p in rt._named}
+        for p in self.module.parameters():
+            if id(p) not in flat_ids:
+                dist.broadcast(p.data, src=0, group=self.process_group)
+        for b in self.module.buffers():
+            dist.broadcast(b, src=0, group=self.process_group)
+
+    def _make_hook(self, rt):
+        def hook(lo: int, hi: int):
+            if self.world_size == 1:
+                return
+            sl = rt.flat_grads[lo:hi]
+            if self._backend == "nccl":
+                work = dist.all_reduce(sl, op=dist.ReduceOp.AVG, group=self.process_group, async_op=True)
+                self._pending.append((work, None))
+            else:
+                work = dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=self.process_group, async_op=True)
+                self._pending.append((work, sl))
+        return hook
+
+    def finish_gradient_sync(self):
+        """Join every in-flight bucket all-reduce (stream-level wait; no host sync on NCCL) and average
+        parameters that live outside the flat buckets."""
+        for work, sl in self._pending:
+            work.wait()
+            if sl is not None:
+                sl.div_(self.world_size)
+        self._pending.clear()
+        if self.world_size > 1:
+            flat_ids = {id(p) for rt in self._runtimes for _, p in rt._named}
+            for p in self.module.parameters():
+                if id(p) not in flat_ids and p.grad is not None:
+                    dist.all_reduce(p.grad, group=self.process_group)
+                    p.grad.div_(self.world_size)
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)

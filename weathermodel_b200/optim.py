@@ -1,0 +1,100 @@
+"""FusedAdam: torch.optim.Adam semantics (the optimiser the reference builds at
+src/base_trainer/base_trainer.py:337) as ONE kernel launch over the flat parameter bucket of an
+EncoderRuntime, plus a per-tensor launch for any parameter that lives outside it (e.g. yield heads).
+
+state_dict()/load_state_dict() keep torch.optim.Adam's format: per-parameter `step`, `exp_avg`,
+`exp_avg_sq` (views into flat state buffers here), so reference checkpoints resume and vice versa.
+"""
+from typing import Optional
+
+import torch
+
+from . import ops
+from .engine import EncoderRuntime
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 runtime: Optional[EncoderRuntime] = None):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        if len(self.param_groups) != 1:
+            raise ValueError("FusedAdam supports a single param group (the reference uses one)")
+        self.runtime = runtime
+        self._flat_m = None
+        self._flat_v = None
+        self._step = 0
+
+    # ---- flat state bound to the runtime's flat parameter buffer ------------------------------------
+    def _bind_flat_state(self):
+        rt = self.runtime
+        if rt is None or rt.flat_params is None:
+            return False
+        n = rt.flat_params.numel()
+        if self._flat_m is None or self._flat_m.numel() != n or self._flat_m.device != rt.flat_params.device:
+            self._flat_m = torch.zeros(n, dtype=torch.float32, device=rt.flat_params.device)
+            self._flat_v = torch.zeros(n, dtype=torch.float32, device=rt.flat_params.device)
+            for (_, p), off in zip(rt._named, rt.offsets):
+                st = self.state[p]
+                m = self._flat_m[off:off + p.numel()].view(p.shape)
+                v = self._flat_v[off:off + p.numel()].view(p.shape)
+                if "exp_avg" in st:  # state loaded from a checkpoint: adopt its values
+                    m.copy_(st["exp_avg"])
+                    v.copy_(st["exp_avg_sq"])
+                    self._step = max(self._step, int(st["step"]))
+                st["exp_avg"], st["exp_avg_sq"] = m, v
+                st.setdefault("step", torch.tensor(float(self._step)))
+        return True
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._flat_m = None  # re-adopt loaded tensors into flat buffers at the next step
+        self._flat_v = None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        group = self.param_groups[0]
+        lr, (b1, b2), eps, wd = group["lr"], group["betas"], group["eps"], group["weight_decay"]
+        rt = self.runtime
+        flat_ids = set()
+        if rt is not None and rt.flat_params is not None and rt.flat_params.is_cuda:
+            rt.ensure_flat(rt.flat_params.device)
+            in_flat = [p for _, p in rt._named]
+            # the flat launch is valid only if every flat parameter received its gradient as a view of
+            # the flat gradient buffer in this step (frozen / unused tensors fall back to per-tensor)
+            if all(p.grad is not None and p.grad.data_ptr() == rt.grad_view(i).data_ptr()
+                   for i, p in enumerate(in_flat)) and self._bind_flat_state():
+                self._step += 1
+                with torch.cuda.device(rt.flat_params.device):
+                    ops.adam_fused(rt.flat_params, rt.flat_grads, self._flat_m, self._flat_v, self._step, lr, b1, b2,
+                                   eps, wd)
+                rt.mark_weights_dirty()
+                for p in in_flat:
+                    self.state[p]["step"] = torch.tensor(float(self._step))
+                flat_ids = {id(p) for p in in_flat}
+        for p in group["params"]:
+            if id(p) in flat_ids or p.grad is None:
+                continue
+            st = self.state[p]
+            if "exp_avg" not in st:
+                st["step"] = torch.tensor(0.0)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["step"] += 1
+            k = int(st["step"])
+            if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous():
+                with torch.cuda.device(p.device):
+                    ops.adam_fused(p, p.grad, st["exp_avg"], st["exp_avg_sq"], k, lr, b1, b2, eps, wd)
+            else:  # host-side tensors only (never the hot path): same update in torch ops
+                g = p.grad if wd == 0 else p.grad.add(p, alpha=wd)
+                st["exp_avg"].lerp_(g, 1 - b1)
+                st["exp_avg_sq"].mul_(b2).addcmul_(g, g, value=1 - b2)
+                denom = (st["exp_avg_sq"].sqrt() / (1 - b2 ** k) ** 0.5).add_(eps)
+                p.addcdiv_(st["exp_avg"], denom, value=-lr / (1 - b1 ** k))
+            if rt is not None:
+                rt.mark_weights_dirty()
+        return loss

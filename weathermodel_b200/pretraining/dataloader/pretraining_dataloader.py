@@ -1,0 +1,147 @@
+"""Batched, on-device streaming loader behind the reference's `streaming_dataloader(...)` signature
+(src/pretraining/dataloader/pretraining_dataloader.py:304-382).
+
+Same data semantics as the reference StreamingDataset (:186-301): chunk files
+`data/nasa_power/processed/weather_dataset_weekly_{id}.pt` (TensorDataset(weather, coords, index)),
+per-rank contiguous chunk partition, year = 1984 + ((idx*365 + t) * interval) / 365 in float32, mask drawn
+for the WHOLE chunk, then `randperm` shuffle, then the `< cutoff_year` filter, then batches of
+`batch_size` that run across chunk boundaries; the RNG is consumed in the same order (mask, randperm), and
+the masks are bit-identical to the reference's torch.rand-based functions for the same generator state
+(CUDA: Philox replay kernels wm_mask_bert / wm_mask_former; CPU: torch.rand itself).
+What changed is the mechanics: no per-sample Python loop, no per-sample host sync, no per-sample collate.
+"""
+import logging
+import random
+from typing import Iterator, List, Optional, Tuple
+
+import torch
+
+from ...utils.constants import DATA_DIR, DRY_RUN, DRY_RUN_TRAIN_CHUNK_IDS, NUM_DATASET_PARTS, VALIDATION_CHUNK_IDS
+
+random.seed(1234)
+logger = logging.getLogger(__name__)
+
+
+class StreamingDataset(torch.utils.data.IterableDataset):
+    """Iterating yields BATCHES (weather [B,365,31], coords [B,2], year [B,365], interval [B,1], mask [B,365,31])."""
+
+    def __init__(self, file_paths, num_input_features=None, num_output_features=None, shuffle=False,
+                 masking_function: Optional[str] = None, masking_prob: float = 0.15, n_masked_features: int = 1,
+                 rank: int = 0, cutoff_year: float = 2002.0, batch_size: int = 1):
+        self.file_paths = list(file_paths)
+        self.num_input_features = num_input_features
+        self.num_output_features = num_output_features
+        self.shuffle = shuffle
+        self.masking_prob = masking_prob
+        self.n_masked_features = n_masked_features
+        self.rank = rank
+        self.cutoff_year = cutoff_year
+        self.batch_size = batch_size
+        self.device = f"cuda:{rank}" if torch.cuda.is_available() else "cpu"
+        table = {"weatherbert": self.weatherbert_masking_function,
+                 "weatherformer": self.weatherformer_masking_function}
+        if masking_function not in table:
+            raise ValueError(f"Masking function {masking_function} is not valid")
+        self.masking_function = table[masking_function]
+
+    # ---- masks (reference :56-84) ------------------------------------------------------------------
+    def weatherbert_masking_function(self, seq_len, n_features, batch_size):
+        if torch.device(self.device).type == "cuda":
+            from ... import ops
+            return ops.mask_bert(seq_len, n_features, batch_size, self.masking_prob, device=self.device)
+        return torch.rand(batch_size, seq_len, n_features, device=self.device) < self.masking_prob
+
+    def weatherformer_masking_function(self, seq_len, n_features, batch_size):
+        if torch.device(self.device).type == "cuda":
+            from ... import ops
+            return ops.mask_former(seq_len, n_features, batch_size, self.n_masked_features, device=self.device)
+        order = torch.argsort(torch.rand(batch_size, n_features, device=self.device), dim=-1)
+        return (order < self.n_masked_features).unsqueeze(1).expand(-1, seq_len, -1)
+
+    # ---- chunk -> tensors -------------------------------------------------------------------------
+    def _load_chunk(self, path) -> Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+        data = torch.load(path, weights_only=False, map_location=self.device)
+        if hasattr(data, "tensors"):
+            weather, coords, index = data.tensors[:3]
+        else:
+            if len(data) == 0:
+                return None
+            weather = torch.stack([s[0] for s in data])
+            coords = torch.stack([s[1] for s in data])
+            index = torch.stack([s[2] for s in data])
+        if weather.shape[0] == 0:
+            return None
+        return weather.to(self.device).float(), coords.to(self.device).float(), index.to(self.device).float()
+
+    def _chunk_samples(self, path):
+        loaded = self._load_chunk(path)
+        if loaded is None:
+            return None
+        weather, coords, index = loaded
+        n, seq_len, n_features = weather.shape
+        interval = index[:, 1:2].contiguous()
+        t = torch.arange(seq_len, dtype=torch.float32, device=self.device)
+        # same float32 op order as the reference's per-sample expression (:251-256)
+        years = 1984.0 + ((index[:, 0:1] * 365 + t) * interval) / 365
+        mask = self.masking_function(seq_len, n_features, n)
+        if self.shuffle and n > 1:
+            perm = torch.randperm(n, device=self.device)
+            weather, coords, years, interval, mask = weather[perm], coords[perm], years[perm], interval[perm], mask[perm]
+        keep = years.max(dim=1).values < self.cutoff_year
+        if not bool(keep.all()):  # one host sync per chunk (the reference syncs once per sample)
+            weather, coords, years, interval, mask = weather[keep], coords[keep], years[keep], interval[keep], mask[keep]
+        return weather, coords, years, interval, mask
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, ...]]:
+        carry: Optional[List[torch.Tensor]] = None
+        n_groups = len(self.file_paths) // 3
+        for gi in range(n_groups):
+            parts = self._chunk_samples(self.file_paths[3 * gi + 1])  # the weekly file of each triple (:198)
+            if parts is not None:
+                parts = list(parts)
+                if carry is not None:
+                    parts = [torch.cat([c, p], 0) for c, p in zip(carry, parts)]
+                    carry = None
+                n = parts[0].shape[0]
+                full = (n // self.batch_size) * self.batch_size
+                for s in range(0, full, self.batch_size):
+                    yield tuple(p[s:s + self.batch_size] for p in parts)
+                if full < n:
+                    carry = [p[full:].contiguous() for p in parts]
+            if gi % 10 == 0 and self.rank == 0:
+                logger.info(f"Dataloader iterated over [{gi + 1}/{n_groups}] chunks")
+        if carry is not None and carry[0].shape[0] > 0:
+            yield tuple(carry)  # last partial batch (the reference DataLoader has drop_last=False)
+
+
+def chunk_ids_for(split: str, world_size: int = 1, rank: int = 0) -> List[int]:
+    """Chunk ids of a split after the reference's per-rank partition (:311-341)."""
+    if DRY_RUN:
+        train_ids, val_ids = DRY_RUN_TRAIN_CHUNK_IDS, VALIDATION_CHUNK_IDS[:4]
+    else:
+        train_ids, val_ids = set(range(NUM_DATASET_PARTS)).difference(VALIDATION_CHUNK_IDS), VALIDATION_CHUNK_IDS
+    ids = list(train_ids if split.lower() == "train" else val_ids)
+    if world_size > 1:
+        per_rank = len(ids) // world_size
+        ids = ids[: per_rank * world_size][rank * per_rank:(rank + 1) * per_rank]
+    return ids
+
+
+def streaming_dataloader(batch_size, split="train", shuffle=False, num_input_features=None, num_output_features=None,
+                         masking_function: Optional[str] = None, masking_prob: float = 0.15, n_masked_features: int = 1,
+                         world_size: int = 1, rank: int = 0):
+    ids = chunk_ids_for(split, world_size, rank)
+    monthly, weekly, daily = list(ids), list(ids), list(ids)
+    if shuffle:  # two draws from Python's RNG, like the reference (:349-351)
+        random.shuffle(weekly)
+        random.shuffle(daily)
+    base = DATA_DIR + "nasa_power/processed/"
+    paths: List[str] = []
+    for m, w, d in zip(monthly, weekly, daily):
+        paths += [base + f"weather_dataset_monthly_{m}.pt", base + f"weather_dataset_weekly_{w}.pt",
+                  base + f"weather_dataset_daily_{d}.pt"]
+    dataset = StreamingDataset(paths, num_input_features=num_input_features, num_output_features=num_output_features,
+                               shuffle=shuffle, masking_function=masking_function, masking_prob=masking_prob,
+                               n_masked_features=n_masked_features, rank=rank, batch_size=batch_size)
+    # batch_size=None: the dataset already yields whole on-device batches
+    return torch.utils.data.DataLoader(dataset, batch_size=None, pin_memory=False, num_workers=0)
