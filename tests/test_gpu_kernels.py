@@ -52,8 +52,8 @@ def test_umma_probe(a_mn, b_mn, N, K):
 # ------------------------------------------------------------------------------------------ gemm_tn
 @pytest.mark.parametrize("M,N,K,tile_n", [
     (128, 128, 64, 128), (300, 200, 48, 0), (1000, 576, 576, 0), (256, 1728, 576, 192), (512, 2304, 576, 256),
-    (640, 576, 2304, 0), (200, 600, 200, 0), (130, 48, 48, 0), (257, 64, 32, 0), (4096, 800, 200, 208),
-    (1024, 1344, 336, 0), (365, 336, 1344, 0), (128, 16, 64, 16), (23360, 576, 576, 0),
+    (640, 576, 2304, 0), (200, 600, 200, 0), (130, 48, 48, 0), (257, 64, 32, 0), (4096, 800, 200, 224),
+    (1024, 1344, 336, 0), (365, 336, 1344, 0), (128, 32, 64, 32), (23360, 576, 576, 0),
 ])
 def test_gemm_tn_plain(M, N, K, tile_n):
     a = _bf(M, K, seed=3)

@@ -55,129 +55,150 @@ WM_DEVICE void keep16_from_philox(uint64_t seed, uint64_t stream, uint64_t grp, 
     for (int b = 0; b < 4; ++b) keep |= (((w[i] >> (8 * b)) & 0xFFu) >= thresh8 ? 1u : 0u) << (i * 4 + b);
 }
 
+WM_DEVICE float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ------------------------------------------------------------------------------------------------
-// forward
+// forward: 12 warps. Warp w reads TMEM lane quarter w%4 (query rows) and owns key tile w/4 (128 score
+// columns) of the current 128-query tile. All scores of the tile sit in TMEM at once (384 columns), so
+// the softmax is exact two-pass (max, then exp/sum) with one MMA round trip per tile instead of one per
+// 64-key chunk; the next tile's QK^T is issued together with this tile's PV so it runs under the epilogue.
 // ------------------------------------------------------------------------------------------------
+constexpr int kFwdThreads = 384;
+
 template <int DHP>
-__global__ void __launch_bounds__(kAttThreads, 2)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse_out,
                 int S, int H, int dh, float scale, uint32_t thresh8, float drop_scale, uint64_t seed,
                 uint64_t stream_id) {
   constexpr uint32_t RS = TileGeom<DHP>::RS;
-  constexpr int KC = 64;                      // keys per score chunk
-  constexpr uint32_t RS_P = (KC / 8) * 128;   // P tile [128, 64]
+  constexpr uint32_t RS_P = (kSP / 8) * 128;  // P tile [128 q, 384 keys]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + 128 * DHP * 2;
+  uint8_t* sK = sQ + kSP * DHP * 2;
   uint8_t* sV = sK + kSP * DHP * 2;
   uint8_t* sP = sV + kSP * DHP * 2;
-  __shared__ uint64_t bar;
+  float* sMax = reinterpret_cast<float*>(sP + 128 * kSP * 2);  // [3][128]
+  float* sSum = sMax + 3 * 128;                                 // [3][128]
+  __shared__ uint64_t bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
 
   const int D = H * dh;
   const int ld = 3 * D;
   const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = warp >> 2;                 // key tile owned by this warp
+  const int row = (warp & 3) * 32 + lane;    // query row inside the tile == TMEM lane
   const __nv_bfloat16* qbase = qkv + static_cast<size_t>(b) * S * ld + h * dh;
-  const int nchunks = (S + KC - 1) / KC;
-  const int ntiles = (S + 127) / 128;
-  const int grp_per_row = (S + 15) / 16;
+  const int ntq = (S + 127) / 128;           // query tiles
+  const int ntk = ntq;                       // key tiles
+  const int nk16 = (S + 15) / 16;            // PV k-steps
+  const int grp_per_row = nk16;
 
+  load_head_tile<DHP>(sQ, qbase, ld, 0, S, kSP, dh);
   load_head_tile<DHP>(sK, qbase + D, ld, 0, S, kSP, dh);
   load_head_tile<DHP>(sV, qbase + 2 * D, ld, 0, S, kSP, dh);
   if (tid == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_o, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<128>(&tmem_slot);
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t tS = tmem, tO = tmem + KC;
-  const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-  uint32_t phase = 0;
-  const uint32_t idesc_s = umma_idesc_bf16(128, KC, 0, 0);
+  const uint32_t tS = tmem, tO = tmem + kSP;
+  const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
   const uint32_t idesc_o = umma_idesc_bf16(128, DHP, 0, 1);
   const float c2 = scale * 1.4426950408889634f;
+  const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
 
-  for (int it = 0; it < ntiles; ++it) {
-    const int q0 = it * 128;
-    const int q = q0 + tid;
-    const bool qvalid = q < S;
-    load_head_tile<DHP>(sQ, qbase, ld, q0, min(128, S - q0), 128, dh);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-
-    // ---- pass 1: row max of the raw scores -------------------------------------------------
-    float mrow = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) {
-      if (tid == 0) {
-        tc_fence_after();
+  auto issue_scores = [&](int it) {  // S[128, 128*ntk] = Q_it K^T
+    for (int jt = 0; jt < ntk; ++jt) {
 #pragma unroll
-        for (int k = 0; k < DHP / 16; ++k) {
-          const uint64_t da = umma_smem_desc(smem_u32(sQ) + k * 256, 128, RS, UMMA_SWZ_NONE);
-          const uint64_t db = umma_smem_desc(smem_u32(sK) + (c * KC / 8) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
-          umma_ss(tS, da, db, idesc_s, k != 0);
-        }
-        umma_commit(&bar);
+      for (int k = 0; k < DHP / 16; ++k) {
+        const uint64_t da = umma_smem_desc(aQ + (it * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
+        const uint64_t db = umma_smem_desc(aK + (jt * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
+        umma_ss(tS + jt * 128, da, db, idesc_s, k != 0);
       }
-      mbar_wait(&bar, phase, 41);
-      phase ^= 1u;
-      tc_fence_after();
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_sel + half * 32, v);
-        tmem_ld_wait();
-        const int kbase = c * KC + half * 32;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (kbase + j < S) mrow = fmaxf(mrow, __uint_as_float(v[j]));
-      }
-      tc_fence_before();
-      __syncthreads();
     }
-    // ---- pass 2: P = exp2((s - m) * c2), O += P V -----------------------------------------------
-    float lsum = 0.0f;
-    const float mneg = -mrow * c2;
-    for (int c = 0; c < nchunks; ++c) {
-      if (tid == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < DHP / 16; ++k) {
-          const uint64_t da = umma_smem_desc(smem_u32(sQ) + k * 256, 128, RS, UMMA_SWZ_NONE);
-          const uint64_t db = umma_smem_desc(smem_u32(sK) + (c * KC / 8) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
-          umma_ss(tS, da, db, idesc_s, k != 0);
-        }
-        umma_commit(&bar);
-      }
-      mbar_wait(&bar, phase, 42);
-      phase ^= 1u;
-      tc_fence_after();
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+    umma_commit(&bar_s);
+  };
+  if (tid == 0) issue_scores(0);
+  uint32_t ph_s = 0, ph_o = 0;
+
+  for (int it = 0; it < ntq; ++it) {
+    const int q = it * 128 + row;
+    const bool qvalid = q < S;
+    mbar_wait(&bar_s, ph_s, 41);
+    ph_s ^= 1u;
+    tc_fence_after();
+    // ---- pass 1: max over this warp's key tile
+    float mloc = -INFINITY;
+    if (grp < ntk) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        const int kbase = grp * 128 + c0;
+        if (kbase >= S) break;
         uint32_t v[32];
-        tmem_ld32(tS + lane_sel + half * 32, v);
+        tmem_ld32(tS + lane_sel + kbase, v);
         tmem_ld_wait();
-        const int kbase = c * KC + half * 32;
+        if (kbase + 32 <= S) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mloc = fmaxf(mloc, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (kbase + j < S) mloc = fmaxf(mloc, __uint_as_float(v[j]));
+        }
+      }
+    }
+    sMax[grp * 128 + row] = mloc;
+    __syncthreads();
+    const float mrow = fmaxf(fmaxf(sMax[row], sMax[128 + row]), sMax[256 + row]);
+    const float mneg = -mrow * c2;
+    // ---- pass 2: exp2, row sum, dropout, P -> smem (bf16, K-major over keys)
+    float lsum = 0.0f;
+    if (grp < ntk) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        const int kbase = grp * 128 + c0;
+        if (kbase >= nk16 * 16) break;
+        uint32_t v[32];
+        tmem_ld32(tS + lane_sel + kbase, v);
+        tmem_ld_wait();
 #pragma unroll
         for (int g16 = 0; g16 < 2; ++g16) {
+          const int k0 = kbase + g16 * 16;
+          if (k0 >= nk16 * 16) break;
           uint32_t keep = 0xFFFFu;
           if (thresh8) {
-            const uint64_t grp = (static_cast<uint64_t>(bh) * S + (qvalid ? q : 0)) * grp_per_row + ((kbase + g16 * 16) >> 4);
-            keep16_from_philox(seed, stream_id, grp, thresh8, keep);
+            const uint64_t gidx = (static_cast<uint64_t>(bh) * S + (qvalid ? q : 0)) * grp_per_row + (k0 >> 4);
+            keep16_from_philox(seed, stream_id, gidx, thresh8, keep);
           }
           float p[16];
+          if (k0 + 16 <= S) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int kk = kbase + g16 * 16 + j;
-            float e = 0.0f;
-            if (kk < S) e = exp2f(fmaf(__uint_as_float(v[g16 * 16 + j]), c2, mneg));
-            lsum += e;
-            p[j] = ((keep >> j) & 1u) ? e : 0.0f;
+            for (int j = 0; j < 16; ++j) {
+              const float e = fast_exp2(fmaf(__uint_as_float(v[g16 * 16 + j]), c2, mneg));
+              lsum += e;
+              p[j] = ((keep >> j) & 1u) ? e : 0.0f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float e = 0.0f;
+              if (k0 + j < S) e = fast_exp2(fmaf(__uint_as_float(v[g16 * 16 + j]), c2, mneg));
+              lsum += e;
+              p[j] = ((keep >> j) & 1u) ? e : 0.0f;
+            }
           }
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8) {
@@ -186,72 +207,96 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
             pk.y = pack_bf16x2(p[g8 * 8 + 2], p[g8 * 8 + 3]);
             pk.z = pack_bf16x2(p[g8 * 8 + 4], p[g8 * 8 + 5]);
             pk.w = pack_bf16x2(p[g8 * 8 + 6], p[g8 * 8 + 7]);
-            const int kc = half * 32 + g16 * 16 + g8 * 8;  // key column within the chunk
-            *reinterpret_cast<uint4*>(sP + (tid >> 3) * RS_P + (kc >> 3) * 128 + (tid & 7) * 16) = pk;
+            const int kc = k0 + g8 * 8;
+            *reinterpret_cast<uint4*>(sP + (row >> 3) * RS_P + (kc >> 3) * 128 + (row & 7) * 16) = pk;
           }
         }
       }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < KC / 16; ++k) {
-          const uint64_t da = umma_smem_desc(smem_u32(sP) + k * 256, 128, RS_P, UMMA_SWZ_NONE);
-          // V as MN-major B: mn = head dim (SBO = 128 between 8-column groups), k = key rows (LBO = RS)
-          const uint64_t db = umma_smem_desc(smem_u32(sV) + ((c * KC + k * 16) / 8) * RS, RS, 128, UMMA_SWZ_NONE);
-          umma_ss(tO, da, db, idesc_o, (c | k) != 0);
-        }
-        umma_commit(&bar);
-      }
-      mbar_wait(&bar, phase, 43);  // P tile and S columns are free again after this
-      phase ^= 1u;
-      tc_fence_after();
     }
-    // ---- epilogue: O / sum -> ctx, LSE -------------------------------------------------------------
-    {
-      const float inv = drop_scale / lsum;
-      __nv_bfloat16* orow = ctx + (static_cast<size_t>(b) * S + (qvalid ? q : 0)) * D + h * dh;
-#pragma unroll
-      for (int c0 = 0; c0 < DHP; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tO + lane_sel + c0, v);
-        tmem_ld_wait();
-        if (qvalid) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            if (c0 + j < dh) {  // dh % 4 == 0
-              uint2 pk;
-              pk.x = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
-              pk.y = pack_bf16x2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
-              *reinterpret_cast<uint2*>(orow + c0 + j) = pk;
-            }
-          }
-        }
-      }
-      if (qvalid && lse_out) lse_out[static_cast<size_t>(bh) * S + q] = mrow * scale + logf(lsum);
-    }
+    sSum[grp * 128 + row] = lsum;
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      for (int k = 0; k < nk16; ++k) {
+        const uint64_t da = umma_smem_desc(aP + k * 256, 128, RS_P, UMMA_SWZ_NONE);
+        // V as MN-major B: mn = head dim (SBO = 128 between 8-column groups), k = key rows (LBO = RS)
+        const uint64_t db = umma_smem_desc(aV + (k * 2) * RS, RS, 128, UMMA_SWZ_NONE);
+        umma_ss(tO, da, db, idesc_o, k != 0);
+      }
+      umma_commit(&bar_o);
+      if (it + 1 < ntq) issue_scores(it + 1);  // runs while the epilogue below drains O
+    }
+    mbar_wait(&bar_o, ph_o, 43);
+    ph_o ^= 1u;
+    tc_fence_after();
+    // ---- epilogue: warp group g writes head-dim columns [16g, 16g+16)
+    if (grp * 16 < DHP) {
+      const float tot = sSum[row] + sSum[128 + row] + sSum[256 + row];
+      const float inv = drop_scale / tot;
+      uint32_t v[16];
+      tmem_ld16(tO + lane_sel + grp * 16, v);
+      tmem_ld_wait();
+      if (qvalid) {
+        __nv_bfloat16* orow = ctx + (static_cast<size_t>(b) * S + q) * D + h * dh + grp * 16;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          if (grp * 16 + j < dh) {  // dh % 4 == 0
+            uint2 pk;
+            pk.x = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+            pk.y = pack_bf16x2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+            *reinterpret_cast<uint2*>(orow + j) = pk;
+          }
+        }
+        if (grp == 0 && lse_out) lse_out[static_cast<size_t>(bh) * S + q] = mrow * scale + logf(tot);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // O drained, sMax / sSum / sP reusable
   }
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem);
+    tmem_dealloc<512>(tmem);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward
+// backward: 16 warps. Warp w reads TMEM lane quarter w%4 (query rows of tile i) and owns 32 of the 128 key
+// columns of tile j (w/4). Per (j, i): S = Q_i K_j^T and dP = dO_i V_j^T land in TMEM, the warps write
+// P and dS (bf16) to smem, then ONE thread issues dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j and
+// immediately the next pair's S / dP, with a single commit -- so the tensor pipe works through five
+// products while the warps are parked on one mbarrier, and nothing round-trips per 64-key chunk.
 // ------------------------------------------------------------------------------------------------
+constexpr int kBwdThreads = 512;
+
 template <int DHP>
-__global__ void __launch_bounds__(kAttThreads, 1)
+WM_DEVICE void store_acc_chunk(uint32_t taddr, __nv_bfloat16* dst, int c0, int dh, bool valid) {
+  uint32_t v[16];
+  tmem_ld16(taddr + c0, v);
+  tmem_ld_wait();
+  if (valid) {
+#pragma unroll
+    for (int jj = 0; jj < 16; jj += 4) {
+      if (c0 + jj < dh) {
+        uint2 pk;
+        pk.x = pack_bf16x2(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]));
+        pk.y = pack_bf16x2(__uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
+        *reinterpret_cast<uint2*>(dst + c0 + jj) = pk;
+      }
+    }
+  }
+}
+
+template <int DHP>
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ ctx,
                 const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
                 __nv_bfloat16* __restrict__ dqkv, int S, int H, int dh, float scale, uint32_t thresh8,
                 float drop_scale, uint64_t seed, uint64_t stream_id) {
   constexpr uint32_t RS = TileGeom<DHP>::RS;
   constexpr uint32_t RS_P = (128 / 8) * 128;  // P / dS tiles are [128 q, 128 keys]
+  constexpr int NCH = DHP / 16;               // 16-column chunks per accumulator
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* sQ = smem;
@@ -260,35 +305,33 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   uint8_t* sdO = sV + kSP * DHP * 2;
   uint8_t* sP = sdO + kSP * DHP * 2;
   uint8_t* sdS = sP + 128 * 128 * 2;
+  float* sLse = reinterpret_cast<float*>(sdS + 128 * 128 * 2);  // [384] (pre-multiplied by -log2 e)
+  float* sDelta = sLse + kSP;                                   // [384]
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
 
   const int D = H * dh;
   const int ld = 3 * D;
   const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = warp >> 2;               // 32-key column slice of the current key tile
+  const int row = (warp & 3) * 32 + lane;  // row inside a 128-row tile == TMEM lane
   const __nv_bfloat16* qbase = qkv + static_cast<size_t>(b) * S * ld + h * dh;
   const __nv_bfloat16* obase = ctx + static_cast<size_t>(b) * S * D + h * dh;
   const __nv_bfloat16* dobase = dctx + static_cast<size_t>(b) * S * D + h * dh;
-  const int ntiles = (S + 127) / 128;
+  const int nt = (S + 127) / 128;
   const int grp_per_row = (S + 15) / 16;
 
   load_head_tile<DHP>(sQ, qbase, ld, 0, S, kSP, dh);
   load_head_tile<DHP>(sK, qbase + D, ld, 0, S, kSP, dh);
   load_head_tile<DHP>(sV, qbase + 2 * D, ld, 0, S, kSP, dh);
   load_head_tile<DHP>(sdO, dobase, D, 0, S, kSP, dh);
-  // per-thread row statistics for the (up to) three q tiles: LSE and delta = sum_d dO * O
-  float lse_r[3], delta_r[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const int q = i * 128 + tid;
-    lse_r[i] = 0.0f;
-    delta_r[i] = 0.0f;
-    if (q < S) {
-      lse_r[i] = lse[static_cast<size_t>(bh) * S + q];
-      float acc = 0.0f;
-      const uint2* po = reinterpret_cast<const uint2*>(obase + static_cast<size_t>(q) * D);
-      const uint2* pd = reinterpret_cast<const uint2*>(dobase + static_cast<size_t>(q) * D);
+  if (tid < kSP) {  // per-row statistics: LSE (scaled to the exp2 domain) and delta = sum_d dO * O
+    float l = 0.0f, acc = 0.0f;
+    if (tid < S) {
+      l = -lse[static_cast<size_t>(bh) * S + tid] * 1.4426950408889634f;
+      const uint2* po = reinterpret_cast<const uint2*>(obase + static_cast<size_t>(tid) * D);
+      const uint2* pd = reinterpret_cast<const uint2*>(dobase + static_cast<size_t>(tid) * D);
       for (int p = 0; p < dh / 4; ++p) {
         const uint2 o = __ldg(po + p), d = __ldg(pd + p);
         acc = fmaf(bf16_lo(o.x), bf16_lo(d.x), acc);
@@ -296,8 +339,9 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
         acc = fmaf(bf16_lo(o.y), bf16_lo(d.y), acc);
         acc = fmaf(bf16_hi(o.y), bf16_hi(d.y), acc);
       }
-      delta_r[i] = acc;
     }
+    sLse[tid] = l;
+    sDelta[tid] = acc;
   }
   if (tid == 0) {
     mbar_init(&bar, 1);
@@ -310,8 +354,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 256 + DHP, tdQ = tmem + 256 + 2 * DHP;
-  const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-  uint32_t phase = 0;
+  const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
   const uint32_t idesc_kv = umma_idesc_bf16(128, DHP, 1, 1);
   const uint32_t idesc_q = umma_idesc_bf16(128, DHP, 0, 1);
@@ -319,71 +362,104 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), adO = smem_u32(sdO);
   const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
 
-  for (int j = 0; j < ntiles; ++j) {
-    for (int i = 0; i < ntiles; ++i) {
-      if (tid == 0) {
-        tc_fence_after();
+  auto issue_scores = [&](int i, int j) {  // S = Q_i K_j^T, dP = dO_i V_j^T
 #pragma unroll
-        for (int k = 0; k < DHP / 16; ++k) {
-          const uint64_t da = umma_smem_desc(aQ + (i * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
-          const uint64_t db = umma_smem_desc(aK + (j * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
-          umma_ss(tS, da, db, idesc_s, k != 0);
-        }
+    for (int k = 0; k < DHP / 16; ++k) {
+      const uint64_t da = umma_smem_desc(aQ + (i * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
+      const uint64_t db = umma_smem_desc(aK + (j * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
+      umma_ss(tS, da, db, idesc_s, k != 0);
+    }
 #pragma unroll
-        for (int k = 0; k < DHP / 16; ++k) {
-          const uint64_t da = umma_smem_desc(adO + (i * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
-          const uint64_t db = umma_smem_desc(aV + (j * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
-          umma_ss(tdP, da, db, idesc_s, k != 0);
-        }
-        umma_commit(&bar);
-      }
-      mbar_wait(&bar, phase, 51);
+    for (int k = 0; k < DHP / 16; ++k) {
+      const uint64_t da = umma_smem_desc(adO + (i * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
+      const uint64_t db = umma_smem_desc(aV + (j * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
+      umma_ss(tdP, da, db, idesc_s, k != 0);
+    }
+  };
+  auto issue_grads = [&](int i, int j) {
+#pragma unroll
+    for (int k = 0; k < 128 / 16; ++k) {
+      // contraction over the 128 query rows of tile i: P / dS read MN-major (mn = keys: SBO = 128,
+      // k = q rows: LBO = RS_P); dO / Q read MN-major (mn = head dim: SBO = 128, k = rows: LBO = RS)
+      const uint64_t dpT = umma_smem_desc(aP + (k * 2) * RS_P, RS_P, 128, UMMA_SWZ_NONE);
+      const uint64_t dsT = umma_smem_desc(adS + (k * 2) * RS_P, RS_P, 128, UMMA_SWZ_NONE);
+      const uint64_t ddo = umma_smem_desc(adO + (i * 16 + k * 2) * RS, RS, 128, UMMA_SWZ_NONE);
+      const uint64_t dq = umma_smem_desc(aQ + (i * 16 + k * 2) * RS, RS, 128, UMMA_SWZ_NONE);
+      umma_ss(tdV, dpT, ddo, idesc_kv, (i | k) != 0);
+      umma_ss(tdK, dsT, dq, idesc_kv, (i | k) != 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 128 / 16; ++k) {
+      // dQ_i += dS K_j: dS K-major over keys (LBO = 128, SBO = RS_P); K_j MN-major over key rows
+      const uint64_t da = umma_smem_desc(adS + k * 256, 128, RS_P, UMMA_SWZ_NONE);
+      const uint64_t db = umma_smem_desc(aK + (j * 16 + k * 2) * RS, RS, 128, UMMA_SWZ_NONE);
+      umma_ss(tdQ + i * DHP, da, db, idesc_q, (j | k) != 0);
+    }
+  };
+  // dK_j / dV_j out of TMEM: thread = key row; the 2*NCH 16-column chunks are dealt round-robin to the 4 groups
+  auto store_kv = [&](int j) {
+    const int kr = j * 128 + row;
+    const bool kvalid = kr < S;
+    __nv_bfloat16* drow = dqkv + (static_cast<size_t>(b) * S + (kvalid ? kr : 0)) * ld + h * dh;
+    for (int c = grp; c < 2 * NCH; c += 4) {
+      const int which = c / NCH, cc = c - which * NCH;
+      store_acc_chunk<DHP>((which == 0 ? tdK : tdV) + lane_sel, drow + (which == 0 ? D : 2 * D), cc * 16, dh, kvalid);
+    }
+  };
+
+  if (tid == 0) {
+    issue_scores(0, 0);
+    umma_commit(&bar);
+  }
+  uint32_t phase = 0;
+  for (int j = 0; j < nt; ++j) {
+    for (int i = 0; i < nt; ++i) {
+      mbar_wait(&bar, phase, 51);  // S/dP of (j, i) ready; every earlier product has completed as well
       phase ^= 1u;
       tc_fence_after();
-      const int q = i * 128 + tid;
+      if (i == 0 && j > 0) store_kv(j - 1);  // dK/dV of the previous key tile are final
+      const int q = i * 128 + row;
       const bool qvalid = q < S;
-      const float lneg = -lse_r[i] * 1.4426950408889634f;
-      const float dl = delta_r[i];
+      const float lneg = sLse[i * 128 + row];
+      const float dl = sDelta[i * 128 + row];
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t vs[32], vd[32];
-        tmem_ld32(tS + lane_sel + c0, vs);
-        tmem_ld32(tdP + lane_sel + c0, vd);
+      for (int hh = 0; hh < 2; ++hh) {
+        const int c0 = grp * 32 + hh * 16;   // column inside the key tile
+        const int k0 = j * 128 + c0;          // global key index
+        uint32_t vs[16], vd[16];
+        tmem_ld16(tS + lane_sel + c0, vs);
+        tmem_ld16(tdP + lane_sel + c0, vd);
         tmem_ld_wait();
-        const int kbase = j * 128 + c0;
+        uint32_t keep = 0xFFFFu;
+        if (thresh8) {
+          const uint64_t gidx = (static_cast<uint64_t>(bh) * S + (qvalid ? q : 0)) * grp_per_row + (k0 >> 4);
+          keep16_from_philox(seed, stream_id, gidx, thresh8, keep);
+        }
+        float pp[16], ds[16];
+        const bool full = qvalid && (k0 + 16 <= S);
 #pragma unroll
-        for (int g16 = 0; g16 < 2; ++g16) {
-          uint32_t keep = 0xFFFFu;
-          if (thresh8) {
-            const uint64_t grp = (static_cast<uint64_t>(bh) * S + (qvalid ? q : 0)) * grp_per_row + ((kbase + g16 * 16) >> 4);
-            keep16_from_philox(seed, stream_id, grp, thresh8, keep);
-          }
-          float pp[16], ds[16];
+        for (int jj = 0; jj < 16; ++jj) {
+          float p = fast_exp2(fmaf(__uint_as_float(vs[jj]), c2, lneg));
+          if (!full && !(qvalid && k0 + jj < S)) p = 0.0f;
+          const float kp = ((keep >> jj) & 1u) ? drop_scale : 0.0f;
+          pp[jj] = p * kp;
+          ds[jj] = (p * scale) * fmaf(__uint_as_float(vd[jj]), kp, -dl);
+        }
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const int kk = kbase + g16 * 16 + jj;
-            float p = 0.0f;
-            if (qvalid && kk < S) p = exp2f(fmaf(__uint_as_float(vs[g16 * 16 + jj]), c2, lneg));
-            const float kp = ((keep >> jj) & 1u) ? drop_scale : 0.0f;
-            pp[jj] = p * kp;
-            ds[jj] = p * (__uint_as_float(vd[g16 * 16 + jj]) * kp - dl) * scale;
-          }
-#pragma unroll
-          for (int g8 = 0; g8 < 2; ++g8) {
-            uint4 pk, dk;
-            pk.x = pack_bf16x2(pp[g8 * 8 + 0], pp[g8 * 8 + 1]);
-            pk.y = pack_bf16x2(pp[g8 * 8 + 2], pp[g8 * 8 + 3]);
-            pk.z = pack_bf16x2(pp[g8 * 8 + 4], pp[g8 * 8 + 5]);
-            pk.w = pack_bf16x2(pp[g8 * 8 + 6], pp[g8 * 8 + 7]);
-            dk.x = pack_bf16x2(ds[g8 * 8 + 0], ds[g8 * 8 + 1]);
-            dk.y = pack_bf16x2(ds[g8 * 8 + 2], ds[g8 * 8 + 3]);
-            dk.z = pack_bf16x2(ds[g8 * 8 + 4], ds[g8 * 8 + 5]);
-            dk.w = pack_bf16x2(ds[g8 * 8 + 6], ds[g8 * 8 + 7]);
-            const int kc = c0 + g16 * 16 + g8 * 8;
-            const uint32_t off = (tid >> 3) * RS_P + (kc >> 3) * 128 + (tid & 7) * 16;
-            *reinterpret_cast<uint4*>(sP + off) = pk;
-            *reinterpret_cast<uint4*>(sdS + off) = dk;
-          }
+        for (int g8 = 0; g8 < 2; ++g8) {
+          uint4 pk, dk;
+          pk.x = pack_bf16x2(pp[g8 * 8 + 0], pp[g8 * 8 + 1]);
+          pk.y = pack_bf16x2(pp[g8 * 8 + 2], pp[g8 * 8 + 3]);
+          pk.z = pack_bf16x2(pp[g8 * 8 + 4], pp[g8 * 8 + 5]);
+          pk.w = pack_bf16x2(pp[g8 * 8 + 6], pp[g8 * 8 + 7]);
+          dk.x = pack_bf16x2(ds[g8 * 8 + 0], ds[g8 * 8 + 1]);
+          dk.y = pack_bf16x2(ds[g8 * 8 + 2], ds[g8 * 8 + 3]);
+          dk.z = pack_bf16x2(ds[g8 * 8 + 4], ds[g8 * 8 + 5]);
+          dk.w = pack_bf16x2(ds[g8 * 8 + 6], ds[g8 * 8 + 7]);
+          const int kc = c0 + g8 * 8;
+          const uint32_t off = (row >> 3) * RS_P + (kc >> 3) * 128 + (row & 7) * 16;
+          *reinterpret_cast<uint4*>(sP + off) = pk;
+          *reinterpret_cast<uint4*>(sdS + off) = dk;
         }
       }
       fence_proxy_async_smem();
@@ -391,82 +467,23 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 128 / 16; ++k) {
-          // contraction over the 128 query rows of tile i: P / dS read MN-major (mn = keys: SBO = 128,
-          // k = q rows: LBO = RS_P); dO / Q read MN-major (mn = head dim: SBO = 128, k = rows: LBO = RS)
-          const uint64_t dpT = umma_smem_desc(aP + (k * 2) * RS_P, RS_P, 128, UMMA_SWZ_NONE);
-          const uint64_t dsT = umma_smem_desc(adS + (k * 2) * RS_P, RS_P, 128, UMMA_SWZ_NONE);
-          const uint64_t ddo = umma_smem_desc(adO + (i * 16 + k * 2) * RS, RS, 128, UMMA_SWZ_NONE);
-          const uint64_t dq = umma_smem_desc(aQ + (i * 16 + k * 2) * RS, RS, 128, UMMA_SWZ_NONE);
-          umma_ss(tdV, dpT, ddo, idesc_kv, (i | k) != 0);
-          umma_ss(tdK, dsT, dq, idesc_kv, (i | k) != 0);
-        }
-#pragma unroll
-        for (int k = 0; k < 128 / 16; ++k) {
-          // dQ_i += dS K_j: dS K-major over keys (LBO = 128, SBO = RS_P); K_j MN-major over key rows
-          const uint64_t da = umma_smem_desc(adS + k * 256, 128, RS_P, UMMA_SWZ_NONE);
-          const uint64_t db = umma_smem_desc(aK + (j * 16 + k * 2) * RS, RS, 128, UMMA_SWZ_NONE);
-          umma_ss(tdQ + i * DHP, da, db, idesc_q, (j | k) != 0);
-        }
+        issue_grads(i, j);
+        const int in = i + 1 < nt ? i + 1 : 0, jn = i + 1 < nt ? j : j + 1;
+        if (jn < nt) issue_scores(in, jn);
         umma_commit(&bar);
       }
-      mbar_wait(&bar, phase, 52);
-      phase ^= 1u;
-      tc_fence_after();
     }
-    // dK_j, dV_j complete: thread = key row
-    {
-      const int kr = j * 128 + tid;
-      const bool kvalid = kr < S;
-      __nv_bfloat16* drow = dqkv + (static_cast<size_t>(b) * S + (kvalid ? kr : 0)) * ld + h * dh;
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        const uint32_t tsrc = which == 0 ? tdK : tdV;
-        __nv_bfloat16* dst = drow + (which == 0 ? D : 2 * D);
-#pragma unroll
-        for (int c0 = 0; c0 < DHP; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(tsrc + lane_sel + c0, v);
-          tmem_ld_wait();
-          if (kvalid) {
-#pragma unroll
-            for (int jj = 0; jj < 16; jj += 4) {
-              if (c0 + jj < dh) {
-                uint2 pk;
-                pk.x = pack_bf16x2(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]));
-                pk.y = pack_bf16x2(__uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
-                *reinterpret_cast<uint2*>(dst + c0 + jj) = pk;
-              }
-            }
-          }
-        }
-      }
-    }
-    tc_fence_before();
-    __syncthreads();
   }
-  for (int i = 0; i < ntiles; ++i) {
-    const int q = i * 128 + tid;
+  mbar_wait(&bar, phase, 52);  // the last gradient products
+  phase ^= 1u;
+  tc_fence_after();
+  store_kv(nt - 1);
+  for (int c = grp; c < nt * NCH; c += 4) {  // dQ: thread = query row
+    const int i = c / NCH, cc = c - i * NCH;
+    const int q = i * 128 + row;
     const bool qvalid = q < S;
     __nv_bfloat16* dst = dqkv + (static_cast<size_t>(b) * S + (qvalid ? q : 0)) * ld + h * dh;
-#pragma unroll
-    for (int c0 = 0; c0 < DHP; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(tdQ + i * DHP + lane_sel + c0, v);
-      tmem_ld_wait();
-      if (qvalid) {
-#pragma unroll
-        for (int jj = 0; jj < 16; jj += 4) {
-          if (c0 + jj < dh) {
-            uint2 pk;
-            pk.x = pack_bf16x2(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]));
-            pk.y = pack_bf16x2(__uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
-            *reinterpret_cast<uint2*>(dst + c0 + jj) = pk;
-          }
-        }
-      }
-    }
+    store_acc_chunk<DHP>(tdQ + i * DHP + lane_sel, dst, cc * 16, dh, qvalid);
   }
   tc_fence_before();
   __syncthreads();
@@ -485,10 +502,10 @@ template <int DHP>
 static int launch_fwd_t(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, int B, int S, int H, int dh,
                         float scale, uint32_t thresh8, float dscale, uint64_t seed, uint64_t stream_id,
                         cudaStream_t stream) {
-  const int smem = 128 * DHP * 2 + 2 * kSP * DHP * 2 + 128 * 64 * 2 + 256;
+  const int smem = 3 * kSP * DHP * 2 + 128 * kSP * 2 + 6 * 128 * 4 + 256;
   if (cudaFuncSetAttribute(attn_fwd_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return WM_ERR_CUDA;
-  attn_fwd_kernel<DHP><<<B * H, kAttThreads, smem, stream>>>(qkv, ctx, lse, S, H, dh, scale, thresh8, dscale, seed,
+  attn_fwd_kernel<DHP><<<B * H, kFwdThreads, smem, stream>>>(qkv, ctx, lse, S, H, dh, scale, thresh8, dscale, seed,
                                                              stream_id);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
@@ -497,10 +514,10 @@ template <int DHP>
 static int launch_bwd_t(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __nv_bfloat16* dctx,
                         const float* lse, __nv_bfloat16* dqkv, int B, int S, int H, int dh, float scale,
                         uint32_t thresh8, float dscale, uint64_t seed, uint64_t stream_id, cudaStream_t stream) {
-  const int smem = 4 * kSP * DHP * 2 + 2 * 128 * 128 * 2 + 256;
+  const int smem = 4 * kSP * DHP * 2 + 2 * 128 * 128 * 2 + 2 * kSP * 4 + 256;
   if (cudaFuncSetAttribute(attn_bwd_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return WM_ERR_CUDA;
-  attn_bwd_kernel<DHP><<<B * H, kAttThreads, smem, stream>>>(qkv, ctx, dctx, lse, dqkv, S, H, dh, scale, thresh8,
+  attn_bwd_kernel<DHP><<<B * H, kBwdThreads, smem, stream>>>(qkv, ctx, dctx, lse, dqkv, S, H, dh, scale, thresh8,
                                                              dscale, seed, stream_id);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;

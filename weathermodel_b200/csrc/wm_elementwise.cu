@@ -214,6 +214,25 @@ WM_DEVICE void ln_load_row(const __nv_bfloat16* row, int nchunks, int lane, floa
   }
 }
 
+WM_DEVICE void ln_load_raw(const __nv_bfloat16* row, int nchunks, int lane, uint4 (&v)[kLnMaxChunks]) {
+#pragma unroll
+  for (int i = 0; i < kLnMaxChunks; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < nchunks ? __ldg(reinterpret_cast<const uint4*>(row) + c) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+WM_DEVICE void ln_unpack(const uint4 (&r)[kLnMaxChunks], float (&v)[kLnMaxChunks][8]) {
+#pragma unroll
+  for (int i = 0; i < kLnMaxChunks; ++i) {
+    const uint32_t aw[4] = {r[i].x, r[i].y, r[i].z, r[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[i][2 * j] = bf16_lo(aw[j]);
+      v[i][2 * j + 1] = bf16_hi(aw[j]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
@@ -303,11 +322,29 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     }
   }
   const float invD = 1.0f / static_cast<float>(D);
-  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+  // the next row's operands are requested before the current row is reduced, so every warp keeps two rows of
+  // loads in flight (8 warps x 2 rows x 2 tensors per SM) instead of stalling a full DRAM round trip per row
+  uint4 nx[kLnMaxChunks], nd[kLnMaxChunks];
+  float nmu = 0.0f, nrs = 0.0f;
+  const int row0 = blockIdx.x * 8 + warp;
+  if (row0 < M) {
+    ln_load_raw(x + static_cast<size_t>(row0) * D, nchunks, lane, nx);
+    ln_load_raw(dy + static_cast<size_t>(row0) * D, nchunks, lane, nd);
+    nmu = mean[row0];
+    nrs = rstd[row0];
+  }
+  for (int row = row0; row < M; row += gridDim.x * 8) {
     float xv[kLnMaxChunks][8], dv[kLnMaxChunks][8];
-    ln_load_row(x + static_cast<size_t>(row) * D, nchunks, lane, xv);
-    ln_load_row(dy + static_cast<size_t>(row) * D, nchunks, lane, dv);
-    const float mu = mean[row], rs = rstd[row];
+    ln_unpack(nx, xv);
+    ln_unpack(nd, dv);
+    const float mu = nmu, rs = nrs;
+    const int rown = row + gridDim.x * 8;
+    if (rown < M) {
+      ln_load_raw(x + static_cast<size_t>(rown) * D, nchunks, lane, nx);
+      ln_load_raw(dy + static_cast<size_t>(rown) * D, nchunks, lane, nd);
+      nmu = mean[rown];
+      nrs = rstd[rown];
+    }
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
     for (int i = 0; i < kLnMaxChunks; ++i) {

@@ -59,7 +59,8 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t c
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxStages = 8;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter)
+constexpr int kWgradThreads = 192;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccStride = 256;
 
@@ -69,30 +70,46 @@ struct GemmSmemTail {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
+  float bias[8][128];  // per epilogue warp: the bias slice of its column half of the current tile
 };
 
-template <int NC, typename OutT>
-WM_DEVICE void epilogue_chunk(uint32_t taddr, const GemmEpilogue& ep, int row, int n0, int M, int N) {
-  uint32_t v[NC];
-  if constexpr (NC == 32) {
-    tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(v));
-  } else {
-    tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(v));
+// Epilogue of one 16-column group pair for one accumulator row. Auxiliary operands (residual / gate rows)
+// arrive already loaded in registers: they are prefetched one chunk ahead so their L2 latency overlaps the
+// TMEM load and the math of the previous chunk (the first version of this epilogue stalled ~25k cycles per
+// tile on dependent global loads: profiles/r01_gemm_v1_stalls.txt).
+struct EpiAux {
+  uint4 res[2];
+  uint4 gate[2];
+};
+
+WM_DEVICE void epi_load_aux(EpiAux& a, const GemmEpilogue& ep, int row, int n0, int M, int N) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int n = n0 + g * 8;
+    const bool ok = row < M && n < N;
+    a.res[g] = make_uint4(0u, 0u, 0u, 0u);
+    a.gate[g] = make_uint4(0u, 0u, 0u, 0u);
+    if (ok && ep.residual)
+      a.res[g] = __ldg(reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(row) * ep.ld_res + n));
+    if (ok && ep.gate)
+      a.gate[g] = __ldg(reinterpret_cast<const uint4*>(ep.gate + static_cast<size_t>(row) * ep.ld_gate + n));
   }
-  tmem_ld_wait();
+}
+
+template <typename OutT>
+WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const float* sbias, const GemmEpilogue& ep,
+                             int row, int n0, int M, int N) {
   if (row >= M) return;
 #pragma unroll
-  for (int g = 0; g < NC / 8; ++g) {
+  for (int g = 0; g < 2; ++g) {
     const int n = n0 + g * 8;
-    if (n >= N) break;  // N is a multiple of 8 at every call site (checked on the host)
+    if (n >= N) break;  // N % 8 == 0 (host-checked)
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
     if (ep.bias) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
-      f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-      f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += sbias[g * 8 + j];
     }
     if (ep.relu) {
 #pragma unroll
@@ -104,9 +121,8 @@ WM_DEVICE void epilogue_chunk(uint32_t taddr, const GemmEpilogue& ep, int row, i
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1u) ? f[j] * ep.drop_scale : 0.0f;
     }
-    if (ep.gate) {  // multiplicative ReLU/dropout gate for dgrad through dropout(relu(.)): aux > 0
-      const uint4 a = __ldg(reinterpret_cast<const uint4*>(ep.gate + static_cast<size_t>(row) * ep.ld_gate + n));
-      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+    if (ep.gate) {  // dgrad through dropout(relu(.)): pass where the saved activation is > 0
+      const uint32_t aw[4] = {aux.gate[g].x, aux.gate[g].y, aux.gate[g].z, aux.gate[g].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         f[2 * j] = bf16_lo(aw[j]) > 0.0f ? f[2 * j] * ep.gate_scale : 0.0f;
@@ -114,8 +130,7 @@ WM_DEVICE void epilogue_chunk(uint32_t taddr, const GemmEpilogue& ep, int row, i
       }
     }
     if (ep.residual) {
-      const uint4 a = __ldg(reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(row) * ep.ld_res + n));
-      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+      const uint32_t aw[4] = {aux.res[g].x, aux.res[g].y, aux.res[g].z, aux.res[g].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         f[2 * j] += bf16_lo(aw[j]);
@@ -165,7 +180,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tail->acc_full[s], 1);
-      mbar_init(&tail->acc_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tail->acc_empty[s], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -221,20 +236,37 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int q = warp & 3;          // TMEM lane quarter this warp may read
+    const int ew = warp - 2;         // 0..7
+    const int half = ew >> 2;        // which half of the tile's columns this warp owns
+    const int cols_per = BN >> 1;    // BN % 32 == 0 (host-checked)
+    float* sbias = tail->bias[ew];
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int m_blk = t / n_tiles, n_blk = t % n_tiles;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1u;
+      const int row = m_blk * kBM + q * 32 + lane;
+      const int n_base = n_blk * BN + half * cols_per;
+      // everything that does not depend on the accumulator is issued before waiting for the MMAs
+      if (ep.bias) {
+        __syncwarp();
+        for (int j = lane; j < cols_per; j += 32) sbias[j] = (n_base + j < N) ? __ldg(ep.bias + n_base + j) : 0.0f;
+        __syncwarp();
+      }
+      EpiAux aux_cur, aux_next;
+      epi_load_aux(aux_cur, ep, row, n_base, M, N);
       mbar_wait(&tail->acc_full[as], aph, 14);
       tc_fence_after();
-      const int row = m_blk * kBM + q * 32 + lane;
-      const uint32_t tbase = tmem_base + as * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-      int c0 = 0;
-      for (; c0 + 32 <= BN; c0 += 32)
-        epilogue_chunk<32, OutT>(tbase + c0, ep, row, n_blk * BN + c0, M, N);
-      if (c0 < BN) epilogue_chunk<16, OutT>(tbase + c0, ep, row, n_blk * BN + c0, M, N);
+      const uint32_t tbase = tmem_base + as * kAccStride + half * cols_per + (static_cast<uint32_t>(q * 32) << 16);
+      for (int c0 = 0; c0 < cols_per; c0 += 16) {
+        if (c0 + 16 < cols_per) epi_load_aux(aux_next, ep, row, n_base + c0 + 16, M, N);
+        uint32_t v[16];
+        tmem_ld16(tbase + c0, v);
+        tmem_ld_wait();
+        epi_process16<OutT>(v, aux_cur, sbias + c0, ep, row, n_base + c0, M, N);
+        aux_cur = aux_next;
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->acc_empty[as]);
@@ -248,12 +280,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// tile width: multiples of 32 up to 256; minimise tiles * (bn + ~32 columns of per-tile overhead), then the
+// padded column count, then prefer the wider tile
 static int pick_bn(int N) {
-  const int nt = (N + 255) / 256;
-  int bn = (N + nt - 1) / nt;
-  bn = (bn + 15) / 16 * 16;
-  if (bn < 16) bn = 16;
-  return bn;
+  int best = 32;
+  long best_cost = -1, best_pad = 0;
+  for (int bn = 32; bn <= 256; bn += 32) {
+    const long tiles = (N + bn - 1) / bn;
+    const long cost = tiles * (bn + 32), pad = tiles * bn;
+    if (best_cost < 0 || cost < best_cost || (cost == best_cost && pad < best_pad) ||
+        (cost == best_cost && pad == best_pad && bn > best)) {
+      best = bn;
+      best_cost = cost;
+      best_pad = pad;
+    }
+  }
+  return best;
 }
 
 static int g_num_sms = 0;
@@ -272,7 +314,7 @@ static int launch_gemm_tn_impl(const void* A, int lda, const void* B, int ldb, i
   if (M <= 0 || N <= 0 || K <= 0 || b_rows <= 0 || b_rows > N) return WM_ERR_SHAPE;
   if ((N & 7) || (K & 7) || (lda & 7) || (ldb & 7) || (ep.ld_out & 7)) return WM_ERR_ALIGN;
   const int BN = bn_override > 0 ? bn_override : pick_bn(N);
-  if (BN & 15 || BN > 256) return WM_ERR_SHAPE;
+  if (BN & 31 || BN > 256 || BN < 32) return WM_ERR_SHAPE;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16(&tmA, A, M, K, lda, kBK, kBM);
   if (rc) return rc;
@@ -320,7 +362,7 @@ struct WgSmemTail {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kWgradThreads, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   int Mtok, int Nout, int Kout, int BN, int tok_per_split, float* __restrict__ partial) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -489,7 +531,7 @@ static int launch_gemm_wgrad_impl(const void* A, int lda, const void* B, int ldb
   if (cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return WM_ERR_CUDA;
   dim3 grid((Nout + kBM - 1) / kBM, (Kout + BN - 1) / BN, splits);
-  gemm_wgrad_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, Mtok, Nout, Kout, BN, tps, workspace);
+  gemm_wgrad_kernel<<<grid, kWgradThreads, smem, stream>>>(tmA, tmB, Mtok, Nout, Kout, BN, tps, workspace);
   WM_COUNT_LAUNCH();
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
   const int64_t n = static_cast<int64_t>(rows_valid) * cols_valid;
