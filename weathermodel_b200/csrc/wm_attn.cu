@@ -29,6 +29,16 @@ struct TileGeom {
 
 // copy rows [0, S) of one head slice (row pitch ld elements, dh valid columns) into a canonical tile of
 // `rows_alloc` rows, zero-filling pad columns and pad rows.
+// Asynchronous (LDGSTS) 8-byte pieces: every thread queues all of its pieces back to back and the
+// caller waits once (cp_async_wait_all) -- the first version used ld.global + st.shared per piece and paid one
+// DRAM round trip per loop iteration (~36 per thread), which was most of the kernel time.
+WM_DEVICE void cp_async8(void* smem_dst, const void* gmem_src, bool valid) {
+  const uint32_t d = smem_u32(smem_dst);
+  const int sz = valid ? 8 : 0;  // src-size 0 => destination is zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
+}
+WM_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 template <int DHP>
 WM_DEVICE void load_head_tile(uint8_t* tile, const __nv_bfloat16* __restrict__ src, int ld, int row0, int nrows_valid,
                               int rows_alloc, int dh) {
@@ -37,11 +47,10 @@ WM_DEVICE void load_head_tile(uint8_t* tile, const __nv_bfloat16* __restrict__ s
   const int pv = dh / 4;
   for (int i = threadIdx.x; i < rows_alloc * PP; i += blockDim.x) {
     const int r = i / PP, p = i - r * PP;
-    uint2 val = make_uint2(0u, 0u);
-    if (r < nrows_valid && p < pv)
-      val = __ldg(reinterpret_cast<const uint2*>(src + static_cast<size_t>(row0 + r) * ld) + p);
+    const bool valid = r < nrows_valid && p < pv;
+    const __nv_bfloat16* g = valid ? src + static_cast<size_t>(row0 + r) * ld + p * 4 : src;
     const int d = p * 4;
-    *reinterpret_cast<uint2*>(tile + (r >> 3) * RS + (d >> 3) * 128 + (r & 7) * 16 + (d & 7) * 2) = val;
+    cp_async8(tile + (r >> 3) * RS + (d >> 3) * 128 + (r & 7) * 16 + (d & 7) * 2, g, valid);
   }
 }
 
@@ -102,6 +111,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   load_head_tile<DHP>(sQ, qbase, ld, 0, S, kSP, dh);
   load_head_tile<DHP>(sK, qbase + D, ld, 0, S, kSP, dh);
   load_head_tile<DHP>(sV, qbase + 2 * D, ld, 0, S, kSP, dh);
+  cp_async_wait_all();
   if (tid == 0) {
     mbar_init(&bar_s, 1);
     mbar_init(&bar_o, 1);
@@ -332,17 +342,25 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
       l = -lse[static_cast<size_t>(bh) * S + tid] * 1.4426950408889634f;
       const uint2* po = reinterpret_cast<const uint2*>(obase + static_cast<size_t>(tid) * D);
       const uint2* pd = reinterpret_cast<const uint2*>(dobase + static_cast<size_t>(tid) * D);
-      for (int p = 0; p < dh / 4; ++p) {
-        const uint2 o = __ldg(po + p), d = __ldg(pd + p);
-        acc = fmaf(bf16_lo(o.x), bf16_lo(d.x), acc);
-        acc = fmaf(bf16_hi(o.x), bf16_hi(d.x), acc);
-        acc = fmaf(bf16_lo(o.y), bf16_lo(d.y), acc);
-        acc = fmaf(bf16_hi(o.y), bf16_hi(d.y), acc);
+      uint2 o[DHP / 4], d[DHP / 4];
+#pragma unroll
+      for (int p = 0; p < DHP / 4; ++p) {  // all loads in flight at once
+        const bool ok = p < dh / 4;
+        o[p] = ok ? __ldg(po + p) : make_uint2(0u, 0u);
+        d[p] = ok ? __ldg(pd + p) : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int p = 0; p < DHP / 4; ++p) {
+        acc = fmaf(bf16_lo(o[p].x), bf16_lo(d[p].x), acc);
+        acc = fmaf(bf16_hi(o[p].x), bf16_hi(d[p].x), acc);
+        acc = fmaf(bf16_lo(o[p].y), bf16_lo(d[p].y), acc);
+        acc = fmaf(bf16_hi(o[p].y), bf16_hi(d[p].y), acc);
       }
     }
     sLse[tid] = l;
     sDelta[tid] = acc;
   }
+  cp_async_wait_all();
   if (tid == 0) {
     mbar_init(&bar, 1);
     fence_barrier_init();

@@ -78,21 +78,17 @@ struct GemmSmemTail {
 // TMEM load and the math of the previous chunk (the first version of this epilogue stalled ~25k cycles per
 // tile on dependent global loads: profiles/r01_gemm_v1_stalls.txt).
 struct EpiAux {
-  uint4 res[2];
-  uint4 gate[2];
+  uint4 a[2];  // the prefetched operand of a 16-column chunk: the gate rows if a gate is given, else the residual rows
 };
 
-WM_DEVICE void epi_load_aux(EpiAux& a, const GemmEpilogue& ep, int row, int n0, int M, int N) {
+WM_DEVICE void epi_load_aux(EpiAux& x, const GemmEpilogue& ep, int row, int n0, int M, int N) {
+  const __nv_bfloat16* base = ep.gate ? ep.gate : ep.residual;
+  const int ldx = ep.gate ? ep.ld_gate : ep.ld_res;
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     const int n = n0 + g * 8;
-    const bool ok = row < M && n < N;
-    a.res[g] = make_uint4(0u, 0u, 0u, 0u);
-    a.gate[g] = make_uint4(0u, 0u, 0u, 0u);
-    if (ok && ep.residual)
-      a.res[g] = __ldg(reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(row) * ep.ld_res + n));
-    if (ok && ep.gate)
-      a.gate[g] = __ldg(reinterpret_cast<const uint4*>(ep.gate + static_cast<size_t>(row) * ep.ld_gate + n));
+    x.a[g] = make_uint4(0u, 0u, 0u, 0u);
+    if (base && row < M && n < N) x.a[g] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(row) * ldx + n));
   }
 }
 
@@ -122,7 +118,7 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
       for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1u) ? f[j] * ep.drop_scale : 0.0f;
     }
     if (ep.gate) {  // dgrad through dropout(relu(.)): pass where the saved activation is > 0
-      const uint32_t aw[4] = {aux.gate[g].x, aux.gate[g].y, aux.gate[g].z, aux.gate[g].w};
+      const uint32_t aw[4] = {aux.a[g].x, aux.a[g].y, aux.a[g].z, aux.a[g].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         f[2 * j] = bf16_lo(aw[j]) > 0.0f ? f[2 * j] * ep.gate_scale : 0.0f;
@@ -130,7 +126,10 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
       }
     }
     if (ep.residual) {
-      const uint32_t aw[4] = {aux.res[g].x, aux.res[g].y, aux.res[g].z, aux.res[g].w};
+      uint4 rr = aux.a[g];
+      if (ep.gate)  // both operands given (not on the training schedule): the residual is loaded in place
+        rr = __ldg(reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(row) * ep.ld_res + n));
+      const uint32_t aw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         f[2 * j] += bf16_lo(aw[j]);
@@ -254,18 +253,27 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = lane; j < cols_per; j += 32) sbias[j] = (n_base + j < N) ? __ldg(ep.bias + n_base + j) : 0.0f;
         __syncwarp();
       }
-      EpiAux aux_cur, aux_next;
-      epi_load_aux(aux_cur, ep, row, n_base, M, N);
+      // ring of kAuxDepth prefetched 16-column chunks per thread: ~32 KB of residual / gate rows in flight per SM
+      constexpr int kAuxDepth = 4;
+      EpiAux aux[kAuxDepth];
+#pragma unroll
+      for (int d = 0; d < kAuxDepth; ++d)
+        if (d * 16 < cols_per) epi_load_aux(aux[d], ep, row, n_base + d * 16, M, N);
       mbar_wait(&tail->acc_full[as], aph, 14);
       tc_fence_after();
       const uint32_t tbase = tmem_base + as * kAccStride + half * cols_per + (static_cast<uint32_t>(q * 32) << 16);
-      for (int c0 = 0; c0 < cols_per; c0 += 16) {
-        if (c0 + 16 < cols_per) epi_load_aux(aux_next, ep, row, n_base + c0 + 16, M, N);
-        uint32_t v[16];
-        tmem_ld16(tbase + c0, v);
-        tmem_ld_wait();
-        epi_process16<OutT>(v, aux_cur, sbias + c0, ep, row, n_base + c0, M, N);
-        aux_cur = aux_next;
+      for (int cb = 0; cb < cols_per; cb += 16 * kAuxDepth) {
+#pragma unroll
+        for (int d = 0; d < kAuxDepth; ++d) {
+          const int c0 = cb + d * 16;
+          if (c0 < cols_per) {
+            uint32_t v[16];
+            tmem_ld16(tbase + c0, v);
+            tmem_ld_wait();
+            epi_process16<OutT>(v, aux[d], sbias + c0, ep, row, n_base + c0, M, N);
+            if (c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
