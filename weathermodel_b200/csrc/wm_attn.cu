@@ -54,15 +54,19 @@ WM_DEVICE void load_head_tile(uint8_t* tile, const __nv_bfloat16* __restrict__ s
   }
 }
 
-WM_DEVICE void keep16_from_philox(uint64_t seed, uint64_t stream, uint64_t grp, uint32_t thresh8, uint32_t& keep) {
-  const Philox4 r = philox4x32_10(seed, stream, grp);
-  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-  keep = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) keep |= (((w[i] >> (8 * b)) & 0xFFu) >= thresh8 ? 1u : 0u) << (i * 4 + b);
+// Dropout on attention probabilities: one Philox4x32-7 block (the 7-round variant is the Crush-resistant
+// minimum of the Random123 paper; nothing here has to match torch's stream) decides 16 consecutive keys of one
+// query row, 8 bits each: keep iff byte >= thresh8. m[w] holds 0xFF in every kept byte of word w.
+constexpr int kAttnPhiloxRounds = 7;
+WM_DEVICE void keep_masks16(uint64_t seed, uint64_t stream, uint64_t grp, uint32_t thresh4, uint32_t (&m)[4]) {
+  const Philox4 r = philox4x32<kAttnPhiloxRounds>(seed, stream, grp);
+  m[0] = __vcmpgeu4(r.x, thresh4);
+  m[1] = __vcmpgeu4(r.y, thresh4);
+  m[2] = __vcmpgeu4(r.z, thresh4);
+  m[3] = __vcmpgeu4(r.w, thresh4);
 }
+// all-ones / all-zeros 32-bit mask of element j (0..15) of the group
+#define WM_KEEP32(m, j) __byte_perm((m)[(j) >> 2], 0u, 0x1111u * ((j) & 3))
 
 WM_DEVICE float fast_exp2(float x) {
   float y;
@@ -73,12 +77,12 @@ WM_DEVICE float fast_exp2(float x) {
 // ------------------------------------------------------------------------------------------------
 // forward: 12 warps. Warp w reads TMEM lane quarter w%4 (query rows) and owns key tile w/4 (128 score
 // columns) of the current 128-query tile. All scores of the tile sit in TMEM at once (384 columns), so
-// the softmax is exact two-pass (max, then exp/sum) with one MMA round trip per tile instead of one per
-// 64-key chunk; the next tile's QK^T is issued together with this tile's PV so it runs under the epilogue.
+// the softmax is exact two-pass (max, then exp/sum) with one MMA round trip per tile; two issuing threads
+// (PV of this tile, QK^T of the next) keep descriptor arithmetic off the critical path.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFwdThreads = 384;
 
-template <int DHP>
+template <int DHP, bool DROP>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse_out,
                 int S, int H, int dh, float scale, uint32_t thresh8, float drop_scale, uint64_t seed,
@@ -103,10 +107,9 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   const int grp = warp >> 2;                 // key tile owned by this warp
   const int row = (warp & 3) * 32 + lane;    // query row inside the tile == TMEM lane
   const __nv_bfloat16* qbase = qkv + static_cast<size_t>(b) * S * ld + h * dh;
-  const int ntq = (S + 127) / 128;           // query tiles
-  const int ntk = ntq;                       // key tiles
-  const int nk16 = (S + 15) / 16;            // PV k-steps
-  const int grp_per_row = nk16;
+  const int ntq = (S + 127) / 128;           // query tiles == key tiles
+  const int nk16 = (S + 15) / 16;            // PV k-steps / dropout groups per row
+  const uint32_t thresh4 = thresh8 * 0x01010101u;
 
   load_head_tile<DHP>(sQ, qbase, ld, 0, S, kSP, dh);
   load_head_tile<DHP>(sK, qbase + D, ld, 0, S, kSP, dh);
@@ -128,20 +131,23 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
   const uint32_t idesc_o = umma_idesc_bf16(128, DHP, 0, 1);
   const float c2 = scale * 1.4426950408889634f;
-  const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+  const bool issuer_o = tid == 0, issuer_s = tid == 128;
+  const uint64_t dQ0 = umma_smem_desc(smem_u32(sQ), 128, RS, UMMA_SWZ_NONE);
+  const uint64_t dK0 = umma_smem_desc(smem_u32(sK), 128, RS, UMMA_SWZ_NONE);
+  const uint64_t dP0 = umma_smem_desc(smem_u32(sP), 128, RS_P, UMMA_SWZ_NONE);
+  // V as MN-major B: mn = head dim (SBO = 128 between 8-column groups), k = key rows (LBO = RS)
+  const uint64_t dV0 = umma_smem_desc(smem_u32(sV), RS, 128, UMMA_SWZ_NONE);
 
-  auto issue_scores = [&](int it) {  // S[128, 128*ntk] = Q_it K^T
-    for (int jt = 0; jt < ntk; ++jt) {
+  auto issue_scores = [&](int it) {  // S[128, 128*ntq] = Q_it K^T
+    for (int jt = 0; jt < ntq; ++jt) {
 #pragma unroll
-      for (int k = 0; k < DHP / 16; ++k) {
-        const uint64_t da = umma_smem_desc(aQ + (it * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
-        const uint64_t db = umma_smem_desc(aK + (jt * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
-        umma_ss(tS + jt * 128, da, db, idesc_s, k != 0);
-      }
+      for (int k = 0; k < DHP / 16; ++k)
+        umma_ss(tS + jt * 128, umma_desc_advance(dQ0, (it * 16) * RS + k * 256),
+                umma_desc_advance(dK0, (jt * 16) * RS + k * 256), idesc_s, k != 0);
     }
     umma_commit(&bar_s);
   };
-  if (tid == 0) issue_scores(0);
+  if (issuer_s) issue_scores(0);
   uint32_t ph_s = 0, ph_o = 0;
 
   for (int it = 0; it < ntq; ++it) {
@@ -152,7 +158,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     tc_fence_after();
     // ---- pass 1: max over this warp's key tile
     float mloc = -INFINITY;
-    if (grp < ntk) {
+    if (grp < ntq) {
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         const int kbase = grp * 128 + c0;
@@ -176,50 +182,42 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     const float mneg = -mrow * c2;
     // ---- pass 2: exp2, row sum, dropout, P -> smem (bf16, K-major over keys)
     float lsum = 0.0f;
-    if (grp < ntk) {
+    if (grp < ntq) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        const int kbase = grp * 128 + c0;
-        if (kbase >= nk16 * 16) break;
-        uint32_t v[32];
-        tmem_ld32(tS + lane_sel + kbase, v);
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        const int k0 = grp * 128 + c0;
+        if (k0 >= nk16 * 16) break;
+        uint32_t v[16];
+        tmem_ld16(tS + lane_sel + k0, v);
         tmem_ld_wait();
+        uint32_t km[4];
+        if (DROP) keep_masks16(seed, stream_id, (static_cast<uint64_t>(bh) * S + (qvalid ? q : 0)) * nk16 + (k0 >> 4), thresh4, km);
+        uint32_t pb[16];  // P as fp32 bit patterns (masked by the keep decision)
+        if (k0 + 16 <= S) {
 #pragma unroll
-        for (int g16 = 0; g16 < 2; ++g16) {
-          const int k0 = kbase + g16 * 16;
-          if (k0 >= nk16 * 16) break;
-          uint32_t keep = 0xFFFFu;
-          if (thresh8) {
-            const uint64_t gidx = (static_cast<uint64_t>(bh) * S + (qvalid ? q : 0)) * grp_per_row + (k0 >> 4);
-            keep16_from_philox(seed, stream_id, gidx, thresh8, keep);
+          for (int j = 0; j < 16; ++j) {
+            const float e = fast_exp2(fmaf(__uint_as_float(v[j]), c2, mneg));
+            lsum += e;
+            pb[j] = DROP ? (__float_as_uint(e) & WM_KEEP32(km, j)) : __float_as_uint(e);
           }
-          float p[16];
-          if (k0 + 16 <= S) {
+        } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float e = fast_exp2(fmaf(__uint_as_float(v[g16 * 16 + j]), c2, mneg));
-              lsum += e;
-              p[j] = ((keep >> j) & 1u) ? e : 0.0f;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float e = 0.0f;
-              if (k0 + j < S) e = fast_exp2(fmaf(__uint_as_float(v[g16 * 16 + j]), c2, mneg));
-              lsum += e;
-              p[j] = ((keep >> j) & 1u) ? e : 0.0f;
-            }
+          for (int j = 0; j < 16; ++j) {
+            float e = 0.0f;
+            if (k0 + j < S) e = fast_exp2(fmaf(__uint_as_float(v[j]), c2, mneg));
+            lsum += e;
+            pb[j] = DROP ? (__float_as_uint(e) & WM_KEEP32(km, j)) : __float_as_uint(e);
           }
+        }
 #pragma unroll
-          for (int g8 = 0; g8 < 2; ++g8) {
-            uint4 pk;
-            pk.x = pack_bf16x2(p[g8 * 8 + 0], p[g8 * 8 + 1]);
-            pk.y = pack_bf16x2(p[g8 * 8 + 2], p[g8 * 8 + 3]);
-            pk.z = pack_bf16x2(p[g8 * 8 + 4], p[g8 * 8 + 5]);
-            pk.w = pack_bf16x2(p[g8 * 8 + 6], p[g8 * 8 + 7]);
-            const int kc = k0 + g8 * 8;
-            *reinterpret_cast<uint4*>(sP + (row >> 3) * RS_P + (kc >> 3) * 128 + (row & 7) * 16) = pk;
-          }
+        for (int g8 = 0; g8 < 2; ++g8) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(pb[g8 * 8 + 0]), __uint_as_float(pb[g8 * 8 + 1]));
+          pk.y = pack_bf16x2(__uint_as_float(pb[g8 * 8 + 2]), __uint_as_float(pb[g8 * 8 + 3]));
+          pk.z = pack_bf16x2(__uint_as_float(pb[g8 * 8 + 4]), __uint_as_float(pb[g8 * 8 + 5]));
+          pk.w = pack_bf16x2(__uint_as_float(pb[g8 * 8 + 6]), __uint_as_float(pb[g8 * 8 + 7]));
+          const int kc = k0 + g8 * 8;
+          *reinterpret_cast<uint4*>(sP + (row >> 3) * RS_P + (kc >> 3) * 128 + (row & 7) * 16) = pk;
         }
       }
     }
@@ -227,16 +225,15 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (issuer_o) {
       tc_fence_after();
-      for (int k = 0; k < nk16; ++k) {
-        const uint64_t da = umma_smem_desc(aP + k * 256, 128, RS_P, UMMA_SWZ_NONE);
-        // V as MN-major B: mn = head dim (SBO = 128 between 8-column groups), k = key rows (LBO = RS)
-        const uint64_t db = umma_smem_desc(aV + (k * 2) * RS, RS, 128, UMMA_SWZ_NONE);
-        umma_ss(tO, da, db, idesc_o, k != 0);
-      }
+      for (int k = 0; k < nk16; ++k)
+        umma_ss(tO, umma_desc_advance(dP0, k * 256), umma_desc_advance(dV0, (k * 2) * RS), idesc_o, k != 0);
       umma_commit(&bar_o);
-      if (it + 1 < ntq) issue_scores(it + 1);  // runs while the epilogue below drains O
+    }
+    if (issuer_s && it + 1 < ntq) {  // scores of the next tile run under this tile's PV and epilogue
+      tc_fence_after();
+      issue_scores(it + 1);
     }
     mbar_wait(&bar_o, ph_o, 43);
     ph_o ^= 1u;
@@ -274,9 +271,10 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
 // ------------------------------------------------------------------------------------------------
 // backward: 16 warps. Warp w reads TMEM lane quarter w%4 (query rows of tile i) and owns 32 of the 128 key
 // columns of tile j (w/4). Per (j, i): S = Q_i K_j^T and dP = dO_i V_j^T land in TMEM, the warps write
-// P and dS (bf16) to smem, then ONE thread issues dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j and
-// immediately the next pair's S / dP, with a single commit -- so the tensor pipe works through five
-// products while the warps are parked on one mbarrier, and nothing round-trips per 64-key chunk.
+// P and dS (bf16) to smem, then THREE threads issue in parallel {dV_j += P^T dO_i, dK_j += dS^T Q_i},
+// {dQ_i += dS K_j} and {next pair's S, dP}; each commits to the same 3-arrival mbarrier.
+// No validity masks are needed: padded query / key rows are zero in every staged tile, so whatever P and dS
+// hold there is multiplied by zero rows or lands in rows that are never stored.
 // ------------------------------------------------------------------------------------------------
 constexpr int kBwdThreads = 512;
 
@@ -298,7 +296,7 @@ WM_DEVICE void store_acc_chunk(uint32_t taddr, __nv_bfloat16* dst, int c0, int d
   }
 }
 
-template <int DHP>
+template <int DHP, bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ ctx,
                 const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
@@ -315,8 +313,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   uint8_t* sdO = sV + kSP * DHP * 2;
   uint8_t* sP = sdO + kSP * DHP * 2;
   uint8_t* sdS = sP + 128 * 128 * 2;
-  float* sLse = reinterpret_cast<float*>(sdS + 128 * 128 * 2);  // [384] (pre-multiplied by -log2 e)
-  float* sDelta = sLse + kSP;                                   // [384]
+  float* sLse = reinterpret_cast<float*>(sdS + 128 * 128 * 2);  // [384] -lse * log2(e) (+ log2(drop_scale))
+  float* sDelta = sLse + kSP;                                   // [384] delta * scale
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
 
@@ -331,12 +329,13 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   const __nv_bfloat16* dobase = dctx + static_cast<size_t>(b) * S * D + h * dh;
   const int nt = (S + 127) / 128;
   const int grp_per_row = (S + 15) / 16;
+  const uint32_t thresh4 = thresh8 * 0x01010101u;
 
   load_head_tile<DHP>(sQ, qbase, ld, 0, S, kSP, dh);
   load_head_tile<DHP>(sK, qbase + D, ld, 0, S, kSP, dh);
   load_head_tile<DHP>(sV, qbase + 2 * D, ld, 0, S, kSP, dh);
   load_head_tile<DHP>(sdO, dobase, D, 0, S, kSP, dh);
-  if (tid < kSP) {  // per-row statistics: LSE (scaled to the exp2 domain) and delta = sum_d dO * O
+  if (tid < kSP) {  // per-row statistics: LSE (exp2 domain) and delta = sum_d dO * O (pre-scaled)
     float l = 0.0f, acc = 0.0f;
     if (tid < S) {
       l = -lse[static_cast<size_t>(bh) * S + tid] * 1.4426950408889634f;
@@ -358,11 +357,11 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
       }
     }
     sLse[tid] = l;
-    sDelta[tid] = acc;
+    sDelta[tid] = acc * scale;
   }
   cp_async_wait_all();
   if (tid == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(&bar, 3);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(&tmem_slot);
@@ -377,45 +376,28 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   const uint32_t idesc_kv = umma_idesc_bf16(128, DHP, 1, 1);
   const uint32_t idesc_q = umma_idesc_bf16(128, DHP, 0, 1);
   const float c2 = scale * 1.4426950408889634f;
-  const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), adO = smem_u32(sdO);
-  const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
+  const float ds_scale = drop_scale * scale;  // dS = P * (dP * keep * drop_scale - delta) * scale
+  const bool issuer_kv = tid == 0, issuer_q = tid == 128, issuer_s = tid == 256;
+  // K-major views (contract over head dim): LBO = 128, SBO = RS. MN-major views (contract over rows): LBO = RS, SBO = 128
+  const uint64_t kQ = umma_smem_desc(smem_u32(sQ), 128, RS, UMMA_SWZ_NONE), mQ = umma_smem_desc(smem_u32(sQ), RS, 128, UMMA_SWZ_NONE);
+  const uint64_t kK = umma_smem_desc(smem_u32(sK), 128, RS, UMMA_SWZ_NONE), mK = umma_smem_desc(smem_u32(sK), RS, 128, UMMA_SWZ_NONE);
+  const uint64_t kV = umma_smem_desc(smem_u32(sV), 128, RS, UMMA_SWZ_NONE);
+  const uint64_t kdO = umma_smem_desc(smem_u32(sdO), 128, RS, UMMA_SWZ_NONE), mdO = umma_smem_desc(smem_u32(sdO), RS, 128, UMMA_SWZ_NONE);
+  // P / dS [128 q, 128 keys]: MN-major (mn = keys, k = q rows) for dV / dK, K-major over keys for dQ
+  const uint64_t mP = umma_smem_desc(smem_u32(sP), RS_P, 128, UMMA_SWZ_NONE);
+  const uint64_t mdS = umma_smem_desc(smem_u32(sdS), RS_P, 128, UMMA_SWZ_NONE);
+  const uint64_t kdS = umma_smem_desc(smem_u32(sdS), 128, RS_P, UMMA_SWZ_NONE);
 
   auto issue_scores = [&](int i, int j) {  // S = Q_i K_j^T, dP = dO_i V_j^T
 #pragma unroll
-    for (int k = 0; k < DHP / 16; ++k) {
-      const uint64_t da = umma_smem_desc(aQ + (i * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
-      const uint64_t db = umma_smem_desc(aK + (j * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
-      umma_ss(tS, da, db, idesc_s, k != 0);
-    }
+    for (int k = 0; k < DHP / 16; ++k)
+      umma_ss(tS, umma_desc_advance(kQ, (i * 16) * RS + k * 256), umma_desc_advance(kK, (j * 16) * RS + k * 256), idesc_s, k != 0);
 #pragma unroll
-    for (int k = 0; k < DHP / 16; ++k) {
-      const uint64_t da = umma_smem_desc(adO + (i * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
-      const uint64_t db = umma_smem_desc(aV + (j * 16) * RS + k * 256, 128, RS, UMMA_SWZ_NONE);
-      umma_ss(tdP, da, db, idesc_s, k != 0);
-    }
+    for (int k = 0; k < DHP / 16; ++k)
+      umma_ss(tdP, umma_desc_advance(kdO, (i * 16) * RS + k * 256), umma_desc_advance(kV, (j * 16) * RS + k * 256), idesc_s, k != 0);
+    umma_commit(&bar);
   };
-  auto issue_grads = [&](int i, int j) {
-#pragma unroll
-    for (int k = 0; k < 128 / 16; ++k) {
-      // contraction over the 128 query rows of tile i: P / dS read MN-major (mn = keys: SBO = 128,
-      // k = q rows: LBO = RS_P); dO / Q read MN-major (mn = head dim: SBO = 128, k = rows: LBO = RS)
-      const uint64_t dpT = umma_smem_desc(aP + (k * 2) * RS_P, RS_P, 128, UMMA_SWZ_NONE);
-      const uint64_t dsT = umma_smem_desc(adS + (k * 2) * RS_P, RS_P, 128, UMMA_SWZ_NONE);
-      const uint64_t ddo = umma_smem_desc(adO + (i * 16 + k * 2) * RS, RS, 128, UMMA_SWZ_NONE);
-      const uint64_t dq = umma_smem_desc(aQ + (i * 16 + k * 2) * RS, RS, 128, UMMA_SWZ_NONE);
-      umma_ss(tdV, dpT, ddo, idesc_kv, (i | k) != 0);
-      umma_ss(tdK, dsT, dq, idesc_kv, (i | k) != 0);
-    }
-#pragma unroll
-    for (int k = 0; k < 128 / 16; ++k) {
-      // dQ_i += dS K_j: dS K-major over keys (LBO = 128, SBO = RS_P); K_j MN-major over key rows
-      const uint64_t da = umma_smem_desc(adS + k * 256, 128, RS_P, UMMA_SWZ_NONE);
-      const uint64_t db = umma_smem_desc(aK + (j * 16 + k * 2) * RS, RS, 128, UMMA_SWZ_NONE);
-      umma_ss(tdQ + i * DHP, da, db, idesc_q, (j | k) != 0);
-    }
-  };
-  // dK_j / dV_j out of TMEM: thread = key row; the 2*NCH 16-column chunks are dealt round-robin to the 4 groups
-  auto store_kv = [&](int j) {
+  auto store_kv = [&](int j) {  // thread = key row; the 2*NCH 16-column chunks are dealt round-robin to the 4 groups
     const int kr = j * 128 + row;
     const bool kvalid = kr < S;
     __nv_bfloat16* drow = dqkv + (static_cast<size_t>(b) * S + (kvalid ? kr : 0)) * ld + h * dh;
@@ -425,10 +407,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
     }
   };
 
-  if (tid == 0) {
-    issue_scores(0, 0);
-    umma_commit(&bar);
-  }
+  if (issuer_s) issue_scores(0, 0);
+  if (issuer_kv || issuer_q) mbar_arrive(&bar);  // only the score issuer has work before the first pair
   uint32_t phase = 0;
   for (int j = 0; j < nt; ++j) {
     for (int i = 0; i < nt; ++i) {
@@ -437,7 +417,6 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
       tc_fence_after();
       if (i == 0 && j > 0) store_kv(j - 1);  // dK/dV of the previous key tile are final
       const int q = i * 128 + row;
-      const bool qvalid = q < S;
       const float lneg = sLse[i * 128 + row];
       const float dl = sDelta[i * 128 + row];
 #pragma unroll 1
@@ -448,20 +427,21 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
         tmem_ld16(tS + lane_sel + c0, vs);
         tmem_ld16(tdP + lane_sel + c0, vd);
         tmem_ld_wait();
-        uint32_t keep = 0xFFFFu;
-        if (thresh8) {
-          const uint64_t gidx = (static_cast<uint64_t>(bh) * S + (qvalid ? q : 0)) * grp_per_row + (k0 >> 4);
-          keep16_from_philox(seed, stream_id, gidx, thresh8, keep);
-        }
+        uint32_t km[4];
+        if (DROP) keep_masks16(seed, stream_id, (static_cast<uint64_t>(bh) * S + (q < S ? q : 0)) * grp_per_row + (k0 >> 4), thresh4, km);
         float pp[16], ds[16];
-        const bool full = qvalid && (k0 + 16 <= S);
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
-          float p = fast_exp2(fmaf(__uint_as_float(vs[jj]), c2, lneg));
-          if (!full && !(qvalid && k0 + jj < S)) p = 0.0f;
-          const float kp = ((keep >> jj) & 1u) ? drop_scale : 0.0f;
-          pp[jj] = p * kp;
-          ds[jj] = (p * scale) * fmaf(__uint_as_float(vd[jj]), kp, -dl);
+          // valid entries have (s - lse) <= 0; the clamp only tames padded keys / rows (inf * 0 would be NaN)
+          const float p = fast_exp2(fminf(fmaf(__uint_as_float(vs[jj]), c2, lneg), 0.0f));
+          if (DROP) {
+            const uint32_t m32 = WM_KEEP32(km, jj);
+            pp[jj] = __uint_as_float(__float_as_uint(p * drop_scale) & m32);
+            ds[jj] = p * fmaf(__uint_as_float(vd[jj] & m32), ds_scale, -dl);
+          } else {
+            pp[jj] = p;
+            ds[jj] = p * fmaf(__uint_as_float(vd[jj]), scale, -dl);
+          }
         }
 #pragma unroll
         for (int g8 = 0; g8 < 2; ++g8) {
@@ -483,12 +463,25 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (issuer_kv) {  // contraction over the 128 query rows of tile i
         tc_fence_after();
-        issue_grads(i, j);
+#pragma unroll
+        for (int k = 0; k < 128 / 16; ++k) {
+          umma_ss(tdV, umma_desc_advance(mP, (k * 2) * RS_P), umma_desc_advance(mdO, (i * 16 + k * 2) * RS), idesc_kv, (i | k) != 0);
+          umma_ss(tdK, umma_desc_advance(mdS, (k * 2) * RS_P), umma_desc_advance(mQ, (i * 16 + k * 2) * RS), idesc_kv, (i | k) != 0);
+        }
+        umma_commit(&bar);
+      } else if (issuer_q) {  // dQ_i += dS K_j, contraction over the 128 keys of tile j
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 128 / 16; ++k)
+          umma_ss(tdQ + i * DHP, umma_desc_advance(kdS, k * 256), umma_desc_advance(mK, (j * 16 + k * 2) * RS), idesc_q, (j | k) != 0);
+        umma_commit(&bar);
+      } else if (issuer_s) {
+        tc_fence_after();
         const int in = i + 1 < nt ? i + 1 : 0, jn = i + 1 < nt ? j : j + 1;
         if (jn < nt) issue_scores(in, jn);
-        umma_commit(&bar);
+        else mbar_arrive(&bar);
       }
     }
   }
@@ -521,10 +514,9 @@ static int launch_fwd_t(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse
                         float scale, uint32_t thresh8, float dscale, uint64_t seed, uint64_t stream_id,
                         cudaStream_t stream) {
   const int smem = 3 * kSP * DHP * 2 + 128 * kSP * 2 + 6 * 128 * 4 + 256;
-  if (cudaFuncSetAttribute(attn_fwd_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-    return WM_ERR_CUDA;
-  attn_fwd_kernel<DHP><<<B * H, kFwdThreads, smem, stream>>>(qkv, ctx, lse, S, H, dh, scale, thresh8, dscale, seed,
-                                                             stream_id);
+  auto kern = thresh8 ? attn_fwd_kernel<DHP, true> : attn_fwd_kernel<DHP, false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
+  kern<<<B * H, kFwdThreads, smem, stream>>>(qkv, ctx, lse, S, H, dh, scale, thresh8, dscale, seed, stream_id);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
@@ -533,10 +525,10 @@ static int launch_bwd_t(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, cons
                         const float* lse, __nv_bfloat16* dqkv, int B, int S, int H, int dh, float scale,
                         uint32_t thresh8, float dscale, uint64_t seed, uint64_t stream_id, cudaStream_t stream) {
   const int smem = 4 * kSP * DHP * 2 + 2 * 128 * 128 * 2 + 2 * kSP * 4 + 256;
-  if (cudaFuncSetAttribute(attn_bwd_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-    return WM_ERR_CUDA;
-  attn_bwd_kernel<DHP><<<B * H, kBwdThreads, smem, stream>>>(qkv, ctx, dctx, lse, dqkv, S, H, dh, scale, thresh8,
-                                                             dscale, seed, stream_id);
+  auto kern = thresh8 ? attn_bwd_kernel<DHP, true> : attn_bwd_kernel<DHP, false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
+  kern<<<B * H, kBwdThreads, smem, stream>>>(qkv, ctx, dctx, lse, dqkv, S, H, dh, scale, thresh8, dscale, seed,
+                                             stream_id);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }

@@ -182,6 +182,11 @@ WM_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" 
 // ---------------------------------------------------------------------------------------------
 enum : uint32_t { UMMA_SWZ_NONE = 0, UMMA_SWZ_128B = 2, UMMA_SWZ_64B = 4, UMMA_SWZ_32B = 6 };
 
+// descriptor of the same layout `byte_off` bytes further into shared memory (start-address field only; the
+// caller guarantees the sum stays below 256 KB so the 14-bit field cannot carry)
+WM_DEVICE uint64_t umma_desc_advance(uint64_t desc, uint32_t byte_off) {
+  return desc + static_cast<uint64_t>(byte_off >> 4);
+}
 WM_DEVICE uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                   uint32_t layout_type) {
   uint64_t d = 0;
@@ -213,13 +218,13 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(uint32_t m, uint32_t n, uint
 struct Philox4 {
   uint32_t x, y, z, w;
 };
-__host__ __device__ inline Philox4 philox4x32_10(uint64_t seed, uint64_t subsequence,
-                                                 uint64_t block_offset) {
+template <int kRounds>
+__host__ __device__ inline Philox4 philox4x32(uint64_t seed, uint64_t subsequence, uint64_t block_offset) {
   uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
   uint32_t c0 = static_cast<uint32_t>(block_offset), c1 = static_cast<uint32_t>(block_offset >> 32);
   uint32_t c2 = static_cast<uint32_t>(subsequence), c3 = static_cast<uint32_t>(subsequence >> 32);
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < kRounds; ++r) {
 #ifdef __CUDA_ARCH__
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
@@ -233,6 +238,9 @@ __host__ __device__ inline Philox4 philox4x32_10(uint64_t seed, uint64_t subsequ
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
   return Philox4{c0, c1, c2, c3};
+}
+__host__ __device__ inline Philox4 philox4x32_10(uint64_t seed, uint64_t subsequence, uint64_t block_offset) {
+  return philox4x32<10>(seed, subsequence, block_offset);
 }
 // curand_uniform: (0,1]
 __host__ __device__ inline float curand_uniform_from_u32(uint32_t x) {

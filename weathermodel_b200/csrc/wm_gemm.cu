@@ -208,6 +208,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(kBM, static_cast<uint32_t>(BN), 0, 0);
+      const uint64_t desc_a0 = umma_smem_desc(smem_u32(smem), 16, 1024, UMMA_SWZ_128B);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -220,14 +221,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&tail->full[s], ph, 13);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
+          // descriptors differ from the stage-0 ones only in the start-address field: one add per MMA
+          const uint64_t da_s = umma_desc_advance(desc_a0, static_cast<uint32_t>(s) * stage_bytes);
+          const uint64_t db_s = umma_desc_advance(da_s, a_bytes);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t da = umma_smem_desc(sa + k * 32, 16, 1024, UMMA_SWZ_128B);
-            const uint64_t db = umma_smem_desc(sb + k * 32, 16, 1024, UMMA_SWZ_128B);
-            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_ss(d_tmem, umma_desc_advance(da_s, k * 32), umma_desc_advance(db_s, k * 32), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
           umma_commit(&tail->empty[s]);
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
@@ -426,20 +426,19 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(kBM, static_cast<uint32_t>(BN), 1, 1);
+      // MN-major SW128: 64-wide MN chunks LBO = 8192 B apart, 8-token groups SBO = 1024 B apart
+      const uint64_t desc_a0 = umma_smem_desc(smem_u32(smem), 8192, 1024, UMMA_SWZ_128B);
       int s = 0;
       uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&tail->full[s], ph, 23);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-        const uint32_t sb = sa + a_bytes;
+        const uint64_t da_s = umma_desc_advance(desc_a0, static_cast<uint32_t>(s) * stage_bytes);
+        const uint64_t db_s = umma_desc_advance(da_s, a_bytes);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // MN-major SW128: 64-wide MN chunks LBO=8192 B apart, 8-token groups SBO=1024 B apart
-          const uint64_t da = umma_smem_desc(sa + k * 2048, 8192, 1024, UMMA_SWZ_128B);
-          const uint64_t db = umma_smem_desc(sb + k * 2048, 8192, 1024, UMMA_SWZ_128B);
-          umma_ss(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < kBK / 16; ++k)
+          umma_ss(tmem_base, umma_desc_advance(da_s, k * 2048), umma_desc_advance(db_s, k * 2048), idesc,
+                  (kb | k) != 0 ? 1u : 0u);
         umma_commit(&tail->empty[s]);
         if (++s == kWgStages) { s = 0; ph ^= 1u; }
       }

@@ -188,27 +188,35 @@ class EncoderRuntime:
         self._active = h
         return y
 
+    def bucket_schedule(self) -> List[Tuple[str, int, int, int, int]]:
+        """Order in which backward finalises slices of the flat gradient buffer (top of the network first):
+        (kind, layer_hi, layer_lo, float_lo, float_hi) with kind in {'head', 'layers', 'embed'}."""
+        L = len(self.module_ref.transformer_encoder.layers)
+        sched = [("head", L, L, self.offsets[-2], self.flat_grads.numel())]
+        hi = L
+        while hi > 0:
+            lo = max(0, hi - self.layers_per_bucket)
+            sched.append(("layers", hi, lo) + self.layer_slice(lo, hi))
+            hi = lo
+        sched.append(("embed", 0, 0, 0, self.offsets[2]))
+        return sched
+
     def backward(self, handle: int, dy_bf16: torch.Tensor):
         """dy_bf16: bf16 [B*S, 32|64] gradient of the loss w.r.t. the padded head output. Fills flat_grads
         (and each parameter's .grad as a view of it); fires grad_ready_hook per bucket, top layers first."""
-        L = len(self.module_ref.transformer_encoder.layers)
         fg, fp = self.flat_grads.data_ptr(), self.flat_params.data_ptr()
         st = ops._stream()
         hook = self.grad_ready_hook
         with torch.cuda.device(self.flat_params.device):
-            check(lib().wm_encoder_backward_head(handle, dy_bf16.data_ptr(), fg, st), "wm_encoder_backward_head")
-            if hook:
-                hook(self.offsets[-2], self.flat_grads.numel())
-            hi = L
-            while hi > 0:
-                lo = max(0, hi - self.layers_per_bucket)
-                check(lib().wm_encoder_backward_layers(handle, fp, hi, lo, fg, st), "wm_encoder_backward_layers")
+            for kind, hi, lo, f_lo, f_hi in self.bucket_schedule():
+                if kind == "head":
+                    check(lib().wm_encoder_backward_head(handle, dy_bf16.data_ptr(), fg, st), "wm_encoder_backward_head")
+                elif kind == "layers":
+                    check(lib().wm_encoder_backward_layers(handle, fp, hi, lo, fg, st), "wm_encoder_backward_layers")
+                else:
+                    check(lib().wm_encoder_backward_embed(handle, fg, st), "wm_encoder_backward_embed")
                 if hook:
-                    hook(*self.layer_slice(lo, hi))
-                hi = lo
-            check(lib().wm_encoder_backward_embed(handle, fg, st), "wm_encoder_backward_embed")
-            if hook:
-                hook(0, self.offsets[2])
+                    hook(f_lo, f_hi)
 
     def publish_grads(self, accumulate_from: Optional[torch.Tensor] = None):
         for i, (_, p) in enumerate(self._named):
