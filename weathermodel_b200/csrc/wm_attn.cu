@@ -80,7 +80,7 @@ WM_DEVICE float fast_exp2(float x) {
 // the softmax is exact two-pass (max, then exp/sum) with one MMA round trip per tile; two issuing threads
 // (PV of this tile, QK^T of the next) keep descriptor arithmetic off the critical path.
 // ------------------------------------------------------------------------------------------------
-constexpr int kFwdThreads = 384;
+constexpr int kFwdThreads = 416;  // 12 softmax warps + 1 MMA-issue warp (its lane 0 never shares a warp with spinning waiters)
 
 template <int DHP, bool DROP>
 __global__ void __launch_bounds__(kFwdThreads, 1)
@@ -131,7 +131,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
   const uint32_t idesc_o = umma_idesc_bf16(128, DHP, 0, 1);
   const float c2 = scale * 1.4426950408889634f;
-  const bool issuer_o = tid == 0, issuer_s = tid == 128;
+  const bool issue_warp = warp == 12;
   const uint64_t dQ0 = umma_smem_desc(smem_u32(sQ), 128, RS, UMMA_SWZ_NONE);
   const uint64_t dK0 = umma_smem_desc(smem_u32(sK), 128, RS, UMMA_SWZ_NONE);
   const uint64_t dP0 = umma_smem_desc(smem_u32(sP), 128, RS_P, UMMA_SWZ_NONE);
@@ -147,9 +147,25 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     }
     umma_commit(&bar_s);
   };
-  if (issuer_s) issue_scores(0);
+  if (issue_warp) {
+    // ---- MMA-issue warp: mirrors the three block barriers of every tile, issues after the second one
+    if (lane == 0) issue_scores(0);
+    for (int it = 0; it < ntq; ++it) {
+      __syncthreads();  // row maxima exchanged
+      __syncthreads();  // P tile complete in smem, all score reads done
+      if (lane == 0) {
+        tc_fence_after();
+        for (int k = 0; k < nk16; ++k)
+          umma_ss(tO, umma_desc_advance(dP0, k * 256), umma_desc_advance(dV0, (k * 2) * RS), idesc_o, k != 0);
+        umma_commit(&bar_o);
+        if (it + 1 < ntq) issue_scores(it + 1);  // runs under this tile's epilogue
+      }
+      __syncwarp();
+      tc_fence_before();
+      __syncthreads();  // epilogue done: O and P reusable
+    }
+  } else {
   uint32_t ph_s = 0, ph_o = 0;
-
   for (int it = 0; it < ntq; ++it) {
     const int q = it * 128 + row;
     const bool qvalid = q < S;
@@ -225,16 +241,6 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (issuer_o) {
-      tc_fence_after();
-      for (int k = 0; k < nk16; ++k)
-        umma_ss(tO, umma_desc_advance(dP0, k * 256), umma_desc_advance(dV0, (k * 2) * RS), idesc_o, k != 0);
-      umma_commit(&bar_o);
-    }
-    if (issuer_s && it + 1 < ntq) {  // scores of the next tile run under this tile's PV and epilogue
-      tc_fence_after();
-      issue_scores(it + 1);
-    }
     mbar_wait(&bar_o, ph_o, 43);
     ph_o ^= 1u;
     tc_fence_after();
@@ -262,6 +268,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     tc_fence_before();
     __syncthreads();  // O drained, sMax / sSum / sP reusable
   }
+  }
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
@@ -276,7 +283,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
 // No validity masks are needed: padded query / key rows are zero in every staged tile, so whatever P and dS
 // hold there is multiplied by zero rows or lands in rows that are never stored.
 // ------------------------------------------------------------------------------------------------
-constexpr int kBwdThreads = 512;
+constexpr int kBwdThreads = 544;  // 16 elementwise warps + 1 MMA-issue warp
 
 template <int DHP>
 WM_DEVICE void store_acc_chunk(uint32_t taddr, __nv_bfloat16* dst, int c0, int dh, bool valid) {
@@ -361,7 +368,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   }
   cp_async_wait_all();
   if (tid == 0) {
-    mbar_init(&bar, 3);
+    mbar_init(&bar, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(&tmem_slot);
@@ -377,7 +384,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   const uint32_t idesc_q = umma_idesc_bf16(128, DHP, 0, 1);
   const float c2 = scale * 1.4426950408889634f;
   const float ds_scale = drop_scale * scale;  // dS = P * (dP * keep * drop_scale - delta) * scale
-  const bool issuer_kv = tid == 0, issuer_q = tid == 128, issuer_s = tid == 256;
+  const bool issue_warp = warp == 16;
   // K-major views (contract over head dim): LBO = 128, SBO = RS. MN-major views (contract over rows): LBO = RS, SBO = 128
   const uint64_t kQ = umma_smem_desc(smem_u32(sQ), 128, RS, UMMA_SWZ_NONE), mQ = umma_smem_desc(smem_u32(sQ), RS, 128, UMMA_SWZ_NONE);
   const uint64_t kK = umma_smem_desc(smem_u32(sK), 128, RS, UMMA_SWZ_NONE), mK = umma_smem_desc(smem_u32(sK), RS, 128, UMMA_SWZ_NONE);
@@ -395,7 +402,6 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
 #pragma unroll
     for (int k = 0; k < DHP / 16; ++k)
       umma_ss(tdP, umma_desc_advance(kdO, (i * 16) * RS + k * 256), umma_desc_advance(kV, (j * 16) * RS + k * 256), idesc_s, k != 0);
-    umma_commit(&bar);
   };
   auto store_kv = [&](int j) {  // thread = key row; the 2*NCH 16-column chunks are dealt round-robin to the 4 groups
     const int kr = j * 128 + row;
@@ -407,94 +413,99 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
     }
   };
 
-  if (issuer_s) issue_scores(0, 0);
-  if (issuer_kv || issuer_q) mbar_arrive(&bar);  // only the score issuer has work before the first pair
-  uint32_t phase = 0;
-  for (int j = 0; j < nt; ++j) {
-    for (int i = 0; i < nt; ++i) {
-      mbar_wait(&bar, phase, 51);  // S/dP of (j, i) ready; every earlier product has completed as well
-      phase ^= 1u;
-      tc_fence_after();
-      if (i == 0 && j > 0) store_kv(j - 1);  // dK/dV of the previous key tile are final
-      const int q = i * 128 + row;
-      const float lneg = sLse[i * 128 + row];
-      const float dl = sDelta[i * 128 + row];
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        const int c0 = grp * 32 + hh * 16;   // column inside the key tile
-        const int k0 = j * 128 + c0;          // global key index
-        uint32_t vs[16], vd[16];
-        tmem_ld16(tS + lane_sel + c0, vs);
-        tmem_ld16(tdP + lane_sel + c0, vd);
-        tmem_ld_wait();
-        uint32_t km[4];
-        if (DROP) keep_masks16(seed, stream_id, (static_cast<uint64_t>(bh) * S + (q < S ? q : 0)) * grp_per_row + (k0 >> 4), thresh4, km);
-        float pp[16], ds[16];
+  if (issue_warp) {
+    // ---- MMA-issue warp: one block barrier per (j, i) pair (P / dS complete), then all five products + commit
+    if (lane == 0) {
+      issue_scores(0, 0);
+      umma_commit(&bar);
+    }
+    for (int j = 0; j < nt; ++j) {
+      for (int i = 0; i < nt; ++i) {
+        __syncthreads();
+        if (lane == 0) {
+          tc_fence_after();
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          // valid entries have (s - lse) <= 0; the clamp only tames padded keys / rows (inf * 0 would be NaN)
-          const float p = fast_exp2(fminf(fmaf(__uint_as_float(vs[jj]), c2, lneg), 0.0f));
-          if (DROP) {
-            const uint32_t m32 = WM_KEEP32(km, jj);
-            pp[jj] = __uint_as_float(__float_as_uint(p * drop_scale) & m32);
-            ds[jj] = p * fmaf(__uint_as_float(vd[jj] & m32), ds_scale, -dl);
-          } else {
-            pp[jj] = p;
-            ds[jj] = p * fmaf(__uint_as_float(vd[jj]), scale, -dl);
+          for (int k = 0; k < 128 / 16; ++k) {  // contraction over the 128 query rows of tile i
+            umma_ss(tdV, umma_desc_advance(mP, (k * 2) * RS_P), umma_desc_advance(mdO, (i * 16 + k * 2) * RS), idesc_kv, (i | k) != 0);
+            umma_ss(tdK, umma_desc_advance(mdS, (k * 2) * RS_P), umma_desc_advance(mQ, (i * 16 + k * 2) * RS), idesc_kv, (i | k) != 0);
           }
-        }
 #pragma unroll
-        for (int g8 = 0; g8 < 2; ++g8) {
-          uint4 pk, dk;
-          pk.x = pack_bf16x2(pp[g8 * 8 + 0], pp[g8 * 8 + 1]);
-          pk.y = pack_bf16x2(pp[g8 * 8 + 2], pp[g8 * 8 + 3]);
-          pk.z = pack_bf16x2(pp[g8 * 8 + 4], pp[g8 * 8 + 5]);
-          pk.w = pack_bf16x2(pp[g8 * 8 + 6], pp[g8 * 8 + 7]);
-          dk.x = pack_bf16x2(ds[g8 * 8 + 0], ds[g8 * 8 + 1]);
-          dk.y = pack_bf16x2(ds[g8 * 8 + 2], ds[g8 * 8 + 3]);
-          dk.z = pack_bf16x2(ds[g8 * 8 + 4], ds[g8 * 8 + 5]);
-          dk.w = pack_bf16x2(ds[g8 * 8 + 6], ds[g8 * 8 + 7]);
-          const int kc = c0 + g8 * 8;
-          const uint32_t off = (row >> 3) * RS_P + (kc >> 3) * 128 + (row & 7) * 16;
-          *reinterpret_cast<uint4*>(sP + off) = pk;
-          *reinterpret_cast<uint4*>(sdS + off) = dk;
+          for (int k = 0; k < 128 / 16; ++k)  // dQ_i += dS K_j, contraction over the 128 keys of tile j
+            umma_ss(tdQ + i * DHP, umma_desc_advance(kdS, k * 256), umma_desc_advance(mK, (j * 16 + k * 2) * RS), idesc_q, (j | k) != 0);
+          const int in = i + 1 < nt ? i + 1 : 0, jn = i + 1 < nt ? j : j + 1;
+          if (jn < nt) issue_scores(in, jn);
+          umma_commit(&bar);
         }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (issuer_kv) {  // contraction over the 128 query rows of tile i
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 128 / 16; ++k) {
-          umma_ss(tdV, umma_desc_advance(mP, (k * 2) * RS_P), umma_desc_advance(mdO, (i * 16 + k * 2) * RS), idesc_kv, (i | k) != 0);
-          umma_ss(tdK, umma_desc_advance(mdS, (k * 2) * RS_P), umma_desc_advance(mQ, (i * 16 + k * 2) * RS), idesc_kv, (i | k) != 0);
-        }
-        umma_commit(&bar);
-      } else if (issuer_q) {  // dQ_i += dS K_j, contraction over the 128 keys of tile j
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 128 / 16; ++k)
-          umma_ss(tdQ + i * DHP, umma_desc_advance(kdS, k * 256), umma_desc_advance(mK, (j * 16 + k * 2) * RS), idesc_q, (j | k) != 0);
-        umma_commit(&bar);
-      } else if (issuer_s) {
-        tc_fence_after();
-        const int in = i + 1 < nt ? i + 1 : 0, jn = i + 1 < nt ? j : j + 1;
-        if (jn < nt) issue_scores(in, jn);
-        else mbar_arrive(&bar);
+        __syncwarp();
       }
     }
-  }
-  mbar_wait(&bar, phase, 52);  // the last gradient products
-  phase ^= 1u;
-  tc_fence_after();
-  store_kv(nt - 1);
-  for (int c = grp; c < nt * NCH; c += 4) {  // dQ: thread = query row
-    const int i = c / NCH, cc = c - i * NCH;
-    const int q = i * 128 + row;
-    const bool qvalid = q < S;
-    __nv_bfloat16* dst = dqkv + (static_cast<size_t>(b) * S + (qvalid ? q : 0)) * ld + h * dh;
-    store_acc_chunk<DHP>(tdQ + i * DHP + lane_sel, dst, cc * 16, dh, qvalid);
+  } else {
+    uint32_t phase = 0;
+    for (int j = 0; j < nt; ++j) {
+      for (int i = 0; i < nt; ++i) {
+        mbar_wait(&bar, phase, 51);  // S/dP of (j, i) ready; every earlier product has completed as well
+        phase ^= 1u;
+        tc_fence_after();
+        if (i == 0 && j > 0) store_kv(j - 1);  // dK/dV of the previous key tile are final
+        const int q = i * 128 + row;
+        const float lneg = sLse[i * 128 + row];
+        const float dl = sDelta[i * 128 + row];
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const int c0 = grp * 32 + hh * 16;   // column inside the key tile
+          const int k0 = j * 128 + c0;          // global key index
+          uint32_t vs[16], vd[16];
+          tmem_ld16(tS + lane_sel + c0, vs);
+          tmem_ld16(tdP + lane_sel + c0, vd);
+          tmem_ld_wait();
+          uint32_t km[4];
+          if (DROP) keep_masks16(seed, stream_id, (static_cast<uint64_t>(bh) * S + (q < S ? q : 0)) * grp_per_row + (k0 >> 4), thresh4, km);
+          float pp[16], ds[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            // valid entries have (s - lse) <= 0; the clamp only tames padded keys / rows (inf * 0 would be NaN)
+            const float p = fast_exp2(fminf(fmaf(__uint_as_float(vs[jj]), c2, lneg), 0.0f));
+            if (DROP) {
+              const uint32_t m32 = WM_KEEP32(km, jj);
+              pp[jj] = __uint_as_float(__float_as_uint(p * drop_scale) & m32);
+              ds[jj] = p * fmaf(__uint_as_float(vd[jj] & m32), ds_scale, -dl);
+            } else {
+              pp[jj] = p;
+              ds[jj] = p * fmaf(__uint_as_float(vd[jj]), scale, -dl);
+            }
+          }
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            uint4 pk, dk;
+            pk.x = pack_bf16x2(pp[g8 * 8 + 0], pp[g8 * 8 + 1]);
+            pk.y = pack_bf16x2(pp[g8 * 8 + 2], pp[g8 * 8 + 3]);
+            pk.z = pack_bf16x2(pp[g8 * 8 + 4], pp[g8 * 8 + 5]);
+            pk.w = pack_bf16x2(pp[g8 * 8 + 6], pp[g8 * 8 + 7]);
+            dk.x = pack_bf16x2(ds[g8 * 8 + 0], ds[g8 * 8 + 1]);
+            dk.y = pack_bf16x2(ds[g8 * 8 + 2], ds[g8 * 8 + 3]);
+            dk.z = pack_bf16x2(ds[g8 * 8 + 4], ds[g8 * 8 + 5]);
+            dk.w = pack_bf16x2(ds[g8 * 8 + 6], ds[g8 * 8 + 7]);
+            const int kc = c0 + g8 * 8;
+            const uint32_t off = (row >> 3) * RS_P + (kc >> 3) * 128 + (row & 7) * 16;
+            *reinterpret_cast<uint4*>(sP + off) = pk;
+            *reinterpret_cast<uint4*>(sdS + off) = dk;
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+      }
+    }
+    mbar_wait(&bar, phase, 52);  // the last gradient products
+    tc_fence_after();
+    store_kv(nt - 1);
+    for (int c = grp; c < nt * NCH; c += 4) {  // dQ: thread = query row
+      const int i = c / NCH, cc = c - i * NCH;
+      const int q = i * 128 + row;
+      const bool qvalid = q < S;
+      __nv_bfloat16* dst = dqkv + (static_cast<size_t>(b) * S + (qvalid ? q : 0)) * ld + h * dh;
+      store_acc_chunk<DHP>(tdQ + i * DHP + lane_sel, dst, cc * 16, dh, qvalid);
+    }
   }
   tc_fence_before();
   __syncthreads();

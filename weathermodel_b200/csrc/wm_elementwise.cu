@@ -106,13 +106,14 @@ embed_fwd_kernel(const float* __restrict__ weather, const uint8_t* __restrict__ 
   extern __shared__ float smf[];
   const int Fin = F + 3;
   const int FinP = (Fin + 3) & ~3;
-  float* sW = smf;                 // [Fin][D]
-  float* sX = smf + Fin * D;       // [kEmbTok][FinP]
+  constexpr int kWLd = 41;         // row pitch of the staged weight rows (odd: conflict-light column reads)
+  float* sW = smf;                 // [D][kWLd], row d = w_in[d, :]
+  float* sX = smf + D * kWLd;      // [kEmbTok][FinP]
   const int64_t M = static_cast<int64_t>(B) * S;
   const int64_t t0 = static_cast<int64_t>(blockIdx.x) * kEmbTok;
-  for (int i = threadIdx.x; i < Fin * D; i += blockDim.x) {
-    const int d = i / Fin, c = i - d * Fin;  // w_in is [D][Fin]
-    sW[c * D + d] = w_in[i];
+  for (int i = threadIdx.x; i < Fin * D; i += blockDim.x) {  // coalesced global read, conflict-free smem write
+    const int d = i / Fin, c = i - d * Fin;
+    sW[d * kWLd + c] = w_in[i];
   }
   for (int i = threadIdx.x; i < kEmbTok * FinP; i += blockDim.x) {
     const int tt = i / FinP, c = i - tt * FinP;
@@ -142,33 +143,46 @@ embed_fwd_kernel(const float* __restrict__ weather, const uint8_t* __restrict__ 
       if (t < M) xin[t * kXinLd + c] = __float2bfloat16(c < Fin ? sX[tt * FinP + c] : 0.0f);
     }
   }
+  const int s0 = static_cast<int>(t0 % S);
   for (int d = threadIdx.x * 2; d < D; d += blockDim.x * 2) {
     float w0[40], w1[40];
 #pragma unroll
     for (int c = 0; c < 40; ++c) {
-      w0[c] = c < Fin ? sW[c * D + d] : 0.0f;
-      w1[c] = c < Fin ? sW[c * D + d + 1] : 0.0f;
+      w0[c] = c < Fin ? sW[d * kWLd + c] : 0.0f;
+      w1[c] = c < Fin ? sW[(d + 1) * kWLd + c] : 0.0f;
     }
     const float bias0 = b_in[d], bias1 = b_in[d + 1];
-    for (int tt = 0; tt < kEmbTok; ++tt) {
-      const int64_t t = t0 + tt;
-      if (t >= M) break;
-      const int s = static_cast<int>(t % S);
-      float a0 = 0.0f, a1 = 0.0f;
-      const float4* xr = reinterpret_cast<const float4*>(sX + tt * FinP);
+#pragma unroll 1
+    for (int tb = 0; tb < kEmbTok; tb += 4) {
+      float2 pev[4];
 #pragma unroll
-      for (int c4 = 0; c4 < 10; ++c4) {
-        if (c4 * 4 < FinP) {
-          const float4 x = xr[c4];
-          a0 = fmaf(x.x, w0[c4 * 4], a0); a1 = fmaf(x.x, w1[c4 * 4], a1);
-          a0 = fmaf(x.y, w0[c4 * 4 + 1], a0); a1 = fmaf(x.y, w1[c4 * 4 + 1], a1);
-          a0 = fmaf(x.z, w0[c4 * 4 + 2], a0); a1 = fmaf(x.z, w1[c4 * 4 + 2], a1);
-          a0 = fmaf(x.w, w0[c4 * 4 + 3], a0); a1 = fmaf(x.w, w1[c4 * 4 + 3], a1);
-        }
+      for (int u = 0; u < 4; ++u) {  // the four position-table loads of this batch are issued together
+        int sidx = s0 + tb + u;
+        if (sidx >= S) sidx -= S;
+        if (sidx >= S) sidx -= S;
+        pev[u] = (t0 + tb + u < M) ? __ldg(reinterpret_cast<const float2*>(pe + static_cast<size_t>(sidx) * D + d))
+                                   : make_float2(0.f, 0.f);
       }
-      a0 = (a0 + bias0) + pe[static_cast<size_t>(s) * D + d];
-      a1 = (a1 + bias1) + pe[static_cast<size_t>(s) * D + d + 1];
-      *reinterpret_cast<uint32_t*>(out + t * D + d) = pack_bf16x2(a0, a1);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int tt = tb + u;
+        const int64_t t = t0 + tt;
+        float a0 = 0.0f, a1 = 0.0f;
+        const float4* xr = reinterpret_cast<const float4*>(sX + tt * FinP);
+#pragma unroll
+        for (int c4 = 0; c4 < 10; ++c4) {
+          if (c4 * 4 < FinP) {
+            const float4 x = xr[c4];
+            a0 = fmaf(x.x, w0[c4 * 4], a0); a1 = fmaf(x.x, w1[c4 * 4], a1);
+            a0 = fmaf(x.y, w0[c4 * 4 + 1], a0); a1 = fmaf(x.y, w1[c4 * 4 + 1], a1);
+            a0 = fmaf(x.z, w0[c4 * 4 + 2], a0); a1 = fmaf(x.z, w1[c4 * 4 + 2], a1);
+            a0 = fmaf(x.w, w0[c4 * 4 + 3], a0); a1 = fmaf(x.w, w1[c4 * 4 + 3], a1);
+          }
+        }
+        a0 = (a0 + bias0) + pev[u].x;
+        a1 = (a1 + bias1) + pev[u].y;
+        if (t < M) *reinterpret_cast<uint32_t*>(out + t * D + d) = pack_bf16x2(a0, a1);
+      }
     }
   }
 }
@@ -179,7 +193,7 @@ int launch_embed_fwd(const float* weather, const uint8_t* mask, int64_t msb, int
   if (B <= 0 || S <= 0 || F <= 0 || F + 3 > 40 || (D & 1)) return WM_ERR_SHAPE;
   const int64_t M = static_cast<int64_t>(B) * S;
   const int Fin = F + 3, FinP = (Fin + 3) & ~3;
-  const int smem = (Fin * D + kEmbTok * FinP) * 4;
+  const int smem = (41 * D + kEmbTok * FinP) * 4;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return WM_ERR_CUDA;
