@@ -33,6 +33,8 @@ const char* wm_strerror(int code);
 int wm_device_error(void);
 /* number of kernels this library has launched so far in this process (host-side counter) */
 long long wm_launch_count(void);
+/* debug: clock64() timestamps that CTA 0 of the attention kernels records at its phase boundaries (HOST pointer) */
+int wm_debug_ticks(long long* out_host, int n);
 /* torch.rand grid size for `numel` elements on the current device
  * (torch:include/ATen/native/cuda/DistributionTemplates.h:50-63 calc_execution_policy). */
 int wm_rand_grid_x(int64_t numel);

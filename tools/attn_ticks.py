@@ -1,0 +1,51 @@
+"""Phase timeline (clock64 deltas, CTA 0) of attn_fwd at the large config: where do a head's cycles go?"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from weathermodel_b200 import ops
+from weathermodel_b200._lib import lib
+
+B, S, H, dh = int(sys.argv[1]) if len(sys.argv) > 1 else 64, 365, 16, 36
+qkv = (torch.randn(B * S, 3 * H * dh, device="cuda") * 0.5).to(torch.bfloat16)
+for p in (0.0, 0.1):
+    for _ in range(3):
+        ops.attn_fwd(qkv, B, S, H, dh, dropout_p=p, seed=1, stream_id=1)
+    buf = (C.c_longlong * 32)()
+    lib().wm_debug_ticks(buf, 32)
+    t = list(buf)
+    names = {0: "start", 1: "cp.async issued", 2: "cp.async landed", 3: "setup sync+alloc"}
+    for it in range(3):
+        for k, nm in enumerate(["tile top", "scores ready", "pass1 done", "max exchanged", "pass2 done", "P synced", "PV done", "epilogue done"]):
+            names[4 + it * 8 + k] = f"t{it} {nm}"
+    names[28] = "end"
+    prev = t[0]
+    print(f"--- attn_fwd p={p}: total {t[28] - t[0]} cycles")
+    for i in sorted(names):
+        print(f"{names[i]:22s} +{t[i] - prev:7d}  (@{t[i] - t[0]})")
+        prev = t[i]
+
+dctx = (torch.randn(B * S, H * dh, device="cuda") * 0.5).to(torch.bfloat16)
+for p in (0.0, 0.1):
+    ctx, lse = ops.attn_fwd(qkv, B, S, H, dh, dropout_p=p, seed=1, stream_id=1)
+    for _ in range(3):
+        ops.attn_bwd(qkv, ctx, dctx, lse, B, S, H, dh, dropout_p=p, seed=1, stream_id=1)
+    buf = (C.c_longlong * 64)()
+    lib().wm_debug_ticks(buf, 64)
+    t = list(buf)
+    names = {32: "start", 49: "Q tile issued", 50: "K,V tiles issued", 33: "dO issued", 51: "delta done", 34: "landed + setup sync"}
+    for i in range(3):
+        names[35 + i * 3] = f"pair(0,{i}) top"
+        names[36 + i * 3] = f"pair(0,{i}) S/dP ready"
+        names[37 + i * 3] = f"pair(0,{i}) P/dS written"
+    for j in range(3):
+        names[44 + j] = f"key tile {j} done"
+    names[48] = "all stored"
+    prev = t[32]
+    print(f"--- attn_bwd p={p}: total {t[48] - t[32]} cycles")
+    for i in sorted(names, key=lambda k: t[k]):
+        print(f"{names[i]:26s} +{t[i] - prev:7d}  (@{t[i] - t[32]})")
+        prev = t[i]

@@ -40,6 +40,12 @@ int wm_device_error(void) {
 
 long long wm_launch_count(void) { return g_wm_launches; }
 
+int wm_debug_ticks(long long* out_host, int n) {
+  if (!out_host || n <= 0 || n > 64) return WM_ERR_ARG;
+  if (cudaDeviceSynchronize() != cudaSuccess) return WM_ERR_CUDA;
+  return cudaMemcpyFromSymbol(out_host, g_wm_ticks, sizeof(long long) * n) == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
 int wm_rand_grid_x(int64_t numel) {
   int dev = 0, sms = 0, tpm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;

@@ -39,18 +39,58 @@ WM_DEVICE void cp_async8(void* smem_dst, const void* gmem_src, bool valid) {
 }
 WM_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-template <int DHP>
-WM_DEVICE void load_head_tile(uint8_t* tile, const __nv_bfloat16* __restrict__ src, int ld, int row0, int nrows_valid,
-                              int rows_alloc, int dh) {
+// Stage NT head slices ([S rows, dh] each, row pitch ld[t]) into canonical tiles.
+//  phase 1: every thread issues ALL of its 8-byte global loads into registers. Indexing is warp-structured
+//           (lane -> (row within the warp's row group, piece), rows advance by a constant) so a piece costs a
+//           handful of integer instructions; the first versions spent ~10k cycles per CTA on index arithmetic
+//           and per-piece zero fills (profiles/r01_attn_phase_ticks.txt).
+//  phase 2: the padding (16-byte chunk columns at/after dh, rows >= S) is zeroed with 16-byte stores while the
+//           loads are in flight;  phase 3: barrier, then the data pieces are stored (they overlap the first
+//           zeroed chunk when dh % 8 == 4).
+template <int DHP, int NT, int kIters>
+WM_DEVICE void load_head_tiles(uint8_t* const (&tile)[NT], const __nv_bfloat16* const (&src)[NT], const int (&ld)[NT],
+                               int S, int rows_alloc, int dh) {
   constexpr uint32_t RS = TileGeom<DHP>::RS;
-  constexpr int PP = DHP / 4;  // 8-byte pieces per padded row
-  const int pv = dh / 4;
-  for (int i = threadIdx.x; i < rows_alloc * PP; i += blockDim.x) {
-    const int r = i / PP, p = i - r * PP;
-    const bool valid = r < nrows_valid && p < pv;
-    const __nv_bfloat16* g = valid ? src + static_cast<size_t>(row0 + r) * ld + p * 4 : src;
-    const int d = p * 4;
-    cp_async8(tile + (r >> 3) * RS + (d >> 3) * 128 + (r & 7) * 16 + (d & 7) * 2, g, valid);
+  const int pv = dh >> 2;                   // valid 8-byte pieces per row
+  const int rpi = 32 / pv;                  // rows covered by one warp instruction
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int rsub = lane / pv, p = lane - rsub * pv;
+  const bool lane_on = rsub < rpi;
+  const int rstep = rpi * nwarps;
+  const uint32_t poff = (p >> 1) * 128 + (p & 1) * 8;
+  uint2 v[NT][kIters];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const uint2* g = reinterpret_cast<const uint2*>(src[t] + static_cast<size_t>(warp * rpi + rsub) * ld[t]) + p;
+    const size_t gstep = static_cast<size_t>(rstep) * ld[t] / 4;  // in uint2 units (ld % 4 == 0)
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int r = warp * rpi + rsub + it * rstep;
+      if (lane_on && r < S) v[t][it] = __ldg(g + it * gstep);
+    }
+  }
+  // zero the padding: chunk columns [dh / 8, DHP / 8) of every row, and whole rows [S, rows_alloc)
+  const int cz = dh >> 3, nz = (DHP >> 3) - cz;
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    for (int i = threadIdx.x; i < (rows_alloc >> 3) * nz * 8; i += blockDim.x) {
+      const int g = i / (nz * 8), w = i - g * (nz * 8);  // w = chunk-in-pad * 8 + row-in-group
+      *reinterpret_cast<uint4*>(tile[t] + g * RS + (cz + (w >> 3)) * 128 + (w & 7) * 16) = z4;
+    }
+    for (int i = threadIdx.x; i < (rows_alloc - S) * cz; i += blockDim.x) {
+      const int rr = S + i / cz, c = i - (i / cz) * cz;
+      *reinterpret_cast<uint4*>(tile[t] + (rr >> 3) * RS + c * 128 + (rr & 7) * 16) = z4;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int r = warp * rpi + rsub + it * rstep;
+      if (lane_on && r < S) *reinterpret_cast<uint2*>(tile[t] + (r >> 3) * RS + (r & 7) * 16 + poff) = v[t][it];
+    }
   }
 }
 
@@ -111,10 +151,16 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   const int nk16 = (S + 15) / 16;            // PV k-steps / dropout groups per row
   const uint32_t thresh4 = thresh8 * 0x01010101u;
 
-  load_head_tile<DHP>(sQ, qbase, ld, 0, S, kSP, dh);
-  load_head_tile<DHP>(sK, qbase + D, ld, 0, S, kSP, dh);
-  load_head_tile<DHP>(sV, qbase + 2 * D, ld, 0, S, kSP, dh);
+  if (warp == 0) WM_TICK(0);
+  {
+    uint8_t* const tiles[3] = {sQ, sK, sV};
+    const __nv_bfloat16* const srcs[3] = {qbase, qbase + D, qbase + 2 * D};
+    const int lds[3] = {ld, ld, ld};
+    load_head_tiles<DHP, 3, (kSP + (32 / (DHP / 4)) * (kFwdThreads / 32) - 1) / ((32 / (DHP / 4)) * (kFwdThreads / 32))>(tiles, srcs, lds, S, kSP, dh);
+  }
+  if (warp == 0) WM_TICK(1);
   cp_async_wait_all();
+  if (warp == 0) WM_TICK(2);
   if (tid == 0) {
     mbar_init(&bar_s, 1);
     mbar_init(&bar_o, 1);
@@ -126,6 +172,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (warp == 0) WM_TICK(3);
   const uint32_t tS = tmem, tO = tmem + kSP;
   const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
@@ -169,9 +216,11 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   for (int it = 0; it < ntq; ++it) {
     const int q = it * 128 + row;
     const bool qvalid = q < S;
+    if (warp == 0) WM_TICK(4 + it * 8);
     mbar_wait(&bar_s, ph_s, 41);
     ph_s ^= 1u;
     tc_fence_after();
+    if (warp == 0) WM_TICK(5 + it * 8);
     // ---- pass 1: max over this warp's key tile
     float mloc = -INFINITY;
     if (grp < ntq) {
@@ -193,7 +242,9 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
       }
     }
     sMax[grp * 128 + row] = mloc;
+    if (warp == 0) WM_TICK(6 + it * 8);
     __syncthreads();
+    if (warp == 0) WM_TICK(7 + it * 8);
     const float mrow = fmaxf(fmaxf(sMax[row], sMax[128 + row]), sMax[256 + row]);
     const float mneg = -mrow * c2;
     // ---- pass 2: exp2, row sum, dropout, P -> smem (bf16, K-major over keys)
@@ -238,12 +289,15 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
       }
     }
     sSum[grp * 128 + row] = lsum;
+    if (warp == 0) WM_TICK(8 + it * 8);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (warp == 0) WM_TICK(9 + it * 8);
     mbar_wait(&bar_o, ph_o, 43);
     ph_o ^= 1u;
     tc_fence_after();
+    if (warp == 0) WM_TICK(10 + it * 8);
     // ---- epilogue: warp group g writes head-dim columns [16g, 16g+16)
     if (grp * 16 < DHP) {
       const float tot = sSum[row] + sSum[128 + row] + sSum[256 + row];
@@ -265,9 +319,11 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
         if (grp == 0 && lse_out) lse_out[static_cast<size_t>(bh) * S + q] = mrow * scale + logf(tot);
       }
     }
+    if (warp == 0) WM_TICK(11 + it * 8);
     tc_fence_before();
     __syncthreads();  // O drained, sMax / sSum / sP reusable
   }
+  if (warp == 0) WM_TICK(28);
   }
   if (warp == 0) {
     tc_fence_after();
@@ -338,10 +394,19 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   const int grp_per_row = (S + 15) / 16;
   const uint32_t thresh4 = thresh8 * 0x01010101u;
 
-  load_head_tile<DHP>(sQ, qbase, ld, 0, S, kSP, dh);
-  load_head_tile<DHP>(sK, qbase + D, ld, 0, S, kSP, dh);
-  load_head_tile<DHP>(sV, qbase + 2 * D, ld, 0, S, kSP, dh);
-  load_head_tile<DHP>(sdO, dobase, D, 0, S, kSP, dh);
+  if (warp == 0) WM_TICK(32);
+  {  // two rounds of two tiles keep the in-flight loads within the 544-thread register budget
+    constexpr int kIt = (kSP + (32 / (DHP / 4)) * (kBwdThreads / 32) - 1) / ((32 / (DHP / 4)) * (kBwdThreads / 32));
+    uint8_t* const t0[2] = {sQ, sK};
+    const __nv_bfloat16* const s0[2] = {qbase, qbase + D};
+    const int l0[2] = {ld, ld};
+    load_head_tiles<DHP, 2, kIt>(t0, s0, l0, S, kSP, dh);
+    uint8_t* const t1[2] = {sV, sdO};
+    const __nv_bfloat16* const s1[2] = {qbase + 2 * D, dobase};
+    const int l1[2] = {ld, D};
+    load_head_tiles<DHP, 2, kIt>(t1, s1, l1, S, kSP, dh);
+  }
+  if (warp == 0) WM_TICK(33);
   if (tid < kSP) {  // per-row statistics: LSE (exp2 domain) and delta = sum_d dO * O (pre-scaled)
     float l = 0.0f, acc = 0.0f;
     if (tid < S) {
@@ -366,6 +431,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
     sLse[tid] = l;
     sDelta[tid] = acc * scale;
   }
+  if (warp == 0) WM_TICK(51);
   cp_async_wait_all();
   if (tid == 0) {
     mbar_init(&bar, 1);
@@ -377,6 +443,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (warp == 0) WM_TICK(34);
   const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 256 + DHP, tdQ = tmem + 256 + 2 * DHP;
   const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
@@ -443,9 +510,11 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
     uint32_t phase = 0;
     for (int j = 0; j < nt; ++j) {
       for (int i = 0; i < nt; ++i) {
+        if (warp == 0 && j == 0) WM_TICK(35 + i * 3);
         mbar_wait(&bar, phase, 51);  // S/dP of (j, i) ready; every earlier product has completed as well
         phase ^= 1u;
         tc_fence_after();
+        if (warp == 0 && j == 0) WM_TICK(36 + i * 3);
         if (i == 0 && j > 0) store_kv(j - 1);  // dK/dV of the previous key tile are final
         const int q = i * 128 + row;
         const float lneg = sLse[i * 128 + row];
@@ -491,10 +560,12 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
             *reinterpret_cast<uint4*>(sdS + off) = dk;
           }
         }
+        if (warp == 0 && j == 0) WM_TICK(37 + i * 3);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
       }
+      if (warp == 0) WM_TICK(44 + j);
     }
     mbar_wait(&bar, phase, 52);  // the last gradient products
     tc_fence_after();
@@ -506,6 +577,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
       __nv_bfloat16* dst = dqkv + (static_cast<size_t>(b) * S + (qvalid ? q : 0)) * ld + h * dh;
       store_acc_chunk<DHP>(tdQ + i * DHP + lane_sel, dst, cc * 16, dh, qvalid);
     }
+    if (warp == 0) WM_TICK(48);
   }
   tc_fence_before();
   __syncthreads();

@@ -26,6 +26,13 @@ static long long g_wm_launches = 0;
 
 #define WM_DEVICE __device__ __forceinline__
 
+// phase timestamps of CTA 0 (debug aid for the warp-specialised kernels; read with wm_debug_ticks)
+__device__ long long g_wm_ticks[64];
+#define WM_TICK(i)                                                    \
+  do {                                                                \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_wm_ticks[(i)] = clock64(); \
+  } while (0)
+
 WM_DEVICE uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -276,6 +283,18 @@ WM_DEVICE float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+// 256-bit global accesses (sm_100+): one full 32-byte sector per lane. Thread-per-row epilogues are bound by the
+// number of sectors the LSU touches (~1 per cycle), so 16-byte accesses that each cover half a sector cost twice.
+WM_DEVICE void ldg256(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
+}
+WM_DEVICE void stg256(void* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+               "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
 }
 WM_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);

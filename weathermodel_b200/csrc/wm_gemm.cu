@@ -81,73 +81,87 @@ struct EpiAux {
   uint4 a[2];  // the prefetched operand of a 16-column chunk: the gate rows if a gate is given, else the residual rows
 };
 
-WM_DEVICE void epi_load_aux(EpiAux& x, const GemmEpilogue& ep, int row, int n0, int M, int N) {
+WM_DEVICE void epi_load_aux(EpiAux& x, const GemmEpilogue& ep, int row, int n0, int M, int N, bool wide) {
   const __nv_bfloat16* base = ep.gate ? ep.gate : ep.residual;
   const int ldx = ep.gate ? ep.ld_gate : ep.ld_res;
-#pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    const int n = n0 + g * 8;
-    x.a[g] = make_uint4(0u, 0u, 0u, 0u);
-    if (base && row < M && n < N) x.a[g] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(row) * ldx + n));
+  x.a[0] = make_uint4(0u, 0u, 0u, 0u);
+  x.a[1] = make_uint4(0u, 0u, 0u, 0u);
+  if (!base || row >= M) return;
+  const __nv_bfloat16* p = base + static_cast<size_t>(row) * ldx + n0;
+  if (wide && n0 + 16 <= N) {
+    ldg256(p, x.a[0], x.a[1]);
+  } else {
+    if (n0 < N) x.a[0] = __ldg(reinterpret_cast<const uint4*>(p));
+    if (n0 + 8 < N) x.a[1] = __ldg(reinterpret_cast<const uint4*>(p) + 1);
   }
 }
 
 template <typename OutT>
 WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const float* sbias, const GemmEpilogue& ep,
-                             int row, int n0, int M, int N) {
-  if (row >= M) return;
+                             int row, int n0, int M, int N, bool wide) {
+  if (row >= M || n0 >= N) return;
+  float f[16];
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    const int n = n0 + g * 8;
-    if (n >= N) break;  // N % 8 == 0 (host-checked)
-    float f[8];
+  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+  if (ep.bias) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-    if (ep.bias) {
+    for (int j = 0; j < 16; ++j) f[j] += sbias[j];
+  }
+  if (ep.relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += sbias[g * 8 + j];
-    }
-    if (ep.relu) {
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+  }
+  if (ep.drop_thresh) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
-    }
-    if (ep.drop_thresh) {
-      const uint64_t grp = (static_cast<uint64_t>(row) * static_cast<uint64_t>(N) + n) >> 3;
+    for (int g = 0; g < 2; ++g) {
+      const uint64_t grp = (static_cast<uint64_t>(row) * static_cast<uint64_t>(N) + n0 + g * 8) >> 3;
       const uint32_t keep = dropout_keep8(ep.seed, ep.stream, grp, ep.drop_thresh);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1u) ? f[j] * ep.drop_scale : 0.0f;
+      for (int j = 0; j < 8; ++j) f[g * 8 + j] = ((keep >> j) & 1u) ? f[g * 8 + j] * ep.drop_scale : 0.0f;
     }
-    if (ep.gate) {  // dgrad through dropout(relu(.)): pass where the saved activation is > 0
-      const uint32_t aw[4] = {aux.a[g].x, aux.a[g].y, aux.a[g].z, aux.a[g].w};
+  }
+  if (ep.gate) {  // dgrad through dropout(relu(.)): pass where the saved activation is > 0
+    const uint32_t aw[8] = {aux.a[0].x, aux.a[0].y, aux.a[0].z, aux.a[0].w, aux.a[1].x, aux.a[1].y, aux.a[1].z, aux.a[1].w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        f[2 * j] = bf16_lo(aw[j]) > 0.0f ? f[2 * j] * ep.gate_scale : 0.0f;
-        f[2 * j + 1] = bf16_hi(aw[j]) > 0.0f ? f[2 * j + 1] * ep.gate_scale : 0.0f;
-      }
+    for (int j = 0; j < 8; ++j) {
+      f[2 * j] = bf16_lo(aw[j]) > 0.0f ? f[2 * j] * ep.gate_scale : 0.0f;
+      f[2 * j + 1] = bf16_hi(aw[j]) > 0.0f ? f[2 * j + 1] * ep.gate_scale : 0.0f;
     }
-    if (ep.residual) {
-      uint4 rr = aux.a[g];
-      if (ep.gate)  // both operands given (not on the training schedule): the residual is loaded in place
-        rr = __ldg(reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(row) * ep.ld_res + n));
-      const uint32_t aw[4] = {rr.x, rr.y, rr.z, rr.w};
+  }
+  if (ep.residual) {
+    uint4 r0 = aux.a[0], r1 = aux.a[1];
+    if (ep.gate) {  // both operands given (not on the training schedule): the residual is loaded in place
+      const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(row) * ep.ld_res + n0);
+      r0 = __ldg(rp);
+      r1 = n0 + 8 < N ? __ldg(rp + 1) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    const uint32_t aw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        f[2 * j] += bf16_lo(aw[j]);
-        f[2 * j + 1] += bf16_hi(aw[j]);
-      }
+    for (int j = 0; j < 8; ++j) {
+      f[2 * j] += bf16_lo(aw[j]);
+      f[2 * j + 1] += bf16_hi(aw[j]);
     }
-    if constexpr (sizeof(OutT) == 2) {
-      uint4 o;
-      o.x = pack_bf16x2(f[0], f[1]);
-      o.y = pack_bf16x2(f[2], f[3]);
-      o.z = pack_bf16x2(f[4], f[5]);
-      o.w = pack_bf16x2(f[6], f[7]);
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(row) * ep.ld_out + n) = o;
+  }
+  const bool second = n0 + 8 < N;  // N % 8 == 0 (host-checked)
+  if constexpr (sizeof(OutT) == 2) {
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+    o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+    o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+    o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(row) * ep.ld_out + n0;
+    if (wide && second) {
+      stg256(o, o0, o1);
     } else {
-      float* o = reinterpret_cast<float*>(ep.out) + static_cast<size_t>(row) * ep.ld_out + n;
-      *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+      *reinterpret_cast<uint4*>(o) = o0;
+      if (second) *reinterpret_cast<uint4*>(o + 8) = o1;
     }
+  } else {
+    float* o = reinterpret_cast<float*>(ep.out) + static_cast<size_t>(row) * ep.ld_out + n0;
+    const int lim = second ? 16 : 8;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+      if (j < lim) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
   }
 }
 
@@ -240,6 +254,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = ew >> 2;        // which half of the tile's columns this warp owns
     const int cols_per = BN >> 1;    // BN % 32 == 0 (host-checked)
     float* sbias = tail->bias[ew];
+    // 32-byte accesses need 32-byte aligned rows: every leading dimension a multiple of 16 bf16 elements
+    const bool wide = ((ep.ld_out | (ep.residual ? ep.ld_res : 0) | (ep.gate ? ep.ld_gate : 0)) & 15) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(ep.out) | reinterpret_cast<uintptr_t>(ep.residual) |
+                        reinterpret_cast<uintptr_t>(ep.gate)) & 31) == 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int m_blk = t / n_tiles, n_blk = t % n_tiles;
@@ -258,7 +276,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       EpiAux aux[kAuxDepth];
 #pragma unroll
       for (int d = 0; d < kAuxDepth; ++d)
-        if (d * 16 < cols_per) epi_load_aux(aux[d], ep, row, n_base + d * 16, M, N);
+        if (d * 16 < cols_per) epi_load_aux(aux[d], ep, row, n_base + d * 16, M, N, wide);
       mbar_wait(&tail->acc_full[as], aph, 14);
       tc_fence_after();
       const uint32_t tbase = tmem_base + as * kAccStride + half * cols_per + (static_cast<uint32_t>(q * 32) << 16);
@@ -270,8 +288,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t v[16];
             tmem_ld16(tbase + c0, v);
             tmem_ld_wait();
-            epi_process16<OutT>(v, aux[d], sbias + c0, ep, row, n_base + c0, M, N);
-            if (c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N);
+            epi_process16<OutT>(v, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide);
+            if (c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
           }
         }
       }
