@@ -23,6 +23,22 @@ class _AliasLoader(importlib.abc.Loader):
     def exec_module(self, module):  # already executed under its real name
         pass
 
+    # `python -m src.<module>` (runpy) asks the loader for the code object / source of the module
+    def _real_loader(self):
+        return importlib.util.find_spec(self.real_name).loader
+
+    def get_code(self, fullname):
+        return self._real_loader().get_code(self.real_name)
+
+    def get_source(self, fullname):
+        return self._real_loader().get_source(self.real_name)
+
+    def get_filename(self, fullname):
+        return self._real_loader().get_filename(self.real_name)
+
+    def is_package(self, fullname):
+        return self._real_loader().is_package(self.real_name)
+
 
 class _AliasFinder(importlib.abc.MetaPathFinder):
     def find_spec(self, fullname, path=None, target=None):

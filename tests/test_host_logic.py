@@ -211,3 +211,12 @@ def test_fused_adam_host_path_matches_torch_adam():
     o3 = FusedAdam([a], lr=1e-2)
     o3.load_state_dict(sd)
     assert float(o3.state[a]["step"]) == 5.0
+
+
+def test_cli_module_is_runnable_with_dash_m(tmp_path):
+    """`python -m src.pretraining.pretraining_main` is how the reference is launched (pretraining.sh:45-51)."""
+    import subprocess
+
+    res = subprocess.run([sys.executable, "-m", "src.pretraining.pretraining_main", "--help"], cwd=tmp_path,
+                         env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and "--n-masked-features" in res.stdout and "--beta" in res.stdout
