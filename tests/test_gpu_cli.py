@@ -54,4 +54,6 @@ def test_pretraining_cli_dry_run(tmp_path, model, extra):
     res2 = subprocess.run(cmd2, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
     assert res2.returncode == 0, res2.stdout[-2000:] + res2.stderr[-4000:]
     js2 = json.load(open(out_dir / (stem + "_output.json")))
-    assert len(js2["losses"]["train"]["total_loss"]) == 4
+    # the reference's WeatherFormerTrainer re-initialises output_json["losses"] AFTER the base class restored the
+    # checkpoint (weatherformer_trainer.py:33-46), so a resumed run logs only its own epochs; WeatherBERT keeps all
+    assert len(js2["losses"]["train"]["total_loss"]) == (1 if model == "weatherformer" else 4)
