@@ -33,6 +33,7 @@ SIGNATURES = {
     "wm_device_error": (_i, []),
     "wm_launch_count": (C.c_longlong, []),
     "wm_debug_ticks": (_i, [C.POINTER(C.c_longlong), _i]),
+    "wm_set_option": (_i, [C.c_char_p, _i]),
     "wm_rand_grid_x": (_i, [_i64]),
     "wm_mask_bert": (_i, [_u64, _u64, _i, _f, _i64, _vp, _vp, _vp]),
     "wm_mask_former": (_i, [_u64, _u64, _i, _i, _i64, _i, _vp, _vp]),

@@ -46,6 +46,17 @@ int wm_debug_ticks(long long* out_host, int n) {
   return cudaMemcpyFromSymbol(out_host, g_wm_ticks, sizeof(long long) * n) == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
+namespace wm { extern int g_gemm_two_cta; }
+int wm_set_option(const char* name, int value) {
+  if (!name) return WM_ERR_ARG;
+  const char* a = name;
+  const char* b = "gemm_two_cta";
+  while (*a && *a == *b) { ++a; ++b; }
+  if (*a || *b) return WM_ERR_ARG;
+  wm::g_gemm_two_cta = value;
+  return WM_OK;
+}
+
 int wm_rand_grid_x(int64_t numel) {
   int dev = 0, sms = 0, tpm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;

@@ -157,6 +157,66 @@ WM_DEVICE void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ---- cta_group::2 (CTA pair) variants: one MMA spans two SMs (M = 256), operands are split between the two
+// CTAs' shared memories, the accumulator rows between their TMEMs. Only the leader CTA (cluster rank 0) issues
+// MMAs and commits; both CTAs issue TMA loads that signal the LEADER's mbarrier. ----
+WM_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+WM_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) as seen in CTA `rank` of the cluster
+WM_DEVICE uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t a;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(p)), "r"(rank));
+  return a;
+}
+WM_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+template <uint32_t kCols>
+WM_DEVICE void tmem_alloc_2cta(uint32_t* smem_slot) {  // one warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_slot)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+template <uint32_t kCols>
+WM_DEVICE void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "n"(kCols) : "memory");
+}
+WM_DEVICE void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all earlier MMAs of this thread are done) on the barrier at this smem offset in BOTH CTAs
+WM_DEVICE void umma_commit_2cta(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+// 2-CTA TMA load: data lands in THIS CTA's smem, completion bytes are credited to the leader's mbarrier
+// (peer bit 24 of the shared::cluster address cleared, as cute::SM100_TMA_2SM_LOAD does)
+WM_DEVICE void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 // TMEM -> registers: lane t of the warp receives 32 / 16 consecutive fp32 columns of TMEM lane
 // (lane_base + t); lane_base must be 32*(warp_id % 4).
 WM_DEVICE void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {

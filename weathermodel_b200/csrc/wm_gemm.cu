@@ -306,6 +306,154 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// gemm_tn2: the same GEMM on CTA PAIRS (cta_group::2). One 256 x BN tile per pair: each CTA stages its own 128
+// rows of A and HALF of the B tile, so the B operand crosses L2 -> smem once per 256 rows instead of once per 128
+// (the single-CTA kernel is L2-feed bound at ~1.0-1.1 PFLOP/s). The leader CTA issues M = 256 MMAs and commits to
+// the barriers of both CTAs; each CTA's 8 epilogue warps drain their own 128 TMEM lanes.
+// ------------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                int M, int N, int K, int BN, int stages, GemmEpilogue ep) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int BNH = BN >> 1;  // B rows staged by each CTA
+  const uint32_t a_bytes = kBM * kBK * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(BNH) * kBK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(smem + static_cast<size_t>(stages) * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int m_tiles = (M + 2 * kBM - 1) / (2 * kBM);
+  const int n_tiles = (N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&tail->full[s], 1);
+      mbar_init(&tail->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tail->acc_full[s], 1);
+      mbar_init(&tail->acc_empty[s], 16);  // 8 epilogue warps in each of the two CTAs (leader's copy is used)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<kTmemCols>(&tail->tmem_base);
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = pair; t < total_tiles; t += npairs) {
+        const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&tail->empty[s], ph ^ 1u, 61);
+          uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
+          if (leader) mbar_arrive_expect_tx(&tail->full[s], 2 * stage_bytes);  // bytes of BOTH CTAs land here
+          tma_load_2d_2cta(sa, &tmA, &tail->full[s], kb * kBK, m_blk * 2 * kBM + static_cast<int>(rank) * kBM);
+          tma_load_2d_2cta(sa + a_bytes, &tmB, &tail->full[s], kb * kBK, n_blk * BN + static_cast<int>(rank) * BNH);
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc_bf16(2 * kBM, static_cast<uint32_t>(BN), 0, 0);
+      const uint64_t desc_a0 = umma_smem_desc(smem_u32(smem), 16, 1024, UMMA_SWZ_128B);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = pair; t < total_tiles; t += npairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1u;
+        mbar_wait(&tail->acc_empty[as], aph ^ 1u, 62);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&tail->full[s], ph, 63);
+          tc_fence_after();
+          const uint64_t da_s = umma_desc_advance(desc_a0, static_cast<uint32_t>(s) * stage_bytes);
+          const uint64_t db_s = umma_desc_advance(da_s, a_bytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_ss_2cta(d_tmem, umma_desc_advance(da_s, k * 32), umma_desc_advance(db_s, k * 32), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2cta(&tail->empty[s]);
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+        umma_commit_2cta(&tail->acc_full[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    const int half = ew >> 2;
+    const int cols_per = BN >> 1;
+    float* sbias = tail->bias[ew];
+    const bool wide = ((ep.ld_out | (ep.residual ? ep.ld_res : 0) | (ep.gate ? ep.ld_gate : 0)) & 15) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(ep.out) | reinterpret_cast<uintptr_t>(ep.residual) |
+                        reinterpret_cast<uintptr_t>(ep.gate)) & 31) == 0;
+    const uint32_t acc_empty_leader[2] = {mapa_u32(&tail->acc_empty[0], 0), mapa_u32(&tail->acc_empty[1], 0)};
+    int it = 0;
+    for (int t = pair; t < total_tiles; t += npairs, ++it) {
+      const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1u;
+      const int row = m_blk * 2 * kBM + static_cast<int>(rank) * kBM + q * 32 + lane;
+      const int n_base = n_blk * BN + half * cols_per;
+      if (ep.bias) {
+        __syncwarp();
+        for (int j = lane; j < cols_per; j += 32) sbias[j] = (n_base + j < N) ? __ldg(ep.bias + n_base + j) : 0.0f;
+        __syncwarp();
+      }
+      constexpr int kAuxDepth = 4;
+      EpiAux aux[kAuxDepth];
+#pragma unroll
+      for (int d = 0; d < kAuxDepth; ++d)
+        if (d * 16 < cols_per) epi_load_aux(aux[d], ep, row, n_base + d * 16, M, N, wide);
+      mbar_wait(&tail->acc_full[as], aph, 64);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + as * kAccStride + half * cols_per + (static_cast<uint32_t>(q * 32) << 16);
+      for (int cb = 0; cb < cols_per; cb += 16 * kAuxDepth) {
+#pragma unroll
+        for (int d = 0; d < kAuxDepth; ++d) {
+          const int c0 = cb + d * 16;
+          if (c0 < cols_per) {
+            uint32_t v[16];
+            tmem_ld16(tbase + c0, v);
+            tmem_ld_wait();
+            epi_process16<OutT>(v, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide);
+            if (c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc_empty_leader[as]);
+    }
+  }
+  __syncwarp();  // reconverge the single-lane role warps: barrier.cluster.*.aligned needs whole warps
+  tc_fence_before();
+  cluster_sync_all();  // no CTA may exit (or free TMEM) while its partner can still touch its smem / barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta<kTmemCols>(tmem_base);
+  }
+}
+
 // tile width: multiples of 32 up to 256; minimise tiles * (bn + ~32 columns of per-tile overhead), then the
 // padded column count, then prefer the wider tile
 static int pick_bn(int N) {
@@ -324,6 +472,7 @@ static int pick_bn(int N) {
   return best;
 }
 
+int g_gemm_two_cta = 1;  // wm_set_option("gemm_two_cta", 0) forces the single-CTA kernel (A/B comparisons, tests)
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -346,6 +495,22 @@ static int launch_gemm_tn_impl(const void* A, int lda, const void* B, int ldb, i
   if (rc) return rc;
   rc = make_tmap_bf16(&tmB, B, b_rows, K, ldb, kBK, BN);
   if (rc) return rc;
+  if (g_gemm_two_cta && !out_fp32 && M >= 1024 && (BN & 31) == 0 && bn_override >= 0) {
+    // CTA-pair path: 256 x BN tiles, each CTA stages 128 rows of A and BN/2 rows of B per k-block
+    rc = make_tmap_bf16(&tmB, B, b_rows, K, ldb, kBK, BN / 2);
+    if (rc) return rc;
+    const int stage2 = (kBM + BN / 2) * kBK * 2;
+    int st2 = (227 * 1024 - 2048 - static_cast<int>(sizeof(GemmSmemTail))) / stage2;
+    if (st2 > kMaxStages) st2 = kMaxStages;
+    const int smem2 = st2 * stage2 + static_cast<int>(sizeof(GemmSmemTail)) + 1024;
+    const int tiles2 = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + BN - 1) / BN);
+    const int pairs = min(tiles2, num_sms() / 2);
+    if (cudaFuncSetAttribute(gemm_tn2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2) != cudaSuccess)
+      return WM_ERR_CUDA;
+    gemm_tn2_kernel<__nv_bfloat16><<<2 * pairs, kGemmThreads, smem2, stream>>>(tmA, tmB, M, N, K, BN, st2, ep);
+    WM_COUNT_LAUNCH();
+    return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+  }
   const int stage_bytes = (kBM + BN) * kBK * 2;
   int stages = (227 * 1024 - 2048 - static_cast<int>(sizeof(GemmSmemTail))) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
