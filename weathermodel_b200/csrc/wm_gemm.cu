@@ -678,6 +678,9 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   out[static_cast<size_t>(r) * ld_out + c] = acc;
 }
 
+// Work items = output tiles x token splits, one per CTA, all the same size: pick the split count that fills whole
+// waves of SMs (the first plan used ceil(2 * SMs / tiles) and lost up to a third of the machine to a nearly empty
+// last wave: 300 items on 148 SMs = 3 waves at 68 %), with a mild preference for fewer partial tiles to reduce.
 int wgrad_plan(int Mtok, int Nout, int Kout, int* BN, int* splits, int* tok_per_split) {
   int bn;
   if (Kout <= 64) bn = 64;
@@ -685,14 +688,28 @@ int wgrad_plan(int Mtok, int Nout, int Kout, int* BN, int* splits, int* tok_per_
   else if (Kout % 192 == 0 || (Kout > 128 && Kout <= 192)) bn = 192;
   else bn = 256;
   const int tiles = ((Nout + kBM - 1) / kBM) * ((Kout + bn - 1) / bn);
-  int sp = (2 * num_sms() + tiles - 1) / tiles;  // ~2 waves of work items
   const int kb_total = (Mtok + kBK - 1) / kBK;
-  if (sp > kb_total) sp = kb_total;
-  if (sp < 1) sp = 1;
-  int kb_per = (kb_total + sp - 1) / sp;
-  sp = (kb_total + kb_per - 1) / kb_per;
+  const int sms = num_sms();
+  int best_sp = 1;
+  double best_score = -1.0;
+  for (int sp = 1; sp <= 48 && sp <= kb_total; ++sp) {
+    const int kb_per = (kb_total + sp - 1) / sp;
+    if (sp > 1 && kb_per < 16) break;  // keep the per-item prologue / epilogue amortised
+    const int sp_eff = (kb_total + kb_per - 1) / kb_per;
+    const long items = static_cast<long>(tiles) * sp_eff;
+    const long waves = (items + sms - 1) / sms;
+    // time ~ waves * k-blocks per item; normalise by the ideal tiles * kb_total / sms
+    const double t = static_cast<double>(waves) * kb_per;
+    const double ideal = static_cast<double>(tiles) * kb_total / sms;
+    const double score = ideal / t - 0.003 * sp_eff;
+    if (score > best_score) {
+      best_score = score;
+      best_sp = sp_eff;
+    }
+  }
+  const int kb_per = (kb_total + best_sp - 1) / best_sp;
   *BN = bn;
-  *splits = sp;
+  *splits = (kb_total + kb_per - 1) / kb_per;
   *tok_per_split = kb_per * kBK;
   return tiles;
 }
