@@ -75,10 +75,11 @@ typedef struct wm_gemm_epilogue {
 int wm_gemm_tn(const void* A_bf16, int lda, const void* B_bf16, int ldb, int M, int N, int K,
                const wm_gemm_epilogue* epilogue /* may be NULL */, void* out, int ld_out, int out_is_fp32,
                int tile_n /* 0 = auto */, void* stream);
-/* dW[Nout,Kout] (+)= A[Mtok,Nout]^T . B[Mtok,Kout]; workspace from wm_gemm_wgrad_workspace_bytes */
+/* dW[Nout,Kout] (+)= A[Mtok,Nout]^T . B[Mtok,Kout]; workspace from wm_gemm_wgrad_workspace_bytes.
+ * dbias (optional, [Nout]): column sums of A over the tokens (the bias gradient), fused into the same kernel. */
 size_t wm_gemm_wgrad_workspace_bytes(int Mtok, int Nout, int Kout);
 int wm_gemm_wgrad(const void* A_bf16, int lda, const void* B_bf16, int ldb, int Mtok, int Nout, int Kout,
-                  float* dW, int accumulate, float* workspace, void* stream);
+                  float* dW, int accumulate, float* workspace, float* dbias /* optional */, void* stream);
 /* hardware probe of the unswizzled UMMA operand layouts used by the attention kernels (tests only) */
 int wm_umma_probe(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int a_mn_major, int b_mn_major,
                   void* stream);

@@ -103,8 +103,9 @@ def test_gemm_wgrad(Mtok, Nout, Kout):
     out = ops.gemm_wgrad(a, b)
     ref = a.double().t() @ b.double()
     _cmp(f"wgrad {Mtok}x{Nout}x{Kout}", out, ref, 2e-3, 2e-3 * math.sqrt(Mtok))
-    out2 = ops.gemm_wgrad(a, b)
+    out2, db = ops.gemm_wgrad(a, b, want_bias_grad=True)
     assert torch.equal(out, out2), "split-K wgrad is not deterministic"
+    _cmp(f"wgrad bias {Mtok}x{Nout}", db, a.double().sum(0), 2e-3, 2e-3 * math.sqrt(Mtok))
 
 
 # ------------------------------------------------------------------------------------------ masks

@@ -40,7 +40,7 @@ SIGNATURES = {
     "wm_embed_fwd": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wm_gemm_tn": (_i, [_vp, _i, _vp, _i, _i, _i, _i, C.POINTER(GemmEpilogue), _vp, _i, _i, _i, _vp]),
     "wm_gemm_wgrad_workspace_bytes": (_sz, [_i, _i, _i]),
-    "wm_gemm_wgrad": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "wm_gemm_wgrad": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "wm_umma_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wm_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _u64, _u64, _vp]),
     "wm_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _u64, _u64, _vp]),

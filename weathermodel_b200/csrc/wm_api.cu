@@ -112,9 +112,9 @@ int wm_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int
 }
 size_t wm_gemm_wgrad_workspace_bytes(int Mtok, int Nout, int Kout) { return wgrad_workspace_bytes(Mtok, Nout, Kout); }
 int wm_gemm_wgrad(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout, float* dW,
-                  int accumulate, float* workspace, void* stream) {
+                  int accumulate, float* workspace, float* dbias, void* stream) {
   if (!A || !B || !dW || !workspace) return WM_ERR_ARG;
-  return launch_gemm_wgrad(A, lda, B, ldb, Mtok, Nout, Kout, dW, accumulate, workspace, S_(stream));
+  return launch_gemm_wgrad(A, lda, B, ldb, Mtok, Nout, Kout, dW, accumulate, workspace, dbias, S_(stream));
 }
 int wm_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_mn, int b_mn, void* stream) {
   if (!A || !B || !D) return WM_ERR_ARG;

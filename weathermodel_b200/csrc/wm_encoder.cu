@@ -364,12 +364,8 @@ int wm_encoder_backward_head(wm_encoder* e, const void* dY_, float* grads, void*
   const wm_encoder_config& c = e->cfg;
   const __nv_bfloat16* dY = reinterpret_cast<const __nv_bfloat16*>(dY_);
   const int M = static_cast<int>(e->M), D = c.D;
-  WM_TRY(launch_colsum(dY, e->outP, M, e->outP, e->scratch, e->scratch + 64, st));
-  if (cudaMemcpyAsync(grads + e->lay.b_out, e->scratch, c.out_dim * sizeof(float), cudaMemcpyDeviceToDevice, st) !=
-      cudaSuccess)
-    return WM_ERR_CUDA;
   WM_TRY(launch_gemm_wgrad_ex(dY, e->outP, e->x_final, D, M, e->outP, D, grads + e->lay.w_out, c.out_dim, D, D,
-                              e->scratch, st));
+                              e->scratch, grads + e->lay.b_out, st));
   GemmEpilogue ep;
   ep.out = e->gX;
   ep.ld_out = D;
@@ -397,7 +393,7 @@ int wm_encoder_backward_layers(wm_encoder* e, const float* params, int layer_hi,
                                 grads + q.g2, grads + q.be2, grads + q.b2, M, D, thr, dscale, e->seed,
                                 stream_id(e->step, l, 3), e->scratch, st));
     // dW2 [D, FF] = gF^T h
-    WM_TRY(launch_gemm_wgrad(gFd, D, a.h, FF, M, D, FF, grads + q.w2, 0, e->scratch, st));
+    WM_TRY(launch_gemm_wgrad(gFd, D, a.h, FF, M, D, FF, grads + q.w2, 0, e->scratch, nullptr, st));
     {  // d h_pre = (gF W2) * [h > 0] / (1 - p)
       GemmEpilogue ep;
       ep.gate = a.h;
@@ -407,8 +403,7 @@ int wm_encoder_backward_layers(wm_encoder* e, const float* params, int layer_hi,
       ep.ld_out = FF;
       WM_TRY(launch_gemm_tn(gFd, D, e->wt[l].w2_t, D, M, FF, D, ep, 0, 0, st));
     }
-    WM_TRY(launch_colsum(e->gH, FF, M, FF, grads + q.b1, e->scratch, st));
-    WM_TRY(launch_gemm_wgrad(e->gH, FF, a.u, D, M, FF, D, grads + q.w1, 0, e->scratch, st));
+    WM_TRY(launch_gemm_wgrad(e->gH, FF, a.u, D, M, FF, D, grads + q.w1, 0, e->scratch, grads + q.b1, st));
     {  // d u = gH W1 + d r2
       GemmEpilogue ep;
       ep.residual = e->gR;
@@ -421,7 +416,7 @@ int wm_encoder_backward_layers(wm_encoder* e, const float* params, int layer_hi,
     WM_TRY(launch_layernorm_bwd(e->gU, a.r1, params + q.g1, a.mean1, a.rstd1, e->gR, thr ? e->gF : nullptr,
                                 grads + q.g1, grads + q.be1, grads + q.b_o, M, D, thr, dscale, e->seed,
                                 stream_id(e->step, l, 1), e->scratch, st));
-    WM_TRY(launch_gemm_wgrad(gFd, D, a.ctx, D, M, D, D, grads + q.w_o, 0, e->scratch, st));
+    WM_TRY(launch_gemm_wgrad(gFd, D, a.ctx, D, M, D, D, grads + q.w_o, 0, e->scratch, nullptr, st));
     {  // d ctx = gF W_o
       GemmEpilogue ep;
       ep.out = e->gC;
@@ -430,8 +425,7 @@ int wm_encoder_backward_layers(wm_encoder* e, const float* params, int layer_hi,
     }
     WM_TRY(launch_attn_bwd(a.qkv, a.ctx, e->gC, a.lse, e->gQKV, c.B, c.S, c.H, dh, thr, dscale, e->seed,
                            stream_id(e->step, l, 0), st));
-    WM_TRY(launch_colsum(e->gQKV, 3 * D, M, 3 * D, grads + q.b_qkv, e->scratch, st));
-    WM_TRY(launch_gemm_wgrad(e->gQKV, 3 * D, a.x, D, M, 3 * D, D, grads + q.w_qkv, 0, e->scratch, st));
+    WM_TRY(launch_gemm_wgrad(e->gQKV, 3 * D, a.x, D, M, 3 * D, D, grads + q.w_qkv, 0, e->scratch, grads + q.b_qkv, st));
     {  // d x_l = gQKV W_qkv + d r1
       GemmEpilogue ep;
       ep.residual = e->gR;
@@ -450,9 +444,8 @@ int wm_encoder_backward_embed(wm_encoder* e, float* grads, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const wm_encoder_config& c = e->cfg;
   const int M = static_cast<int>(e->M), D = c.D, Fin = c.F + 3;
-  WM_TRY(launch_colsum(e->gX, D, M, D, grads + e->lay.b_in, e->scratch, st));
   WM_TRY(launch_gemm_wgrad_ex(e->gX, D, e->xin, kXinCols, M, D, kXinCols, grads + e->lay.w_in, D, Fin, Fin,
-                              e->scratch, st));
+                              e->scratch, grads + e->lay.b_in, st));
   return WM_OK;
 }
 

@@ -555,12 +555,18 @@ struct WgSmemTail {
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  int Mtok, int Nout, int Kout, int BN, int tok_per_split, float* __restrict__ partial) {
+                  int Mtok, int Nout, int Kout, int BN, int tok_per_split, float* __restrict__ partial,
+                  float* __restrict__ bias_partial) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_bytes = kBM * kBK * 2;                             // 2 boxes of 64 tok x 64 n
   const uint32_t b_bytes = static_cast<uint32_t>(BN) * kBK * 2;       // BN/64 boxes
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  // Fused bias gradient (column sums of A over the tokens): an all-ones 64 x 64 chunk sits right behind the B
+  // tile of every stage, so the k_blk == 0 CTAs simply run their MMAs 16 columns wider (N = BN + 16) and find
+  // sum_t A[t, n] in accumulator column BN -- no separate pass over the activation gradient.
+  const bool fuse_bias = bias_partial != nullptr;
+  const uint32_t ones_bytes = fuse_bias ? 8192u : 0u;
+  const uint32_t stage_bytes = a_bytes + b_bytes + ones_bytes;
   WgSmemTail* tail = reinterpret_cast<WgSmemTail*>(smem + static_cast<size_t>(kWgStages) * stage_bytes);
 
   const int warp = threadIdx.x >> 5;
@@ -583,6 +589,12 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<256>(&tail->tmem_base);
+  if (fuse_bias && k_blk == 0) {
+    const uint4 ones = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);  // bf16 1.0 x 8
+    for (int i = threadIdx.x; i < kWgStages * 512; i += blockDim.x)
+      *reinterpret_cast<uint4*>(smem + static_cast<size_t>(i >> 9) * stage_bytes + a_bytes + b_bytes + (i & 511) * 16) = ones;
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -595,7 +607,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&tail->empty[s], ph ^ 1u, 21);
         uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
-        mbar_arrive_expect_tx(&tail->full[s], stage_bytes);
+        mbar_arrive_expect_tx(&tail->full[s], a_bytes + b_bytes);
         const int t = tok0 + kb * kBK;
         // NOTE: token rows past tok1 but < Mtok would belong to the next split; tok_per_split is a
         // multiple of 64 so a box never straddles a split boundary; rows >= Mtok are zero-filled.
@@ -608,7 +620,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kBM, static_cast<uint32_t>(BN), 1, 1);
+      const uint32_t idesc = umma_idesc_bf16(kBM, static_cast<uint32_t>(BN + (fuse_bias && k_blk == 0 ? 16 : 0)), 1, 1);
       // MN-major SW128: 64-wide MN chunks LBO = 8192 B apart, 8-token groups SBO = 1024 B apart
       const uint64_t desc_a0 = umma_smem_desc(smem_u32(smem), 8192, 1024, UMMA_SWZ_128B);
       int s = 0;
@@ -655,6 +667,16 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
+    if (fuse_bias && k_blk == 0) {
+      uint32_t v[16];
+      if (num_kb > 0) {
+        tmem_ld16(tmem_base + BN + (static_cast<uint32_t>(q * 32) << 16), v);
+        tmem_ld_wait();
+      } else {
+        v[0] = 0u;
+      }
+      if (row < Nout) bias_partial[static_cast<size_t>(split) * Nout + row] = __uint_as_float(v[0]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -681,6 +703,15 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 // Work items = output tiles x token splits, one per CTA, all the same size: pick the split count that fills whole
 // waves of SMs (the first plan used ceil(2 * SMs / tiles) and lost up to a third of the machine to a nearly empty
 // last wave: 300 items on 148 SMs = 3 waves at 68 %), with a mild preference for fewer partial tiles to reduce.
+__global__ void wgrad_bias_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int Nout,
+                                         int rows_valid, int splits) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows_valid) return;
+  float acc = 0.0f;
+  for (int s = 0; s < splits; ++s) acc += partial[static_cast<size_t>(s) * Nout + r];
+  out[r] = acc;
+}
+
 int wgrad_plan(int Mtok, int Nout, int Kout, int* BN, int* splits, int* tok_per_split) {
   int bn;
   if (Kout <= 64) bn = 64;
@@ -717,12 +748,15 @@ int wgrad_plan(int Mtok, int Nout, int Kout, int* BN, int* splits, int* tok_per_
 size_t wgrad_workspace_bytes(int Mtok, int Nout, int Kout) {
   int bn, sp, tps;
   wgrad_plan(Mtok, Nout, Kout, &bn, &sp, &tps);
-  return static_cast<size_t>(sp) * Nout * Kout * sizeof(float);
+  size_t bytes = static_cast<size_t>(sp) * Nout * Kout * sizeof(float) + static_cast<size_t>(sp) * Nout * sizeof(float);
+  // fallback path of the fused bias gradient (BN == 256): column-sum workspace + one row of results
+  const size_t cs = colsum_workspace_bytes(Mtok, Nout) + static_cast<size_t>(Nout) * sizeof(float);
+  return bytes > cs ? bytes : cs;
 }
 
 static int launch_gemm_wgrad_impl(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout,
                                   float* dW, int rows_valid, int cols_valid, int ld_dw, int accumulate,
-                                  float* workspace, cudaStream_t stream) {
+                                  float* workspace, float* dbias, cudaStream_t stream) {
   if (Mtok <= 0 || Nout <= 0 || Kout <= 0) return WM_ERR_SHAPE;
   if (rows_valid > Nout || cols_valid > Kout || ld_dw < cols_valid) return WM_ERR_SHAPE;
   if ((Nout & 7) || (Kout & 7) || (lda & 7) || (ldb & 7)) return WM_ERR_ALIGN;
@@ -733,12 +767,14 @@ static int launch_gemm_wgrad_impl(const void* A, int lda, const void* B, int ldb
   if (rc) return rc;
   rc = make_tmap_bf16(&tmB, B, Mtok, Kout, ldb, 64, kBK);
   if (rc) return rc;
-  const int stage_bytes = (kBM + BN) * kBK * 2;
+  const bool fuse = dbias != nullptr && BN + 16 <= 256;
+  float* bias_partial = fuse ? workspace + static_cast<size_t>(splits) * Nout * Kout : nullptr;
+  const int stage_bytes = (kBM + BN) * kBK * 2 + (fuse ? 8192 : 0);
   const int smem = kWgStages * stage_bytes + static_cast<int>(sizeof(WgSmemTail)) + 1024;
   if (cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return WM_ERR_CUDA;
   dim3 grid((Nout + kBM - 1) / kBM, (Kout + BN - 1) / BN, splits);
-  gemm_wgrad_kernel<<<grid, kWgradThreads, smem, stream>>>(tmA, tmB, Mtok, Nout, Kout, BN, tps, workspace);
+  gemm_wgrad_kernel<<<grid, kWgradThreads, smem, stream>>>(tmA, tmB, Mtok, Nout, Kout, BN, tps, workspace, bias_partial);
   WM_COUNT_LAUNCH();
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
   const int64_t n = static_cast<int64_t>(rows_valid) * cols_valid;
@@ -747,17 +783,34 @@ static int launch_gemm_wgrad_impl(const void* A, int lda, const void* B, int ldb
   wgrad_reduce_kernel<<<blocks, threads, 0, stream>>>(workspace, dW, Nout, Kout, rows_valid, cols_valid, ld_dw,
                                                       splits, accumulate);
   WM_COUNT_LAUNCH();
+  if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
+  if (dbias) {
+    if (fuse) {
+      wgrad_bias_reduce_kernel<<<(rows_valid + 255) / 256, 256, 0, stream>>>(bias_partial, dbias, Nout, rows_valid, splits);
+      WM_COUNT_LAUNCH();
+    } else {  // 256-wide tiles leave no room for the ones chunk: separate column-sum pass (stream-ordered reuse of
+              // the workspace: the partials above have been consumed by wgrad_reduce)
+      float* tmp = workspace + colsum_workspace_bytes(Mtok, Nout) / sizeof(float);
+      const int rc2 = launch_colsum(reinterpret_cast<const __nv_bfloat16*>(A), lda, Mtok, Nout, tmp, workspace, stream);
+      if (rc2) return rc2;
+      if (cudaMemcpyAsync(dbias, tmp, static_cast<size_t>(rows_valid) * sizeof(float), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+        return WM_ERR_CUDA;
+      return WM_OK;
+    }
+  }
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 int launch_gemm_wgrad(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout, float* dW,
-                      int accumulate, float* workspace, cudaStream_t stream) {
-  return launch_gemm_wgrad_impl(A, lda, B, ldb, Mtok, Nout, Kout, dW, Nout, Kout, Kout, accumulate, workspace, stream);
+                      int accumulate, float* workspace, float* dbias, cudaStream_t stream) {
+  return launch_gemm_wgrad_impl(A, lda, B, ldb, Mtok, Nout, Kout, dW, Nout, Kout, Kout, accumulate, workspace, dbias,
+                                stream);
 }
 // only the top-left [rows_valid, cols_valid] block of the product is written, with row pitch ld_dw
 int launch_gemm_wgrad_ex(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout, float* dW,
-                         int rows_valid, int cols_valid, int ld_dw, float* workspace, cudaStream_t stream) {
+                         int rows_valid, int cols_valid, int ld_dw, float* workspace, float* dbias,
+                         cudaStream_t stream) {
   return launch_gemm_wgrad_impl(A, lda, B, ldb, Mtok, Nout, Kout, dW, rows_valid, cols_valid, ld_dw, 0, workspace,
-                                stream);
+                                dbias, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -40,10 +40,12 @@ int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N,
 int launch_gemm_tn_rows(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int b_rows,
                         const GemmEpilogue& ep, int out_fp32, cudaStream_t stream);
 int launch_gemm_wgrad_ex(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout, float* dW,
-                         int rows_valid, int cols_valid, int ld_dw, float* workspace, cudaStream_t stream);
+                         int rows_valid, int cols_valid, int ld_dw, float* workspace, float* dbias,
+                         cudaStream_t stream);
 size_t wgrad_workspace_bytes(int Mtok, int Nout, int Kout);
+// dbias (optional): column sums of A over the tokens = bias gradient of the layer whose output gradient A is
 int launch_gemm_wgrad(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout,
-                      float* dW, int accumulate, float* workspace, cudaStream_t stream);
+                      float* dW, int accumulate, float* workspace, float* dbias, cudaStream_t stream);
 int launch_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_mn, int b_mn,
                       cudaStream_t stream);
 

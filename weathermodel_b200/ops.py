@@ -121,16 +121,18 @@ def gemm_tn(a, b, bias=None, relu=False, dropout_p=0.0, seed=0, stream_id=0, gat
     return out
 
 
-def gemm_wgrad(a, b, accumulate_into=None):
-    """dW[Nout,Kout] = a[Mtok,Nout]^T @ b[Mtok,Kout] (fp32 out, deterministic split-K)."""
+def gemm_wgrad(a, b, accumulate_into=None, want_bias_grad=False):
+    """dW[Nout,Kout] = a[Mtok,Nout]^T @ b[Mtok,Kout] (fp32 out, deterministic split-K); optionally also
+    db[Nout] = a.sum(0) from the same kernel."""
     _cuda(a, b)
     Mtok, Nout = a.shape
     Kout = b.shape[1]
     ws = torch.empty(lib().wm_gemm_wgrad_workspace_bytes(Mtok, Nout, Kout) // 4, dtype=torch.float32, device=a.device)
     out = accumulate_into if accumulate_into is not None else torch.empty((Nout, Kout), dtype=torch.float32, device=a.device)
+    db = torch.empty(Nout, dtype=torch.float32, device=a.device) if want_bias_grad else None
     check(lib().wm_gemm_wgrad(_p(a), a.stride(0), _p(b), b.stride(0), Mtok, Nout, Kout, _p(out),
-                              int(accumulate_into is not None), _p(ws), _stream()), "wm_gemm_wgrad")
-    return out
+                              int(accumulate_into is not None), _p(ws), _p(db), _stream()), "wm_gemm_wgrad")
+    return (out, db) if want_bias_grad else out
 
 
 def umma_probe(a, b, a_mn=False, b_mn=False):
