@@ -213,6 +213,20 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     }
   } else {
   uint32_t ph_s = 0, ph_o = 0;
+  // Dropout keep masks of a whole query tile (8 Philox blocks per thread) are generated while the thread would
+  // otherwise sit in an mbarrier wait (first tile: under the score MMAs; later tiles: under the previous PV).
+  uint32_t kmask[8][4];
+  auto gen_masks = [&](int it) {
+    if (!DROP || grp >= ntq) return;
+    const int qq = it * 128 + row;
+    const uint64_t rowbase = (static_cast<uint64_t>(bh) * S + (qq < S ? qq : 0)) * nk16;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int k0 = grp * 128 + c * 16;
+      if (k0 < nk16 * 16) keep_masks16(seed, stream_id, rowbase + (k0 >> 4), thresh4, kmask[c]);
+    }
+  };
+  gen_masks(0);
   for (int it = 0; it < ntq; ++it) {
     const int q = it * 128 + row;
     const bool qvalid = q < S;
@@ -250,15 +264,14 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     // ---- pass 2: exp2, row sum, dropout, P -> smem (bf16, K-major over keys)
     float lsum = 0.0f;
     if (grp < ntq) {
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 16) {
         const int k0 = grp * 128 + c0;
         if (k0 >= nk16 * 16) break;
         uint32_t v[16];
         tmem_ld16(tS + lane_sel + k0, v);
         tmem_ld_wait();
-        uint32_t km[4];
-        if (DROP) keep_masks16(seed, stream_id, (static_cast<uint64_t>(bh) * S + (qvalid ? q : 0)) * nk16 + (k0 >> 4), thresh4, km);
+        const uint32_t(&km)[4] = kmask[c0 >> 4];
         uint32_t pb[16];  // P as fp32 bit patterns (masked by the keep decision)
         if (k0 + 16 <= S) {
 #pragma unroll
@@ -294,6 +307,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     tc_fence_before();
     __syncthreads();
     if (warp == 0) WM_TICK(9 + it * 8);
+    if (it + 1 < ntq) gen_masks(it + 1);
     mbar_wait(&bar_o, ph_o, 43);
     ph_o ^= 1u;
     tc_fence_after();
@@ -511,6 +525,15 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
     for (int j = 0; j < nt; ++j) {
       for (int i = 0; i < nt; ++i) {
         if (warp == 0 && j == 0) WM_TICK(35 + i * 3);
+        // this pair's dropout masks (2 Philox blocks per thread) are generated under the MMA wait below
+        uint32_t kmA[4], kmB[4];
+        if (DROP) {
+          const int qq = i * 128 + row;
+          const uint64_t rowbase = (static_cast<uint64_t>(bh) * S + (qq < S ? qq : 0)) * grp_per_row;
+          const int kk = j * 128 + grp * 32;
+          keep_masks16(seed, stream_id, rowbase + (kk >> 4), thresh4, kmA);
+          keep_masks16(seed, stream_id, rowbase + (kk >> 4) + 1, thresh4, kmB);
+        }
         mbar_wait(&bar, phase, 51);  // S/dP of (j, i) ready; every earlier product has completed as well
         phase ^= 1u;
         tc_fence_after();
@@ -528,7 +551,10 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
           tmem_ld16(tdP + lane_sel + c0, vd);
           tmem_ld_wait();
           uint32_t km[4];
-          if (DROP) keep_masks16(seed, stream_id, (static_cast<uint64_t>(bh) * S + (q < S ? q : 0)) * grp_per_row + (k0 >> 4), thresh4, km);
+          if (DROP) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) km[w] = hh ? kmB[w] : kmA[w];
+          }
           float pp[16], ds[16];
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) {
