@@ -105,9 +105,15 @@ WM_DEVICE void keep_masks16(uint64_t seed, uint64_t stream, uint64_t grp, uint32
   m[2] = __vcmpgeu4(r.z, thresh4);
   m[3] = __vcmpgeu4(r.w, thresh4);
 }
+// pins a value in a register at this point of the instruction stream: without it the compiler sinks the (pure)
+// Philox arithmetic below the mbarrier wait it is supposed to overlap with
+#define WM_PIN(x) asm volatile("" : "+r"(x))
 // all-ones / all-zeros 32-bit mask of element j (0..15) of the group
 #define WM_KEEP32(m, j) __byte_perm((m)[(j) >> 2], 0u, 0x1111u * ((j) & 3))
 
+WM_DEVICE void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 WM_DEVICE float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -137,6 +143,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   uint8_t* sP = sV + kSP * DHP * 2;
   float* sMax = reinterpret_cast<float*>(sP + 128 * kSP * 2);  // [3][128]
   float* sSum = sMax + 3 * 128;                                 // [3][128]
+  uint8_t* sOut = reinterpret_cast<uint8_t*>(sSum + 3 * 128);   // [128][dh] bf16 output staging
   __shared__ uint64_t bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
 
@@ -223,7 +230,10 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const int k0 = grp * 128 + c * 16;
-      if (k0 < nk16 * 16) keep_masks16(seed, stream_id, rowbase + (k0 >> 4), thresh4, kmask[c]);
+      if (k0 < nk16 * 16) {
+        keep_masks16(seed, stream_id, rowbase + (k0 >> 4), thresh4, kmask[c]);
+        WM_PIN(kmask[c][0]); WM_PIN(kmask[c][1]); WM_PIN(kmask[c][2]); WM_PIN(kmask[c][3]);
+      }
     }
   };
   gen_masks(0);
@@ -312,25 +322,37 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     ph_o ^= 1u;
     tc_fence_after();
     if (warp == 0) WM_TICK(10 + it * 8);
-    // ---- epilogue: warp group g writes head-dim columns [16g, 16g+16)
+    // ---- epilogue: warp group g scales head-dim columns [16g, 16g+16) of its row and parks them in a compact
+    // [rows, dh] staging tile; the tile then leaves with row-contiguous 8-byte pieces (about 3 rows per warp
+    // store instead of 32 different rows: thread-per-row global stores cost ~1 LSU cycle per 32-byte sector)
+    const float tot = sSum[row] + sSum[128 + row] + sSum[256 + row];
     if (grp * 16 < DHP) {
-      const float tot = sSum[row] + sSum[128 + row] + sSum[256 + row];
       const float inv = drop_scale / tot;
       uint32_t v[16];
       tmem_ld16(tO + lane_sel + grp * 16, v);
       tmem_ld_wait();
-      if (qvalid) {
-        __nv_bfloat16* orow = ctx + (static_cast<size_t>(b) * S + q) * D + h * dh + grp * 16;
+      uint8_t* srow = sOut + row * (dh * 2) + grp * 32;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          if (grp * 16 + j < dh) {  // dh % 4 == 0
-            uint2 pk;
-            pk.x = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
-            pk.y = pack_bf16x2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
-            *reinterpret_cast<uint2*>(orow + j) = pk;
-          }
+      for (int j = 0; j < 16; j += 4) {
+        if (grp * 16 + j < dh) {  // dh % 4 == 0
+          uint2 pk;
+          pk.x = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+          pk.y = pack_bf16x2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+          *reinterpret_cast<uint2*>(srow + j * 2) = pk;
         }
-        if (grp == 0 && lse_out) lse_out[static_cast<size_t>(bh) * S + q] = mrow * scale + logf(tot);
+      }
+      if (grp == 0 && qvalid && lse_out) lse_out[static_cast<size_t>(bh) * S + q] = mrow * scale + logf(tot);
+    }
+    named_bar_sync(1, kFwdThreads - 32);
+    {
+      const int pv = dh >> 2;
+      const int nrows = min(128, S - it * 128);
+      const float inv_pv = 1.0f / static_cast<float>(pv);
+      __nv_bfloat16* obase = ctx + (static_cast<size_t>(b) * S + it * 128) * D + h * dh;
+      for (int i = tid; i < nrows * pv; i += kFwdThreads - 32) {
+        const int r = static_cast<int>((static_cast<float>(i) + 0.5f) * inv_pv);
+        const int pp = i - r * pv;
+        *reinterpret_cast<uint2*>(obase + static_cast<size_t>(r) * D + pp * 4) = *reinterpret_cast<const uint2*>(sOut + i * 8);
       }
     }
     if (warp == 0) WM_TICK(11 + it * 8);
@@ -533,6 +555,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
           const int kk = j * 128 + grp * 32;
           keep_masks16(seed, stream_id, rowbase + (kk >> 4), thresh4, kmA);
           keep_masks16(seed, stream_id, rowbase + (kk >> 4) + 1, thresh4, kmB);
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { WM_PIN(kmA[w]); WM_PIN(kmB[w]); }
         }
         mbar_wait(&bar, phase, 51);  // S/dP of (j, i) ready; every earlier product has completed as well
         phase ^= 1u;
@@ -622,7 +646,7 @@ template <int DHP>
 static int launch_fwd_t(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, int B, int S, int H, int dh,
                         float scale, uint32_t thresh8, float dscale, uint64_t seed, uint64_t stream_id,
                         cudaStream_t stream) {
-  const int smem = 3 * kSP * DHP * 2 + 128 * kSP * 2 + 6 * 128 * 4 + 256;
+  const int smem = 3 * kSP * DHP * 2 + 128 * kSP * 2 + 6 * 128 * 4 + 128 * DHP * 2 + 256;
   auto kern = thresh8 ? attn_fwd_kernel<DHP, true> : attn_fwd_kernel<DHP, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
   kern<<<B * H, kFwdThreads, smem, stream>>>(qkv, ctx, lse, S, H, dh, scale, thresh8, dscale, seed, stream_id);
