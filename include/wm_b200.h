@@ -35,7 +35,7 @@ int wm_device_error(void);
 long long wm_launch_count(void);
 /* debug: clock64() timestamps that CTA 0 of the attention kernels records at its phase boundaries (HOST pointer) */
 int wm_debug_ticks(long long* out_host, int n);
-/* tuning switches (tests / A-B measurements): "gemm_two_cta" = 1 (default) uses the cta_group::2 GEMM for M >= 1024 */
+/* tuning switches (tests / A-B measurements): "gemm_two_cta" = 1 selects the cta_group::2 GEMM for M >= 1024 (default 0) */
 int wm_set_option(const char* name, int value);
 /* torch.rand grid size for `numel` elements on the current device
  * (torch:include/ATen/native/cuda/DistributionTemplates.h:50-63 calc_execution_policy). */

@@ -63,6 +63,26 @@ def test_gemm_tn_plain(M, N, K, tile_n):
     _cmp(f"gemm_tn {M}x{N}x{K}", out, ref, 1e-2, 1e-2)
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 576, 576), (4099, 1728, 576), (2048, 2304, 192), (1500, 192, 2304)])
+def test_gemm_cta_pair_kernel_is_bit_identical(M, N, K):
+    """The cta_group::2 kernel (256-row tiles over two SMs) must reproduce the single-CTA kernel exactly."""
+    from weathermodel_b200._lib import lib
+
+    a = _bf(M, K, seed=30)
+    b = _bf(N, K, scale=K ** -0.5, seed=31)
+    bias = torch.randn(N, device="cuda")
+    res = _bf(M, N, seed=32)
+    try:
+        lib().wm_set_option(b"gemm_two_cta", 0)
+        ref = ops.gemm_tn(a, b, bias=bias, relu=True, residual=res)
+        lib().wm_set_option(b"gemm_two_cta", 1)
+        got = ops.gemm_tn(a, b, bias=bias, relu=True, residual=res)
+    finally:
+        lib().wm_set_option(b"gemm_two_cta", 0)
+    assert torch.equal(ref, got)
+    _cmp("cta-pair gemm", got, torch.relu(a.float() @ b.float().t() + bias) + res.float(), 1e-2, 2e-2)
+
+
 def test_gemm_tn_epilogues():
     M, N, K = 777, 576, 576
     a = _bf(M, K, seed=5)

@@ -472,7 +472,8 @@ static int pick_bn(int N) {
   return best;
 }
 
-int g_gemm_two_cta = 1;  // wm_set_option("gemm_two_cta", 0) forces the single-CTA kernel (A/B comparisons, tests)
+int g_gemm_two_cta = 0;  // wm_set_option("gemm_two_cta", 1) selects the CTA-pair kernel: bit-identical, measured 0-9 % slower on
+                          // this model's shapes (tools/gemm_ab.py), so the single-CTA kernel stays the default
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
