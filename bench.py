@@ -268,7 +268,7 @@ def run_ours(args, rank, world, local_rank):
         achieved = 2.0 * M * FF * D / (gemm_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tn_kernel<bf16> (linear1: M x 4D x D, bias+ReLU epilogue)",
                 "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
-                "traffic": None, "peak_source": pk["source"] + " burst (kernel timed alone)",
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((M, FF, D)), "peak_source": pk["source"] + " burst (kernel timed alone)",
                 "launch_ms": gemm_ms, "shape": [M, FF, D]}
         also["step_tensor_frac_of_sustained"] = (value / world) * flops_seq / (pk["tf_sustained"] * 1e12)
         also["algorithmic_gflop_per_seq"] = flops_seq / 1e9
@@ -305,6 +305,11 @@ def run_ours(args, rank, world, local_rank):
         }
         line.update(also)
         print(json.dumps(line), flush=True)
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the one `ncu --set full`
+# capture kept under profiles/ (r01_gemm_lin1_full.txt); keyed by the GEMM shape it was taken on, null for the others.
+NCU_DRAM_BYTES_PER_LAUNCH = {(186880, 2304, 576): 218345472 + 811393536}
 
 
 def main():

@@ -1,0 +1,107 @@
+"""Yield fine-tune path (BASELINE config 5): dataset semantics on CPU, end-to-end CLI on a B200."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SOIL = ["bdod", "cec", "cfvo", "clay", "nitrogen", "ocd", "ocs", "phh2o", "sand", "silt", "soc"]
+DEPTHS = ["0-5cm", "5-15cm", "15-30cm", "30-60cm", "60-100cm", "100-200cm"]
+
+
+def synthetic_yield_csv(path, n_counties=12, years=range(1995, 2019), seed=0):
+    """CSV in the khaki_multi_crop_yield.csv layout: one row per (county, year)."""
+    rs = np.random.RandomState(seed)
+    rows = []
+    for loc in range(n_counties):
+        lat, lng = rs.uniform(30, 48), rs.uniform(-100, -80)
+        for y in years:
+            r = {"loc_ID": loc, "year": y, "State": "S", "County": f"C{loc}", "lat": lat, "lng": lng,
+                 "soybean_yield": 45 + 8 * rs.randn()}
+            w = rs.randn(6, 52) * 3 + 10
+            for i in range(6):
+                for j in range(52):
+                    r[f"W_{i + 1}_{j + 1}"] = w[i, j]
+            for i in range(14):
+                r[f"P_{i + 1}"] = rs.rand()
+            for m in SOIL:
+                for d in DEPTHS:
+                    r[f"{m}_mean_{d}"] = rs.rand()
+            rows.append(r)
+    df = pd.DataFrame(rows)
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    df.to_csv(path, index=False)
+    return df
+
+
+def test_crop_dataset_sample_semantics(tmp_path):
+    from src.crop_yield.dataloader.yield_dataloader import CropDataset, WEATHER_INDICES, get_train_test_loaders
+
+    df = synthetic_yield_csv(str(tmp_path / "d.csv"), n_counties=4, years=range(2000, 2012))
+    df = df.sort_values(["loc_ID", "year"])
+    n_past = 3
+    ds = CropDataset(df.copy(), start_year=2005, test_year=2010, test_dataset=False, n_past_years=n_past)
+    # literal restatement of the reference sample construction for every candidate
+    want = df[(df["year"] >= 2005) & (df["year"] < 2010)]
+    assert len(ds) == len(want) == 4 * 5
+    for k, (_, row) in enumerate(want.iterrows()):
+        q = df[(df["year"] <= row["year"]) & (df["loc_ID"] == row["loc_ID"])].tail(n_past + 1)
+        wcols = [f"W_{i}_{j}" for i in range(1, 7) for j in range(1, 53)]
+        weather = q[wcols].values.astype("float32").reshape(-1, 6, 52).transpose(0, 2, 1).reshape(-1, 6)
+        padded, coord, year, interval, mask, practices, soil, y_past, y = ds[k]
+        assert padded.shape == (4 * 52, 31) and mask.shape == (4 * 52, 31)
+        assert np.array_equal(padded[:, WEATHER_INDICES].numpy(), weather)
+        rest = [c for c in range(31) if c not in WEATHER_INDICES]
+        assert (padded[:, rest] == 0).all() and mask[:, rest].all() and not mask[:, WEATHER_INDICES].any()
+        exp_year = (torch.tensor(q["year"].values.astype("float32")).unsqueeze(1)
+                    + torch.arange(1, 53, dtype=torch.float32).unsqueeze(0) / 52).reshape(-1)
+        assert torch.equal(year, exp_year) and interval.item() == 7.0
+        yy = q["soybean_yield"].values.astype("float32")
+        assert y.item() == yy[-1] and y_past[-1] == yy[-2] and np.array_equal(y_past[:-1], yy[:-1])
+        assert np.allclose(coord.numpy(), q[["lat", "lng"]].values.astype("float32")[0])
+    with pytest.raises(ValueError):
+        CropDataset(df.copy(), 2005, 2010, n_past_years=7)  # 8 * 52 > 365
+    tr, te = get_train_test_loaders(df, n_train_years=4, test_year=2010, n_past_years=3, batch_size=5, shuffle=False,
+                                    num_workers=0, crop_type="soybean", country="usa")
+    b = next(iter(tr))
+    assert len(b) == 9 and b[0].shape == (5, 208, 31) and b[4].dtype == torch.bool and b[8].shape == (5, 1)
+    assert len(te.dataset) == 4
+
+
+def test_yield_models_build_and_share_the_encoder_classes():
+    from src.crop_yield.models.weatherbert_yield_model import WeatherBERTYieldModel
+    from src.crop_yield.models.weatherformer_yield_model import WeatherFormerYieldModel
+    from src.pretraining.models.weatherformer import WeatherFormer
+
+    hp = dict(num_heads=4, num_layers=2, hidden_dim_factor=12)
+    m = WeatherFormerYieldModel("weatherformer_soybean_yield", torch.device("cpu"), 31, 6, **hp)
+    assert isinstance(m.weather_model, WeatherFormer) and m.yield_mlp[0].in_features == 31 + 6 + 1
+    heads = 31 * 16 + 16 + 16 + 1 + 38 * 120 + 120 + 120 + 1
+    assert m.total_params() == 61262 + heads
+    b = WeatherBERTYieldModel("weatherbert_soybean_yield", torch.device("cpu"), 31, 6, **hp)
+    b.freeze_weather_model()
+    assert not any(p.requires_grad for p in b.weather_model.parameters()) and b.yield_mlp[0].weight.requires_grad
+    b.unfreeze_weather_model()
+    assert all(p.requires_grad for p in b.weather_model.parameters())
+    with pytest.raises(ValueError):
+        b.load_pretrained(torch.nn.Linear(2, 2))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["weatherformer", "weatherbert"])
+def test_yield_cli_single_fold_on_gpu(tmp_path, model):
+    synthetic_yield_csv(str(tmp_path / "data" / "khaki_soybeans" / "khaki_multi_crop_yield.csv"))
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    cmd = [sys.executable, "-m", "src.crop_yield.yield_main", "--model", model, "--model-size", "mini",
+           "--batch-size", "16", "--n-past-years", "6", "--n-train-years", "8", "--n-epochs", "4",
+           "--n-warmup-epochs", "1", "--test-year", "2016", "--init-lr", "0.002", "--beta", "0.0001"]
+    res = subprocess.run(cmd, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-4000:]
+    assert "Final average best RMSE for soybean" in res.stderr + res.stdout
+    out_dir = tmp_path / "data" / "trained_models" / "crop_yield"
+    files = sorted(os.listdir(out_dir))
+    assert any(f.endswith("_best.pth") for f in files) and any(f.endswith("_output.json") for f in files), files
