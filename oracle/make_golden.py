@@ -101,6 +101,57 @@ def model_case(kind, size, batch, beta=0.5):
     return rec, model, mask, loss
 
 
+def yield_case(kind, batch=6, n_past=5):
+    """Reference yield models (crop_yield/models/weatherbert_yield_model.py, weatherformer_yield_model.py) on the
+    yield loader's input shape: (n_past+1)*52 weekly steps, 6 observed features, the other 25 masked and imputed."""
+    from src.crop_yield.models.weatherbert_yield_model import WeatherBERTYieldModel
+    from src.crop_yield.models.weatherformer_yield_model import WeatherFormerYieldModel
+
+    torch.manual_seed(1234)
+    cls = WeatherBERTYieldModel if kind == "weatherbert" else WeatherFormerYieldModel
+    model = cls(name=kind + "_yield", device=torch.device("cpu"), weather_dim=31, n_past_years=n_past,
+                **get_model_params("mini"))
+    model.train()
+    neutralise_dropout(model)
+    S = (n_past + 1) * 52
+    g = torch.Generator().manual_seed(7)
+    obs = [7, 8, 11, 1, 2, 29]
+    w = torch.zeros(batch, S, 31)
+    w[:, :, obs] = torch.randn(batch, S, 6, generator=g)
+    coords = torch.stack([torch.rand(batch, generator=g) * 20 + 30, -(torch.rand(batch, generator=g) * 30 + 80)], 1)
+    y0 = torch.randint(1990, 2015, (batch,), generator=g).float()
+    week = torch.arange(1, 53, dtype=torch.float32) / 52
+    year = (y0[:, None, None] + torch.arange(n_past + 1).float()[None, :, None] + week[None, None, :]).reshape(batch, S)
+    interval = torch.full((batch, 1), 7.0)
+    mask = torch.ones(batch, S, 31, dtype=torch.bool)
+    mask[:, :, obs] = False
+    y_past = torch.randn(batch, n_past + 1, generator=g)
+    target = torch.randn(batch, 1, generator=g)
+    rec = dict(weather=w.numpy(), coords=coords.numpy(), year=year.numpy(), interval=interval.numpy(),
+               mask=mask.numpy(), y_past=y_past.numpy(), target=target.numpy())
+    torch.manual_seed(99)  # epsilon of the reparameterisation (weatherformer_yield_model.py:58)
+    out = model(w, coords, year, interval, mask, y_past)
+    if kind == "weatherbert":
+        pred = out
+        loss = nn.MSELoss(reduction="mean")(pred, target)
+    else:
+        pred, z, mu, var = out
+        torch.manual_seed(99)
+        rec["epsilon"] = torch.randn_like(mu).numpy()
+        kl = compute_gaussian_kl_divergence(mask, mu, var, torch.zeros_like(mu), torch.ones_like(var)).mean()
+        loss = nn.MSELoss(reduction="mean")(pred, target) + 1e-4 * kl
+        rec["kl"] = np.array([kl.item()])
+        rec["mu"], rec["var"] = mu.detach().numpy(), var.detach().numpy()
+    loss.backward()
+    rec["pred"] = pred.detach().numpy()
+    rec["loss"] = np.array([loss.item()])
+    for k, v in model.state_dict().items():
+        rec["param/" + k] = v.detach().numpy().copy()
+    for k, v in model.named_parameters():
+        rec["grad/" + k] = v.grad.detach().numpy().copy()
+    return rec
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # ---- masks on the CPU generator (config 1), SURVEY.md 8(c) golden values
@@ -140,6 +191,10 @@ def main():
     assert abs(model.in_proj.weight.grad.norm().item() - 0.07980558) < 1e-6
     assert abs(model.out_proj.weight.grad.norm().item() - 0.70168072) < 1e-6
     np.savez_compressed(os.path.join(OUT, "weatherformer_mini_b8.npz"), **rec)
+
+    # ---- yield fine-tune models (BASELINE.json configs[5])
+    for kind in ["weatherbert", "weatherformer"]:
+        np.savez_compressed(os.path.join(OUT, f"{kind}_yield_mini_b6.npz"), **yield_case(kind))
 
     # ---- scheduler + sizes
     sched = {}

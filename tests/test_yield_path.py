@@ -105,3 +105,65 @@ def test_yield_cli_single_fold_on_gpu(tmp_path, model):
     out_dir = tmp_path / "data" / "trained_models" / "crop_yield"
     files = sorted(os.listdir(out_dir))
     assert any(f.endswith("_best.pth") for f in files) and any(f.endswith("_output.json") for f in files), files
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["weatherbert", "weatherformer"])
+def test_yield_model_matches_reference_golden(kind, monkeypatch):
+    """Prediction, loss and every gradient of the reference's yield models (tests/golden/*_yield_mini_b6.npz,
+    written by oracle/make_golden.py from the unmodified reference) on the loader's input shape: 312 weekly
+    steps, 25 of 31 features masked and imputed. Tolerance: 1e-3 relative on the loss, 3e-2 per-tensor
+    Frobenius on gradients (bf16 activations), 5e-3 on gradient norms."""
+    from src.crop_yield.models.weatherbert_yield_model import WeatherBERTYieldModel
+    from src.crop_yield.models.weatherformer_yield_model import WeatherFormerYieldModel
+    from src.utils.losses import compute_gaussian_kl_divergence
+    from src.utils.utils import get_model_params
+
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"{kind}_yield_mini_b6.npz")))
+    cls = WeatherBERTYieldModel if kind == "weatherbert" else WeatherFormerYieldModel
+    torch.manual_seed(1234)
+    model = cls(name="y", device=torch.device("cpu"), weather_dim=31, n_past_years=5, **get_model_params("mini"))
+    state = {k[len("param/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param/")}
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), state[k]), f"initial weight {k} differs from the reference's for seed 1234"
+    model = model.to("cuda").train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+    t = lambda k: torch.from_numpy(g[k]).to("cuda")  # noqa: E731
+    w, c, yr, iv, mask, y_past, target = (t(k) for k in ("weather", "coords", "year", "interval", "mask", "y_past", "target"))
+    if kind == "weatherformer":
+        eps = t("epsilon")
+        monkeypatch.setattr(torch, "randn_like", lambda x, *a, **k: eps)
+    out = model(w, c, yr, iv, mask, y_past)
+    if kind == "weatherbert":
+        pred = out
+        loss = torch.nn.functional.mse_loss(pred, target)
+    else:
+        pred, z, mu, var = out
+        assert _rel(mu.detach().cpu().numpy(), g["mu"]) <= 1e-2
+        assert _rel(var.detach().cpu().numpy(), g["var"]) <= 1e-2
+        kl = compute_gaussian_kl_divergence(mask, mu, var, torch.zeros_like(mu), torch.ones_like(var)).mean()
+        assert abs(kl.item() - g["kl"][0]) <= 2e-3 * abs(g["kl"][0]), (kl.item(), g["kl"][0])
+        loss = torch.nn.functional.mse_loss(pred, target) + 1e-4 * kl
+    loss.backward()
+    assert _rel(pred.detach().cpu().numpy(), g["pred"]) <= 5e-3, (pred.flatten(), g["pred"].flatten())
+    assert abs(loss.item() - g["loss"][0]) <= 2e-3 * abs(g["loss"][0]), (loss.item(), g["loss"][0])
+    worst = (0.0, "")
+    for name, p in model.named_parameters():
+        r = g["grad/" + name].astype(np.float64)
+        assert p.grad is not None, name
+        got = p.grad.detach().float().cpu().numpy().astype(np.float64)
+        nr = np.linalg.norm(r)
+        assert abs(np.linalg.norm(got) - nr) <= 1e-2 * nr + 1e-9, name
+        rel = _rel(got, r)
+        worst = max(worst, (rel, name))
+        assert rel <= 3e-2, f"{kind} yield: grad {name} rel err {rel:.4g}"
+    print(kind, "yield: loss", loss.item(), "ref", g["loss"][0], "worst grad", worst)

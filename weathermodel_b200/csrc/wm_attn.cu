@@ -121,247 +121,388 @@ WM_DEVICE float fast_exp2(float x) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward: 12 warps. Warp w reads TMEM lane quarter w%4 (query rows) and owns key tile w/4 (128 score
-// columns) of the current 128-query tile. All scores of the tile sit in TMEM at once (384 columns), so
-// the softmax is exact two-pass (max, then exp/sum) with one MMA round trip per tile; two issuing threads
-// (PV of this tile, QK^T of the next) keep descriptor arithmetic off the critical path.
+// forward (v5): persistent, warp-specialised, TMA-fed.
+//   warps 0-11  softmax: warp w reads TMEM lane quarter w%4 (query rows of the current 128-row tile) and owns
+//               the 32-column slice w/4 of every 96-key score chunk
+//   warp 12     MMA issue (lane 0): S chunk = Q_i K_c^T (N = 96), O += P_c V_c
+//   warp 13     TMA producer (lane 0): K/V of the next head, Q tiles of the next head (one head ahead)
+//   warp 14     ctx store: drains the bf16 output staging tile with row-contiguous 8-byte stores
+// Q/K/V head slices are NOT 16-byte aligned in the token-major QKV activation (head pitch dh*2 = 24..72 B), so
+// the producer loads the enclosing 8-column-aligned window [c0, c0 + 8*NCH) with one TMA box per 8-column chunk
+// ({8 cols, 128 rows} -> 128 consecutive 16-byte rows = a column of core matrices). The window carries 4 columns
+// of the neighbouring head on one side; they are zeroed in the Q tile (one 8-byte store per row) so they drop
+// out of Q K^T, and they only produce unused output columns in P V. When 8*NCH is not a multiple of 16 the last
+// k-step takes its second core-matrix column from a shared all-zero chunk (per-descriptor leading byte offset).
+// Software pipeline over the 96-key chunks of consecutive tiles: as soon as all softmax warps have turned score
+// chunk c of tile t into P (bf16, smem ring of two chunk buffers), the issue thread queues O_t += P_c V_c and
+// then S_{t+1} chunk c into the TMEM columns just released, so the tensor pipe runs under the exp2 pass and
+// the next tile's scores are complete when the current tile's softmax ends.
 // ------------------------------------------------------------------------------------------------
-constexpr int kFwdThreads = 416;  // 12 softmax warps + 1 MMA-issue warp (its lane 0 never shares a warp with spinning waiters)
+constexpr int kFwdSoftmaxWarps = 12;
+constexpr int kFwdThreads = 32 * 15;
+constexpr int kKC = 96;  // keys per score chunk (3 slices of 32 columns)
 
-template <int DHP, bool DROP>
+struct AttnFwdBars {
+  uint64_t q_full[3], q_ready[3], q_free[3];
+  uint64_t k_full[2], k_free[2], v_full[2], v_free[2];
+  uint64_t s_full;
+  uint64_t p_full[2], p_free[2];
+  uint64_t o_full[2], o_free[2];
+  uint64_t out_full[2], out_free[2];
+};
+
+template <int NCH>
+struct AttnFwdGeom {
+  static constexpr int DHP = (NCH * 8 + 15) / 16 * 16;
+  static constexpr int KVB = NCH <= 5 ? 2 : 1;         // K / V buffers (double-buffered when they fit)
+  static constexpr uint32_t CSQ = 128 * 16;            // chunk stride inside a 128-row tile
+  static constexpr uint32_t CSK = kSP * 16;            // chunk stride inside a 384-row tile
+  static constexpr uint32_t QT = NCH * CSQ, KT = NCH * CSK;
+  static constexpr uint32_t PB = 128 * kKC * 2;        // one P chunk buffer
+  static constexpr uint32_t OUTB = NCH * 8 * 2 * 128;  // output staging tile (>= 128 * dh * 2)
+  static constexpr uint32_t kSmem = 3 * QT + 2 * KVB * KT + 2 * PB + 2 * OUTB + 2048 + 2 * 3 * 128 * 4 + 128;
+};
+
+template <int NCH, bool DROP>
 __global__ void __launch_bounds__(kFwdThreads, 1)
-attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse_out,
-                int S, int H, int dh, float scale, uint32_t thresh8, float drop_scale, uint64_t seed,
-                uint64_t stream_id) {
-  constexpr uint32_t RS = TileGeom<DHP>::RS;
-  constexpr uint32_t RS_P = (kSP / 8) * 128;  // P tile [128 q, 384 keys]
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ ctx,
+                float* __restrict__ lse_out, int nitems, int S, int H, int dh, float scale, uint32_t thresh8,
+                float drop_scale, uint64_t seed, uint64_t stream_id) {
+  using G = AttnFwdGeom<NCH>;
+  constexpr int DHP = G::DHP, KVB = G::KVB, KSTEPS = DHP / 16;
+  constexpr bool kZeroTail = (NCH & 1) != 0;  // last k-step: second core-matrix column comes from the zero chunk
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kSP * DHP * 2;
-  uint8_t* sV = sK + kSP * DHP * 2;
-  uint8_t* sP = sV + kSP * DHP * 2;
-  float* sMax = reinterpret_cast<float*>(sP + 128 * kSP * 2);  // [3][128]
-  float* sSum = sMax + 3 * 128;                                 // [3][128]
-  uint8_t* sOut = reinterpret_cast<uint8_t*>(sSum + 3 * 128);   // [128][dh] bf16 output staging
-  __shared__ uint64_t bar_s, bar_o;
+  uint8_t* sK = sQ + 3 * G::QT;
+  uint8_t* sV = sK + KVB * G::KT;
+  uint8_t* sP = sV + KVB * G::KT;
+  uint8_t* sOut = sP + 2 * G::PB;
+  uint8_t* sZero = sOut + 2 * G::OUTB;
+  float* sMax = reinterpret_cast<float*>(sZero + 2048);  // [3][128]
+  float* sSum = sMax + 3 * 128;                          // [3][128]
+  __shared__ AttnFwdBars bars;
   __shared__ uint32_t tmem_slot;
 
-  const int D = H * dh;
-  const int ld = 3 * D;
-  const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = warp >> 2;                 // key tile owned by this warp
-  const int row = (warp & 3) * 32 + lane;    // query row inside the tile == TMEM lane
-  const __nv_bfloat16* qbase = qkv + static_cast<size_t>(b) * S * ld + h * dh;
-  const int ntq = (S + 127) / 128;           // query tiles == key tiles
-  const int nk16 = (S + 15) / 16;            // PV k-steps / dropout groups per row
-  const uint32_t thresh4 = thresh8 * 0x01010101u;
+  const int D = H * dh;
+  const int ntq = (S + 127) / 128;             // query tiles per head
+  const int nkc = (S + kKC - 1) / kKC;         // score chunks per tile
+  const int nrb = (nkc * kKC + 127) / 128;     // 128-row K/V blocks that the chunks touch
+  const int nk16 = (S + 15) / 16;              // dropout groups per query row
+  const int nmine = nitems > static_cast<int>(blockIdx.x) ? (nitems - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (warp == 0) WM_TICK(0);
-  {
-    uint8_t* const tiles[3] = {sQ, sK, sV};
-    const __nv_bfloat16* const srcs[3] = {qbase, qbase + D, qbase + 2 * D};
-    const int lds[3] = {ld, ld, ld};
-    load_head_tiles<DHP, 3, (kSP + (32 / (DHP / 4)) * (kFwdThreads / 32) - 1) / ((32 / (DHP / 4)) * (kFwdThreads / 32))>(tiles, srcs, lds, S, kSP, dh);
-  }
-  if (warp == 0) WM_TICK(1);
-  cp_async_wait_all();
-  if (warp == 0) WM_TICK(2);
   if (tid == 0) {
-    mbar_init(&bar_s, 1);
-    mbar_init(&bar_o, 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&bars.q_full[i], 1);
+      mbar_init(&bars.q_ready[i], 4);
+      mbar_init(&bars.q_free[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.k_full[i], 1);
+      mbar_init(&bars.k_free[i], 1);
+      mbar_init(&bars.v_full[i], 1);
+      mbar_init(&bars.v_free[i], 1);
+      mbar_init(&bars.p_full[i], kFwdSoftmaxWarps);
+      mbar_init(&bars.p_free[i], 1);
+      mbar_init(&bars.o_full[i], 1);
+      mbar_init(&bars.o_free[i], kFwdSoftmaxWarps);
+      mbar_init(&bars.out_full[i], kFwdSoftmaxWarps);
+      mbar_init(&bars.out_free[i], 1);
+    }
+    mbar_init(&bars.s_full, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  for (int i = tid; i < 2048 / 16; i += kFwdThreads) reinterpret_cast<uint4*>(sZero)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 12) tmem_alloc<512>(&tmem_slot);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (warp == 0) WM_TICK(3);
-  const uint32_t tS = tmem, tO = tmem + kSP;
-  const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-  const uint32_t idesc_o = umma_idesc_bf16(128, DHP, 0, 1);
-  const float c2 = scale * 1.4426950408889634f;
-  const bool issue_warp = warp == 12;
-  const uint64_t dQ0 = umma_smem_desc(smem_u32(sQ), 128, RS, UMMA_SWZ_NONE);
-  const uint64_t dK0 = umma_smem_desc(smem_u32(sK), 128, RS, UMMA_SWZ_NONE);
-  const uint64_t dP0 = umma_smem_desc(smem_u32(sP), 128, RS_P, UMMA_SWZ_NONE);
-  // V as MN-major B: mn = head dim (SBO = 128 between 8-column groups), k = key rows (LBO = RS)
-  const uint64_t dV0 = umma_smem_desc(smem_u32(sV), RS, 128, UMMA_SWZ_NONE);
+  const uint32_t tS = tmem, tO = tmem + kSP;  // O buffers at +0 / +64
 
-  auto issue_scores = [&](int it) {  // S[128, 128*ntq] = Q_it K^T
-    for (int jt = 0; jt < ntq; ++jt) {
-#pragma unroll
-      for (int k = 0; k < DHP / 16; ++k)
-        umma_ss(tS + jt * 128, umma_desc_advance(dQ0, (it * 16) * RS + k * 256),
-                umma_desc_advance(dK0, (jt * 16) * RS + k * 256), idesc_s, k != 0);
-    }
-    umma_commit(&bar_s);
-  };
-  if (issue_warp) {
-    // ---- MMA-issue warp: mirrors the three block barriers of every tile, issues after the second one
-    if (lane == 0) issue_scores(0);
-    for (int it = 0; it < ntq; ++it) {
-      __syncthreads();  // row maxima exchanged
-      __syncthreads();  // P tile complete in smem, all score reads done
-      if (lane == 0) {
-        tc_fence_after();
-        for (int k = 0; k < nk16; ++k)
-          umma_ss(tO, umma_desc_advance(dP0, k * 256), umma_desc_advance(dV0, (k * 2) * RS), idesc_o, k != 0);
-        umma_commit(&bar_o);
-        if (it + 1 < ntq) issue_scores(it + 1);  // runs under this tile's epilogue
+  if (warp == 13) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      for (int n = 0; n < nmine; ++n) {
+        const int item = blockIdx.x + n * gridDim.x;
+        const int b = item / H, h = item - b * H;
+        const int col0 = (h * dh) & ~7;  // 8-column aligned window start inside the Q block
+        const int kb = n % KVB;
+        if (n >= KVB) mbar_wait(&bars.k_free[kb], ((n / KVB) - 1) & 1, 60);
+        mbar_arrive_expect_tx(&bars.k_full[kb], NCH * nrb * 2048);
+        for (int ch = 0; ch < NCH; ++ch)
+          for (int rb = 0; rb < nrb; ++rb)
+            tma_load_3d(sK + kb * G::KT + ch * G::CSK + rb * 2048, &tm_qkv, &bars.k_full[kb], D + col0 + ch * 8, rb * 128, b);
+        if (n >= KVB) mbar_wait(&bars.v_free[kb], ((n / KVB) - 1) & 1, 61);
+        mbar_arrive_expect_tx(&bars.v_full[kb], NCH * nrb * 2048);
+        for (int ch = 0; ch < NCH; ++ch)
+          for (int rb = 0; rb < nrb; ++rb)
+            tma_load_3d(sV + kb * G::KT + ch * G::CSK + rb * 2048, &tm_qkv, &bars.v_full[kb], 2 * D + col0 + ch * 8, rb * 128, b);
+        for (int i = 0; i < ntq; ++i) {
+          if (n >= 1) mbar_wait(&bars.q_free[i], (n - 1) & 1, 62);
+          mbar_arrive_expect_tx(&bars.q_full[i], NCH * 2048);
+          for (int ch = 0; ch < NCH; ++ch)
+            tma_load_3d(sQ + i * G::QT + ch * G::CSQ, &tm_qkv, &bars.q_full[i], col0 + ch * 8, i * 128, b);
+        }
       }
-      __syncwarp();
-      tc_fence_before();
-      __syncthreads();  // epilogue done: O and P reusable
+    }
+    __syncwarp();
+  } else if (warp == 12) {
+    // ------------------------------------------------------------------ MMA issue
+    if (lane == 0 && nmine > 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, kKC, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, DHP, 0, 1);
+      const uint32_t zero_addr = smem_u32(sZero);
+      auto issue_scores = [&](int i, int kb, int c) {  // S[:, 96c : 96c+96] = Q_i K[96c : 96c+96]^T
+        const uint32_t qa = smem_u32(sQ + i * G::QT), ka = smem_u32(sK + kb * G::KT) + c * kKC * 16;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint32_t a0 = qa + ks * 2 * G::CSQ, b0 = ka + ks * 2 * G::CSK;
+          const bool tail = kZeroTail && ks == KSTEPS - 1;
+          umma_ss(tS + c * kKC, umma_smem_desc(a0, tail ? zero_addr - a0 : G::CSQ, 128, UMMA_SWZ_NONE),
+                  umma_smem_desc(b0, tail ? zero_addr - b0 : G::CSK, 128, UMMA_SWZ_NONE), idesc_s, ks != 0);
+        }
+      };
+      uint32_t t = 0, pc = 0;
+      // prologue: all score chunks of the first tile
+      mbar_wait(&bars.k_full[0], 0, 63);
+      mbar_wait(&bars.q_ready[0], 0, 64);
+      tc_fence_after();
+      for (int c = 0; c < nkc; ++c) issue_scores(0, 0, c);
+      umma_commit(&bars.s_full);
+      umma_commit(&bars.q_free[0]);
+      if (ntq == 1) umma_commit(&bars.k_free[0]);
+      for (int n = 0; n < nmine; ++n) {
+        const int kb = n % KVB;
+        for (int i = 0; i < ntq; ++i, ++t) {
+          const uint32_t ob = t & 1u;
+          if (t >= 2) mbar_wait(&bars.o_free[ob], ((t >> 1) - 1) & 1, 65);
+          if (i == 0) mbar_wait(&bars.v_full[kb], (n / KVB) & 1, 66);
+          const bool has_next = (i + 1 < ntq) || (n + 1 < nmine);
+          const int i1 = i + 1 < ntq ? i + 1 : 0, n1 = i + 1 < ntq ? n : n + 1;
+          const int kb1 = n1 % KVB;
+          const uint32_t va = smem_u32(sV + kb * G::KT), td = tO + ob * 64;
+          for (int c = 0; c < nkc; ++c, ++pc) {
+            const uint32_t pb = pc & 1u;
+            mbar_wait(&bars.p_full[pb], (pc >> 1) & 1, 67);
+            tc_fence_after();
+            const uint32_t pa = smem_u32(sP + pb * G::PB);
+            const int ksteps = min(kKC / 16, (S - c * kKC + 15) / 16);
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_ss(td, umma_smem_desc(pa + ks * 4096, 2048, 128, UMMA_SWZ_NONE),
+                      umma_smem_desc(va + (c * kKC + ks * 16) * 16, 128, G::CSK, UMMA_SWZ_NONE), idesc_o, (c | ks) != 0);
+            umma_commit(&bars.p_free[pb]);
+            if (c == nkc - 1) {
+              umma_commit(&bars.o_full[ob]);
+              if (i == ntq - 1) umma_commit(&bars.v_free[kb]);
+            }
+            if (has_next) {
+              if (c == 0) {
+                if (i1 == 0) mbar_wait(&bars.k_full[kb1], (n1 / KVB) & 1, 68);
+                mbar_wait(&bars.q_ready[i1], n1 & 1, 69);
+                tc_fence_after();
+              }
+              issue_scores(i1, kb1, c);
+              if (c == nkc - 1) {
+                umma_commit(&bars.s_full);
+                umma_commit(&bars.q_free[i1]);
+                if (i1 == ntq - 1) umma_commit(&bars.k_free[kb1]);
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 14) {
+    // ------------------------------------------------------------------ ctx store
+    const int pv = dh >> 2;  // 8-byte pieces per row
+    const float inv_pv = 1.0f / static_cast<float>(pv);
+    uint32_t t = 0;
+    for (int n = 0; n < nmine; ++n) {
+      const int item = blockIdx.x + n * gridDim.x;
+      const int b = item / H, h = item - b * H;
+      for (int i = 0; i < ntq; ++i, ++t) {
+        const uint32_t ob = t & 1u;
+        mbar_wait(&bars.out_full[ob], (t >> 1) & 1, 70);
+        const int nrows = min(128, S - i * 128);
+        const uint8_t* src = sOut + ob * G::OUTB;
+        __nv_bfloat16* obase = ctx + (static_cast<size_t>(b) * S + i * 128) * D + h * dh;
+        for (int idx = lane; idx < nrows * pv; idx += 32) {
+          const int r = static_cast<int>((static_cast<float>(idx) + 0.5f) * inv_pv);
+          const int pp = idx - r * pv;
+          *reinterpret_cast<uint2*>(obase + static_cast<size_t>(r) * D + pp * 4) = *reinterpret_cast<const uint2*>(src + idx * 8);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.out_free[ob]);
+      }
     }
   } else {
-  uint32_t ph_s = 0, ph_o = 0;
-  // Dropout keep masks of a whole query tile (8 Philox blocks per thread) are generated while the thread would
-  // otherwise sit in an mbarrier wait (first tile: under the score MMAs; later tiles: under the previous PV).
-  uint32_t kmask[8][4];
-  auto gen_masks = [&](int it) {
-    if (!DROP || grp >= ntq) return;
-    const int qq = it * 128 + row;
-    const uint64_t rowbase = (static_cast<uint64_t>(bh) * S + (qq < S ? qq : 0)) * nk16;
+    // ------------------------------------------------------------------ softmax warps
+    const int lq = warp & 3, sl = warp >> 2;   // TMEM lane quarter, 32-column slice of each chunk
+    const int row = lq * 32 + lane;            // query row inside the tile == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>(lq * 32) << 16;
+    const uint32_t thresh4 = thresh8 * 0x01010101u;
+    const float c2 = scale * 1.4426950408889634f;
+    const bool need_fix = (dh & 7) != 0;
+    uint32_t kmask[DROP ? 8 : 1][4];
+    auto gen_masks = [&](int item, int i) {
+      if (!DROP) return;
+      const int qq = i * 128 + row;
+      const uint64_t rowbase = (static_cast<uint64_t>(item) * S + (qq < S ? qq : 0)) * nk16;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int k0 = grp * 128 + c * 16;
-      if (k0 < nk16 * 16) {
-        keep_masks16(seed, stream_id, rowbase + (k0 >> 4), thresh4, kmask[c]);
-        WM_PIN(kmask[c][0]); WM_PIN(kmask[c][1]); WM_PIN(kmask[c][2]); WM_PIN(kmask[c][3]);
+      for (int c = 0; c < 4; ++c) {
+        const int k0 = c * kKC + sl * 32;
+        if (k0 < nk16 * 16) {
+          uint32_t(&ma)[4] = kmask[DROP ? 2 * c : 0];
+          uint32_t(&mb)[4] = kmask[DROP ? 2 * c + 1 : 0];
+          keep_masks16(seed, stream_id, rowbase + (k0 >> 4), thresh4, ma);
+          keep_masks16(seed, stream_id, rowbase + (k0 >> 4) + 1, thresh4, mb);
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { WM_PIN(ma[w]); WM_PIN(mb[w]); }
+        }
       }
+    };
+    // zero the neighbouring head's 4 columns of Q tile i (window columns [0, front) or [front + dh, 8 * NCH))
+    auto fix_q = [&](int n, int i, int h) {
+      if (sl != 0) return;
+      mbar_wait(&bars.q_full[i], n & 1, 71);
+      if (need_fix) {
+        const int z0 = ((h * dh) & 7) ? 0 : dh;
+        *reinterpret_cast<uint2*>(sQ + i * G::QT + (z0 >> 3) * G::CSQ + row * 16 + (z0 & 7) * 2) = make_uint2(0u, 0u);
+        fence_proxy_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.q_ready[i]);
+    };
+    uint32_t t = 0, pc = 0;
+    if (nmine > 0) {
+      const int item0 = blockIdx.x;
+      fix_q(0, 0, item0 % H);
+      gen_masks(item0, 0);
     }
-  };
-  gen_masks(0);
-  for (int it = 0; it < ntq; ++it) {
-    const int q = it * 128 + row;
-    const bool qvalid = q < S;
-    if (warp == 0) WM_TICK(4 + it * 8);
-    mbar_wait(&bar_s, ph_s, 41);
-    ph_s ^= 1u;
-    tc_fence_after();
-    if (warp == 0) WM_TICK(5 + it * 8);
-    // ---- pass 1: max over this warp's key tile
-    float mloc = -INFINITY;
-    if (grp < ntq) {
+    for (int n = 0; n < nmine; ++n) {
+      const int item = blockIdx.x + n * gridDim.x;
+      const int b = item / H, h = item - b * H;
+      const int front = (h * dh) & 7;
+      for (int i = 0; i < ntq; ++i, ++t) {
+        const bool has_next = (i + 1 < ntq) || (n + 1 < nmine);
+        const int i1 = i + 1 < ntq ? i + 1 : 0, n1 = i + 1 < ntq ? n : n + 1;
+        const int item1 = blockIdx.x + n1 * gridDim.x;
+        if (has_next) fix_q(n1, i1, item1 % H);
+        const int q = i * 128 + row;
+        mbar_wait(&bars.s_full, t & 1, 72);
+        tc_fence_after();
+        // ---- pass 1: row max over this warp's slices
+        float mloc = -INFINITY;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        const int kbase = grp * 128 + c0;
-        if (kbase >= S) break;
-        uint32_t v[32];
-        tmem_ld32(tS + lane_sel + kbase, v);
-        tmem_ld_wait();
-        if (kbase + 32 <= S) {
+        for (int c = 0; c < nkc; ++c) {
+          const int k0 = c * kKC + sl * 32;
+          if (k0 >= S) break;
+          uint32_t v[32];
+          tmem_ld32(tS + lane_sel + k0, v);
+          tmem_ld_wait();
+          if (k0 + 32 <= S) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mloc = fmaxf(mloc, __uint_as_float(v[j]));
-        } else {
+            for (int j = 0; j < 32; ++j) mloc = fmaxf(mloc, __uint_as_float(v[j]));
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (kbase + j < S) mloc = fmaxf(mloc, __uint_as_float(v[j]));
-        }
-      }
-    }
-    sMax[grp * 128 + row] = mloc;
-    if (warp == 0) WM_TICK(6 + it * 8);
-    __syncthreads();
-    if (warp == 0) WM_TICK(7 + it * 8);
-    const float mrow = fmaxf(fmaxf(sMax[row], sMax[128 + row]), sMax[256 + row]);
-    const float mneg = -mrow * c2;
-    // ---- pass 2: exp2, row sum, dropout, P -> smem (bf16, K-major over keys)
-    float lsum = 0.0f;
-    if (grp < ntq) {
-#pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 16) {
-        const int k0 = grp * 128 + c0;
-        if (k0 >= nk16 * 16) break;
-        uint32_t v[16];
-        tmem_ld16(tS + lane_sel + k0, v);
-        tmem_ld_wait();
-        const uint32_t(&km)[4] = kmask[c0 >> 4];
-        uint32_t pb[16];  // P as fp32 bit patterns (masked by the keep decision)
-        if (k0 + 16 <= S) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float e = fast_exp2(fmaf(__uint_as_float(v[j]), c2, mneg));
-            lsum += e;
-            pb[j] = DROP ? (__float_as_uint(e) & WM_KEEP32(km, j)) : __float_as_uint(e);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float e = 0.0f;
-            if (k0 + j < S) e = fast_exp2(fmaf(__uint_as_float(v[j]), c2, mneg));
-            lsum += e;
-            pb[j] = DROP ? (__float_as_uint(e) & WM_KEEP32(km, j)) : __float_as_uint(e);
+            for (int j = 0; j < 32; ++j)
+              if (k0 + j < S) mloc = fmaxf(mloc, __uint_as_float(v[j]));
           }
         }
+        sMax[sl * 128 + row] = mloc;
+        named_bar_sync(1 + lq, 96);
+        const float mrow = fmaxf(fmaxf(sMax[row], sMax[128 + row]), sMax[256 + row]);
+        const float mneg = -mrow * c2;
+        // ---- pass 2: exp2, row sum, dropout, P chunk -> smem ring, one mbarrier arrival per chunk and warp
+        float lsum = 0.0f;
 #pragma unroll
-        for (int g8 = 0; g8 < 2; ++g8) {
-          uint4 pk;
-          pk.x = pack_bf16x2(__uint_as_float(pb[g8 * 8 + 0]), __uint_as_float(pb[g8 * 8 + 1]));
-          pk.y = pack_bf16x2(__uint_as_float(pb[g8 * 8 + 2]), __uint_as_float(pb[g8 * 8 + 3]));
-          pk.z = pack_bf16x2(__uint_as_float(pb[g8 * 8 + 4]), __uint_as_float(pb[g8 * 8 + 5]));
-          pk.w = pack_bf16x2(__uint_as_float(pb[g8 * 8 + 6]), __uint_as_float(pb[g8 * 8 + 7]));
-          const int kc = k0 + g8 * 8;
-          *reinterpret_cast<uint4*>(sP + (row >> 3) * RS_P + (kc >> 3) * 128 + (row & 7) * 16) = pk;
+        for (int c = 0; c < 4; ++c) {
+          if (c < nkc) {
+            const uint32_t pb = pc & 1u;
+            if (pc >= 2) mbar_wait(&bars.p_free[pb], ((pc >> 1) - 1) & 1, 73);
+            const int k0 = c * kKC + sl * 32;
+            uint32_t v[32];
+            tmem_ld32(tS + lane_sel + k0, v);
+            tmem_ld_wait();
+            uint32_t pbits[32];
+            if (k0 + 32 <= S) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float e = fast_exp2(fmaf(__uint_as_float(v[j]), c2, mneg));
+                lsum += e;
+                pbits[j] = DROP ? (__float_as_uint(e) & WM_KEEP32(kmask[DROP ? 2 * c + (j >> 4) : 0], j & 15)) : __float_as_uint(e);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float e = 0.0f;
+                if (k0 + j < S) e = fast_exp2(fmaf(__uint_as_float(v[j]), c2, mneg));
+                lsum += e;
+                pbits[j] = DROP ? (__float_as_uint(e) & WM_KEEP32(kmask[DROP ? 2 * c + (j >> 4) : 0], j & 15)) : __float_as_uint(e);
+              }
+            }
+            uint8_t* pdst = sP + pb * G::PB + (sl * 4) * 2048 + row * 16;
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              uint4 pk;
+              pk.x = pack_bf16x2(__uint_as_float(pbits[g8 * 8 + 0]), __uint_as_float(pbits[g8 * 8 + 1]));
+              pk.y = pack_bf16x2(__uint_as_float(pbits[g8 * 8 + 2]), __uint_as_float(pbits[g8 * 8 + 3]));
+              pk.z = pack_bf16x2(__uint_as_float(pbits[g8 * 8 + 4]), __uint_as_float(pbits[g8 * 8 + 5]));
+              pk.w = pack_bf16x2(__uint_as_float(pbits[g8 * 8 + 6]), __uint_as_float(pbits[g8 * 8 + 7]));
+              *reinterpret_cast<uint4*>(pdst + g8 * 2048) = pk;
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.p_full[pb]);
+            ++pc;
+          }
+        }
+        sSum[sl * 128 + row] = lsum;
+        // the next tile's keep masks are generated while the tensor pipe finishes this tile's P V
+        if (has_next) gen_masks(item1, i1);
+        named_bar_sync(1 + lq, 96);
+        const float tot = sSum[row] + sSum[128 + row] + sSum[256 + row];
+        // ---- epilogue: O / (row sum) -> bf16 staging tile (compact [128, dh]); slice sl takes columns [16 sl, 16 sl + 16)
+        const uint32_t ob = t & 1u;
+        mbar_wait(&bars.o_full[ob], (t >> 1) & 1, 74);
+        tc_fence_after();
+        if (t >= 2) mbar_wait(&bars.out_free[ob], ((t >> 1) - 1) & 1, 75);
+        if (sl * 16 < DHP) {
+          const float inv = drop_scale / tot;
+          uint32_t v[16];
+          tmem_ld16(tO + ob * 64 + lane_sel + sl * 16, v);
+          tmem_ld_wait();
+          uint8_t* srow = sOut + ob * G::OUTB + row * (dh * 2);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const int d = sl * 16 + j - front;  // head-dim index of TMEM column sl*16 + j
+            if (d >= 0 && d < dh) {
+              uint2 pk;
+              pk.x = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+              pk.y = pack_bf16x2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+              *reinterpret_cast<uint2*>(srow + d * 2) = pk;
+            }
+          }
+        }
+        if (sl == 0 && q < S && lse_out) lse_out[static_cast<size_t>(item) * S + q] = mrow * scale + logf(tot);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bars.o_free[ob]);
+          mbar_arrive(&bars.out_full[ob]);
         }
       }
     }
-    sSum[grp * 128 + row] = lsum;
-    if (warp == 0) WM_TICK(8 + it * 8);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) WM_TICK(9 + it * 8);
-    if (it + 1 < ntq) gen_masks(it + 1);
-    mbar_wait(&bar_o, ph_o, 43);
-    ph_o ^= 1u;
-    tc_fence_after();
-    if (warp == 0) WM_TICK(10 + it * 8);
-    // ---- epilogue: warp group g scales head-dim columns [16g, 16g+16) of its row and parks them in a compact
-    // [rows, dh] staging tile; the tile then leaves with row-contiguous 8-byte pieces (about 3 rows per warp
-    // store instead of 32 different rows: thread-per-row global stores cost ~1 LSU cycle per 32-byte sector)
-    const float tot = sSum[row] + sSum[128 + row] + sSum[256 + row];
-    if (grp * 16 < DHP) {
-      const float inv = drop_scale / tot;
-      uint32_t v[16];
-      tmem_ld16(tO + lane_sel + grp * 16, v);
-      tmem_ld_wait();
-      uint8_t* srow = sOut + row * (dh * 2) + grp * 32;
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        if (grp * 16 + j < dh) {  // dh % 4 == 0
-          uint2 pk;
-          pk.x = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
-          pk.y = pack_bf16x2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
-          *reinterpret_cast<uint2*>(srow + j * 2) = pk;
-        }
-      }
-      if (grp == 0 && qvalid && lse_out) lse_out[static_cast<size_t>(bh) * S + q] = mrow * scale + logf(tot);
-    }
-    named_bar_sync(1, kFwdThreads - 32);
-    {
-      const int pv = dh >> 2;
-      const int nrows = min(128, S - it * 128);
-      const float inv_pv = 1.0f / static_cast<float>(pv);
-      __nv_bfloat16* obase = ctx + (static_cast<size_t>(b) * S + it * 128) * D + h * dh;
-      for (int i = tid; i < nrows * pv; i += kFwdThreads - 32) {
-        const int r = static_cast<int>((static_cast<float>(i) + 0.5f) * inv_pv);
-        const int pp = i - r * pv;
-        *reinterpret_cast<uint2*>(obase + static_cast<size_t>(r) * D + pp * 4) = *reinterpret_cast<const uint2*>(sOut + i * 8);
-      }
-    }
-    if (warp == 0) WM_TICK(11 + it * 8);
-    tc_fence_before();
-    __syncthreads();  // O drained, sMax / sSum / sP reusable
   }
-  if (warp == 0) WM_TICK(28);
-  }
-  if (warp == 0) {
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
@@ -642,14 +783,31 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
 // ------------------------------------------------------------------------------------------------
 static int padded_dh(int dh) { return dh <= 16 ? 16 : dh <= 32 ? 32 : dh <= 48 ? 48 : 0; }
 
-template <int DHP>
+static int attn_sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  return sms;
+}
+// 16-byte chunks that cover one head's columns from the 8-column-aligned window start (worst-case offset 4)
+static int attn_chunks(int dh) { return (dh & 7) ? (dh + 4) / 8 : dh / 8; }
+
+template <int NCH>
 static int launch_fwd_t(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, int B, int S, int H, int dh,
                         float scale, uint32_t thresh8, float dscale, uint64_t seed, uint64_t stream_id,
                         cudaStream_t stream) {
-  const int smem = 3 * kSP * DHP * 2 + 128 * kSP * 2 + 6 * 128 * 4 + 128 * DHP * 2 + 256;
-  auto kern = thresh8 ? attn_fwd_kernel<DHP, true> : attn_fwd_kernel<DHP, false>;
+  CUtensorMap tm;
+  const int D = H * dh;
+  int rc = make_tmap_bf16_rows3d(&tm, qkv, 3 * D, S, B, 3 * D, 128);
+  if (rc != WM_OK) return rc;
+  const int smem = AttnFwdGeom<NCH>::kSmem;
+  auto kern = thresh8 ? attn_fwd_kernel<NCH, true> : attn_fwd_kernel<NCH, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
-  kern<<<B * H, kFwdThreads, smem, stream>>>(qkv, ctx, lse, S, H, dh, scale, thresh8, dscale, seed, stream_id);
+  const int nitems = B * H;
+  const int grid = nitems < attn_sm_count() ? nitems : attn_sm_count();
+  kern<<<grid, kFwdThreads, smem, stream>>>(tm, ctx, lse, nitems, S, H, dh, scale, thresh8, dscale, seed, stream_id);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
@@ -675,17 +833,19 @@ static void attn_drop_params(uint32_t drop_thresh16, uint32_t* thresh8, float* s
 int launch_attn_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, int B, int S, int H, int dh,
                     uint32_t drop_thresh, float drop_scale, uint64_t seed, uint64_t stream_id, cudaStream_t stream) {
   (void)drop_scale;
-  if (B <= 0 || H <= 0 || S <= 0 || S > kSP || (dh & 3)) return WM_ERR_SHAPE;
-  const int dhp = padded_dh(dh);
-  if (!dhp) return WM_ERR_SHAPE;
+  // TMA needs 16-byte aligned row pitches and head-block starts: D = H * dh a multiple of 8
+  if (B <= 0 || H <= 0 || S <= 0 || S > kSP || (dh & 3) || dh < 8 || dh > 48 || ((H * dh) & 7)) return WM_ERR_SHAPE;
   uint32_t t8;
   float ds;
   attn_drop_params(drop_thresh, &t8, &ds);
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
-  switch (dhp) {
-    case 16: return launch_fwd_t<16>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
-    case 32: return launch_fwd_t<32>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
-    default: return launch_fwd_t<48>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
+  switch (attn_chunks(dh)) {
+    case 1: return WM_ERR_SHAPE;
+    case 2: return launch_fwd_t<2>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
+    case 3: return launch_fwd_t<3>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
+    case 4: return launch_fwd_t<4>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
+    case 5: return launch_fwd_t<5>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
+    default: return launch_fwd_t<6>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
   }
 }
 

@@ -53,6 +53,25 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t c
   return r == CUDA_SUCCESS ? WM_OK : WM_ERR_DRIVER;
 }
 
+// 3D view {cols, S rows, B batches} of a token-major bf16 activation [B*S, ld] for the attention kernels:
+// box = {8 columns (one 16-byte core-matrix row), box_rows, 1}, no swizzle -- every box lands as box_rows
+// consecutive 16-byte rows, i.e. a column of canonical 8x16B core matrices. Rows >= S read as zero, so a tile
+// never sees the next sequence of the batch.
+int make_tmap_bf16_rows3d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t S, uint64_t B, uint64_t ld,
+                          uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return WM_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((ld * 2) & 15u)) return WM_ERR_ALIGN;
+  cuuint64_t gdim[3] = {cols, S, B};
+  cuuint64_t gstr[2] = {ld * 2, S * ld * 2};
+  cuuint32_t box[3] = {8, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? WM_OK : WM_ERR_DRIVER;
+}
+
 // ------------------------------------------------------------------------------------------------
 // gemm_tn
 // ------------------------------------------------------------------------------------------------
