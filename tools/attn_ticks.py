@@ -14,18 +14,23 @@ qkv = (torch.randn(B * S, 3 * H * dh, device="cuda") * 0.5).to(torch.bfloat16)
 for p in (0.0, 0.1):
     for _ in range(3):
         ops.attn_fwd(qkv, B, S, H, dh, dropout_p=p, seed=1, stream_id=1)
-    buf = (C.c_longlong * 32)()
-    lib().wm_debug_ticks(buf, 32)
+    buf = (C.c_longlong * 64)()
+    lib().wm_debug_ticks(buf, 64)
     t = list(buf)
-    names = {0: "start", 1: "cp.async issued", 2: "cp.async landed", 3: "setup sync+alloc"}
+    names = {}
     for it in range(3):
-        for k, nm in enumerate(["tile top", "scores ready", "pass1 done", "max exchanged", "pass2 done", "P synced", "PV done", "epilogue done"]):
-            names[4 + it * 8 + k] = f"t{it} {nm}"
-    names[28] = "end"
+        for c in range(4):
+            names[36 + (it * 4 + c) * 2] = f"   MMA: t{it} P chunk{c} seen"
+            names[37 + (it * 4 + c) * 2] = f"   MMA: t{it} chunk{c} PV + next S issued"
+    for it in range(3):
+        for k, nm in enumerate(["tile top", "next Q fixed", "scores ready", "pass1 done", "max exchanged", "chunk0 -> P",
+                                "chunk1 -> P", "chunk2 -> P", "chunk3 -> P", "masks + sum exchanged", "O ready",
+                                "epilogue done"]):
+            names[it * 12 + k] = f"t{it} {nm}"
     prev = t[0]
-    print(f"--- attn_fwd p={p}: total {t[28] - t[0]} cycles")
-    for i in sorted(names):
-        print(f"{names[i]:22s} +{t[i] - prev:7d}  (@{t[i] - t[0]})")
+    print(f"--- attn_fwd v5 p={p}: second head of CTA 0, softmax warp 0 + MMA thread: total {t[35] - t[0]} cycles")
+    for i in sorted(names, key=lambda k: t[k]):
+        print(f"{names[i]:40s} +{t[i] - prev:7d}  (@{t[i] - t[0]})")
         prev = t[i]
 
 dctx = (torch.randn(B * S, H * dh, device="cuda") * 0.5).to(torch.bfloat16)

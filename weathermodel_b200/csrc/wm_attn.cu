@@ -13,7 +13,7 @@
 //   bwd : per (kv tile j, q tile i): S = Q K^T, dP = dO V^T in TMEM; P, dS -> smem (bf16);
 //         dV_j += P^T dO, dK_j += dS^T Q, dQ_i += dS K; all five accumulators live in TMEM (<= 496 cols).
 // Dropout on P uses Philox4x32-10 keyed by (seed, stream, (bh*S + q)*ceil(S/16) + k/16), 8 bits / element
-// (keep iff byte >= thresh8), regenerated identically in backward.
+// (keep iff (byte & 0x7F) >= thresh7), regenerated identically in backward.
 #include "wm_kernels.h"
 
 namespace wm {
@@ -96,14 +96,33 @@ WM_DEVICE void load_head_tiles(uint8_t* const (&tile)[NT], const __nv_bfloat16* 
 
 // Dropout on attention probabilities: one Philox4x32-7 block (the 7-round variant is the Crush-resistant
 // minimum of the Random123 paper; nothing here has to match torch's stream) decides 16 consecutive keys of one
-// query row, 8 bits each: keep iff byte >= thresh8. m[w] holds 0xFF in every kept byte of word w.
+// query row, one byte each (7 bits used).
 constexpr int kAttnPhiloxRounds = 7;
-WM_DEVICE void keep_masks16(uint64_t seed, uint64_t stream, uint64_t grp, uint32_t thresh4, uint32_t (&m)[4]) {
+// keep iff (byte & 0x7F) >= thresh7: adding (128 - thresh7) to the 7-bit value carries into bit 7 of the byte exactly
+// then (no carry crosses a byte). add4 = (128 - thresh7) * 0x01010101; f[w] carries the keep flag of element
+// 4w + b in bit 7 of byte b (the other bits are noise) -- two integer ops per four elements.
+WM_DEVICE void keep_flags16(uint64_t seed, uint64_t stream, uint64_t grp, uint32_t add4, uint32_t (&f)[4]) {
   const Philox4 r = philox4x32<kAttnPhiloxRounds>(seed, stream, grp);
-  m[0] = __vcmpgeu4(r.x, thresh4);
-  m[1] = __vcmpgeu4(r.y, thresh4);
-  m[2] = __vcmpgeu4(r.z, thresh4);
-  m[3] = __vcmpgeu4(r.w, thresh4);
+  f[0] = (r.x & 0x7F7F7F7Fu) + add4;
+  f[1] = (r.y & 0x7F7F7F7Fu) + add4;
+  f[2] = (r.z & 0x7F7F7F7Fu) + add4;
+  f[3] = (r.w & 0x7F7F7F7Fu) + add4;
+}
+// 0xFFFF / 0x0000 in each half of the result: keep flags of elements j (low half) and j + 1 (high half), j even,
+// for masking a packed bf16x2 pair -- one PRMT in sign-replicate mode (selector nibble bit 3)
+WM_DEVICE uint32_t keep_pair_mask(uint32_t fword, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(fword), "r"(0u), "r"(sel));
+  return d;
+}
+#define WM_PAIR_SEL(j) ((((j) & 3) | 8u) * 0x11u | ((((j) & 3) + 1u) | 8u) * 0x1100u)
+#define WM_KEEP_PAIR(f, j) keep_pair_mask((f)[(j) >> 2], WM_PAIR_SEL(j))
+// byte-mask form (0xFF in every kept byte) used by the v4 backward kernel
+WM_DEVICE void keep_masks16(uint64_t seed, uint64_t stream, uint64_t grp, uint32_t add4, uint32_t (&m)[4]) {
+  uint32_t f[4];
+  keep_flags16(seed, stream, grp, add4, f);
+#pragma unroll
+  for (int w = 0; w < 4; ++w) m[w] = ((f[w] >> 7) & 0x01010101u) * 0xFFu;
 }
 // pins a value in a register at this point of the instruction stream: without it the compiler sinks the (pure)
 // Philox arithmetic below the mbarrier wait it is supposed to overlap with
@@ -121,11 +140,11 @@ WM_DEVICE float fast_exp2(float x) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward (v5): persistent, warp-specialised, TMA-fed.
+// forward: persistent, warp-specialised, TMA-fed; probabilities never leave tensor memory.
 //   warps 0-11  softmax: warp w reads TMEM lane quarter w%4 (query rows of the current 128-row tile) and owns
 //               the 32-column slice w/4 of every 96-key score chunk
-//   warp 12     MMA issue (lane 0): S chunk = Q_i K_c^T (N = 96), O += P_c V_c
-//   warp 13     TMA producer (lane 0): K/V of the next head, Q tiles of the next head (one head ahead)
+//   warp 12     MMA issue (whole warp convergent, one elected lane): O += P_c V_c, then S_{t+1} chunk c
+//   warp 13     TMA producer: K/V and Q tiles one head ahead; zeroes the neighbour-head columns of each Q tile
 //   warp 14     ctx store: drains the bf16 output staging tile with row-contiguous 8-byte stores
 // Q/K/V head slices are NOT 16-byte aligned in the token-major QKV activation (head pitch dh*2 = 24..72 B), so
 // the producer loads the enclosing 8-column-aligned window [c0, c0 + 8*NCH) with one TMA box per 8-column chunk
@@ -133,10 +152,13 @@ WM_DEVICE float fast_exp2(float x) {
 // of the neighbouring head on one side; they are zeroed in the Q tile (one 8-byte store per row) so they drop
 // out of Q K^T, and they only produce unused output columns in P V. When 8*NCH is not a multiple of 16 the last
 // k-step takes its second core-matrix column from a shared all-zero chunk (per-descriptor leading byte offset).
-// Software pipeline over the 96-key chunks of consecutive tiles: as soon as all softmax warps have turned score
-// chunk c of tile t into P (bf16, smem ring of two chunk buffers), the issue thread queues O_t += P_c V_c and
-// then S_{t+1} chunk c into the TMEM columns just released, so the tensor pipe runs under the exp2 pass and
-// the next tile's scores are complete when the current tile's softmax ends.
+// Softmax is exact two-pass over scores that sit in TMEM (384 fp32 columns per tile). In pass 2 a warp turns its
+// 32 score columns of chunk c into 16 columns of packed bf16 P written back IN PLACE (tcgen05.st); the issue warp
+// feeds them to the tensor core as the TMEM A operand of O_t += P_c V_c and then queues S_{t+1} chunk c into the
+// same columns (tcgen05.mma executes in issue order), so the next tile's scores are complete when the current
+// tile's softmax ends. No shared-memory round trip, no proxy fence and no extra barrier for P.
+// (v5 staged P through shared memory: a fence.proxy.async per warp and chunk cost ~300 cycles each and a single
+// thread could not issue ~35 small MMAs per tile fast enough -- profiles/r01_attn_phase_ticks.txt.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kFwdSoftmaxWarps = 12;
 constexpr int kFwdThreads = 32 * 15;
@@ -145,8 +167,7 @@ constexpr int kKC = 96;  // keys per score chunk (3 slices of 32 columns)
 struct AttnFwdBars {
   uint64_t q_full[3], q_ready[3], q_free[3];
   uint64_t k_full[2], k_free[2], v_full[2], v_free[2];
-  uint64_t s_full;
-  uint64_t p_full[2], p_free[2];
+  uint64_t s_full, p_full[4];
   uint64_t o_full[2], o_free[2];
   uint64_t out_full[2], out_free[2];
 };
@@ -154,19 +175,19 @@ struct AttnFwdBars {
 template <int NCH>
 struct AttnFwdGeom {
   static constexpr int DHP = (NCH * 8 + 15) / 16 * 16;
-  static constexpr int KVB = NCH <= 5 ? 2 : 1;         // K / V buffers (double-buffered when they fit)
+  static constexpr int KVB = 2;                        // K / V buffers
   static constexpr uint32_t CSQ = 128 * 16;            // chunk stride inside a 128-row tile
   static constexpr uint32_t CSK = kSP * 16;            // chunk stride inside a 384-row tile
   static constexpr uint32_t QT = NCH * CSQ, KT = NCH * CSK;
-  static constexpr uint32_t PB = 128 * kKC * 2;        // one P chunk buffer
   static constexpr uint32_t OUTB = NCH * 8 * 2 * 128;  // output staging tile (>= 128 * dh * 2)
-  static constexpr uint32_t kSmem = 3 * QT + 2 * KVB * KT + 2 * PB + 2 * OUTB + 2048 + 2 * 3 * 128 * 4 + 128;
+  // + one chunk of slack: an MN-major B descriptor with N = DHP > 8 * NCH reads one chunk past the last V buffer
+  static constexpr uint32_t kSmem = 3 * QT + 2 * KVB * KT + CSK + 2 * OUTB + 2048 + 2 * 3 * 128 * 4 + 128;
 };
 
 template <int NCH, bool DROP>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ ctx,
-                float* __restrict__ lse_out, int nitems, int S, int H, int dh, float scale, uint32_t thresh8,
+                float* __restrict__ lse_out, int nitems, int S, int H, int dh, float scale, uint32_t thresh7,
                 float drop_scale, uint64_t seed, uint64_t stream_id) {
   using G = AttnFwdGeom<NCH>;
   constexpr int DHP = G::DHP, KVB = G::KVB, KSTEPS = DHP / 16;
@@ -176,15 +197,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + 3 * G::QT;
   uint8_t* sV = sK + KVB * G::KT;
-  uint8_t* sP = sV + KVB * G::KT;
-  uint8_t* sOut = sP + 2 * G::PB;
+  uint8_t* sOut = sV + KVB * G::KT + G::CSK;
   uint8_t* sZero = sOut + 2 * G::OUTB;
   float* sMax = reinterpret_cast<float*>(sZero + 2048);  // [3][128]
   float* sSum = sMax + 3 * 128;                          // [3][128]
   __shared__ AttnFwdBars bars;
   __shared__ uint32_t tmem_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const int D = H * dh;
   const int ntq = (S + 127) / 128;             // query tiles per head
   const int nkc = (S + kKC - 1) / kKC;         // score chunks per tile
@@ -195,7 +215,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) {
       mbar_init(&bars.q_full[i], 1);
-      mbar_init(&bars.q_ready[i], 4);
+      mbar_init(&bars.q_ready[i], 1);
       mbar_init(&bars.q_free[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -203,14 +223,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
       mbar_init(&bars.k_free[i], 1);
       mbar_init(&bars.v_full[i], 1);
       mbar_init(&bars.v_free[i], 1);
-      mbar_init(&bars.p_full[i], kFwdSoftmaxWarps);
-      mbar_init(&bars.p_free[i], 1);
       mbar_init(&bars.o_full[i], 1);
       mbar_init(&bars.o_free[i], kFwdSoftmaxWarps);
       mbar_init(&bars.out_full[i], kFwdSoftmaxWarps);
       mbar_init(&bars.out_free[i], 1);
     }
     mbar_init(&bars.s_full, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars.p_full[i], kFwdSoftmaxWarps);
     fence_barrier_init();
   }
   for (int i = tid; i < 2048 / 16; i += kFwdThreads) reinterpret_cast<uint4*>(sZero)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -223,14 +242,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   const uint32_t tS = tmem, tO = tmem + kSP;  // O buffers at +0 / +64
 
   if (warp == 13) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      tma_prefetch_desc(&tm_qkv);
-      for (int n = 0; n < nmine; ++n) {
-        const int item = blockIdx.x + n * gridDim.x;
-        const int b = item / H, h = item - b * H;
-        const int col0 = (h * dh) & ~7;  // 8-column aligned window start inside the Q block
-        const int kb = n % KVB;
+    // ------------------------------------------------------------------ TMA producer (+ Q fix-up)
+    if (lane == 0) tma_prefetch_desc(&tm_qkv);
+    const bool need_fix = (dh & 7) != 0;
+    for (int n = 0; n < nmine; ++n) {
+      const int item = blockIdx.x + n * gridDim.x;
+      const int b = item / H, h = item - b * H;
+      const int col0 = (h * dh) & ~7;  // 8-column aligned window start inside the Q block
+      const int kb = n % KVB;
+      if (lane == 0) {
         if (n >= KVB) mbar_wait(&bars.k_free[kb], ((n / KVB) - 1) & 1, 60);
         mbar_arrive_expect_tx(&bars.k_full[kb], NCH * nrb * 2048);
         for (int ch = 0; ch < NCH; ++ch)
@@ -248,75 +268,93 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
             tma_load_3d(sQ + i * G::QT + ch * G::CSQ, &tm_qkv, &bars.q_full[i], col0 + ch * 8, i * 128, b);
         }
       }
+      __syncwarp();
+      // zero the neighbouring head's 4 columns of every Q tile (window columns [0, 4) or [dh, dh + 4)), then
+      // publish the tile to the issue warp
+      const int z0 = ((h * dh) & 7) ? 0 : dh;
+      for (int i = 0; i < ntq; ++i) {
+        mbar_wait(&bars.q_full[i], n & 1, 71);
+        if (need_fix) {
+          uint8_t* zp = sQ + i * G::QT + (z0 >> 3) * G::CSQ + (z0 & 7) * 2;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) *reinterpret_cast<uint2*>(zp + (r * 32 + lane) * 16) = make_uint2(0u, 0u);
+          fence_proxy_async_smem();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.q_ready[i]);
+      }
     }
-    __syncwarp();
   } else if (warp == 12) {
     // ------------------------------------------------------------------ MMA issue
-    if (lane == 0 && nmine > 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, kKC, 0, 0);
-      const uint32_t idesc_o = umma_idesc_bf16(128, DHP, 0, 1);
-      const uint32_t zero_addr = smem_u32(sZero);
-      auto issue_scores = [&](int i, int kb, int c) {  // S[:, 96c : 96c+96] = Q_i K[96c : 96c+96]^T
-        const uint32_t qa = smem_u32(sQ + i * G::QT), ka = smem_u32(sK + kb * G::KT) + c * kKC * 16;
+    // (all 32 lanes run this code convergently; umma_*_warp elect the issuing lane)
+    const uint32_t idesc_o = umma_idesc_bf16(128, DHP, 0, 1);
+    const uint32_t idesc_s = umma_idesc_bf16(128, kKC, 0, 0);
+    const uint32_t zero_addr = smem_u32(sZero);
+    auto issue_scores = [&](int i, int kb, int c) {  // S[:, 96c : 96c+96] = Q_i K[96c : 96c+96]^T
+      const uint32_t qa = smem_u32(sQ + i * G::QT), ka = smem_u32(sK + kb * G::KT) + c * kKC * 16;
+      const uint64_t qd = umma_smem_desc(qa, G::CSQ, 128, UMMA_SWZ_NONE), kd = umma_smem_desc(ka, G::CSK, 128, UMMA_SWZ_NONE);
 #pragma unroll
-        for (int ks = 0; ks < KSTEPS; ++ks) {
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        if (kZeroTail && ks == KSTEPS - 1) {
           const uint32_t a0 = qa + ks * 2 * G::CSQ, b0 = ka + ks * 2 * G::CSK;
-          const bool tail = kZeroTail && ks == KSTEPS - 1;
-          umma_ss(tS + c * kKC, umma_smem_desc(a0, tail ? zero_addr - a0 : G::CSQ, 128, UMMA_SWZ_NONE),
-                  umma_smem_desc(b0, tail ? zero_addr - b0 : G::CSK, 128, UMMA_SWZ_NONE), idesc_s, ks != 0);
+          umma_ss_warp(tS + c * kKC, umma_smem_desc(a0, zero_addr - a0, 128, UMMA_SWZ_NONE),
+                       umma_smem_desc(b0, zero_addr - b0, 128, UMMA_SWZ_NONE), idesc_s, ks != 0);
+        } else {
+          umma_ss_warp(tS + c * kKC, qd + ks * ((2 * G::CSQ) >> 4), kd + ks * ((2 * G::CSK) >> 4), idesc_s, ks != 0);
         }
-      };
-      uint32_t t = 0, pc = 0;
+      }
+    };
+    if (nmine > 0) {
       // prologue: all score chunks of the first tile
       mbar_wait(&bars.k_full[0], 0, 63);
       mbar_wait(&bars.q_ready[0], 0, 64);
       tc_fence_after();
       for (int c = 0; c < nkc; ++c) issue_scores(0, 0, c);
-      umma_commit(&bars.s_full);
-      umma_commit(&bars.q_free[0]);
-      if (ntq == 1) umma_commit(&bars.k_free[0]);
-      for (int n = 0; n < nmine; ++n) {
-        const int kb = n % KVB;
-        for (int i = 0; i < ntq; ++i, ++t) {
-          const uint32_t ob = t & 1u;
-          if (t >= 2) mbar_wait(&bars.o_free[ob], ((t >> 1) - 1) & 1, 65);
-          if (i == 0) mbar_wait(&bars.v_full[kb], (n / KVB) & 1, 66);
-          const bool has_next = (i + 1 < ntq) || (n + 1 < nmine);
-          const int i1 = i + 1 < ntq ? i + 1 : 0, n1 = i + 1 < ntq ? n : n + 1;
-          const int kb1 = n1 % KVB;
-          const uint32_t va = smem_u32(sV + kb * G::KT), td = tO + ob * 64;
-          for (int c = 0; c < nkc; ++c, ++pc) {
-            const uint32_t pb = pc & 1u;
-            mbar_wait(&bars.p_full[pb], (pc >> 1) & 1, 67);
-            tc_fence_after();
-            const uint32_t pa = smem_u32(sP + pb * G::PB);
-            const int ksteps = min(kKC / 16, (S - c * kKC + 15) / 16);
-            for (int ks = 0; ks < ksteps; ++ks)
-              umma_ss(td, umma_smem_desc(pa + ks * 4096, 2048, 128, UMMA_SWZ_NONE),
-                      umma_smem_desc(va + (c * kKC + ks * 16) * 16, 128, G::CSK, UMMA_SWZ_NONE), idesc_o, (c | ks) != 0);
-            umma_commit(&bars.p_free[pb]);
-            if (c == nkc - 1) {
-              umma_commit(&bars.o_full[ob]);
-              if (i == ntq - 1) umma_commit(&bars.v_free[kb]);
-            }
-            if (has_next) {
-              if (c == 0) {
-                if (i1 == 0) mbar_wait(&bars.k_full[kb1], (n1 / KVB) & 1, 68);
-                mbar_wait(&bars.q_ready[i1], n1 & 1, 69);
-                tc_fence_after();
-              }
-              issue_scores(i1, kb1, c);
-              if (c == nkc - 1) {
-                umma_commit(&bars.s_full);
-                umma_commit(&bars.q_free[i1]);
-                if (i1 == ntq - 1) umma_commit(&bars.k_free[kb1]);
-              }
-            }
+      umma_commit_warp(&bars.s_full);
+      umma_commit_warp(&bars.q_free[0]);
+      if (ntq == 1) umma_commit_warp(&bars.k_free[0]);
+    }
+    uint32_t t = 0;
+    for (int n = 0; n < nmine; ++n) {
+      const int kb = n % KVB;
+      // V as MN-major B: k = key rows (LBO = 128 between 8-row groups), mn = head dim (SBO = chunk stride)
+      const uint64_t vbase = umma_smem_desc(smem_u32(sV + kb * G::KT), 128, G::CSK, UMMA_SWZ_NONE);
+      for (int i = 0; i < ntq; ++i, ++t) {
+        const uint32_t ob = t & 1u;
+        if (t >= 2) mbar_wait(&bars.o_free[ob], ((t >> 1) - 1) & 1, 65);
+        if (i == 0) mbar_wait(&bars.v_full[kb], (n / KVB) & 1, 66);
+        const bool has_next = (i + 1 < ntq) || (n + 1 < nmine);
+        const int i1 = i + 1 < ntq ? i + 1 : 0, n1 = i + 1 < ntq ? n : n + 1;
+        const int kb1 = n1 % KVB;
+        if (has_next) {
+          if (i1 == 0) mbar_wait(&bars.k_full[kb1], (n1 / KVB) & 1, 68);
+          mbar_wait(&bars.q_ready[i1], n1 & 1, 69);
+        }
+        const uint32_t td = tO + ob * 64;
+        for (int c = 0; c < nkc; ++c) {
+          mbar_wait(&bars.p_full[c], t & 1, 67);  // P chunk c sits in TMEM, every warp is done with S chunk c
+          tc_fence_after();
+          if (n == 1) WM_TICK(36 + (i * 4 + c) * 2);
+          const uint64_t vd = vbase + ((c * kKC * 16) >> 4);
+          const int ksteps = min(kKC / 16, (S - c * kKC + 15) / 16);
+#pragma unroll
+          for (int ks = 0; ks < kKC / 16; ++ks)  // 16 keys = 8 packed columns; slice ks/2 keeps its P in its own first 16 columns
+            if (ks < ksteps)
+              umma_ts_warp(td, tS + c * kKC + (ks >> 1) * 32 + (ks & 1) * 8, vd + ks * (256 >> 4), idesc_o, (c | ks) != 0);
+          if (c == nkc - 1) {
+            umma_commit_warp(&bars.o_full[ob]);
+            if (i == ntq - 1) umma_commit_warp(&bars.v_free[kb]);
           }
+          if (has_next) issue_scores(i1, kb1, c);  // executes after the P V products above (issue order)
+          if (n == 1) WM_TICK(37 + (i * 4 + c) * 2);
+        }
+        if (has_next) {
+          umma_commit_warp(&bars.s_full);
+          umma_commit_warp(&bars.q_free[i1]);
+          if (i1 == ntq - 1) umma_commit_warp(&bars.k_free[kb1]);
         }
       }
     }
-    __syncwarp();
   } else if (warp == 14) {
     // ------------------------------------------------------------------ ctx store
     const int pv = dh >> 2;  // 8-byte pieces per row
@@ -345,133 +383,112 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
     const int lq = warp & 3, sl = warp >> 2;   // TMEM lane quarter, 32-column slice of each chunk
     const int row = lq * 32 + lane;            // query row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(lq * 32) << 16;
-    const uint32_t thresh4 = thresh8 * 0x01010101u;
+    const uint32_t thresh4 = (128u - thresh7) * 0x01010101u;  // per-byte addend of the 7-bit keep test
     const float c2 = scale * 1.4426950408889634f;
-    const bool need_fix = (dh & 7) != 0;
-    uint32_t kmask[DROP ? 8 : 1][4];
-    auto gen_masks = [&](int item, int i) {
-      if (!DROP) return;
-      const int qq = i * 128 + row;
-      const uint64_t rowbase = (static_cast<uint64_t>(item) * S + (qq < S ? qq : 0)) * nk16;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int k0 = c * kKC + sl * 32;
-        if (k0 < nk16 * 16) {
-          uint32_t(&ma)[4] = kmask[DROP ? 2 * c : 0];
-          uint32_t(&mb)[4] = kmask[DROP ? 2 * c + 1 : 0];
-          keep_masks16(seed, stream_id, rowbase + (k0 >> 4), thresh4, ma);
-          keep_masks16(seed, stream_id, rowbase + (k0 >> 4) + 1, thresh4, mb);
-#pragma unroll
-          for (int w = 0; w < 4; ++w) { WM_PIN(ma[w]); WM_PIN(mb[w]); }
-        }
-      }
-    };
-    // zero the neighbouring head's 4 columns of Q tile i (window columns [0, front) or [front + dh, 8 * NCH))
-    auto fix_q = [&](int n, int i, int h) {
-      if (sl != 0) return;
-      mbar_wait(&bars.q_full[i], n & 1, 71);
-      if (need_fix) {
-        const int z0 = ((h * dh) & 7) ? 0 : dh;
-        *reinterpret_cast<uint2*>(sQ + i * G::QT + (z0 >> 3) * G::CSQ + row * 16 + (z0 & 7) * 2) = make_uint2(0u, 0u);
-        fence_proxy_async_smem();
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.q_ready[i]);
-    };
-    uint32_t t = 0, pc = 0;
-    if (nmine > 0) {
-      const int item0 = blockIdx.x;
-      fix_q(0, 0, item0 % H);
-      gen_masks(item0, 0);
-    }
+    uint32_t t = 0;
     for (int n = 0; n < nmine; ++n) {
       const int item = blockIdx.x + n * gridDim.x;
-      const int b = item / H, h = item - b * H;
+      const int h = item % H;
       const int front = (h * dh) & 7;
       for (int i = 0; i < ntq; ++i, ++t) {
-        const bool has_next = (i + 1 < ntq) || (n + 1 < nmine);
-        const int i1 = i + 1 < ntq ? i + 1 : 0, n1 = i + 1 < ntq ? n : n + 1;
-        const int item1 = blockIdx.x + n1 * gridDim.x;
-        if (has_next) fix_q(n1, i1, item1 % H);
+#define WM_FTICK(k) do { if (warp == 0 && n == 1) WM_TICK(i * 12 + (k)); } while (0)
+        WM_FTICK(0);
         const int q = i * 128 + row;
+        // dropout group (16 keys) index of this row's key 0: identical numbering in forward and backward
+        const uint64_t rowbase = (static_cast<uint64_t>(item) * S + (q < S ? q : 0)) * nk16;
         mbar_wait(&bars.s_full, t & 1, 72);
         tc_fence_after();
-        // ---- pass 1: row max over this warp's slices
+        WM_FTICK(2);
+        // ---- pass 1: row max over this warp's slices (next chunk's TMEM load in flight under the reduction)
         float mloc = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < nkc; ++c) {
-          const int k0 = c * kKC + sl * 32;
-          if (k0 >= S) break;
-          uint32_t v[32];
-          tmem_ld32(tS + lane_sel + k0, v);
-          tmem_ld_wait();
-          if (k0 + 32 <= S) {
+        {
+          uint32_t va[32], vb[32];
+          tmem_ld32(tS + lane_sel + sl * 32, va);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mloc = fmaxf(mloc, __uint_as_float(v[j]));
-          } else {
+          for (int c = 0; c < 4; ++c) {
+            if (c < nkc) {
+              uint32_t(&cur)[32] = (c & 1) ? vb : va;
+              uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+              tmem_ld_wait();
+              if (c + 1 < nkc) tmem_ld32(tS + lane_sel + (c + 1) * kKC + sl * 32, nxt);
+              const int k0 = c * kKC + sl * 32;
+              if (k0 + 32 <= S) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (k0 + j < S) mloc = fmaxf(mloc, __uint_as_float(v[j]));
+                for (int j = 0; j < 32; ++j) mloc = fmaxf(mloc, __uint_as_float(cur[j]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (k0 + j < S) mloc = fmaxf(mloc, __uint_as_float(cur[j]));
+              }
+            }
           }
         }
         sMax[sl * 128 + row] = mloc;
+        WM_FTICK(3);
         named_bar_sync(1 + lq, 96);
+        WM_FTICK(4);
         const float mrow = fmaxf(fmaxf(sMax[row], sMax[128 + row]), sMax[256 + row]);
         const float mneg = -mrow * c2;
-        // ---- pass 2: exp2, row sum, dropout, P chunk -> smem ring, one mbarrier arrival per chunk and warp
+        // ---- pass 2: exp2, row sum, dropout; P (bf16 pairs) replaces the first 16 columns of the slice in TMEM
         float lsum = 0.0f;
+        {
+          uint32_t va[32], vb[32];
+          tmem_ld32(tS + lane_sel + sl * 32, va);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < nkc) {
-            const uint32_t pb = pc & 1u;
-            if (pc >= 2) mbar_wait(&bars.p_free[pb], ((pc >> 1) - 1) & 1, 73);
-            const int k0 = c * kKC + sl * 32;
-            uint32_t v[32];
-            tmem_ld32(tS + lane_sel + k0, v);
-            tmem_ld_wait();
-            uint32_t pbits[32];
-            if (k0 + 32 <= S) {
+          for (int c = 0; c < 4; ++c) {
+            if (c < nkc) {
+              uint32_t(&cur)[32] = (c & 1) ? vb : va;
+              uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+              tmem_ld_wait();
+              if (c + 1 < nkc) tmem_ld32(tS + lane_sel + (c + 1) * kKC + sl * 32, nxt);
+              const int k0 = c * kKC + sl * 32;
+              uint32_t pk[16];
+              if (k0 + 32 <= S) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float e = fast_exp2(fmaf(__uint_as_float(v[j]), c2, mneg));
-                lsum += e;
-                pbits[j] = DROP ? (__float_as_uint(e) & WM_KEEP32(kmask[DROP ? 2 * c + (j >> 4) : 0], j & 15)) : __float_as_uint(e);
+                for (int w = 0; w < 16; ++w) {
+                  const float e0 = fast_exp2(fmaf(__uint_as_float(cur[2 * w]), c2, mneg));
+                  const float e1 = fast_exp2(fmaf(__uint_as_float(cur[2 * w + 1]), c2, mneg));
+                  lsum += e0 + e1;
+                  pk[w] = pack_bf16x2(e0, e1);
+                }
+              } else {
+#pragma unroll
+                for (int w = 0; w < 16; ++w) {
+                  float e0 = 0.0f, e1 = 0.0f;
+                  if (k0 + 2 * w < S) e0 = fast_exp2(fmaf(__uint_as_float(cur[2 * w]), c2, mneg));
+                  if (k0 + 2 * w + 1 < S) e1 = fast_exp2(fmaf(__uint_as_float(cur[2 * w + 1]), c2, mneg));
+                  lsum += e0 + e1;
+                  pk[w] = pack_bf16x2(e0, e1);
+                }
               }
-            } else {
+              if (DROP) {
+                uint32_t fa[4], fb[4];
+                keep_flags16(seed, stream_id, rowbase + (k0 >> 4), thresh4, fa);
+                keep_flags16(seed, stream_id, rowbase + (k0 >> 4) + 1, thresh4, fb);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float e = 0.0f;
-                if (k0 + j < S) e = fast_exp2(fmaf(__uint_as_float(v[j]), c2, mneg));
-                lsum += e;
-                pbits[j] = DROP ? (__float_as_uint(e) & WM_KEEP32(kmask[DROP ? 2 * c + (j >> 4) : 0], j & 15)) : __float_as_uint(e);
+                for (int w = 0; w < 8; ++w) {
+                  pk[w] &= WM_KEEP_PAIR(fa, 2 * w);
+                  pk[w + 8] &= WM_KEEP_PAIR(fb, 2 * w);
+                }
               }
+              tmem_st16(tS + lane_sel + k0, pk);
+              tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bars.p_full[c]);
+              WM_FTICK(5 + c);
             }
-            uint8_t* pdst = sP + pb * G::PB + (sl * 4) * 2048 + row * 16;
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              uint4 pk;
-              pk.x = pack_bf16x2(__uint_as_float(pbits[g8 * 8 + 0]), __uint_as_float(pbits[g8 * 8 + 1]));
-              pk.y = pack_bf16x2(__uint_as_float(pbits[g8 * 8 + 2]), __uint_as_float(pbits[g8 * 8 + 3]));
-              pk.z = pack_bf16x2(__uint_as_float(pbits[g8 * 8 + 4]), __uint_as_float(pbits[g8 * 8 + 5]));
-              pk.w = pack_bf16x2(__uint_as_float(pbits[g8 * 8 + 6]), __uint_as_float(pbits[g8 * 8 + 7]));
-              *reinterpret_cast<uint4*>(pdst + g8 * 2048) = pk;
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars.p_full[pb]);
-            ++pc;
           }
         }
         sSum[sl * 128 + row] = lsum;
-        // the next tile's keep masks are generated while the tensor pipe finishes this tile's P V
-        if (has_next) gen_masks(item1, i1);
         named_bar_sync(1 + lq, 96);
+        WM_FTICK(9);
         const float tot = sSum[row] + sSum[128 + row] + sSum[256 + row];
         // ---- epilogue: O / (row sum) -> bf16 staging tile (compact [128, dh]); slice sl takes columns [16 sl, 16 sl + 16)
         const uint32_t ob = t & 1u;
         mbar_wait(&bars.o_full[ob], (t >> 1) & 1, 74);
         tc_fence_after();
+        WM_FTICK(10);
         if (t >= 2) mbar_wait(&bars.out_free[ob], ((t >> 1) - 1) & 1, 75);
         if (sl * 16 < DHP) {
           const float inv = drop_scale / tot;
@@ -483,10 +500,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
           for (int j = 0; j < 16; j += 4) {
             const int d = sl * 16 + j - front;  // head-dim index of TMEM column sl*16 + j
             if (d >= 0 && d < dh) {
-              uint2 pk;
-              pk.x = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
-              pk.y = pack_bf16x2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
-              *reinterpret_cast<uint2*>(srow + d * 2) = pk;
+              uint2 o2;
+              o2.x = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+              o2.y = pack_bf16x2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+              *reinterpret_cast<uint2*>(srow + d * 2) = o2;
             }
           }
         }
@@ -497,6 +514,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
           mbar_arrive(&bars.o_free[ob]);
           mbar_arrive(&bars.out_full[ob]);
         }
+        WM_FTICK(11);
       }
     }
   }
@@ -540,7 +558,7 @@ template <int DHP, bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ ctx,
                 const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
-                __nv_bfloat16* __restrict__ dqkv, int S, int H, int dh, float scale, uint32_t thresh8,
+                __nv_bfloat16* __restrict__ dqkv, int S, int H, int dh, float scale, uint32_t thresh7,
                 float drop_scale, uint64_t seed, uint64_t stream_id) {
   constexpr uint32_t RS = TileGeom<DHP>::RS;
   constexpr uint32_t RS_P = (128 / 8) * 128;  // P / dS tiles are [128 q, 128 keys]
@@ -569,7 +587,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   const __nv_bfloat16* dobase = dctx + static_cast<size_t>(b) * S * D + h * dh;
   const int nt = (S + 127) / 128;
   const int grp_per_row = (S + 15) / 16;
-  const uint32_t thresh4 = thresh8 * 0x01010101u;
+  const uint32_t thresh4 = (128u - thresh7) * 0x01010101u;  // per-byte addend of the 7-bit keep test
 
   if (warp == 0) WM_TICK(32);
   {  // two rounds of two tiles keep the in-flight loads within the 544-thread register budget
@@ -796,38 +814,38 @@ static int attn_chunks(int dh) { return (dh & 7) ? (dh + 4) / 8 : dh / 8; }
 
 template <int NCH>
 static int launch_fwd_t(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, int B, int S, int H, int dh,
-                        float scale, uint32_t thresh8, float dscale, uint64_t seed, uint64_t stream_id,
+                        float scale, uint32_t thresh7, float dscale, uint64_t seed, uint64_t stream_id,
                         cudaStream_t stream) {
   CUtensorMap tm;
   const int D = H * dh;
   int rc = make_tmap_bf16_rows3d(&tm, qkv, 3 * D, S, B, 3 * D, 128);
   if (rc != WM_OK) return rc;
   const int smem = AttnFwdGeom<NCH>::kSmem;
-  auto kern = thresh8 ? attn_fwd_kernel<NCH, true> : attn_fwd_kernel<NCH, false>;
+  auto kern = thresh7 ? attn_fwd_kernel<NCH, true> : attn_fwd_kernel<NCH, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
   const int nitems = B * H;
   const int grid = nitems < attn_sm_count() ? nitems : attn_sm_count();
-  kern<<<grid, kFwdThreads, smem, stream>>>(tm, ctx, lse, nitems, S, H, dh, scale, thresh8, dscale, seed, stream_id);
+  kern<<<grid, kFwdThreads, smem, stream>>>(tm, ctx, lse, nitems, S, H, dh, scale, thresh7, dscale, seed, stream_id);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 template <int DHP>
 static int launch_bwd_t(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __nv_bfloat16* dctx,
                         const float* lse, __nv_bfloat16* dqkv, int B, int S, int H, int dh, float scale,
-                        uint32_t thresh8, float dscale, uint64_t seed, uint64_t stream_id, cudaStream_t stream) {
+                        uint32_t thresh7, float dscale, uint64_t seed, uint64_t stream_id, cudaStream_t stream) {
   const int smem = 4 * kSP * DHP * 2 + 2 * 128 * 128 * 2 + 2 * kSP * 4 + 256;
-  auto kern = thresh8 ? attn_bwd_kernel<DHP, true> : attn_bwd_kernel<DHP, false>;
+  auto kern = thresh7 ? attn_bwd_kernel<DHP, true> : attn_bwd_kernel<DHP, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
-  kern<<<B * H, kBwdThreads, smem, stream>>>(qkv, ctx, dctx, lse, dqkv, S, H, dh, scale, thresh8, dscale, seed,
+  kern<<<B * H, kBwdThreads, smem, stream>>>(qkv, ctx, dctx, lse, dqkv, S, H, dh, scale, thresh7, dscale, seed,
                                              stream_id);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
-// drop_thresh is the 16-bit threshold used everywhere else (round(p*65536)); attention rounds it to 8 bits
-static void attn_drop_params(uint32_t drop_thresh16, uint32_t* thresh8, float* scale) {
-  *thresh8 = (drop_thresh16 + 128u) >> 8;
-  *scale = *thresh8 ? 256.0f / static_cast<float>(256u - *thresh8) : 1.0f;
+// drop_thresh is the 16-bit threshold used everywhere else (round(p*65536)); attention rounds it to 7 bits
+static void attn_drop_params(uint32_t drop_thresh16, uint32_t* thresh7, float* scale) {
+  *thresh7 = (drop_thresh16 + 256u) >> 9;
+  *scale = *thresh7 ? 128.0f / static_cast<float>(128u - *thresh7) : 1.0f;
 }
 
 int launch_attn_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, int B, int S, int H, int dh,

@@ -173,6 +173,56 @@ WM_DEVICE void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// Warp-convergent variants: EVERY lane of the warp executes the call (uniform control flow, so the compiler keeps
+// descriptor arithmetic in uniform registers and emits no per-active-lane issue loop); one elected lane issues.
+WM_DEVICE void umma_ss_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b32 r;\n\t"
+      "elect.sync r|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+WM_DEVICE void umma_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      ".reg .b32 r;\n\t"
+      "elect.sync r|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+// A operand from tensor memory (128 lanes x 8 columns of packed bf16x2 per k-step of 16), B from shared memory
+WM_DEVICE void umma_ts_warp(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b32 r;\n\t"
+      "elect.sync r|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> TMEM: lane t of the warp writes 16 consecutive 32-bit columns of TMEM lane (lane_base + t)
+WM_DEVICE void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+WM_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+// warp index that the compiler can prove warp-uniform (role dispatch on it stays convergent)
+WM_DEVICE int warp_idx_uniform() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
+
 // ---- cta_group::2 (CTA pair) variants: one MMA spans two SMs (M = 256), operands are split between the two
 // CTAs' shared memories, the accumulator rows between their TMEMs. Only the leader CTA (cluster rank 0) issues
 // MMAs and commits; both CTAs issue TMA loads that signal the LEADER's mbarrier. ----
