@@ -86,11 +86,16 @@ int wm_umma_probe(const void* A_bf16, const void* B_bf16, float* D, int N, int K
 
 /* ---- attention: F.scaled_dot_product_attention inside nn.MultiheadAttention
  *      (torch:nn/functional.py:6666-6696). qkv: bf16 [B*S, 3*H*dh] (Q|K|V, head-major columns);
- *      ctx: bf16 [B*S, H*dh]; lse: fp32 [B*H, S]. ------------------------------------------------- */
-int wm_attn_fwd(const void* qkv_bf16, void* ctx_bf16, float* lse, int B, int S, int H, int dh, float dropout_p,
-                uint64_t seed, uint64_t stream_id, void* stream);
+ *      ctx: bf16 [B*S, H*dh]; lse: fp32 [B*H, S]. S <= 384, dh in {12..48} a multiple of 4, H*dh a multiple of 8.
+ *      With dropout_p > 0 the forward call also writes its keep decisions (one bit per (query, key), buffer of
+ *      wm_attn_dropout_words_bytes) and the backward call reads them back instead of re-deriving the Philox stream;
+ *      drop_words may be NULL when dropout_p == 0. workspace: wm_attn_bwd_workspace_bytes bytes (row statistics). */
+size_t wm_attn_dropout_words_bytes(int B, int S, int H);
+size_t wm_attn_bwd_workspace_bytes(int B, int S, int H);
+int wm_attn_fwd(const void* qkv_bf16, void* ctx_bf16, float* lse, void* drop_words, int B, int S, int H, int dh,
+                float dropout_p, uint64_t seed, uint64_t stream_id, void* stream);
 int wm_attn_bwd(const void* qkv_bf16, const void* ctx_bf16, const void* dctx_bf16, const float* lse,
-                void* dqkv_bf16, int B, int S, int H, int dh, float dropout_p, uint64_t seed, uint64_t stream_id,
+                void* dqkv_bf16, const void* drop_words, void* workspace, int B, int S, int H, int dh, float dropout_p,
                 void* stream);
 
 /* ---- LayerNorm (post-LN norm1 / norm2, torch:nn/modules/transformer.py:951-957; eps 1e-5) ------------- */

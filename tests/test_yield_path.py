@@ -157,12 +157,16 @@ def test_yield_model_matches_reference_golden(kind, monkeypatch):
     assert _rel(pred.detach().cpu().numpy(), g["pred"]) <= 5e-3, (pred.flatten(), g["pred"].flatten())
     assert abs(loss.item() - g["loss"][0]) <= 2e-3 * abs(g["loss"][0]), (loss.item(), g["loss"][0])
     worst = (0.0, "")
+    gnorm = np.sqrt(sum(float(np.linalg.norm(v.astype(np.float64))) ** 2 for k, v in g.items() if k.startswith("grad/")))
     for name, p in model.named_parameters():
         r = g["grad/" + name].astype(np.float64)
         assert p.grad is not None, name
         got = p.grad.detach().float().cpu().numpy().astype(np.float64)
         nr = np.linalg.norm(r)
-        assert abs(np.linalg.norm(got) - nr) <= 1e-2 * nr + 1e-9, name
+        if nr < 1e-6 * gnorm:  # mathematically zero (the bias in front of the pooling softmax): only rounding noise
+            assert np.linalg.norm(got) < 1e-5 * gnorm, name
+            continue
+        assert abs(np.linalg.norm(got) - nr) <= 1e-2 * nr, name
         rel = _rel(got, r)
         worst = max(worst, (rel, name))
         assert rel <= 3e-2, f"{kind} yield: grad {name} rel err {rel:.4g}"

@@ -33,24 +33,3 @@ for p in (0.0, 0.1):
         print(f"{names[i]:40s} +{t[i] - prev:7d}  (@{t[i] - t[0]})")
         prev = t[i]
 
-dctx = (torch.randn(B * S, H * dh, device="cuda") * 0.5).to(torch.bfloat16)
-for p in (0.0, 0.1):
-    ctx, lse = ops.attn_fwd(qkv, B, S, H, dh, dropout_p=p, seed=1, stream_id=1)
-    for _ in range(3):
-        ops.attn_bwd(qkv, ctx, dctx, lse, B, S, H, dh, dropout_p=p, seed=1, stream_id=1)
-    buf = (C.c_longlong * 64)()
-    lib().wm_debug_ticks(buf, 64)
-    t = list(buf)
-    names = {32: "start", 49: "Q tile issued", 50: "K,V tiles issued", 33: "dO issued", 51: "delta done", 34: "landed + setup sync"}
-    for i in range(3):
-        names[35 + i * 3] = f"pair(0,{i}) top"
-        names[36 + i * 3] = f"pair(0,{i}) S/dP ready"
-        names[37 + i * 3] = f"pair(0,{i}) P/dS written"
-    for j in range(3):
-        names[44 + j] = f"key tile {j} done"
-    names[48] = "all stored"
-    prev = t[32]
-    print(f"--- attn_bwd p={p}: total {t[48] - t[32]} cycles")
-    for i in sorted(names, key=lambda k: t[k]):
-        print(f"{names[i]:26s} +{t[i] - prev:7d}  (@{t[i] - t[32]})")
-        prev = t[i]

@@ -71,7 +71,7 @@ def main():
             ms = timeit(lambda: ops.attn_fwd(qkv, B, S, H, f, dropout_p=p, seed=1, stream_id=1), a.reps)
             rec(f"attn_fwd p={p}", ms, 4.0 * S * S * D * B, per_layer=L)
             ctx, lse = ops.attn_fwd(qkv, B, S, H, f, dropout_p=p, seed=1, stream_id=1)
-            ms = timeit(lambda: ops.attn_bwd(qkv, ctx, x, lse, B, S, H, f, dropout_p=p, seed=1, stream_id=1), a.reps)
+            ms = timeit(lambda: ops.attn_bwd(qkv, ctx, x, lse, B, S, H, f, dropout_p=p), a.reps)
             rec(f"attn_bwd p={p}", ms, 8.0 * S * S * D * B, per_layer=L)
     if a.only in ("", "mem"):
         gamma, beta = torch.ones(D, device=dev), torch.zeros(D, device=dev)

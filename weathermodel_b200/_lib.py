@@ -42,8 +42,10 @@ SIGNATURES = {
     "wm_gemm_wgrad_workspace_bytes": (_sz, [_i, _i, _i]),
     "wm_gemm_wgrad": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "wm_umma_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "wm_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _u64, _u64, _vp]),
-    "wm_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _u64, _u64, _vp]),
+    "wm_attn_dropout_words_bytes": (_sz, [_i, _i, _i]),
+    "wm_attn_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "wm_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _u64, _u64, _vp]),
+    "wm_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "wm_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "wm_layernorm_bwd_workspace_bytes": (_sz, [_i, _i]),
     "wm_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _u64, _u64, _vp, _vp]),

@@ -121,18 +121,19 @@ int wm_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_mn
   return launch_umma_probe(A, B, D, N, K, a_mn, b_mn, S_(stream));
 }
 
-int wm_attn_fwd(const void* qkv, void* ctx, float* lse, int B, int S, int H, int dh, float dropout_p, uint64_t seed,
-                uint64_t stream_id, void* stream) {
+size_t wm_attn_dropout_words_bytes(int B, int S, int H) { return attn_dropout_words_bytes(B, S, H); }
+size_t wm_attn_bwd_workspace_bytes(int B, int S, int H) { return attn_bwd_workspace_bytes(B, S, H); }
+int wm_attn_fwd(const void* qkv, void* ctx, float* lse, void* drop_words, int B, int S, int H, int dh, float dropout_p,
+                uint64_t seed, uint64_t stream_id, void* stream) {
   if (!qkv || !ctx) return WM_ERR_ARG;
-  const uint32_t t = thresh16(dropout_p);
-  return launch_attn_fwd(CB(qkv), MB(ctx), lse, B, S, H, dh, t, keep_scale(t), seed, stream_id, S_(stream));
+  return launch_attn_fwd(CB(qkv), MB(ctx), lse, static_cast<uint32_t*>(drop_words), B, S, H, dh, thresh16(dropout_p), seed,
+                         stream_id, S_(stream));
 }
-int wm_attn_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv, int B, int S,
-                int H, int dh, float dropout_p, uint64_t seed, uint64_t stream_id, void* stream) {
+int wm_attn_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv, const void* drop_words,
+                void* workspace, int B, int S, int H, int dh, float dropout_p, void* stream) {
   if (!qkv || !ctx || !dctx || !lse || !dqkv) return WM_ERR_ARG;
-  const uint32_t t = thresh16(dropout_p);
-  return launch_attn_bwd(CB(qkv), CB(ctx), CB(dctx), lse, MB(dqkv), B, S, H, dh, t, keep_scale(t), seed, stream_id,
-                         S_(stream));
+  return launch_attn_bwd(CB(qkv), CB(ctx), CB(dctx), lse, MB(dqkv), static_cast<const uint32_t*>(drop_words), workspace, B,
+                         S, H, dh, thresh16(dropout_p), S_(stream));
 }
 
 int wm_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M,

@@ -2,97 +2,22 @@
 //
 // Replaces F.scaled_dot_product_attention(q, k, v, None, dropout_p, False) as reached from
 // nn.TransformerEncoderLayer (torch/nn/functional.py:6666-6696; reference call site
-// src/pretraining/models/weatherbert.py:45-54,116-118). Head dims of this model family are 12/20/28/36:
-// Q/K/V rows are copied from the token-major [M, 3D] QKV activation into zero-padded, UNSWIZZLED
-// canonical core-matrix tiles in shared memory (8 rows x 16 B per core matrix), which one and the same
-// tile can feed to tcgen05.mma either K-major (contract over head dim) or MN-major (contract over rows).
-//
-// One CTA per (batch, head); thread t owns query row t of the current 128-row tile (TMEM lane t), so
-// row max / row sum / LSE / delta are plain per-thread scalars -- no shuffles, no atomics.
-//   fwd : pass 1 row max over 64-key score chunks, pass 2 exp2 + dropout + P(bf16)->smem, O += P V.
-//   bwd : per (kv tile j, q tile i): S = Q K^T, dP = dO V^T in TMEM; P, dS -> smem (bf16);
-//         dV_j += P^T dO, dK_j += dS^T Q, dQ_i += dS K; all five accumulators live in TMEM (<= 496 cols).
-// Dropout on P uses Philox4x32-10 keyed by (seed, stream, (bh*S + q)*ceil(S/16) + k/16), 8 bits / element
-// (keep iff (byte & 0x7F) >= thresh7), regenerated identically in backward.
+// src/pretraining/models/weatherbert.py:45-54,116-118). Head dims of this model family are 12/20/28/36.
+// Both kernels are persistent (one CTA per SM walks over (batch, head) items), warp-specialised (TMA producer,
+// MMA issue, elementwise, store) and keep probabilities in tensor memory; see the comments in front of each.
+// Operand tiles are UNSWIZZLED canonical core-matrix columns: an 8-column chunk of R rows is R consecutive
+// 16-byte rows (elem(r, d) at (d/8)*R*16 + r*16 + (d%8)*2), which one and the same tile can feed to tcgen05.mma
+// either K-major (contract over head dim: LBO = R*16, SBO = 128) or MN-major (contract over rows: LBO = 128,
+// SBO = R*16).
+// Dropout on P: one Philox4x32-7 block keyed by (seed, stream, (bh*S + q)*ceil(S/16) + k/16) decides 16 consecutive
+// keys of a query row, one byte each; the forward kernel also stores the decisions as one 32-bit word per
+// (query row, 32-key slice) for the backward kernel.
 #include "wm_kernels.h"
 
 namespace wm {
 
-constexpr int kAttThreads = 128;
-constexpr int kSP = 384;  // key rows staged per head (S <= 384)
-
-// canonical unswizzled tile [rows, DHP]: elem(r, d) at (r/8)*RS + (d/8)*128 + (r%8)*16 + (d%8)*2
-template <int DHP>
-struct TileGeom {
-  static constexpr uint32_t RS = (DHP / 8) * 128;
-};
-
-// copy rows [0, S) of one head slice (row pitch ld elements, dh valid columns) into a canonical tile of
-// `rows_alloc` rows, zero-filling pad columns and pad rows.
-// Asynchronous (LDGSTS) 8-byte pieces: every thread queues all of its pieces back to back and the
-// caller waits once (cp_async_wait_all) -- the first version used ld.global + st.shared per piece and paid one
-// DRAM round trip per loop iteration (~36 per thread), which was most of the kernel time.
-WM_DEVICE void cp_async8(void* smem_dst, const void* gmem_src, bool valid) {
-  const uint32_t d = smem_u32(smem_dst);
-  const int sz = valid ? 8 : 0;  // src-size 0 => destination is zero-filled
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
-}
-WM_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
-// Stage NT head slices ([S rows, dh] each, row pitch ld[t]) into canonical tiles.
-//  phase 1: every thread issues ALL of its 8-byte global loads into registers. Indexing is warp-structured
-//           (lane -> (row within the warp's row group, piece), rows advance by a constant) so a piece costs a
-//           handful of integer instructions; the first versions spent ~10k cycles per CTA on index arithmetic
-//           and per-piece zero fills (profiles/r01_attn_phase_ticks.txt).
-//  phase 2: the padding (16-byte chunk columns at/after dh, rows >= S) is zeroed with 16-byte stores while the
-//           loads are in flight;  phase 3: barrier, then the data pieces are stored (they overlap the first
-//           zeroed chunk when dh % 8 == 4).
-template <int DHP, int NT, int kIters>
-WM_DEVICE void load_head_tiles(uint8_t* const (&tile)[NT], const __nv_bfloat16* const (&src)[NT], const int (&ld)[NT],
-                               int S, int rows_alloc, int dh) {
-  constexpr uint32_t RS = TileGeom<DHP>::RS;
-  const int pv = dh >> 2;                   // valid 8-byte pieces per row
-  const int rpi = 32 / pv;                  // rows covered by one warp instruction
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int rsub = lane / pv, p = lane - rsub * pv;
-  const bool lane_on = rsub < rpi;
-  const int rstep = rpi * nwarps;
-  const uint32_t poff = (p >> 1) * 128 + (p & 1) * 8;
-  uint2 v[NT][kIters];
-#pragma unroll
-  for (int t = 0; t < NT; ++t) {
-    const uint2* g = reinterpret_cast<const uint2*>(src[t] + static_cast<size_t>(warp * rpi + rsub) * ld[t]) + p;
-    const size_t gstep = static_cast<size_t>(rstep) * ld[t] / 4;  // in uint2 units (ld % 4 == 0)
-#pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int r = warp * rpi + rsub + it * rstep;
-      if (lane_on && r < S) v[t][it] = __ldg(g + it * gstep);
-    }
-  }
-  // zero the padding: chunk columns [dh / 8, DHP / 8) of every row, and whole rows [S, rows_alloc)
-  const int cz = dh >> 3, nz = (DHP >> 3) - cz;
-  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-  for (int t = 0; t < NT; ++t) {
-    for (int i = threadIdx.x; i < (rows_alloc >> 3) * nz * 8; i += blockDim.x) {
-      const int g = i / (nz * 8), w = i - g * (nz * 8);  // w = chunk-in-pad * 8 + row-in-group
-      *reinterpret_cast<uint4*>(tile[t] + g * RS + (cz + (w >> 3)) * 128 + (w & 7) * 16) = z4;
-    }
-    for (int i = threadIdx.x; i < (rows_alloc - S) * cz; i += blockDim.x) {
-      const int rr = S + i / cz, c = i - (i / cz) * cz;
-      *reinterpret_cast<uint4*>(tile[t] + (rr >> 3) * RS + c * 128 + (rr & 7) * 16) = z4;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int t = 0; t < NT; ++t) {
-#pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int r = warp * rpi + rsub + it * rstep;
-      if (lane_on && r < S) *reinterpret_cast<uint2*>(tile[t] + (r >> 3) * RS + (r & 7) * 16 + poff) = v[t][it];
-    }
-  }
-}
+constexpr int kSP = 384;                   // key rows staged per head (S <= 384)
+constexpr int kAttnMaskSlices = kSP / 32;  // 32-key slices per query row in the dropout word buffer
 
 // Dropout on attention probabilities: one Philox4x32-7 block (the 7-round variant is the Crush-resistant
 // minimum of the Random123 paper; nothing here has to match torch's stream) decides 16 consecutive keys of one
@@ -117,18 +42,9 @@ WM_DEVICE uint32_t keep_pair_mask(uint32_t fword, uint32_t sel) {
 }
 #define WM_PAIR_SEL(j) ((((j) & 3) | 8u) * 0x11u | ((((j) & 3) + 1u) | 8u) * 0x1100u)
 #define WM_KEEP_PAIR(f, j) keep_pair_mask((f)[(j) >> 2], WM_PAIR_SEL(j))
-// byte-mask form (0xFF in every kept byte) used by the v4 backward kernel
-WM_DEVICE void keep_masks16(uint64_t seed, uint64_t stream, uint64_t grp, uint32_t add4, uint32_t (&m)[4]) {
-  uint32_t f[4];
-  keep_flags16(seed, stream, grp, add4, f);
-#pragma unroll
-  for (int w = 0; w < 4; ++w) m[w] = ((f[w] >> 7) & 0x01010101u) * 0xFFu;
-}
 // pins a value in a register at this point of the instruction stream: without it the compiler sinks the (pure)
 // Philox arithmetic below the mbarrier wait it is supposed to overlap with
 #define WM_PIN(x) asm volatile("" : "+r"(x))
-// all-ones / all-zeros 32-bit mask of element j (0..15) of the group
-#define WM_KEEP32(m, j) __byte_perm((m)[(j) >> 2], 0u, 0x1111u * ((j) & 3))
 
 WM_DEVICE void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -187,8 +103,8 @@ struct AttnFwdGeom {
 template <int NCH, bool DROP>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ ctx,
-                float* __restrict__ lse_out, int nitems, int S, int H, int dh, float scale, uint32_t thresh7,
-                float drop_scale, uint64_t seed, uint64_t stream_id) {
+                float* __restrict__ lse_out, uint32_t* __restrict__ drop_words, int nitems, int S, int H, int dh,
+                float scale, uint32_t thresh7, float drop_scale, uint64_t seed, uint64_t stream_id) {
   using G = AttnFwdGeom<NCH>;
   constexpr int DHP = G::DHP, KVB = G::KVB, KSTEPS = DHP / 16;
   constexpr bool kZeroTail = (NCH & 1) != 0;  // last k-step: second core-matrix column comes from the zero chunk
@@ -470,6 +386,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
                   pk[w] &= WM_KEEP_PAIR(fa, 2 * w);
                   pk[w + 8] &= WM_KEEP_PAIR(fb, 2 * w);
                 }
+                if (drop_words) {  // bit k = keep flag of key k0 + k: the backward kernel reads these instead of Philox
+                  uint32_t bits = 0u;
+#pragma unroll
+                  for (int w = 3; w >= 0; --w) bits = (bits << 4) | ((((fb[w] >> 7) & 0x01010101u) * 0x01020408u) >> 24);
+#pragma unroll
+                  for (int w = 3; w >= 0; --w) bits = (bits << 4) | ((((fa[w] >> 7) & 0x01010101u) * 0x01020408u) >> 24);
+                  drop_words[(static_cast<size_t>(item) * kAttnMaskSlices + (k0 >> 5)) * kSP + q] = bits;
+                }
               }
               tmem_st16(tS + lane_sel + k0, pk);
               tmem_st_wait();
@@ -527,270 +451,443 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: 16 warps. Warp w reads TMEM lane quarter w%4 (query rows of tile i) and owns 32 of the 128 key
-// columns of tile j (w/4). Per (j, i): S = Q_i K_j^T and dP = dO_i V_j^T land in TMEM, the warps write
-// P and dS (bf16) to smem, then THREE threads issue in parallel {dV_j += P^T dO_i, dK_j += dS^T Q_i},
-// {dQ_i += dS K_j} and {next pair's S, dP}; each commits to the same 3-arrival mbarrier.
-// No validity masks are needed: padded query / key rows are zero in every staged tile, so whatever P and dS
-// hold there is multiplied by zero rows or lands in rows that are never stored.
+// backward: persistent, warp-specialised, TMA-fed; TRANSPOSED score tiles so that P^T and dS^T can feed the
+// tensor core straight from tensor memory.
+//   warps 0-15  elementwise, two groups of 8 that ping-pong over the stream of half-tiles: group g&1 owns TMEM
+//               region g&1. A half-tile is (key tile j: 128 keys = TMEM lanes) x (64 query rows = columns);
+//               warp w of a group reads lane quarter w%4 (32 keys) and the 32-query column slice (w/4)%2.
+//   warp 16     MMA issue (whole warp convergent, one elected lane)
+//   warp 17     TMA producer: K_j/V_j tiles (double buffered, fixed up), Q/dO half-tiles + dropout words (ring)
+//   warp 18     dQ/dK/dV store: drains five bf16 staging tiles with row-contiguous 8-byte stores
+// Per half-tile (j, ih):   S^T = K_j Q_ih^T and dP^T = V_j dO_ih^T land in region r (2 x 64 fp32 columns);
+//   the group turns them into P^T and dS^T (packed bf16, written back IN PLACE with tcgen05.st) and also parks dS^T
+//   in shared memory; then dV_j += P^T dO_ih and dK_j += dS^T Q_ih take their A operand from TMEM, and once both
+//   halves of query tile i are there dQ_i += dS_i K_j reads dS from shared memory (MN-major A). The next-but-one
+//   half-tile's S^T / dP^T are queued into the same region right behind (tcgen05.mma executes in issue order).
+// All five accumulators (dV_j, dK_j, dQ_0..2) stay in TMEM: 2*128 + 5*48 = 496 columns.
+// Padded query / key rows are zero in every staged tile (TMA zero fill), so no validity masks are needed: whatever
+// P and dS hold there is multiplied by zero rows or lands in rows that are never stored; P is clamped to <= 1
+// so that nothing becomes inf * 0.
+// Dropout: the forward kernel stores its keep decisions as one 32-bit word per (query row, 32-key slice); a thread
+// here owns one key (bit = lane) and walks over query rows, so it shifts its bit into the sign position
+// (regenerating Philox in this transposed order would cost one Philox block per element).
 // ------------------------------------------------------------------------------------------------
-constexpr int kBwdThreads = 544;  // 16 elementwise warps + 1 MMA-issue warp
+constexpr int kBwdEwWarps = 16;
+constexpr int kBwdThreads = 32 * 19;
 
-template <int DHP>
-WM_DEVICE void store_acc_chunk(uint32_t taddr, __nv_bfloat16* dst, int c0, int dh, bool valid) {
-  uint32_t v[16];
-  tmem_ld16(taddr + c0, v);
-  tmem_ld_wait();
-  if (valid) {
-#pragma unroll
-    for (int jj = 0; jj < 16; jj += 4) {
-      if (c0 + jj < dh) {
-        uint2 pk;
-        pk.x = pack_bf16x2(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]));
-        pk.y = pack_bf16x2(__uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
-        *reinterpret_cast<uint2*>(dst + c0 + jj) = pk;
-      }
+struct AttnBwdBars {
+  uint64_t kv_full[2], kv_ready[2], kv_free[2];
+  uint64_t qd_full[4], qd_free[4];
+  uint64_t st_full[3];
+  uint64_t sdp_full[2], pds_full[2];
+  uint64_t ds_free[2];
+  uint64_t acc_full, acc_free;
+  uint64_t out_full[5], out_free[5];
+};
+
+template <int NCH>
+struct AttnBwdGeom {
+  static constexpr int DHP = (NCH * 8 + 15) / 16 * 16;
+  static constexpr int RQ = NCH <= 5 ? 4 : 3;          // Q/dO half-tile ring depth
+  static constexpr uint32_t CS128 = 128 * 16, CS64 = 64 * 16;
+  static constexpr uint32_t T128 = NCH * CS128, T64 = NCH * CS64;
+  static constexpr uint32_t SLOT = 2 * T64 + 1024;     // Q half-tile, dO half-tile, 4 x 64 dropout words
+  static constexpr uint32_t DSB = 128 * 128 * 2;       // dS tile [16 q chunks][128 keys][16 B]
+  static constexpr uint32_t OUTB = NCH * 8 * 2 * 128;  // staging tile (>= 128 * dh * 2)
+  static constexpr uint32_t STB = kSP * 8;             // per-row statistics of one head (float2)
+  static constexpr uint32_t kSmem = 4 * T128 + CS128 + RQ * SLOT + 2 * DSB + 5 * OUTB + 3 * STB + 2048 + 128;
+};
+
+// per (batch, head, query row): x = -lse * log2(e) + log2(drop_scale), y = (sum_d dO * O) * scale / drop_scale;
+// rows >= S are zero. One thread per (b, q, h); h runs fastest so a warp reads whole token rows.
+__global__ void attn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
+                                      const float* __restrict__ lse, float2* __restrict__ stats, int B, int S, int H,
+                                      int dh, float scale, float drop_scale) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * kSP * H;
+  if (idx >= total) return;
+  const int h = static_cast<int>(idx % H);
+  const int q = static_cast<int>((idx / H) % kSP);
+  const int b = static_cast<int>(idx / (static_cast<long long>(H) * kSP));
+  float2 out = make_float2(0.0f, 0.0f);
+  if (q < S) {
+    const size_t off = (static_cast<size_t>(b) * S + q) * (static_cast<size_t>(H) * dh) + static_cast<size_t>(h) * dh;
+    const uint2* po = reinterpret_cast<const uint2*>(ctx + off);
+    const uint2* pd = reinterpret_cast<const uint2*>(dctx + off);
+    float acc = 0.0f;
+    for (int p = 0; p < dh / 4; ++p) {
+      const uint2 o = __ldg(po + p), d = __ldg(pd + p);
+      acc = fmaf(bf16_lo(o.x), bf16_lo(d.x), acc);
+      acc = fmaf(bf16_hi(o.x), bf16_hi(d.x), acc);
+      acc = fmaf(bf16_lo(o.y), bf16_lo(d.y), acc);
+      acc = fmaf(bf16_hi(o.y), bf16_hi(d.y), acc);
     }
+    out.x = -lse[(static_cast<size_t>(b) * H + h) * S + q] * 1.4426950408889634f + log2f(drop_scale);
+    out.y = acc * scale / drop_scale;
   }
+  stats[(static_cast<size_t>(b) * H + h) * kSP + q] = out;
 }
 
-template <int DHP, bool DROP>
+template <int NCH, bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
-attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ ctx,
-                const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
-                __nv_bfloat16* __restrict__ dqkv, int S, int H, int dh, float scale, uint32_t thresh7,
-                float drop_scale, uint64_t seed, uint64_t stream_id) {
-  constexpr uint32_t RS = TileGeom<DHP>::RS;
-  constexpr uint32_t RS_P = (128 / 8) * 128;  // P / dS tiles are [128 q, 128 keys]
-  constexpr int NCH = DHP / 16;               // 16-column chunks per accumulator
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
+                const __grid_constant__ CUtensorMap tm_do, const float2* __restrict__ stats,
+                const uint32_t* __restrict__ drop_words, __nv_bfloat16* __restrict__ dqkv, int nitems, int S, int H,
+                int dh, float scale, float drop_scale) {
+  using G = AttnBwdGeom<NCH>;
+  constexpr int DHP = G::DHP, KSTEPS = DHP / 16, RQ = G::RQ, NCG = DHP / 16;
+  constexpr bool kZeroTail = (NCH & 1) != 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kSP * DHP * 2;
-  uint8_t* sV = sK + kSP * DHP * 2;
-  uint8_t* sdO = sV + kSP * DHP * 2;
-  uint8_t* sP = sdO + kSP * DHP * 2;
-  uint8_t* sdS = sP + 128 * 128 * 2;
-  float* sLse = reinterpret_cast<float*>(sdS + 128 * 128 * 2);  // [384] -lse * log2(e) (+ log2(drop_scale))
-  float* sDelta = sLse + kSP;                                   // [384] delta * scale
-  __shared__ uint64_t bar;
+  uint8_t* sK = smem;                       // [2][T128]
+  uint8_t* sV = sK + 2 * G::T128;           // [2][T128] (+ one chunk of slack for N = DHP > 8 NCH reads)
+  uint8_t* sRing = sV + 2 * G::T128 + G::CS128;
+  uint8_t* sdS = sRing + RQ * G::SLOT;      // [2][DSB]
+  uint8_t* sOut = sdS + 2 * G::DSB;         // [5][OUTB]: dK_j, dV_j, dQ_0..2
+  uint8_t* sStat = sOut + 5 * G::OUTB;      // [3][STB]: the producer runs up to two heads ahead when S <= 128
+  uint8_t* sZero = sStat + 3 * G::STB;
+  __shared__ AttnBwdBars bars;
   __shared__ uint32_t tmem_slot;
 
+  const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const int D = H * dh;
-  const int ld = 3 * D;
-  const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = warp >> 2;               // 32-key column slice of the current key tile
-  const int row = (warp & 3) * 32 + lane;  // row inside a 128-row tile == TMEM lane
-  const __nv_bfloat16* qbase = qkv + static_cast<size_t>(b) * S * ld + h * dh;
-  const __nv_bfloat16* obase = ctx + static_cast<size_t>(b) * S * D + h * dh;
-  const __nv_bfloat16* dobase = dctx + static_cast<size_t>(b) * S * D + h * dh;
-  const int nt = (S + 127) / 128;
-  const int grp_per_row = (S + 15) / 16;
-  const uint32_t thresh4 = (128u - thresh7) * 0x01010101u;  // per-byte addend of the 7-bit keep test
+  const int nt = (S + 127) / 128;   // key tiles == query tiles per head
+  const int nh = 2 * nt;            // 64-row query half-tiles per key tile
+  const int nmine = nitems > static_cast<int>(blockIdx.x) ? (nitems - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int nJ = nmine * nt;        // key tiles this CTA walks through
+  const int nG = nJ * nh;           // half-tiles this CTA walks through
 
-  if (warp == 0) WM_TICK(32);
-  {  // two rounds of two tiles keep the in-flight loads within the 544-thread register budget
-    constexpr int kIt = (kSP + (32 / (DHP / 4)) * (kBwdThreads / 32) - 1) / ((32 / (DHP / 4)) * (kBwdThreads / 32));
-    uint8_t* const t0[2] = {sQ, sK};
-    const __nv_bfloat16* const s0[2] = {qbase, qbase + D};
-    const int l0[2] = {ld, ld};
-    load_head_tiles<DHP, 2, kIt>(t0, s0, l0, S, kSP, dh);
-    uint8_t* const t1[2] = {sV, sdO};
-    const __nv_bfloat16* const s1[2] = {qbase + 2 * D, dobase};
-    const int l1[2] = {ld, D};
-    load_head_tiles<DHP, 2, kIt>(t1, s1, l1, S, kSP, dh);
-  }
-  if (warp == 0) WM_TICK(33);
-  if (tid < kSP) {  // per-row statistics: LSE (exp2 domain) and delta = sum_d dO * O (pre-scaled)
-    float l = 0.0f, acc = 0.0f;
-    if (tid < S) {
-      l = -lse[static_cast<size_t>(bh) * S + tid] * 1.4426950408889634f;
-      const uint2* po = reinterpret_cast<const uint2*>(obase + static_cast<size_t>(tid) * D);
-      const uint2* pd = reinterpret_cast<const uint2*>(dobase + static_cast<size_t>(tid) * D);
-      uint2 o[DHP / 4], d[DHP / 4];
-#pragma unroll
-      for (int p = 0; p < DHP / 4; ++p) {  // all loads in flight at once
-        const bool ok = p < dh / 4;
-        o[p] = ok ? __ldg(po + p) : make_uint2(0u, 0u);
-        d[p] = ok ? __ldg(pd + p) : make_uint2(0u, 0u);
-      }
-#pragma unroll
-      for (int p = 0; p < DHP / 4; ++p) {
-        acc = fmaf(bf16_lo(o[p].x), bf16_lo(d[p].x), acc);
-        acc = fmaf(bf16_hi(o[p].x), bf16_hi(d[p].x), acc);
-        acc = fmaf(bf16_lo(o[p].y), bf16_lo(d[p].y), acc);
-        acc = fmaf(bf16_hi(o[p].y), bf16_hi(d[p].y), acc);
-      }
-    }
-    sLse[tid] = l;
-    sDelta[tid] = acc * scale;
-  }
-  if (warp == 0) WM_TICK(51);
-  cp_async_wait_all();
   if (tid == 0) {
-    mbar_init(&bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.kv_full[i], 1);
+      mbar_init(&bars.kv_ready[i], 1);
+      mbar_init(&bars.kv_free[i], 1);
+      mbar_init(&bars.sdp_full[i], 1);
+      mbar_init(&bars.pds_full[i], 8);
+      mbar_init(&bars.ds_free[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) mbar_init(&bars.st_full[i], 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&bars.qd_full[i], 1);
+      mbar_init(&bars.qd_free[i], 1);
+    }
+    mbar_init(&bars.acc_full, 1);
+    mbar_init(&bars.acc_free, 8);
+    for (int i = 0; i < 5; ++i) {
+      mbar_init(&bars.out_full[i], 4);
+      mbar_init(&bars.out_free[i], 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  for (int i = tid; i < 2048 / 16; i += kBwdThreads) reinterpret_cast<uint4*>(sZero)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 16) tmem_alloc<512>(&tmem_slot);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (warp == 0) WM_TICK(34);
-  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 256 + DHP, tdQ = tmem + 256 + 2 * DHP;
-  const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-  const uint32_t idesc_kv = umma_idesc_bf16(128, DHP, 1, 1);
-  const uint32_t idesc_q = umma_idesc_bf16(128, DHP, 0, 1);
-  const float c2 = scale * 1.4426950408889634f;
-  const float ds_scale = drop_scale * scale;  // dS = P * (dP * keep * drop_scale - delta) * scale
-  const bool issue_warp = warp == 16;
-  // K-major views (contract over head dim): LBO = 128, SBO = RS. MN-major views (contract over rows): LBO = RS, SBO = 128
-  const uint64_t kQ = umma_smem_desc(smem_u32(sQ), 128, RS, UMMA_SWZ_NONE), mQ = umma_smem_desc(smem_u32(sQ), RS, 128, UMMA_SWZ_NONE);
-  const uint64_t kK = umma_smem_desc(smem_u32(sK), 128, RS, UMMA_SWZ_NONE), mK = umma_smem_desc(smem_u32(sK), RS, 128, UMMA_SWZ_NONE);
-  const uint64_t kV = umma_smem_desc(smem_u32(sV), 128, RS, UMMA_SWZ_NONE);
-  const uint64_t kdO = umma_smem_desc(smem_u32(sdO), 128, RS, UMMA_SWZ_NONE), mdO = umma_smem_desc(smem_u32(sdO), RS, 128, UMMA_SWZ_NONE);
-  // P / dS [128 q, 128 keys]: MN-major (mn = keys, k = q rows) for dV / dK, K-major over keys for dQ
-  const uint64_t mP = umma_smem_desc(smem_u32(sP), RS_P, 128, UMMA_SWZ_NONE);
-  const uint64_t mdS = umma_smem_desc(smem_u32(sdS), RS_P, 128, UMMA_SWZ_NONE);
-  const uint64_t kdS = umma_smem_desc(smem_u32(sdS), 128, RS_P, UMMA_SWZ_NONE);
+  // region r: S^T at r*128 + [0, 64), dP^T at r*128 + [64, 128); accumulators behind
+  const uint32_t tdV = tmem + 256, tdK = tmem + 256 + DHP, tdQ = tmem + 256 + 2 * DHP;
 
-  auto issue_scores = [&](int i, int j) {  // S = Q_i K_j^T, dP = dO_i V_j^T
-#pragma unroll
-    for (int k = 0; k < DHP / 16; ++k)
-      umma_ss(tS, umma_desc_advance(kQ, (i * 16) * RS + k * 256), umma_desc_advance(kK, (j * 16) * RS + k * 256), idesc_s, k != 0);
-#pragma unroll
-    for (int k = 0; k < DHP / 16; ++k)
-      umma_ss(tdP, umma_desc_advance(kdO, (i * 16) * RS + k * 256), umma_desc_advance(kV, (j * 16) * RS + k * 256), idesc_s, k != 0);
-  };
-  auto store_kv = [&](int j) {  // thread = key row; the 2*NCH 16-column chunks are dealt round-robin to the 4 groups
-    const int kr = j * 128 + row;
-    const bool kvalid = kr < S;
-    __nv_bfloat16* drow = dqkv + (static_cast<size_t>(b) * S + (kvalid ? kr : 0)) * ld + h * dh;
-    for (int c = grp; c < 2 * NCH; c += 4) {
-      const int which = c / NCH, cc = c - which * NCH;
-      store_acc_chunk<DHP>((which == 0 ? tdK : tdV) + lane_sel, drow + (which == 0 ? D : 2 * D), cc * 16, dh, kvalid);
-    }
-  };
-
-  if (issue_warp) {
-    // ---- MMA-issue warp: one block barrier per (j, i) pair (P / dS complete), then all five products + commit
+  if (warp == 17) {
+    // ------------------------------------------------------------------ TMA producer (+ K/V fix-up)
     if (lane == 0) {
-      issue_scores(0, 0);
-      umma_commit(&bar);
+      tma_prefetch_desc(&tm_kv);
+      tma_prefetch_desc(&tm_q);
+      tma_prefetch_desc(&tm_do);
     }
-    for (int j = 0; j < nt; ++j) {
-      for (int i = 0; i < nt; ++i) {
-        __syncthreads();
+    const bool need_fix = (dh & 7) != 0;
+    auto load_kv = [&](int J) {  // lane 0: K_j, V_j of key tile J (and the head's statistics with its first tile)
+      const int n = J / nt, j = J - n * nt;
+      const int item = blockIdx.x + n * gridDim.x;
+      const int b = item / H, h = item - b * H;
+      const int col0 = (h * dh) & ~7;
+      const int kb = J & 1;
+      if (J >= 2) mbar_wait(&bars.kv_free[kb], ((J >> 1) - 1) & 1, 80);
+      mbar_arrive_expect_tx(&bars.kv_full[kb], 2 * NCH * 2048);
+      for (int ch = 0; ch < NCH; ++ch) {
+        tma_load_3d(sK + kb * G::T128 + ch * G::CS128, &tm_kv, &bars.kv_full[kb], D + col0 + ch * 8, j * 128, b);
+        tma_load_3d(sV + kb * G::T128 + ch * G::CS128, &tm_kv, &bars.kv_full[kb], 2 * D + col0 + ch * 8, j * 128, b);
+      }
+      if (j == 0) {
+        mbar_arrive_expect_tx(&bars.st_full[n % 3], G::STB);
+        bulk_load_1d(sStat + (n % 3) * G::STB, stats + static_cast<size_t>(item) * kSP, G::STB, &bars.st_full[n % 3]);
+      }
+    };
+    auto fix_kv = [&](int J) {  // whole warp: zero the neighbouring head's 4 columns of K_j and V_j, publish
+      const int n = J / nt;
+      const int item = blockIdx.x + n * gridDim.x;
+      const int h = item % H;
+      const int kb = J & 1;
+      mbar_wait(&bars.kv_full[kb], (J >> 1) & 1, 81);
+      if (need_fix) {
+        const int z0 = ((h * dh) & 7) ? 0 : dh;
+        const uint32_t zoff = (z0 >> 3) * G::CS128 + (z0 & 7) * 2;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          *reinterpret_cast<uint2*>(sK + kb * G::T128 + zoff + (r * 32 + lane) * 16) = make_uint2(0u, 0u);
+          *reinterpret_cast<uint2*>(sV + kb * G::T128 + zoff + (r * 32 + lane) * 16) = make_uint2(0u, 0u);
+        }
+        fence_proxy_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.kv_ready[kb]);
+    };
+    if (nJ > 0) {
+      if (lane == 0) load_kv(0);
+      __syncwarp();
+      fix_kv(0);
+    }
+    const int ih_load = RQ < nh - 1 ? RQ : nh - 1;  // late enough that kv_free of key tile J - 1 has been committed
+    int g = 0;
+    for (int J = 0; J < nJ; ++J) {
+      const int n = J / nt;
+      const int item = blockIdx.x + n * gridDim.x;
+      const int b = item / H, h = item - b * H;
+      const int col0 = (h * dh) & ~7;
+      for (int ih = 0; ih < nh; ++ih, ++g) {
         if (lane == 0) {
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 128 / 16; ++k) {  // contraction over the 128 query rows of tile i
-            umma_ss(tdV, umma_desc_advance(mP, (k * 2) * RS_P), umma_desc_advance(mdO, (i * 16 + k * 2) * RS), idesc_kv, (i | k) != 0);
-            umma_ss(tdK, umma_desc_advance(mdS, (k * 2) * RS_P), umma_desc_advance(mQ, (i * 16 + k * 2) * RS), idesc_kv, (i | k) != 0);
+          if (ih == ih_load && J + 1 < nJ) load_kv(J + 1);
+          const int slot = g % RQ;
+          if (g >= RQ) mbar_wait(&bars.qd_free[slot], ((g / RQ) - 1) & 1, 82);
+          uint8_t* dst = sRing + slot * G::SLOT;
+          mbar_arrive_expect_tx(&bars.qd_full[slot], 2 * NCH * 1024 + (DROP ? 1024 : 0));
+          for (int ch = 0; ch < NCH; ++ch) {
+            tma_load_3d(dst + ch * G::CS64, &tm_q, &bars.qd_full[slot], col0 + ch * 8, ih * 64, b);
+            tma_load_3d(dst + G::T64 + ch * G::CS64, &tm_do, &bars.qd_full[slot], col0 + ch * 8, ih * 64, b);
           }
+          if (DROP) {
+            const int j = J - n * nt;
+            const uint32_t* src = drop_words + (static_cast<size_t>(item) * kAttnMaskSlices + 4 * j) * kSP + ih * 64;
 #pragma unroll
-          for (int k = 0; k < 128 / 16; ++k)  // dQ_i += dS K_j, contraction over the 128 keys of tile j
-            umma_ss(tdQ + i * DHP, umma_desc_advance(kdS, k * 256), umma_desc_advance(mK, (j * 16 + k * 2) * RS), idesc_q, (j | k) != 0);
-          const int in = i + 1 < nt ? i + 1 : 0, jn = i + 1 < nt ? j : j + 1;
-          if (jn < nt) issue_scores(in, jn);
-          umma_commit(&bar);
+            for (int s4 = 0; s4 < 4; ++s4)
+              bulk_load_1d(dst + 2 * G::T64 + s4 * 256, src + static_cast<size_t>(s4) * kSP, 256, &bars.qd_full[slot]);
+          }
         }
         __syncwarp();
+        if (ih == nh - 1 && J + 1 < nJ) fix_kv(J + 1);
       }
+    }
+  } else if (warp == 16) {
+    // ------------------------------------------------------------------ MMA issue
+    const uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+    const uint32_t idesc_kv = umma_idesc_bf16(128, DHP, 0, 1);  // A = P^T / dS^T from TMEM, B MN-major
+    const uint32_t idesc_q = umma_idesc_bf16(128, DHP, 1, 1);   // A = dS (MN-major, smem), B = K_j MN-major
+    const uint32_t zero_addr = smem_u32(sZero);
+    auto issue_scores = [&](int g2) {  // S^T = K_j Q_ih^T, dP^T = V_j dO_ih^T into region g2 & 1
+      const int J2 = g2 / nh;
+      const int kb = J2 & 1, slot = g2 % RQ;
+      mbar_wait(&bars.kv_ready[kb], (J2 >> 1) & 1, 83);
+      mbar_wait(&bars.qd_full[slot], (g2 / RQ) & 1, 84);
+      tc_fence_after();
+      const uint32_t ka = smem_u32(sK + kb * G::T128), va = smem_u32(sV + kb * G::T128);
+      const uint32_t qa = smem_u32(sRing + slot * G::SLOT), da = qa + G::T64;
+      const uint32_t tS = tmem + (g2 & 1) * 128;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t a = which ? va : ka, bq = which ? da : qa;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint32_t a0 = a + ks * 2 * G::CS128, b0 = bq + ks * 2 * G::CS64;
+          const bool tail = kZeroTail && ks == KSTEPS - 1;
+          umma_ss_warp(tS + which * 64, umma_smem_desc(a0, tail ? zero_addr - a0 : G::CS128, 128, UMMA_SWZ_NONE),
+                       umma_smem_desc(b0, tail ? zero_addr - b0 : G::CS64, 128, UMMA_SWZ_NONE), idesc_s, ks != 0);
+        }
+      }
+      umma_commit_warp(&bars.sdp_full[g2 & 1]);
+    };
+    if (nG > 0) issue_scores(0);
+    if (nG > 1) issue_scores(1);
+    int g = 0;
+    for (int J = 0; J < nJ; ++J) {
+      const int j = J % nt;
+      const int kb = J & 1;
+      const uint32_t ka = smem_u32(sK + kb * G::T128);
+      for (int ih = 0; ih < nh; ++ih, ++g) {
+        const int r = g & 1, slot = g % RQ;
+        const uint32_t tS = tmem + r * 128;
+        const uint32_t qa = smem_u32(sRing + slot * G::SLOT), da = qa + G::T64;
+        mbar_wait(&bars.pds_full[r], (g >> 1) & 1, 85);  // P^T, dS^T in TMEM; dS half in shared memory
+        if (ih == 0 && J >= 1) mbar_wait(&bars.acc_free, (J - 1) & 1, 86);  // previous dK/dV (dQ) drained
+        tc_fence_after();
+        // dV_j += P^T dO_ih, dK_j += dS^T Q_ih: k = 64 query rows, A k-step = 8 packed columns of the slice's first 16
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t acol = (ks >> 1) * 32 + (ks & 1) * 8;
+          umma_ts_warp(tdV, tS + acol, umma_smem_desc(da + ks * 256, 128, G::CS64, UMMA_SWZ_NONE), idesc_kv, (ih | ks) != 0);
+          umma_ts_warp(tdK, tS + 64 + acol, umma_smem_desc(qa + ks * 256, 128, G::CS64, UMMA_SWZ_NONE), idesc_kv, (ih | ks) != 0);
+        }
+        if (ih & 1) {  // both halves of query tile i are in the dS buffer: dQ_i += dS_i K_j (k = 128 keys)
+          const int i = ih >> 1, tb = (g >> 1) & 1;
+          const uint32_t sa = smem_u32(sdS + tb * G::DSB);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_ss_warp(tdQ + i * DHP, umma_smem_desc(sa + ks * 256, 128, 2048, UMMA_SWZ_NONE),
+                         umma_smem_desc(ka + ks * 256, 128, G::CS128, UMMA_SWZ_NONE), idesc_q, (j | ks) != 0);
+          umma_commit_warp(&bars.ds_free[tb]);
+        }
+        umma_commit_warp(&bars.qd_free[slot]);
+        if (ih == nh - 1) {
+          umma_commit_warp(&bars.kv_free[kb]);
+          umma_commit_warp(&bars.acc_full);
+        }
+        if (g + 2 < nG) issue_scores(g + 2);
+      }
+    }
+  } else if (warp == 18) {
+    // ------------------------------------------------------------------ gradient store
+    const int pv = dh >> 2;
+    const float inv_pv = 1.0f / static_cast<float>(pv);
+    auto drain = [&](int slot, uint32_t parity, __nv_bfloat16* gbase, int nrows) {
+      mbar_wait(&bars.out_full[slot], parity, 87);
+      const uint8_t* src = sOut + slot * G::OUTB;
+      const int total = nrows * pv;
+      for (int base = 0; base < total; base += 32 * 6) {
+        uint2 v[6];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const int idx = base + u * 32 + lane;
+          if (idx < total) v[u] = *reinterpret_cast<const uint2*>(src + idx * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const int idx = base + u * 32 + lane;
+          if (idx < total) {
+            const int r = static_cast<int>((static_cast<float>(idx) + 0.5f) * inv_pv);
+            *reinterpret_cast<uint2*>(gbase + static_cast<size_t>(r) * (3 * D) + (idx - r * pv) * 4) = v[u];
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.out_free[slot]);
+    };
+    for (int J = 0; J < nJ; ++J) {
+      const int n = J / nt, j = J - n * nt;
+      const int item = blockIdx.x + n * gridDim.x;
+      const int b = item / H, h = item - b * H;
+      __nv_bfloat16* hb = dqkv + static_cast<size_t>(b) * S * (3 * D) + h * dh;
+      const int nrows = min(128, S - j * 128);
+      drain(0, J & 1, hb + static_cast<size_t>(j) * 128 * (3 * D) + D, nrows);
+      drain(1, J & 1, hb + static_cast<size_t>(j) * 128 * (3 * D) + 2 * D, nrows);
+      if (j == nt - 1)
+        for (int i = 0; i < nt; ++i) drain(2 + i, n & 1, hb + static_cast<size_t>(i) * 128 * (3 * D), min(128, S - i * 128));
     }
   } else {
-    uint32_t phase = 0;
-    for (int j = 0; j < nt; ++j) {
-      for (int i = 0; i < nt; ++i) {
-        if (warp == 0 && j == 0) WM_TICK(35 + i * 3);
-        // this pair's dropout masks (2 Philox blocks per thread) are generated under the MMA wait below
-        uint32_t kmA[4], kmB[4];
-        if (DROP) {
-          const int qq = i * 128 + row;
-          const uint64_t rowbase = (static_cast<uint64_t>(bh) * S + (qq < S ? qq : 0)) * grp_per_row;
-          const int kk = j * 128 + grp * 32;
-          keep_masks16(seed, stream_id, rowbase + (kk >> 4), thresh4, kmA);
-          keep_masks16(seed, stream_id, rowbase + (kk >> 4) + 1, thresh4, kmB);
+    // ------------------------------------------------------------------ elementwise warps
+    const int grp = warp >> 3;                 // TMEM region / half-tile parity owned by this group
+    const int lq = warp & 3, h2 = (warp >> 2) & 1;
+    const int krow = lq * 32 + lane;           // key row inside the tile == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>(lq * 32) << 16;
+    const float c2 = scale * 1.4426950408889634f;
+    const float clampv = log2f(drop_scale);
+    const uint32_t tS = tmem + grp * 128 + lane_sel;
+    // TMEM accumulator columns [16 cg, 16 cg + 16) of this thread's row -> bf16 staging row (compact [128, dh])
+    auto stage_acc = [&](uint32_t tacc, uint8_t* srow, int front) {
 #pragma unroll
-          for (int w = 0; w < 4; ++w) { WM_PIN(kmA[w]); WM_PIN(kmB[w]); }
-        }
-        mbar_wait(&bar, phase, 51);  // S/dP of (j, i) ready; every earlier product has completed as well
-        phase ^= 1u;
-        tc_fence_after();
-        if (warp == 0 && j == 0) WM_TICK(36 + i * 3);
-        if (i == 0 && j > 0) store_kv(j - 1);  // dK/dV of the previous key tile are final
-        const int q = i * 128 + row;
-        const float lneg = sLse[i * 128 + row];
-        const float dl = sDelta[i * 128 + row];
-#pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-          const int c0 = grp * 32 + hh * 16;   // column inside the key tile
-          const int k0 = j * 128 + c0;          // global key index
-          uint32_t vs[16], vd[16];
-          tmem_ld16(tS + lane_sel + c0, vs);
-          tmem_ld16(tdP + lane_sel + c0, vd);
-          tmem_ld_wait();
-          uint32_t km[4];
-          if (DROP) {
+      for (int cg = 0; cg < NCG; ++cg) {
+        uint32_t v[16];
+        tmem_ld16(tacc + lane_sel + cg * 16, v);
+        tmem_ld_wait();
 #pragma unroll
-            for (int w = 0; w < 4; ++w) km[w] = hh ? kmB[w] : kmA[w];
+        for (int jj = 0; jj < 16; jj += 4) {
+          const int d = cg * 16 + jj - front;
+          if (d >= 0 && d < dh) {
+            uint2 o2;
+            o2.x = pack_bf16x2(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]));
+            o2.y = pack_bf16x2(__uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
+            *reinterpret_cast<uint2*>(srow + d * 2) = o2;
           }
-          float pp[16], ds[16];
+        }
+      }
+    };
+    for (int g = grp; g < nG; g += 2) {
+      const int J = g / nh, ih = g - J * nh;
+      const int n = J / nt, j = J - n * nt;
+      const int slot = g % RQ;
+      const int tb = (g >> 1) & 1;  // dS buffer of this query tile
+      const float2* st = reinterpret_cast<const float2*>(sStat + (n % 3) * G::STB) + ih * 64 + h2 * 32;
+      const uint32_t* mw = reinterpret_cast<const uint32_t*>(sRing + slot * G::SLOT + 2 * G::T64) + lq * 64 + h2 * 32;
+      if (j == 0 && ih < 2) mbar_wait(&bars.st_full[n % 3], (n / 3) & 1, 88);
+      mbar_wait(&bars.sdp_full[grp], (g >> 1) & 1, 89);
+      tc_fence_after();
+      if (DROP) mbar_wait(&bars.qd_full[slot], (g / RQ) & 1, 90);  // dropout words of this half-tile (long landed)
+      if ((g >> 1) >= 2) mbar_wait(&bars.ds_free[tb], (((g >> 1) >> 1) - 1) & 1, 91);
+      // dS tile layout: [q chunk of 8][128 keys][16 B]; this thread fills key row krow of chunks (ih&1)*8 + h2*4 + 0..3
+      uint8_t* dsrow = sdS + tb * G::DSB + ((ih & 1) * 8 + h2 * 4) * 2048 + krow * 16;
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            // valid entries have (s - lse) <= 0; the clamp only tames padded keys / rows (inf * 0 would be NaN)
-            const float p = fast_exp2(fminf(fmaf(__uint_as_float(vs[jj]), c2, lneg), 0.0f));
+      for (int bt = 0; bt < 2; ++bt) {
+        uint32_t vs[16], vd[16];
+        tmem_ld16(tS + h2 * 32 + bt * 16, vs);
+        tmem_ld16(tS + 64 + h2 * 32 + bt * 16, vd);
+        tmem_ld_wait();
+        uint32_t pk[8], dk[8];
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) {  // four query rows at a time: two 16-byte statistics loads, one of dropout words
+          const int e0 = bt * 16 + w4 * 4;
+          const float4 sa = *reinterpret_cast<const float4*>(st + e0), sb = *reinterpret_cast<const float4*>(st + e0 + 2);
+          const float lx[4] = {sa.x, sa.z, sb.x, sb.z};  // -lse * log2e + log2(drop_scale)
+          const float dl[4] = {sa.y, sa.w, sb.y, sb.w};  // delta * scale / drop_scale
+          uint32_t mword[4] = {0u, 0u, 0u, 0u};
+          if (DROP) {
+            const uint4 m4 = *reinterpret_cast<const uint4*>(mw + e0);
+            mword[0] = m4.x; mword[1] = m4.y; mword[2] = m4.z; mword[3] = m4.w;
+          }
+          float pp[4], dd[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float p = fast_exp2(fminf(fmaf(__uint_as_float(vs[w4 * 4 + u]), c2, lx[u]), clampv));
             if (DROP) {
-              const uint32_t m32 = WM_KEEP32(km, jj);
-              pp[jj] = __uint_as_float(__float_as_uint(p * drop_scale) & m32);
-              ds[jj] = p * fmaf(__uint_as_float(vd[jj] & m32), ds_scale, -dl);
+              const uint32_t sm = static_cast<uint32_t>(static_cast<int32_t>(mword[u] << (31 - lane)) >> 31);
+              pp[u] = __uint_as_float(__float_as_uint(p) & sm);
+              dd[u] = p * fmaf(__uint_as_float(vd[w4 * 4 + u] & sm), scale, -dl[u]);
             } else {
-              pp[jj] = p;
-              ds[jj] = p * fmaf(__uint_as_float(vd[jj]), scale, -dl);
+              pp[u] = p;
+              dd[u] = p * fmaf(__uint_as_float(vd[w4 * 4 + u]), scale, -dl[u]);
             }
           }
-#pragma unroll
-          for (int g8 = 0; g8 < 2; ++g8) {
-            uint4 pk, dk;
-            pk.x = pack_bf16x2(pp[g8 * 8 + 0], pp[g8 * 8 + 1]);
-            pk.y = pack_bf16x2(pp[g8 * 8 + 2], pp[g8 * 8 + 3]);
-            pk.z = pack_bf16x2(pp[g8 * 8 + 4], pp[g8 * 8 + 5]);
-            pk.w = pack_bf16x2(pp[g8 * 8 + 6], pp[g8 * 8 + 7]);
-            dk.x = pack_bf16x2(ds[g8 * 8 + 0], ds[g8 * 8 + 1]);
-            dk.y = pack_bf16x2(ds[g8 * 8 + 2], ds[g8 * 8 + 3]);
-            dk.z = pack_bf16x2(ds[g8 * 8 + 4], ds[g8 * 8 + 5]);
-            dk.w = pack_bf16x2(ds[g8 * 8 + 6], ds[g8 * 8 + 7]);
-            const int kc = c0 + g8 * 8;
-            const uint32_t off = (row >> 3) * RS_P + (kc >> 3) * 128 + (row & 7) * 16;
-            *reinterpret_cast<uint4*>(sP + off) = pk;
-            *reinterpret_cast<uint4*>(sdS + off) = dk;
+          pk[w4 * 2] = pack_bf16x2(pp[0], pp[1]);
+          pk[w4 * 2 + 1] = pack_bf16x2(pp[2], pp[3]);
+          dk[w4 * 2] = pack_bf16x2(dd[0], dd[1]);
+          dk[w4 * 2 + 1] = pack_bf16x2(dd[2], dd[3]);
+        }
+        tmem_st8(tS + h2 * 32 + bt * 8, pk);        // P^T: 16 query rows = 8 packed columns
+        tmem_st8(tS + 64 + h2 * 32 + bt * 8, dk);   // dS^T
+        *reinterpret_cast<uint4*>(dsrow + (bt * 2) * 2048) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+        *reinterpret_cast<uint4*>(dsrow + (bt * 2 + 1) * 2048) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+      }
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.pds_full[grp]);
+      // ---- drains (group 1 handles the last half-tile of every key tile)
+      if (ih == nh - 1) {
+        const int item = blockIdx.x + n * gridDim.x;
+        const int front = ((item % H) * dh) & 7;
+        mbar_wait(&bars.acc_full, J & 1, 92);
+        tc_fence_after();
+        // dK_j -> slot 0 (warps with h2 == 0), dV_j -> slot 1 (h2 == 1); thread = key row
+        if (J >= 1) mbar_wait(&bars.out_free[h2], (J - 1) & 1, 93);
+        stage_acc(h2 ? tdV : tdK, sOut + h2 * G::OUTB + krow * (dh * 2), front);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.out_full[h2]);
+        if (j == nt - 1) {  // dQ tiles of the head: thread = query row; h2 == 0 takes tiles 0 and 2, h2 == 1 tile 1
+          for (int i = h2; i < nt; i += 2) {
+            if (n >= 1) mbar_wait(&bars.out_free[2 + i], (n - 1) & 1, 94);
+            stage_acc(tdQ + i * DHP, sOut + (2 + i) * G::OUTB + krow * (dh * 2), front);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.out_full[2 + i]);
           }
         }
-        if (warp == 0 && j == 0) WM_TICK(37 + i * 3);
-        fence_proxy_async_smem();
         tc_fence_before();
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.acc_free);
       }
-      if (warp == 0) WM_TICK(44 + j);
     }
-    mbar_wait(&bar, phase, 52);  // the last gradient products
-    tc_fence_after();
-    store_kv(nt - 1);
-    for (int c = grp; c < nt * NCH; c += 4) {  // dQ: thread = query row
-      const int i = c / NCH, cc = c - i * NCH;
-      const int q = i * 128 + row;
-      const bool qvalid = q < S;
-      __nv_bfloat16* dst = dqkv + (static_cast<size_t>(b) * S + (qvalid ? q : 0)) * ld + h * dh;
-      store_acc_chunk<DHP>(tdQ + i * DHP + lane_sel, dst, cc * 16, dh, qvalid);
-    }
-    if (warp == 0) WM_TICK(48);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
@@ -799,8 +896,6 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-static int padded_dh(int dh) { return dh <= 16 ? 16 : dh <= 32 ? 32 : dh <= 48 ? 48 : 0; }
-
 static int attn_sm_count() {
   static int sms = 0;
   if (!sms) {
@@ -813,8 +908,8 @@ static int attn_sm_count() {
 static int attn_chunks(int dh) { return (dh & 7) ? (dh + 4) / 8 : dh / 8; }
 
 template <int NCH>
-static int launch_fwd_t(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, int B, int S, int H, int dh,
-                        float scale, uint32_t thresh7, float dscale, uint64_t seed, uint64_t stream_id,
+static int launch_fwd_t(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, uint32_t* drop_words, int B, int S,
+                        int H, int dh, float scale, uint32_t thresh7, float dscale, uint64_t seed, uint64_t stream_id,
                         cudaStream_t stream) {
   CUtensorMap tm;
   const int D = H * dh;
@@ -825,19 +920,33 @@ static int launch_fwd_t(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
   const int nitems = B * H;
   const int grid = nitems < attn_sm_count() ? nitems : attn_sm_count();
-  kern<<<grid, kFwdThreads, smem, stream>>>(tm, ctx, lse, nitems, S, H, dh, scale, thresh7, dscale, seed, stream_id);
+  kern<<<grid, kFwdThreads, smem, stream>>>(tm, ctx, lse, drop_words, nitems, S, H, dh, scale, thresh7, dscale, seed,
+                                            stream_id);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
-template <int DHP>
+template <int NCH>
 static int launch_bwd_t(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __nv_bfloat16* dctx,
-                        const float* lse, __nv_bfloat16* dqkv, int B, int S, int H, int dh, float scale,
-                        uint32_t thresh7, float dscale, uint64_t seed, uint64_t stream_id, cudaStream_t stream) {
-  const int smem = 4 * kSP * DHP * 2 + 2 * 128 * 128 * 2 + 2 * kSP * 4 + 256;
-  auto kern = thresh7 ? attn_bwd_kernel<DHP, true> : attn_bwd_kernel<DHP, false>;
+                        const float* lse, __nv_bfloat16* dqkv, const uint32_t* drop_words, float2* stats, int B, int S,
+                        int H, int dh, float scale, bool drop, float dscale, cudaStream_t stream) {
+  const int D = H * dh;
+  CUtensorMap tm_kv, tm_q, tm_do;
+  int rc = make_tmap_bf16_rows3d(&tm_kv, qkv, 3 * D, S, B, 3 * D, 128);
+  if (rc == WM_OK) rc = make_tmap_bf16_rows3d(&tm_q, qkv, 3 * D, S, B, 3 * D, 64);
+  if (rc == WM_OK) rc = make_tmap_bf16_rows3d(&tm_do, dctx, D, S, B, D, 64);
+  if (rc != WM_OK) return rc;
+  {
+    const long long total = static_cast<long long>(B) * kSP * H;
+    attn_bwd_stats_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(ctx, dctx, lse, stats, B, S, H, dh,
+                                                                                         scale, dscale);
+    WM_COUNT_LAUNCH();
+  }
+  const int smem = AttnBwdGeom<NCH>::kSmem;
+  auto kern = drop ? attn_bwd_kernel<NCH, true> : attn_bwd_kernel<NCH, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
-  kern<<<B * H, kBwdThreads, smem, stream>>>(qkv, ctx, dctx, lse, dqkv, S, H, dh, scale, thresh7, dscale, seed,
-                                             stream_id);
+  const int nitems = B * H;
+  const int grid = nitems < attn_sm_count() ? nitems : attn_sm_count();
+  kern<<<grid, kBwdThreads, smem, stream>>>(tm_kv, tm_q, tm_do, stats, drop_words, dqkv, nitems, S, H, dh, scale, dscale);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
@@ -847,41 +956,57 @@ static void attn_drop_params(uint32_t drop_thresh16, uint32_t* thresh7, float* s
   *thresh7 = (drop_thresh16 + 256u) >> 9;
   *scale = *thresh7 ? 128.0f / static_cast<float>(128u - *thresh7) : 1.0f;
 }
+// TMA needs 16-byte aligned row pitches and head-block starts: D = H * dh a multiple of 8
+static bool attn_shape_ok(int B, int S, int H, int dh) {
+  return B > 0 && H > 0 && S > 0 && S <= kSP && !(dh & 3) && dh >= 12 && dh <= 48 && !((H * dh) & 7);
+}
 
-int launch_attn_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, int B, int S, int H, int dh,
-                    uint32_t drop_thresh, float drop_scale, uint64_t seed, uint64_t stream_id, cudaStream_t stream) {
-  (void)drop_scale;
-  // TMA needs 16-byte aligned row pitches and head-block starts: D = H * dh a multiple of 8
-  if (B <= 0 || H <= 0 || S <= 0 || S > kSP || (dh & 3) || dh < 8 || dh > 48 || ((H * dh) & 7)) return WM_ERR_SHAPE;
-  uint32_t t8;
+size_t attn_dropout_words_bytes(int B, int S, int H) {
+  (void)S;
+  return static_cast<size_t>(B) * H * kAttnMaskSlices * kSP * sizeof(uint32_t);
+}
+size_t attn_bwd_workspace_bytes(int B, int S, int H) {
+  (void)S;
+  return static_cast<size_t>(B) * H * kSP * sizeof(float2);
+}
+
+int launch_attn_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, uint32_t* drop_words, int B, int S, int H,
+                    int dh, uint32_t drop_thresh, uint64_t seed, uint64_t stream_id, cudaStream_t stream) {
+  if (!attn_shape_ok(B, S, H, dh)) return WM_ERR_SHAPE;
+  uint32_t t7;
   float ds;
-  attn_drop_params(drop_thresh, &t8, &ds);
+  attn_drop_params(drop_thresh, &t7, &ds);
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
   switch (attn_chunks(dh)) {
-    case 1: return WM_ERR_SHAPE;
-    case 2: return launch_fwd_t<2>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
-    case 3: return launch_fwd_t<3>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
-    case 4: return launch_fwd_t<4>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
-    case 5: return launch_fwd_t<5>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
-    default: return launch_fwd_t<6>(qkv, ctx, lse, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
+    case 2: return launch_fwd_t<2>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t7, ds, seed, stream_id, stream);
+    case 3: return launch_fwd_t<3>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t7, ds, seed, stream_id, stream);
+    case 4: return launch_fwd_t<4>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t7, ds, seed, stream_id, stream);
+    case 5: return launch_fwd_t<5>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t7, ds, seed, stream_id, stream);
+    case 6: return launch_fwd_t<6>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t7, ds, seed, stream_id, stream);
+    default: return WM_ERR_SHAPE;
   }
 }
 
+// drop_words: the buffer the forward call filled (required when drop_thresh rounds to a non-zero probability);
+// workspace: attn_bwd_workspace_bytes(B, S, H) bytes, 16-byte aligned.
 int launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __nv_bfloat16* dctx, const float* lse,
-                    __nv_bfloat16* dqkv, int B, int S, int H, int dh, uint32_t drop_thresh, float drop_scale,
-                    uint64_t seed, uint64_t stream_id, cudaStream_t stream) {
-  (void)drop_scale;
-  if (B <= 0 || H <= 0 || S <= 0 || S > kSP || (dh & 3)) return WM_ERR_SHAPE;
-  const int dhp = padded_dh(dh);
-  if (!dhp) return WM_ERR_SHAPE;
-  uint32_t t8;
+                    __nv_bfloat16* dqkv, const uint32_t* drop_words, void* workspace, int B, int S, int H, int dh,
+                    uint32_t drop_thresh, cudaStream_t stream) {
+  if (!attn_shape_ok(B, S, H, dh)) return WM_ERR_SHAPE;
+  uint32_t t7;
   float ds;
-  attn_drop_params(drop_thresh, &t8, &ds);
+  attn_drop_params(drop_thresh, &t7, &ds);
+  if (!workspace || (t7 && !drop_words)) return WM_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 15u) || (reinterpret_cast<uintptr_t>(drop_words) & 15u)) return WM_ERR_ALIGN;
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
-  switch (dhp) {
-    case 16: return launch_bwd_t<16>(qkv, ctx, dctx, lse, dqkv, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
-    case 32: return launch_bwd_t<32>(qkv, ctx, dctx, lse, dqkv, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
-    default: return launch_bwd_t<48>(qkv, ctx, dctx, lse, dqkv, B, S, H, dh, scale, t8, ds, seed, stream_id, stream);
+  float2* st = static_cast<float2*>(workspace);
+  switch (attn_chunks(dh)) {
+    case 2: return launch_bwd_t<2>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t7 != 0, ds, stream);
+    case 3: return launch_bwd_t<3>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t7 != 0, ds, stream);
+    case 4: return launch_bwd_t<4>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t7 != 0, ds, stream);
+    case 5: return launch_bwd_t<5>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t7 != 0, ds, stream);
+    case 6: return launch_bwd_t<6>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t7 != 0, ds, stream);
+    default: return WM_ERR_SHAPE;
   }
 }
 

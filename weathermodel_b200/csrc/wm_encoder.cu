@@ -67,6 +67,7 @@ static ParamLayout make_layout(const wm_encoder_config& c) {
 struct LayerAct {
   __nv_bfloat16 *x, *qkv, *ctx, *r1, *u, *h, *r2;
   float *lse, *mean1, *rstd1, *mean2, *rstd2;
+  uint32_t* dropw;  // attention dropout keep bits (forward -> backward); nullptr when the model has no dropout
 };
 struct LayerWt {  // transposed bf16 copies for dgrad
   __nv_bfloat16 *wqkv_t, *wo_t, *w1_t, *w2_t;
@@ -108,6 +109,7 @@ static size_t scratch_need(const wm_encoder_config& c, int64_t M, int outP) {
   upd(colsum_workspace_bytes(Mi, 3 * c.D));
   upd(colsum_workspace_bytes(Mi, c.FF));
   upd(layernorm_bwd_workspace_bytes(Mi, c.D));
+  upd(attn_bwd_workspace_bytes(c.B, c.S, c.H));
   return need;
 }
 
@@ -143,6 +145,7 @@ static size_t carve(wm_encoder* e, uint8_t* base) {
     a.h = bf(M * FF);
     a.r2 = bf(M * D);
     a.lse = f32(static_cast<int64_t>(c.B) * c.H * c.S);
+    a.dropw = c.dropout_p > 0.0f ? reinterpret_cast<uint32_t*>(take(attn_dropout_words_bytes(c.B, c.S, c.H))) : nullptr;
     a.mean1 = f32(M);
     a.rstd1 = f32(M);
     a.mean2 = f32(M);
@@ -167,7 +170,7 @@ static int check_cfg(const wm_encoder_config* c) {
   if (c->B <= 0 || c->S <= 0 || c->S > 384 || c->F <= 0 || c->F > 37 || c->L <= 0 || c->H <= 0) return WM_ERR_SHAPE;
   if (c->D <= 0 || c->D % c->H || (c->D & 7) || c->D > 768) return WM_ERR_SHAPE;
   const int dh = c->D / c->H;
-  if ((dh & 3) || dh > 48) return WM_ERR_SHAPE;
+  if ((dh & 3) || dh < 12 || dh > 48) return WM_ERR_SHAPE;
   if (c->FF <= 0 || (c->FF & 7)) return WM_ERR_SHAPE;
   if (c->out_dim <= 0 || c->out_dim > 64) return WM_ERR_SHAPE;
   if (c->dropout_p < 0.0f || c->dropout_p >= 1.0f) return WM_ERR_ARG;
@@ -305,7 +308,7 @@ int wm_encoder_forward(wm_encoder* e, const float* params, const float* weather,
       ep.ld_out = 3 * D;
       WM_TRY(launch_gemm_tn(a.x, D, e->shadow + q.w_qkv, D, M, 3 * D, D, ep, 0, 0, st));
     }
-    WM_TRY(launch_attn_fwd(a.qkv, a.ctx, a.lse, c.B, c.S, c.H, dh, thr, dscale, seed, stream_id(step, l, 0), st));
+    WM_TRY(launch_attn_fwd(a.qkv, a.ctx, a.lse, a.dropw, c.B, c.S, c.H, dh, thr, seed, stream_id(step, l, 0), st));
     {  // out-proj + dropout1 + residual
       GemmEpilogue ep;
       ep.bias = params + q.b_o;
@@ -423,8 +426,7 @@ int wm_encoder_backward_layers(wm_encoder* e, const float* params, int layer_hi,
       ep.ld_out = D;
       WM_TRY(launch_gemm_tn(gFd, D, e->wt[l].wo_t, D, M, D, D, ep, 0, 0, st));
     }
-    WM_TRY(launch_attn_bwd(a.qkv, a.ctx, e->gC, a.lse, e->gQKV, c.B, c.S, c.H, dh, thr, dscale, e->seed,
-                           stream_id(e->step, l, 0), st));
+    WM_TRY(launch_attn_bwd(a.qkv, a.ctx, e->gC, a.lse, e->gQKV, a.dropw, e->scratch, c.B, c.S, c.H, dh, thr, st));
     WM_TRY(launch_gemm_wgrad(e->gQKV, 3 * D, a.x, D, M, 3 * D, D, grads + q.w_qkv, 0, e->scratch, grads + q.b_qkv, st));
     {  // d x_l = gQKV W_qkv + d r1
       GemmEpilogue ep;

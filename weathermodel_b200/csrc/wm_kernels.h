@@ -82,11 +82,14 @@ int launch_cast_transpose(const float* w, __nv_bfloat16* wt, int rows, int cols,
 int launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream);
 
 // ---- attention (wm_attn.cu) --------------------------------------------------------------------
-int launch_attn_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, int B, int S, int H, int dh,
-                    uint32_t drop_thresh, float drop_scale, uint64_t seed, uint64_t stream_id,
-                    cudaStream_t stream);
-int launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __nv_bfloat16* dctx,
-                    const float* lse, __nv_bfloat16* dqkv, int B, int S, int H, int dh, uint32_t drop_thresh,
-                    float drop_scale, uint64_t seed, uint64_t stream_id, cudaStream_t stream);
+// drop_words: optional [B*H][12][384] uint32 keep-bit buffer written by the forward call and read by the backward
+// call (required by both when dropout is on); workspace: attn_bwd_workspace_bytes() bytes.
+size_t attn_dropout_words_bytes(int B, int S, int H);
+size_t attn_bwd_workspace_bytes(int B, int S, int H);
+int launch_attn_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, uint32_t* drop_words, int B, int S, int H,
+                    int dh, uint32_t drop_thresh, uint64_t seed, uint64_t stream_id, cudaStream_t stream);
+int launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __nv_bfloat16* dctx, const float* lse,
+                    __nv_bfloat16* dqkv, const uint32_t* drop_words, void* workspace, int B, int S, int H, int dh,
+                    uint32_t drop_thresh, cudaStream_t stream);
 
 }  // namespace wm

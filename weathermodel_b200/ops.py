@@ -146,20 +146,29 @@ def umma_probe(a, b, a_mn=False, b_mn=False):
 # ---------------------------------------------------------------------------------------------
 # attention
 # ---------------------------------------------------------------------------------------------
-def attn_fwd(qkv, B, S, H, dh, dropout_p=0.0, seed=0, stream_id=0):
+def attn_fwd(qkv, B, S, H, dh, dropout_p=0.0, seed=0, stream_id=0, drop_words=None):
+    """-> (ctx, lse). With dropout the keep bits are written to `drop_words` (allocated here and attached to the
+    returned ctx as `ctx.drop_words` when not supplied): attn_bwd needs them."""
     _cuda(qkv)
     ctx = torch.empty((B * S, H * dh), dtype=BF16, device=qkv.device)
     lse = torch.empty((B * H, S), dtype=torch.float32, device=qkv.device)
-    check(lib().wm_attn_fwd(_p(qkv), _p(ctx), _p(lse), B, S, H, dh, float(dropout_p), int(seed), int(stream_id),
-                            _stream()), "wm_attn_fwd")
+    if dropout_p > 0 and drop_words is None:
+        drop_words = torch.empty(lib().wm_attn_dropout_words_bytes(B, S, H) // 4, dtype=torch.int32, device=qkv.device)
+    check(lib().wm_attn_fwd(_p(qkv), _p(ctx), _p(lse), _p(drop_words) if drop_words is not None else None, B, S, H, dh,
+                            float(dropout_p), int(seed), int(stream_id), _stream()), "wm_attn_fwd")
+    ctx.drop_words = drop_words
     return ctx, lse
 
 
-def attn_bwd(qkv, ctx, dctx, lse, B, S, H, dh, dropout_p=0.0, seed=0, stream_id=0):
+def attn_bwd(qkv, ctx, dctx, lse, B, S, H, dh, dropout_p=0.0, drop_words=None):
     _cuda(qkv, ctx, dctx, lse)
     dqkv = torch.empty_like(qkv)
-    check(lib().wm_attn_bwd(_p(qkv), _p(ctx), _p(dctx), _p(lse), _p(dqkv), B, S, H, dh, float(dropout_p), int(seed),
-                            int(stream_id), _stream()), "wm_attn_bwd")
+    if drop_words is None:
+        drop_words = getattr(ctx, "drop_words", None)
+    ws = torch.empty(lib().wm_attn_bwd_workspace_bytes(B, S, H), dtype=torch.uint8, device=qkv.device)
+    check(lib().wm_attn_bwd(_p(qkv), _p(ctx), _p(dctx), _p(lse), _p(dqkv),
+                            _p(drop_words) if drop_words is not None else None, _p(ws), B, S, H, dh, float(dropout_p),
+                            _stream()), "wm_attn_bwd")
     return dqkv
 
 
