@@ -33,3 +33,31 @@ for p in (0.0, 0.1):
         print(f"{names[i]:40s} +{t[i] - prev:7d}  (@{t[i] - t[0]})")
         prev = t[i]
 
+
+dctx = (torch.randn(B * S, H * dh, device="cuda") * 0.5).to(torch.bfloat16)
+for p in (0.0, 0.1):
+    ctx, lse = ops.attn_fwd(qkv, B, S, H, dh, dropout_p=p, seed=1, stream_id=1)
+    for _ in range(3):
+        ops.attn_bwd(qkv, ctx, dctx, lse, B, S, H, dh, dropout_p=p)
+    buf = (C.c_longlong * 64)()
+    lib().wm_debug_ticks(buf, 64)
+    t = list(buf)
+    names = {}
+    for g in range(0, 18, 2):
+        names[g] = f"EW g0: half-tile {g} S^T/dP^T seen"
+        names[g + 1] = f"EW g0: half-tile {g} P^T/dS^T done"
+    for g in range(18):
+        pass
+        names[36 + g] = f"   MMA: half-tile {g} products + next scores issued"
+    for j in range(3):
+        names[18 + j * 6] = f"         STORE: key tile {j} start (before waiting dK staging)"
+        names[19 + j * 6] = f"         STORE: key tile {j} dK stored"
+        names[20 + j * 6] = f"         STORE: key tile {j} dV stored"
+        names[54 + 2 * j] = f"      EW g1: key tile {j} accumulators final"
+        names[55 + 2 * j] = f"      EW g1: key tile {j} drained"
+    t0 = t[0]
+    prev = t0
+    print(f"--- attn_bwd v6 p={p}: second head of CTA 0")
+    for i in sorted(names, key=lambda k: t[k]):
+        print(f"{names[i]:52s} +{t[i] - prev:7d}  (@{t[i] - t0})")
+        prev = t[i]

@@ -46,6 +46,35 @@ WM_DEVICE uint32_t keep_pair_mask(uint32_t fword, uint32_t sel) {
 // Philox arithmetic below the mbarrier wait it is supposed to overlap with
 #define WM_PIN(x) asm volatile("" : "+r"(x))
 
+// One warp copies a compact staging tile [nrows, 8 * pv bytes] from shared memory to global rows of pitch ld
+// (elements) with row-contiguous 8-byte pieces (head slices are only 8-byte aligned). Piece idx = lane + 32 k lives
+// in row idx / pv: row and piece advance incrementally (a single warp runs ~1 dependent instruction per 5-10 cycles,
+// the first version's per-piece float divide made a tile cost ~5k cycles), six pieces in flight.
+WM_DEVICE void store_staged_tile(const uint8_t* src, __nv_bfloat16* gbase, size_t ld, int nrows, int pv, int lane) {
+  const int total = nrows * pv;
+  int r = lane / pv, p = lane - r * pv;
+  const int dr = 32 / pv, dp = 32 - dr * pv;
+  for (int base = 0; base < total; base += 32 * 6) {
+    uint2 v[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const int idx = base + u * 32 + lane;
+      if (idx < total) v[u] = *reinterpret_cast<const uint2*>(src + idx * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const int idx = base + u * 32 + lane;
+      if (idx < total) *reinterpret_cast<uint2*>(gbase + static_cast<size_t>(r) * ld + p * 4) = v[u];
+      p += dp;
+      r += dr;
+      if (p >= pv) {
+        p -= pv;
+        ++r;
+      }
+    }
+  }
+}
+
 WM_DEVICE void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -274,7 +303,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   } else if (warp == 14) {
     // ------------------------------------------------------------------ ctx store
     const int pv = dh >> 2;  // 8-byte pieces per row
-    const float inv_pv = 1.0f / static_cast<float>(pv);
     uint32_t t = 0;
     for (int n = 0; n < nmine; ++n) {
       const int item = blockIdx.x + n * gridDim.x;
@@ -285,11 +313,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
         const int nrows = min(128, S - i * 128);
         const uint8_t* src = sOut + ob * G::OUTB;
         __nv_bfloat16* obase = ctx + (static_cast<size_t>(b) * S + i * 128) * D + h * dh;
-        for (int idx = lane; idx < nrows * pv; idx += 32) {
-          const int r = static_cast<int>((static_cast<float>(idx) + 0.5f) * inv_pv);
-          const int pp = idx - r * pv;
-          *reinterpret_cast<uint2*>(obase + static_cast<size_t>(r) * D + pp * 4) = *reinterpret_cast<const uint2*>(src + idx * 8);
-        }
+        store_staged_tile(src, obase, D, nrows, pv, lane);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.out_free[ob]);
       }
@@ -458,7 +482,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
 //               warp w of a group reads lane quarter w%4 (32 keys) and the 32-query column slice (w/4)%2.
 //   warp 16     MMA issue (whole warp convergent, one elected lane)
 //   warp 17     TMA producer: K_j/V_j tiles (double buffered, fixed up), Q/dO half-tiles + dropout words (ring)
-//   warp 18     dQ/dK/dV store: drains five bf16 staging tiles with row-contiguous 8-byte stores
+//   warps 18-19 dQ/dK/dV store: drain five bf16 staging tiles with row-contiguous 8-byte stores
 // Per half-tile (j, ih):   S^T = K_j Q_ih^T and dP^T = V_j dO_ih^T land in region r (2 x 64 fp32 columns);
 //   the group turns them into P^T and dS^T (packed bf16, written back IN PLACE with tcgen05.st) and also parks dS^T
 //   in shared memory; then dV_j += P^T dO_ih and dK_j += dS^T Q_ih take their A operand from TMEM, and once both
@@ -473,7 +497,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
 // (regenerating Philox in this transposed order would cost one Philox block per element).
 // ------------------------------------------------------------------------------------------------
 constexpr int kBwdEwWarps = 16;
-constexpr int kBwdThreads = 32 * 19;
+constexpr int kBwdThreads = 32 * 20;
 
 struct AttnBwdBars {
   uint64_t kv_full[2], kv_ready[2], kv_free[2];
@@ -708,6 +732,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
         const uint32_t tS = tmem + r * 128;
         const uint32_t qa = smem_u32(sRing + slot * G::SLOT), da = qa + G::T64;
         mbar_wait(&bars.pds_full[r], (g >> 1) & 1, 85);  // P^T, dS^T in TMEM; dS half in shared memory
+        // if (J >= nt && J < 2 * nt) WM_TICK(18 + (g - nt * nh));
         if (ih == 0 && J >= 1) mbar_wait(&bars.acc_free, (J - 1) & 1, 86);  // previous dK/dV (dQ) drained
         tc_fence_after();
         // dV_j += P^T dO_ih, dK_j += dS^T Q_ih: k = 64 query rows, A k-step = 8 packed columns of the slice's first 16
@@ -732,32 +757,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
           umma_commit_warp(&bars.acc_full);
         }
         if (g + 2 < nG) issue_scores(g + 2);
+        if (J >= nt && J < 2 * nt) WM_TICK(36 + (g - nt * nh));
       }
     }
-  } else if (warp == 18) {
-    // ------------------------------------------------------------------ gradient store
-    const int pv = dh >> 2;
-    const float inv_pv = 1.0f / static_cast<float>(pv);
+  } else if (warp >= 18) {
+    // ------------------------------------------------------------------ gradient store (two warps)
+    // warp 18: dK_j (slot 0), dQ_0, dQ_2 (slots 2, 4); warp 19: dV_j (slot 1), dQ_1 (slot 3)
+    const int pv = dh >> 2, sw = warp - 18;
     auto drain = [&](int slot, uint32_t parity, __nv_bfloat16* gbase, int nrows) {
       mbar_wait(&bars.out_full[slot], parity, 87);
-      const uint8_t* src = sOut + slot * G::OUTB;
-      const int total = nrows * pv;
-      for (int base = 0; base < total; base += 32 * 6) {
-        uint2 v[6];
-#pragma unroll
-        for (int u = 0; u < 6; ++u) {
-          const int idx = base + u * 32 + lane;
-          if (idx < total) v[u] = *reinterpret_cast<const uint2*>(src + idx * 8);
-        }
-#pragma unroll
-        for (int u = 0; u < 6; ++u) {
-          const int idx = base + u * 32 + lane;
-          if (idx < total) {
-            const int r = static_cast<int>((static_cast<float>(idx) + 0.5f) * inv_pv);
-            *reinterpret_cast<uint2*>(gbase + static_cast<size_t>(r) * (3 * D) + (idx - r * pv) * 4) = v[u];
-          }
-        }
-      }
+      store_staged_tile(sOut + slot * G::OUTB, gbase, 3 * static_cast<size_t>(D), nrows, pv, lane);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.out_free[slot]);
     };
@@ -766,11 +775,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       const int item = blockIdx.x + n * gridDim.x;
       const int b = item / H, h = item - b * H;
       __nv_bfloat16* hb = dqkv + static_cast<size_t>(b) * S * (3 * D) + h * dh;
-      const int nrows = min(128, S - j * 128);
-      drain(0, J & 1, hb + static_cast<size_t>(j) * 128 * (3 * D) + D, nrows);
-      drain(1, J & 1, hb + static_cast<size_t>(j) * 128 * (3 * D) + 2 * D, nrows);
+      drain(sw, J & 1, hb + static_cast<size_t>(j) * 128 * (3 * D) + (1 + sw) * D, min(128, S - j * 128));
       if (j == nt - 1)
-        for (int i = 0; i < nt; ++i) drain(2 + i, n & 1, hb + static_cast<size_t>(i) * 128 * (3 * D), min(128, S - i * 128));
+        for (int i = sw; i < nt; i += 2) drain(2 + i, n & 1, hb + static_cast<size_t>(i) * 128 * (3 * D), min(128, S - i * 128));
     }
   } else {
     // ------------------------------------------------------------------ elementwise warps
@@ -810,6 +817,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       if (j == 0 && ih < 2) mbar_wait(&bars.st_full[n % 3], (n / 3) & 1, 88);
       mbar_wait(&bars.sdp_full[grp], (g >> 1) & 1, 89);
       tc_fence_after();
+      if (warp == 0 && n == 1) WM_TICK(g - nt * nh);
       if (DROP) mbar_wait(&bars.qd_full[slot], (g / RQ) & 1, 90);  // dropout words of this half-tile (long landed)
       if ((g >> 1) >= 2) mbar_wait(&bars.ds_free[tb], (((g >> 1) >> 1) - 1) & 1, 91);
       // dS tile layout: [q chunk of 8][128 keys][16 B]; this thread fills key row krow of chunks (ih&1)*8 + h2*4 + 0..3
@@ -860,12 +868,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.pds_full[grp]);
+      if (warp == 0 && n == 1) WM_TICK(g - nt * nh + 1);
       // ---- drains (group 1 handles the last half-tile of every key tile)
       if (ih == nh - 1) {
         const int item = blockIdx.x + n * gridDim.x;
         const int front = ((item % H) * dh) & 7;
         mbar_wait(&bars.acc_full, J & 1, 92);
         tc_fence_after();
+        if (warp == 8 && n == 1) WM_TICK(54 + 2 * j);
         // dK_j -> slot 0 (warps with h2 == 0), dV_j -> slot 1 (h2 == 1); thread = key row
         if (J >= 1) mbar_wait(&bars.out_free[h2], (J - 1) & 1, 93);
         stage_acc(h2 ? tdV : tdK, sOut + h2 * G::OUTB + krow * (dh * 2), front);
@@ -882,6 +892,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.acc_free);
+        if (warp == 8 && n == 1) WM_TICK(55 + 2 * j);
       }
     }
   }
