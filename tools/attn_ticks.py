@@ -50,11 +50,14 @@ for p in (0.0, 0.1):
         pass
         names[36 + g] = f"   MMA: half-tile {g} products + next scores issued"
     for j in range(3):
-        names[18 + j * 6] = f"         STORE: key tile {j} start (before waiting dK staging)"
-        names[19 + j * 6] = f"         STORE: key tile {j} dK stored"
-        names[20 + j * 6] = f"         STORE: key tile {j} dV stored"
-        names[54 + 2 * j] = f"      EW g1: key tile {j} accumulators final"
-        names[55 + 2 * j] = f"      EW g1: key tile {j} drained"
+        pass
+    for ih in range(6):
+        names[18 + ih * 3] = f"   MMA*: half-tile {6 + ih} P^T/dS^T seen"
+        names[19 + ih * 3] = f"   MMA*: half-tile {6 + ih} TS issued, operands of half-tile {8 + ih} landed"
+        names[20 + ih * 3] = f"   MMA*: half-tile {6 + ih} all issued"
+        pass
+    for ih in range(6):
+        names[54 + ih] = f"   MMA*: half-tile {6 + ih} 8 TS products issued"
     t0 = t[0]
     prev = t0
     print(f"--- attn_bwd v6 p={p}: second head of CTA 0")

@@ -18,6 +18,12 @@ namespace wm {
 
 constexpr int kSP = 384;                   // key rows staged per head (S <= 384)
 constexpr int kAttnMaskSlices = kSP / 32;  // 32-key slices per query row in the dropout word buffer
+// Dropout keep words: one 32-bit word per (query row, 32-key slice), bit k = key 32*slice + k. Stored so that the
+// block the backward kernel needs for one half-tile -- key tile j (4 slices) x 64 query rows -- is contiguous:
+// [item][key tile j (3)][query block of 64 (6)][slice in tile (4)][query row in block (64)].
+__host__ __device__ inline size_t attn_drop_word_index(int item, int j, int qblk, int slice_in_tile, int qrow) {
+  return (((static_cast<size_t>(item) * 3 + j) * 6 + qblk) * 4 + slice_in_tile) * 64 + qrow;
+}
 
 // Dropout on attention probabilities: one Philox4x32-7 block (the 7-round variant is the Crush-resistant
 // minimum of the Random123 paper; nothing here has to match torch's stream) decides 16 consecutive keys of one
@@ -416,7 +422,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
                   for (int w = 3; w >= 0; --w) bits = (bits << 4) | ((((fb[w] >> 7) & 0x01010101u) * 0x01020408u) >> 24);
 #pragma unroll
                   for (int w = 3; w >= 0; --w) bits = (bits << 4) | ((((fa[w] >> 7) & 0x01010101u) * 0x01020408u) >> 24);
-                  drop_words[(static_cast<size_t>(item) * kAttnMaskSlices + (k0 >> 5)) * kSP + q] = bits;
+                  drop_words[attn_drop_word_index(item, k0 >> 7, q >> 6, (k0 >> 5) & 3, q & 63)] = bits;
                 }
               }
               tmem_st16(tS + lane_sel + k0, pk);
@@ -501,7 +507,7 @@ constexpr int kBwdThreads = 32 * 20;
 
 struct AttnBwdBars {
   uint64_t kv_full[2], kv_ready[2], kv_free[2];
-  uint64_t qd_full[4], qd_free[4];
+  uint64_t qd_full[6], qd_free[6];
   uint64_t st_full[3];
   uint64_t sdp_full[2], pds_full[2];
   uint64_t ds_free[2];
@@ -512,7 +518,7 @@ struct AttnBwdBars {
 template <int NCH>
 struct AttnBwdGeom {
   static constexpr int DHP = (NCH * 8 + 15) / 16 * 16;
-  static constexpr int RQ = NCH <= 5 ? 4 : 3;          // Q/dO half-tile ring depth
+  static constexpr int RQ = NCH <= 5 ? 5 : 3;          // Q/dO half-tile ring depth (loads run RQ - 2 half-tiles ahead)
   static constexpr uint32_t CS128 = 128 * 16, CS64 = 64 * 16;
   static constexpr uint32_t T128 = NCH * CS128, T64 = NCH * CS64;
   static constexpr uint32_t SLOT = 2 * T64 + 1024;     // Q half-tile, dO half-tile, 4 x 64 dropout words
@@ -591,7 +597,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       mbar_init(&bars.ds_free[i], 1);
     }
     for (int i = 0; i < 3; ++i) mbar_init(&bars.st_full[i], 1);
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 6; ++i) {
       mbar_init(&bars.qd_full[i], 1);
       mbar_init(&bars.qd_free[i], 1);
     }
@@ -629,10 +635,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       const int kb = J & 1;
       if (J >= 2) mbar_wait(&bars.kv_free[kb], ((J >> 1) - 1) & 1, 80);
       mbar_arrive_expect_tx(&bars.kv_full[kb], 2 * NCH * 2048);
-      for (int ch = 0; ch < NCH; ++ch) {
-        tma_load_3d(sK + kb * G::T128 + ch * G::CS128, &tm_kv, &bars.kv_full[kb], D + col0 + ch * 8, j * 128, b);
-        tma_load_3d(sV + kb * G::T128 + ch * G::CS128, &tm_kv, &bars.kv_full[kb], 2 * D + col0 + ch * 8, j * 128, b);
-      }
+      tma_load_4d(sK + kb * G::T128, &tm_kv, &bars.kv_full[kb], 0, j * 128, (D + col0) >> 3, b);
+      tma_load_4d(sV + kb * G::T128, &tm_kv, &bars.kv_full[kb], 0, j * 128, (2 * D + col0) >> 3, b);
       if (j == 0) {
         mbar_arrive_expect_tx(&bars.st_full[n % 3], G::STB);
         bulk_load_1d(sStat + (n % 3) * G::STB, stats + static_cast<size_t>(item) * kSP, G::STB, &bars.st_full[n % 3]);
@@ -676,16 +680,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
           if (g >= RQ) mbar_wait(&bars.qd_free[slot], ((g / RQ) - 1) & 1, 82);
           uint8_t* dst = sRing + slot * G::SLOT;
           mbar_arrive_expect_tx(&bars.qd_full[slot], 2 * NCH * 1024 + (DROP ? 1024 : 0));
-          for (int ch = 0; ch < NCH; ++ch) {
-            tma_load_3d(dst + ch * G::CS64, &tm_q, &bars.qd_full[slot], col0 + ch * 8, ih * 64, b);
-            tma_load_3d(dst + G::T64 + ch * G::CS64, &tm_do, &bars.qd_full[slot], col0 + ch * 8, ih * 64, b);
-          }
-          if (DROP) {
+          tma_load_4d(dst, &tm_q, &bars.qd_full[slot], 0, ih * 64, col0 >> 3, b);
+          tma_load_4d(dst + G::T64, &tm_do, &bars.qd_full[slot], 0, ih * 64, col0 >> 3, b);
+          if (DROP) {  // [4 key slices][64 query rows] keep words of this half-tile: 1 KB, contiguous
             const int j = J - n * nt;
-            const uint32_t* src = drop_words + (static_cast<size_t>(item) * kAttnMaskSlices + 4 * j) * kSP + ih * 64;
-#pragma unroll
-            for (int s4 = 0; s4 < 4; ++s4)
-              bulk_load_1d(dst + 2 * G::T64 + s4 * 256, src + static_cast<size_t>(s4) * kSP, 256, &bars.qd_full[slot]);
+            bulk_load_1d(dst + 2 * G::T64, drop_words + attn_drop_word_index(item, j, ih, 0, 0), 1024, &bars.qd_full[slot]);
           }
         }
         __syncwarp();
@@ -704,24 +703,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       mbar_wait(&bars.kv_ready[kb], (J2 >> 1) & 1, 83);
       mbar_wait(&bars.qd_full[slot], (g2 / RQ) & 1, 84);
       tc_fence_after();
+      if (g2 >= 2 && (g2 - 2) / nh == nt + 1) WM_TICK(19 + ((g2 - 2) % nh) * 3);
       const uint32_t ka = smem_u32(sK + kb * G::T128), va = smem_u32(sV + kb * G::T128);
       const uint32_t qa = smem_u32(sRing + slot * G::SLOT), da = qa + G::T64;
       const uint32_t tS = tmem + (g2 & 1) * 128;
 #pragma unroll
       for (int which = 0; which < 2; ++which) {
         const uint32_t a = which ? va : ka, bq = which ? da : qa;
+        const uint64_t ad = umma_smem_desc(a, G::CS128, 128, UMMA_SWZ_NONE), bd = umma_smem_desc(bq, G::CS64, 128, UMMA_SWZ_NONE);
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks) {
-          const uint32_t a0 = a + ks * 2 * G::CS128, b0 = bq + ks * 2 * G::CS64;
-          const bool tail = kZeroTail && ks == KSTEPS - 1;
-          umma_ss_warp(tS + which * 64, umma_smem_desc(a0, tail ? zero_addr - a0 : G::CS128, 128, UMMA_SWZ_NONE),
-                       umma_smem_desc(b0, tail ? zero_addr - b0 : G::CS64, 128, UMMA_SWZ_NONE), idesc_s, ks != 0);
+          if (kZeroTail && ks == KSTEPS - 1) {
+            const uint32_t a0 = a + ks * 2 * G::CS128, b0 = bq + ks * 2 * G::CS64;
+            umma_ss_warp(tS + which * 64, umma_smem_desc(a0, zero_addr - a0, 128, UMMA_SWZ_NONE),
+                         umma_smem_desc(b0, zero_addr - b0, 128, UMMA_SWZ_NONE), idesc_s, ks != 0);
+          } else {
+            umma_ss_warp(tS + which * 64, ad + ks * ((2 * G::CS128) >> 4), bd + ks * ((2 * G::CS64) >> 4), idesc_s, ks != 0);
+          }
         }
       }
       umma_commit_warp(&bars.sdp_full[g2 & 1]);
     };
+    // Only the first half-tile's scores up front: the second region starts half a period later (its scores are
+    // queued when the first elementwise pass ends), so that one group's elementwise pass runs while the tensor
+    // pipe works on the other group's products. Started together, the two groups stay in phase: both fight for
+    // issue slots, then both wait for the tensor pipe -- measured 2x slower (profiles/r01_attn_phase_ticks.txt).
     if (nG > 0) issue_scores(0);
-    if (nG > 1) issue_scores(1);
     int g = 0;
     for (int J = 0; J < nJ; ++J) {
       const int j = J % nt;
@@ -732,23 +739,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
         const uint32_t tS = tmem + r * 128;
         const uint32_t qa = smem_u32(sRing + slot * G::SLOT), da = qa + G::T64;
         mbar_wait(&bars.pds_full[r], (g >> 1) & 1, 85);  // P^T, dS^T in TMEM; dS half in shared memory
-        // if (J >= nt && J < 2 * nt) WM_TICK(18 + (g - nt * nh));
+        if (J == nt + 1) WM_TICK(18 + ih * 3);
         if (ih == 0 && J >= 1) mbar_wait(&bars.acc_free, (J - 1) & 1, 86);  // previous dK/dV (dQ) drained
         tc_fence_after();
+        if (g == 0 && nG > 1) issue_scores(1);
         // dV_j += P^T dO_ih, dK_j += dS^T Q_ih: k = 64 query rows, A k-step = 8 packed columns of the slice's first 16
+        {
+          const uint64_t dod = umma_smem_desc(da, 128, G::CS64, UMMA_SWZ_NONE), qd = umma_smem_desc(qa, 128, G::CS64, UMMA_SWZ_NONE);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t acol = (ks >> 1) * 32 + (ks & 1) * 8;
-          umma_ts_warp(tdV, tS + acol, umma_smem_desc(da + ks * 256, 128, G::CS64, UMMA_SWZ_NONE), idesc_kv, (ih | ks) != 0);
-          umma_ts_warp(tdK, tS + 64 + acol, umma_smem_desc(qa + ks * 256, 128, G::CS64, UMMA_SWZ_NONE), idesc_kv, (ih | ks) != 0);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t acol = (ks >> 1) * 32 + (ks & 1) * 8;
+            umma_ts_warp(tdV, tS + acol, dod + ks * (256 >> 4), idesc_kv, (ih | ks) != 0);
+            umma_ts_warp(tdK, tS + 64 + acol, qd + ks * (256 >> 4), idesc_kv, (ih | ks) != 0);
+          }
         }
+        // the region is free as soon as these have run: queue the next-but-one half-tile's scores BEFORE the dQ
+        // product so that they do not wait behind it in the (in-order) tensor pipe
+        if (J == nt + 1) WM_TICK(54 + ih);
+        if (g + 2 < nG) issue_scores(g + 2);
         if (ih & 1) {  // both halves of query tile i are in the dS buffer: dQ_i += dS_i K_j (k = 128 keys)
           const int i = ih >> 1, tb = (g >> 1) & 1;
-          const uint32_t sa = smem_u32(sdS + tb * G::DSB);
+          const uint64_t sd = umma_smem_desc(smem_u32(sdS + tb * G::DSB), 128, 2048, UMMA_SWZ_NONE);
+          const uint64_t kd = umma_smem_desc(ka, 128, G::CS128, UMMA_SWZ_NONE);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_ss_warp(tdQ + i * DHP, umma_smem_desc(sa + ks * 256, 128, 2048, UMMA_SWZ_NONE),
-                         umma_smem_desc(ka + ks * 256, 128, G::CS128, UMMA_SWZ_NONE), idesc_q, (j | ks) != 0);
+            umma_ss_warp(tdQ + i * DHP, sd + ks * (256 >> 4), kd + ks * (256 >> 4), idesc_q, (j | ks) != 0);
           umma_commit_warp(&bars.ds_free[tb]);
         }
         umma_commit_warp(&bars.qd_free[slot]);
@@ -756,8 +771,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
           umma_commit_warp(&bars.kv_free[kb]);
           umma_commit_warp(&bars.acc_full);
         }
-        if (g + 2 < nG) issue_scores(g + 2);
         if (J >= nt && J < 2 * nt) WM_TICK(36 + (g - nt * nh));
+        if (J == nt + 1) WM_TICK(20 + ih * 3);
       }
     }
   } else if (warp >= 18) {
@@ -875,7 +890,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
         const int front = ((item % H) * dh) & 7;
         mbar_wait(&bars.acc_full, J & 1, 92);
         tc_fence_after();
-        if (warp == 8 && n == 1) WM_TICK(54 + 2 * j);
         // dK_j -> slot 0 (warps with h2 == 0), dV_j -> slot 1 (h2 == 1); thread = key row
         if (J >= 1) mbar_wait(&bars.out_free[h2], (J - 1) & 1, 93);
         stage_acc(h2 ? tdV : tdK, sOut + h2 * G::OUTB + krow * (dh * 2), front);
@@ -892,7 +906,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.acc_free);
-        if (warp == 8 && n == 1) WM_TICK(55 + 2 * j);
       }
     }
   }
@@ -942,9 +955,9 @@ static int launch_bwd_t(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, cons
                         int H, int dh, float scale, bool drop, float dscale, cudaStream_t stream) {
   const int D = H * dh;
   CUtensorMap tm_kv, tm_q, tm_do;
-  int rc = make_tmap_bf16_rows3d(&tm_kv, qkv, 3 * D, S, B, 3 * D, 128);
-  if (rc == WM_OK) rc = make_tmap_bf16_rows3d(&tm_q, qkv, 3 * D, S, B, 3 * D, 64);
-  if (rc == WM_OK) rc = make_tmap_bf16_rows3d(&tm_do, dctx, D, S, B, D, 64);
+  int rc = make_tmap_bf16_chunked4d(&tm_kv, qkv, 3 * D, S, B, 3 * D, 128, NCH);
+  if (rc == WM_OK) rc = make_tmap_bf16_chunked4d(&tm_q, qkv, 3 * D, S, B, 3 * D, 64, NCH);
+  if (rc == WM_OK) rc = make_tmap_bf16_chunked4d(&tm_do, dctx, D, S, B, D, 64, NCH);
   if (rc != WM_OK) return rc;
   {
     const long long total = static_cast<long long>(B) * kSP * H;

@@ -72,6 +72,24 @@ int make_tmap_bf16_rows3d(CUtensorMap* map, const void* base, uint64_t cols, uin
   return r == CUDA_SUCCESS ? WM_OK : WM_ERR_DRIVER;
 }
 
+// 4D view {8 columns, S rows, cols/8 chunks, B batches} of the same activation: one box {8, box_rows, box_chunks, 1}
+// lands as box_chunks consecutive core-matrix columns ([chunk][row][16 B]) -- a whole operand tile per TMA instruction
+// instead of one per chunk. Coordinates: (0, row, first column / 8, batch).
+int make_tmap_bf16_chunked4d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t S, uint64_t B, uint64_t ld,
+                             uint32_t box_rows, uint32_t box_chunks) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return WM_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((ld * 2) & 15u) || (cols & 7u)) return WM_ERR_ALIGN;
+  cuuint64_t gdim[4] = {8, S, cols / 8, B};
+  cuuint64_t gstr[3] = {ld * 2, 16, S * ld * 2};
+  cuuint32_t box[4] = {8, box_rows, box_chunks, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? WM_OK : WM_ERR_DRIVER;
+}
+
 // ------------------------------------------------------------------------------------------------
 // gemm_tn
 // ------------------------------------------------------------------------------------------------
