@@ -510,7 +510,6 @@ struct AttnBwdBars {
   uint64_t qd_full[6], qd_free[6];
   uint64_t st_full[3];
   uint64_t sdp_full[2], pds_full[2];
-  uint64_t ds_free[2];
   uint64_t acc_full, acc_free;
   uint64_t out_full[5], out_free[5];
 };
@@ -594,7 +593,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       mbar_init(&bars.kv_free[i], 1);
       mbar_init(&bars.sdp_full[i], 1);
       mbar_init(&bars.pds_full[i], 8);
-      mbar_init(&bars.ds_free[i], 1);
     }
     for (int i = 0; i < 3; ++i) mbar_init(&bars.st_full[i], 1);
     for (int i = 0; i < 6; ++i) {
@@ -700,7 +698,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
     auto issue_scores = [&](int g2) {  // S^T = K_j Q_ih^T, dP^T = V_j dO_ih^T into region g2 & 1
       const int J2 = g2 / nh;
       const int kb = J2 & 1, slot = g2 % RQ;
-      mbar_wait(&bars.kv_ready[kb], (J2 >> 1) & 1, 83);
+      if (g2 - J2 * nh == 0) mbar_wait(&bars.kv_ready[kb], (J2 >> 1) & 1, 83);  // first half-tile of a key tile
       mbar_wait(&bars.qd_full[slot], (g2 / RQ) & 1, 84);
       tc_fence_after();
       if (g2 >= 2 && (g2 - 2) / nh == nt + 1) WM_TICK(19 + ((g2 - 2) % nh) * 3);
@@ -764,7 +762,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
             umma_ss_warp(tdQ + i * DHP, sd + ks * (256 >> 4), kd + ks * (256 >> 4), idesc_q, (j | ks) != 0);
-          umma_commit_warp(&bars.ds_free[tb]);
         }
         umma_commit_warp(&bars.qd_free[slot]);
         if (ih == nh - 1) {
@@ -833,8 +830,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       mbar_wait(&bars.sdp_full[grp], (g >> 1) & 1, 89);
       tc_fence_after();
       if (warp == 0 && n == 1) WM_TICK(g - nt * nh);
-      if (DROP) mbar_wait(&bars.qd_full[slot], (g / RQ) & 1, 90);  // dropout words of this half-tile (long landed)
-      if ((g >> 1) >= 2) mbar_wait(&bars.ds_free[tb], (((g >> 1) >> 1) - 1) & 1, 91);
+      // No wait for the dropout words (same transaction barrier as Q/dO, which the issue warp observed before it
+      // queued this half-tile's scores) nor for the dS buffer (its previous reader, the dQ product of tile
+      // (g >> 1) - 2, was queued before these scores and tcgen05.mma completes in order).
       // dS tile layout: [q chunk of 8][128 keys][16 B]; this thread fills key row krow of chunks (ih&1)*8 + h2*4 + 0..3
       uint8_t* dsrow = sdS + tb * G::DSB + ((ih & 1) * 8 + h2 * 4) * 2048 + krow * 16;
 #pragma unroll
