@@ -486,7 +486,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
 //   warps 0-15  elementwise, two groups of 8 that ping-pong over the stream of half-tiles: group g&1 owns TMEM
 //               region g&1. A half-tile is (key tile j: 128 keys = TMEM lanes) x (64 query rows = columns);
 //               warp w of a group reads lane quarter w%4 (32 keys) and the 32-query column slice (w/4)%2.
-//   warp 16     MMA issue (whole warp convergent, one elected lane)
+//   warp 16     MMA issue: gradient products (whole warp convergent, one elected lane)
+//   warp 20     MMA issue: score tiles of the next-but-one half-tile (a second issue warp: every wait / commit costs
+//               a few hundred cycles, one warp doing both was the critical path)
 //   warp 17     TMA producer: K_j/V_j tiles (double buffered, fixed up), Q/dO half-tiles + dropout words (ring)
 //   warps 18-19 dQ/dK/dV store: drain five bf16 staging tiles with row-contiguous 8-byte stores
 // Per half-tile (j, ih):   S^T = K_j Q_ih^T and dP^T = V_j dO_ih^T land in region r (2 x 64 fp32 columns);
@@ -503,13 +505,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
 // (regenerating Philox in this transposed order would cost one Philox block per element).
 // ------------------------------------------------------------------------------------------------
 constexpr int kBwdEwWarps = 16;
-constexpr int kBwdThreads = 32 * 20;
+constexpr int kBwdThreads = 32 * 21;
 
 struct AttnBwdBars {
   uint64_t kv_full[2], kv_ready[2], kv_free[2];
   uint64_t qd_full[6], qd_free[6];
   uint64_t st_full[3];
-  uint64_t sdp_full[2], pds_full[2];
+  uint64_t sdp_full[2], pds_full[2], ts_done[2];
   uint64_t acc_full, acc_free;
   uint64_t out_full[5], out_free[5];
 };
@@ -593,6 +595,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       mbar_init(&bars.kv_free[i], 1);
       mbar_init(&bars.sdp_full[i], 1);
       mbar_init(&bars.pds_full[i], 8);
+      mbar_init(&bars.ts_done[i], 1);
     }
     for (int i = 0; i < 3; ++i) mbar_init(&bars.st_full[i], 1);
     for (int i = 0; i < 6; ++i) {
@@ -625,20 +628,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       tma_prefetch_desc(&tm_do);
     }
     const bool need_fix = (dh & 7) != 0;
-    auto load_kv = [&](int J) {  // lane 0: K_j, V_j of key tile J (and the head's statistics with its first tile)
+    // All 32 lanes wait (a lone polling lane wakes up late -- see the note in wm_common.cuh), lane 0 issues.
+    auto load_kv = [&](int J) {  // K_j, V_j of key tile J (and the head's statistics with its first tile)
       const int n = J / nt, j = J - n * nt;
       const int item = blockIdx.x + n * gridDim.x;
       const int b = item / H, h = item - b * H;
       const int col0 = (h * dh) & ~7;
       const int kb = J & 1;
       if (J >= 2) mbar_wait(&bars.kv_free[kb], ((J >> 1) - 1) & 1, 80);
-      mbar_arrive_expect_tx(&bars.kv_full[kb], 2 * NCH * 2048);
-      tma_load_4d(sK + kb * G::T128, &tm_kv, &bars.kv_full[kb], 0, j * 128, (D + col0) >> 3, b);
-      tma_load_4d(sV + kb * G::T128, &tm_kv, &bars.kv_full[kb], 0, j * 128, (2 * D + col0) >> 3, b);
-      if (j == 0) {
-        mbar_arrive_expect_tx(&bars.st_full[n % 3], G::STB);
-        bulk_load_1d(sStat + (n % 3) * G::STB, stats + static_cast<size_t>(item) * kSP, G::STB, &bars.st_full[n % 3]);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&bars.kv_full[kb], 2 * NCH * 2048);
+        tma_load_4d(sK + kb * G::T128, &tm_kv, &bars.kv_full[kb], 0, j * 128, (D + col0) >> 3, b);
+        tma_load_4d(sV + kb * G::T128, &tm_kv, &bars.kv_full[kb], 0, j * 128, (2 * D + col0) >> 3, b);
+        if (j == 0) {
+          mbar_arrive_expect_tx(&bars.st_full[n % 3], G::STB);
+          bulk_load_1d(sStat + (n % 3) * G::STB, stats + static_cast<size_t>(item) * kSP, G::STB, &bars.st_full[n % 3]);
+        }
       }
+      __syncwarp();
     };
     auto fix_kv = [&](int J) {  // whole warp: zero the neighbouring head's 4 columns of K_j and V_j, publish
       const int n = J / nt;
@@ -660,8 +667,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       if (lane == 0) mbar_arrive(&bars.kv_ready[kb]);
     };
     if (nJ > 0) {
-      if (lane == 0) load_kv(0);
-      __syncwarp();
+      load_kv(0);
       fix_kv(0);
     }
     const int ih_load = RQ < nh - 1 ? RQ : nh - 1;  // late enough that kv_free of key tile J - 1 has been committed
@@ -672,10 +678,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       const int b = item / H, h = item - b * H;
       const int col0 = (h * dh) & ~7;
       for (int ih = 0; ih < nh; ++ih, ++g) {
+        if (ih == ih_load && J + 1 < nJ) load_kv(J + 1);
+        const int slot = g % RQ;
+        if (g >= RQ) mbar_wait(&bars.qd_free[slot], ((g / RQ) - 1) & 1, 82);
         if (lane == 0) {
-          if (ih == ih_load && J + 1 < nJ) load_kv(J + 1);
-          const int slot = g % RQ;
-          if (g >= RQ) mbar_wait(&bars.qd_free[slot], ((g / RQ) - 1) & 1, 82);
           uint8_t* dst = sRing + slot * G::SLOT;
           mbar_arrive_expect_tx(&bars.qd_full[slot], 2 * NCH * 1024 + (DROP ? 1024 : 0));
           tma_load_4d(dst, &tm_q, &bars.qd_full[slot], 0, ih * 64, col0 >> 3, b);
@@ -689,22 +695,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
         if (ih == nh - 1 && J + 1 < nJ) fix_kv(J + 1);
       }
     }
-  } else if (warp == 16) {
-    // ------------------------------------------------------------------ MMA issue
+  } else if (warp == 20) {
+    // ------------------------------------------------------------------ MMA issue: S^T = K_j Q_ih^T, dP^T = V_j dO_ih^T
     const uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-    const uint32_t idesc_kv = umma_idesc_bf16(128, DHP, 0, 1);  // A = P^T / dS^T from TMEM, B MN-major
-    const uint32_t idesc_q = umma_idesc_bf16(128, DHP, 1, 1);   // A = dS (MN-major, smem), B = K_j MN-major
     const uint32_t zero_addr = smem_u32(sZero);
-    auto issue_scores = [&](int g2) {  // S^T = K_j Q_ih^T, dP^T = V_j dO_ih^T into region g2 & 1
+    for (int g2 = 0; g2 < nG; ++g2) {
+      const int r = g2 & 1;
       const int J2 = g2 / nh;
       const int kb = J2 & 1, slot = g2 % RQ;
+      // Region r is free once the products that read half-tile g2 - 2's P^T / dS^T have run. The second region
+      // starts half a period late (after the first elementwise pass): started together, the two elementwise groups
+      // stay in phase -- both fight for issue slots, then both wait for the tensor pipe (2x slower, measured).
+      if (g2 >= 2) mbar_wait(&bars.ts_done[r], ((g2 - 2) >> 1) & 1, 96);
+      if (g2 == 1) mbar_wait(&bars.pds_full[0], 0, 97);
       if (g2 - J2 * nh == 0) mbar_wait(&bars.kv_ready[kb], (J2 >> 1) & 1, 83);  // first half-tile of a key tile
       mbar_wait(&bars.qd_full[slot], (g2 / RQ) & 1, 84);
       tc_fence_after();
-      if (g2 >= 2 && (g2 - 2) / nh == nt + 1) WM_TICK(19 + ((g2 - 2) % nh) * 3);
       const uint32_t ka = smem_u32(sK + kb * G::T128), va = smem_u32(sV + kb * G::T128);
       const uint32_t qa = smem_u32(sRing + slot * G::SLOT), da = qa + G::T64;
-      const uint32_t tS = tmem + (g2 & 1) * 128;
+      const uint32_t tS = tmem + r * 128;
 #pragma unroll
       for (int which = 0; which < 2; ++which) {
         const uint32_t a = which ? va : ka, bq = which ? da : qa;
@@ -720,13 +729,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
           }
         }
       }
-      umma_commit_warp(&bars.sdp_full[g2 & 1]);
-    };
-    // Only the first half-tile's scores up front: the second region starts half a period later (its scores are
-    // queued when the first elementwise pass ends), so that one group's elementwise pass runs while the tensor
-    // pipe works on the other group's products. Started together, the two groups stay in phase: both fight for
-    // issue slots, then both wait for the tensor pipe -- measured 2x slower (profiles/r01_attn_phase_ticks.txt).
-    if (nG > 0) issue_scores(0);
+      umma_commit_warp(&bars.sdp_full[r]);
+    }
+  } else if (warp == 16) {
+    // ------------------------------------------------------------------ MMA issue: gradient products
+    const uint32_t idesc_kv = umma_idesc_bf16(128, DHP, 0, 1);  // A = P^T / dS^T from TMEM, B MN-major
+    const uint32_t idesc_q = umma_idesc_bf16(128, DHP, 1, 1);   // A = dS (MN-major, smem), B = K_j MN-major
     int g = 0;
     for (int J = 0; J < nJ; ++J) {
       const int j = J % nt;
@@ -737,10 +745,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
         const uint32_t tS = tmem + r * 128;
         const uint32_t qa = smem_u32(sRing + slot * G::SLOT), da = qa + G::T64;
         mbar_wait(&bars.pds_full[r], (g >> 1) & 1, 85);  // P^T, dS^T in TMEM; dS half in shared memory
-        if (J == nt + 1) WM_TICK(18 + ih * 3);
         if (ih == 0 && J >= 1) mbar_wait(&bars.acc_free, (J - 1) & 1, 86);  // previous dK/dV (dQ) drained
         tc_fence_after();
-        if (g == 0 && nG > 1) issue_scores(1);
         // dV_j += P^T dO_ih, dK_j += dS^T Q_ih: k = 64 query rows, A k-step = 8 packed columns of the slice's first 16
         {
           const uint64_t dod = umma_smem_desc(da, 128, G::CS64, UMMA_SWZ_NONE), qd = umma_smem_desc(qa, 128, G::CS64, UMMA_SWZ_NONE);
@@ -751,10 +757,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
             umma_ts_warp(tdK, tS + 64 + acol, qd + ks * (256 >> 4), idesc_kv, (ih | ks) != 0);
           }
         }
-        // the region is free as soon as these have run: queue the next-but-one half-tile's scores BEFORE the dQ
-        // product so that they do not wait behind it in the (in-order) tensor pipe
-        if (J == nt + 1) WM_TICK(54 + ih);
-        if (g + 2 < nG) issue_scores(g + 2);
+        umma_commit_warp(&bars.ts_done[r]);     // region r may take the next-but-one half-tile's scores
+        umma_commit_warp(&bars.qd_free[slot]);  // last readers of this half-tile's Q / dO
         if (ih & 1) {  // both halves of query tile i are in the dS buffer: dQ_i += dS_i K_j (k = 128 keys)
           const int i = ih >> 1, tb = (g >> 1) & 1;
           const uint64_t sd = umma_smem_desc(smem_u32(sdS + tb * G::DSB), 128, 2048, UMMA_SWZ_NONE);
@@ -763,16 +767,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
           for (int ks = 0; ks < 8; ++ks)
             umma_ss_warp(tdQ + i * DHP, sd + ks * (256 >> 4), kd + ks * (256 >> 4), idesc_q, (j | ks) != 0);
         }
-        umma_commit_warp(&bars.qd_free[slot]);
         if (ih == nh - 1) {
           umma_commit_warp(&bars.kv_free[kb]);
           umma_commit_warp(&bars.acc_full);
         }
-        if (J >= nt && J < 2 * nt) WM_TICK(36 + (g - nt * nh));
-        if (J == nt + 1) WM_TICK(20 + ih * 3);
       }
     }
-  } else if (warp >= 18) {
+  } else if (warp >= 18) {  // (warps 18, 19)
     // ------------------------------------------------------------------ gradient store (two warps)
     // warp 18: dK_j (slot 0), dQ_0, dQ_2 (slots 2, 4); warp 19: dV_j (slot 1), dQ_1 (slot 3)
     const int pv = dh >> 2, sw = warp - 18;
@@ -830,9 +831,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       mbar_wait(&bars.sdp_full[grp], (g >> 1) & 1, 89);
       tc_fence_after();
       if (warp == 0 && n == 1) WM_TICK(g - nt * nh);
-      // No wait for the dropout words (same transaction barrier as Q/dO, which the issue warp observed before it
-      // queued this half-tile's scores) nor for the dS buffer (its previous reader, the dQ product of tile
-      // (g >> 1) - 2, was queued before these scores and tcgen05.mma completes in order).
+      // No wait for the dropout words (same transaction barrier as Q/dO, which the score-issue warp observed before
+      // it queued this half-tile's scores) nor for the dS buffer: its previous reader, the dQ product of tile
+      // (g >> 1) - 2, was queued by the product-issue warp before the products whose completion (ts_done) released
+      // this region to the score-issue warp, and tcgen05.mma of one thread completes in order.
       // dS tile layout: [q chunk of 8][128 keys][16 B]; this thread fills key row krow of chunks (ih&1)*8 + h2*4 + 0..3
       uint8_t* dsrow = sdS + tb * G::DSB + ((ih & 1) * 8 + h2 * 4) * 2048 + krow * 16;
 #pragma unroll
