@@ -401,7 +401,9 @@ __host__ __device__ inline float curand_uniform_from_u32(uint32_t x) {
 // keep iff lane >= thresh16 where thresh16 = round(p * 65536).
 WM_DEVICE uint32_t dropout_keep8(uint64_t seed, uint64_t stream, uint64_t group_index,
                                  uint32_t thresh16) {
-  Philox4 r = philox4x32_10(seed, stream, group_index);
+  // 7 rounds: the Crush-resistant minimum of the Random123 paper (only the torch.rand replay of the input masks has
+  // to match curand's 10-round stream); 30 % fewer instructions in the GEMM epilogues and LayerNorm backward
+  Philox4 r = philox4x32<7>(seed, stream, group_index);
   uint32_t m = 0;
   m |= ((r.x & 0xFFFFu) >= thresh16) << 0;
   m |= ((r.x >> 16) >= thresh16) << 1;

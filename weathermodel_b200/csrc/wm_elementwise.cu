@@ -93,12 +93,12 @@ int launch_mask_former(uint64_t seed, uint64_t philox_offset, int grid_x, int n_
 }
 
 // ------------------------------------------------------------------------------------------------
-// embed_fwd. CTA = 32 tokens x all D; W_in^T staged in smem as [Fin][D] fp32.
+// embed_fwd. CTA = 128 tokens x all D; rows of W_in staged in smem as [D][41] fp32.
 // ------------------------------------------------------------------------------------------------
-constexpr int kEmbTok = 32;
+constexpr int kEmbTok = 128;  // tokens per CTA: amortises staging the 34 x D weight matrix (was 32: staging ~= compute)
 constexpr int kXinLd = 64;  // padded bf16 copy of the 34-channel input row (wgrad operand)
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 embed_fwd_kernel(const float* __restrict__ weather, const uint8_t* __restrict__ mask, int64_t msb, int64_t mss,
                  const float* __restrict__ year, const float* __restrict__ coords,
                  const float* __restrict__ w_in, const float* __restrict__ b_in, const float* __restrict__ pe,
@@ -157,9 +157,7 @@ embed_fwd_kernel(const float* __restrict__ weather, const uint8_t* __restrict__ 
       float2 pev[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {  // the four position-table loads of this batch are issued together
-        int sidx = s0 + tb + u;
-        if (sidx >= S) sidx -= S;
-        if (sidx >= S) sidx -= S;
+        const int sidx = (s0 + tb + u) % S;
         pev[u] = (t0 + tb + u < M) ? __ldg(reinterpret_cast<const float2*>(pe + static_cast<size_t>(sidx) * D + d))
                                    : make_float2(0.f, 0.f);
       }
@@ -198,8 +196,12 @@ int launch_embed_fwd(const float* weather, const uint8_t* mask, int64_t msb, int
       cudaFuncSetAttribute(embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return WM_ERR_CUDA;
   const int blocks = static_cast<int>((M + kEmbTok - 1) / kEmbTok);
-  embed_fwd_kernel<<<blocks, 256, smem, stream>>>(weather, mask, msb, mss, year, coords, w_in, b_in, pe, out,
-                                                  xin, B, S, F, D);
+  // one thread per output column pair: D / 2 threads rounded up to a warp (256 threads left 7 of 8 warps idle in a
+  // second pass over d at D = 576)
+  int threads = ((D / 2 + 31) / 32) * 32;
+  if (threads > 512) threads = 512;
+  embed_fwd_kernel<<<blocks, threads, smem, stream>>>(weather, mask, msb, mss, year, coords, w_in, b_in, pe, out,
+                                                      xin, B, S, F, D);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
@@ -336,23 +338,31 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     }
   }
   const float invD = 1.0f / static_cast<float>(D);
-  // the next row's operands are requested before the current row is reduced, so every warp keeps two rows of
-  // loads in flight (8 warps x 2 rows x 2 tensors per SM) instead of stalling a full DRAM round trip per row
-  uint4 nx[kLnMaxChunks], nd[kLnMaxChunks];
-  float nmu = 0.0f, nrs = 0.0f;
+  // The operands of the next TWO rows are requested before the current row is reduced: the kernel holds ~200
+  // registers per thread (column partials), so only 8 warps live on an SM and the bytes in flight -- 8 warps x rows
+  // x 2 tensors x 1152 B -- decide the bandwidth (one row ahead: 37 KB per SM = ~3 TB/s by Little's law).
+  uint4 x0[kLnMaxChunks], d0[kLnMaxChunks], x1[kLnMaxChunks], d1[kLnMaxChunks];
+  float mu0 = 0.0f, rs0 = 0.0f, mu1 = 0.0f, rs1 = 0.0f;
   const int row0 = blockIdx.x * 8 + warp;
+  const int stride = gridDim.x * 8;
   if (row0 < M) {
-    ln_load_raw(x + static_cast<size_t>(row0) * D, nchunks, lane, nx);
-    ln_load_raw(dy + static_cast<size_t>(row0) * D, nchunks, lane, nd);
-    nmu = mean[row0];
-    nrs = rstd[row0];
+    ln_load_raw(x + static_cast<size_t>(row0) * D, nchunks, lane, x0);
+    ln_load_raw(dy + static_cast<size_t>(row0) * D, nchunks, lane, d0);
+    mu0 = mean[row0];
+    rs0 = rstd[row0];
   }
-  for (int row = row0; row < M; row += gridDim.x * 8) {
+  if (row0 + stride < M) {
+    ln_load_raw(x + static_cast<size_t>(row0 + stride) * D, nchunks, lane, x1);
+    ln_load_raw(dy + static_cast<size_t>(row0 + stride) * D, nchunks, lane, d1);
+    mu1 = mean[row0 + stride];
+    rs1 = rstd[row0 + stride];
+  }
+  auto body = [&](int row, uint4(&nx)[kLnMaxChunks], uint4(&nd)[kLnMaxChunks], float& nmu, float& nrs) {
     float xv[kLnMaxChunks][8], dv[kLnMaxChunks][8];
     ln_unpack(nx, xv);
     ln_unpack(nd, dv);
     const float mu = nmu, rs = nrs;
-    const int rown = row + gridDim.x * 8;
+    const int rown = row + 2 * stride;
     if (rown < M) {
       ln_load_raw(x + static_cast<size_t>(rown) * D, nchunks, lane, nx);
       ln_load_raw(dy + static_cast<size_t>(rown) * D, nchunks, lane, nd);
@@ -407,6 +417,10 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         }
       }
     }
+  };
+  for (int row = row0; row < M; row += 2 * stride) {
+    body(row, x0, d0, mu0, rs0);
+    if (row + stride < M) body(row + stride, x1, d1, mu1, rs1);
   }
   // CTA reduce: warp w writes its registers, then 256 threads fold 8 warps per column
 #pragma unroll
