@@ -93,12 +93,12 @@ int launch_mask_former(uint64_t seed, uint64_t philox_offset, int grid_x, int n_
 }
 
 // ------------------------------------------------------------------------------------------------
-// embed_fwd. CTA = 128 tokens x all D; rows of W_in staged in smem as [D][41] fp32.
+// embed_fwd. CTA = 64 tokens x all D; rows of W_in staged in smem as [D][41] fp32.
 // ------------------------------------------------------------------------------------------------
-constexpr int kEmbTok = 128;  // tokens per CTA: amortises staging the 34 x D weight matrix (was 32: staging ~= compute)
+constexpr int kEmbTok = 64;  // tokens per CTA (the 34 x D weight matrix is staged once per CTA)
 constexpr int kXinLd = 64;  // padded bf16 copy of the 34-channel input row (wgrad operand)
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(768)
 embed_fwd_kernel(const float* __restrict__ weather, const uint8_t* __restrict__ mask, int64_t msb, int64_t mss,
                  const float* __restrict__ year, const float* __restrict__ coords,
                  const float* __restrict__ w_in, const float* __restrict__ b_in, const float* __restrict__ pe,
@@ -143,43 +143,41 @@ embed_fwd_kernel(const float* __restrict__ weather, const uint8_t* __restrict__ 
       if (t < M) xin[t * kXinLd + c] = __float2bfloat16(c < Fin ? sX[tt * FinP + c] : 0.0f);
     }
   }
+  // One output column per thread (its 34 weights live in registers), two tokens in flight per step: with column
+  // PAIRS the kernel needed 118 registers and 112 KB of smem -- one 9-warp CTA per SM, 65 % of cycles without an
+  // eligible warp (ncu) and 1.27 ms for a 0.2 ms job.
   const int s0 = static_cast<int>(t0 % S);
-  for (int d = threadIdx.x * 2; d < D; d += blockDim.x * 2) {
-    float w0[40], w1[40];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float w0[40];
 #pragma unroll
-    for (int c = 0; c < 40; ++c) {
-      w0[c] = c < Fin ? sW[d * kWLd + c] : 0.0f;
-      w1[c] = c < Fin ? sW[(d + 1) * kWLd + c] : 0.0f;
-    }
-    const float bias0 = b_in[d], bias1 = b_in[d + 1];
+    for (int c = 0; c < 40; ++c) w0[c] = c < Fin ? sW[d * kWLd + c] : 0.0f;
+    const float bias0 = b_in[d];
 #pragma unroll 1
     for (int tb = 0; tb < kEmbTok; tb += 4) {
-      float2 pev[4];
+      float pev[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {  // the four position-table loads of this batch are issued together
         const int sidx = (s0 + tb + u) % S;
-        pev[u] = (t0 + tb + u < M) ? __ldg(reinterpret_cast<const float2*>(pe + static_cast<size_t>(sidx) * D + d))
-                                   : make_float2(0.f, 0.f);
+        pev[u] = (t0 + tb + u < M) ? __ldg(pe + static_cast<size_t>(sidx) * D + d) : 0.0f;
+      }
+      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int c4 = 0; c4 < 10; ++c4) {
+        if (c4 * 4 < FinP) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 x = reinterpret_cast<const float4*>(sX + (tb + u) * FinP)[c4];
+            acc[u] = fmaf(x.x, w0[c4 * 4], acc[u]);
+            acc[u] = fmaf(x.y, w0[c4 * 4 + 1], acc[u]);
+            acc[u] = fmaf(x.z, w0[c4 * 4 + 2], acc[u]);
+            acc[u] = fmaf(x.w, w0[c4 * 4 + 3], acc[u]);
+          }
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int tt = tb + u;
-        const int64_t t = t0 + tt;
-        float a0 = 0.0f, a1 = 0.0f;
-        const float4* xr = reinterpret_cast<const float4*>(sX + tt * FinP);
-#pragma unroll
-        for (int c4 = 0; c4 < 10; ++c4) {
-          if (c4 * 4 < FinP) {
-            const float4 x = xr[c4];
-            a0 = fmaf(x.x, w0[c4 * 4], a0); a1 = fmaf(x.x, w1[c4 * 4], a1);
-            a0 = fmaf(x.y, w0[c4 * 4 + 1], a0); a1 = fmaf(x.y, w1[c4 * 4 + 1], a1);
-            a0 = fmaf(x.z, w0[c4 * 4 + 2], a0); a1 = fmaf(x.z, w1[c4 * 4 + 2], a1);
-            a0 = fmaf(x.w, w0[c4 * 4 + 3], a0); a1 = fmaf(x.w, w1[c4 * 4 + 3], a1);
-          }
-        }
-        a0 = (a0 + bias0) + pev[u].x;
-        a1 = (a1 + bias1) + pev[u].y;
-        if (t < M) *reinterpret_cast<uint32_t*>(out + t * D + d) = pack_bf16x2(a0, a1);
+        const int64_t t = t0 + tb + u;
+        if (t < M) out[t * D + d] = __float2bfloat16((acc[u] + bias0) + pev[u]);
       }
     }
   }
@@ -196,10 +194,8 @@ int launch_embed_fwd(const float* weather, const uint8_t* mask, int64_t msb, int
       cudaFuncSetAttribute(embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return WM_ERR_CUDA;
   const int blocks = static_cast<int>((M + kEmbTok - 1) / kEmbTok);
-  // one thread per output column pair: D / 2 threads rounded up to a warp (256 threads left 7 of 8 warps idle in a
-  // second pass over d at D = 576)
-  int threads = ((D / 2 + 31) / 32) * 32;
-  if (threads > 512) threads = 512;
+  int threads = ((D + 31) / 32) * 32;  // one thread per output column
+  if (threads > 768) threads = 768;
   embed_fwd_kernel<<<blocks, threads, smem, stream>>>(weather, mask, msb, mss, year, coords, w_in, b_in, pe, out,
                                                       xin, B, S, F, D);
   WM_COUNT_LAUNCH();
