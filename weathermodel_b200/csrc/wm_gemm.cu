@@ -107,7 +107,7 @@ struct GemmSmemTail {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
-  float bias[8][128];  // per epilogue warp: the bias slice of its column half of the current tile
+  alignas(16) float bias[8][128];  // per epilogue warp: the bias slice of its column half of the current tile
 };
 
 // Epilogue of one 16-column group pair for one accumulator row. Auxiliary operands (residual / gate rows)
@@ -140,9 +140,17 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
   float f[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-  if (ep.bias) {
+  if (ep.bias) {  // four 16-byte broadcast loads (the scalar form cost ~2 L1 wavefronts per column: 38 % of the
+                  // kernel's L1 data-pipe traffic in profiles/r01_gemm_lin1_full.txt)
+    const float4* b4 = reinterpret_cast<const float4*>(sbias);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] += sbias[j];
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 bv = b4[j4];
+      f[4 * j4] += bv.x;
+      f[4 * j4 + 1] += bv.y;
+      f[4 * j4 + 2] += bv.z;
+      f[4 * j4 + 3] += bv.w;
+    }
   }
   if (ep.relu) {
 #pragma unroll
