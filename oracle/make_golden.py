@@ -196,6 +196,35 @@ def main():
     for kind in ["weatherbert", "weatherformer"]:
         np.savez_compressed(os.path.join(OUT, f"{kind}_yield_mini_b6.npz"), **yield_case(kind))
 
+    # ---- checkpoint interchange fixtures: what BaseTrainer.save_checkpoint writes
+    # (src/base_trainer/base_trainer.py:121-170): the whole pickled module and the resume dictionary, after one
+    # Adam step on the golden gradients of the mini WeatherBERT case
+    torch.manual_seed(1234)
+    ref = WeatherBERT(weather_dim=31, output_dim=31, device=torch.device("cpu"), **get_model_params("mini"))
+    g = dict(np.load(os.path.join(OUT, "weatherbert_mini_b8.npz")))
+    for k, prm in ref.named_parameters():
+        prm.grad = torch.from_numpy(g["grad/" + k].copy())
+    opt = torch.optim.Adam(ref.parameters(), lr=5e-4)
+    sch = get_scheduler(opt, 2, 10, 0.99)
+    for _ in range(3):  # epoch 0 has lr 0 under warm-up: step a few epochs so the moments AND the weights move
+        opt.step()
+        sch.step()
+    ref.eval()
+    w, coords, year, interval, _ = inputs(2)
+    mask = torch.zeros(2, 365, 31, dtype=torch.bool)
+    mask[:, :, ::3] = True
+    with torch.no_grad():
+        y = ref(w, coords, year, interval, weather_feature_mask=mask)
+    torch.save(ref, os.path.join(OUT, "ref_weatherbert_mini_latest.pth"))
+    torch.save({"epoch": 3, "model_state_dict": ref.state_dict(), "optimizer_state_dict": opt.state_dict(),
+                "scheduler_state_dict": sch.state_dict(), "best_val_loss": 1.25,
+                "output_json": {"model_config": {"total_params": ref.total_params()},
+                                "losses": {"train": {"total_loss": [1.5, 1.4, 1.3]}, "val": {"total_loss": [1.6, 1.5, 1.25]}}}},
+               os.path.join(OUT, "ref_weatherbert_mini_latest_checkpoint.pth"))
+    np.savez_compressed(os.path.join(OUT, "ref_weatherbert_mini_eval.npz"), weather=w.numpy(), coords=coords.numpy(),
+                        year=year.numpy(), interval=interval.numpy(), mask=mask.numpy(), y=y.numpy(),
+                        lr=np.array([opt.param_groups[0]["lr"]]))
+
     # ---- scheduler + sizes
     sched = {}
     for nm, warm, total, decay in [("exp", 10.0, 100, 0.99), ("cos", 5, 50, None), ("nowarm", 0, 20, 0.9)]:

@@ -200,7 +200,7 @@ def test_fused_adam_host_path_matches_torch_adam():
     torch.manual_seed(0)
     a = torch.nn.Parameter(torch.randn(50))
     b = torch.nn.Parameter(a.detach().clone())
-    o1, o2 = FusedAdam([a], lr=1e-2), torch.optim.Adam([b], lr=1e-2)
+    o1, o2 = FusedAdam([a], lr=1e-2, allow_host_params=True), torch.optim.Adam([b], lr=1e-2)
     for _ in range(5):
         gr = torch.randn(50)
         a.grad, b.grad = gr.clone(), gr.clone()
@@ -208,7 +208,7 @@ def test_fused_adam_host_path_matches_torch_adam():
         o2.step()
     assert torch.allclose(a, b, rtol=1e-6, atol=1e-8)
     sd = o1.state_dict()
-    o3 = FusedAdam([a], lr=1e-2)
+    o3 = FusedAdam([a], lr=1e-2, allow_host_params=True)
     o3.load_state_dict(sd)
     assert float(o3.state[a]["step"]) == 5.0
 

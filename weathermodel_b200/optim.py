@@ -15,12 +15,15 @@ from .engine import EncoderRuntime
 
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
-                 runtime: Optional[EncoderRuntime] = None):
+                 runtime: Optional[EncoderRuntime] = None, allow_host_params: bool = False):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         if len(self.param_groups) != 1:
             raise ValueError("FusedAdam supports a single param group (the reference uses one)")
         self.runtime = runtime
+        # host (CPU) parameters are refused unless a test of the state-dict / bookkeeping logic asks for them:
+        # there is no CPU path in the product
+        self.allow_host_params = allow_host_params
         self._flat_m = None
         self._flat_v = None
         self._step = 0
@@ -89,7 +92,10 @@ class FusedAdam(torch.optim.Optimizer):
             if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous():
                 with torch.cuda.device(p.device):
                     ops.adam_fused(p, p.grad, st["exp_avg"], st["exp_avg_sq"], k, lr, b1, b2, eps, wd)
-            else:  # host-side tensors only (never the hot path): same update in torch ops
+            else:
+                if not self.allow_host_params:
+                    raise RuntimeError("FusedAdam: parameter is not a contiguous fp32 CUDA tensor (no CPU fallback; "
+                                       "pass allow_host_params=True only to test host-side bookkeeping)")
                 g = p.grad if wd == 0 else p.grad.add(p, alpha=wd)
                 st["exp_avg"].lerp_(g, 1 - b1)
                 st["exp_avg_sq"].mul_(b2).addcmul_(g, g, value=1 - b2)
