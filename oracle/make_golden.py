@@ -152,6 +152,51 @@ def yield_case(kind, batch=6, n_past=5):
     return rec
 
 
+def sibling_case(kind, batch=4, beta=0.5):
+    """WeatherFormerSinusoid / WeatherFormerMixture: one trainer-formula loss and its
+    gradients on the mini size. Parameters are not stored (same seed => same draws, checked through checksums);
+    big gradient tensors are stored as norms plus a strided sample."""
+    from src.pretraining.models.weatherformer_mixture import WeatherFormerMixture
+    from src.pretraining.models.weatherformer_sinusoid import WeatherFormerSinusoid
+    from src.utils.losses import compute_mixture_kl_divergence
+
+    torch.manual_seed(1234)
+    if kind == "sinusoid":
+        model = WeatherFormerSinusoid(weather_dim=31, output_dim=31, k=4, device=torch.device("cpu"), **get_model_params("mini"))
+    else:
+        model = WeatherFormerMixture(weather_dim=31, output_dim=31, k=7, device=torch.device("cpu"), **get_model_params("mini"))
+    model.train()
+    neutralise_dropout(model)
+    w, coords, year, interval, _ = inputs(batch)
+    torch.manual_seed(1234)
+    mask = dataset("weatherformer", n=10).masking_function(365, 31, batch)
+    out = model(w, coords, year, interval, weather_feature_mask=mask)
+    mu, var = out[0], out[1]
+    nm = mask.sum(dim=(1, 2)).float().mean()
+    recon = (-gaussian_log_likelihood(w, mu, var, mask) / nm).mean()
+    rec = {}
+    if kind == "sinusoid":
+        kl_raw = compute_gaussian_kl_divergence(mask, mu, var, out[2], out[3])
+    else:
+        torch.manual_seed(99)
+        eps = torch.randn_like(mu)
+        rec["epsilon"] = eps.numpy()
+        z = mu + torch.sqrt(var) * eps
+        kl_raw = compute_mixture_kl_divergence(z=z, feature_mask=mask, mu_x=mu, var_x=var, mu_k=out[2], var_k=out[3], log_w_k=out[4])
+    kl = beta * kl_raw.mean() / nm
+    loss = recon + kl
+    loss.backward()
+    rec["loss"] = np.array([loss.item(), recon.item(), kl.item()], dtype=np.float64)
+    rec.update(weather=w.numpy(), coords=coords.numpy(), year=year.numpy(), interval=interval.numpy(),
+               mask=mask.contiguous().numpy()[:, 0, :], beta=np.array([beta]))
+    for k, v in model.named_parameters():
+        gnp = v.grad.detach().numpy()
+        rec["gnorm/" + k] = np.array([np.linalg.norm(gnp.astype(np.float64))])
+        rec["psum/" + k] = np.array([v.detach().double().sum().item(), v.detach().double().abs().sum().item()])
+        rec["gsample/" + k] = gnp.reshape(-1)[::max(1, gnp.size // 2048)].copy()
+    return rec
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # ---- masks on the CPU generator (config 1), SURVEY.md 8(c) golden values
@@ -171,6 +216,12 @@ def main():
         masks[name + "_sha16"] = np.frombuffer(want_sha.encode(), dtype=np.uint8)
         masks[name + "_row00"] = m[0, 0]
         masks[name + "_packed"] = np.packbits(m if kind == "weatherbert" else m[:, 0, :])
+    for name, pm in [("simmtm_p15", 0.15), ("simmtm_p30", 0.30)]:  # contiguous-segment masks (reference :86-184)
+        torch.manual_seed(1234)
+        m = dataset("simmtm", p=pm).masking_function(365, 31, 64).contiguous().numpy()
+        assert (m == m[:, :, :1]).all() and int(m[:, :, 0].sum(1).max()) <= int(365 * pm)
+        masks[name + "_sum"] = np.array([m.sum()])
+        masks[name + "_packed"] = np.packbits(m[:, :, 0])
     torch.manual_seed(1234)
     r5 = torch.rand(5).numpy()
     assert np.allclose(r5, [0.028979241847991943, 0.4018985629081726, 0.25984418392181396, 0.3666413426399231,
@@ -195,6 +246,10 @@ def main():
     # ---- yield fine-tune models (BASELINE.json configs[5])
     for kind in ["weatherbert", "weatherformer"]:
         np.savez_compressed(os.path.join(OUT, f"{kind}_yield_mini_b6.npz"), **yield_case(kind))
+
+    # ---- encoder siblings with learned priors
+    for kind in ["sinusoid", "mixture"]:
+        np.savez_compressed(os.path.join(OUT, f"weatherformer_{kind}_mini_b4.npz"), **sibling_case(kind))
 
     # ---- checkpoint interchange fixtures: what BaseTrainer.save_checkpoint writes
     # (src/base_trainer/base_trainer.py:121-170): the whole pickled module and the resume dictionary, after one

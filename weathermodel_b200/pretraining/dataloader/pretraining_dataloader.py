@@ -39,7 +39,8 @@ class StreamingDataset(torch.utils.data.IterableDataset):
         self.batch_size = batch_size
         self.device = f"cuda:{rank}" if torch.cuda.is_available() else "cpu"
         table = {"weatherbert": self.weatherbert_masking_function,
-                 "weatherformer": self.weatherformer_masking_function}
+                 "weatherformer": self.weatherformer_masking_function,
+                 "simmtm": self.simmtm_masking_function}
         if masking_function not in table:
             raise ValueError(f"Masking function {masking_function} is not valid")
         self.masking_function = table[masking_function]
@@ -57,6 +58,36 @@ class StreamingDataset(torch.utils.data.IterableDataset):
             return ops.mask_former(seq_len, n_features, batch_size, self.n_masked_features, device=self.device)
         order = torch.argsort(torch.rand(batch_size, n_features, device=self.device), dim=-1)
         return (order < self.n_masked_features).unsqueeze(1).expand(-1, seq_len, -1)
+
+    def simmtm_masking_function(self, seq_len, n_features, batch_size):
+        """Contiguous time segments (geometric lengths, mean 5), the same positions for every feature, trimmed to
+        int(seq_len * masking_prob) positions per sample (reference :86-184). Not a hot kernel -- once per chunk
+        -- so it stays torch ops on the loader's device, drawing from the generator in the reference's order
+        (Geometric.sample, rand, and rand_like only when a sample has to be trimmed): same seed, same masks."""
+        dev = self.device
+        target = int(seq_len * self.masking_prob)
+        if target == 0:
+            return torch.zeros(batch_size, seq_len, n_features, dtype=torch.bool, device=dev)
+        nseg = max(1, target // 5 + 5)  # candidate segments per sample
+        total = batch_size * nseg
+        length = torch.distributions.Geometric(probs=torch.tensor(1 / 5, device=dev)).sample((total,)).int()
+        length = torch.clamp(length, min=1, max=seq_len)
+        room = torch.clamp(seq_len - length, min=0)
+        start = (torch.rand(total, device=dev) * (room + 1).float()).long()
+        length, start = length.view(batch_size, nseg), start.view(batch_size, nseg)
+        order = torch.argsort(start, dim=-1)
+        start, length = torch.gather(start, -1, order), torch.gather(length, -1, order)
+        end = start + length
+        prev_end = torch.cat([torch.zeros(batch_size, 1, device=dev, dtype=torch.long), end[:, :-1]], dim=-1)
+        keep_seg = (start >= prev_end).unsqueeze(-1)  # drop a segment that starts inside its predecessor
+        pos = torch.arange(seq_len, device=dev)[None, None, :]
+        hit = ((pos >= start.unsqueeze(-1)) & (pos < end.unsqueeze(-1)) & keep_seg).any(dim=1)  # [B, S]
+        too_many = hit.sum(dim=1) > target
+        if too_many.any():  # keep a random subset of exactly `target` masked positions in those samples
+            r = torch.where(hit, torch.rand_like(hit.float()), torch.inf)
+            rank = torch.argsort(torch.argsort(r, dim=1), dim=1)
+            hit = torch.where(too_many.unsqueeze(1), rank < target, hit)
+        return hit.unsqueeze(-1).expand(-1, -1, n_features)
 
     # ---- chunk -> tensors -------------------------------------------------------------------------
     def _load_chunk(self, path) -> Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:

@@ -3,9 +3,10 @@
     python -m src.pretraining.pretraining_main --model weatherformer --model-size small --batch-size 128
     torchrun --nnodes=1 --nproc-per-node=8 -m src.pretraining.pretraining_main --model weatherformer ...
 
-`--model` accepts the encoder families this B200 path implements (weatherformer, weatherbert); the
-reference's ablation/baseline model names are rejected with a clear message instead of silently running
-something else."""
+`--model` accepts every model that is built on the transformer encoder of the B200 path: weatherformer,
+weatherbert and their siblings weatherautoencoder, simmtm, weatherformersinusoid, weatherformermixture (they
+inherit the encoder; their priors / masks are small torch-op additions). The MLP / CNN baselines are rejected
+with a clear message instead of silently running something else."""
 import argparse
 import logging
 
@@ -24,7 +25,7 @@ _FLAGS = [
     ("--decay-factor", dict(default=0.99, type=float, help="exponential LR decay factor after warm-up")),
     ("--model-size", dict(default="small", type=str, help="mini (60k), small (2M), medium (8M), large (32M)")),
     ("--masking-prob", dict(default=0.30, type=float, help="fraction of elements to mask (weatherbert)")),
-    ("--n-mixture-components", dict(default=1, type=int, help="accepted for CLI compatibility; unused here")),
+    ("--n-mixture-components", dict(default=1, type=int, help="mixture / sinusoid components (weatherformermixture, weatherformersinusoid)")),
     ("--beta", dict(default=0.5, type=float, help="weight of the KL term (weatherformer)")),
 ]
 
@@ -44,8 +45,17 @@ def main():
             from .trainers.weatherformer_trainer import weatherformer_training_loop as loop
         elif kind == "weatherbert":
             from .trainers.weatherbert_trainer import weatherbert_training_loop as loop
+        elif kind == "weatherautoencoder":
+            from .trainers.weatherautoencoder_trainer import weatherautoencoder_training_loop as loop
+        elif kind == "simmtm":
+            from .trainers.simmtm_trainer import simmtm_training_loop as loop
+        elif kind == "weatherformersinusoid":
+            from .trainers.weatherformer_sinusoid_trainer import weatherformer_sinusoid_training_loop as loop
+        elif kind == "weatherformermixture":
+            from .trainers.weatherformer_mixture_trainer import weatherformer_mixture_training_loop as loop
         else:
-            raise ValueError(f"model '{kind}' is outside the B200 hot path (supported: weatherformer, weatherbert)")
+            raise ValueError(f"model '{kind}' is outside the B200 hot path (supported: weatherformer, weatherbert, "
+                             "weatherautoencoder, simmtm, weatherformersinusoid, weatherformermixture)")
         best = loop(args_dict)
         if rank == 0:
             logging.getLogger(__name__).info(f"best validation loss: {best}")
