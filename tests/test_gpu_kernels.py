@@ -308,7 +308,10 @@ def _attn_ref(qkv, B, S, H, dh):
 
 
 @pytest.mark.parametrize("B,S,H,dh", [(2, 365, 4, 12), (2, 365, 10, 20), (1, 364, 12, 28), (3, 365, 16, 36),
-                                      (2, 128, 2, 36), (1, 70, 3, 16), (1, 384, 2, 48)])
+                                      (2, 128, 2, 36), (1, 70, 3, 16), (1, 384, 2, 48),
+                                      # ragged tiles / every chunk count: S around the 64 / 96 / 128-row boundaries
+                                      (1, 5, 2, 12), (2, 64, 2, 24), (1, 97, 4, 32), (1, 129, 2, 40), (1, 257, 2, 44),
+                                      (3, 300, 6, 20), (5, 193, 2, 36)])
 def test_attention_fwd_bwd(B, S, H, dh):
     D = H * dh
     qkv = _bf(B * S, 3 * D, seed=20)
@@ -328,10 +331,50 @@ def test_attention_fwd_bwd(B, S, H, dh):
     _cmp("attn dqkv", dqkv, ref, 5e-2, 5e-2)
 
 
-def test_attention_dropout_consistency():
+def _decode_keep_bits(words, B, S, H):
+    """keep[b, h, q, k] from the word buffer attn_fwd writes: one uint32 per (query row, 32-key slice), laid out
+    [item][key tile (3)][query block of 64 (6)][slice in tile (4)][query row in block (64)], bit = key & 31."""
+    w = words.view(B * H, 3, 6, 4, 64).to(torch.int64) & 0xFFFFFFFF
+    q = torch.arange(S, device=words.device)
+    k = torch.arange(S, device=words.device)
+    sel = w[:, (k >> 7)[None, :], (q >> 6)[:, None], ((k >> 5) & 3)[None, :], (q & 63)[:, None]]  # [BH, S(q), S(k)]
+    keep = (sel >> (k & 31)[None, None, :]) & 1
+    return keep.bool().view(B, H, S, S)
+
+
+@pytest.mark.parametrize("B,S,H,dh", [(2, 365, 4, 12), (1, 150, 2, 36), (2, 365, 16, 36)])
+def test_attention_dropout_matches_torch_with_the_same_mask(B, S, H, dh):
+    """Forward and backward with dropout against autograd of softmax(QK^T/sqrt(dh)) * keep / (1 - p_eff) @ V, with
+    `keep` decoded from the bits the forward kernel hands to the backward kernel (p_eff = round(128 p) / 128)."""
+    D = H * dh
+    p = 0.1
+    qkv = _bf(B * S, 3 * D, seed=30)
+    dctx = _bf(B * S, D, seed=31)
+    ctx, lse = ops.attn_fwd(qkv, B, S, H, dh, dropout_p=p, seed=5, stream_id=2)
+    keep = _decode_keep_bits(ctx.drop_words, B, S, H)
+    t7 = int(p * 128 + 0.5)
+    frac = keep.float().mean().item()
+    assert abs(frac - (1 - t7 / 128)) < 3e-3, f"keep fraction {frac}"
+    qd = qkv.double().requires_grad_(True)
+    x = qd.view(B, S, 3, H, dh).permute(2, 0, 3, 1, 4)
+    q, k, v = x[0], x[1], x[2]
+    s = q @ k.transpose(-1, -2) / math.sqrt(dh)
+    pr = torch.softmax(s, dim=-1) * keep.double() * (128.0 / (128 - t7))
+    o = (pr @ v).permute(0, 2, 1, 3).reshape(B * S, D)
+    _cmp("attn ctx (dropout)", ctx, o.detach(), 2e-2, 2e-2)
+    _cmp("attn lse (dropout)", lse, torch.logsumexp(s, dim=-1).reshape(B * H, S).detach(), 1e-3, 1e-3)
+    o.backward(dctx.double())
+    dqkv = ops.attn_bwd(qkv, ctx, dctx, lse, B, S, H, dh, dropout_p=p)
+    ref = qd.grad
+    for nm, sl in [("dQ", slice(0, D)), ("dK", slice(D, 2 * D)), ("dV", slice(2 * D, 3 * D))]:
+        r = ((dqkv[:, sl].double() - ref[:, sl]).norm() / ref[:, sl].norm()).item()
+        assert r < 2e-2, f"attn {nm} (dropout) rel fro err {r:.4g}"
+
+
+@pytest.mark.parametrize("B,S,H,dh", [(2, 365, 4, 12), (1, 200, 2, 36), (3, 365, 16, 36)])
+def test_attention_dropout_consistency(B, S, H, dh):
     """With dropout the kernels cannot be compared with torch's RNG; check the algebra instead:
     fwd is linear in V for a fixed mask, E[ctx] ~ no-dropout ctx, and bwd == finite differences of fwd."""
-    B, S, H, dh = 2, 365, 4, 12
     D = H * dh
     p = 0.1
     qkv = _bf(B * S, 3 * D, seed=22)
