@@ -43,24 +43,11 @@ for p in (0.0, 0.1):
     lib().wm_debug_ticks(buf, 64)
     t = list(buf)
     names = {}
-    for g in range(0, 18, 2):
-        names[g] = f"EW g0: half-tile {g} S^T/dP^T seen"
-        names[g + 1] = f"EW g0: half-tile {g} P^T/dS^T done"
-    for g in range(18):
-        pass
-        names[36 + g] = f"   MMA: half-tile {g} products + next scores issued"
-    for j in range(3):
-        pass
-    for ih in range(6):
-        names[18 + ih * 3] = f"   MMA*: half-tile {6 + ih} P^T/dS^T seen"
-        names[19 + ih * 3] = f"   MMA*: half-tile {6 + ih} TS issued, operands of half-tile {8 + ih} landed"
-        names[20 + ih * 3] = f"   MMA*: half-tile {6 + ih} all issued"
-        pass
-    for ih in range(6):
-        names[54 + ih] = f"   MMA*: half-tile {6 + ih} 8 TS products issued"
-    t0 = t[0]
-    prev = t0
-    print(f"--- attn_bwd v6 p={p}: second head of CTA 0")
-    for i in sorted(names, key=lambda k: t[k]):
-        print(f"{names[i]:52s} +{t[i] - prev:7d}  (@{t[i] - t0})")
+    for g in range(0, 18, 2):  # elementwise group 0 handles the even half-tiles of the head
+        names[g] = f"EW group 0: half-tile {g:2d} scores seen"
+        names[g + 1] = f"EW group 0: half-tile {g:2d} P^T / dS^T written"
+    prev = t[0]
+    print(f"--- attn_bwd v6 p={p}: second head of CTA 0, elementwise warp 0: {t[17] - t[0]} cycles for 9 of its 18 half-tiles")
+    for i in sorted(names):
+        print(f"{names[i]:46s} +{t[i] - prev:7d}  (@{t[i] - t[0]})")
         prev = t[i]
