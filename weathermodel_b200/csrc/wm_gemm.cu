@@ -222,7 +222,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t stage_bytes = a_bytes + b_bytes;
   GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(smem + static_cast<size_t>(stages) * stage_bytes);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const int m_tiles = (M + kBM - 1) / kBM;
   const int n_tiles = (N + BN - 1) / BN;
@@ -265,33 +265,34 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kBM, static_cast<uint32_t>(BN), 0, 0);
-      const uint64_t desc_a0 = umma_smem_desc(smem_u32(smem), 16, 1024, UMMA_SWZ_128B);
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aph = (it >> 1) & 1u;
-        mbar_wait(&tail->acc_empty[as], aph ^ 1u, 12);
+    // MMA issue: the WHOLE warp runs this loop convergently and umma_*_warp elect the issuing lane. One thread inside
+    // `if (lane == 0)` makes the compiler wrap every tcgen05 instruction in a per-active-lane loop: ~100 cycles per
+    // MMA (tools/mmabench.cu), i.e. 400 of the 512 cycles a k-block's four N = 256 MMAs take, plus the barrier wait.
+    const uint32_t idesc = umma_idesc_bf16(kBM, static_cast<uint32_t>(BN), 0, 0);
+    const uint64_t desc_a0 = umma_smem_desc(smem_u32(smem), 16, 1024, UMMA_SWZ_128B);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1u;
+      mbar_wait(&tail->acc_empty[as], aph ^ 1u, 12);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * kAccStride;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&tail->full[s], ph, 13);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * kAccStride;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&tail->full[s], ph, 13);
-          tc_fence_after();
-          // descriptors differ from the stage-0 ones only in the start-address field: one add per MMA
-          const uint64_t da_s = umma_desc_advance(desc_a0, static_cast<uint32_t>(s) * stage_bytes);
-          const uint64_t db_s = umma_desc_advance(da_s, a_bytes);
+        // descriptors differ from the stage-0 ones only in the start-address field: one add per MMA
+        const uint64_t da_s = umma_desc_advance(desc_a0, static_cast<uint32_t>(s) * stage_bytes);
+        const uint64_t db_s = umma_desc_advance(da_s, a_bytes);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            umma_ss(d_tmem, umma_desc_advance(da_s, k * 32), umma_desc_advance(db_s, k * 32), idesc,
-                    (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&tail->empty[s]);
-          if (++s == stages) { s = 0; ph ^= 1u; }
-        }
-        umma_commit(&tail->acc_full[as]);
+        for (int k = 0; k < kBK / 16; ++k)
+          umma_ss_warp(d_tmem, umma_desc_advance(da_s, k * 32), umma_desc_advance(db_s, k * 32), idesc,
+                       (kb | k) != 0 ? 1u : 0u);
+        umma_commit_warp(&tail->empty[s]);
+        if (++s == stages) { s = 0; ph ^= 1u; }
       }
+      umma_commit_warp(&tail->acc_full[as]);
     }
   } else {
     const int q = warp & 3;          // TMEM lane quarter this warp may read
@@ -615,7 +616,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t stage_bytes = a_bytes + b_bytes + ones_bytes;
   WgSmemTail* tail = reinterpret_cast<WgSmemTail*>(smem + static_cast<size_t>(kWgStages) * stage_bytes);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const int n_blk = blockIdx.x;  // tile over Nout (UMMA M side)
   const int k_blk = blockIdx.y;  // tile over Kout (UMMA N side)
@@ -665,26 +666,25 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kBM, static_cast<uint32_t>(BN + (fuse_bias && k_blk == 0 ? 16 : 0)), 1, 1);
-      // MN-major SW128: 64-wide MN chunks LBO = 8192 B apart, 8-token groups SBO = 1024 B apart
-      const uint64_t desc_a0 = umma_smem_desc(smem_u32(smem), 8192, 1024, UMMA_SWZ_128B);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&tail->full[s], ph, 23);
-        tc_fence_after();
-        const uint64_t da_s = umma_desc_advance(desc_a0, static_cast<uint32_t>(s) * stage_bytes);
-        const uint64_t db_s = umma_desc_advance(da_s, a_bytes);
+    // MMA issue, whole warp convergent (see gemm_tn_kernel)
+    const uint32_t idesc = umma_idesc_bf16(kBM, static_cast<uint32_t>(BN + (fuse_bias && k_blk == 0 ? 16 : 0)), 1, 1);
+    // MN-major SW128: 64-wide MN chunks LBO = 8192 B apart, 8-token groups SBO = 1024 B apart
+    const uint64_t desc_a0 = umma_smem_desc(smem_u32(smem), 8192, 1024, UMMA_SWZ_128B);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&tail->full[s], ph, 23);
+      tc_fence_after();
+      const uint64_t da_s = umma_desc_advance(desc_a0, static_cast<uint32_t>(s) * stage_bytes);
+      const uint64_t db_s = umma_desc_advance(da_s, a_bytes);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k)
-          umma_ss(tmem_base, umma_desc_advance(da_s, k * 2048), umma_desc_advance(db_s, k * 2048), idesc,
-                  (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&tail->empty[s]);
-        if (++s == kWgStages) { s = 0; ph ^= 1u; }
-      }
-      umma_commit(&tail->acc_full);
+      for (int k = 0; k < kBK / 16; ++k)
+        umma_ss_warp(tmem_base, umma_desc_advance(da_s, k * 2048), umma_desc_advance(db_s, k * 2048), idesc,
+                     (kb | k) != 0 ? 1u : 0u);
+      umma_commit_warp(&tail->empty[s]);
+      if (++s == kWgStages) { s = 0; ph ^= 1u; }
     }
+    umma_commit_warp(&tail->acc_full);
   } else {
     const int q = warp & 3;
     float* out = partial + static_cast<size_t>(split) * Nout * Kout;
