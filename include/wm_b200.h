@@ -59,7 +59,10 @@ int wm_embed_fwd(const float* weather, const uint8_t* mask, int64_t mask_stride_
 
 /* ---- dense layers: nn.Linear / MHA in- and out-projection / FFN
  *      (src/pretraining/models/weatherbert.py:34,45-56; torch:nn/modules/transformer.py:944-982).
- *      C[M,N] = epilogue(A[M,K] . B[N,K]^T): +bias, ReLU, dropout, ReLU-gate, +residual (all optional). */
+ *      C[M,N] = epilogue(A[M,K] . B[N,K]^T): +bias, ReLU, dropout, ReLU-gate, +residual (all optional).
+ *      sign_bits_out / gate_bits: one bit per output element ("> 0 after ReLU / dropout"), written by the forward
+ *      GEMM of a ReLU layer and read by the dgrad GEMM through that ReLU in place of gate_bf16
+ *      (wm_gemm_sign_bits_bytes(M, N) bytes; uint16 per (row, 16-column chunk), [row/32][chunk][row%32]). */
 typedef struct wm_gemm_epilogue {
   const float* bias;
   int relu;
@@ -71,7 +74,10 @@ typedef struct wm_gemm_epilogue {
   float gate_scale;
   const void* residual_bf16;
   int ld_res;
+  void* sign_bits_out;
+  const void* gate_bits;
 } wm_gemm_epilogue;
+size_t wm_gemm_sign_bits_bytes(int M, int N);
 int wm_gemm_tn(const void* A_bf16, int lda, const void* B_bf16, int ldb, int M, int N, int K,
                const wm_gemm_epilogue* epilogue /* may be NULL */, void* out, int ld_out, int out_is_fp32,
                int tile_n /* 0 = auto */, void* stream);

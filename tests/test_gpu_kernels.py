@@ -97,6 +97,13 @@ def test_gemm_tn_epilogues():
     gate = _bf(M, N, seed=8)
     _cmp("gate", ops.gemm_tn(a, b, gate=gate, gate_scale=1.25),
          torch.where(gate.float() > 0, acc * 1.25, torch.zeros_like(acc)), 1e-2, 1e-2)
+    # sign side channel: the bits a ReLU GEMM writes gate a later GEMM exactly like the activation itself would
+    bits = ops.gemm_sign_bits(M, N, "cuda")
+    h = ops.gemm_tn(a, b, bias=bias, relu=True, sign_bits_out=bits)
+    g1 = ops.gemm_tn(a, b, gate=h, gate_scale=1.25)
+    g2 = ops.gemm_tn(a, b, gate_bits=bits, gate_scale=1.25)
+    assert torch.equal(g1, g2), "gate through sign bits differs from gate through the bf16 activation"
+    assert ((h > 0) == (g2 != 0)).float().mean().item() > 0.999
     # dropout: kept fraction ~ 1-p, kept values scaled by 65536/(65536-thresh), identical across calls
     p = 0.1
     d1 = ops.gemm_tn(a, b, bias=bias, dropout_p=p, seed=11, stream_id=5, out_fp32=True)

@@ -16,6 +16,7 @@ class GemmEpilogue(C.Structure):
     _fields_ = [
         ("bias", _vp), ("relu", _i), ("dropout_p", _f), ("seed", _u64), ("stream_id", _u64),
         ("gate_bf16", _vp), ("ld_gate", _i), ("gate_scale", _f), ("residual_bf16", _vp), ("ld_res", _i),
+        ("sign_bits_out", _vp), ("gate_bits", _vp),
     ]
 
 
@@ -39,6 +40,7 @@ SIGNATURES = {
     "wm_mask_former": (_i, [_u64, _u64, _i, _i, _i64, _i, _vp, _vp]),
     "wm_embed_fwd": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wm_gemm_tn": (_i, [_vp, _i, _vp, _i, _i, _i, _i, C.POINTER(GemmEpilogue), _vp, _i, _i, _i, _vp]),
+    "wm_gemm_sign_bits_bytes": (_sz, [_i, _i]),
     "wm_gemm_wgrad_workspace_bytes": (_sz, [_i, _i, _i]),
     "wm_gemm_wgrad": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "wm_umma_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -88,6 +88,7 @@ int wm_embed_fwd(const float* weather, const uint8_t* mask, int64_t mask_stride_
                           MB(out_bf16), MB(xin_bf16), B, S, F, D, S_(stream));
 }
 
+size_t wm_gemm_sign_bits_bytes(int M, int N) { return gemm_sign_bits_bytes(M, N); }
 int wm_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const wm_gemm_epilogue* e,
                void* out, int ld_out, int out_is_fp32, int tile_n, void* stream) {
   if (!A || !B || !out) return WM_ERR_ARG;
@@ -104,6 +105,8 @@ int wm_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int
     ep.gate_scale = e->gate_scale;
     ep.residual = CB(e->residual_bf16);
     ep.ld_res = e->ld_res;
+    ep.sign_bits_out = static_cast<uint16_t*>(e->sign_bits_out);
+    ep.gate_bits = static_cast<const uint16_t*>(e->gate_bits);
     if ((ep.gate && (ep.ld_gate & 7)) || (ep.residual && (ep.ld_res & 7))) return WM_ERR_ALIGN;
   }
   ep.out = out;

@@ -68,6 +68,7 @@ struct LayerAct {
   __nv_bfloat16 *x, *qkv, *ctx, *r1, *u, *h, *r2;
   float *lse, *mean1, *rstd1, *mean2, *rstd2;
   uint32_t* dropw;  // attention dropout keep bits (forward -> backward); nullptr when the model has no dropout
+  uint16_t* hbits;  // sign bits of h (post ReLU / dropout): the gate of the linear2 dgrad
 };
 struct LayerWt {  // transposed bf16 copies for dgrad
   __nv_bfloat16 *wqkv_t, *wo_t, *w1_t, *w2_t;
@@ -145,6 +146,7 @@ static size_t carve(wm_encoder* e, uint8_t* base) {
     a.h = bf(M * FF);
     a.r2 = bf(M * D);
     a.lse = f32(static_cast<int64_t>(c.B) * c.H * c.S);
+    a.hbits = reinterpret_cast<uint16_t*>(take(gemm_sign_bits_bytes(static_cast<int>(M), c.FF)));
     a.dropw = c.dropout_p > 0.0f ? reinterpret_cast<uint32_t*>(take(attn_dropout_words_bytes(c.B, c.S, c.H))) : nullptr;
     a.mean1 = f32(M);
     a.rstd1 = f32(M);
@@ -331,6 +333,7 @@ int wm_encoder_forward(wm_encoder* e, const float* params, const float* weather,
       ep.drop_scale = dscale;
       ep.seed = seed;
       ep.stream = stream_id(step, l, 2);
+      ep.sign_bits_out = a.hbits;
       ep.out = a.h;
       ep.ld_out = FF;
       WM_TRY(launch_gemm_tn(a.u, D, e->shadow + q.w1, D, M, FF, D, ep, 0, 0, st));
@@ -399,8 +402,7 @@ int wm_encoder_backward_layers(wm_encoder* e, const float* params, int layer_hi,
     WM_TRY(launch_gemm_wgrad(gFd, D, a.h, FF, M, D, FF, grads + q.w2, 0, e->scratch, nullptr, st));
     {  // d h_pre = (gF W2) * [h > 0] / (1 - p)
       GemmEpilogue ep;
-      ep.gate = a.h;
-      ep.ld_gate = FF;
+      ep.gate_bits = a.hbits;  // one bit per element instead of re-reading the 2-byte activation
       ep.gate_scale = dscale;
       ep.out = e->gH;
       ep.ld_out = FF;

@@ -116,13 +116,23 @@ struct GemmSmemTail {
 // tile on dependent global loads: profiles/r01_gemm_v1_stalls.txt).
 struct EpiAux {
   uint4 a[2];  // the prefetched operand of a 16-column chunk: the gate rows if a gate is given, else the residual rows
+  uint32_t bits;  // sign bits of the chunk (ep.gate_bits): bit j = element n0 + j of this row passes the gate
 };
+// bit of element j (0..15) of a chunk inside its uint16: even elements in the low byte, odd ones in the high byte
+// (the order in which the packed bf16x2 output words yield them)
+__host__ __device__ constexpr int sign_bit_pos(int j) { return (j & 1) * 8 + (j >> 1); }
+WM_DEVICE size_t sign_bits_index(int row, int n0, int N) {
+  return (static_cast<size_t>(row >> 5) * static_cast<size_t>((N + 15) >> 4) + static_cast<size_t>(n0 >> 4)) * 32 + (row & 31);
+}
 
 WM_DEVICE void epi_load_aux(EpiAux& x, const GemmEpilogue& ep, int row, int n0, int M, int N, bool wide) {
   const __nv_bfloat16* base = ep.gate ? ep.gate : ep.residual;
   const int ldx = ep.gate ? ep.ld_gate : ep.ld_res;
   x.a[0] = make_uint4(0u, 0u, 0u, 0u);
   x.a[1] = make_uint4(0u, 0u, 0u, 0u);
+  x.bits = 0u;
+  // (the buffer covers whole 32-row blocks of the M rows, not whole 128-row tiles)
+  if (ep.gate_bits && n0 < N && row < ((M + 31) & ~31)) x.bits = __ldg(ep.gate_bits + sign_bits_index(row, n0, N));
   if (!base || row >= M) return;
   const __nv_bfloat16* p = base + static_cast<size_t>(row) * ldx + n0;
   if (wide && n0 + 16 <= N) {
@@ -136,7 +146,8 @@ WM_DEVICE void epi_load_aux(EpiAux& x, const GemmEpilogue& ep, int row, int n0, 
 template <typename OutT>
 WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const float* sbias, const GemmEpilogue& ep,
                              int row, int n0, int M, int N, bool wide) {
-  if (row >= M || n0 >= N) return;
+  if (n0 >= N) return;
+  if (row >= M && (!ep.sign_bits_out || row >= ((M + 31) & ~31))) return;
   float f[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
@@ -165,7 +176,10 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
       for (int j = 0; j < 8; ++j) f[g * 8 + j] = ((keep >> j) & 1u) ? f[g * 8 + j] * ep.drop_scale : 0.0f;
     }
   }
-  if (ep.gate) {  // dgrad through dropout(relu(.)): pass where the saved activation is > 0
+  if (ep.gate_bits) {  // dgrad through dropout(relu(.)): pass where the producing GEMM recorded a positive output
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = ((aux.bits >> sign_bit_pos(j)) & 1u) ? f[j] * ep.gate_scale : 0.0f;
+  } else if (ep.gate) {  // the same from the saved bf16 activation itself
     const uint32_t aw[8] = {aux.a[0].x, aux.a[0].y, aux.a[0].z, aux.a[0].w, aux.a[1].x, aux.a[1].y, aux.a[1].z, aux.a[1].w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -188,12 +202,33 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
     }
   }
   const bool second = n0 + 8 < N;  // N % 8 == 0 (host-checked)
+  if constexpr (sizeof(OutT) != 2) {
+    if (ep.sign_bits_out) {
+      uint32_t m = 0u;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) m |= (f[j] > 0.0f && row < M && (j < 8 || second)) ? (1u << sign_bit_pos(j)) : 0u;
+      ep.sign_bits_out[sign_bits_index(row, n0, N)] = static_cast<uint16_t>(m);
+      if (row >= M) return;
+    }
+  }
   if constexpr (sizeof(OutT) == 2) {
     uint4 o0, o1;
     o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
     o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
     o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
     o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+    if (ep.sign_bits_out) {
+      // 32 lanes x 2 bytes, contiguous: the rows of a whole 32-row block (rows >= M write zeros). The outputs are
+      // >= 0 here (post ReLU), so "positive" is "non-zero halfword": one packed min per word, then shift-adds.
+      const uint32_t w8[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+      uint32_t acc = 0u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc += __vminu2(w8[i], 0x00010001u) << i;  // even elements at bit i, odd at 16 + i
+      uint32_t m = (acc & 0xFFu) | ((acc >> 8) & 0xFF00u);
+      if (!second) m &= 0x0F0Fu;
+      ep.sign_bits_out[sign_bits_index(row, n0, N)] = static_cast<uint16_t>(row < M ? m : 0u);
+      if (row >= M) return;
+    }
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(row) * ep.ld_out + n0;
     if (wide && second) {
       stg256(o, o0, o1);
@@ -577,6 +612,10 @@ static int launch_gemm_tn_impl(const void* A, int lda, const void* B, int ldb, i
     WM_COUNT_LAUNCH();
   }
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+size_t gemm_sign_bits_bytes(int M, int N) {
+  return static_cast<size_t>((M + 31) / 32) * static_cast<size_t>((N + 15) / 16) * 32 * sizeof(uint16_t);
 }
 
 int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K,

@@ -28,6 +28,13 @@ struct GemmEpilogue {
   float gate_scale = 1.0f;
   const __nv_bfloat16* residual = nullptr;  // [M, ld_res]
   int ld_res = 0;
+  // Sign side channel for the ReLU-gate dgrad: the producing GEMM writes one bit per output element (value > 0
+  // after ReLU / dropout), the dgrad GEMM reads the bits instead of the bf16 activation (1/16 of the bytes, one
+  // coalesced 64-byte access per warp and 16-column chunk instead of 32 row-strided sectors). Layout: one uint16
+  // per (row, 16-column chunk): [row / 32][chunk][row % 32], element j at bit (j & 1) * 8 + (j >> 1);
+  // gemm_sign_bits_bytes(M, N) bytes. Only meaningful behind a ReLU (outputs >= 0).
+  uint16_t* sign_bits_out = nullptr;
+  const uint16_t* gate_bits = nullptr;   // replaces `gate` when given (gate_scale still applies)
   void* out = nullptr;                   // [M, ld_out] bf16 or fp32
   int ld_out = 0;
 };
@@ -35,6 +42,7 @@ struct GemmEpilogue {
 int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                    uint32_t box_cols, uint32_t box_rows);
 
+size_t gemm_sign_bits_bytes(int M, int N);
 int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
                    const GemmEpilogue& ep, int out_fp32, int bn_override, cudaStream_t stream);
 int launch_gemm_tn_rows(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int b_rows,

@@ -106,16 +106,21 @@ def embed_fwd(weather, mask, year, coords, w_in, b_in, pos_encoding, want_xin=Fa
 # ---------------------------------------------------------------------------------------------
 # GEMMs
 # ---------------------------------------------------------------------------------------------
+def gemm_sign_bits(M, N, device):
+    """Buffer for the sign side channel of gemm_tn (sign_bits_out= / gate_bits=)."""
+    return torch.empty(lib().wm_gemm_sign_bits_bytes(M, N) // 2, dtype=torch.int16, device=device)
+
+
 def gemm_tn(a, b, bias=None, relu=False, dropout_p=0.0, seed=0, stream_id=0, gate=None, gate_scale=1.0,
-            residual=None, out_fp32=False, tile_n=0):
+            residual=None, out_fp32=False, tile_n=0, sign_bits_out=None, gate_bits=None):
     """out[M,N] = epilogue(a[M,K] @ b[N,K]^T); a, b bf16 row-major."""
-    _cuda(a, b, bias, gate, residual)
+    _cuda(a, b, bias, gate, residual, sign_bits_out, gate_bits)
     M, K = a.shape
     N = b.shape[0]
     out = torch.empty((M, N), dtype=torch.float32 if out_fp32 else BF16, device=a.device)
     ep = _lib.GemmEpilogue(_p(bias), int(relu), float(dropout_p), int(seed), int(stream_id), _p(gate),
                            gate.stride(0) if gate is not None else 0, float(gate_scale), _p(residual),
-                           residual.stride(0) if residual is not None else 0)
+                           residual.stride(0) if residual is not None else 0, _p(sign_bits_out), _p(gate_bits))
     check(lib().wm_gemm_tn(_p(a), a.stride(0), _p(b), b.stride(0), M, N, K, C.byref(ep), _p(out), out.stride(0),
                            int(out_fp32), int(tile_n), _stream()), "wm_gemm_tn")
     return out
