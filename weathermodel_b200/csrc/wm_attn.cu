@@ -144,7 +144,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   constexpr int DHP = G::DHP, KVB = G::KVB, KSTEPS = DHP / 16;
   constexpr bool kZeroTail = (NCH & 1) != 0;  // last k-step: second core-matrix column comes from the zero chunk
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = smem_align_up(smem_raw, 128);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + 3 * G::QT;
   uint8_t* sV = sK + KVB * G::KT;
@@ -569,7 +569,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
   constexpr int DHP = G::DHP, KSTEPS = DHP / 16, RQ = G::RQ, NCG = DHP / 16;
   constexpr bool kZeroTail = (NCH & 1) != 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = smem_align_up(smem_raw, 128);
   uint8_t* sK = smem;                       // [2][T128]
   uint8_t* sV = sK + 2 * G::T128;           // [2][T128] (+ one chunk of slack for N = DHP > 8 NCH reads)
   uint8_t* sRing = sV + 2 * G::T128 + G::CS128;

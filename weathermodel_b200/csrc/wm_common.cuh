@@ -37,6 +37,15 @@ WM_DEVICE uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Round a pointer into the dynamic shared-memory array up to `align` bytes WITHOUT leaving the shared address
+// space: an integer offset added to the __shared__ array. Rounding through uintptr_t makes the compiler forget the
+// address space -- every access through the result became a generic LD.E / ST.E instead of LDS / STS (found in the
+// ncu source view of attn_bwd: the top stall was the scoreboard of those generic loads).
+WM_DEVICE uint8_t* smem_align_up(uint8_t* smem_raw, uint32_t align) {
+  const uint32_t a = smem_u32(smem_raw);
+  return smem_raw + (((a + align - 1u) & ~(align - 1u)) - a);
+}
+
 WM_DEVICE uint32_t lane_id() { return threadIdx.x & 31u; }
 
 WM_DEVICE bool elect_one() {

@@ -251,7 +251,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                int M, int N, int K, int BN, int stages, GemmEpilogue ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024B-align the tile ring (SWIZZLE_128B atoms)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align_up(smem_raw, 1024);
   const uint32_t a_bytes = kBM * kBK * 2;
   const uint32_t b_bytes = static_cast<uint32_t>(BN) * kBK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -398,7 +398,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 int M, int N, int K, int BN, int stages, GemmEpilogue ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align_up(smem_raw, 1024);
   const int BNH = BN >> 1;  // B rows staged by each CTA
   const uint32_t a_bytes = kBM * kBK * 2;
   const uint32_t b_bytes = static_cast<uint32_t>(BNH) * kBK * 2;
@@ -644,7 +644,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   int Mtok, int Nout, int Kout, int BN, int tok_per_split, float* __restrict__ partial,
                   float* __restrict__ bias_partial) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align_up(smem_raw, 1024);
   const uint32_t a_bytes = kBM * kBK * 2;                             // 2 boxes of 64 tok x 64 n
   const uint32_t b_bytes = static_cast<uint32_t>(BN) * kBK * 2;       // BN/64 boxes
   // Fused bias gradient (column sums of A over the tokens): an all-ones 64 x 64 chunk sits right behind the B
@@ -908,7 +908,7 @@ __global__ void __launch_bounds__(128, 1)
 umma_probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
                   float* __restrict__ D, int N, int K, int a_mn, int b_mn) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align_up(smem_raw, 1024);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int kg = K / 8;  // core matrices along K
