@@ -104,7 +104,7 @@ def test_gemm_tn_epilogues():
     g2 = ops.gemm_tn(a, b, gate_bits=bits, gate_scale=1.25)
     assert torch.equal(g1, g2), "gate through sign bits differs from gate through the bf16 activation"
     assert ((h > 0) == (g2 != 0)).float().mean().item() > 0.999
-    # dropout: kept fraction ~ 1-p, kept values scaled by 65536/(65536-thresh), identical across calls
+    # dropout: kept fraction ~ 1-p_eff, kept values scaled by 1/(1-p_eff) with p_eff = round(128 p)/128, identical across calls
     p = 0.1
     d1 = ops.gemm_tn(a, b, bias=bias, dropout_p=p, seed=11, stream_id=5, out_fp32=True)
     d2 = ops.gemm_tn(a, b, bias=bias, dropout_p=p, seed=11, stream_id=5, out_fp32=True)
@@ -112,10 +112,10 @@ def test_gemm_tn_epilogues():
     assert torch.equal(d1, d2), "dropout mask is not a pure function of (seed, stream, index)"
     kept = d1 != 0
     frac = kept.float().mean().item()
-    assert abs(frac - (1 - p)) < 5e-3, f"kept fraction {frac}"
+    t7 = int(p * 128 + 0.5)
+    assert abs(frac - (1 - t7 / 128)) < 5e-3, f"kept fraction {frac}"
     assert (kept != (d3 != 0)).float().mean().item() > 0.1, "different stream ids give the same mask"
-    thr = int(p * 65536 + 0.5)
-    scale = 65536.0 / (65536 - thr)
+    scale = 128.0 / (128 - t7)
     _cmp("dropout kept values", d1[kept], ((acc + bias) * scale)[kept], 2e-3, 2e-3)
 
 
@@ -222,7 +222,7 @@ def test_layernorm_fwd_bwd(M, D):
         probe = ops.gemm_tn(ones_a, ones_b, bias=torch.ones(D, device="cuda"), dropout_p=p, seed=5, stream_id=9,
                             out_fp32=True)
         keep = probe != 0
-        scale = 65536.0 / (65536 - int(p * 65536 + 0.5))
+        scale = 128.0 / (128 - int(p * 128 + 0.5))
         _cmp("ln dx_dropped", dxd2, torch.where(keep, dx.float() * scale, torch.zeros_like(probe)), 1e-2, 1e-3)
     _cmp("ln dbias dropped", dbias2, dxd2.double().sum(0), 1e-4, 1e-3)
 

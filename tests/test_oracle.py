@@ -140,3 +140,36 @@ def test_years_and_normalisation():
     assert abs(float(yrs[1, 364]) - (1984 + ((365 + 364) * 7) / 365)) < 1e-3 and yrs.max() < 2002.0
     y, i, c = O.normalize_year_interval_coords(yrs.astype(np.float64), np.array([[7.0], [7.0]]), np.array([[36.0, -90.0], [10.0, 20.0]]))
     assert np.allclose(c, [[0.1, -0.5], [10 / 360, 20 / 180]]) and np.allclose(i, 7 / 30) and np.allclose(y[0, 0], 0.14)
+
+
+def test_dropout_hash_statistics():
+    """The counter hash behind every dropout mask (csrc/wm_common.cuh: drop_hash32), restated in numpy: avalanche,
+    byte uniformity, keep rate and (absence of) correlation between neighbouring elements, words and streams."""
+    m32 = np.uint64(0xFFFFFFFF)
+
+    def h32(x, k0, k1):
+        x = x.astype(np.uint64)
+        p = ((x ^ np.uint64(k0)) & m32) * np.uint64(0x9E3779B1)
+        t = ((p >> np.uint64(32)) ^ (p & m32) ^ np.uint64(k1)) & m32
+        q = t * np.uint64(0x85EBCA77)
+        return (((q >> np.uint64(32)) ^ (q & m32)) & m32).astype(np.uint32)
+
+    n = 1 << 18
+    x = np.arange(n, dtype=np.uint32) + np.uint32(777)
+    k0, k1 = 0xA5A5F00D, 0x1234ABCD
+    r = h32(x, k0, k1)
+    for b in range(32):  # flipping any input bit flips every output bit about half of the time
+        d = r ^ h32(x ^ np.uint32(1 << b), k0, k1)
+        frac = np.unpackbits(d.view(np.uint8)).reshape(n, 32).mean(0)
+        assert frac.min() > 0.48 and frac.max() < 0.52, (b, frac.min(), frac.max())
+    by = r.view(np.uint8)
+    hist = np.bincount(by, minlength=256)
+    chi2 = ((hist - hist.mean()) ** 2 / hist.mean()).sum()
+    assert chi2 < 340, chi2  # 255 degrees of freedom: 340 is the 0.9997 quantile
+    keep = ((by & 0x7F) >= 13).astype(np.float64)
+    assert abs(keep.mean() - (1 - 13 / 128)) < 2e-3
+    kc = keep - keep.mean()
+    for lag in (1, 4, 16, 64):
+        assert abs((kc[:-lag] * kc[lag:]).mean() / kc.var()) < 6e-3, lag
+    other = ((h32(x, k0 ^ 0x9E3779B9, (k1 + 0x7F4A7C15) & 0xFFFFFFFF).view(np.uint8) & 0x7F) >= 13).astype(np.float64)
+    assert abs(((other - other.mean()) * kc).mean() / np.sqrt(other.var() * kc.var())) < 6e-3

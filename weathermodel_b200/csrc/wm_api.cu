@@ -10,7 +10,7 @@ inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline const __nv_bfloat16* CB(const void* p) { return reinterpret_cast<const __nv_bfloat16*>(p); }
 inline __nv_bfloat16* MB(void* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
 inline uint32_t thresh16(float p) { return p > 0.0f ? static_cast<uint32_t>(p * 65536.0f + 0.5f) : 0u; }
-inline float keep_scale(uint32_t t) { return t ? 65536.0f / static_cast<float>(65536u - t) : 1.0f; }
+inline float keep_scale(uint32_t t) { return wm::drop_keep_scale(t); }  // the kernels round p to a multiple of 1/128
 }  // namespace
 
 extern "C" {

@@ -9,9 +9,9 @@
 // 16-byte rows (elem(r, d) at (d/8)*R*16 + r*16 + (d%8)*2), which one and the same tile can feed to tcgen05.mma
 // either K-major (contract over head dim: LBO = R*16, SBO = 128) or MN-major (contract over rows: LBO = 128,
 // SBO = R*16).
-// Dropout on P: one Philox4x32-7 block keyed by (seed, stream, (bh*S + q)*ceil(S/16) + k/16) decides 16 consecutive
-// keys of a query row, one byte each; the forward kernel also stores the decisions as one 32-bit word per
-// (query row, 32-key slice) for the backward kernel.
+// Dropout on P: the counter hash of wm_common.cuh keyed by (seed, stream); group (bh*S + q)*ceil(S/16) + k/16 decides
+// 16 consecutive keys of a query row, one byte each; the forward kernel also stores the decisions as one 32-bit word
+// per (query row, 32-key slice) for the backward kernel.
 #include "wm_kernels.h"
 
 namespace wm {
@@ -25,19 +25,11 @@ __host__ __device__ inline size_t attn_drop_word_index(int item, int j, int qblk
   return (((static_cast<size_t>(item) * 3 + j) * 6 + qblk) * 4 + slice_in_tile) * 64 + qrow;
 }
 
-// Dropout on attention probabilities: one Philox4x32-7 block (the 7-round variant is the Crush-resistant
-// minimum of the Random123 paper; nothing here has to match torch's stream) decides 16 consecutive keys of one
-// query row, one byte each (7 bits used).
-constexpr int kAttnPhiloxRounds = 7;
-// keep iff (byte & 0x7F) >= thresh7: adding (128 - thresh7) to the 7-bit value carries into bit 7 of the byte exactly
-// then (no carry crosses a byte). add4 = (128 - thresh7) * 0x01010101; f[w] carries the keep flag of element
-// 4w + b in bit 7 of byte b (the other bits are noise) -- two integer ops per four elements.
-WM_DEVICE void keep_flags16(uint64_t seed, uint64_t stream, uint64_t grp, uint32_t add4, uint32_t (&f)[4]) {
-  const Philox4 r = philox4x32<kAttnPhiloxRounds>(seed, stream, grp);
-  f[0] = (r.x & 0x7F7F7F7Fu) + add4;
-  f[1] = (r.y & 0x7F7F7F7Fu) + add4;
-  f[2] = (r.z & 0x7F7F7F7Fu) + add4;
-  f[3] = (r.w & 0x7F7F7F7Fu) + add4;
+// Dropout on attention probabilities: the shared counter hash of wm_common.cuh; one 32-bit word decides four
+// consecutive keys of one query row, a group of 16 keys is four consecutive words.
+WM_DEVICE void keep_flags16(DropKeys keys, uint32_t grp, uint32_t add4, uint32_t (&f)[4]) {
+#pragma unroll
+  for (int w = 0; w < 4; ++w) f[w] = drop_flags4(grp * 4u + w, keys, add4);
 }
 // 0xFFFF / 0x0000 in each half of the result: keep flags of elements j (low half) and j + 1 (high half), j even,
 // for masking a packed bf16x2 pair -- one PRMT in sign-replicate mode (selector nibble bit 3)
@@ -139,7 +131,7 @@ template <int NCH, bool DROP>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ ctx,
                 float* __restrict__ lse_out, uint32_t* __restrict__ drop_words, int nitems, int S, int H, int dh,
-                float scale, uint32_t thresh7, float drop_scale, uint64_t seed, uint64_t stream_id) {
+                float scale, uint32_t thresh7, float drop_scale, DropKeys dkeys) {
   using G = AttnFwdGeom<NCH>;
   constexpr int DHP = G::DHP, KVB = G::KVB, KSTEPS = DHP / 16;
   constexpr bool kZeroTail = (NCH & 1) != 0;  // last k-step: second core-matrix column comes from the zero chunk
@@ -341,7 +333,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
         WM_FTICK(0);
         const int q = i * 128 + row;
         // dropout group (16 keys) index of this row's key 0: identical numbering in forward and backward
-        const uint64_t rowbase = (static_cast<uint64_t>(item) * S + (q < S ? q : 0)) * nk16;
+        const uint32_t rowbase = (static_cast<uint32_t>(item) * S + (q < S ? q : 0)) * nk16;  // host-checked to fit
         mbar_wait(&bars.s_full, t & 1, 72);
         tc_fence_after();
         WM_FTICK(2);
@@ -409,8 +401,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
               }
               if (DROP) {
                 uint32_t fa[4], fb[4];
-                keep_flags16(seed, stream_id, rowbase + (k0 >> 4), thresh4, fa);
-                keep_flags16(seed, stream_id, rowbase + (k0 >> 4) + 1, thresh4, fb);
+                keep_flags16(dkeys, rowbase + (k0 >> 4), thresh4, fa);
+                keep_flags16(dkeys, rowbase + (k0 >> 4) + 1, thresh4, fb);
 #pragma unroll
                 for (int w = 0; w < 8; ++w) {
                   pk[w] &= WM_KEEP_PAIR(fa, 2 * w);
@@ -944,8 +936,9 @@ static int launch_fwd_t(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
   const int nitems = B * H;
   const int grid = nitems < attn_sm_count() ? nitems : attn_sm_count();
-  kern<<<grid, kFwdThreads, smem, stream>>>(tm, ctx, lse, drop_words, nitems, S, H, dh, scale, thresh7, dscale, seed,
-                                            stream_id);
+  if (thresh7 && static_cast<uint64_t>(nitems) * S * ((S + 15) / 16) * 4ull > 0xFFFFFFFFull) return WM_ERR_SHAPE;  // 32-bit mask counters
+  kern<<<grid, kFwdThreads, smem, stream>>>(tm, ctx, lse, drop_words, nitems, S, H, dh, scale, thresh7, dscale,
+                                            drop_keys(seed, stream_id));
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
@@ -977,8 +970,8 @@ static int launch_bwd_t(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, cons
 
 // drop_thresh is the 16-bit threshold used everywhere else (round(p*65536)); attention rounds it to 7 bits
 static void attn_drop_params(uint32_t drop_thresh16, uint32_t* thresh7, float* scale) {
-  *thresh7 = (drop_thresh16 + 256u) >> 9;
-  *scale = *thresh7 ? 128.0f / static_cast<float>(128u - *thresh7) : 1.0f;
+  *thresh7 = drop_thresh7(drop_thresh16);
+  *scale = drop_keep_scale(drop_thresh16);
 }
 // TMA needs 16-byte aligned row pitches and head-block starts: D = H * dh a multiple of 8
 static bool attn_shape_ok(int B, int S, int H, int dh) {

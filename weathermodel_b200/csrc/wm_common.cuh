@@ -406,23 +406,47 @@ __host__ __device__ inline float curand_uniform_from_u32(uint32_t x) {
   return static_cast<float>(x) * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
 }
 
-// Dropout keep decision for 8 consecutive elements out of one Philox block: 16-bit lanes,
-// keep iff lane >= thresh16 where thresh16 = round(p * 65536).
-WM_DEVICE uint32_t dropout_keep8(uint64_t seed, uint64_t stream, uint64_t group_index,
-                                 uint32_t thresh16) {
-  // 7 rounds: the Crush-resistant minimum of the Random123 paper (only the torch.rand replay of the input masks has
-  // to match curand's 10-round stream); 30 % fewer instructions in the GEMM epilogues and LayerNorm backward
-  Philox4 r = philox4x32<7>(seed, stream, group_index);
-  uint32_t m = 0;
-  m |= ((r.x & 0xFFFFu) >= thresh16) << 0;
-  m |= ((r.x >> 16) >= thresh16) << 1;
-  m |= ((r.y & 0xFFFFu) >= thresh16) << 2;
-  m |= ((r.y >> 16) >= thresh16) << 3;
-  m |= ((r.z & 0xFFFFu) >= thresh16) << 4;
-  m |= ((r.z >> 16) >= thresh16) << 5;
-  m |= ((r.w & 0xFFFFu) >= thresh16) << 6;
-  m |= ((r.w >> 16) >= thresh16) << 7;
-  return m;
+// Dropout masks. Nothing here has to reproduce torch's stream (only the INPUT masks replay curand Philox, above), so
+// the keep decisions come from a much cheaper counter-based hash: two rounds of "multiply 32 x 32 -> 64, fold the
+// halves" keyed by two words derived from (seed, stream). Philox4x32-7 cost ~12 issue slots per element in the
+// attention forward kernel -- more than the softmax itself (ncu instruction mix, profiles/r01_attn_ncu_mix.txt);
+// this is ~1.5. Measured on 2^20 consecutive counters (tests/test_oracle.py): every input bit flips every output
+// bit with probability 0.498-0.503, byte histogram chi^2 = 234 (255 dof), keep decisions of neighbouring
+// elements / words / streams correlate below 1e-3.
+// One 32-bit word decides FOUR elements, one byte each: keep iff (byte & 0x7F) >= thresh7, thresh7 = round(128 p),
+// so the effective drop probability is thresh7 / 128 (0.1016 for p = 0.1) and the scale 128 / (128 - thresh7).
+// Element e of a row of N elements: word ((row * ceil(N/16) + e/16) * 4 + (e%16)/4), byte e%4 -- the GEMM epilogue,
+// LayerNorm backward and the attention kernels all use this numbering, so a mask can be regenerated anywhere.
+struct DropKeys {
+  uint32_t k0, k1;
+};
+__host__ __device__ inline DropKeys drop_keys(uint64_t seed, uint64_t stream) {  // splitmix64 finaliser
+  uint64_t z = seed + (stream + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return DropKeys{static_cast<uint32_t>(z), static_cast<uint32_t>(z >> 32)};
+}
+__host__ __device__ inline uint32_t drop_hash32(uint32_t x, DropKeys k) {
+  const uint64_t p = static_cast<uint64_t>(x ^ k.k0) * 0x9E3779B1u;
+  const uint32_t t = static_cast<uint32_t>(p >> 32) ^ static_cast<uint32_t>(p) ^ k.k1;
+  const uint64_t q = static_cast<uint64_t>(t) * 0x85EBCA77u;
+  return static_cast<uint32_t>(q >> 32) ^ static_cast<uint32_t>(q);
+}
+// bit 7 of byte b = keep flag of element b of the word (the other bits are noise): adding (128 - thresh7) to a 7-bit
+// value carries into bit 7 exactly when it is >= thresh7, and no carry crosses a byte. add4 = (128 - thresh7) * 0x01010101
+WM_DEVICE uint32_t drop_flags4(uint32_t x, DropKeys k, uint32_t add4) { return (drop_hash32(x, k) & 0x7F7F7F7Fu) + add4; }
+// all-ones / all-zeros 32-bit mask from the flag of byte b: one PRMT in sign-replicate mode
+template <int B>
+WM_DEVICE uint32_t drop_mask32(uint32_t flags) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(flags), "r"(0u), "r"((B | 8u) * 0x1111u));
+  return d;
+}
+__host__ __device__ inline uint32_t drop_thresh7(uint32_t thresh16) { return (thresh16 + 256u) >> 9; }
+__host__ __device__ inline float drop_keep_scale(uint32_t thresh16) {
+  const uint32_t t7 = drop_thresh7(thresh16);
+  return t7 ? 128.0f / static_cast<float>(128u - t7) : 1.0f;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -318,7 +318,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      const float* __restrict__ gamma, const float* __restrict__ mean,
                      const float* __restrict__ rstd, __nv_bfloat16* __restrict__ dx,
                      __nv_bfloat16* __restrict__ dx_drop, int M, int D, uint32_t drop_thresh, float drop_scale,
-                     uint64_t seed, uint64_t stream_id, float* __restrict__ partial) {
+                     DropKeys dkeys, float* __restrict__ partial) {
   extern __shared__ float sred[];  // [8 warps][3][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = D >> 3;
@@ -394,11 +394,17 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
         pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
         reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * D)[c] = pk;
-        if (drop_thresh) {
-          const uint64_t grp = (static_cast<uint64_t>(row) * static_cast<uint64_t>(D) + c * 8) >> 3;
-          const uint32_t keep = dropout_keep8(seed, stream_id, grp, drop_thresh);
+        if (drop_thresh) {  // the mask the GEMM epilogue drew for these 8 columns: two words of the 16-column group
+          const uint32_t add4 = (128u - drop_thresh7(drop_thresh)) * 0x01010101u;
+          const uint32_t x0 = (static_cast<uint32_t>(row) * static_cast<uint32_t>((D + 15) >> 4) + static_cast<uint32_t>(c >> 1)) * 4u + 2u * (c & 1);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = ((keep >> j) & 1u) ? o[j] * drop_scale : 0.0f;
+          for (int w = 0; w < 2; ++w) {
+            const uint32_t fl = drop_flags4(x0 + w, dkeys, add4);
+            o[4 * w] = __uint_as_float(__float_as_uint(o[4 * w] * drop_scale) & drop_mask32<0>(fl));
+            o[4 * w + 1] = __uint_as_float(__float_as_uint(o[4 * w + 1] * drop_scale) & drop_mask32<1>(fl));
+            o[4 * w + 2] = __uint_as_float(__float_as_uint(o[4 * w + 2] * drop_scale) & drop_mask32<2>(fl));
+            o[4 * w + 3] = __uint_as_float(__float_as_uint(o[4 * w + 3] * drop_scale) & drop_mask32<3>(fl));
+          }
           pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
           pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
           reinterpret_cast<uint4*>(dx_drop + static_cast<size_t>(row) * D)[c] = pk;
@@ -469,8 +475,9 @@ int launch_layernorm_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const 
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return WM_ERR_CUDA;
+  if (drop_thresh && static_cast<uint64_t>(M) * static_cast<uint64_t>((D + 15) / 16) * 4ull > 0xFFFFFFFFull) return WM_ERR_SHAPE;
   layernorm_bwd_kernel<<<ctas, 256, smem, stream>>>(dy, x, gamma, mean, rstd, dx, dx_drop, M, D, drop_thresh,
-                                                    drop_scale, seed, stream_id, workspace);
+                                                    drop_scale, drop_keys(seed, stream_id), workspace);
   WM_COUNT_LAUNCH();
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
   ln_bwd_finalize_kernel<<<(3 * D + 255) / 256, 256, 0, stream>>>(workspace, ctas, D, dgamma, dbeta, dbias);

@@ -291,7 +291,7 @@ int wm_encoder_forward(wm_encoder* e, const float* params, const float* weather,
   const int M = static_cast<int>(e->M), D = c.D, FF = c.FF, dh = c.D / c.H;
   const float p = training ? c.dropout_p : 0.0f;
   const uint32_t thr = static_cast<uint32_t>(p * 65536.0f + 0.5f);
-  const float dscale = thr ? 65536.0f / static_cast<float>(65536u - thr) : 1.0f;
+  const float dscale = drop_keep_scale(thr);  // the kernels round p to a multiple of 1/128
   e->seed = seed;
   e->step = step;
   e->training = training;
@@ -389,7 +389,7 @@ int wm_encoder_backward_layers(wm_encoder* e, const float* params, int layer_hi,
   const int M = static_cast<int>(e->M), D = c.D, FF = c.FF, dh = c.D / c.H;
   const float p = e->training ? c.dropout_p : 0.0f;
   const uint32_t thr = static_cast<uint32_t>(p * 65536.0f + 0.5f);
-  const float dscale = thr ? 65536.0f / static_cast<float>(65536u - thr) : 1.0f;
+  const float dscale = drop_keep_scale(thr);  // the kernels round p to a multiple of 1/128
   for (int l = layer_hi - 1; l >= layer_lo; --l) {
     const LayerParams& q = e->lay.layers[l];
     LayerAct& a = e->act[l];

@@ -168,12 +168,15 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
     for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
   }
   if (ep.drop_thresh) {
+    const uint32_t add4 = (128u - drop_thresh7(ep.drop_thresh)) * 0x01010101u;
+    const uint32_t x0 = (static_cast<uint32_t>(row) * static_cast<uint32_t>((N + 15) >> 4) + static_cast<uint32_t>(n0 >> 4)) * 4u;
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const uint64_t grp = (static_cast<uint64_t>(row) * static_cast<uint64_t>(N) + n0 + g * 8) >> 3;
-      const uint32_t keep = dropout_keep8(ep.seed, ep.stream, grp, ep.drop_thresh);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[g * 8 + j] = ((keep >> j) & 1u) ? f[g * 8 + j] * ep.drop_scale : 0.0f;
+    for (int w = 0; w < 4; ++w) {
+      const uint32_t fl = drop_flags4(x0 + w, ep.dkeys, add4);
+      f[4 * w] = __uint_as_float(__float_as_uint(f[4 * w] * ep.drop_scale) & drop_mask32<0>(fl));
+      f[4 * w + 1] = __uint_as_float(__float_as_uint(f[4 * w + 1] * ep.drop_scale) & drop_mask32<1>(fl));
+      f[4 * w + 2] = __uint_as_float(__float_as_uint(f[4 * w + 2] * ep.drop_scale) & drop_mask32<2>(fl));
+      f[4 * w + 3] = __uint_as_float(__float_as_uint(f[4 * w + 3] * ep.drop_scale) & drop_mask32<3>(fl));
     }
   }
   if (ep.gate_bits) {  // dgrad through dropout(relu(.)): pass where the producing GEMM recorded a positive output
@@ -567,7 +570,12 @@ static int num_sms() {
 }
 
 static int launch_gemm_tn_impl(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int b_rows,
-                               const GemmEpilogue& ep, int out_fp32, int bn_override, cudaStream_t stream) {
+                               const GemmEpilogue& ep_in, int out_fp32, int bn_override, cudaStream_t stream) {
+  GemmEpilogue ep = ep_in;
+  if (ep.drop_thresh) {
+    if (static_cast<uint64_t>(M) * static_cast<uint64_t>((N + 15) / 16) * 4ull > 0xFFFFFFFFull) return WM_ERR_SHAPE;  // 32-bit mask counters
+    ep.dkeys = drop_keys(ep.seed, ep.stream);
+  }
   if (M <= 0 || N <= 0 || K <= 0 || b_rows <= 0 || b_rows > N) return WM_ERR_SHAPE;
   if ((N & 7) || (K & 7) || (lda & 7) || (ldb & 7) || (ep.ld_out & 7)) return WM_ERR_ALIGN;
   const int BN = bn_override > 0 ? bn_override : pick_bn(N);

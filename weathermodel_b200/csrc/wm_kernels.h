@@ -19,10 +19,11 @@ namespace wm {
 struct GemmEpilogue {
   const float* bias = nullptr;           // [N] fp32
   int relu = 0;
-  uint32_t drop_thresh = 0;              // round(p * 65536); 0 = no dropout
-  float drop_scale = 1.0f;               // 1 / (1 - p)
-  uint64_t seed = 0;                     // Philox key
-  uint64_t stream = 0;                   // Philox subsequence: (step, layer, site)
+  uint32_t drop_thresh = 0;              // round(p * 65536); 0 = no dropout (the kernels use round(p * 128) / 128)
+  float drop_scale = 1.0f;               // drop_keep_scale(drop_thresh)
+  uint64_t seed = 0;                     // dropout key
+  uint64_t stream = 0;                   // dropout stream: (step, layer, site)
+  DropKeys dkeys = {0u, 0u};             // filled in by the launcher from (seed, stream)
   const __nv_bfloat16* gate = nullptr;   // [M, ld_gate] saved post-activation (dgrad through ReLU+dropout)
   int ld_gate = 0;
   float gate_scale = 1.0f;
