@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
                 const __grid_constant__ CUtensorMap tm_do, const float2* __restrict__ stats,
                 const uint32_t* __restrict__ drop_words, __nv_bfloat16* __restrict__ dqkv, int nitems, int S, int H,
-                int dh, float scale, float drop_scale) {
+                int dh, float scale, float clampv) {
   using G = AttnBwdGeom<NCH>;
   constexpr int DHP = G::DHP, KSTEPS = DHP / 16, RQ = G::RQ, NCG = DHP / 16;
   constexpr bool kZeroTail = (NCH & 1) != 0;
@@ -791,7 +791,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
     const int krow = lq * 32 + lane;           // key row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(lq * 32) << 16;
     const float c2 = scale * 1.4426950408889634f;
-    const float clampv = log2f(drop_scale);
+    // clampv = log2(drop_scale), computed on the host: log2f() in here put its zero / denormal special case (an FSEL
+    // per element) into the inner loop
     const uint32_t tS = tmem + grp * 128 + lane_sel;
     // TMEM accumulator columns [16 cg, 16 cg + 16) of this thread's row -> bf16 staging row (compact [128, dh])
     auto stage_acc = [&](uint32_t tacc, uint8_t* srow, int front) {
@@ -963,7 +964,8 @@ static int launch_bwd_t(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, cons
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
   const int nitems = B * H;
   const int grid = nitems < attn_sm_count() ? nitems : attn_sm_count();
-  kern<<<grid, kBwdThreads, smem, stream>>>(tm_kv, tm_q, tm_do, stats, drop_words, dqkv, nitems, S, H, dh, scale, dscale);
+  kern<<<grid, kBwdThreads, smem, stream>>>(tm_kv, tm_q, tm_do, stats, drop_words, dqkv, nitems, S, H, dh, scale,
+                                            log2f(dscale));
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
