@@ -33,6 +33,9 @@ def _cmp(name, got, ref, rtol, atol):
             f"first {first} got {got[first]:.5g} ref {ref[first]:.5g}; bad rows~{rows} cols~{cols}")
 
 
+GEMM_DEFAULTS = {"gemm_two_cta": -1, "gemm_epi_warps": 0}  # -1 / 0 = automatic choice  # library defaults (wm_gemm.cu)
+
+
 def _bf(*shape, scale=1.0, seed=0):
     g = torch.Generator(device="cuda").manual_seed(seed)
     return (torch.randn(*shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
@@ -78,9 +81,69 @@ def test_gemm_cta_pair_kernel_is_bit_identical(M, N, K):
         lib().wm_set_option(b"gemm_two_cta", 1)
         got = ops.gemm_tn(a, b, bias=bias, relu=True, residual=res)
     finally:
-        lib().wm_set_option(b"gemm_two_cta", 0)
+        lib().wm_set_option(b"gemm_two_cta", GEMM_DEFAULTS["gemm_two_cta"])
     assert torch.equal(ref, got)
     _cmp("cta-pair gemm", got, torch.relu(a.float() @ b.float().t() + bias) + res.float(), 1e-2, 2e-2)
+
+
+@pytest.mark.parametrize("M,N,K,tile_n", [
+    (1024, 576, 576, 0), (4099, 1728, 576, 0), (2085, 2304, 576, 0), (1500, 576, 2304, 0), (1031, 200, 200, 0),
+    (130, 48, 48, 0), (1111, 600, 200, 64), (2048, 1344, 336, 128), (365, 40, 64, 0),
+])
+def test_gemm_kernel_variants_are_bit_identical(M, N, K, tile_n):
+    """8 vs 16 epilogue warps (gemm_epi_warps) and single-CTA vs CTA-pair tiles (gemm_two_cta) must agree bit for
+    bit, incl. clipped rows / columns, dropout, the sign side channel, a residual and the fp32 output."""
+    from weathermodel_b200._lib import lib
+
+    a = _bf(M, K, seed=40)
+    b = _bf(N, K, scale=K ** -0.5, seed=41)
+    bias = torch.randn(N, device="cuda")
+    res = _bf(M, N, seed=42)
+    nbytes = lib().wm_gemm_sign_bits_bytes(M, N)
+
+    def run():
+        bits = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        o1 = ops.gemm_tn(a, b, bias=bias, relu=True, dropout_p=0.1, seed=11, stream_id=5, sign_bits_out=bits, tile_n=tile_n)
+        o2 = ops.gemm_tn(a, b, bias=bias, residual=res, dropout_p=0.1, seed=12, stream_id=6, tile_n=tile_n)
+        o3 = ops.gemm_tn(a, b, tile_n=tile_n)
+        o4 = ops.gemm_tn(a, b, bias=bias, out_fp32=True, tile_n=tile_n)
+        o5 = ops.gemm_tn(a, b, gate_bits=bits, gate_scale=1.0 / 0.9, tile_n=tile_n)
+        return o1, bits, o2, o3, o4, o5
+
+    try:
+        lib().wm_set_option(b"gemm_two_cta", 0)
+        lib().wm_set_option(b"gemm_epi_warps", 8)
+        ref = run()
+        for two, ew in ((0, 16), (1, 8), (1, 16)):
+            lib().wm_set_option(b"gemm_two_cta", two)
+            lib().wm_set_option(b"gemm_epi_warps", ew)
+            got = run()
+            for i, (r, g) in enumerate(zip(ref, got)):
+                assert torch.equal(r, g), f"two_cta={two} epi_warps={ew}: output {i} differs"
+    finally:
+        for k, v in GEMM_DEFAULTS.items():
+            lib().wm_set_option(k.encode(), v)
+    _cmp("gemm variants", ref[3], a.float() @ b.float().t(), 1e-2, 1e-2)
+    assert ops.device_error() == 0
+
+
+def test_gemm_site_tuner_records_a_variant_and_keeps_results():
+    """tune_gemm_sites times the four variants per call site and stores one; outputs before == after."""
+    from weathermodel_b200._lib import lib
+
+    M, D, FF = 8192, 192, 768
+    a = _bf(M, D, seed=50)
+    b = _bf(FF, D, scale=D ** -0.5, seed=51)
+    bias = torch.randn(FF, device="cuda")
+    before = ops.gemm_tn(a, b, bias=bias, relu=True)
+    chosen = ops.tune_gemm_sites(M, D, FF, 0.1, a.device)
+    assert set(chosen) == {"qkv", "out_proj", "linear1", "linear2", "linear2_dgrad", "linear1_dgrad", "out_proj_dgrad",
+                           "qkv_dgrad"}
+    assert all(v in ops.GEMM_VARIANTS for v in chosen.values())
+    assert ops.tune_gemm_sites(M, D, FF, 0.1, a.device) == {}  # once per shape and process
+    assert torch.equal(before, ops.gemm_tn(a, b, bias=bias, relu=True))
+    assert lib().wm_gemm_set_variant(M, FF, D, None, 0, 2, 8) != 0  # rejects unknown variants
+    assert ops.device_error() == 0
 
 
 def test_gemm_tn_epilogues():

@@ -1,4 +1,5 @@
-"""A/B: single-CTA gemm_tn vs CTA-pair gemm_tn2 on the large-config shapes."""
+"""A/B of the gemm_tn variants on the large-config shapes: single-CTA vs CTA-pair tiles (gemm_two_cta) x 8 vs 16
+epilogue warps (gemm_epi_warps). Every variant must be bit-identical."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,17 +14,21 @@ def t(fn, reps=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
-M = 186880
+M = int(os.environ.get("M", 186880))
 for N, K in [(1728, 576), (576, 576), (2304, 576), (576, 2304), (576, 1728)]:
     a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
     w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
     bias = torch.zeros(N, device="cuda")
-    ref = None
-    for mode in (0, 1):
-        lib().wm_set_option(b"gemm_two_cta", mode)
-        out = ops.gemm_tn(a, w, bias=bias)
-        if ref is None: ref = out
-        else: assert torch.equal(ref, out), "2-CTA result differs from 1-CTA"
-        ms = t(lambda: ops.gemm_tn(a, w, bias=bias))
-        print(f"N={N:5d} K={K:5d} two_cta={mode}: {ms:.4f} ms  {2.0*M*N*K/ms/1e9:7.1f} TFLOP/s", flush=True)
+    res = (torch.randn(M, N, device="cuda") * 0.5).to(torch.bfloat16)
+    for label, kw in (("bias", {}), ("bias+relu+drop", dict(relu=True, dropout_p=0.1, seed=3, stream_id=9)),
+                      ("bias+res", dict(residual=res))):
+        ref = None
+        for two, tma in ((0, 8), (0, 16), (1, 8), (1, 16)):
+            lib().wm_set_option(b"gemm_two_cta", two)
+            lib().wm_set_option(b"gemm_epi_warps", tma)
+            out = ops.gemm_tn(a, w, bias=bias, **kw)
+            if ref is None: ref = out
+            else: assert torch.equal(ref, out), f"variant two_cta={two} epi_warps={tma:2d} differs"
+            ms = t(lambda: ops.gemm_tn(a, w, bias=bias, **kw))
+            print(f"N={N:5d} K={K:5d} {label:15s} two_cta={two} epi_warps={tma:2d}: {ms:.4f} ms  {2.0*M*N*K/ms/1e9:7.1f} TFLOP/s", flush=True)
 print("device_error", ops.device_error())

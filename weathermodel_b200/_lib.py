@@ -40,6 +40,7 @@ SIGNATURES = {
     "wm_mask_former": (_i, [_u64, _u64, _i, _i, _i64, _i, _vp, _vp]),
     "wm_embed_fwd": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wm_gemm_tn": (_i, [_vp, _i, _vp, _i, _i, _i, _i, C.POINTER(GemmEpilogue), _vp, _i, _i, _i, _vp]),
+    "wm_gemm_set_variant": (_i, [_i, _i, _i, C.POINTER(GemmEpilogue), _i, _i, _i]),
     "wm_gemm_sign_bits_bytes": (_sz, [_i, _i]),
     "wm_gemm_wgrad_workspace_bytes": (_sz, [_i, _i, _i]),
     "wm_gemm_wgrad": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
@@ -87,6 +88,11 @@ def lib():
             fn.argtypes = args
         if handle.wm_abi_version() != 1:
             raise RuntimeError("libwm_b200.so ABI version mismatch")
+        # WM_OPTIONS="name=value,..." applies wm_set_option tuning switches at load time (A/B measurements)
+        for item in filter(None, os.environ.get("WM_OPTIONS", "").split(",")):
+            name, _, value = item.partition("=")
+            if handle.wm_set_option(name.strip().encode(), int(value or 1)) != 0:
+                raise RuntimeError(f"WM_OPTIONS: unknown option {name!r}")
         _lib = handle
     return _lib
 

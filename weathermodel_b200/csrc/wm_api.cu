@@ -46,15 +46,21 @@ int wm_debug_ticks(long long* out_host, int n) {
   return cudaMemcpyFromSymbol(out_host, g_wm_ticks, sizeof(long long) * n) == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
-namespace wm { extern int g_gemm_two_cta; }
+namespace wm { extern int g_gemm_two_cta, g_gemm_epi_warps; }
 int wm_set_option(const char* name, int value) {
   if (!name) return WM_ERR_ARG;
-  const char* a = name;
-  const char* b = "gemm_two_cta";
-  while (*a && *a == *b) { ++a; ++b; }
-  if (*a || *b) return WM_ERR_ARG;
-  wm::g_gemm_two_cta = value;
-  return WM_OK;
+  struct Opt { const char* name; int* slot; };
+  const Opt opts[] = {{"gemm_two_cta", &wm::g_gemm_two_cta}, {"gemm_epi_warps", &wm::g_gemm_epi_warps}};
+  for (const Opt& o : opts) {
+    const char* a = name;
+    const char* b = o.name;
+    while (*a && *a == *b) { ++a; ++b; }
+    if (!*a && !*b) {
+      *o.slot = value;
+      return WM_OK;
+    }
+  }
+  return WM_ERR_ARG;
 }
 
 int wm_rand_grid_x(int64_t numel) {
@@ -89,29 +95,39 @@ int wm_embed_fwd(const float* weather, const uint8_t* mask, int64_t mask_stride_
 }
 
 size_t wm_gemm_sign_bits_bytes(int M, int N) { return gemm_sign_bits_bytes(M, N); }
+static int fill_epilogue(GemmEpilogue& ep, const wm_gemm_epilogue* e) {
+  if (!e) return WM_OK;
+  ep.bias = e->bias;
+  ep.relu = e->relu;
+  ep.drop_thresh = thresh16(e->dropout_p);
+  ep.drop_scale = keep_scale(ep.drop_thresh);
+  ep.seed = e->seed;
+  ep.stream = e->stream_id;
+  ep.gate = CB(e->gate_bf16);
+  ep.ld_gate = e->ld_gate;
+  ep.gate_scale = e->gate_scale;
+  ep.residual = CB(e->residual_bf16);
+  ep.ld_res = e->ld_res;
+  ep.sign_bits_out = static_cast<uint16_t*>(e->sign_bits_out);
+  ep.gate_bits = static_cast<const uint16_t*>(e->gate_bits);
+  if ((ep.gate && (ep.ld_gate & 7)) || (ep.residual && (ep.ld_res & 7))) return WM_ERR_ALIGN;
+  return WM_OK;
+}
 int wm_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const wm_gemm_epilogue* e,
                void* out, int ld_out, int out_is_fp32, int tile_n, void* stream) {
   if (!A || !B || !out) return WM_ERR_ARG;
   GemmEpilogue ep;
-  if (e) {
-    ep.bias = e->bias;
-    ep.relu = e->relu;
-    ep.drop_thresh = thresh16(e->dropout_p);
-    ep.drop_scale = keep_scale(ep.drop_thresh);
-    ep.seed = e->seed;
-    ep.stream = e->stream_id;
-    ep.gate = CB(e->gate_bf16);
-    ep.ld_gate = e->ld_gate;
-    ep.gate_scale = e->gate_scale;
-    ep.residual = CB(e->residual_bf16);
-    ep.ld_res = e->ld_res;
-    ep.sign_bits_out = static_cast<uint16_t*>(e->sign_bits_out);
-    ep.gate_bits = static_cast<const uint16_t*>(e->gate_bits);
-    if ((ep.gate && (ep.ld_gate & 7)) || (ep.residual && (ep.ld_res & 7))) return WM_ERR_ALIGN;
-  }
+  const int rc = fill_epilogue(ep, e);
+  if (rc) return rc;
   ep.out = out;
   ep.ld_out = ld_out;
   return launch_gemm_tn(A, lda, B, ldb, M, N, K, ep, out_is_fp32, tile_n, S_(stream));
+}
+int wm_gemm_set_variant(int M, int N, int K, const wm_gemm_epilogue* e, int out_is_fp32, int two_cta, int epi_warps) {
+  GemmEpilogue ep;
+  const int rc = fill_epilogue(ep, e);
+  if (rc) return rc;
+  return gemm_set_variant(M, N, K, gemm_signature(ep, out_is_fp32), two_cta, epi_warps);
 }
 size_t wm_gemm_wgrad_workspace_bytes(int Mtok, int Nout, int Kout) { return wgrad_workspace_bytes(Mtok, Nout, Kout); }
 int wm_gemm_wgrad(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout, float* dW,

@@ -309,6 +309,46 @@ WM_DEVICE void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* m, uint64_t* 
       : "memory");
 }
 
+// warp-convergent cta_group::2 issue (see umma_ss_warp): every lane of the leader CTA's issue warp calls these
+WM_DEVICE void umma_ss_2cta_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b32 r;\n\t"
+      "elect.sync r|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+WM_DEVICE void umma_commit_2cta_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      ".reg .b32 r;\n\t"
+      "elect.sync r|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+// TMA store: one box of a 2D tiled tensor map from shared memory to global memory (bulk async-group of the
+// issuing thread). Elements outside the tensor's bounds are not written.
+WM_DEVICE void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+WM_DEVICE void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+// wait until at most kPending of this thread's bulk groups still have to READ their shared-memory source
+template <int kPending>
+WM_DEVICE void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(kPending) : "memory");
+}
+
 // TMEM -> registers: lane t of the warp receives 32 / 16 consecutive fp32 columns of TMEM lane
 // (lane_base + t); lane_base must be 32*(warp_id % 4).
 WM_DEVICE void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {

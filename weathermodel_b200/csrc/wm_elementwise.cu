@@ -308,154 +308,204 @@ int launch_layernorm_fwd(const __nv_bfloat16* x, const float* gamma, const float
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
-// LayerNorm backward. Each warp walks rows (grid-stride) keeping per-column partial sums of
-// dgamma, dbeta and the bias gradient of the producing linear in registers; CTA partials go to a
-// workspace and a second kernel folds them in a fixed order (deterministic).
-constexpr int kLnBwdCtas = 148 * 4;
+// LayerNorm backward. Persistent: one CTA per SM, 8 consumer warps + 1 producer warp. The producer streams blocks of
+// 8 consecutive rows of x and dy (one contiguous span each: the activations are token-major) into a shared-memory
+// ring with 1-D bulk copies (cp.async.bulk, mbarrier completion); consumer warp w owns row w of every block and
+// keeps per-column partial sums of dgamma, dbeta and the bias gradient of the producing linear in registers. CTA
+// partials go to a workspace and a second kernel folds them in a fixed order (deterministic).
+// Why the ring: the column partials cost ~150 registers per thread, so only 8 consumer warps fit on an SM, and with
+// register prefetch (the previous version: two rows ahead = 37 KB in flight per SM) Little's law capped the kernel
+// at ~3.1 TB/s. The ring keeps up to 8 blocks x 2 tensors x 8 rows (147 KB at D = 576) in flight per SM.
+constexpr int kLnBwdCtas = 148 * 4;  // workspace bound (the kernel launches min(row blocks, SMs) CTAs)
+constexpr int kLnBwdMaxStages = 8;
+constexpr int kLnBwdThreads = 288;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kLnBwdThreads, 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean,
                      const float* __restrict__ rstd, __nv_bfloat16* __restrict__ dx,
                      __nv_bfloat16* __restrict__ dx_drop, int M, int D, uint32_t drop_thresh, float drop_scale,
-                     DropKeys dkeys, float* __restrict__ partial) {
-  extern __shared__ float sred[];  // [8 warps][3][D]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                     DropKeys dkeys, float* __restrict__ partial, int stages) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const uint32_t row_bytes = static_cast<uint32_t>(D) * 2u;
+  const uint32_t tens_bytes = 8u * row_bytes;
+  const uint32_t stage_bytes = 2u * tens_bytes;  // [x rows | dy rows]
+  uint8_t* ring = ln_smem;
+  float* sred = reinterpret_cast<float*>(ring + static_cast<size_t>(stages) * stage_bytes);  // [8 warps][3][D]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sred + 8 * 3 * D);
+  uint64_t* empty = full + stages;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int nchunks = D >> 3;
-  float g[kLnMaxChunks][8];
-  float ag[kLnMaxChunks][8], ab[kLnMaxChunks][8], ad[kLnMaxChunks][8];
-#pragma unroll
-  for (int i = 0; i < kLnMaxChunks; ++i) {
-    const int c = lane + 32 * i;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      g[i][j] = c < nchunks ? gamma[c * 8 + j] : 0.0f;
-      ag[i][j] = 0.0f; ab[i][j] = 0.0f; ad[i][j] = 0.0f;
+  const int nblk = (M + 7) >> 3;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 8);  // one arrive per consumer warp
     }
+    fence_barrier_init();
   }
-  const float invD = 1.0f / static_cast<float>(D);
-  // The operands of the next TWO rows are requested before the current row is reduced: the kernel holds ~200
-  // registers per thread (column partials), so only 8 warps live on an SM and the bytes in flight -- 8 warps x rows
-  // x 2 tensors x 1152 B -- decide the bandwidth (one row ahead: 37 KB per SM = ~3 TB/s by Little's law).
-  uint4 x0[kLnMaxChunks], d0[kLnMaxChunks], x1[kLnMaxChunks], d1[kLnMaxChunks];
-  float mu0 = 0.0f, rs0 = 0.0f, mu1 = 0.0f, rs1 = 0.0f;
-  const int row0 = blockIdx.x * 8 + warp;
-  const int stride = gridDim.x * 8;
-  if (row0 < M) {
-    ln_load_raw(x + static_cast<size_t>(row0) * D, nchunks, lane, x0);
-    ln_load_raw(dy + static_cast<size_t>(row0) * D, nchunks, lane, d0);
-    mu0 = mean[row0];
-    rs0 = rstd[row0];
-  }
-  if (row0 + stride < M) {
-    ln_load_raw(x + static_cast<size_t>(row0 + stride) * D, nchunks, lane, x1);
-    ln_load_raw(dy + static_cast<size_t>(row0 + stride) * D, nchunks, lane, d1);
-    mu1 = mean[row0 + stride];
-    rs1 = rstd[row0 + stride];
-  }
-  auto body = [&](int row, uint4(&nx)[kLnMaxChunks], uint4(&nd)[kLnMaxChunks], float& nmu, float& nrs) {
-    float xv[kLnMaxChunks][8], dv[kLnMaxChunks][8];
-    ln_unpack(nx, xv);
-    ln_unpack(nd, dv);
-    const float mu = nmu, rs = nrs;
-    const int rown = row + 2 * stride;
-    if (rown < M) {
-      ln_load_raw(x + static_cast<size_t>(rown) * D, nchunks, lane, nx);
-      ln_load_raw(dy + static_cast<size_t>(rown) * D, nchunks, lane, nd);
-      nmu = mean[rown];
-      nrs = rstd[rown];
+  __syncthreads();
+
+  if (warp == 8) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int b = blockIdx.x; b < nblk; b += gridDim.x) {
+        mbar_wait(&empty[s], ph ^ 1u, 41);
+        const int r0 = b * 8;
+        const uint32_t bytes = static_cast<uint32_t>(min(8, M - r0)) * row_bytes;
+        uint8_t* dst = ring + static_cast<size_t>(s) * stage_bytes;
+        mbar_arrive_expect_tx(&full[s], 2u * bytes);
+        bulk_load_1d(dst, x + static_cast<size_t>(r0) * D, bytes, &full[s]);
+        bulk_load_1d(dst + tens_bytes, dy + static_cast<size_t>(r0) * D, bytes, &full[s]);
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
     }
-    float s1 = 0.0f, s2 = 0.0f;
+  } else {
+    float g[kLnMaxChunks][8];
+    float ag[kLnMaxChunks][8], ab[kLnMaxChunks][8], ad[kLnMaxChunks][8];
 #pragma unroll
     for (int i = 0; i < kLnMaxChunks; ++i) {
-      if (lane + 32 * i < nchunks) {
+      const int c = lane + 32 * i;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (xv[i][j] - mu) * rs;
-          const float gd = dv[i][j] * g[i][j];
-          s1 += gd;
-          s2 = fmaf(gd, xh, s2);
-          ag[i][j] = fmaf(dv[i][j], xh, ag[i][j]);
-          ab[i][j] += dv[i][j];
-          xv[i][j] = xh;
+      for (int j = 0; j < 8; ++j) {
+        g[i][j] = c < nchunks ? gamma[c * 8 + j] : 0.0f;
+        ag[i][j] = 0.0f; ab[i][j] = 0.0f; ad[i][j] = 0.0f;
+      }
+    }
+    const float invD = 1.0f / static_cast<float>(D);
+    int s = 0;
+    uint32_t ph = 0;
+    float mu_n = 0.0f, rs_n = 0.0f;  // row statistics one block ahead
+    {
+      const int r = blockIdx.x * 8 + warp;
+      if (blockIdx.x < nblk && r < M) { mu_n = __ldg(mean + r); rs_n = __ldg(rstd + r); }
+    }
+    for (int b = blockIdx.x; b < nblk; b += gridDim.x) {
+      const int row = b * 8 + warp;
+      const float mu = mu_n, rs = rs_n;
+      {
+        const int rn = (b + static_cast<int>(gridDim.x)) * 8 + warp;
+        if (rn < M) { mu_n = __ldg(mean + rn); rs_n = __ldg(rstd + rn); }
+      }
+      mbar_wait(&full[s], ph, 42);
+      float xv[kLnMaxChunks][8], dv[kLnMaxChunks][8];
+      {
+        const uint4* sx = reinterpret_cast<const uint4*>(ring + static_cast<size_t>(s) * stage_bytes + warp * row_bytes);
+        const uint4* sd = reinterpret_cast<const uint4*>(ring + static_cast<size_t>(s) * stage_bytes + tens_bytes + warp * row_bytes);
+        uint4 xr[kLnMaxChunks], dr[kLnMaxChunks];
+#pragma unroll
+        for (int i = 0; i < kLnMaxChunks; ++i) {
+          const int c = lane + 32 * i;
+          const bool ok = c < nchunks && row < M;
+          xr[i] = ok ? sx[c] : make_uint4(0u, 0u, 0u, 0u);
+          dr[i] = ok ? sd[c] : make_uint4(0u, 0u, 0u, 0u);
+        }
+        ln_unpack(xr, xv);
+        ln_unpack(dr, dv);
+      }
+      __syncwarp();  // every lane has its copy: hand the slot back to the producer
+      if (lane == 0) mbar_arrive(&empty[s]);
+      if (++s == stages) { s = 0; ph ^= 1u; }
+      if (row >= M) continue;  // warp-uniform (tail block)
+      float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+      for (int i = 0; i < kLnMaxChunks; ++i) {
+        if (lane + 32 * i < nchunks) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = (xv[i][j] - mu) * rs;
+            const float gd = dv[i][j] * g[i][j];
+            s1 += gd;
+            s2 = fmaf(gd, xh, s2);
+            ag[i][j] = fmaf(dv[i][j], xh, ag[i][j]);
+            ab[i][j] += dv[i][j];
+            xv[i][j] = xh;
+          }
+        }
+      }
+      s1 = warp_sum(s1) * invD;
+      s2 = warp_sum(s2) * invD;
+#pragma unroll
+      for (int i = 0; i < kLnMaxChunks; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunks) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = rs * (dv[i][j] * g[i][j] - s1 - xv[i][j] * s2);
+          uint4 pk;
+          pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
+          pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+          reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * D)[c] = pk;
+          if (drop_thresh) {  // the mask the GEMM epilogue drew for these 8 columns: two words of the 16-column group
+            const uint32_t add4 = (128u - drop_thresh7(drop_thresh)) * 0x01010101u;
+            const uint32_t x0 = (static_cast<uint32_t>(row) * static_cast<uint32_t>((D + 15) >> 4) + static_cast<uint32_t>(c >> 1)) * 4u + 2u * (c & 1);
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+              const uint32_t fl = drop_flags4(x0 + w, dkeys, add4);
+              o[4 * w] = __uint_as_float(__float_as_uint(o[4 * w] * drop_scale) & drop_mask32<0>(fl));
+              o[4 * w + 1] = __uint_as_float(__float_as_uint(o[4 * w + 1] * drop_scale) & drop_mask32<1>(fl));
+              o[4 * w + 2] = __uint_as_float(__float_as_uint(o[4 * w + 2] * drop_scale) & drop_mask32<2>(fl));
+              o[4 * w + 3] = __uint_as_float(__float_as_uint(o[4 * w + 3] * drop_scale) & drop_mask32<3>(fl));
+            }
+            pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
+            pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+            reinterpret_cast<uint4*>(dx_drop + static_cast<size_t>(row) * D)[c] = pk;
+          }
+          // bias gradient of the producing linear sums what that linear's output actually received;
+          // use the bf16-rounded values so it matches the wgrad operand exactly
+          const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ad[i][2 * j] += bf16_lo(pw[j]);
+            ad[i][2 * j + 1] += bf16_hi(pw[j]);
+          }
         }
       }
     }
-    s1 = warp_sum(s1) * invD;
-    s2 = warp_sum(s2) * invD;
+    // CTA reduce: warp w writes its registers, then the CTA folds 8 warps per column
 #pragma unroll
     for (int i = 0; i < kLnMaxChunks; ++i) {
       const int c = lane + 32 * i;
       if (c < nchunks) {
-        float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rs * (dv[i][j] * g[i][j] - s1 - xv[i][j] * s2);
-        uint4 pk;
-        pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
-        pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
-        reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * D)[c] = pk;
-        if (drop_thresh) {  // the mask the GEMM epilogue drew for these 8 columns: two words of the 16-column group
-          const uint32_t add4 = (128u - drop_thresh7(drop_thresh)) * 0x01010101u;
-          const uint32_t x0 = (static_cast<uint32_t>(row) * static_cast<uint32_t>((D + 15) >> 4) + static_cast<uint32_t>(c >> 1)) * 4u + 2u * (c & 1);
-#pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            const uint32_t fl = drop_flags4(x0 + w, dkeys, add4);
-            o[4 * w] = __uint_as_float(__float_as_uint(o[4 * w] * drop_scale) & drop_mask32<0>(fl));
-            o[4 * w + 1] = __uint_as_float(__float_as_uint(o[4 * w + 1] * drop_scale) & drop_mask32<1>(fl));
-            o[4 * w + 2] = __uint_as_float(__float_as_uint(o[4 * w + 2] * drop_scale) & drop_mask32<2>(fl));
-            o[4 * w + 3] = __uint_as_float(__float_as_uint(o[4 * w + 3] * drop_scale) & drop_mask32<3>(fl));
-          }
-          pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
-          pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
-          reinterpret_cast<uint4*>(dx_drop + static_cast<size_t>(row) * D)[c] = pk;
+        for (int j = 0; j < 8; ++j) {
+          sred[(warp * 3 + 0) * D + c * 8 + j] = ag[i][j];
+          sred[(warp * 3 + 1) * D + c * 8 + j] = ab[i][j];
+          sred[(warp * 3 + 2) * D + c * 8 + j] = ad[i][j];
         }
-        // bias gradient of the producing linear sums what that linear's output actually received;
-        // use the bf16-rounded values so it matches the wgrad operand exactly
-        const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          ad[i][2 * j] += bf16_lo(pw[j]);
-          ad[i][2 * j + 1] += bf16_hi(pw[j]);
-        }
-      }
-    }
-  };
-  for (int row = row0; row < M; row += 2 * stride) {
-    body(row, x0, d0, mu0, rs0);
-    if (row + stride < M) body(row + stride, x1, d1, mu1, rs1);
-  }
-  // CTA reduce: warp w writes its registers, then 256 threads fold 8 warps per column
-#pragma unroll
-  for (int i = 0; i < kLnMaxChunks; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nchunks) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sred[(warp * 3 + 0) * D + c * 8 + j] = ag[i][j];
-        sred[(warp * 3 + 1) * D + c * 8 + j] = ab[i][j];
-        sred[(warp * 3 + 2) * D + c * 8 + j] = ad[i][j];
       }
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
-    float s = 0.0f;
+    float sum = 0.0f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += sred[w * 3 * D + i];
-    partial[static_cast<size_t>(blockIdx.x) * 3 * D + i] = s;
+    for (int w = 0; w < 8; ++w) sum += sred[w * 3 * D + i];
+    partial[static_cast<size_t>(blockIdx.x) * 3 * D + i] = sum;
   }
 }
 
-// out_k[c] (+)= sum_{cta} partial[cta][k][c]
-__global__ void ln_bwd_finalize_kernel(const float* __restrict__ partial, int ncta, int D, float* dgamma,
-                                       float* dbeta, float* dbias) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 3 * D) return;
+// out_k[c] (+)= sum_{cta} partial[cta][k][c]: 64 columns per CTA, four threads per column each folding a quarter of
+// the CTAs in order, then a fixed-order fold of the four
+__global__ void __launch_bounds__(256)
+ln_bwd_finalize_kernel(const float* __restrict__ partial, int ncta, int D, float* dgamma, float* dbeta, float* dbias) {
+  __shared__ float part[4][64];
+  const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int q = threadIdx.x >> 6;
+  const int per = (ncta + 3) >> 2;
   float s = 0.0f;
-  for (int c = 0; c < ncta; ++c) s += partial[static_cast<size_t>(c) * 3 * D + i];
-  const int k = i / D, col = i - k * D;
-  float* dst = k == 0 ? dgamma : k == 1 ? dbeta : dbias;
-  if (dst) dst[col] = s;
+  if (i < 3 * D)
+    for (int c = q * per; c < min(ncta, (q + 1) * per); ++c) s += partial[static_cast<size_t>(c) * 3 * D + i];
+  part[q][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (q == 0 && i < 3 * D) {
+    const int t = threadIdx.x;
+    const float sum = ((part[0][t] + part[1][t]) + part[2][t]) + part[3][t];
+    const int k = i / D, col = i - k * D;
+    float* dst = k == 0 ? dgamma : k == 1 ? dbeta : dbias;
+    if (dst) dst[col] = sum;
+  }
 }
 
 size_t layernorm_bwd_workspace_bytes(int M, int D) {
@@ -469,18 +519,33 @@ int launch_layernorm_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const 
                          uint64_t seed, uint64_t stream_id, float* workspace, cudaStream_t stream) {
   if (M <= 0 || D <= 0 || (D & 7) || D > kLnMaxChunks * 256) return WM_ERR_SHAPE;
   if (drop_thresh && !dx_drop) return WM_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
+       reinterpret_cast<uintptr_t>(dx_drop)) & 15u)
+    return WM_ERR_ALIGN;  // bulk copies and 16-byte stores
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
   int ctas = (M + 7) / 8;
+  if (ctas > sms) ctas = sms;
   if (ctas > kLnBwdCtas) ctas = kLnBwdCtas;
-  const int smem = 8 * 3 * D * 4;
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+  const int stage_bytes = 2 * 8 * D * 2;
+  const int fixed = 8 * 3 * D * 4 + 2 * kLnBwdMaxStages * 8 + 128;
+  int stages = (227 * 1024 - fixed) / stage_bytes;
+  if (stages > kLnBwdMaxStages) stages = kLnBwdMaxStages;
+  if (stages < 2) return WM_ERR_SHAPE;
+  const int smem = stages * stage_bytes + fixed;
+  if (cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return WM_ERR_CUDA;
   if (drop_thresh && static_cast<uint64_t>(M) * static_cast<uint64_t>((D + 15) / 16) * 4ull > 0xFFFFFFFFull) return WM_ERR_SHAPE;
-  layernorm_bwd_kernel<<<ctas, 256, smem, stream>>>(dy, x, gamma, mean, rstd, dx, dx_drop, M, D, drop_thresh,
-                                                    drop_scale, drop_keys(seed, stream_id), workspace);
+  layernorm_bwd_kernel<<<ctas, kLnBwdThreads, smem, stream>>>(dy, x, gamma, mean, rstd, dx, dx_drop, M, D, drop_thresh,
+                                                              drop_scale, drop_keys(seed, stream_id), workspace, stages);
   WM_COUNT_LAUNCH();
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
-  ln_bwd_finalize_kernel<<<(3 * D + 255) / 256, 256, 0, stream>>>(workspace, ctas, D, dgamma, dbeta, dbias);
+  ln_bwd_finalize_kernel<<<(3 * D + 63) / 64, 256, 0, stream>>>(workspace, ctas, D, dgamma, dbeta, dbias);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }

@@ -38,8 +38,8 @@ static PFN_encodeTiled get_encode() {
 
 // 2D bf16 row-major tensor [rows, cols] with row pitch ld (elements); box = {box_cols, box_rows};
 // 128B swizzle (box_cols must be 64 bf16 = 128 B). Out-of-bounds elements read as zero.
-int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                   uint32_t box_cols, uint32_t box_rows) {
+static int make_tmap_bf16_swz(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                              uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swizzle) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return WM_ERR_DRIVER;
   if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((ld * 2) & 15u)) return WM_ERR_ALIGN;
@@ -48,9 +48,13 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t c
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? WM_OK : WM_ERR_DRIVER;
+}
+int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                   uint32_t box_cols, uint32_t box_rows) {
+  return make_tmap_bf16_swz(map, base, rows, cols, ld, box_cols, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // 3D view {cols, S rows, B batches} of a token-major bf16 activation [B*S, ld] for the attention kernels:
@@ -96,7 +100,12 @@ int make_tmap_bf16_chunked4d(CUtensorMap* map, const void* base, uint64_t cols, 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxStages = 8;
-constexpr int kGemmThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter)
+// warp0 TMA, warp1 MMA, then kEW epilogue warps: kEW / 4 per TMEM lane quarter, each owning BN / (kEW / 4) columns.
+// The epilogue is latency-bound per warp (ncu source view: ~1,070 cycles per 16-column chunk at ~130 issued
+// instructions -- fixed-latency waits, TMEM-load and smem scoreboards, instruction fetch), and with K = 576 it, not
+// the MMAs (4,608 cycles per 128 x 256 tile), set the pace (8,590 cycles per tile). 16 warps (4 per scheduler) halve
+// the per-tile epilogue time; 8 remain for tiles whose width is not a multiple of 64.
+constexpr int gemm_threads(int ew) { return 64 + 32 * ew; }
 constexpr int kWgradThreads = 192;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccStride = 256;
@@ -107,7 +116,7 @@ struct GemmSmemTail {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
-  alignas(16) float bias[8][128];  // per epilogue warp: the bias slice of its column half of the current tile
+  alignas(16) float bias[1024];    // per epilogue warp (kEW x 1024 / kEW floats): the bias slice of its columns of the current tile
 };
 
 // Epilogue of one 16-column group pair for one accumulator row. Auxiliary operands (residual / gate rows)
@@ -146,8 +155,9 @@ WM_DEVICE void epi_load_aux(EpiAux& x, const GemmEpilogue& ep, int row, int n0, 
 template <typename OutT>
 WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const float* sbias, const GemmEpilogue& ep,
                              int row, int n0, int M, int N, bool wide) {
-  if (n0 >= N) return;
-  if (row >= M && (!ep.sign_bits_out || row >= ((M + 31) & ~31))) return;
+  if (n0 >= N) return;  // warp-uniform
+  const int m32 = (M + 31) & ~31;
+  if (row >= M && (!ep.sign_bits_out || row >= m32)) return;
   float f[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
@@ -194,8 +204,8 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
     uint4 r0 = aux.a[0], r1 = aux.a[1];
     if (ep.gate) {  // both operands given (not on the training schedule): the residual is loaded in place
       const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(row) * ep.ld_res + n0);
-      r0 = __ldg(rp);
-      r1 = n0 + 8 < N ? __ldg(rp + 1) : make_uint4(0u, 0u, 0u, 0u);
+      r0 = row < M ? __ldg(rp) : make_uint4(0u, 0u, 0u, 0u);
+      r1 = (row < M && n0 + 8 < N) ? __ldg(rp + 1) : make_uint4(0u, 0u, 0u, 0u);
     }
     const uint32_t aw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
@@ -229,7 +239,7 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
       for (int i = 0; i < 8; ++i) acc += __vminu2(w8[i], 0x00010001u) << i;  // even elements at bit i, odd at 16 + i
       uint32_t m = (acc & 0xFFu) | ((acc >> 8) & 0xFF00u);
       if (!second) m &= 0x0F0Fu;
-      ep.sign_bits_out[sign_bits_index(row, n0, N)] = static_cast<uint16_t>(row < M ? m : 0u);
+      if (row < m32) ep.sign_bits_out[sign_bits_index(row, n0, N)] = static_cast<uint16_t>(row < M ? m : 0u);
       if (row >= M) return;
     }
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(row) * ep.ld_out + n0;
@@ -248,8 +258,50 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
   }
 }
 
-template <typename OutT>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// One epilogue warp's share of one accumulator tile: its 32 TMEM lanes (rows) x cols_per columns from n_base on.
+// Everything that does not depend on the accumulator (bias slice, first residual / gate chunks) is issued before
+// waiting for the MMAs; TMEM loads run one 16-column chunk ahead of the arithmetic.
+template <typename OutT, int kAuxDepth>
+WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t* acc_full, uint32_t aph,
+                                  uint32_t wait_code, uint32_t tbase, int row, int n_base, int cols_per, int M, int N,
+                                  bool wide, int lane) {
+  if (ep.bias) {
+    __syncwarp();
+    for (int j = lane; j < cols_per; j += 32) sbias[j] = (n_base + j < N) ? __ldg(ep.bias + n_base + j) : 0.0f;
+    __syncwarp();
+  }
+  // ring of kAuxDepth prefetched 16-column chunks per thread (4 with 8 epilogue warps, 2 with 16): ~32 KB of
+  // residual / gate rows in flight per SM
+  static_assert(kAuxDepth == 2 || kAuxDepth == 4, "the TMEM double buffer alternates on the chunk parity");
+  EpiAux aux[kAuxDepth];
+#pragma unroll
+  for (int d = 0; d < kAuxDepth; ++d)
+    if (d * 16 < cols_per) epi_load_aux(aux[d], ep, row, n_base + d * 16, M, N, wide);
+  mbar_wait(acc_full, aph, wait_code);
+  tc_fence_after();
+  uint32_t va[16], vb[16];
+  tmem_ld16(tbase, va);
+  for (int cb = 0; cb < cols_per; cb += 16 * kAuxDepth) {
+#pragma unroll
+    for (int d = 0; d < kAuxDepth; ++d) {
+      const int c0 = cb + d * 16;
+      if (c0 < cols_per) {
+        tmem_ld_wait();
+        if (d & 1) {
+          if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, va);
+          epi_process16<OutT>(vb, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide);
+        } else {
+          if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, vb);
+          epi_process16<OutT>(va, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide);
+        }
+        if (c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
+      }
+    }
+  }
+}
+
+template <typename OutT, int kEW>
+__global__ void __launch_bounds__(gemm_threads(kEW), 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, int BN, int stages, GemmEpilogue ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -276,7 +328,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tail->acc_full[s], 1);
-      mbar_init(&tail->acc_empty[s], 8);  // one arrive per epilogue warp
+      mbar_init(&tail->acc_empty[s], kEW);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -334,10 +386,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     const int q = warp & 3;          // TMEM lane quarter this warp may read
-    const int ew = warp - 2;         // 0..7
-    const int half = ew >> 2;        // which half of the tile's columns this warp owns
-    const int cols_per = BN >> 1;    // BN % 32 == 0 (host-checked)
-    float* sbias = tail->bias[ew];
+    const int ew = warp - 2;              // 0..kEW-1
+    const int half = ew >> 2;             // which slice of the tile's columns this warp owns
+    const int cols_per = BN / (kEW / 4);  // a multiple of 16 (host-checked)
+    float* sbias = tail->bias + ew * (1024 / kEW);
     // 32-byte accesses need 32-byte aligned rows: every leading dimension a multiple of 16 bf16 elements
     const bool wide = ((ep.ld_out | (ep.residual ? ep.ld_res : 0) | (ep.gate ? ep.ld_gate : 0)) & 15) == 0 &&
                       ((reinterpret_cast<uintptr_t>(ep.out) | reinterpret_cast<uintptr_t>(ep.residual) |
@@ -347,36 +399,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_blk = t / n_tiles, n_blk = t % n_tiles;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1u;
-      const int row = m_blk * kBM + q * 32 + lane;
-      const int n_base = n_blk * BN + half * cols_per;
-      // everything that does not depend on the accumulator is issued before waiting for the MMAs
-      if (ep.bias) {
-        __syncwarp();
-        for (int j = lane; j < cols_per; j += 32) sbias[j] = (n_base + j < N) ? __ldg(ep.bias + n_base + j) : 0.0f;
-        __syncwarp();
-      }
-      // ring of kAuxDepth prefetched 16-column chunks per thread: ~32 KB of residual / gate rows in flight per SM
-      constexpr int kAuxDepth = 4;
-      EpiAux aux[kAuxDepth];
-#pragma unroll
-      for (int d = 0; d < kAuxDepth; ++d)
-        if (d * 16 < cols_per) epi_load_aux(aux[d], ep, row, n_base + d * 16, M, N, wide);
-      mbar_wait(&tail->acc_full[as], aph, 14);
-      tc_fence_after();
       const uint32_t tbase = tmem_base + as * kAccStride + half * cols_per + (static_cast<uint32_t>(q * 32) << 16);
-      for (int cb = 0; cb < cols_per; cb += 16 * kAuxDepth) {
-#pragma unroll
-        for (int d = 0; d < kAuxDepth; ++d) {
-          const int c0 = cb + d * 16;
-          if (c0 < cols_per) {
-            uint32_t v[16];
-            tmem_ld16(tbase + c0, v);
-            tmem_ld_wait();
-            epi_process16<OutT>(v, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide);
-            if (c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
-          }
-        }
-      }
+      gemm_epilogue_tile<OutT, (kEW == 16 ? 2 : 4)>(ep, sbias, &tail->acc_full[as], aph, 14, tbase, m_blk * kBM + q * 32 + lane,
+                               n_blk * BN + half * cols_per, cols_per, M, N, wide, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->acc_empty[as]);
@@ -396,8 +421,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // (the single-CTA kernel is L2-feed bound at ~1.0-1.1 PFLOP/s). The leader CTA issues M = 256 MMAs and commits to
 // the barriers of both CTAs; each CTA's 8 epilogue warps drain their own 128 TMEM lanes.
 // ------------------------------------------------------------------------------------------------
-template <typename OutT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+template <typename OutT, int kEW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(kEW), 1)
 gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 int M, int N, int K, int BN, int stages, GemmEpilogue ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -408,7 +433,7 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t stage_bytes = a_bytes + b_bytes;
   GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(smem + static_cast<size_t>(stages) * stage_bytes);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -427,7 +452,7 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tail->acc_full[s], 1);
-      mbar_init(&tail->acc_empty[s], 16);  // 8 epilogue warps in each of the two CTAs (leader's copy is used)
+      mbar_init(&tail->acc_empty[s], 2 * kEW);  // the epilogue warps of both CTAs (the leader's copy is used)
     }
     fence_barrier_init();
   }
@@ -454,7 +479,7 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {  // whole warp, convergent issue (see gemm_tn_kernel)
       const uint32_t idesc = umma_idesc_bf16(2 * kBM, static_cast<uint32_t>(BN), 0, 0);
       const uint64_t desc_a0 = umma_smem_desc(smem_u32(smem), 16, 1024, UMMA_SWZ_128B);
       int s = 0;
@@ -473,20 +498,20 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint64_t db_s = umma_desc_advance(da_s, a_bytes);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
-            umma_ss_2cta(d_tmem, umma_desc_advance(da_s, k * 32), umma_desc_advance(db_s, k * 32), idesc,
-                         (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2cta(&tail->empty[s]);
+            umma_ss_2cta_warp(d_tmem, umma_desc_advance(da_s, k * 32), umma_desc_advance(db_s, k * 32), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2cta_warp(&tail->empty[s]);
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit_2cta(&tail->acc_full[as]);
+        umma_commit_2cta_warp(&tail->acc_full[as]);
       }
     }
   } else {
     const int q = warp & 3;
     const int ew = warp - 2;
     const int half = ew >> 2;
-    const int cols_per = BN >> 1;
-    float* sbias = tail->bias[ew];
+    const int cols_per = BN / (kEW / 4);
+    float* sbias = tail->bias + ew * (1024 / kEW);
     const bool wide = ((ep.ld_out | (ep.residual ? ep.ld_res : 0) | (ep.gate ? ep.ld_gate : 0)) & 15) == 0 &&
                       ((reinterpret_cast<uintptr_t>(ep.out) | reinterpret_cast<uintptr_t>(ep.residual) |
                         reinterpret_cast<uintptr_t>(ep.gate)) & 31) == 0;
@@ -496,34 +521,10 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m_blk = t / n_tiles, n_blk = t % n_tiles;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1u;
-      const int row = m_blk * 2 * kBM + static_cast<int>(rank) * kBM + q * 32 + lane;
-      const int n_base = n_blk * BN + half * cols_per;
-      if (ep.bias) {
-        __syncwarp();
-        for (int j = lane; j < cols_per; j += 32) sbias[j] = (n_base + j < N) ? __ldg(ep.bias + n_base + j) : 0.0f;
-        __syncwarp();
-      }
-      constexpr int kAuxDepth = 4;
-      EpiAux aux[kAuxDepth];
-#pragma unroll
-      for (int d = 0; d < kAuxDepth; ++d)
-        if (d * 16 < cols_per) epi_load_aux(aux[d], ep, row, n_base + d * 16, M, N, wide);
-      mbar_wait(&tail->acc_full[as], aph, 64);
-      tc_fence_after();
       const uint32_t tbase = tmem_base + as * kAccStride + half * cols_per + (static_cast<uint32_t>(q * 32) << 16);
-      for (int cb = 0; cb < cols_per; cb += 16 * kAuxDepth) {
-#pragma unroll
-        for (int d = 0; d < kAuxDepth; ++d) {
-          const int c0 = cb + d * 16;
-          if (c0 < cols_per) {
-            uint32_t v[16];
-            tmem_ld16(tbase + c0, v);
-            tmem_ld_wait();
-            epi_process16<OutT>(v, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide);
-            if (c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
-          }
-        }
-      }
+      gemm_epilogue_tile<OutT, (kEW == 16 ? 2 : 4)>(ep, sbias, &tail->acc_full[as], aph, 64, tbase,
+                               m_blk * 2 * kBM + static_cast<int>(rank) * kBM + q * 32 + lane,
+                               n_blk * BN + half * cols_per, cols_per, M, N, wide, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc_empty_leader[as]);
@@ -556,8 +557,51 @@ static int pick_bn(int N) {
   return best;
 }
 
-int g_gemm_two_cta = 0;  // wm_set_option("gemm_two_cta", 1) selects the CTA-pair kernel: bit-identical, measured 0-9 % slower on
-                          // this model's shapes (tools/gemm_ab.py), so the single-CTA kernel stays the default
+// Kernel variant per call site. All variants are bit-identical (tests/test_gpu_kernels.py), so the choice is purely a
+// matter of speed: CTA-pair tiles halve the shared-memory operand traffic per SM and win when the main loop dominates
+// (K >= 1024: +6-19 %), 16 epilogue warps win when the epilogue does (K = 576: +1-9 %); tools/gemm_sites.py.
+// Order of precedence: forced option (wm_set_option) > tuned table entry (wm_gemm_set_variant) > heuristic.
+int g_gemm_two_cta = -1;   // "gemm_two_cta": -1 auto, 0 single-CTA tiles, 1 CTA-pair tiles (M >= 1024)
+int g_gemm_epi_warps = 0;  // "gemm_epi_warps": 0 auto, 8 or 16 (16 needs a tile width that is a multiple of 64)
+
+struct GemmVariant { int M, N, K; uint32_t sig; int two_cta, epi_warps; };
+constexpr int kMaxGemmVariants = 128;
+static GemmVariant g_gemm_variants[kMaxGemmVariants];
+static int g_num_gemm_variants = 0;
+
+uint32_t gemm_signature(const GemmEpilogue& ep, int out_fp32) {
+  return (ep.bias ? 1u : 0u) | (ep.relu ? 2u : 0u) | (ep.drop_thresh ? 4u : 0u) | (ep.gate ? 8u : 0u) |
+         (ep.gate_bits ? 16u : 0u) | (ep.residual ? 32u : 0u) | (ep.sign_bits_out ? 64u : 0u) | (out_fp32 ? 128u : 0u);
+}
+int gemm_set_variant(int M, int N, int K, uint32_t sig, int two_cta, int epi_warps) {
+  if ((two_cta != 0 && two_cta != 1) || (epi_warps != 8 && epi_warps != 16)) return WM_ERR_ARG;
+  for (int i = 0; i < g_num_gemm_variants; ++i) {
+    GemmVariant& v = g_gemm_variants[i];
+    if (v.M == M && v.N == N && v.K == K && v.sig == sig) {
+      v.two_cta = two_cta;
+      v.epi_warps = epi_warps;
+      return WM_OK;
+    }
+  }
+  if (g_num_gemm_variants == kMaxGemmVariants) g_num_gemm_variants = 0;  // start over rather than fail
+  g_gemm_variants[g_num_gemm_variants++] = GemmVariant{M, N, K, sig, two_cta, epi_warps};
+  return WM_OK;
+}
+static void gemm_pick_variant(int M, int N, int K, uint32_t sig, int* two_cta, int* epi_warps) {
+  int two = (K >= 1024) ? 1 : 0, ew = (K >= 1024) ? 8 : 16;
+  for (int i = 0; i < g_num_gemm_variants; ++i) {
+    const GemmVariant& v = g_gemm_variants[i];
+    if (v.M == M && v.N == N && v.K == K && v.sig == sig) {
+      two = v.two_cta;
+      ew = v.epi_warps;
+      break;
+    }
+  }
+  if (g_gemm_two_cta >= 0) two = g_gemm_two_cta;
+  if (g_gemm_epi_warps > 0) ew = g_gemm_epi_warps;
+  *two_cta = two;
+  *epi_warps = ew;
+}
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -585,40 +629,38 @@ static int launch_gemm_tn_impl(const void* A, int lda, const void* B, int ldb, i
   if (rc) return rc;
   rc = make_tmap_bf16(&tmB, B, b_rows, K, ldb, kBK, BN);
   if (rc) return rc;
-  if (g_gemm_two_cta && !out_fp32 && M >= 1024 && (BN & 31) == 0 && bn_override >= 0) {
+  int want_two, want_ew;
+  gemm_pick_variant(M, N, K, gemm_signature(ep, out_fp32), &want_two, &want_ew);
+  const int ew = (want_ew >= 16 && (BN & 63) == 0) ? 16 : 8;
+  const int threads = gemm_threads(ew);
+  const int fixed_smem = 2048 + static_cast<int>(sizeof(GemmSmemTail));
+  if (want_two && !out_fp32 && M >= 1024 && (BN & 31) == 0 && bn_override >= 0) {
     // CTA-pair path: 256 x BN tiles, each CTA stages 128 rows of A and BN/2 rows of B per k-block
     rc = make_tmap_bf16(&tmB, B, b_rows, K, ldb, kBK, BN / 2);
     if (rc) return rc;
     const int stage2 = (kBM + BN / 2) * kBK * 2;
-    int st2 = (227 * 1024 - 2048 - static_cast<int>(sizeof(GemmSmemTail))) / stage2;
+    int st2 = (227 * 1024 - fixed_smem) / stage2;
     if (st2 > kMaxStages) st2 = kMaxStages;
-    const int smem2 = st2 * stage2 + static_cast<int>(sizeof(GemmSmemTail)) + 1024;
+    const int smem2 = st2 * stage2 + fixed_smem - 1024;
     const int tiles2 = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + BN - 1) / BN);
     const int pairs = min(tiles2, num_sms() / 2);
-    if (cudaFuncSetAttribute(gemm_tn2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2) != cudaSuccess)
-      return WM_ERR_CUDA;
-    gemm_tn2_kernel<__nv_bfloat16><<<2 * pairs, kGemmThreads, smem2, stream>>>(tmA, tmB, M, N, K, BN, st2, ep);
+    auto kern2 = ew == 16 ? gemm_tn2_kernel<__nv_bfloat16, 16> : gemm_tn2_kernel<__nv_bfloat16, 8>;
+    if (cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2) != cudaSuccess) return WM_ERR_CUDA;
+    kern2<<<2 * pairs, threads, smem2, stream>>>(tmA, tmB, M, N, K, BN, st2, ep);
     WM_COUNT_LAUNCH();
     return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
   }
   const int stage_bytes = (kBM + BN) * kBK * 2;
-  int stages = (227 * 1024 - 2048 - static_cast<int>(sizeof(GemmSmemTail))) / stage_bytes;
+  int stages = (227 * 1024 - fixed_smem) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  const int smem = stages * stage_bytes + static_cast<int>(sizeof(GemmSmemTail)) + 1024;
+  const int smem = stages * stage_bytes + fixed_smem - 1024;
   const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + BN - 1) / BN;
   const int grid = min(m_tiles * n_tiles, num_sms());
-  cudaError_t e;
-  if (out_fp32) {
-    e = cudaFuncSetAttribute(gemm_tn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return WM_ERR_CUDA;
-    gemm_tn_kernel<float><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, BN, stages, ep);
-    WM_COUNT_LAUNCH();
-  } else {
-    e = cudaFuncSetAttribute(gemm_tn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return WM_ERR_CUDA;
-    gemm_tn_kernel<__nv_bfloat16><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, BN, stages, ep);
-    WM_COUNT_LAUNCH();
-  }
+  auto kern = out_fp32 ? (ew == 16 ? gemm_tn_kernel<float, 16> : gemm_tn_kernel<float, 8>)
+                       : (ew == 16 ? gemm_tn_kernel<__nv_bfloat16, 16> : gemm_tn_kernel<__nv_bfloat16, 8>);
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
+  kern<<<grid, threads, smem, stream>>>(tmA, tmB, M, N, K, BN, stages, ep);
+  WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 

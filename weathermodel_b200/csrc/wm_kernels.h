@@ -44,6 +44,8 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t c
                    uint32_t box_cols, uint32_t box_rows);
 
 size_t gemm_sign_bits_bytes(int M, int N);
+uint32_t gemm_signature(const GemmEpilogue& ep, int out_fp32);
+int gemm_set_variant(int M, int N, int K, uint32_t sig, int two_cta, int epi_warps);
 int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
                    const GemmEpilogue& ep, int out_fp32, int bn_override, cudaStream_t stream);
 int launch_gemm_tn_rows(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int b_rows,

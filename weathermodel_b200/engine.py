@@ -138,6 +138,9 @@ class EncoderRuntime:
                 check(lib().wm_encoder_create(C.byref(cfg), self.workspace.data_ptr(), self.workspace.numel(),
                                               C.byref(out)), "wm_encoder_create")
             self._handles[key] = out.value
+            # once per shape: pick the faster (bit-identical) kernel variant for each of the layer's GEMM call sites
+            D, _, FF, _, _ = self._dims()
+            ops.tune_gemm_sites(B * S, D, FF, self.dropout_p, self.flat_params.device)
         return self._handles[key]
 
     def _destroy_handles(self):

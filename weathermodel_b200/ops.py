@@ -6,6 +6,7 @@ allocated with `torch.empty`. Nothing is computed in PyTorch; a missing library 
 raises (see `_lib.check`).
 """
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -118,12 +119,83 @@ def gemm_tn(a, b, bias=None, relu=False, dropout_p=0.0, seed=0, stream_id=0, gat
     M, K = a.shape
     N = b.shape[0]
     out = torch.empty((M, N), dtype=torch.float32 if out_fp32 else BF16, device=a.device)
-    ep = _lib.GemmEpilogue(_p(bias), int(relu), float(dropout_p), int(seed), int(stream_id), _p(gate),
-                           gate.stride(0) if gate is not None else 0, float(gate_scale), _p(residual),
-                           residual.stride(0) if residual is not None else 0, _p(sign_bits_out), _p(gate_bits))
+    ep = _gemm_epilogue(bias, relu, dropout_p, seed, stream_id, gate, gate_scale, residual, sign_bits_out, gate_bits)
     check(lib().wm_gemm_tn(_p(a), a.stride(0), _p(b), b.stride(0), M, N, K, C.byref(ep), _p(out), out.stride(0),
                            int(out_fp32), int(tile_n), _stream()), "wm_gemm_tn")
     return out
+
+
+def _gemm_epilogue(bias=None, relu=False, dropout_p=0.0, seed=0, stream_id=0, gate=None, gate_scale=1.0, residual=None,
+                   sign_bits_out=None, gate_bits=None):
+    return _lib.GemmEpilogue(_p(bias), int(relu), float(dropout_p), int(seed), int(stream_id), _p(gate),
+                             gate.stride(0) if gate is not None else 0, float(gate_scale), _p(residual),
+                             residual.stride(0) if residual is not None else 0, _p(sign_bits_out), _p(gate_bits))
+
+
+_TUNED_SITES = set()
+GEMM_VARIANTS = ((0, 8), (0, 16), (1, 8), (1, 16))  # (two_cta, epi_warps); all bit-identical
+
+
+def tune_gemm_sites(M, D, FF, dropout_p, device, min_tokens=8192, reps=5):
+    """Time the (bit-identical) gemm_tn kernel variants on the eight GEMM call sites of one encoder layer --
+    forward and dgrad, with the epilogues wm_encoder_forward / backward use -- on scratch operands of the real
+    shapes, and record the fastest per site in the library (wm_gemm_set_variant). Runs once per (M, D, FF, dropout)
+    and process; small problems (M < min_tokens) keep the built-in heuristic. Returns {site: (two_cta, epi_warps)}."""
+    key = (int(M), int(D), int(FF), dropout_p > 0, str(device))
+    if key in _TUNED_SITES or M < min_tokens or (D & 7) or (FF & 7):
+        return {}
+    _TUNED_SITES.add(key)
+    L = lib()
+    forced = os.environ.get("WM_OPTIONS", "")
+    if "gemm_two_cta" in forced or "gemm_epi_warps" in forced:
+        return {}
+    with torch.cuda.device(device):
+        bf = lambda *shape: torch.zeros(*shape, dtype=BF16, device=device).normal_(0, 0.5)  # noqa: E731
+        big = bf(M, max(FF, 3 * D))
+        x, res = bf(M, D), bf(M, D)
+        bits = torch.zeros(L.wm_gemm_sign_bits_bytes(M, FF), dtype=torch.uint8, device=device)
+        drop = dict(dropout_p=dropout_p, seed=1, stream_id=2) if dropout_p > 0 else {}
+        sites = [  # name, A, N, K, epilogue fields (wm_encoder.cu: encoder_forward / encoder_backward_layers)
+            ("qkv", x, 3 * D, D, dict(bias=True)),
+            ("out_proj", x, D, D, dict(bias=True, residual=res, **drop)),
+            ("linear1", x, FF, D, dict(bias=True, relu=True, sign_bits_out=bits, **drop)),
+            ("linear2", big[:, :FF], D, FF, dict(bias=True, residual=res, **drop)),
+            ("linear2_dgrad", x, FF, D, dict(gate_bits=bits, gate_scale=1.0)),
+            ("linear1_dgrad", big[:, :FF], D, FF, dict(residual=res)),
+            ("out_proj_dgrad", x, D, D, dict()),
+            ("qkv_dgrad", big[:, :3 * D], D, 3 * D, dict(residual=res)),
+        ]
+        out_buf = torch.empty(M, max(FF, 3 * D), dtype=BF16, device=device)
+        chosen = {}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for name, A, N, K, kw in sites:
+            kw = dict(kw)
+            if kw.pop("bias", False):
+                kw["bias"] = torch.zeros(N, dtype=torch.float32, device=device)
+            w = bf(N, K)
+            ep = _gemm_epilogue(**kw)
+            out = out_buf.view(-1)[: M * N].view(M, N)
+
+            def launch():
+                check(L.wm_gemm_tn(_p(A), A.stride(0), _p(w), w.stride(0), M, N, K, C.byref(ep), _p(out), N, 0, 0,
+                                   _stream()), "wm_gemm_tn (tuning)")
+
+            best, best_ms = None, float("inf")
+            for _ in range(2):  # two passes over the variants: the first also warms clocks and caches
+                for two, ew in GEMM_VARIANTS:
+                    check(L.wm_gemm_set_variant(M, N, K, C.byref(ep), 0, two, ew), "wm_gemm_set_variant")
+                    launch()
+                    e0.record()
+                    for _ in range(reps):
+                        launch()
+                    e1.record()
+                    e1.synchronize()
+                    ms = e0.elapsed_time(e1) / reps
+                    if ms < best_ms:
+                        best, best_ms = (two, ew), ms
+            check(L.wm_gemm_set_variant(M, N, K, C.byref(ep), 0, best[0], best[1]), "wm_gemm_set_variant")
+            chosen[name] = best
+    return chosen
 
 
 def gemm_wgrad(a, b, accumulate_into=None, want_bias_grad=False):
