@@ -37,7 +37,8 @@ long long wm_launch_count(void);
 int wm_debug_ticks(long long* out_host, int n);
 /* tuning switches (tests / A-B measurements; results are bit-identical either way): "gemm_two_cta" = -1 auto
  * (default) / 0 / 1 selects the cta_group::2 GEMM for M >= 1024, "gemm_epi_warps" = 0 auto (default) / 8 / 16 epilogue
- * warps per GEMM CTA. A forced value overrides wm_gemm_set_variant and the built-in heuristic. */
+ * warps per GEMM CTA, "gemm_staged" = -1 auto (default) / 0 / 1 writes bf16 outputs through a shared-memory staging
+ * tile with coalesced stores instead of thread-per-row stores. A forced value overrides wm_gemm_set_variant and the built-in heuristic. */
 int wm_set_option(const char* name, int value);
 /* torch.rand grid size for `numel` elements on the current device
  * (torch:include/ATen/native/cuda/DistributionTemplates.h:50-63 calc_execution_policy). */
@@ -84,10 +85,10 @@ int wm_gemm_tn(const void* A_bf16, int lda, const void* B_bf16, int ldb, int M, 
                const wm_gemm_epilogue* epilogue /* may be NULL */, void* out, int ld_out, int out_is_fp32,
                int tile_n /* 0 = auto */, void* stream);
 /* Record the faster of the (bit-identical) kernel variants for the call site (M, N, K, which epilogue fields are
- * set): two_cta 0 / 1, epi_warps 8 / 16. The host-side tuner (weathermodel_b200/ops.py: tune_gemm_sites) times the
+ * set): two_cta 0 / 1, epi_warps 8 / 16, staged_stores 0 / 1. The host-side tuner (weathermodel_b200/ops.py: tune_gemm_sites) times the
  * variants of an encoder's eight GEMM sites once per shape; untuned sites use a heuristic (K >= 1024: CTA pairs). */
 int wm_gemm_set_variant(int M, int N, int K, const wm_gemm_epilogue* epilogue /* may be NULL */, int out_is_fp32,
-                        int two_cta, int epi_warps);
+                        int two_cta, int epi_warps, int staged_stores);
 /* dW[Nout,Kout] (+)= A[Mtok,Nout]^T . B[Mtok,Kout]; workspace from wm_gemm_wgrad_workspace_bytes.
  * dbias (optional, [Nout]): column sums of A over the tokens (the bias gradient), fused into the same kernel. */
 size_t wm_gemm_wgrad_workspace_bytes(int Mtok, int Nout, int Kout);

@@ -33,7 +33,7 @@ def _cmp(name, got, ref, rtol, atol):
             f"first {first} got {got[first]:.5g} ref {ref[first]:.5g}; bad rows~{rows} cols~{cols}")
 
 
-GEMM_DEFAULTS = {"gemm_two_cta": -1, "gemm_epi_warps": 0}  # -1 / 0 = automatic choice  # library defaults (wm_gemm.cu)
+GEMM_DEFAULTS = {"gemm_two_cta": -1, "gemm_epi_warps": 0, "gemm_staged": -1}  # -1 / 0 = automatic choice  # library defaults (wm_gemm.cu)
 
 
 def _bf(*shape, scale=1.0, seed=0):
@@ -91,8 +91,9 @@ def test_gemm_cta_pair_kernel_is_bit_identical(M, N, K):
     (130, 48, 48, 0), (1111, 600, 200, 64), (2048, 1344, 336, 128), (365, 40, 64, 0),
 ])
 def test_gemm_kernel_variants_are_bit_identical(M, N, K, tile_n):
-    """8 vs 16 epilogue warps (gemm_epi_warps) and single-CTA vs CTA-pair tiles (gemm_two_cta) must agree bit for
-    bit, incl. clipped rows / columns, dropout, the sign side channel, a residual and the fp32 output."""
+    """8 vs 16 epilogue warps (gemm_epi_warps), single-CTA vs CTA-pair tiles (gemm_two_cta) and thread-per-row vs
+    staged coalesced stores (gemm_staged) must agree bit for bit, incl. clipped rows / columns, dropout, the sign
+    side channel, a residual and the fp32 output."""
     from weathermodel_b200._lib import lib
 
     a = _bf(M, K, seed=40)
@@ -113,13 +114,15 @@ def test_gemm_kernel_variants_are_bit_identical(M, N, K, tile_n):
     try:
         lib().wm_set_option(b"gemm_two_cta", 0)
         lib().wm_set_option(b"gemm_epi_warps", 8)
+        lib().wm_set_option(b"gemm_staged", 0)
         ref = run()
-        for two, ew in ((0, 16), (1, 8), (1, 16)):
+        for two, ew, stg in ops.GEMM_VARIANTS[1:]:
             lib().wm_set_option(b"gemm_two_cta", two)
             lib().wm_set_option(b"gemm_epi_warps", ew)
+            lib().wm_set_option(b"gemm_staged", stg)
             got = run()
             for i, (r, g) in enumerate(zip(ref, got)):
-                assert torch.equal(r, g), f"two_cta={two} epi_warps={ew}: output {i} differs"
+                assert torch.equal(r, g), f"two_cta={two} epi_warps={ew} staged={stg}: output {i} differs"
     finally:
         for k, v in GEMM_DEFAULTS.items():
             lib().wm_set_option(k.encode(), v)
@@ -142,7 +145,7 @@ def test_gemm_site_tuner_records_a_variant_and_keeps_results():
     assert all(v in ops.GEMM_VARIANTS for v in chosen.values())
     assert ops.tune_gemm_sites(M, D, FF, 0.1, a.device) == {}  # once per shape and process
     assert torch.equal(before, ops.gemm_tn(a, b, bias=bias, relu=True))
-    assert lib().wm_gemm_set_variant(M, FF, D, None, 0, 2, 8) != 0  # rejects unknown variants
+    assert lib().wm_gemm_set_variant(M, FF, D, None, 0, 2, 8, 0) != 0  # rejects unknown variants
     assert ops.device_error() == 0
 
 

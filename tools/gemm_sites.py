@@ -1,5 +1,5 @@
 """The eight gemm_tn call sites of one encoder layer (forward + dgrad) with their real epilogues, timed under every
-kernel variant (gemm_two_cta x gemm_epi_warps). Decides the per-site variant choice in launch_gemm_tn_impl.
+kernel variant (gemm_two_cta, gemm_epi_warps, gemm_staged). Decides the per-site variant choice in launch_gemm_tn_impl.
     python tools/gemm_sites.py [workload]"""
 import os, sys
 import torch
@@ -33,20 +33,22 @@ sites = [  # name, A, N, K, kwargs
     ("B3 out-proj dgrad (plain)", x, D, D, dict()),
     ("B4 qkv dgrad (+res)", qkv, D, 3 * D, dict(residual=x2)),
 ]
+TILE_N = int(os.environ.get("TILE_N", 0))  # force the tile width (sites whose N it does not divide keep the default)
 total = {}
 for name, A, N, K, kw in sites:
     w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
     kw = dict(kw)
     if kw.pop("bias", False): kw["bias"] = torch.zeros(N, device="cuda")
+    if TILE_N and N % TILE_N == 0: kw["tile_n"] = TILE_N
     ref, line = None, []
-    for two, ew in ((0, 8), (0, 16), (1, 8), (1, 16)):
-        lib().wm_set_option(b"gemm_two_cta", two); lib().wm_set_option(b"gemm_epi_warps", ew)
+    for two, ew, stg in ops.GEMM_VARIANTS:
+        lib().wm_set_option(b"gemm_two_cta", two); lib().wm_set_option(b"gemm_epi_warps", ew); lib().wm_set_option(b"gemm_staged", stg)
         out = ops.gemm_tn(A, w, **kw)
         if ref is None: ref = out
-        else: assert torch.equal(ref, out), f"{name}: variant ({two},{ew}) differs"
+        else: assert torch.equal(ref, out), f"{name}: variant ({two},{ew},{stg}) differs"
         ms = t(lambda: ops.gemm_tn(A, w, **kw))
-        total[(two, ew)] = total.get((two, ew), 0.0) + ms
-        line.append(f"({two},{ew:2d}) {ms:.4f} ms {2.0*M*N*K/ms/1e9:6.0f} TF")
+        total[(two, ew, stg)] = total.get((two, ew, stg), 0.0) + ms
+        line.append(f"({two},{ew:2d},{stg}) {ms:.4f}")
     print(f"{name:34s} [{M}x{N}x{K}]  " + "  ".join(line), flush=True)
 print("sum per layer:", {k: round(v, 4) for k, v in total.items()})
 print("device_error", ops.device_error())

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwm_b200.so")
+LIB_PATH = os.environ.get("WM_B200_LIB") or os.path.join(_HERE, "libwm_b200.so")  # override: diagnostic builds (tools/)
 
 _vp, _i, _i64, _u64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
 
@@ -40,7 +40,7 @@ SIGNATURES = {
     "wm_mask_former": (_i, [_u64, _u64, _i, _i, _i64, _i, _vp, _vp]),
     "wm_embed_fwd": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wm_gemm_tn": (_i, [_vp, _i, _vp, _i, _i, _i, _i, C.POINTER(GemmEpilogue), _vp, _i, _i, _i, _vp]),
-    "wm_gemm_set_variant": (_i, [_i, _i, _i, C.POINTER(GemmEpilogue), _i, _i, _i]),
+    "wm_gemm_set_variant": (_i, [_i, _i, _i, C.POINTER(GemmEpilogue), _i, _i, _i, _i]),
     "wm_gemm_sign_bits_bytes": (_sz, [_i, _i]),
     "wm_gemm_wgrad_workspace_bytes": (_sz, [_i, _i, _i]),
     "wm_gemm_wgrad": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),

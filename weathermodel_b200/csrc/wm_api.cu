@@ -46,11 +46,12 @@ int wm_debug_ticks(long long* out_host, int n) {
   return cudaMemcpyFromSymbol(out_host, g_wm_ticks, sizeof(long long) * n) == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
-namespace wm { extern int g_gemm_two_cta, g_gemm_epi_warps; }
+namespace wm { extern int g_gemm_two_cta, g_gemm_epi_warps, g_gemm_staged; }
 int wm_set_option(const char* name, int value) {
   if (!name) return WM_ERR_ARG;
   struct Opt { const char* name; int* slot; };
-  const Opt opts[] = {{"gemm_two_cta", &wm::g_gemm_two_cta}, {"gemm_epi_warps", &wm::g_gemm_epi_warps}};
+  const Opt opts[] = {{"gemm_two_cta", &wm::g_gemm_two_cta}, {"gemm_epi_warps", &wm::g_gemm_epi_warps},
+                      {"gemm_staged", &wm::g_gemm_staged}};
   for (const Opt& o : opts) {
     const char* a = name;
     const char* b = o.name;
@@ -60,6 +61,14 @@ int wm_set_option(const char* name, int value) {
       return WM_OK;
     }
   }
+#ifdef WM_DIAG
+  {
+    const char* a = name;
+    const char* b = "gemm_diag";
+    while (*a && *a == *b) { ++a; ++b; }
+    if (!*a && !*b) return wm::gemm_set_diag(value);
+  }
+#endif
   return WM_ERR_ARG;
 }
 
@@ -123,11 +132,12 @@ int wm_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int
   ep.ld_out = ld_out;
   return launch_gemm_tn(A, lda, B, ldb, M, N, K, ep, out_is_fp32, tile_n, S_(stream));
 }
-int wm_gemm_set_variant(int M, int N, int K, const wm_gemm_epilogue* e, int out_is_fp32, int two_cta, int epi_warps) {
+int wm_gemm_set_variant(int M, int N, int K, const wm_gemm_epilogue* e, int out_is_fp32, int two_cta, int epi_warps,
+                        int staged) {
   GemmEpilogue ep;
   const int rc = fill_epilogue(ep, e);
   if (rc) return rc;
-  return gemm_set_variant(M, N, K, gemm_signature(ep, out_is_fp32), two_cta, epi_warps);
+  return gemm_set_variant(M, N, K, gemm_signature(ep, out_is_fp32), two_cta, epi_warps, staged);
 }
 size_t wm_gemm_wgrad_workspace_bytes(int Mtok, int Nout, int Kout) { return wgrad_workspace_bytes(Mtok, Nout, Kout); }
 int wm_gemm_wgrad(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout, float* dW,

@@ -152,12 +152,27 @@ WM_DEVICE void epi_load_aux(EpiAux& x, const GemmEpilogue& ep, int row, int n0, 
   }
 }
 
+#ifdef WM_DIAG
+// Diagnostic build only (tools/gemm_diag.py; never part of libwm_b200.so): bit 0 skips the output stores, bit 1 the
+// arithmetic as well, bit 2 the TMEM loads, bit 3 stores the tile transposed-free into a compact per-CTA scratch.
+int g_gemm_diag = 0;  // copied into GemmEpilogue::diag by the launcher
+#endif
+
 template <typename OutT>
 WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const float* sbias, const GemmEpilogue& ep,
-                             int row, int n0, int M, int N, bool wide) {
+                             int row, int n0, int M, int N, bool wide, uint8_t* sdst) {
+  // sdst (bf16 outputs only): this lane's 32 bytes of the chunk inside the warp's shared-memory staging tile; the
+  // tile leaves through coalesced stores once all chunks are in (gemm_epilogue_tile). nullptr: direct stores.
   if (n0 >= N) return;  // warp-uniform
+#ifdef WM_DIAG
+  const int diag = ep.diag;
+  if (diag & 2) {
+    if (v[0] == 0x7fc12345u) reinterpret_cast<uint32_t*>(ep.out)[0] = v[3];  // keep the loads alive
+    return;
+  }
+#endif
   const int m32 = (M + 31) & ~31;
-  if (row >= M && (!ep.sign_bits_out || row >= m32)) return;
+  if (!sdst && row >= M && (!ep.sign_bits_out || row >= m32)) return;
   float f[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
@@ -240,8 +255,24 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
       uint32_t m = (acc & 0xFFu) | ((acc >> 8) & 0xFF00u);
       if (!second) m &= 0x0F0Fu;
       if (row < m32) ep.sign_bits_out[sign_bits_index(row, n0, N)] = static_cast<uint16_t>(row < M ? m : 0u);
-      if (row >= M) return;
+      if (!sdst && row >= M) return;
     }
+    if (sdst) {
+      *reinterpret_cast<uint4*>(sdst) = o0;
+      *reinterpret_cast<uint4*>(sdst + 16) = o1;
+      return;
+    }
+#ifdef WM_DIAG
+    if (diag & 1) {
+      if (o0.x == 0x7fc17fc1u && o1.w == 0x12345678u) reinterpret_cast<uint32_t*>(ep.out)[0] = o0.y;
+      return;
+    }
+    if (diag & 8) {  // same bytes, but every row of the tile lands in one contiguous 64 KB block per CTA
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (static_cast<size_t>(blockIdx.x) * 128 + (row & 127)) * 256 + (n0 & 255);
+      stg256(o, o0, o1);
+      return;
+    }
+#endif
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(row) * ep.ld_out + n0;
     if (wide && second) {
       stg256(o, o0, o1);
@@ -264,7 +295,12 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
 template <typename OutT, int kAuxDepth>
 WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t* acc_full, uint32_t aph,
                                   uint32_t wait_code, uint32_t tbase, int row, int n_base, int cols_per, int M, int N,
-                                  bool wide, int lane) {
+                                  bool wide, int lane, uint8_t* stage) {
+  // stage: this warp's 32 x (cols_per * 2 + 16)-byte staging tile or nullptr. Thread-per-row stores (32 bytes per
+  // lane, rows a leading dimension apart) cost the LSU / L1 one line per lane: ~8 B/clk/SM, and with K = 576 they,
+  // not the MMAs, set the pace (tools/gemm_diag.py: linear1 0.505 ms with, 0.359 ms without the stores). Staged, a
+  // warp-wide 16-byte store covers whole row segments: 4 - 5 lines per instruction instead of 32.
+  const uint32_t pitch = static_cast<uint32_t>(cols_per) * 2u + 16u;  // odd number of 16-byte units: conflict-free
   if (ep.bias) {
     __syncwarp();
     for (int j = lane; j < cols_per; j += 32) sbias[j] = (n_base + j < N) ? __ldg(ep.bias + n_base + j) : 0.0f;
@@ -286,16 +322,46 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
     for (int d = 0; d < kAuxDepth; ++d) {
       const int c0 = cb + d * 16;
       if (c0 < cols_per) {
+#ifdef WM_DIAG
+        if (ep.diag & 4) continue;
+#endif
         tmem_ld_wait();
         if (d & 1) {
           if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, va);
-          epi_process16<OutT>(vb, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide);
+          epi_process16<OutT>(vb, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide,
+                              stage ? stage + lane * pitch + c0 * 2 : nullptr);
         } else {
           if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, vb);
-          epi_process16<OutT>(va, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide);
+          epi_process16<OutT>(va, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide,
+                              stage ? stage + lane * pitch + c0 * 2 : nullptr);
         }
         if (c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
       }
+    }
+  }
+#ifdef WM_DIAG
+  tmem_ld_wait();
+#endif
+  if constexpr (sizeof(OutT) == 2) {
+    if (stage) {
+      __syncwarp();
+      // 16-byte units of the tile in row-major order, 32 per instruction: unit i = lane + 32 k is piece i % u of
+      // row i / u (u = units per row); consecutive lanes write consecutive global addresses within a row
+      const int u = cols_per >> 3;
+      const int q32 = 32 / u, m32u = 32 - q32 * u;
+      int r = lane / u, piece = lane - r * u;
+      const int row0 = row - lane;
+      __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(ep.out);
+      for (int k = 0; k < u; ++k) {
+        const int col = n_base + piece * 8;
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + r * pitch + piece * 16);
+        if (row0 + r < M && col < N)
+          *reinterpret_cast<uint4*>(outp + static_cast<size_t>(row0 + r) * ep.ld_out + col) = val;
+        r += q32;
+        piece += m32u;
+        if (piece >= u) { piece -= u; ++r; }
+      }
+      __syncwarp();  // the next tile's chunks overwrite the staging tile
     }
   }
 }
@@ -303,14 +369,17 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
 template <typename OutT, int kEW>
 __global__ void __launch_bounds__(gemm_threads(kEW), 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               int M, int N, int K, int BN, int stages, GemmEpilogue ep) {
+               int M, int N, int K, int BN, int stages, int staged, GemmEpilogue ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024B-align the tile ring (SWIZZLE_128B atoms)
   uint8_t* smem = smem_align_up(smem_raw, 1024);
   const uint32_t a_bytes = kBM * kBK * 2;
   const uint32_t b_bytes = static_cast<uint32_t>(BN) * kBK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  // [tile ring][epilogue staging: kEW x 32 rows x (BN / (kEW / 4) * 2 + 16) bytes, if staged][tail]
+  uint8_t* epi_stage = smem + static_cast<size_t>(stages) * stage_bytes;
+  const uint32_t epi_stage_warp = 32u * (static_cast<uint32_t>(BN / (kEW / 4)) * 2u + 16u);
+  GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(epi_stage + (staged ? kEW * epi_stage_warp : 0u));
 
   const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
@@ -401,7 +470,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t aph = (it >> 1) & 1u;
       const uint32_t tbase = tmem_base + as * kAccStride + half * cols_per + (static_cast<uint32_t>(q * 32) << 16);
       gemm_epilogue_tile<OutT, (kEW == 16 ? 2 : 4)>(ep, sbias, &tail->acc_full[as], aph, 14, tbase, m_blk * kBM + q * 32 + lane,
-                               n_blk * BN + half * cols_per, cols_per, M, N, wide, lane);
+                               n_blk * BN + half * cols_per, cols_per, M, N, wide, lane,
+                               staged ? epi_stage + static_cast<uint32_t>(ew) * epi_stage_warp : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->acc_empty[as]);
@@ -424,14 +494,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <typename OutT, int kEW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(kEW), 1)
 gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                int M, int N, int K, int BN, int stages, GemmEpilogue ep) {
+                int M, int N, int K, int BN, int stages, int staged, GemmEpilogue ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_align_up(smem_raw, 1024);
   const int BNH = BN >> 1;  // B rows staged by each CTA
   const uint32_t a_bytes = kBM * kBK * 2;
   const uint32_t b_bytes = static_cast<uint32_t>(BNH) * kBK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  // [tile ring][epilogue staging: kEW x 32 rows x (BN / (kEW / 4) * 2 + 16) bytes, if staged][tail]
+  uint8_t* epi_stage = smem + static_cast<size_t>(stages) * stage_bytes;
+  const uint32_t epi_stage_warp = 32u * (static_cast<uint32_t>(BN / (kEW / 4)) * 2u + 16u);
+  GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(epi_stage + (staged ? kEW * epi_stage_warp : 0u));
 
   const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
@@ -524,7 +597,8 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t tbase = tmem_base + as * kAccStride + half * cols_per + (static_cast<uint32_t>(q * 32) << 16);
       gemm_epilogue_tile<OutT, (kEW == 16 ? 2 : 4)>(ep, sbias, &tail->acc_full[as], aph, 64, tbase,
                                m_blk * 2 * kBM + static_cast<int>(rank) * kBM + q * 32 + lane,
-                               n_blk * BN + half * cols_per, cols_per, M, N, wide, lane);
+                               n_blk * BN + half * cols_per, cols_per, M, N, wide, lane,
+                               staged ? epi_stage + static_cast<uint32_t>(ew) * epi_stage_warp : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc_empty_leader[as]);
@@ -563,44 +637,52 @@ static int pick_bn(int N) {
 // Order of precedence: forced option (wm_set_option) > tuned table entry (wm_gemm_set_variant) > heuristic.
 int g_gemm_two_cta = -1;   // "gemm_two_cta": -1 auto, 0 single-CTA tiles, 1 CTA-pair tiles (M >= 1024)
 int g_gemm_epi_warps = 0;  // "gemm_epi_warps": 0 auto, 8 or 16 (16 needs a tile width that is a multiple of 64)
+int g_gemm_staged = -1;    // "gemm_staged": -1 auto, 0 thread-per-row stores, 1 stores staged through shared memory
 
-struct GemmVariant { int M, N, K; uint32_t sig; int two_cta, epi_warps; };
+struct GemmVariant { int M, N, K; uint32_t sig; int two_cta, epi_warps, staged; };
 constexpr int kMaxGemmVariants = 128;
 static GemmVariant g_gemm_variants[kMaxGemmVariants];
 static int g_num_gemm_variants = 0;
 
+#ifdef WM_DIAG
+int gemm_set_diag(int v) { g_gemm_diag = v; return WM_OK; }
+#endif
 uint32_t gemm_signature(const GemmEpilogue& ep, int out_fp32) {
   return (ep.bias ? 1u : 0u) | (ep.relu ? 2u : 0u) | (ep.drop_thresh ? 4u : 0u) | (ep.gate ? 8u : 0u) |
          (ep.gate_bits ? 16u : 0u) | (ep.residual ? 32u : 0u) | (ep.sign_bits_out ? 64u : 0u) | (out_fp32 ? 128u : 0u);
 }
-int gemm_set_variant(int M, int N, int K, uint32_t sig, int two_cta, int epi_warps) {
-  if ((two_cta != 0 && two_cta != 1) || (epi_warps != 8 && epi_warps != 16)) return WM_ERR_ARG;
+int gemm_set_variant(int M, int N, int K, uint32_t sig, int two_cta, int epi_warps, int staged) {
+  if ((two_cta != 0 && two_cta != 1) || (epi_warps != 8 && epi_warps != 16) || (staged != 0 && staged != 1)) return WM_ERR_ARG;
   for (int i = 0; i < g_num_gemm_variants; ++i) {
     GemmVariant& v = g_gemm_variants[i];
     if (v.M == M && v.N == N && v.K == K && v.sig == sig) {
       v.two_cta = two_cta;
       v.epi_warps = epi_warps;
+      v.staged = staged;
       return WM_OK;
     }
   }
   if (g_num_gemm_variants == kMaxGemmVariants) g_num_gemm_variants = 0;  // start over rather than fail
-  g_gemm_variants[g_num_gemm_variants++] = GemmVariant{M, N, K, sig, two_cta, epi_warps};
+  g_gemm_variants[g_num_gemm_variants++] = GemmVariant{M, N, K, sig, two_cta, epi_warps, staged};
   return WM_OK;
 }
-static void gemm_pick_variant(int M, int N, int K, uint32_t sig, int* two_cta, int* epi_warps) {
-  int two = (K >= 1024) ? 1 : 0, ew = (K >= 1024) ? 8 : 16;
+static void gemm_pick_variant(int M, int N, int K, uint32_t sig, int* two_cta, int* epi_warps, int* staged) {
+  int two = (K >= 1024) ? 1 : 0, ew = (K >= 1024) ? 8 : 16, stg = (K >= 1024) ? 0 : 1;
   for (int i = 0; i < g_num_gemm_variants; ++i) {
     const GemmVariant& v = g_gemm_variants[i];
     if (v.M == M && v.N == N && v.K == K && v.sig == sig) {
       two = v.two_cta;
       ew = v.epi_warps;
+      stg = v.staged;
       break;
     }
   }
   if (g_gemm_two_cta >= 0) two = g_gemm_two_cta;
   if (g_gemm_epi_warps > 0) ew = g_gemm_epi_warps;
+  if (g_gemm_staged >= 0) stg = g_gemm_staged;
   *two_cta = two;
   *epi_warps = ew;
+  *staged = stg;
 }
 static int g_num_sms = 0;
 static int num_sms() {
@@ -616,6 +698,9 @@ static int num_sms() {
 static int launch_gemm_tn_impl(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int b_rows,
                                const GemmEpilogue& ep_in, int out_fp32, int bn_override, cudaStream_t stream) {
   GemmEpilogue ep = ep_in;
+#ifdef WM_DIAG
+  ep.diag = g_gemm_diag;
+#endif
   if (ep.drop_thresh) {
     if (static_cast<uint64_t>(M) * static_cast<uint64_t>((N + 15) / 16) * 4ull > 0xFFFFFFFFull) return WM_ERR_SHAPE;  // 32-bit mask counters
     ep.dkeys = drop_keys(ep.seed, ep.stream);
@@ -629,37 +714,42 @@ static int launch_gemm_tn_impl(const void* A, int lda, const void* B, int ldb, i
   if (rc) return rc;
   rc = make_tmap_bf16(&tmB, B, b_rows, K, ldb, kBK, BN);
   if (rc) return rc;
-  int want_two, want_ew;
-  gemm_pick_variant(M, N, K, gemm_signature(ep, out_fp32), &want_two, &want_ew);
+  int want_two, want_ew, want_staged;
+  gemm_pick_variant(M, N, K, gemm_signature(ep, out_fp32), &want_two, &want_ew, &want_staged);
   const int ew = (want_ew >= 16 && (BN & 63) == 0) ? 16 : 8;
   const int threads = gemm_threads(ew);
   const int fixed_smem = 2048 + static_cast<int>(sizeof(GemmSmemTail));
+  // staged stores: 16-byte aligned rows and at least three pipeline stages left next to the staging tiles
+  const int staging = ew * 32 * (BN / (ew / 4) * 2 + 16);
+  const bool can_stage = want_staged && !out_fp32 && (ep.ld_out & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0;
   if (want_two && !out_fp32 && M >= 1024 && (BN & 31) == 0 && bn_override >= 0) {
     // CTA-pair path: 256 x BN tiles, each CTA stages 128 rows of A and BN/2 rows of B per k-block
     rc = make_tmap_bf16(&tmB, B, b_rows, K, ldb, kBK, BN / 2);
     if (rc) return rc;
     const int stage2 = (kBM + BN / 2) * kBK * 2;
-    int st2 = (227 * 1024 - fixed_smem) / stage2;
+    const int staged2 = (can_stage && (227 * 1024 - fixed_smem - staging) / stage2 >= 3) ? 1 : 0;
+    int st2 = (227 * 1024 - fixed_smem - (staged2 ? staging : 0)) / stage2;
     if (st2 > kMaxStages) st2 = kMaxStages;
-    const int smem2 = st2 * stage2 + fixed_smem - 1024;
+    const int smem2 = st2 * stage2 + fixed_smem - 1024 + (staged2 ? staging : 0);
     const int tiles2 = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + BN - 1) / BN);
     const int pairs = min(tiles2, num_sms() / 2);
     auto kern2 = ew == 16 ? gemm_tn2_kernel<__nv_bfloat16, 16> : gemm_tn2_kernel<__nv_bfloat16, 8>;
     if (cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2) != cudaSuccess) return WM_ERR_CUDA;
-    kern2<<<2 * pairs, threads, smem2, stream>>>(tmA, tmB, M, N, K, BN, st2, ep);
+    kern2<<<2 * pairs, threads, smem2, stream>>>(tmA, tmB, M, N, K, BN, st2, staged2, ep);
     WM_COUNT_LAUNCH();
     return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
   }
   const int stage_bytes = (kBM + BN) * kBK * 2;
-  int stages = (227 * 1024 - fixed_smem) / stage_bytes;
+  const int staged1 = (can_stage && (227 * 1024 - fixed_smem - staging) / stage_bytes >= 3) ? 1 : 0;
+  int stages = (227 * 1024 - fixed_smem - (staged1 ? staging : 0)) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  const int smem = stages * stage_bytes + fixed_smem - 1024;
+  const int smem = stages * stage_bytes + fixed_smem - 1024 + (staged1 ? staging : 0);
   const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + BN - 1) / BN;
   const int grid = min(m_tiles * n_tiles, num_sms());
   auto kern = out_fp32 ? (ew == 16 ? gemm_tn_kernel<float, 16> : gemm_tn_kernel<float, 8>)
                        : (ew == 16 ? gemm_tn_kernel<__nv_bfloat16, 16> : gemm_tn_kernel<__nv_bfloat16, 8>);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
-  kern<<<grid, threads, smem, stream>>>(tmA, tmB, M, N, K, BN, stages, ep);
+  kern<<<grid, threads, smem, stream>>>(tmA, tmB, M, N, K, BN, stages, staged1, ep);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }

@@ -38,6 +38,9 @@ struct GemmEpilogue {
   const uint16_t* gate_bits = nullptr;   // replaces `gate` when given (gate_scale still applies)
   void* out = nullptr;                   // [M, ld_out] bf16 or fp32
   int ld_out = 0;
+#ifdef WM_DIAG
+  int diag = 0;                          // diagnostic builds only (tools/gemm_diag.py)
+#endif
 };
 
 int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
@@ -45,7 +48,7 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t c
 
 size_t gemm_sign_bits_bytes(int M, int N);
 uint32_t gemm_signature(const GemmEpilogue& ep, int out_fp32);
-int gemm_set_variant(int M, int N, int K, uint32_t sig, int two_cta, int epi_warps);
+int gemm_set_variant(int M, int N, int K, uint32_t sig, int two_cta, int epi_warps, int staged);
 int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
                    const GemmEpilogue& ep, int out_fp32, int bn_override, cudaStream_t stream);
 int launch_gemm_tn_rows(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int b_rows,

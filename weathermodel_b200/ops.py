@@ -133,21 +133,21 @@ def _gemm_epilogue(bias=None, relu=False, dropout_p=0.0, seed=0, stream_id=0, ga
 
 
 _TUNED_SITES = set()
-GEMM_VARIANTS = ((0, 8), (0, 16), (1, 8), (1, 16))  # (two_cta, epi_warps); all bit-identical
+GEMM_VARIANTS = tuple((two, ew, st) for st in (0, 1) for two in (0, 1) for ew in (8, 16))  # (two_cta, epi_warps, staged stores); all bit-identical
 
 
 def tune_gemm_sites(M, D, FF, dropout_p, device, min_tokens=8192, reps=5):
     """Time the (bit-identical) gemm_tn kernel variants on the eight GEMM call sites of one encoder layer --
     forward and dgrad, with the epilogues wm_encoder_forward / backward use -- on scratch operands of the real
     shapes, and record the fastest per site in the library (wm_gemm_set_variant). Runs once per (M, D, FF, dropout)
-    and process; small problems (M < min_tokens) keep the built-in heuristic. Returns {site: (two_cta, epi_warps)}."""
+    and process; small problems (M < min_tokens) keep the built-in heuristic. Returns {site: (two_cta, epi_warps, staged)}."""
     key = (int(M), int(D), int(FF), dropout_p > 0, str(device))
     if key in _TUNED_SITES or M < min_tokens or (D & 7) or (FF & 7):
         return {}
     _TUNED_SITES.add(key)
     L = lib()
     forced = os.environ.get("WM_OPTIONS", "")
-    if "gemm_two_cta" in forced or "gemm_epi_warps" in forced:
+    if "gemm_" in forced:
         return {}
     with torch.cuda.device(device):
         bf = lambda *shape: torch.zeros(*shape, dtype=BF16, device=device).normal_(0, 0.5)  # noqa: E731
@@ -182,8 +182,8 @@ def tune_gemm_sites(M, D, FF, dropout_p, device, min_tokens=8192, reps=5):
 
             best, best_ms = None, float("inf")
             for _ in range(2):  # two passes over the variants: the first also warms clocks and caches
-                for two, ew in GEMM_VARIANTS:
-                    check(L.wm_gemm_set_variant(M, N, K, C.byref(ep), 0, two, ew), "wm_gemm_set_variant")
+                for two, ew, stg in GEMM_VARIANTS:
+                    check(L.wm_gemm_set_variant(M, N, K, C.byref(ep), 0, two, ew, stg), "wm_gemm_set_variant")
                     launch()
                     e0.record()
                     for _ in range(reps):
@@ -192,8 +192,8 @@ def tune_gemm_sites(M, D, FF, dropout_p, device, min_tokens=8192, reps=5):
                     e1.synchronize()
                     ms = e0.elapsed_time(e1) / reps
                     if ms < best_ms:
-                        best, best_ms = (two, ew), ms
-            check(L.wm_gemm_set_variant(M, N, K, C.byref(ep), 0, best[0], best[1]), "wm_gemm_set_variant")
+                        best, best_ms = (two, ew, stg), ms
+            check(L.wm_gemm_set_variant(M, N, K, C.byref(ep), 0, *best), "wm_gemm_set_variant")
             chosen[name] = best
     return chosen
 
