@@ -867,11 +867,17 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     const int q = warp & 3;
     float* out = partial + static_cast<size_t>(split) * Nout * Kout;
-    const int row = n_blk * kBM + q * 32 + lane;
+    const int row0 = n_blk * kBM + q * 32;
     if (num_kb > 0) {
       mbar_wait(&tail->acc_full, 0, 24);
       tc_fence_after();
     }
+    // All MMAs are done, so the tile ring is free: the warp's 32 x BN fp32 block goes through it (row pitch
+    // BN * 4 + 16 bytes: an odd number of 16-byte units, conflict-free for lane = row) and leaves as coalesced
+    // 512-byte row segments. Thread-per-row float4 stores (32 lines per instruction) cost ~8 B/clk/SM -- 12k cycles
+    // for a 128 x 192 tile, against ~100k cycles of MMAs per work item.
+    const uint32_t pitch = static_cast<uint32_t>(BN) * 4u + 16u;
+    uint8_t* stage = smem + static_cast<uint32_t>(q) * 32u * pitch;
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
       if (num_kb > 0) {
@@ -881,17 +887,26 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0u;
       }
-      if (row < Nout) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int n = k_blk * BN + c0 + g * 4;
-          if (n < Kout)  // Kout % 4 == 0 (host-checked)
-            *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * Kout + n) =
-                make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
-                            __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
-        }
+      for (int g = 0; g < 8; ++g)
+        *reinterpret_cast<uint4*>(stage + lane * pitch + (c0 + g * 4) * 4) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+    }
+    __syncwarp();
+    {
+      const int u = BN >> 2;  // 16-byte units per row
+      const int q32 = 32 / u, m32u = 32 - q32 * u;
+      int r = lane / u, piece = lane - r * u;
+      for (int k = 0; k < u; ++k) {
+        const int n = k_blk * BN + piece * 4;
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + r * pitch + piece * 16);
+        if (row0 + r < Nout && n < Kout)  // Kout % 4 == 0 (host-checked)
+          *reinterpret_cast<uint4*>(out + static_cast<size_t>(row0 + r) * Kout + n) = val;
+        r += q32;
+        piece += m32u;
+        if (piece >= u) { piece -= u; ++r; }
       }
     }
+    const int row = row0 + lane;
     if (fuse_bias && k_blk == 0) {
       uint32_t v[16];
       if (num_kb > 0) {
