@@ -20,13 +20,13 @@ for N, K in [(2304, 576), (576, 576), (1728, 576), (576, 2304)]:
     a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
     w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
     bias = torch.zeros(N, device="cuda")
-    for ew in (8, 16):
-        lib().wm_set_option(b"gemm_two_cta", 0); lib().wm_set_option(b"gemm_epi_warps", ew)
+    for ew, stg in ((8, 0), (16, 0), (16, 1)):
+        lib().wm_set_option(b"gemm_two_cta", 0); lib().wm_set_option(b"gemm_epi_warps", ew); lib().wm_set_option(b"gemm_staged", stg)
         line = []
         for diag, label in ((0, "full"), (8, "compact stores"), (1, "no stores"), (2, "no math/stores"), (6, "no tmem ld")):
             assert lib().wm_set_option(b"gemm_diag", diag) == 0
             ms = t(lambda: ops.gemm_tn(a, w, bias=bias, relu=True))
             line.append(f"{label}: {ms:.4f} ms {2.0*M*N*K/ms/1e9:5.0f} TF")
         lib().wm_set_option(b"gemm_diag", 0)
-        print(f"N={N} K={K} epi_warps={ew:2d}  " + " | ".join(line), flush=True)
+        print(f"N={N} K={K} epi_warps={ew:2d} staged={stg}  " + " | ".join(line), flush=True)
 print("device_error", ops.device_error())

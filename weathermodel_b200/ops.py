@@ -147,7 +147,7 @@ def tune_gemm_sites(M, D, FF, dropout_p, device, min_tokens=8192, reps=5):
     _TUNED_SITES.add(key)
     L = lib()
     forced = os.environ.get("WM_OPTIONS", "")
-    if "gemm_" in forced:
+    if "gemm_" in forced or os.environ.get("WM_GEMM_TUNE", "1") == "0":  # forced variants / heuristic only
         return {}
     with torch.cuda.device(device):
         bf = lambda *shape: torch.zeros(*shape, dtype=BF16, device=device).normal_(0, 0.5)  # noqa: E731
