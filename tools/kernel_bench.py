@@ -79,9 +79,11 @@ def main():
         rec("layernorm_fwd", ms, bytes_=4.0 * M * D, per_layer=2 * L)
         y, mean, rstd = ops.layernorm_fwd(x, gamma, beta)
         ms = timeit(lambda: ops.layernorm_bwd(x, x, gamma, mean, rstd), a.reps)
-        rec("layernorm_bwd", ms, bytes_=6.0 * M * D, per_layer=2 * L)
+        rec("layernorm_bwd", ms, bytes_=6.0 * M * D, per_layer=0)
         ms = timeit(lambda: ops.layernorm_bwd(x, x, gamma, mean, rstd, dropout_p=0.1, seed=1, stream_id=1), a.reps)
-        rec("layernorm_bwd +dropout", ms, bytes_=8.0 * M * D, per_layer=2 * L)
+        rec("layernorm_bwd +dropout (with bias gradient, 8 row warps)", ms, bytes_=8.0 * M * D, per_layer=0)
+        ms = timeit(lambda: ops.layernorm_bwd(x, x, gamma, mean, rstd, dropout_p=0.1, seed=1, stream_id=1, want_bias_grad=False), a.reps)
+        rec("layernorm_bwd +dropout (encoder form, 15 row warps)", ms, bytes_=8.0 * M * D, per_layer=2 * L)
         ms = timeit(lambda: ops.colsum(h), a.reps)
         rec("colsum [M,FF]", ms, bytes_=2.0 * M * FF, per_layer=L)
         ms = timeit(lambda: ops.colsum(qkv), a.reps)

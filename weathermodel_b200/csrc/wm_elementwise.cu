@@ -318,9 +318,11 @@ int launch_layernorm_fwd(const __nv_bfloat16* x, const float* gamma, const float
 // at ~3.1 TB/s. The ring keeps up to 8 blocks x 2 tensors x 8 rows (147 KB at D = 576) in flight per SM.
 constexpr int kLnBwdCtas = 148 * 4;  // workspace bound (the kernel launches min(row blocks, SMs) CTAs)
 constexpr int kLnBwdMaxStages = 8;
-constexpr int kLnBwdThreads = 288;
-
-__global__ void __launch_bounds__(kLnBwdThreads, 1)
+// kBias: also accumulate the bias gradient of the producing linear (column sums of the bf16-rounded dx / dx_drop).
+// The encoder takes that gradient from the wgrad GEMM instead (its fused all-ones chunk), which frees 24 registers
+// per thread: 15 consumer warps (rows per block) fit instead of 8 -- the kernel is issue/latency-bound, so warps count.
+template <bool kBias, int kRows>
+__global__ void __launch_bounds__(32 * (kRows + 1), 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean,
                      const float* __restrict__ rstd, __nv_bfloat16* __restrict__ dx,
@@ -328,32 +330,33 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      DropKeys dkeys, float* __restrict__ partial, int stages) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const uint32_t row_bytes = static_cast<uint32_t>(D) * 2u;
-  const uint32_t tens_bytes = 8u * row_bytes;
+  const uint32_t tens_bytes = static_cast<uint32_t>(kRows) * row_bytes;
   const uint32_t stage_bytes = 2u * tens_bytes;  // [x rows | dy rows]
   uint8_t* ring = ln_smem;
-  float* sred = reinterpret_cast<float*>(ring + static_cast<size_t>(stages) * stage_bytes);  // [8 warps][3][D]
-  uint64_t* full = reinterpret_cast<uint64_t*>(sred + 8 * 3 * D);
+  constexpr int kSums = kBias ? 3 : 2;
+  float* sred = reinterpret_cast<float*>(ring + static_cast<size_t>(stages) * stage_bytes);  // [kRows warps][kSums][D]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sred + kRows * kSums * D);
   uint64_t* empty = full + stages;
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int nchunks = D >> 3;
-  const int nblk = (M + 7) >> 3;
+  const int nblk = (M + kRows - 1) / kRows;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 8);  // one arrive per consumer warp
+      mbar_init(&empty[s], kRows);  // one arrive per consumer warp
     }
     fence_barrier_init();
   }
   __syncthreads();
 
-  if (warp == 8) {
+  if (warp == kRows) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
       for (int b = blockIdx.x; b < nblk; b += gridDim.x) {
         mbar_wait(&empty[s], ph ^ 1u, 41);
-        const int r0 = b * 8;
-        const uint32_t bytes = static_cast<uint32_t>(min(8, M - r0)) * row_bytes;
+        const int r0 = b * kRows;
+        const uint32_t bytes = static_cast<uint32_t>(min(kRows, M - r0)) * row_bytes;
         uint8_t* dst = ring + static_cast<size_t>(s) * stage_bytes;
         mbar_arrive_expect_tx(&full[s], 2u * bytes);
         bulk_load_1d(dst, x + static_cast<size_t>(r0) * D, bytes, &full[s]);
@@ -378,14 +381,14 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     uint32_t ph = 0;
     float mu_n = 0.0f, rs_n = 0.0f;  // row statistics one block ahead
     {
-      const int r = blockIdx.x * 8 + warp;
+      const int r = blockIdx.x * kRows + warp;
       if (blockIdx.x < nblk && r < M) { mu_n = __ldg(mean + r); rs_n = __ldg(rstd + r); }
     }
     for (int b = blockIdx.x; b < nblk; b += gridDim.x) {
-      const int row = b * 8 + warp;
+      const int row = b * kRows + warp;
       const float mu = mu_n, rs = rs_n;
       {
-        const int rn = (b + static_cast<int>(gridDim.x)) * 8 + warp;
+        const int rn = (b + static_cast<int>(gridDim.x)) * kRows + warp;
         if (rn < M) { mu_n = __ldg(mean + rn); rs_n = __ldg(rstd + rn); }
       }
       mbar_wait(&full[s], ph, 42);
@@ -454,11 +457,13 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
           }
           // bias gradient of the producing linear sums what that linear's output actually received;
           // use the bf16-rounded values so it matches the wgrad operand exactly
-          const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+          if constexpr (kBias) {
+            const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            ad[i][2 * j] += bf16_lo(pw[j]);
-            ad[i][2 * j + 1] += bf16_hi(pw[j]);
+            for (int j = 0; j < 4; ++j) {
+              ad[i][2 * j] += bf16_lo(pw[j]);
+              ad[i][2 * j + 1] += bf16_hi(pw[j]);
+            }
           }
         }
       }
@@ -470,18 +475,18 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       if (c < nchunks) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          sred[(warp * 3 + 0) * D + c * 8 + j] = ag[i][j];
-          sred[(warp * 3 + 1) * D + c * 8 + j] = ab[i][j];
-          sred[(warp * 3 + 2) * D + c * 8 + j] = ad[i][j];
+          sred[(warp * kSums + 0) * D + c * 8 + j] = ag[i][j];
+          sred[(warp * kSums + 1) * D + c * 8 + j] = ab[i][j];
+          if constexpr (kBias) sred[(warp * kSums + 2) * D + c * 8 + j] = ad[i][j];
         }
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kSums * D; i += blockDim.x) {
     float sum = 0.0f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) sum += sred[w * 3 * D + i];
+    for (int w = 0; w < kRows; ++w) sum += sred[w * kSums * D + i];
     partial[static_cast<size_t>(blockIdx.x) * 3 * D + i] = sum;
   }
 }
@@ -494,12 +499,13 @@ ln_bwd_finalize_kernel(const float* __restrict__ partial, int ncta, int D, float
   const int i = blockIdx.x * 64 + (threadIdx.x & 63);
   const int q = threadIdx.x >> 6;
   const int per = (ncta + 3) >> 2;
+  const int nsum = dbias ? 3 : 2;  // without dbias the main kernel wrote only the first two [D] blocks of each partial
   float s = 0.0f;
-  if (i < 3 * D)
+  if (i < nsum * D)
     for (int c = q * per; c < min(ncta, (q + 1) * per); ++c) s += partial[static_cast<size_t>(c) * 3 * D + i];
   part[q][threadIdx.x & 63] = s;
   __syncthreads();
-  if (q == 0 && i < 3 * D) {
+  if (q == 0 && i < nsum * D) {
     const int t = threadIdx.x;
     const float sum = ((part[0][t] + part[1][t]) + part[2][t]) + part[3][t];
     const int k = i / D, col = i - k * D;
@@ -529,20 +535,22 @@ int launch_layernorm_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  int ctas = (M + 7) / 8;
+  const int rows = dbias ? 8 : 15;
+  const int nsum = dbias ? 3 : 2;
+  int ctas = (M + rows - 1) / rows;
   if (ctas > sms) ctas = sms;
   if (ctas > kLnBwdCtas) ctas = kLnBwdCtas;
-  const int stage_bytes = 2 * 8 * D * 2;
-  const int fixed = 8 * 3 * D * 4 + 2 * kLnBwdMaxStages * 8 + 128;
+  const int stage_bytes = 2 * rows * D * 2;
+  const int fixed = rows * nsum * D * 4 + 2 * kLnBwdMaxStages * 8 + 128;
   int stages = (227 * 1024 - fixed) / stage_bytes;
   if (stages > kLnBwdMaxStages) stages = kLnBwdMaxStages;
   if (stages < 2) return WM_ERR_SHAPE;
   const int smem = stages * stage_bytes + fixed;
-  if (cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-    return WM_ERR_CUDA;
   if (drop_thresh && static_cast<uint64_t>(M) * static_cast<uint64_t>((D + 15) / 16) * 4ull > 0xFFFFFFFFull) return WM_ERR_SHAPE;
-  layernorm_bwd_kernel<<<ctas, kLnBwdThreads, smem, stream>>>(dy, x, gamma, mean, rstd, dx, dx_drop, M, D, drop_thresh,
-                                                              drop_scale, drop_keys(seed, stream_id), workspace, stages);
+  auto kern = dbias ? layernorm_bwd_kernel<true, 8> : layernorm_bwd_kernel<false, 15>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
+  kern<<<ctas, 32 * (rows + 1), smem, stream>>>(dy, x, gamma, mean, rstd, dx, dx_drop, M, D, drop_thresh, drop_scale,
+                                                drop_keys(seed, stream_id), workspace, stages);
   WM_COUNT_LAUNCH();
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
   ln_bwd_finalize_kernel<<<(3 * D + 63) / 64, 256, 0, stream>>>(workspace, ctas, D, dgamma, dbeta, dbias);

@@ -263,14 +263,16 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dropout_p=0.0, seed=0, stream_id=0):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dropout_p=0.0, seed=0, stream_id=0, want_bias_grad=True):
+    """want_bias_grad=False is what the encoder uses (the bias gradient then comes from the wgrad GEMM): a leaner
+    instantiation of the kernel with 15 instead of 8 row warps per SM; dbias is returned as None."""
     _cuda(dy, x, gamma, mean, rstd)
     M, D = x.shape
     dx = torch.empty_like(x)
     dxd = torch.empty_like(x) if dropout_p > 0 else None
     dg = torch.empty(D, dtype=torch.float32, device=x.device)
     db = torch.empty(D, dtype=torch.float32, device=x.device)
-    dbias = torch.empty(D, dtype=torch.float32, device=x.device)
+    dbias = torch.empty(D, dtype=torch.float32, device=x.device) if want_bias_grad else None
     ws = torch.empty(lib().wm_layernorm_bwd_workspace_bytes(M, D) // 4, dtype=torch.float32, device=x.device)
     check(lib().wm_layernorm_bwd(_p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dxd), _p(dg), _p(db),
                                  _p(dbias), M, D, float(dropout_p), int(seed), int(stream_id), _p(ws), _stream()),
