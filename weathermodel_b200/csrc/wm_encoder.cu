@@ -390,16 +390,20 @@ int wm_encoder_backward_layers(wm_encoder* e, const float* params, int layer_hi,
   const float p = e->training ? c.dropout_p : 0.0f;
   const uint32_t thr = static_cast<uint32_t>(p * 65536.0f + 0.5f);
   const float dscale = drop_keep_scale(thr);  // the kernels round p to a multiple of 1/128
+  // d b2 / d b_o = column sums of the (dropout-masked) LayerNorm input gradients: taken from the wgrad GEMM of the
+  // same layer when its tile leaves room for the fused all-ones chunk (then the LayerNorm backward kernel runs its
+  // leaner 15-warp form), else accumulated by the LayerNorm backward kernel itself
+  const bool b2_from_wgrad = wgrad_fuses_bias(M, D, FF), bo_from_wgrad = wgrad_fuses_bias(M, D, D);
   for (int l = layer_hi - 1; l >= layer_lo; --l) {
     const LayerParams& q = e->lay.layers[l];
     LayerAct& a = e->act[l];
     __nv_bfloat16* gFd = thr ? e->gF : e->gR;  // gradient seen by the linear output (after dropout mask)
     // LN2 backward: gX -> gR (d r2), gF (dropout2-masked), d gamma2 / d beta2
     WM_TRY(launch_layernorm_bwd(e->gX, a.r2, params + q.g2, a.mean2, a.rstd2, e->gR, thr ? e->gF : nullptr,
-                                grads + q.g2, grads + q.be2, nullptr, M, D, thr, dscale, e->seed,
+                                grads + q.g2, grads + q.be2, b2_from_wgrad ? nullptr : grads + q.b2, M, D, thr, dscale, e->seed,
                                 stream_id(e->step, l, 3), e->scratch, st));
     // dW2 [D, FF] = gF^T h, d b2 = column sums of gF (fused all-ones chunk of the same GEMM)
-    WM_TRY(launch_gemm_wgrad(gFd, D, a.h, FF, M, D, FF, grads + q.w2, 0, e->scratch, grads + q.b2, st));
+    WM_TRY(launch_gemm_wgrad(gFd, D, a.h, FF, M, D, FF, grads + q.w2, 0, e->scratch, b2_from_wgrad ? grads + q.b2 : nullptr, st));
     {  // d h_pre = (gF W2) * [h > 0] / (1 - p)
       GemmEpilogue ep;
       ep.gate_bits = a.hbits;  // one bit per element instead of re-reading the 2-byte activation
@@ -419,9 +423,9 @@ int wm_encoder_backward_layers(wm_encoder* e, const float* params, int layer_hi,
     }
     // LN1 backward: gU -> gR (d r1), gF (dropout1-masked), d gamma1 / d beta1; d b_o from the wgrad below
     WM_TRY(launch_layernorm_bwd(e->gU, a.r1, params + q.g1, a.mean1, a.rstd1, e->gR, thr ? e->gF : nullptr,
-                                grads + q.g1, grads + q.be1, nullptr, M, D, thr, dscale, e->seed,
+                                grads + q.g1, grads + q.be1, bo_from_wgrad ? nullptr : grads + q.b_o, M, D, thr, dscale, e->seed,
                                 stream_id(e->step, l, 1), e->scratch, st));
-    WM_TRY(launch_gemm_wgrad(gFd, D, a.ctx, D, M, D, D, grads + q.w_o, 0, e->scratch, grads + q.b_o, st));
+    WM_TRY(launch_gemm_wgrad(gFd, D, a.ctx, D, M, D, D, grads + q.w_o, 0, e->scratch, bo_from_wgrad ? grads + q.b_o : nullptr, st));
     {  // d ctx = gF W_o
       GemmEpilogue ep;
       ep.out = e->gC;

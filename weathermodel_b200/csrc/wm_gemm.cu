@@ -670,7 +670,10 @@ int gemm_set_variant(int M, int N, int K, uint32_t sig, int two_cta, int epi_war
   return WM_OK;
 }
 static void gemm_pick_variant(int M, int N, int K, uint32_t sig, int* two_cta, int* epi_warps, int* staged) {
-  int two = (K >= 1024) ? 1 : 0, ew = (K >= 1024) ? 8 : 16, stg = (K >= 1024) ? 0 : 1;
+  // untuned sites: CTA pairs where the main loop dominates, 16 epilogue warps + staged stores where the epilogue does
+  // (measured on the D = 576 shapes; narrower models gain nothing from either and keep the plain variant)
+  const bool wide_model = N >= 512 && K >= 512;
+  int two = (wide_model && K >= 1024) ? 1 : 0, ew = (wide_model && K < 1024) ? 16 : 8, stg = (wide_model && K < 1024) ? 1 : 0;
   for (int i = 0; i < g_num_gemm_variants; ++i) {
     const GemmVariant& v = g_gemm_variants[i];
     if (v.M == M && v.N == N && v.K == K && v.sig == sig) {
@@ -986,6 +989,13 @@ int wgrad_plan(int Mtok, int Nout, int Kout, int* BN, int* splits, int* tok_per_
   *splits = (kb_total + kb_per - 1) / kb_per;
   *tok_per_split = kb_per * kBK;
   return tiles;
+}
+
+// true if launch_gemm_wgrad produces the bias gradient inside the GEMM (room for the all-ones chunk next to the tile)
+bool wgrad_fuses_bias(int Mtok, int Nout, int Kout) {
+  int bn, sp, tps;
+  wgrad_plan(Mtok, Nout, Kout, &bn, &sp, &tps);
+  return bn + 16 <= 256;
 }
 
 size_t wgrad_workspace_bytes(int Mtok, int Nout, int Kout) {

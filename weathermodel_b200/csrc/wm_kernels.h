@@ -57,6 +57,7 @@ int launch_gemm_wgrad_ex(const void* A, int lda, const void* B, int ldb, int Mto
                          int rows_valid, int cols_valid, int ld_dw, float* workspace, float* dbias,
                          cudaStream_t stream);
 size_t wgrad_workspace_bytes(int Mtok, int Nout, int Kout);
+bool wgrad_fuses_bias(int Mtok, int Nout, int Kout);
 // dbias (optional): column sums of A over the tokens = bias gradient of the layer whose output gradient A is
 int launch_gemm_wgrad(const void* A, int lda, const void* B, int ldb, int Mtok, int Nout, int Kout,
                       float* dW, int accumulate, float* workspace, float* dbias, cudaStream_t stream);

@@ -136,7 +136,7 @@ _TUNED_SITES = set()
 GEMM_VARIANTS = tuple((two, ew, st) for st in (0, 1) for two in (0, 1) for ew in (8, 16))  # (two_cta, epi_warps, staged stores); all bit-identical
 
 
-def tune_gemm_sites(M, D, FF, dropout_p, device, min_tokens=8192, reps=5):
+def tune_gemm_sites(M, D, FF, dropout_p, device, min_tokens=8192, reps=5, margin=0.03):
     """Time the (bit-identical) gemm_tn kernel variants on the eight GEMM call sites of one encoder layer --
     forward and dgrad, with the epilogues wm_encoder_forward / backward use -- on scratch operands of the real
     shapes, and record the fastest per site in the library (wm_gemm_set_variant). Runs once per (M, D, FF, dropout)
@@ -180,19 +180,22 @@ def tune_gemm_sites(M, D, FF, dropout_p, device, min_tokens=8192, reps=5):
                 check(L.wm_gemm_tn(_p(A), A.stride(0), _p(w), w.stride(0), M, N, K, C.byref(ep), _p(out), N, 0, 0,
                                    _stream()), "wm_gemm_tn (tuning)")
 
-            best, best_ms = None, float("inf")
+            times = {}
             for _ in range(2):  # two passes over the variants: the first also warms clocks and caches
-                for two, ew, stg in GEMM_VARIANTS:
-                    check(L.wm_gemm_set_variant(M, N, K, C.byref(ep), 0, two, ew, stg), "wm_gemm_set_variant")
+                for var in GEMM_VARIANTS:
+                    check(L.wm_gemm_set_variant(M, N, K, C.byref(ep), 0, *var), "wm_gemm_set_variant")
                     launch()
                     e0.record()
                     for _ in range(reps):
                         launch()
                     e1.record()
                     e1.synchronize()
-                    ms = e0.elapsed_time(e1) / reps
-                    if ms < best_ms:
-                        best, best_ms = (two, ew, stg), ms
+                    times[var] = min(times.get(var, float("inf")), e0.elapsed_time(e1) / reps)
+            # leave the plain variant unless another one is clearly (> 3 %) faster: timings of a kernel alone are
+            # noisy at the per-cent level on a power-capped GPU and do not carry over to the step below that
+            best = min(times, key=times.get)
+            if times[best] > (1.0 - margin) * times[GEMM_VARIANTS[0]]:
+                best = GEMM_VARIANTS[0]
             check(L.wm_gemm_set_variant(M, N, K, C.byref(ep), 0, *best), "wm_gemm_set_variant")
             chosen[name] = best
     return chosen
