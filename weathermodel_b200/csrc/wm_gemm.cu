@@ -295,7 +295,10 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
 template <typename OutT, int kAuxDepth>
 WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t* acc_full, uint32_t aph,
                                   uint32_t wait_code, uint32_t tbase, int row, int n_base, int cols_per, int M, int N,
-                                  bool wide, int lane, uint8_t* stage) {
+                                  bool wide, int lane, uint8_t* stage, uint64_t* acc_empty, uint32_t acc_empty_cluster) {
+  // acc_empty / acc_empty_cluster: the barrier that hands the accumulator stage back to the MMA warp (a local
+  // barrier, or the leader CTA's as a shared::cluster address when acc_empty is nullptr). It is released as soon as
+  // the last TMEM load has landed -- with staged stores that is before the tile is written out.
   // stage: this warp's 32 x (cols_per * 2 + 16)-byte staging tile or nullptr. Thread-per-row stores (32 bytes per
   // lane, rows a leading dimension apart) cost the LSU / L1 one line per lane: ~8 B/clk/SM, and with K = 576 they,
   // not the MMAs, set the pace (tools/gemm_diag.py: linear1 0.505 ms with, 0.359 ms without the stores). Staged, a
@@ -342,6 +345,12 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
 #ifdef WM_DIAG
   tmem_ld_wait();
 #endif
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) {
+    if (acc_empty) mbar_arrive(acc_empty);
+    else mbar_arrive_cluster(acc_empty_cluster);
+  }
   if constexpr (sizeof(OutT) == 2) {
     if (stage) {
       __syncwarp();
@@ -474,10 +483,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t tbase = tmem_base + as * kAccStride + half * cols_per + (static_cast<uint32_t>(q * 32) << 16);
       gemm_epilogue_tile<OutT, (kEW == 16 ? 2 : 4)>(ep, sbias, &tail->acc_full[as], aph, 14, tbase, m_blk * kBM + q * 32 + lane,
                                n_blk * BN + half * cols_per, cols_per, M, N, wide, lane,
-                               staged ? epi_stage + static_cast<uint32_t>(ew) * epi_stage_warp : nullptr);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tail->acc_empty[as]);
+                               staged ? epi_stage + static_cast<uint32_t>(ew) * epi_stage_warp : nullptr,
+                               &tail->acc_empty[as], 0u);
     }
   }
   tc_fence_before();
@@ -601,10 +608,8 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       gemm_epilogue_tile<OutT, (kEW == 16 ? 2 : 4)>(ep, sbias, &tail->acc_full[as], aph, 64, tbase,
                                m_blk * 2 * kBM + static_cast<int>(rank) * kBM + q * 32 + lane,
                                n_blk * BN + half * cols_per, cols_per, M, N, wide, lane,
-                               staged ? epi_stage + static_cast<uint32_t>(ew) * epi_stage_warp : nullptr);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(acc_empty_leader[as]);
+                               staged ? epi_stage + static_cast<uint32_t>(ew) * epi_stage_warp : nullptr,
+                               nullptr, acc_empty_leader[as]);
     }
   }
   __syncwarp();  // reconverge the single-lane role warps: barrier.cluster.*.aligned needs whole warps
