@@ -230,7 +230,8 @@ def test_mask_former_bit_exact(n, k):
 
 
 # ------------------------------------------------------------------------------------------ embedding
-@pytest.mark.parametrize("B,S,D", [(4, 365, 48), (3, 364, 200), (2, 365, 576), (1, 7, 336)])
+@pytest.mark.parametrize("B,S,D", [(4, 365, 48), (3, 364, 200), (2, 365, 576), (1, 7, 336),
+                                   (421, 365, 48)])  # the last one is large enough for the 256-token CTAs
 def test_embed_fwd(B, S, D):
     g = torch.Generator(device="cuda").manual_seed(0)
     w = torch.randn(B, S, 31, device="cuda", generator=g)

@@ -95,14 +95,16 @@ int launch_mask_former(uint64_t seed, uint64_t philox_offset, int grid_x, int n_
 // ------------------------------------------------------------------------------------------------
 // embed_fwd. CTA = 64 tokens x all D; rows of W_in staged in smem as [D][41] fp32.
 // ------------------------------------------------------------------------------------------------
-constexpr int kEmbTok = 64;  // tokens per CTA (the 34 x D weight matrix is staged once per CTA)
+// tokens per CTA: the 34 x D weight matrix is staged once per CTA (94 KB at D = 576), so long CTAs amortise it
+// (256 tokens: 0.74 -> 0.64 ms at the large shape); short ones keep small batches spread over all SMs
+constexpr int kEmbTokLong = 256, kEmbTokShort = 64;
 constexpr int kXinLd = 64;  // padded bf16 copy of the 34-channel input row (wgrad operand)
 
 __global__ void __launch_bounds__(768)
 embed_fwd_kernel(const float* __restrict__ weather, const uint8_t* __restrict__ mask, int64_t msb, int64_t mss,
                  const float* __restrict__ year, const float* __restrict__ coords,
                  const float* __restrict__ w_in, const float* __restrict__ b_in, const float* __restrict__ pe,
-                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ xin, int B, int S, int F, int D) {
+                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ xin, int B, int S, int F, int D, int kEmbTok) {
   extern __shared__ float smf[];
   const int Fin = F + 3;
   const int FinP = (Fin + 3) & ~3;
@@ -189,15 +191,19 @@ int launch_embed_fwd(const float* weather, const uint8_t* mask, int64_t msb, int
   if (B <= 0 || S <= 0 || F <= 0 || F + 3 > 40 || (D & 1)) return WM_ERR_SHAPE;
   const int64_t M = static_cast<int64_t>(B) * S;
   const int Fin = F + 3, FinP = (Fin + 3) & ~3;
-  const int smem = (41 * D + kEmbTok * FinP) * 4;
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tok = (M >= static_cast<int64_t>(kEmbTokLong) * 4 * (sms > 0 ? sms : 148)) ? kEmbTokLong : kEmbTokShort;
+  const int smem = (41 * D + tok * FinP) * 4;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return WM_ERR_CUDA;
-  const int blocks = static_cast<int>((M + kEmbTok - 1) / kEmbTok);
+  const int blocks = static_cast<int>((M + tok - 1) / tok);
   int threads = ((D + 31) / 32) * 32;  // one thread per output column
   if (threads > 768) threads = 768;
   embed_fwd_kernel<<<blocks, threads, smem, stream>>>(weather, mask, msb, mss, year, coords, w_in, b_in, pe, out,
-                                                      xin, B, S, F, D);
+                                                      xin, B, S, F, D, tok);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
