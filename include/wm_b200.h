@@ -118,7 +118,8 @@ int wm_layernorm_fwd(const void* x_bf16, const float* gamma, const float* beta, 
 size_t wm_layernorm_bwd_workspace_bytes(int M, int D);
 int wm_layernorm_bwd(const void* dy_bf16, const void* x_bf16, const float* gamma, const float* mean,
                      const float* rstd, void* dx_bf16, void* dx_dropped_bf16 /* NULL if p == 0 */, float* dgamma,
-                     float* dbeta, float* dbias /* optional: column sums of the (dropped) dx */, int M, int D,
+                     float* dbeta, float* dbias /* optional: column sums of the (dropped) dx; NULL selects a leaner
+                     kernel (15 instead of 8 row warps per SM) -- the encoder takes this gradient from wm_gemm_wgrad */, int M, int D,
                      float dropout_p, uint64_t seed, uint64_t stream_id, float* workspace, void* stream);
 size_t wm_colsum_workspace_bytes(int M, int N);
 int wm_colsum(const void* x_bf16, int ld, int M, int N, float* out, float* workspace, void* stream);
