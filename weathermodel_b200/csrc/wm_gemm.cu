@@ -951,6 +951,19 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   out[static_cast<size_t>(r) * ld_out + c] = acc;
 }
 
+// the same for full-width outputs whose rows are 16-byte aligned: one float4 per thread and split
+__global__ void wgrad_reduce4_kernel(const float4* __restrict__ partial, float4* __restrict__ out, int64_t n4_per_split,
+                                     int64_t n4_valid, int splits, int accumulate) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4_valid) return;
+  float4 acc = accumulate ? out[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = __ldg(partial + s * n4_per_split + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  out[i] = acc;
+}
+
 // Work items = output tiles x token splits, one per CTA, all the same size: pick the split count that fills whole
 // waves of SMs (the first plan used ceil(2 * SMs / tiles) and lost up to a third of the machine to a nearly empty
 // last wave: 300 items on 148 SMs = 3 waves at 68 %), with a mild preference for fewer partial tiles to reduce.
@@ -1037,9 +1050,18 @@ static int launch_gemm_wgrad_impl(const void* A, int lda, const void* B, int ldb
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
   const int64_t n = static_cast<int64_t>(rows_valid) * cols_valid;
   const int threads = 256;
-  const int blocks = static_cast<int>((n + threads - 1) / threads);
-  wgrad_reduce_kernel<<<blocks, threads, 0, stream>>>(workspace, dW, Nout, Kout, rows_valid, cols_valid, ld_dw,
-                                                      splits, accumulate);
+  if (cols_valid == Kout && ld_dw == Kout && (Kout & 3) == 0 && (reinterpret_cast<uintptr_t>(dW) & 15u) == 0 &&
+      (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0) {
+    // contiguous [rows_valid, Kout] block: same element order and summation order, four columns per thread
+    const int64_t n4 = n / 4;
+    wgrad_reduce4_kernel<<<static_cast<int>((n4 + threads - 1) / threads), threads, 0, stream>>>(
+        reinterpret_cast<const float4*>(workspace), reinterpret_cast<float4*>(dW),
+        static_cast<int64_t>(Nout) * Kout / 4, n4, splits, accumulate);
+  } else {
+    const int blocks = static_cast<int>((n + threads - 1) / threads);
+    wgrad_reduce_kernel<<<blocks, threads, 0, stream>>>(workspace, dW, Nout, Kout, rows_valid, cols_valid, ld_dw,
+                                                        splits, accumulate);
+  }
   WM_COUNT_LAUNCH();
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
   if (dbias) {
