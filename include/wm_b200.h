@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WM_B200_ABI_VERSION 1
+#define WM_B200_ABI_VERSION 2
 
 int wm_abi_version(void);
 const char* wm_strerror(int code);
@@ -138,6 +138,14 @@ int wm_loss_former(const float* y, int ldy, const float* weather, const uint8_t*
                    int64_t mask_stride_s, int B, int S, int F, float beta, float* scratch, float* loss_out,
                    void* dy_bf16, int lddy, float* mu_out /* optional [M,F] */, float* var_out /* optional */,
                    void* stream);
+/* The autograd backward of the two losses (torch: `loss.backward()` reaching MSELoss / the ELBO sum, same files):
+ * dy = grad_scale[0] * dLoss/dY from the partial sums an earlier wm_loss_* call (with dy_bf16 == NULL) left in
+ * `scratch`. grad_scale is a DEVICE scalar (the upstream gradient; NULL = 1): no host read-back, no fp32 copy of dy. */
+int wm_loss_bert_grad(const float* y, int ldy, const float* weather, const uint8_t* mask, int64_t M, int F,
+                      const float* scratch, const float* grad_scale, void* dy_bf16, int lddy, void* stream);
+int wm_loss_former_grad(const float* y, int ldy, const float* weather, const uint8_t* mask, int64_t mask_stride_b,
+                        int64_t mask_stride_s, int B, int S, int F, float beta, const float* scratch,
+                        const float* grad_scale, void* dy_bf16, int lddy, void* stream);
 
 /* ---- optimiser: torch.optim.Adam as built at src/base_trainer/base_trainer.py:337 ------------------- */
 int wm_adam_fused(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
@@ -152,6 +160,9 @@ typedef struct wm_encoder_config {
   int out_dim;      /* 31 (WeatherBERT) or 62 (WeatherFormer: mu | logvar) */
   float dropout_p;  /* 0.1 in the reference (nn.TransformerEncoderLayer default) */
   float ln_eps;     /* 1e-5 */
+  int eval_only;    /* 1: validation / inference handle (the reference's model.eval() + torch.no_grad(),
+                       src/base_trainer/base_trainer.py:262-285): workspace holds ONE layer of activations and no
+                       backward temporaries; wm_encoder_forward must be called with save_for_backward = 0 */
 } wm_encoder_config;
 typedef struct wm_encoder wm_encoder;
 
@@ -163,11 +174,14 @@ size_t wm_encoder_workspace_bytes(const wm_encoder_config* cfg);
 int wm_encoder_create(const wm_encoder_config* cfg, void* workspace, size_t workspace_bytes, wm_encoder** out);
 int wm_encoder_destroy(wm_encoder* enc);
 int wm_encoder_refresh_weights(wm_encoder* enc, const float* params, void* stream);
-/* y_out: fp32 [B*S, 32 or 64] (columns >= out_dim are padding) */
+/* y_out: fp32 [B*S, 32 or 64] (columns >= out_dim are padding). training: dropout live (nn.Module.train()).
+ * save_for_backward = 1 keeps every layer's activations for wm_encoder_backward_*; 0 is the lean schedule of a
+ * forward that no backward follows (torch.no_grad()): all layers reuse one set of buffers and nothing that only the
+ * backward pass reads is written; the backward entry points then return an error until the next saving forward. */
 int wm_encoder_forward(wm_encoder* enc, const float* params, const float* weather, const uint8_t* mask,
                        int64_t mask_stride_b, int64_t mask_stride_s, const float* year, const float* coords,
-                       const float* pos_encoding, float* y_out, int training, uint64_t seed, uint64_t step,
-                       void* stream);
+                       const float* pos_encoding, float* y_out, int training, int save_for_backward, uint64_t seed,
+                       uint64_t step, void* stream);
 int wm_encoder_backward_head(wm_encoder* enc, const void* dy_bf16, float* grads, void* stream);
 int wm_encoder_backward_layers(wm_encoder* enc, const float* params, int layer_hi, int layer_lo, float* grads,
                                void* stream);

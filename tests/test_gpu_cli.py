@@ -45,7 +45,10 @@ def test_pretraining_cli_dry_run(tmp_path, model, extra):
     if model == "weatherformer":
         assert set(js["losses"]["train"]) == {"total_loss", "reconstruction", "kl_term"}
     ckpt = torch.load(out_dir / (stem + "_latest_checkpoint.pth"), weights_only=False, map_location="cpu")
-    assert set(ckpt) == {"epoch", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict", "best_val_loss", "output_json"}
+    # the reference's keys plus one of ours (position of the dropout streams; the reference's loader ignores it)
+    assert set(ckpt) == {"epoch", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict", "best_val_loss", "output_json",
+                         "wm_dropout_steps"}
+    assert ckpt["wm_dropout_steps"] and ckpt["wm_dropout_steps"][0] > 0
     assert ckpt["epoch"] == 3 and "in_proj.weight" in ckpt["model_state_dict"]
     assert set(ckpt["optimizer_state_dict"]["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
     # resume from the checkpoint for one more epoch

@@ -170,7 +170,8 @@ def test_gemm_tn_epilogues():
     g2 = ops.gemm_tn(a, b, gate_bits=bits, gate_scale=1.25)
     assert torch.equal(g1, g2), "gate through sign bits differs from gate through the bf16 activation"
     assert ((h > 0) == (g2 != 0)).float().mean().item() > 0.999
-    # dropout: kept fraction ~ 1-p_eff, kept values scaled by 1/(1-p_eff) with p_eff = round(128 p)/128, identical across calls
+    # dropout: kept fraction ~ 1-p_eff, kept values scaled by 1/(1-p_eff) with p_eff = round(32768 p)/32768 (0.100006 for
+    # the reference's p = 0.1), identical across calls
     p = 0.1
     d1 = ops.gemm_tn(a, b, bias=bias, dropout_p=p, seed=11, stream_id=5, out_fp32=True)
     d2 = ops.gemm_tn(a, b, bias=bias, dropout_p=p, seed=11, stream_id=5, out_fp32=True)
@@ -178,10 +179,11 @@ def test_gemm_tn_epilogues():
     assert torch.equal(d1, d2), "dropout mask is not a pure function of (seed, stream, index)"
     kept = d1 != 0
     frac = kept.float().mean().item()
-    t7 = int(p * 128 + 0.5)
-    assert abs(frac - (1 - t7 / 128)) < 5e-3, f"kept fraction {frac}"
+    t15 = (int(p * 65536 + 0.5) + 1) >> 1
+    assert abs(t15 / 32768 - p) < 1e-5, "effective dropout probability must be the reference's to 1e-5"
+    assert abs(frac - (1 - t15 / 32768)) < 5e-3, f"kept fraction {frac}"
     assert (kept != (d3 != 0)).float().mean().item() > 0.1, "different stream ids give the same mask"
-    scale = 128.0 / (128 - t7)
+    scale = 32768.0 / (32768 - t15)
     _cmp("dropout kept values", d1[kept], ((acc + bias) * scale)[kept], 2e-3, 2e-3)
 
 
@@ -289,7 +291,7 @@ def test_layernorm_fwd_bwd(M, D):
         probe = ops.gemm_tn(ones_a, ones_b, bias=torch.ones(D, device="cuda"), dropout_p=p, seed=5, stream_id=9,
                             out_fp32=True)
         keep = probe != 0
-        scale = 128.0 / (128 - int(p * 128 + 0.5))
+        scale = 32768.0 / (32768 - ((int(p * 65536 + 0.5) + 1) >> 1))
         _cmp("ln dx_dropped", dxd2, torch.where(keep, dx.float() * scale, torch.zeros_like(probe)), 1e-2, 1e-3)
     _cmp("ln dbias dropped", dbias2, dxd2.double().sum(0), 1e-4, 1e-3)
     # the encoder's instantiation (no bias gradient, 15 row warps per SM) must give the same results bit for bit
@@ -321,6 +323,12 @@ def test_loss_bert():
     assert out[1].item() == mask.sum().item()
     _cmp("bert dy", dy[:, :F], yd.grad, 1e-2, 1e-9)
     assert (dy[:, F:] == 0).all()
+    # the autograd split: value now, gradient later, scaled by a DEVICE scalar (the upstream gradient of the loss)
+    out2, scratch = ops.loss_bert_value(y, w, mask)
+    assert torch.equal(out2, out)
+    assert torch.equal(ops.loss_bert_grad(y, w, mask, scratch, None, ld_grad=32), dy)
+    gs = torch.tensor(2.5, device="cuda")
+    _cmp("bert dy * 2.5", ops.loss_bert_grad(y, w, mask, scratch, gs, ld_grad=32)[:, :F], 2.5 * yd.grad, 1e-2, 1e-9)
 
 
 @pytest.mark.parametrize("expand", [False, True])
@@ -352,6 +360,12 @@ def test_loss_former(expand):
     _cmp("former var", var, var_r.detach(), 1e-6, 1e-12)
     _cmp("former dy", dy[:, :2 * F], yd.grad[:, :2 * F], 1e-2, 1e-9)
     assert (dy[:, 2 * F:] == 0).all()
+    out2, scratch = ops.loss_former_value(y, w, mask, beta)
+    assert torch.equal(out2, out)
+    assert torch.equal(ops.loss_former_grad(y, w, mask, beta, scratch, None, ld_grad=64), dy)
+    gs = torch.tensor(-0.75, device="cuda")
+    _cmp("former dy * -0.75", ops.loss_former_grad(y, w, mask, beta, scratch, gs, ld_grad=64)[:, :2 * F],
+         -0.75 * yd.grad[:, :2 * F], 1e-2, 1e-9)
 
 
 def test_adam_matches_torch():
@@ -413,33 +427,35 @@ def test_attention_fwd_bwd(B, S, H, dh):
 
 def _decode_keep_bits(words, B, S, H):
     """keep[b, h, q, k] from the word buffer attn_fwd writes: one uint32 per (query row, 32-key slice), laid out
-    [item][key tile (3)][query block of 64 (6)][slice in tile (4)][query row in block (64)], bit = key & 31."""
+    [item][key tile (3)][query block of 64 (6)][slice in tile (4)][query row in block (64)]; key k of the slice sits
+    at bit (k >> 1) + 16 * (k & 1) (csrc/wm_attn.cu: attn_keep_bit)."""
     w = words.view(B * H, 3, 6, 4, 64).to(torch.int64) & 0xFFFFFFFF
     q = torch.arange(S, device=words.device)
     k = torch.arange(S, device=words.device)
     sel = w[:, (k >> 7)[None, :], (q >> 6)[:, None], ((k >> 5) & 3)[None, :], (q & 63)[:, None]]  # [BH, S(q), S(k)]
-    keep = (sel >> (k & 31)[None, None, :]) & 1
+    kk = k & 31
+    keep = (sel >> ((kk >> 1) + 16 * (kk & 1))[None, None, :]) & 1
     return keep.bool().view(B, H, S, S)
 
 
 @pytest.mark.parametrize("B,S,H,dh", [(2, 365, 4, 12), (1, 150, 2, 36), (2, 365, 16, 36)])
 def test_attention_dropout_matches_torch_with_the_same_mask(B, S, H, dh):
     """Forward and backward with dropout against autograd of softmax(QK^T/sqrt(dh)) * keep / (1 - p_eff) @ V, with
-    `keep` decoded from the bits the forward kernel hands to the backward kernel (p_eff = round(128 p) / 128)."""
+    `keep` decoded from the bits the forward kernel hands to the backward kernel (p_eff = round(32768 p) / 32768)."""
     D = H * dh
     p = 0.1
     qkv = _bf(B * S, 3 * D, seed=30)
     dctx = _bf(B * S, D, seed=31)
     ctx, lse = ops.attn_fwd(qkv, B, S, H, dh, dropout_p=p, seed=5, stream_id=2)
     keep = _decode_keep_bits(ctx.drop_words, B, S, H)
-    t7 = int(p * 128 + 0.5)
+    t15 = (int(p * 65536 + 0.5) + 1) >> 1
     frac = keep.float().mean().item()
-    assert abs(frac - (1 - t7 / 128)) < 3e-3, f"keep fraction {frac}"
+    assert abs(frac - (1 - t15 / 32768)) < 2e-3, f"keep fraction {frac}"
     qd = qkv.double().requires_grad_(True)
     x = qd.view(B, S, 3, H, dh).permute(2, 0, 3, 1, 4)
     q, k, v = x[0], x[1], x[2]
     s = q @ k.transpose(-1, -2) / math.sqrt(dh)
-    pr = torch.softmax(s, dim=-1) * keep.double() * (128.0 / (128 - t7))
+    pr = torch.softmax(s, dim=-1) * keep.double() * (32768.0 / (32768 - t15))
     o = (pr @ v).permute(0, 2, 1, 3).reshape(B * S, D)
     _cmp("attn ctx (dropout)", ctx, o.detach(), 2e-2, 2e-2)
     _cmp("attn lse (dropout)", lse, torch.logsumexp(s, dim=-1).reshape(B * H, S).detach(), 1e-3, 1e-3)

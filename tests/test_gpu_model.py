@@ -56,9 +56,19 @@ def _check_losses(got, ref):
         assert abs(got[k] - r) <= min(1e-3 * total, 3e-3 * abs(r)), (k, got[k], r)
 
 
+def _record(line):
+    """Every measured parity figure goes to stdout (pytest -s) and, on the GPU box, into gpurun_out/ so that the
+    numbers behind the asserts are kept (the errors were never printed into a kept log)."""
+    print(line)
+    keep = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(keep):
+        with open(os.path.join(keep, "r02_test_parity.log"), "a") as fh:
+            fh.write(line + "\n")
+
+
 def _check_grads(model, ref_grads, tag):
-    tot_g, tot_r = 0.0, 0.0
-    worst = (0.0, "")
+    tot_g, tot_r, tot_d = 0.0, 0.0, 0.0
+    worst, worst_norm = (0.0, ""), (0.0, "")
     for name, p in model.named_parameters():
         assert p.grad is not None, f"{tag}: {name} has no gradient"
         g = p.grad.detach().float().cpu().numpy().astype(np.float64)
@@ -67,11 +77,18 @@ def _check_grads(model, ref_grads, tag):
         ng, nr = np.linalg.norm(g), np.linalg.norm(r)
         tot_g += ng ** 2
         tot_r += nr ** 2
+        tot_d += np.linalg.norm(g - r) ** 2
+        worst_norm = max(worst_norm, (abs(ng - nr) / (nr + 1e-30), name))
         assert abs(ng - nr) <= 5e-3 * nr + 1e-9, f"{tag}: ||grad {name}|| {ng:.6g} vs {nr:.6g}"
         rel = _rel(g, r)
         worst = max(worst, (rel, name))
         assert rel <= 3e-2, f"{tag}: grad {name} rel fro err {rel:.4g}"
-    assert abs(np.sqrt(tot_g) - np.sqrt(tot_r)) <= 3e-3 * np.sqrt(tot_r), f"{tag}: global grad norm"
+    gn = abs(np.sqrt(tot_g) - np.sqrt(tot_r)) / np.sqrt(tot_r)
+    gf = np.sqrt(tot_d / tot_r)
+    _record(f"{tag}: gradient rel fro worst {worst[0]:.3e} ({worst[1]}), norm err worst {worst_norm[0]:.3e} ({worst_norm[1]}), "
+            f"global rel fro {gf:.3e}, global norm err {gn:.3e}")
+    assert gn <= 3e-3, f"{tag}: global grad norm"
+    assert gf <= 2e-2, f"{tag}: global gradient field"
     return worst
 
 
@@ -190,6 +207,42 @@ def test_fused_adam_training_reduces_loss_and_matches_torch_adam():
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 6.0
 
 
+def test_fused_adam_restarts_like_torch_adam_after_loading_a_state_dict():
+    """load_state_dict must reset the flat step counter. Step 5 times, load (a) the empty initial state and
+    (b) the state after 2 steps, and compare the next update with torch.optim.Adam doing the same."""
+    torch.manual_seed(13)
+    hp = O.get_model_params("mini")
+    model = WeatherBERT(31, 31, torch.device(DEV), **hp).to(DEV).train()
+    _neutralise_dropout(model)
+    weather, coords, year, interval = (torch.from_numpy(a).to(DEV) for a in O.synthetic_batch(4, 365, seed=6))
+    mask = torch.rand(4, 365, 31, device=DEV) < 0.15
+    opt = FusedAdam(model.parameters(), lr=1e-3, runtime=model.runtime)
+    shadow = [p.detach().clone().requires_grad_(True) for p in model.parameters()]
+    ref = torch.optim.Adam(shadow, lr=1e-3)
+    import copy
+    states = {0: (copy.deepcopy(opt.state_dict()), copy.deepcopy(ref.state_dict()))}
+
+    def one_step():
+        opt.zero_grad()
+        engine.bert_masked_mse(model.forward_raw(weather, coords, year, interval, mask), weather, mask).backward()
+        for s_, p in zip(shadow, model.parameters()):
+            s_.grad = p.grad.detach().clone()
+        opt.step()
+        ref.step()
+
+    for k in range(5):
+        one_step()
+        if k == 1:
+            states[2] = (copy.deepcopy(opt.state_dict()), copy.deepcopy(ref.state_dict()))
+    for at in (0, 2):
+        opt.load_state_dict(states[at][0])
+        ref.load_state_dict(states[at][1])
+        one_step()
+        for s_, (n, p) in zip(shadow, model.named_parameters()):
+            assert torch.allclose(p.detach(), s_.detach(), rtol=1e-5, atol=1e-7), f"after reload at step {at}: {n}"
+        assert float(opt.state_dict()["state"][0]["step"]) == at + 1
+
+
 def test_dropout_training_mode_runs_and_is_replayable():
     torch.manual_seed(3)
     model = WeatherBERT(31, 31, torch.device(DEV), **O.get_model_params("small")).to(DEV).train()
@@ -239,3 +292,79 @@ def test_checkpoint_roundtrip_and_load_pretrained(tmp_path):
     assert mu.shape == (2, 365, 31) and (var > 0).all() and (var <= 1).all()
     with pytest.raises(ValueError):
         WeatherBERT(30, 30, torch.device(DEV), **hp).to(DEV).load_pretrained(again)
+
+
+def test_eval_forward_is_lean_and_matches_the_saving_forward():
+    """Validation path (reference: model.eval() + torch.no_grad(), base_trainer.py:262-285): the no-save schedule must
+    give bit-identical outputs to the saving one, from a handle whose workspace holds one layer of activations."""
+    import ctypes as C
+
+    from weathermodel_b200 import _lib
+
+    torch.manual_seed(21)
+    hp = O.get_model_params("small")
+    model = WeatherFormer(31, 31, torch.device(DEV), **hp).to(DEV).train()
+    _neutralise_dropout(model)
+    weather, coords, year, interval = (torch.from_numpy(a).to(DEV) for a in O.synthetic_batch(5, 365, seed=8))
+    mask = (torch.rand(5, 31, device=DEV) < 0.3).unsqueeze(1).expand(-1, 365, -1)
+    rt = model.runtime
+    with torch.no_grad():  # first use of this shape under no_grad: an eval-only handle
+        y_eval = model.forward_raw(weather, coords, year, interval, mask)
+    assert (5, 365, True) in rt._handles and (5, 365, False) not in rt._handles
+    ws_eval = rt.workspace.numel()
+    y_train = model.forward_raw(weather, coords, year, interval, mask)  # grad enabled: saving schedule, bigger workspace
+    assert y_train.requires_grad and (5, 365, False) in rt._handles
+    assert torch.equal(y_eval, y_train.detach())
+    cfg_t, cfg_e = rt._config(5, 365, False), rt._config(5, 365, True)
+    need_t = _lib.lib().wm_encoder_workspace_bytes(C.byref(cfg_t))
+    need_e = _lib.lib().wm_encoder_workspace_bytes(C.byref(cfg_e))
+    assert ws_eval >= need_e and need_e < 0.45 * need_t, (need_e, need_t)  # 4 layers: one set of activations instead of four + temporaries
+    model.eval()
+    with torch.no_grad():  # the training handle exists now: reused with the lean schedule
+        mu, var = model(weather, coords, year, interval, weather_feature_mask=mask)
+    assert torch.equal(mu, y_train.detach()[..., :31])
+    # backward after a lean forward on the same handle must be refused, not silently wrong
+    model.train()
+    y2 = model.forward_raw(weather, coords, year, interval, mask)
+    with torch.no_grad():
+        model.forward_raw(weather, coords, year, interval, mask)
+    with pytest.raises(RuntimeError):
+        engine.former_elbo(y2, weather, mask, 0.5)["total_loss"].backward()
+
+
+def test_backward_accumulates_without_zero_grad_and_mixes_with_torch_ops():
+    """ a second backward without zero_grad() adds to .grad like torch; and a loss that uses the head output
+    through the fused kernel AND through torch ops gets both gradient contributions."""
+    torch.manual_seed(22)
+    hp = O.get_model_params("mini")
+    model = WeatherBERT(31, 31, torch.device(DEV), **hp).to(DEV).train()
+    _neutralise_dropout(model)
+    weather, coords, year, interval = (torch.from_numpy(a).to(DEV) for a in O.synthetic_batch(4, 365, seed=9))
+    mask = torch.rand(4, 365, 31, device=DEV) < 0.15
+
+    def fused():
+        return engine.bert_masked_mse(model.forward_raw(weather, coords, year, interval, mask), weather, mask)
+
+    fused().backward()
+    g1 = {n: p.grad.clone() for n, p in model.named_parameters()}
+    fused().backward()  # no zero_grad in between
+    for n, p in model.named_parameters():
+        assert torch.allclose(p.grad, 2 * g1[n], rtol=1e-6, atol=1e-12), n
+    model.zero_grad()
+    y = model.forward_raw(weather, coords, year, interval, mask)
+    extra = 1e-3 * (y[..., :31] ** 2).mean()
+    (engine.bert_masked_mse(y, weather, mask) + extra).backward()
+    g_both = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.zero_grad()
+    y = model.forward_raw(weather, coords, year, interval, mask)
+    (1e-3 * (y[..., :31] ** 2).mean()).backward()
+    for n, p in model.named_parameters():
+        ref = g1[n] + p.grad
+        err = (g_both[n] - ref).norm() / (ref.norm() + 1e-30)
+        assert err < 2e-2, (n, err.item())  # two bf16 roundings of dy instead of one
+    # a scaled loss: the upstream gradient reaches the kernels as a device scalar
+    model.zero_grad()
+    (3.0 * fused()).backward()
+    for n, p in model.named_parameters():
+        err = (p.grad - 3 * g1[n]).norm() / (3 * g1[n]).norm()
+        assert err < 1e-2, (n, err.item())  # 3 * dy is rounded to bf16 at different points than dy

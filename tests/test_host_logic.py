@@ -220,3 +220,26 @@ def test_cli_module_is_runnable_with_dash_m(tmp_path):
     res = subprocess.run([sys.executable, "-m", "src.pretraining.pretraining_main", "--help"], cwd=tmp_path,
                          env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=120)
     assert res.returncode == 0 and "--n-masked-features" in res.stdout and "--beta" in res.stdout
+
+
+def test_lr_finder_matches_the_reference_rule():
+    """weathermodel_b200's find_optimal_lr against the learning rates the UNMODIFIED reference function returned for
+    the same loss curves (tests/golden/lr_finder.npz, written by oracle/make_golden_lr.py): steepest decline / 10,
+    floored at 10 * start_lr, iterator restarted when the loader runs out, optimiser LR restored."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from make_golden_lr import StubTrainer
+
+    from weathermodel_b200.base_trainer.find_optimal_lr import find_optimal_lr, select_lr
+
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "lr_finder.npz")))
+    keys = sorted({k.rsplit("/", 1)[0] for k in gold})
+    assert len(keys) >= 10
+    loader = [(torch.zeros(2, 1),)] * 7
+    for key in keys:
+        start_lr = float(key.split("/")[1])
+        tr = StubTrainer(gold[key + "/curve"])
+        lr = find_optimal_lr(tr, loader, start_lr=start_lr)
+        assert abs(lr - float(gold[key + "/lr"])) <= 1e-12 * max(1.0, abs(lr)), (key, lr, float(gold[key + "/lr"]))
+        assert tr.calls == int(gold[key + "/calls"]), (key, tr.calls)
+        assert tr.optimizer.param_groups[0]["lr"] == float(gold[key + "/restored_lr"]) == 123.0
+    assert select_lr([], [], 1e-4) == 1e-3  # nothing recorded: conservative default

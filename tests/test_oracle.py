@@ -143,33 +143,45 @@ def test_years_and_normalisation():
 
 
 def test_dropout_hash_statistics():
-    """The counter hash behind every dropout mask (csrc/wm_common.cuh: drop_hash32), restated in numpy: avalanche,
-    byte uniformity, keep rate and (absence of) correlation between neighbouring elements, words and streams."""
+    """The counter hash behind every dropout mask (csrc/wm_common.cuh: drop_hash64), restated in numpy: avalanche,
+    uniformity, the keep rate of the 15-bit compare for the reference's p = 0.1 and (absence of) correlation between
+    the four elements of a counter, neighbouring counters and streams."""
     m32 = np.uint64(0xFFFFFFFF)
 
-    def h32(x, k0, k1):
+    def fold(v):
+        return ((v >> np.uint64(32)) ^ (v & m32)) & m32
+
+    def h64(x, k0, k1, k2):
         x = x.astype(np.uint64)
-        p = ((x ^ np.uint64(k0)) & m32) * np.uint64(0x9E3779B1)
-        t = ((p >> np.uint64(32)) ^ (p & m32) ^ np.uint64(k1)) & m32
-        q = t * np.uint64(0x85EBCA77)
-        return (((q >> np.uint64(32)) ^ (q & m32)) & m32).astype(np.uint32)
+        hl = fold(((x ^ np.uint64(k0)) & m32) * np.uint64(0x9E3779B1))
+        a = fold(((hl ^ np.uint64(k1)) & m32) * np.uint64(0x85EBCA77))
+        b = fold(((hl ^ np.uint64(k2)) & m32) * np.uint64(0xC2B2AE3D))
+        return a.astype(np.uint32), b.astype(np.uint32)
 
     n = 1 << 18
     x = np.arange(n, dtype=np.uint32) + np.uint32(777)
-    k0, k1 = 0xA5A5F00D, 0x1234ABCD
-    r = h32(x, k0, k1)
-    for b in range(32):  # flipping any input bit flips every output bit about half of the time
-        d = r ^ h32(x ^ np.uint32(1 << b), k0, k1)
-        frac = np.unpackbits(d.view(np.uint8)).reshape(n, 32).mean(0)
-        assert frac.min() > 0.48 and frac.max() < 0.52, (b, frac.min(), frac.max())
-    by = r.view(np.uint8)
+    k0, k1, k2 = 0xA5A5F00D, 0x1234ABCD, 0x77AA1357
+    a, b = h64(x, k0, k1, k2)
+    for bit in range(32):  # flipping any input bit flips every output bit about half of the time
+        a2, b2 = h64(x ^ np.uint32(1 << bit), k0, k1, k2)
+        for r, r2 in ((a, a2), (b, b2)):
+            frac = np.unpackbits((r ^ r2).view(np.uint8)).reshape(n, 32).mean(0)
+            assert frac.min() > 0.48 and frac.max() < 0.52, (bit, frac.min(), frac.max())
+    by = np.concatenate([a, b]).view(np.uint8)
     hist = np.bincount(by, minlength=256)
     chi2 = ((hist - hist.mean()) ** 2 / hist.mean()).sum()
     assert chi2 < 340, chi2  # 255 degrees of freedom: 340 is the 0.9997 quantile
-    keep = ((by & 0x7F) >= 13).astype(np.float64)
-    assert abs(keep.mean() - (1 - 13 / 128)) < 2e-3
-    kc = keep - keep.mean()
-    for lag in (1, 4, 16, 64):
+    # the kernels' test: keep iff (half & 0x7FFF) >= thresh15, thresh15 = (round(65536 p) + 1) >> 1
+    t15 = (int(0.1 * 65536 + 0.5) + 1) >> 1
+    assert abs(t15 / 32768 - 0.1) < 1e-5  # the reference's nn.Dropout(0.1) to 1e-5 (round 1 trained at 13/128 = 0.1016)
+    fields = np.stack([a & 0x7FFF, (a >> 16) & 0x7FFF, b & 0x7FFF, (b >> 16) & 0x7FFF], 1).astype(np.int64)
+    keep = (fields >= t15).astype(np.float64)
+    assert np.abs(keep.mean(0) - (1 - t15 / 32768)).max() < 2.5e-3
+    assert np.abs(np.corrcoef(keep.T) - np.eye(4)).max() < 8e-3  # the four elements of one counter
+    flat = keep.reshape(-1)
+    kc = flat - flat.mean()
+    for lag in (1, 2, 4, 16, 64):
         assert abs((kc[:-lag] * kc[lag:]).mean() / kc.var()) < 6e-3, lag
-    other = ((h32(x, k0 ^ 0x9E3779B9, (k1 + 0x7F4A7C15) & 0xFFFFFFFF).view(np.uint8) & 0x7F) >= 13).astype(np.float64)
+    oa, ob = h64(x, k0 ^ 0x9E3779B9, (k1 + 0x7F4A7C15) & 0xFFFFFFFF, (k2 + 0x5851F42D) & 0xFFFFFFFF)
+    other = (np.stack([oa & 0x7FFF, (oa >> 16) & 0x7FFF, ob & 0x7FFF, (ob >> 16) & 0x7FFF], 1) >= t15).astype(np.float64).reshape(-1)
     assert abs(((other - other.mean()) * kc).mean() / np.sqrt(other.var() * kc.var())) < 6e-3

@@ -23,8 +23,11 @@ class GemmEpilogue(C.Structure):
 class EncoderConfig(C.Structure):
     _fields_ = [
         ("B", _i), ("S", _i), ("F", _i), ("D", _i), ("H", _i), ("L", _i), ("FF", _i), ("out_dim", _i),
-        ("dropout_p", _f), ("ln_eps", _f),
+        ("dropout_p", _f), ("ln_eps", _f), ("eval_only", _i),
     ]
+
+    def __init__(self, B=0, S=0, F=0, D=0, H=0, L=0, FF=0, out_dim=0, dropout_p=0.0, ln_eps=1e-5, eval_only=0):
+        super().__init__(B, S, F, D, H, L, FF, out_dim, dropout_p, ln_eps, eval_only)
 
 
 # name -> (restype, argtypes); kept in the order of include/wm_b200.h
@@ -56,6 +59,8 @@ SIGNATURES = {
     "wm_colsum": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "wm_loss_bert": (_i, [_vp, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp]),
     "wm_loss_former": (_i, [_vp, _i, _vp, _vp, _i64, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "wm_loss_bert_grad": (_i, [_vp, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp]),
+    "wm_loss_former_grad": (_i, [_vp, _i, _vp, _vp, _i64, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp]),
     "wm_adam_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "wm_encoder_param_count": (_i64, [C.POINTER(EncoderConfig)]),
     "wm_encoder_param_layout": (_i, [C.POINTER(EncoderConfig), C.POINTER(_i64), _i]),
@@ -63,7 +68,7 @@ SIGNATURES = {
     "wm_encoder_create": (_i, [C.POINTER(EncoderConfig), _vp, _sz, C.POINTER(_vp)]),
     "wm_encoder_destroy": (_i, [_vp]),
     "wm_encoder_refresh_weights": (_i, [_vp, _vp, _vp]),
-    "wm_encoder_forward": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i, _u64, _u64, _vp]),
+    "wm_encoder_forward": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i, _i, _u64, _u64, _vp]),
     "wm_encoder_backward_head": (_i, [_vp, _vp, _vp, _vp]),
     "wm_encoder_backward_layers": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "wm_encoder_backward_embed": (_i, [_vp, _vp, _vp]),
@@ -86,7 +91,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.wm_abi_version() != 1:
+        if handle.wm_abi_version() != 2:
             raise RuntimeError("libwm_b200.so ABI version mismatch")
         # WM_OPTIONS="name=value,..." applies wm_set_option tuning switches at load time (A/B measurements)
         for item in filter(None, os.environ.get("WM_OPTIONS", "").split(",")):

@@ -94,6 +94,9 @@ class BaseTrainer(ABC):
             "scheduler_state_dict": self.scheduler.state_dict(),
             "best_val_loss": self.best_val_loss,
             "output_json": self.output_json,
+            # extra key (ignored by the reference loader): position of the dropout streams, so that a resumed run does
+            # not replay the masks of its first steps
+            "wm_dropout_steps": [m.runtime.step_counter for m in net.modules() if hasattr(m, "runtime")],
         }
         stem = self.model_dir + self.get_model_name()
         numbered = [f"{stem}_epoch_{epoch}_checkpoint.pth", f"{stem}_epoch_{epoch}.pth"]
@@ -111,6 +114,9 @@ class BaseTrainer(ABC):
         self.start_epoch = ckpt["epoch"]
         self.best_val_loss = ckpt["best_val_loss"]
         self.output_json = ckpt["output_json"]
+        owners = [m for m in self._get_underlying_model().modules() if hasattr(m, "runtime")]
+        for m, steps in zip(owners, ckpt.get("wm_dropout_steps", [])):  # absent in reference-written checkpoints
+            m.runtime.step_counter = int(steps)
         if self.rank == 0:
             self.logger.info(f"Loaded checkpoint from {checkpoint_path}, resuming from epoch {self.start_epoch}")
 

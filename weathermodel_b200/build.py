@@ -49,5 +49,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines, verbose: bool = False) -> str:
+    """A/B build of the same sources with extra -D switches -> tools/_diag/libwm_b200_<name>.so (never the product
+    library; select it with WM_B200_LIB=... for one measurement)."""
+    out_dir = os.path.join(HERE, "..", "tools", "_diag")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.abspath(os.path.join(out_dir, f"libwm_b200_{name}.so"))
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + \
+        [os.path.join(CSRC, "wm_lib.cu"), "-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError(f"nvcc failed building {out}")
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a[2:] for a in sys.argv[i + 2:] if a.startswith("-D")], verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

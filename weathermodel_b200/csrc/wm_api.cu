@@ -10,7 +10,7 @@ inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline const __nv_bfloat16* CB(const void* p) { return reinterpret_cast<const __nv_bfloat16*>(p); }
 inline __nv_bfloat16* MB(void* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
 inline uint32_t thresh16(float p) { return p > 0.0f ? static_cast<uint32_t>(p * 65536.0f + 0.5f) : 0u; }
-inline float keep_scale(uint32_t t) { return wm::drop_keep_scale(t); }  // the kernels round p to a multiple of 1/128
+inline float keep_scale(uint32_t t) { return wm::drop_keep_scale(t); }  // the kernels compare 15 bits: p_eff = round(32768 p) / 32768
 }  // namespace
 
 extern "C" {
@@ -188,7 +188,13 @@ int wm_colsum(const void* x, int ld, int M, int N, float* out, float* workspace,
 int wm_loss_bert(const float* y, int ldy, const float* weather, const uint8_t* mask, int64_t M, int F,
                  float* scratch, float* loss_out, void* dy, int lddy, void* stream) {
   if (!y || !weather || !mask || !scratch || !loss_out) return WM_ERR_ARG;
-  return launch_loss_bert(y, ldy, weather, mask, M, F, scratch, loss_out, MB(dy), lddy, S_(stream));
+  return launch_loss_bert(y, ldy, weather, mask, M, F, scratch, loss_out, nullptr, MB(dy), lddy, S_(stream));
+}
+int wm_loss_bert_grad(const float* y, int ldy, const float* weather, const uint8_t* mask, int64_t M, int F,
+                      const float* scratch, const float* grad_scale, void* dy, int lddy, void* stream) {
+  if (!y || !weather || !mask || !scratch || !dy) return WM_ERR_ARG;
+  return launch_loss_bert(y, ldy, weather, mask, M, F, const_cast<float*>(scratch), nullptr, grad_scale, MB(dy), lddy,
+                          S_(stream));
 }
 int wm_loss_former(const float* y, int ldy, const float* weather, const uint8_t* mask, int64_t mask_stride_b,
                    int64_t mask_stride_s, int B, int S, int F, float beta, float* scratch, float* loss_out, void* dy,
@@ -196,7 +202,14 @@ int wm_loss_former(const float* y, int ldy, const float* weather, const uint8_t*
   if (!y || !weather || !mask || !scratch || !loss_out) return WM_ERR_ARG;
   if ((mu_out == nullptr) != (var_out == nullptr)) return WM_ERR_ARG;
   return launch_loss_former(y, ldy, weather, mask, mask_stride_b, mask_stride_s, B, S, F, beta, scratch, loss_out,
-                            MB(dy), lddy, mu_out, var_out, S_(stream));
+                            nullptr, MB(dy), lddy, mu_out, var_out, S_(stream));
+}
+int wm_loss_former_grad(const float* y, int ldy, const float* weather, const uint8_t* mask, int64_t mask_stride_b,
+                        int64_t mask_stride_s, int B, int S, int F, float beta, const float* scratch,
+                        const float* grad_scale, void* dy, int lddy, void* stream) {
+  if (!y || !weather || !mask || !scratch || !dy) return WM_ERR_ARG;
+  return launch_loss_former(y, ldy, weather, mask, mask_stride_b, mask_stride_s, B, S, F, beta,
+                            const_cast<float*>(scratch), nullptr, grad_scale, MB(dy), lddy, nullptr, nullptr, S_(stream));
 }
 
 int wm_adam_fused(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow, int64_t n,

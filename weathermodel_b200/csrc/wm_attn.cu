@@ -25,24 +25,28 @@ __host__ __device__ inline size_t attn_drop_word_index(int item, int j, int qblk
   return (((static_cast<size_t>(item) * 3 + j) * 6 + qblk) * 4 + slice_in_tile) * 64 + qrow;
 }
 
-// Dropout on attention probabilities: the shared counter hash of wm_common.cuh; one 32-bit word decides four
-// consecutive keys of one query row, a group of 16 keys is four consecutive words.
-WM_DEVICE void keep_flags16(DropKeys keys, uint32_t grp, uint32_t add4, uint32_t (&f)[4]) {
-#pragma unroll
-  for (int w = 0; w < 4; ++w) f[w] = drop_flags4(grp * 4u + w, keys, add4);
-}
-// 0xFFFF / 0x0000 in each half of the result: keep flags of elements j (low half) and j + 1 (high half), j even,
-// for masking a packed bf16x2 pair -- one PRMT in sign-replicate mode (selector nibble bit 3)
-WM_DEVICE uint32_t keep_pair_mask(uint32_t fword, uint32_t sel) {
+// Dropout on attention probabilities: the shared counter hash of wm_common.cuh; one counter decides four
+// consecutive keys of one query row (two flag words of two keys each), a group of 16 keys is four consecutive counters.
+// The forward kernel stores its decisions for the backward kernel as one 32-bit word per (query row, 32-key slice):
+// key k of the slice sits at bit attn_keep_bit(k) -- even keys in the low half, odd keys in the high half, the order
+// in which the packed bf16x2 pair masks yield them (one LOP3 per pair gathers two bits).
+__host__ __device__ constexpr int attn_keep_bit(int k) { return (k >> 1) + 16 * (k & 1); }
+// bf16x2 packing: cvt.rn.bf16x2.f32 runs at ~7.5 thread instructions per clock and SM on B200 (tools/mufubench.cu;
+// the exp2 of the same two elements costs as much again), the integer form -- round half away from zero by adding
+// 0x8000 to the bit patterns, then one PRMT taking the two upper halves -- moves that work to the ALU pipe.
+// -DWM_ATTN_INT_PACK=1 selects it for the P / dS tiles of both attention kernels (A/B: profiles/r02_attn_variants.txt).
+#ifndef WM_ATTN_INT_PACK
+#define WM_ATTN_INT_PACK 0
+#endif
+WM_DEVICE uint32_t attn_pack2(float lo, float hi) {
+#if WM_ATTN_INT_PACK
   uint32_t d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(fword), "r"(0u), "r"(sel));
+  asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(d) : "r"(__float_as_uint(lo) + 0x8000u), "r"(__float_as_uint(hi) + 0x8000u));
   return d;
+#else
+  return pack_bf16x2(lo, hi);
+#endif
 }
-#define WM_PAIR_SEL(j) ((((j) & 3) | 8u) * 0x11u | ((((j) & 3) + 1u) | 8u) * 0x1100u)
-#define WM_KEEP_PAIR(f, j) keep_pair_mask((f)[(j) >> 2], WM_PAIR_SEL(j))
-// pins a value in a register at this point of the instruction stream: without it the compiler sinks the (pure)
-// Philox arithmetic below the mbarrier wait it is supposed to overlap with
-#define WM_PIN(x) asm volatile("" : "+r"(x))
 
 // One warp copies a compact staging tile [nrows, 8 * pv bytes] from shared memory to global rows of pitch ld
 // (elements) with row-contiguous 8-byte pieces (head slices are only 8-byte aligned). Piece idx = lane + 32 k lives
@@ -131,7 +135,7 @@ template <int NCH, bool DROP>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ ctx,
                 float* __restrict__ lse_out, uint32_t* __restrict__ drop_words, int nitems, int S, int H, int dh,
-                float scale, uint32_t thresh7, float drop_scale, DropKeys dkeys) {
+                float scale, uint32_t thresh15, float drop_scale, DropKeys dkeys) {
   using G = AttnFwdGeom<NCH>;
   constexpr int DHP = G::DHP, KVB = G::KVB, KSTEPS = DHP / 16;
   constexpr bool kZeroTail = (NCH & 1) != 0;  // last k-step: second core-matrix column comes from the zero chunk
@@ -321,7 +325,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
     const int lq = warp & 3, sl = warp >> 2;   // TMEM lane quarter, 32-column slice of each chunk
     const int row = lq * 32 + lane;            // query row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(lq * 32) << 16;
-    const uint32_t thresh4 = (128u - thresh7) * 0x01010101u;  // per-byte addend of the 7-bit keep test
+    const uint32_t add2 = (0x8000u - thresh15) * 0x00010001u;  // per-half addend of the 15-bit keep test (drop_add2)
     const float c2 = scale * 1.4426950408889634f;
     uint32_t t = 0;
     for (int n = 0; n < nmine; ++n) {
@@ -337,7 +341,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
         mbar_wait(&bars.s_full, t & 1, 72);
         tc_fence_after();
         WM_FTICK(2);
-        // ---- pass 1: row max over this warp's slices (next chunk's TMEM load in flight under the reduction)
+        // ---- pass 1: row max over this warp's slices (next chunk's TMEM load in flight under the reduction);
+        // three-input maxima: 16 instead of 32 issue slots per 32 columns
         float mloc = -INFINITY;
         {
           uint32_t va[32], vb[32];
@@ -352,7 +357,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
               const int k0 = c * kKC + sl * 32;
               if (k0 + 32 <= S) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mloc = fmaxf(mloc, __uint_as_float(cur[j]));
+                for (int j = 0; j < 32; j += 2) mloc = fmax3(mloc, __uint_as_float(cur[j]), __uint_as_float(cur[j + 1]));
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
@@ -367,8 +372,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
         WM_FTICK(4);
         const float mrow = fmaxf(fmaxf(sMax[row], sMax[128 + row]), sMax[256 + row]);
         const float mneg = -mrow * c2;
-        // ---- pass 2: exp2, row sum, dropout; P (bf16 pairs) replaces the first 16 columns of the slice in TMEM
-        float lsum = 0.0f;
+        const uint64_t c2p = f2_pack(c2, c2), mnegp = f2_pack(mneg, mneg);
+        // ---- pass 2: exp2, row sum, dropout; P (bf16 pairs) replaces the first 16 columns of the slice in TMEM.
+        // Packed fp32 pairs: one FFMA2 scales and shifts two scores, one FADD2 adds two probabilities to the row sum.
+        uint64_t lsum2 = f2_pack(0.0f, 0.0f);
         {
           uint32_t va[32], vb[32];
           tmem_ld32(tS + lane_sel + sl * 32, va);
@@ -377,17 +384,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
             if (c < nkc) {
               uint32_t(&cur)[32] = (c & 1) ? vb : va;
               uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+              const int k0 = c * kKC + sl * 32;
               tmem_ld_wait();
               if (c + 1 < nkc) tmem_ld32(tS + lane_sel + (c + 1) * kKC + sl * 32, nxt);
-              const int k0 = c * kKC + sl * 32;
               uint32_t pk[16];
               if (k0 + 32 <= S) {
 #pragma unroll
                 for (int w = 0; w < 16; ++w) {
-                  const float e0 = fast_exp2(fmaf(__uint_as_float(cur[2 * w]), c2, mneg));
-                  const float e1 = fast_exp2(fmaf(__uint_as_float(cur[2 * w + 1]), c2, mneg));
-                  lsum += e0 + e1;
-                  pk[w] = pack_bf16x2(e0, e1);
+                  float x0f, x1f;
+                  f2_unpack(f2_fma(f2_pack_u(cur[2 * w], cur[2 * w + 1]), c2p, mnegp), x0f, x1f);
+                  const float e0 = fast_exp2(x0f), e1 = fast_exp2(x1f);
+                  lsum2 = f2_add(lsum2, f2_pack(e0, e1));
+                  pk[w] = attn_pack2(e0, e1);
                 }
               } else {
 #pragma unroll
@@ -395,27 +403,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
                   float e0 = 0.0f, e1 = 0.0f;
                   if (k0 + 2 * w < S) e0 = fast_exp2(fmaf(__uint_as_float(cur[2 * w]), c2, mneg));
                   if (k0 + 2 * w + 1 < S) e1 = fast_exp2(fmaf(__uint_as_float(cur[2 * w + 1]), c2, mneg));
-                  lsum += e0 + e1;
-                  pk[w] = pack_bf16x2(e0, e1);
+                  lsum2 = f2_add(lsum2, f2_pack(e0, e1));
+                  pk[w] = attn_pack2(e0, e1);
                 }
               }
-              if (DROP) {
-                uint32_t fa[4], fb[4];
-                keep_flags16(dkeys, rowbase + (k0 >> 4), thresh4, fa);
-                keep_flags16(dkeys, rowbase + (k0 >> 4) + 1, thresh4, fb);
+              if (DROP) {  // keep flags of the 32 keys: 8 counters, two flag words (= two bf16x2 pairs) each
+                const uint32_t x0 = (rowbase + static_cast<uint32_t>(k0 >> 4)) * 4u;
+                uint32_t bits = 0u;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) {
-                  pk[w] &= WM_KEEP_PAIR(fa, 2 * w);
-                  pk[w + 8] &= WM_KEEP_PAIR(fb, 2 * w);
+                  const DropWords f = drop_flags4(x0 + w, dkeys, add2);
+                  const uint32_t ma = drop_pair_mask(f.a), mb = drop_pair_mask(f.b);
+                  pk[2 * w] &= ma;
+                  pk[2 * w + 1] &= mb;
+                  // key 2i -> bit i, key 2i + 1 -> bit 16 + i (attn_keep_bit)
+                  bits |= (ma & (0x00010001u << (2 * w))) | (mb & (0x00010001u << (2 * w + 1)));
                 }
-                if (drop_words) {  // bit k = keep flag of key k0 + k: the backward kernel reads these instead of Philox
-                  uint32_t bits = 0u;
-#pragma unroll
-                  for (int w = 3; w >= 0; --w) bits = (bits << 4) | ((((fb[w] >> 7) & 0x01010101u) * 0x01020408u) >> 24);
-#pragma unroll
-                  for (int w = 3; w >= 0; --w) bits = (bits << 4) | ((((fa[w] >> 7) & 0x01010101u) * 0x01020408u) >> 24);
-                  drop_words[attn_drop_word_index(item, k0 >> 7, q >> 6, (k0 >> 5) & 3, q & 63)] = bits;
-                }
+                // the backward kernel reads these instead of re-deriving the hash in its transposed order
+                if (drop_words) drop_words[attn_drop_word_index(item, k0 >> 7, q >> 6, (k0 >> 5) & 3, q & 63)] = bits;
               }
               tmem_st16(tS + lane_sel + k0, pk);
               tmem_st_wait();
@@ -425,6 +430,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
               WM_FTICK(5 + c);
             }
           }
+        }
+        float lsum;
+        {
+          float l0, l1;
+          f2_unpack(lsum2, l0, l1);
+          lsum = l0 + l1;
         }
         sSum[sl * 128 + row] = lsum;
         named_bar_sync(1 + lq, 96);
@@ -517,14 +528,16 @@ struct AttnBwdGeom {
   static constexpr uint32_t SLOT = 2 * T64 + 1024;     // Q half-tile, dO half-tile, 4 x 64 dropout words
   static constexpr uint32_t DSB = 128 * 128 * 2;       // dS tile [16 q chunks][128 keys][16 B]
   static constexpr uint32_t OUTB = NCH * 8 * 2 * 128;  // staging tile (>= 128 * dh * 2)
-  static constexpr uint32_t STB = kSP * 8;             // per-row statistics of one head (float2)
+  static constexpr uint32_t STB = kSP * 8;             // per-row statistics of one head (two planes of kSP floats)
   static constexpr uint32_t kSmem = 4 * T128 + CS128 + RQ * SLOT + 2 * DSB + 5 * OUTB + 3 * STB + 2048 + 128;
 };
 
-// per (batch, head, query row): x = -lse * log2(e) + log2(drop_scale), y = (sum_d dO * O) * scale / drop_scale;
-// rows >= S are zero. One thread per (b, q, h); h runs fastest so a warp reads whole token rows.
+// per (batch, head): two planes of kSP floats, x[q] = -lse * log2(e) + log2(drop_scale) and
+// y[q] = -(sum_d dO * O) * scale / drop_scale; rows >= S are zero. Planes (not interleaved pairs) so that one 16-byte
+// shared-memory load in the backward kernel yields four consecutive x (or y): aligned register pairs for the packed
+// fp32 instructions. One thread per (b, q, h); h runs fastest so a warp reads whole token rows.
 __global__ void attn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
-                                      const float* __restrict__ lse, float2* __restrict__ stats, int B, int S, int H,
+                                      const float* __restrict__ lse, float* __restrict__ stats, int B, int S, int H,
                                       int dh, float scale, float drop_scale) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * kSP * H;
@@ -532,7 +545,7 @@ __global__ void attn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ ctx, con
   const int h = static_cast<int>(idx % H);
   const int q = static_cast<int>((idx / H) % kSP);
   const int b = static_cast<int>(idx / (static_cast<long long>(H) * kSP));
-  float2 out = make_float2(0.0f, 0.0f);
+  float ox = 0.0f, oy = 0.0f;
   if (q < S) {
     const size_t off = (static_cast<size_t>(b) * S + q) * (static_cast<size_t>(H) * dh) + static_cast<size_t>(h) * dh;
     const uint2* po = reinterpret_cast<const uint2*>(ctx + off);
@@ -545,16 +558,18 @@ __global__ void attn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ ctx, con
       acc = fmaf(bf16_lo(o.y), bf16_lo(d.y), acc);
       acc = fmaf(bf16_hi(o.y), bf16_hi(d.y), acc);
     }
-    out.x = -lse[(static_cast<size_t>(b) * H + h) * S + q] * 1.4426950408889634f + log2f(drop_scale);
-    out.y = acc * scale / drop_scale;
+    ox = -lse[(static_cast<size_t>(b) * H + h) * S + q] * 1.4426950408889634f + log2f(drop_scale);
+    oy = -acc * scale / drop_scale;
   }
-  stats[(static_cast<size_t>(b) * H + h) * kSP + q] = out;
+  float* base = stats + (static_cast<size_t>(b) * H + h) * (2 * kSP);
+  base[q] = ox;
+  base[kSP + q] = oy;
 }
 
 template <int NCH, bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
-                const __grid_constant__ CUtensorMap tm_do, const float2* __restrict__ stats,
+                const __grid_constant__ CUtensorMap tm_do, const float* __restrict__ stats,
                 const uint32_t* __restrict__ drop_words, __nv_bfloat16* __restrict__ dqkv, int nitems, int S, int H,
                 int dh, float scale, float clampv) {
   using G = AttnBwdGeom<NCH>;
@@ -634,7 +649,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
         tma_load_4d(sV + kb * G::T128, &tm_kv, &bars.kv_full[kb], 0, j * 128, (2 * D + col0) >> 3, b);
         if (j == 0) {
           mbar_arrive_expect_tx(&bars.st_full[n % 3], G::STB);
-          bulk_load_1d(sStat + (n % 3) * G::STB, stats + static_cast<size_t>(item) * kSP, G::STB, &bars.st_full[n % 3]);
+          bulk_load_1d(sStat + (n % 3) * G::STB, stats + static_cast<size_t>(item) * (2 * kSP), G::STB, &bars.st_full[n % 3]);
         }
       }
       __syncwarp();
@@ -791,6 +806,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
     const int krow = lq * 32 + lane;           // key row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(lq * 32) << 16;
     const float c2 = scale * 1.4426950408889634f;
+    const uint64_t c2p = f2_pack(c2, c2), scalep = f2_pack(scale, scale);
+    const uint32_t lanebit = 1u << attn_keep_bit(lane);  // this thread's key inside a keep word of the forward kernel
     // clampv = log2(drop_scale), computed on the host: log2f() in here put its zero / denormal special case (an FSEL
     // per element) into the inner loop
     const uint32_t tS = tmem + grp * 128 + lane_sel;
@@ -818,7 +835,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       const int n = J / nt, j = J - n * nt;
       const int slot = g % RQ;
       const int tb = (g >> 1) & 1;  // dS buffer of this query tile
-      const float2* st = reinterpret_cast<const float2*>(sStat + (n % 3) * G::STB) + ih * 64 + h2 * 32;
+      const float* stx = reinterpret_cast<const float*>(sStat + (n % 3) * G::STB) + ih * 64 + h2 * 32;  // -lse log2e + log2(drop_scale)
+      const float* sty = stx + kSP;                                                                      // -delta scale / drop_scale
       const uint32_t* mw = reinterpret_cast<const uint32_t*>(sRing + slot * G::SLOT + 2 * G::T64) + lq * 64 + h2 * 32;
       if (j == 0 && ih < 2) mbar_wait(&bars.st_full[n % 3], (n / 3) & 1, 88);
       mbar_wait(&bars.sdp_full[grp], (g >> 1) & 1, 89);
@@ -840,31 +858,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
 #pragma unroll
         for (int w4 = 0; w4 < 4; ++w4) {  // four query rows at a time: two 16-byte statistics loads, one of dropout words
           const int e0 = bt * 16 + w4 * 4;
-          const float4 sa = *reinterpret_cast<const float4*>(st + e0), sb = *reinterpret_cast<const float4*>(st + e0 + 2);
-          const float lx[4] = {sa.x, sa.z, sb.x, sb.z};  // -lse * log2e + log2(drop_scale)
-          const float dl[4] = {sa.y, sa.w, sb.y, sb.w};  // delta * scale / drop_scale
+          const float4 lx4 = *reinterpret_cast<const float4*>(stx + e0);
+          const float4 nd4 = *reinterpret_cast<const float4*>(sty + e0);
+          const float lx[4] = {lx4.x, lx4.y, lx4.z, lx4.w};
+          const float nd[4] = {nd4.x, nd4.y, nd4.z, nd4.w};
           uint32_t mword[4] = {0u, 0u, 0u, 0u};
           if (DROP) {
             const uint4 m4 = *reinterpret_cast<const uint4*>(mw + e0);
             mword[0] = m4.x; mword[1] = m4.y; mword[2] = m4.z; mword[3] = m4.w;
           }
-          float pp[4], dd[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float p = fast_exp2(fminf(fmaf(__uint_as_float(vs[w4 * 4 + u]), c2, lx[u]), clampv));
-            if (DROP) {
-              const uint32_t sm = static_cast<uint32_t>(static_cast<int32_t>(mword[u] << (31 - lane)) >> 31);
-              pp[u] = __uint_as_float(__float_as_uint(p) & sm);
-              dd[u] = p * fmaf(__uint_as_float(vd[w4 * 4 + u] & sm), scale, -dl[u]);
+          for (int hh = 0; hh < 2; ++hh) {  // packed fp32 pairs: query rows e0 + 2hh, e0 + 2hh + 1
+            const int i0 = w4 * 4 + 2 * hh;
+            float xa, xb;
+            f2_unpack(f2_fma(f2_pack_u(vs[i0], vs[i0 + 1]), c2p, f2_pack(lx[2 * hh], lx[2 * hh + 1])), xa, xb);
+            const float pa = fast_exp2(fminf(xa, clampv)), pb = fast_exp2(fminf(xb, clampv));
+            const uint64_t p2 = f2_pack(pa, pb);
+            const uint64_t nd2 = f2_pack(nd[2 * hh], nd[2 * hh + 1]);
+            const uint64_t vd2 = f2_pack_u(vd[i0], vd[i0 + 1]);
+            float da, db;
+            if (DROP) {  // dS = P (keep dP scale - delta) = (keep P) (dP scale) + P (-delta): one select per element
+              const float qa = (mword[2 * hh] & lanebit) ? pa : 0.0f, qb = (mword[2 * hh + 1] & lanebit) ? pb : 0.0f;
+              f2_unpack(f2_fma(f2_pack(qa, qb), f2_mul(vd2, scalep), f2_mul(p2, nd2)), da, db);
+              pk[w4 * 2 + hh] = attn_pack2(qa, qb);
             } else {
-              pp[u] = p;
-              dd[u] = p * fmaf(__uint_as_float(vd[w4 * 4 + u]), scale, -dl[u]);
+              f2_unpack(f2_mul(p2, f2_fma(vd2, scalep, nd2)), da, db);
+              pk[w4 * 2 + hh] = attn_pack2(pa, pb);
             }
+            dk[w4 * 2 + hh] = attn_pack2(da, db);
           }
-          pk[w4 * 2] = pack_bf16x2(pp[0], pp[1]);
-          pk[w4 * 2 + 1] = pack_bf16x2(pp[2], pp[3]);
-          dk[w4 * 2] = pack_bf16x2(dd[0], dd[1]);
-          dk[w4 * 2 + 1] = pack_bf16x2(dd[2], dd[3]);
         }
         tmem_st8(tS + h2 * 32 + bt * 8, pk);        // P^T: 16 query rows = 8 packed columns
         tmem_st8(tS + 64 + h2 * 32 + bt * 8, dk);   // dS^T
@@ -926,26 +948,26 @@ static int attn_chunks(int dh) { return (dh & 7) ? (dh + 4) / 8 : dh / 8; }
 
 template <int NCH>
 static int launch_fwd_t(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, uint32_t* drop_words, int B, int S,
-                        int H, int dh, float scale, uint32_t thresh7, float dscale, uint64_t seed, uint64_t stream_id,
+                        int H, int dh, float scale, uint32_t thresh15, float dscale, uint64_t seed, uint64_t stream_id,
                         cudaStream_t stream) {
   CUtensorMap tm;
   const int D = H * dh;
   int rc = make_tmap_bf16_rows3d(&tm, qkv, 3 * D, S, B, 3 * D, 128);
   if (rc != WM_OK) return rc;
   const int smem = AttnFwdGeom<NCH>::kSmem;
-  auto kern = thresh7 ? attn_fwd_kernel<NCH, true> : attn_fwd_kernel<NCH, false>;
+  auto kern = thresh15 ? attn_fwd_kernel<NCH, true> : attn_fwd_kernel<NCH, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
   const int nitems = B * H;
   const int grid = nitems < attn_sm_count() ? nitems : attn_sm_count();
-  if (thresh7 && static_cast<uint64_t>(nitems) * S * ((S + 15) / 16) * 4ull > 0xFFFFFFFFull) return WM_ERR_SHAPE;  // 32-bit mask counters
-  kern<<<grid, kFwdThreads, smem, stream>>>(tm, ctx, lse, drop_words, nitems, S, H, dh, scale, thresh7, dscale,
+  if (thresh15 && static_cast<uint64_t>(nitems) * S * ((S + 15) / 16) * 4ull > 0xFFFFFFFFull) return WM_ERR_SHAPE;  // 32-bit mask counters
+  kern<<<grid, kFwdThreads, smem, stream>>>(tm, ctx, lse, drop_words, nitems, S, H, dh, scale, thresh15, dscale,
                                             drop_keys(seed, stream_id));
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 template <int NCH>
 static int launch_bwd_t(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __nv_bfloat16* dctx,
-                        const float* lse, __nv_bfloat16* dqkv, const uint32_t* drop_words, float2* stats, int B, int S,
+                        const float* lse, __nv_bfloat16* dqkv, const uint32_t* drop_words, float* stats, int B, int S,
                         int H, int dh, float scale, bool drop, float dscale, cudaStream_t stream) {
   const int D = H * dh;
   CUtensorMap tm_kv, tm_q, tm_do;
@@ -970,9 +992,9 @@ static int launch_bwd_t(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, cons
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
-// drop_thresh is the 16-bit threshold used everywhere else (round(p*65536)); attention rounds it to 7 bits
-static void attn_drop_params(uint32_t drop_thresh16, uint32_t* thresh7, float* scale) {
-  *thresh7 = drop_thresh7(drop_thresh16);
+// drop_thresh is the 16-bit threshold of the C ABI (round(p*65536)); every kernel compares 15 bits (wm_common.cuh)
+static void attn_drop_params(uint32_t drop_thresh16, uint32_t* thresh15, float* scale) {
+  *thresh15 = drop_thresh15(drop_thresh16);
   *scale = drop_keep_scale(drop_thresh16);
 }
 // TMA needs 16-byte aligned row pitches and head-block starts: D = H * dh a multiple of 8
@@ -992,16 +1014,16 @@ size_t attn_bwd_workspace_bytes(int B, int S, int H) {
 int launch_attn_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* lse, uint32_t* drop_words, int B, int S, int H,
                     int dh, uint32_t drop_thresh, uint64_t seed, uint64_t stream_id, cudaStream_t stream) {
   if (!attn_shape_ok(B, S, H, dh)) return WM_ERR_SHAPE;
-  uint32_t t7;
+  uint32_t t15;
   float ds;
-  attn_drop_params(drop_thresh, &t7, &ds);
+  attn_drop_params(drop_thresh, &t15, &ds);
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
   switch (attn_chunks(dh)) {
-    case 2: return launch_fwd_t<2>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t7, ds, seed, stream_id, stream);
-    case 3: return launch_fwd_t<3>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t7, ds, seed, stream_id, stream);
-    case 4: return launch_fwd_t<4>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t7, ds, seed, stream_id, stream);
-    case 5: return launch_fwd_t<5>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t7, ds, seed, stream_id, stream);
-    case 6: return launch_fwd_t<6>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t7, ds, seed, stream_id, stream);
+    case 2: return launch_fwd_t<2>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t15, ds, seed, stream_id, stream);
+    case 3: return launch_fwd_t<3>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t15, ds, seed, stream_id, stream);
+    case 4: return launch_fwd_t<4>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t15, ds, seed, stream_id, stream);
+    case 5: return launch_fwd_t<5>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t15, ds, seed, stream_id, stream);
+    case 6: return launch_fwd_t<6>(qkv, ctx, lse, drop_words, B, S, H, dh, scale, t15, ds, seed, stream_id, stream);
     default: return WM_ERR_SHAPE;
   }
 }
@@ -1012,19 +1034,19 @@ int launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __
                     __nv_bfloat16* dqkv, const uint32_t* drop_words, void* workspace, int B, int S, int H, int dh,
                     uint32_t drop_thresh, cudaStream_t stream) {
   if (!attn_shape_ok(B, S, H, dh)) return WM_ERR_SHAPE;
-  uint32_t t7;
+  uint32_t t15;
   float ds;
-  attn_drop_params(drop_thresh, &t7, &ds);
-  if (!workspace || (t7 && !drop_words)) return WM_ERR_ARG;
+  attn_drop_params(drop_thresh, &t15, &ds);
+  if (!workspace || (t15 && !drop_words)) return WM_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(workspace) & 15u) || (reinterpret_cast<uintptr_t>(drop_words) & 15u)) return WM_ERR_ALIGN;
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
-  float2* st = static_cast<float2*>(workspace);
+  float* st = static_cast<float*>(workspace);
   switch (attn_chunks(dh)) {
-    case 2: return launch_bwd_t<2>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t7 != 0, ds, stream);
-    case 3: return launch_bwd_t<3>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t7 != 0, ds, stream);
-    case 4: return launch_bwd_t<4>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t7 != 0, ds, stream);
-    case 5: return launch_bwd_t<5>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t7 != 0, ds, stream);
-    case 6: return launch_bwd_t<6>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t7 != 0, ds, stream);
+    case 2: return launch_bwd_t<2>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t15 != 0, ds, stream);
+    case 3: return launch_bwd_t<3>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t15 != 0, ds, stream);
+    case 4: return launch_bwd_t<4>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t15 != 0, ds, stream);
+    case 5: return launch_bwd_t<5>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t15 != 0, ds, stream);
+    case 6: return launch_bwd_t<6>(qkv, ctx, dctx, lse, dqkv, drop_words, st, B, S, H, dh, scale, t15 != 0, ds, stream);
     default: return WM_ERR_SHAPE;
   }
 }

@@ -447,46 +447,66 @@ __host__ __device__ inline float curand_uniform_from_u32(uint32_t x) {
 }
 
 // Dropout masks. Nothing here has to reproduce torch's stream (only the INPUT masks replay curand Philox, above), so
-// the keep decisions come from a much cheaper counter-based hash: two rounds of "multiply 32 x 32 -> 64, fold the
-// halves" keyed by two words derived from (seed, stream). Philox4x32-7 cost ~12 issue slots per element in the
-// attention forward kernel -- more than the softmax itself (ncu instruction mix, profiles/r01_attn_ncu_mix.txt);
-// this is ~1.5. Measured on 2^20 consecutive counters (tests/test_oracle.py): every input bit flips every output
-// bit with probability 0.498-0.503, byte histogram chi^2 = 234 (255 dof), keep decisions of neighbouring
-// elements / words / streams correlate below 1e-3.
-// One 32-bit word decides FOUR elements, one byte each: keep iff (byte & 0x7F) >= thresh7, thresh7 = round(128 p),
-// so the effective drop probability is thresh7 / 128 (0.1016 for p = 0.1) and the scale 128 / (128 - thresh7).
-// Element e of a row of N elements: word ((row * ceil(N/16) + e/16) * 4 + (e%16)/4), byte e%4 -- the GEMM epilogue,
-// LayerNorm backward and the attention kernels all use this numbering, so a mask can be regenerated anywhere.
+// the keep decisions come from a much cheaper counter-based hash: rounds of "multiply 32 x 32 -> 64, fold the
+// halves" keyed by words derived from (seed, stream). Philox4x32-7 cost ~12 issue slots per element in the
+// attention forward kernel -- more than the softmax itself (ncu instruction mix, profiles/r01_attn_ncu_mix.txt).
+// One counter x decides FOUR elements with 15-bit resolution each: the first round gives t(x); two second-round
+// products of t under different keys give two well-mixed 32-bit words A, B; element 0 / 1 = low / high half of A,
+// element 2 / 3 = low / high half of B. keep iff (half & 0x7FFF) >= thresh15, thresh15 = round(32768 p): the drop
+// probability is thresh15 / 32768 (0.100006 for p = 0.1, the reference's nn.Dropout(0.1); round 1 compared 7 bits
+// and trained at 0.1016) and the keep scale 32768 / (32768 - thresh15). Measured on 2^18 consecutive counters
+// (tests/test_oracle.py): every input bit flips every output bit with probability 0.48-0.52, keep decisions of
+// neighbouring elements / words / streams correlate below 6e-3.
+// Element e of a row of N elements: counter (row * ceil(N/16) + e/16) * 4 + (e%16)/4, element e%4 of it -- the GEMM
+// epilogue, LayerNorm backward and the attention kernels all use this numbering, so a mask can be regenerated anywhere.
 struct DropKeys {
-  uint32_t k0, k1;
+  uint32_t k0, k1, k2;
 };
 __host__ __device__ inline DropKeys drop_keys(uint64_t seed, uint64_t stream) {  // splitmix64 finaliser
   uint64_t z = seed + (stream + 1) * 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   z ^= z >> 31;
-  return DropKeys{static_cast<uint32_t>(z), static_cast<uint32_t>(z >> 32)};
+  const uint32_t a = static_cast<uint32_t>(z), b = static_cast<uint32_t>(z >> 32);
+  return DropKeys{a, b, (b ^ 0x68E31DA4u) + a * 0x2545F491u};
 }
-__host__ __device__ inline uint32_t drop_hash32(uint32_t x, DropKeys k) {
+struct DropWords {
+  uint32_t a, b;  // a: elements 0 (bits 0-15) and 1 (bits 16-31) of the counter; b: elements 2 and 3
+};
+__host__ __device__ inline DropWords drop_hash64(uint32_t x, DropKeys k) {
   const uint64_t p = static_cast<uint64_t>(x ^ k.k0) * 0x9E3779B1u;
-  const uint32_t t = static_cast<uint32_t>(p >> 32) ^ static_cast<uint32_t>(p) ^ k.k1;
-  const uint64_t q = static_cast<uint64_t>(t) * 0x85EBCA77u;
-  return static_cast<uint32_t>(q >> 32) ^ static_cast<uint32_t>(q);
+  const uint32_t hl = static_cast<uint32_t>(p >> 32) ^ static_cast<uint32_t>(p);
+  const uint64_t q = static_cast<uint64_t>(hl ^ k.k1) * 0x85EBCA77u;
+  const uint64_t r = static_cast<uint64_t>(hl ^ k.k2) * 0xC2B2AE3Du;
+  return DropWords{static_cast<uint32_t>(q >> 32) ^ static_cast<uint32_t>(q),
+                   static_cast<uint32_t>(r >> 32) ^ static_cast<uint32_t>(r)};
 }
-// bit 7 of byte b = keep flag of element b of the word (the other bits are noise): adding (128 - thresh7) to a 7-bit
-// value carries into bit 7 exactly when it is >= thresh7, and no carry crosses a byte. add4 = (128 - thresh7) * 0x01010101
-WM_DEVICE uint32_t drop_flags4(uint32_t x, DropKeys k, uint32_t add4) { return (drop_hash32(x, k) & 0x7F7F7F7Fu) + add4; }
-// all-ones / all-zeros 32-bit mask from the flag of byte b: one PRMT in sign-replicate mode
-template <int B>
-WM_DEVICE uint32_t drop_mask32(uint32_t flags) {
+__host__ __device__ inline uint32_t drop_thresh15(uint32_t thresh16) { return (thresh16 + 1u) >> 1; }
+__host__ __device__ inline float drop_keep_scale(uint32_t thresh16) {
+  const uint32_t t = drop_thresh15(thresh16);
+  return t ? 32768.0f / static_cast<float>(32768u - t) : 1.0f;
+}
+// per-half addend of the keep test: (half & 0x7FFF) + (0x8000 - thresh15) carries into bit 15 exactly when the
+// 15-bit value is >= thresh15, and no carry crosses a half
+__host__ __device__ inline uint32_t drop_add2(uint32_t thresh16) { return (0x8000u - drop_thresh15(thresh16)) * 0x00010001u; }
+// bit 15 / 31 of .a = keep flags of elements 0 / 1, of .b = elements 2 / 3 (the other bits are noise)
+WM_DEVICE DropWords drop_flags4(uint32_t x, DropKeys k, uint32_t add2) {
+  const DropWords h = drop_hash64(x, k);
+  return DropWords{(h.a & 0x7FFF7FFFu) + add2, (h.b & 0x7FFF7FFFu) + add2};
+}
+// all-ones / all-zeros 32-bit mask from the flag of element E (0..3) of the counter: one PRMT in sign-replicate mode
+template <int E>
+WM_DEVICE uint32_t drop_mask32(const DropWords& f) {
   uint32_t d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(flags), "r"(0u), "r"((B | 8u) * 0x1111u));
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"((E & 2) ? f.b : f.a), "r"(0u), "r"((((E & 1) ? 3u : 1u) | 8u) * 0x1111u));
   return d;
 }
-__host__ __device__ inline uint32_t drop_thresh7(uint32_t thresh16) { return (thresh16 + 256u) >> 9; }
-__host__ __device__ inline float drop_keep_scale(uint32_t thresh16) {
-  const uint32_t t7 = drop_thresh7(thresh16);
-  return t7 ? 128.0f / static_cast<float>(128u - t7) : 1.0f;
+// 0xFFFF / 0x0000 in each half of the result: the keep flags of the two elements of one flag word, for masking a
+// packed bf16x2 pair
+WM_DEVICE uint32_t drop_pair_mask(uint32_t fword) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(fword), "r"(0u), "r"(0xBB99u));
+  return d;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -513,6 +533,40 @@ WM_DEVICE void stg256(void* p, const uint4& lo, const uint4& hi) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z),
                "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
                : "memory");
+}
+// Packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 work on an aligned register pair, one issue slot for two
+// elements) and the three-input maximum (FMNMX3). The softmax loops of the attention kernels are issue-bound, so
+// halving the slots of their FMAs / adds is a direct gain.
+WM_DEVICE uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+WM_DEVICE uint64_t f2_pack_u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+WM_DEVICE void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+WM_DEVICE uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+WM_DEVICE uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+WM_DEVICE uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+WM_DEVICE float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 WM_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);

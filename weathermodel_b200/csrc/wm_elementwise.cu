@@ -453,11 +453,11 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
           pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
           reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * D)[c] = pk;
           if (drop_thresh) {  // the mask the GEMM epilogue drew for these 8 columns: two words of the 16-column group
-            const uint32_t add4 = (128u - drop_thresh7(drop_thresh)) * 0x01010101u;
+            const uint32_t add2 = drop_add2(drop_thresh);
             const uint32_t x0 = (static_cast<uint32_t>(row) * static_cast<uint32_t>((D + 15) >> 4) + static_cast<uint32_t>(c >> 1)) * 4u + 2u * (c & 1);
 #pragma unroll
             for (int w = 0; w < 2; ++w) {
-              const uint32_t fl = drop_flags4(x0 + w, dkeys, add4);
+              const DropWords fl = drop_flags4(x0 + w, dkeys, add2);
               o[4 * w] = __uint_as_float(__float_as_uint(o[4 * w] * drop_scale) & drop_mask32<0>(fl));
               o[4 * w + 1] = __uint_as_float(__float_as_uint(o[4 * w + 1] * drop_scale) & drop_mask32<1>(fl));
               o[4 * w + 2] = __uint_as_float(__float_as_uint(o[4 * w + 2] * drop_scale) & drop_mask32<2>(fl));
@@ -695,16 +695,18 @@ loss_bert_partial_kernel(const float* __restrict__ y, int ldy, const float* __re
 __global__ void __launch_bounds__(256)
 loss_bert_grad_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ weather,
                       const uint8_t* __restrict__ mask, int64_t M, int F, const float* __restrict__ scratch,
-                      int nctas, float* __restrict__ loss_out, __nv_bfloat16* __restrict__ dy, int lddy) {
+                      int nctas, float* __restrict__ loss_out, const float* __restrict__ gscale,
+                      __nv_bfloat16* __restrict__ dy, int lddy) {
   __shared__ float sbuf[32];
   float tot[4];
   fold_partials(scratch, nctas, tot, sbuf);
-  const float inv = 1.0f / tot[1];  // NaN/Inf if nothing is masked, exactly as the reference's mean over []
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  float inv = 1.0f / tot[1];  // NaN/Inf if nothing is masked, exactly as the reference's mean over []
+  if (loss_out && blockIdx.x == 0 && threadIdx.x == 0) {
     loss_out[0] = tot[0] * inv;
     loss_out[1] = tot[1];
   }
   if (!dy) return;
+  if (gscale) inv *= __ldg(gscale);  // upstream gradient of the scalar loss (a device scalar: no host read-back)
   const int64_t n = M * lddy;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -716,15 +718,22 @@ loss_bert_grad_kernel(const float* __restrict__ y, int ldy, const float* __restr
   }
 }
 
+// loss_out != nullptr: partial sums -> scratch, then the fold (+ dy if given). loss_out == nullptr: dy only, from the
+// partial sums an earlier call left in scratch (the autograd backward of the loss: dy = grad_scale[0] * dLoss/dY).
 int launch_loss_bert(const float* y, int ldy, const float* weather, const uint8_t* mask, int64_t M, int F,
-                     float* scratch, float* loss_out, __nv_bfloat16* dy, int lddy, cudaStream_t stream) {
+                     float* scratch, float* loss_out, const float* grad_scale, __nv_bfloat16* dy, int lddy,
+                     cudaStream_t stream) {
   if (M <= 0 || F <= 0) return WM_ERR_SHAPE;
+  if (!loss_out && !dy) return WM_ERR_ARG;
   int ctas = static_cast<int>((M * F + 255) / 256);
   if (ctas > kLossCtas) ctas = kLossCtas;
-  loss_bert_partial_kernel<<<ctas, 256, 0, stream>>>(y, ldy, weather, mask, M, F, scratch);
-  WM_COUNT_LAUNCH();
-  if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
-  loss_bert_grad_kernel<<<kLossCtas, 256, 0, stream>>>(y, ldy, weather, mask, M, F, scratch, ctas, loss_out, dy, lddy);
+  if (loss_out) {
+    loss_bert_partial_kernel<<<ctas, 256, 0, stream>>>(y, ldy, weather, mask, M, F, scratch);
+    WM_COUNT_LAUNCH();
+    if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
+  }
+  loss_bert_grad_kernel<<<dy ? kLossCtas : 1, 256, 0, stream>>>(y, ldy, weather, mask, M, F, scratch, ctas, loss_out,
+                                                               grad_scale, dy, lddy);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
@@ -782,13 +791,13 @@ __global__ void __launch_bounds__(256)
 loss_former_grad_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ weather,
                         const uint8_t* __restrict__ mask, int64_t msb, int64_t mss, int B, int S, int F,
                         float beta, const float* __restrict__ scratch, int nctas, float* __restrict__ loss_out,
-                        __nv_bfloat16* __restrict__ dy, int lddy) {
+                        const float* __restrict__ gscale, __nv_bfloat16* __restrict__ dy, int lddy) {
   __shared__ float sbuf[32];
   float tot[4];
   fold_partials(scratch, nctas, tot, sbuf);
   // n_bar = tot[2] / B ; recon = (1/B) sum_b nll_b / n_bar = tot[0] / tot[2] ; kl likewise * beta
-  const float inv = 1.0f / tot[2];
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  float inv = 1.0f / tot[2];
+  if (loss_out && blockIdx.x == 0 && threadIdx.x == 0) {
     const float recon = tot[0] * inv, kl = beta * tot[1] * inv;
     loss_out[0] = recon + kl;
     loss_out[1] = recon;
@@ -796,6 +805,7 @@ loss_former_grad_kernel(const float* __restrict__ y, int ldy, const float* __res
     loss_out[3] = tot[2];
   }
   if (!dy) return;
+  if (gscale) inv *= __ldg(gscale);  // upstream gradient of the scalar loss (device scalar)
   const int64_t M = static_cast<int64_t>(B) * S;
   const int64_t n = M * F;
   // zero the padding columns [2F, lddy)
@@ -822,16 +832,20 @@ loss_former_grad_kernel(const float* __restrict__ y, int ldy, const float* __res
 
 int launch_loss_former(const float* y, int ldy, const float* weather, const uint8_t* mask, int64_t msb,
                        int64_t mss, int B, int S, int F, float beta, float* scratch, float* loss_out,
-                       __nv_bfloat16* dy, int lddy, float* mu_out, float* var_out, cudaStream_t stream) {
+                       const float* grad_scale, __nv_bfloat16* dy, int lddy, float* mu_out, float* var_out,
+                       cudaStream_t stream) {
   if (B <= 0 || S <= 0 || F <= 0 || (dy && lddy < 2 * F)) return WM_ERR_SHAPE;
+  if (!loss_out && !dy) return WM_ERR_ARG;
   const int64_t n = static_cast<int64_t>(B) * S * F;
   int ctas = static_cast<int>((n + 255) / 256);
   if (ctas > kLossCtas) ctas = kLossCtas;
-  loss_former_partial_kernel<<<ctas, 256, 0, stream>>>(y, ldy, weather, mask, msb, mss, B, S, F, scratch, mu_out, var_out);
-  WM_COUNT_LAUNCH();
-  if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
-  loss_former_grad_kernel<<<kLossCtas, 256, 0, stream>>>(y, ldy, weather, mask, msb, mss, B, S, F, beta, scratch,
-                                                         ctas, loss_out, dy, lddy);
+  if (loss_out) {  // (see launch_loss_bert: loss_out == nullptr is the gradient-only second call)
+    loss_former_partial_kernel<<<ctas, 256, 0, stream>>>(y, ldy, weather, mask, msb, mss, B, S, F, scratch, mu_out, var_out);
+    WM_COUNT_LAUNCH();
+    if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
+  }
+  loss_former_grad_kernel<<<dy ? kLossCtas : 1, 256, 0, stream>>>(y, ldy, weather, mask, msb, mss, B, S, F, beta, scratch,
+                                                                 ctas, loss_out, grad_scale, dy, lddy);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }

@@ -93,6 +93,7 @@ struct wm_encoder {
   size_t scratch_bytes;
   uint64_t seed, step;
   int training;
+  int saved;  // the last forward call kept its activations: backward may run
 };
 
 namespace wm {
@@ -135,8 +136,12 @@ static size_t carve(wm_encoder* e, uint8_t* base) {
     e->wt[l].w2_t = bf(FF * D);
   }
   e->wout_t = bf(D * e->outP);
-  e->act.resize(c.L);
-  for (int l = 0; l < c.L; ++l) {
+  // eval_only: one layer's worth of activation buffers (every layer reuses them, x ping-pongs between act[0].x and
+  // x_final), no saved statistics / sign bits / keep bits, no backward temporaries: 12 M D bytes instead of
+  // (12 L + 14) M D + ... -- 2.6 GB instead of 22 GB at WeatherFormer large, B = 512
+  const int n_act = c.eval_only ? 1 : c.L;
+  e->act.resize(n_act);
+  for (int l = 0; l < n_act; ++l) {
     LayerAct& a = e->act[l];
     a.x = bf(M * D);
     a.qkv = bf(M * 3 * D);
@@ -145,6 +150,12 @@ static size_t carve(wm_encoder* e, uint8_t* base) {
     a.u = bf(M * D);
     a.h = bf(M * FF);
     a.r2 = bf(M * D);
+    if (c.eval_only) {
+      a.lse = a.mean1 = a.rstd1 = a.mean2 = a.rstd2 = nullptr;
+      a.hbits = nullptr;
+      a.dropw = nullptr;
+      continue;
+    }
     a.lse = f32(static_cast<int64_t>(c.B) * c.H * c.S);
     a.hbits = reinterpret_cast<uint16_t*>(take(gemm_sign_bits_bytes(static_cast<int>(M), c.FF)));
     a.dropw = c.dropout_p > 0.0f ? reinterpret_cast<uint32_t*>(take(attn_dropout_words_bytes(c.B, c.S, c.H))) : nullptr;
@@ -154,6 +165,12 @@ static size_t carve(wm_encoder* e, uint8_t* base) {
     a.rstd2 = f32(M);
   }
   e->x_final = bf(M * D);
+  if (c.eval_only) {
+    e->xin = e->gX = e->gR = e->gF = e->gU = e->gC = e->gH = e->gQKV = nullptr;
+    e->scratch_bytes = 0;
+    e->scratch = nullptr;
+    return off;
+  }
   e->xin = bf(M * kXinCols);
   e->gX = bf(M * D);
   e->gR = bf(M * D);
@@ -254,6 +271,7 @@ int wm_encoder_create(const wm_encoder_config* cfg, void* workspace, size_t work
   e->seed = 0;
   e->step = 0;
   e->training = 0;
+  e->saved = 0;
   *out = e;
   return WM_OK;
 }
@@ -283,34 +301,44 @@ int wm_encoder_refresh_weights(wm_encoder* e, const float* params, void* stream_
 
 int wm_encoder_forward(wm_encoder* e, const float* params, const float* weather, const uint8_t* mask,
                        int64_t mask_stride_b, int64_t mask_stride_s, const float* year, const float* coords,
-                       const float* pos_encoding, float* y_out, int training, uint64_t seed, uint64_t step,
-                       void* stream_) {
+                       const float* pos_encoding, float* y_out, int training, int save_for_backward, uint64_t seed,
+                       uint64_t step, void* stream_) {
   if (!e || !params || !weather || !mask || !year || !coords || !pos_encoding || !y_out) return WM_ERR_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const wm_encoder_config& c = e->cfg;
+  if (save_for_backward && c.eval_only) return WM_ERR_ARG;  // an eval-only handle has nowhere to save activations
+  const bool save = save_for_backward != 0;
   const int M = static_cast<int>(e->M), D = c.D, FF = c.FF, dh = c.D / c.H;
   const float p = training ? c.dropout_p : 0.0f;
   const uint32_t thr = static_cast<uint32_t>(p * 65536.0f + 0.5f);
-  const float dscale = drop_keep_scale(thr);  // the kernels round p to a multiple of 1/128
+  const float dscale = drop_keep_scale(thr);  // the kernels compare 15 bits: p_eff = round(32768 p) / 32768
   e->seed = seed;
   e->step = step;
   e->training = training;
+  e->saved = save ? 1 : 0;
 
-  __nv_bfloat16* x0 = e->act[0].x;
+  // save: layer l keeps its own activations for the backward pass. Otherwise (validation / inference: the reference's
+  // model.eval() + torch.no_grad(), src/base_trainer/base_trainer.py:262-285) every layer reuses layer 0's buffers, x
+  // ping-pongs between act[0].x and x_final, and nothing that only backward reads is written (row statistics, lse,
+  // sign bits, keep bits, the bf16 input copy).
+  __nv_bfloat16* x_cur = e->act[0].x;
+  __nv_bfloat16* x_alt = e->x_final;
   WM_TRY(launch_embed_fwd(weather, mask, mask_stride_b, mask_stride_s, year, coords, params + e->lay.w_in,
-                          params + e->lay.b_in, pos_encoding, x0, e->xin, c.B, c.S, c.F, D, st));
+                          params + e->lay.b_in, pos_encoding, x_cur, save ? e->xin : nullptr, c.B, c.S, c.F, D, st));
   for (int l = 0; l < c.L; ++l) {
     const LayerParams& q = e->lay.layers[l];
-    LayerAct& a = e->act[l];
-    __nv_bfloat16* x_next = l + 1 < c.L ? e->act[l + 1].x : e->x_final;
+    LayerAct& a = e->act[save ? l : 0];
+    __nv_bfloat16* x_in = save ? a.x : x_cur;
+    __nv_bfloat16* x_next = save ? (l + 1 < c.L ? e->act[l + 1].x : e->x_final) : x_alt;
     {  // QKV projection
       GemmEpilogue ep;
       ep.bias = params + q.b_qkv;
       ep.out = a.qkv;
       ep.ld_out = 3 * D;
-      WM_TRY(launch_gemm_tn(a.x, D, e->shadow + q.w_qkv, D, M, 3 * D, D, ep, 0, 0, st));
+      WM_TRY(launch_gemm_tn(x_in, D, e->shadow + q.w_qkv, D, M, 3 * D, D, ep, 0, 0, st));
     }
-    WM_TRY(launch_attn_fwd(a.qkv, a.ctx, a.lse, a.dropw, c.B, c.S, c.H, dh, thr, seed, stream_id(step, l, 0), st));
+    WM_TRY(launch_attn_fwd(a.qkv, a.ctx, save ? a.lse : nullptr, save ? a.dropw : nullptr, c.B, c.S, c.H, dh, thr, seed,
+                           stream_id(step, l, 0), st));
     {  // out-proj + dropout1 + residual
       GemmEpilogue ep;
       ep.bias = params + q.b_o;
@@ -318,13 +346,14 @@ int wm_encoder_forward(wm_encoder* e, const float* params, const float* weather,
       ep.drop_scale = dscale;
       ep.seed = seed;
       ep.stream = stream_id(step, l, 1);
-      ep.residual = a.x;
+      ep.residual = x_in;
       ep.ld_res = D;
       ep.out = a.r1;
       ep.ld_out = D;
       WM_TRY(launch_gemm_tn(a.ctx, D, e->shadow + q.w_o, D, M, D, D, ep, 0, 0, st));
     }
-    WM_TRY(launch_layernorm_fwd(a.r1, params + q.g1, params + q.be1, a.u, a.mean1, a.rstd1, M, D, c.ln_eps, st));
+    WM_TRY(launch_layernorm_fwd(a.r1, params + q.g1, params + q.be1, a.u, save ? a.mean1 : nullptr,
+                                save ? a.rstd1 : nullptr, M, D, c.ln_eps, st));
     {  // linear1 + ReLU + dropout
       GemmEpilogue ep;
       ep.bias = params + q.b1;
@@ -333,7 +362,7 @@ int wm_encoder_forward(wm_encoder* e, const float* params, const float* weather,
       ep.drop_scale = dscale;
       ep.seed = seed;
       ep.stream = stream_id(step, l, 2);
-      ep.sign_bits_out = a.hbits;
+      ep.sign_bits_out = save ? a.hbits : nullptr;
       ep.out = a.h;
       ep.ld_out = FF;
       WM_TRY(launch_gemm_tn(a.u, D, e->shadow + q.w1, D, M, FF, D, ep, 0, 0, st));
@@ -351,14 +380,20 @@ int wm_encoder_forward(wm_encoder* e, const float* params, const float* weather,
       ep.ld_out = D;
       WM_TRY(launch_gemm_tn(a.h, FF, e->shadow + q.w2, FF, M, D, FF, ep, 0, 0, st));
     }
-    WM_TRY(launch_layernorm_fwd(a.r2, params + q.g2, params + q.be2, x_next, a.mean2, a.rstd2, M, D, c.ln_eps, st));
+    WM_TRY(launch_layernorm_fwd(a.r2, params + q.g2, params + q.be2, x_next, save ? a.mean2 : nullptr,
+                                save ? a.rstd2 : nullptr, M, D, c.ln_eps, st));
+    if (!save) {
+      x_alt = x_cur;
+      x_cur = x_next;
+    }
   }
+  const __nv_bfloat16* x_last = save ? e->x_final : x_cur;
   {  // output head -> fp32 [M, outP]; weight rows >= out_dim are TMA zero-fill, bias pad is the zero gap
     GemmEpilogue ep;
     ep.bias = params + e->lay.b_out;
     ep.out = y_out;
     ep.ld_out = e->outP;
-    WM_TRY(launch_gemm_tn_rows(e->x_final, D, e->shadow + e->lay.w_out, D, M, e->outP, D, c.out_dim, ep, 1, st));
+    WM_TRY(launch_gemm_tn_rows(x_last, D, e->shadow + e->lay.w_out, D, M, e->outP, D, c.out_dim, ep, 1, st));
   }
   return WM_OK;
 }
@@ -366,6 +401,7 @@ int wm_encoder_forward(wm_encoder* e, const float* params, const float* weather,
 // gradient of the loss w.r.t. the padded head output (bf16 [M, outP]) -> head grads + grad of x_L
 int wm_encoder_backward_head(wm_encoder* e, const void* dY_, float* grads, void* stream_) {
   if (!e || !dY_ || !grads) return WM_ERR_ARG;
+  if (!e->saved) return WM_ERR_ARG;  // the last forward ran the lean (no-save) schedule
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const wm_encoder_config& c = e->cfg;
   const __nv_bfloat16* dY = reinterpret_cast<const __nv_bfloat16*>(dY_);
@@ -382,14 +418,14 @@ int wm_encoder_backward_head(wm_encoder* e, const void* dY_, float* grads, void*
 // backward through layers layer_hi-1 ... layer_lo (gX holds dLoss/dx_{layer_hi} on entry, dLoss/dx_{layer_lo} on exit)
 int wm_encoder_backward_layers(wm_encoder* e, const float* params, int layer_hi, int layer_lo, float* grads,
                                void* stream_) {
-  if (!e || !params || !grads) return WM_ERR_ARG;
+  if (!e || !params || !grads || !e->saved) return WM_ERR_ARG;
   const wm_encoder_config& c = e->cfg;
   if (layer_lo < 0 || layer_hi > c.L || layer_lo > layer_hi) return WM_ERR_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const int M = static_cast<int>(e->M), D = c.D, FF = c.FF, dh = c.D / c.H;
   const float p = e->training ? c.dropout_p : 0.0f;
   const uint32_t thr = static_cast<uint32_t>(p * 65536.0f + 0.5f);
-  const float dscale = drop_keep_scale(thr);  // the kernels round p to a multiple of 1/128
+  const float dscale = drop_keep_scale(thr);  // the kernels compare 15 bits: p_eff = round(32768 p) / 32768
   // d b2 / d b_o = column sums of the (dropout-masked) LayerNorm input gradients: taken from the wgrad GEMM of the
   // same layer when its tile leaves room for the fused all-ones chunk (then the LayerNorm backward kernel runs its
   // leaner 15-warp form), else accumulated by the LayerNorm backward kernel itself
@@ -448,7 +484,7 @@ int wm_encoder_backward_layers(wm_encoder* e, const float* params, int layer_hi,
 
 // in_proj gradients from dLoss/dx_0 (left in gX by backward_layers(…, 0))
 int wm_encoder_backward_embed(wm_encoder* e, float* grads, void* stream_) {
-  if (!e || !grads) return WM_ERR_ARG;
+  if (!e || !grads || !e->saved) return WM_ERR_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const wm_encoder_config& c = e->cfg;
   const int M = static_cast<int>(e->M), D = c.D, Fin = c.F + 3;
@@ -463,7 +499,7 @@ const void* wm_encoder_activation(wm_encoder* e, int layer, int which) {
   if (!e) return nullptr;
   if (which == 7) return e->x_final;
   if (which == 8) return e->gX;
-  if (layer < 0 || layer >= e->cfg.L) return nullptr;
+  if (layer < 0 || layer >= static_cast<int>(e->act.size())) return nullptr;
   const LayerAct& a = e->act[layer];
   switch (which) {
     case 0: return a.x;

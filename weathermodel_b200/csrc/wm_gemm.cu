@@ -193,11 +193,11 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
     for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
   }
   if (ep.drop_thresh) {
-    const uint32_t add4 = (128u - drop_thresh7(ep.drop_thresh)) * 0x01010101u;
+    const uint32_t add2 = drop_add2(ep.drop_thresh);
     const uint32_t x0 = (static_cast<uint32_t>(row) * static_cast<uint32_t>((N + 15) >> 4) + static_cast<uint32_t>(n0 >> 4)) * 4u;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-      const uint32_t fl = drop_flags4(x0 + w, ep.dkeys, add4);
+      const DropWords fl = drop_flags4(x0 + w, ep.dkeys, add2);
       f[4 * w] = __uint_as_float(__float_as_uint(f[4 * w] * ep.drop_scale) & drop_mask32<0>(fl));
       f[4 * w + 1] = __uint_as_float(__float_as_uint(f[4 * w + 1] * ep.drop_scale) & drop_mask32<1>(fl));
       f[4 * w + 2] = __uint_as_float(__float_as_uint(f[4 * w + 2] * ep.drop_scale) & drop_mask32<2>(fl));

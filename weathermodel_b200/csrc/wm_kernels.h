@@ -19,11 +19,11 @@ namespace wm {
 struct GemmEpilogue {
   const float* bias = nullptr;           // [N] fp32
   int relu = 0;
-  uint32_t drop_thresh = 0;              // round(p * 65536); 0 = no dropout (the kernels use round(p * 128) / 128)
+  uint32_t drop_thresh = 0;              // round(p * 65536); 0 = no dropout (the kernels compare 15 bits: p_eff = round(p * 32768) / 32768)
   float drop_scale = 1.0f;               // drop_keep_scale(drop_thresh)
   uint64_t seed = 0;                     // dropout key
   uint64_t stream = 0;                   // dropout stream: (step, layer, site)
-  DropKeys dkeys = {0u, 0u};             // filled in by the launcher from (seed, stream)
+  DropKeys dkeys = {0u, 0u, 0u};            // filled in by the launcher from (seed, stream)
   const __nv_bfloat16* gate = nullptr;   // [M, ld_gate] saved post-activation (dgrad through ReLU+dropout)
   int ld_gate = 0;
   float gate_scale = 1.0f;
@@ -85,11 +85,12 @@ size_t colsum_workspace_bytes(int M, int N);
 int launch_colsum(const __nv_bfloat16* x, int ld, int M, int N, float* out, float* workspace,
                   cudaStream_t stream);
 int launch_loss_bert(const float* y, int ldy, const float* weather, const uint8_t* mask, int64_t M, int F,
-                     float* scratch, float* loss_out, __nv_bfloat16* dy, int lddy, cudaStream_t stream);
+                     float* scratch, float* loss_out, const float* grad_scale, __nv_bfloat16* dy, int lddy,
+                     cudaStream_t stream);
 int launch_loss_former(const float* y, int ldy, const float* weather, const uint8_t* mask,
                        int64_t mask_stride_b, int64_t mask_stride_s, int B, int S, int F, float beta,
-                       float* scratch, float* loss_out, __nv_bfloat16* dy, int lddy, float* mu_out,
-                       float* var_out, cudaStream_t stream);
+                       float* scratch, float* loss_out, const float* grad_scale, __nv_bfloat16* dy, int lddy,
+                       float* mu_out, float* var_out, cudaStream_t stream);
 int launch_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, __nv_bfloat16* shadow,
                 int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                 float grad_scale, cudaStream_t stream);

@@ -22,18 +22,34 @@ class BucketedDataParallel(nn.Module):
         self.process_group = process_group
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self._pending: List = []
-        self._runtimes = [m.runtime for m in module.modules() if hasattr(m, "runtime")]
-        if not self._runtimes:
+        self.bucket_cap_mb = bucket_cap_mb
+        self._owners = [m for m in module.modules() if hasattr(m, "runtime")]
+        if not self._owners:
             raise ValueError("BucketedDataParallel wraps models built on weathermodel_b200's encoder")
-        dev = next(module.parameters()).device
+        self._backend = dist.get_backend(process_group) if dist.is_initialized() else "none"
+        self._attach()
+        self._broadcast_parameters()
+
+    @property
+    def _runtimes(self):
+        """The owners' CURRENT runtimes: load_pretrained() / deepcopy make a module rebuild its runtime lazily."""
+        return [m.runtime for m in self._owners]
+
+    def _attach(self):
+        """(Re)install the bucket hook on every runtime that lacks it. Cheap; called at wrap time and before every
+        forward, so a runtime rebuilt after wrapping cannot drop out of the gradient all-reduce silently."""
+        dev = next(self.module.parameters()).device
         for rt in self._runtimes:
+            if getattr(rt, "_dp_owner", None) is self and rt.grad_ready_hook is not None:
+                continue
             rt.ensure_flat(dev)
             # bucket = as many whole layers as fit the cap (DDP default 25 MiB)
             per_layer = (rt.offsets[14] - rt.offsets[2]) * 4 if len(rt.offsets) > 14 else rt.flat_params.numel() * 4
-            rt.layers_per_bucket = max(1, int(bucket_cap_mb * 2 ** 20 // max(1, per_layer)))
+            rt.layers_per_bucket = max(1, int(self.bucket_cap_mb * 2 ** 20 // max(1, per_layer)))
             rt.grad_ready_hook = self._make_hook(rt)
-        self._broadcast_parameters()
-        self._backend = dist.get_backend(process_group) if dist.is_initialized() else "none"
+            rt._dp_owner = self
+            if dist.is_initialized():  # every rank draws its own dropout masks (one generator per process in torch DDP, too)
+                rt.seed = (rt.base_seed ^ (0x9E3779B97F4A7C15 * (dist.get_rank(self.process_group) + 1))) & 0xFFFFFFFFFFFFFFFF
 
     def _broadcast_parameters(self):
         if self.world_size == 1:
@@ -64,6 +80,10 @@ class BucketedDataParallel(nn.Module):
     def finish_gradient_sync(self):
         """Join every in-flight bucket all-reduce (stream-level wait; no host sync on NCCL) and average
         parameters that live outside the flat buckets."""
+        for rt in self._runtimes:
+            if self.world_size > 1 and getattr(rt, "_dp_owner", None) is not self:
+                raise RuntimeError("BucketedDataParallel: an encoder runtime was rebuilt after wrapping and ran its "
+                                   "backward without the bucket hook (call the wrapper's forward, or re-wrap)")
         for work, sl in self._pending:
             work.wait()
             if sl is not None:
@@ -77,4 +97,10 @@ class BucketedDataParallel(nn.Module):
                     p.grad.div_(self.world_size)
 
     def forward(self, *args, **kwargs):
+        self._attach()
         return self.module(*args, **kwargs)
+
+    def forward_raw(self, *args, **kwargs):
+        """The wrapped encoder's padded raw head output (the trainers' fused-loss path)."""
+        self._attach()
+        return self.module.forward_raw(*args, **kwargs)

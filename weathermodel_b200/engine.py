@@ -46,11 +46,12 @@ class EncoderRuntime:
         self.flat_grads: Optional[torch.Tensor] = None
         self.offsets: List[int] = []
         self.workspace: Optional[torch.Tensor] = None
-        self._handles: Dict[Tuple[int, int], int] = {}
+        self._handles: Dict[Tuple[int, int, bool], int] = {}
         self._active: Optional[int] = None
         self._shadow_version = None
         self.step_counter = 0
-        self.seed = 0x5EED_2002
+        self.base_seed = 0x5EED_2002
+        self.seed = self.base_seed  # BucketedDataParallel folds the rank in
         # called as hook(lo_float_offset, hi_float_offset) right after the gradients of that slice of
         # the flat buffer are final (data-parallel bucket all-reduce); set by BucketedDataParallel
         self.grad_ready_hook: Optional[Callable[[int, int], None]] = None
@@ -64,9 +65,9 @@ class EncoderRuntime:
         FF = m.transformer_encoder.layers[0].linear1.out_features
         return D, L, FF, m.out_proj.out_features, m.weather_dim
 
-    def _config(self, B: int, S: int) -> _lib.EncoderConfig:
+    def _config(self, B: int, S: int, eval_only: bool = False) -> _lib.EncoderConfig:
         D, L, FF, out_dim, F = self._dims()
-        return _lib.EncoderConfig(B, S, F, D, self.num_heads, L, FF, out_dim, self.dropout_p, self.ln_eps)
+        return _lib.EncoderConfig(B, S, F, D, self.num_heads, L, FF, out_dim, self.dropout_p, self.ln_eps, int(eval_only))
 
     def named_flat_params(self):
         D, L, _, _, _ = self._dims()
@@ -123,9 +124,14 @@ class EncoderRuntime:
         return lo, hi
 
     # ------------------------------------------------------------------ engine handles
-    def _handle(self, B: int, S: int) -> int:
-        key = (B, S)
-        cfg = self._config(B, S)
+    def _handle(self, B: int, S: int, eval_only: bool = False) -> int:
+        """C handle for this (batch, seq_len). A forward that no backward follows (torch.no_grad(): validation,
+        inference) reuses the training handle of the same shape if one exists, else gets an eval-only handle whose
+        workspace holds one layer of activations instead of all of them (include/wm_b200.h: eval_only)."""
+        if eval_only and (B, S, False) in self._handles:
+            eval_only = False
+        key = (B, S, eval_only)
+        cfg = self._config(B, S, eval_only)
         need = lib().wm_encoder_workspace_bytes(C.byref(cfg))
         if need == 0:
             raise ValueError(f"unsupported encoder shape B={B} S={S}")
@@ -170,12 +176,13 @@ class EncoderRuntime:
             self._shadow_version = ver
 
     # ------------------------------------------------------------------ forward / backward
-    def forward(self, weather, coords, year, mask, training: bool) -> torch.Tensor:
-        """Returns the padded raw head output: fp32 [B, S, 32|64]."""
+    def forward(self, weather, coords, year, mask, training: bool, save_for_backward: bool = True) -> torch.Tensor:
+        """Returns the padded raw head output: fp32 [B, S, 32|64]. save_for_backward=False is the lean schedule for
+        torch.no_grad() callers (BaseTrainer._validate_epoch: model.eval() + no_grad, reference base_trainer.py:262-285)."""
         B, S, F = weather.shape
         dev = weather.device
         self.ensure_flat(dev)
-        h = self._handle(B, S)
+        h = self._handle(B, S, eval_only=not save_for_backward)
         with torch.cuda.device(dev):
             self._refresh_if_needed(h)
             m = self.module_ref
@@ -186,7 +193,8 @@ class EncoderRuntime:
             pe = m.positional_encoding.pos_encoding
             check(lib().wm_encoder_forward(h, self.flat_params.data_ptr(), weather.data_ptr(), mask.data_ptr(), msb, mss,
                                            year.data_ptr(), coords.data_ptr(), pe.data_ptr(), y.data_ptr(),
-                                           int(training), self.seed, self.step_counter, ops._stream()),
+                                           int(training), int(save_for_backward), self.seed, self.step_counter,
+                                           ops._stream()),
                   "wm_encoder_forward")
         self._active = h
         return y
@@ -221,15 +229,42 @@ class EncoderRuntime:
                 if hook:
                     hook(f_lo, f_hi)
 
-    def publish_grads(self, accumulate_from: Optional[torch.Tensor] = None):
+    def grads_are_live(self) -> bool:
+        """True if some parameter's .grad already IS its slice of the flat gradient buffer, i.e. a backward ran and
+        nobody called zero_grad() since: the next backward has to accumulate, as torch does."""
+        if self.flat_grads is None:
+            return False
+        return any(p.grad is not None and p.grad.data_ptr() == self.grad_view(i).data_ptr()
+                   for i, (_, p) in enumerate(self._named))
+
+    def publish_grads(self):
         for i, (_, p) in enumerate(self._named):
             if not p.requires_grad:
                 continue
             g = self.grad_view(i)
             if p.grad is None or p.grad.data_ptr() == g.data_ptr():
                 p.grad = g
-            else:  # gradient accumulation across several backward passes without zero_grad()
+            else:  # a foreign gradient tensor (e.g. produced through torch ops): add ours to it, out of place
                 p.grad = p.grad + g
+
+
+# The fused loss heads hand their bf16 gradient to the encoder backward directly: autograd insists that the
+# gradient of the fp32 head output be an fp32 tensor of the same shape, which would cost a bf16 -> fp32 -> bf16 round
+# trip of [B*S, 64] values per step (VERDICT r1, item 12). The loss backward therefore returns a stride-0 expand of a
+# zero scalar and parks the real gradient on the runtime, keyed by the forward step it belongs to.
+_ZERO_SCALARS: Dict[torch.device, torch.Tensor] = {}
+
+
+def _placeholder_grad(shape, device) -> torch.Tensor:
+    z = _ZERO_SCALARS.get(device)
+    if z is None:
+        z = _ZERO_SCALARS[device] = torch.zeros((), dtype=torch.float32, device=device)
+    return z.expand(shape)
+
+
+def _is_placeholder(t: torch.Tensor) -> bool:
+    z = _ZERO_SCALARS.get(t.device)
+    return z is not None and t.data_ptr() == z.data_ptr() and all(s == 0 for s in t.stride())
 
 
 class _EncoderFn(torch.autograd.Function):
@@ -238,7 +273,7 @@ class _EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, anchor, runtime: EncoderRuntime, weather, coords, year, mask, training):
-        y = runtime.forward(weather, coords, year, mask, training)
+        y = runtime.forward(weather, coords, year, mask, training, save_for_backward=True)
         ctx.runtime = runtime
         ctx.handle = runtime._active
         ctx.step = runtime.step_counter
@@ -250,8 +285,20 @@ class _EncoderFn(torch.autograd.Function):
         if ctx.step != rt.step_counter:
             raise RuntimeError("encoder backward called after another forward reused the activation workspace")
         B, S, P = dy.shape
-        dyb = dy.reshape(B * S, P).to(torch.bfloat16).contiguous()
+        side = rt.__dict__.pop("_side_dy", None)
+        if side is not None and side[0] != ctx.step:
+            side = None
+        if side is not None and _is_placeholder(dy):
+            dyb = side[1]  # bf16 [B*S, P] straight from the fused loss kernel
+        else:
+            dyf = dy.reshape(B * S, P)
+            if side is not None:  # the head output fed the fused loss AND other torch ops: add both gradients
+                dyf = dyf + side[1].float()
+            dyb = dyf.to(torch.bfloat16).contiguous()
+        backup = rt.flat_grads.clone() if rt.grads_are_live() else None  # second backward without zero_grad()
         rt.backward(ctx.handle, dyb)
+        if backup is not None:
+            rt.flat_grads.add_(backup)
         rt.publish_grads()
         return (None,) * 7
 
@@ -267,52 +314,70 @@ def encoder_apply(runtime: EncoderRuntime, weather, coords, year, mask, training
     runtime.ensure_flat(weather.device)
     anchor = runtime._named[0][1]
     if torch.is_grad_enabled() and any(p.requires_grad for _, p in runtime._named):
-        return _EncoderFn.apply(anchor, runtime, weather, coords, year, mask, training)
-    return runtime.forward(weather, coords, year, mask, training)
+        y = _EncoderFn.apply(anchor, runtime, weather, coords, year, mask, training)
+        y._wm_src = (runtime, runtime.step_counter)  # lets a fused loss park its bf16 gradient for this forward
+        return y
+    return runtime.forward(weather, coords, year, mask, training, save_for_backward=False)
 
 
 # ---------------------------------------------------------------------------------------------
 # fused loss heads on the raw (padded) encoder output
 # ---------------------------------------------------------------------------------------------
+def _hand_over(src, dy_bf16: torch.Tensor, shape, device):
+    """Park the bf16 loss gradient for the encoder backward of the forward it came from; the fp32 copy autograd
+    would otherwise demand is made only when the head output did not come straight from the encoder."""
+    if src is not None:
+        rt, step = src
+        cur = rt.__dict__.get("_side_dy")
+        if rt.step_counter == step and (cur is None or cur[0] != step):  # (a second fused loss on the same output adds in fp32)
+            rt.__dict__["_side_dy"] = (step, dy_bf16)
+            return _placeholder_grad(shape, device)
+    return dy_bf16.view(shape).float()
+
+
 class _BertLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y_pad, weather, mask):
+    def forward(ctx, y_pad, weather, mask, src):
         B, S, P = y_pad.shape
         F = weather.shape[-1]
-        out, dy = ops.loss_bert(y_pad.view(B * S, P), weather.reshape(B * S, F).contiguous(),
-                                mask.reshape(B * S, F).contiguous(), want_grad=True, ld_grad=P)
-        ctx.save_for_backward(dy)
-        ctx.shape = (B, S, P)
+        w2, m2 = weather.reshape(B * S, F).contiguous(), mask.reshape(B * S, F).contiguous()
+        out, scratch = ops.loss_bert_value(y_pad.view(B * S, P), w2, m2)
+        ctx.save_for_backward(y_pad, w2, m2, scratch)
+        ctx.src = src
         return out[0]
 
     @staticmethod
     def backward(ctx, g):
-        (dy,) = ctx.saved_tensors
-        return (dy.view(ctx.shape).float() * g), None, None
+        y_pad, w2, m2, scratch = ctx.saved_tensors
+        B, S, P = y_pad.shape
+        dy = ops.loss_bert_grad(y_pad.view(B * S, P), w2, m2, scratch, g, ld_grad=P)
+        return _hand_over(ctx.src, dy, (B, S, P), y_pad.device), None, None, None
 
 
 class _FormerLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y_pad, weather, mask, beta):
+    def forward(ctx, y_pad, weather, mask, beta, src):
         B, S, P = y_pad.shape
-        out, dy, _, _ = ops.loss_former(y_pad.view(B * S, P), weather, mask, beta, want_grad=True, ld_grad=P)
-        ctx.save_for_backward(dy)
-        ctx.shape = (B, S, P)
+        out, scratch = ops.loss_former_value(y_pad.view(B * S, P), weather, mask, beta)
+        ctx.save_for_backward(y_pad, weather, mask, scratch)
+        ctx.beta, ctx.src = beta, src
         ctx.mark_non_differentiable(out)
         return out[0], out
 
     @staticmethod
     def backward(ctx, g, _g_all):
-        (dy,) = ctx.saved_tensors
-        return (dy.view(ctx.shape).float() * g), None, None, None
+        y_pad, weather, mask, scratch = ctx.saved_tensors
+        B, S, P = y_pad.shape
+        dy = ops.loss_former_grad(y_pad.view(B * S, P), weather, mask, ctx.beta, scratch, g, ld_grad=P)
+        return _hand_over(ctx.src, dy, (B, S, P), y_pad.device), None, None, None, None
 
 
 def bert_masked_mse(y_pad, weather, mask) -> torch.Tensor:
     """mean((weather[mask] - y[mask])**2) without the boolean gathers (weatherbert_trainer.py:55-60)."""
-    return _BertLossFn.apply(y_pad, weather.contiguous().float(), mask)
+    return _BertLossFn.apply(y_pad, weather.contiguous().float(), mask, getattr(y_pad, "_wm_src", None))
 
 
 def former_elbo(y_pad, weather, mask, beta: float) -> Dict[str, torch.Tensor]:
     """ELBO of weatherformer_trainer.py:68-111 straight from the raw head output [mu | logvar | pad]."""
-    total, allv = _FormerLossFn.apply(y_pad, weather.contiguous().float(), mask, float(beta))
+    total, allv = _FormerLossFn.apply(y_pad, weather.contiguous().float(), mask, float(beta), getattr(y_pad, "_wm_src", None))
     return {"total_loss": total, "reconstruction": allv[1], "kl_term": allv[2]}

@@ -326,6 +326,58 @@ def loss_former(y, weather, mask, beta, want_grad=True, ld_grad=64, want_mu_var=
     return out, dy, mu, var
 
 
+def _grad_scale(g: Optional[torch.Tensor], device):
+    if g is None:
+        return None
+    if g.dtype != torch.float32 or g.device != device or g.numel() != 1:
+        g = g.to(device=device, dtype=torch.float32).reshape(())
+    return g.contiguous()
+
+
+def loss_bert_value(y, weather, mask):
+    """Forward half of the masked MSE: (loss[2] = value, sum(mask); scratch with the partial sums for loss_bert_grad)."""
+    _cuda(y, weather, mask)
+    M, F = weather.shape
+    scratch = torch.empty(LOSS_SCRATCH_FLOATS, dtype=torch.float32, device=y.device)
+    out = torch.empty(2, dtype=torch.float32, device=y.device)
+    check(lib().wm_loss_bert(_p(y), y.stride(0), _p(weather), _p(mask), M, F, _p(scratch), _p(out), None, 0, _stream()),
+          "wm_loss_bert")
+    return out, scratch
+
+
+def loss_bert_grad(y, weather, mask, scratch, grad_scale=None, ld_grad=32):
+    """Backward half: dy bf16 [M, ld_grad] = grad_scale * dLoss/dy; grad_scale is a DEVICE scalar (no host sync)."""
+    _cuda(y, weather, mask, scratch)
+    M, F = weather.shape
+    g = _grad_scale(grad_scale, y.device)
+    dy = torch.empty((M, ld_grad), dtype=BF16, device=y.device)
+    check(lib().wm_loss_bert_grad(_p(y), y.stride(0), _p(weather), _p(mask), M, F, _p(scratch), _p(g), _p(dy), ld_grad,
+                                  _stream()), "wm_loss_bert_grad")
+    return dy
+
+
+def loss_former_value(y, weather, mask, beta):
+    _cuda(y, weather, mask)
+    B, S, F = weather.shape
+    mask, msb, mss = mask_strides(mask)
+    scratch = torch.empty(LOSS_SCRATCH_FLOATS, dtype=torch.float32, device=y.device)
+    out = torch.empty(4, dtype=torch.float32, device=y.device)
+    check(lib().wm_loss_former(_p(y), y.stride(0), _p(weather.contiguous()), _p(mask), msb, mss, B, S, F, float(beta),
+                               _p(scratch), _p(out), None, 0, None, None, _stream()), "wm_loss_former")
+    return out, scratch
+
+
+def loss_former_grad(y, weather, mask, beta, scratch, grad_scale=None, ld_grad=64):
+    _cuda(y, weather, mask, scratch)
+    B, S, F = weather.shape
+    mask, msb, mss = mask_strides(mask)
+    g = _grad_scale(grad_scale, y.device)
+    dy = torch.empty((B * S, ld_grad), dtype=BF16, device=y.device)
+    check(lib().wm_loss_former_grad(_p(y), y.stride(0), _p(weather.contiguous()), _p(mask), msb, mss, B, S, F, float(beta),
+                                    _p(scratch), _p(g), _p(dy), ld_grad, _stream()), "wm_loss_former_grad")
+    return dy
+
+
 def adam_fused(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
                shadow=None, grad_scale=1.0):
     _cuda(param, grad, exp_avg, exp_avg_sq, shadow)

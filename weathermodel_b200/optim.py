@@ -20,7 +20,10 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         if len(self.param_groups) != 1:
             raise ValueError("FusedAdam supports a single param group (the reference uses one)")
-        self.runtime = runtime
+        # the runtime is looked up through its module at every step: load_pretrained() / deepcopy drop a module's
+        # runtime and a new one (new flat buffers) is built lazily -- a stored reference would go stale silently
+        self._runtime_owner = runtime.module_ref if runtime is not None else None
+        self._step_t = torch.tensor(0.0)  # the `step` entry shared by all flat parameters' state (torch format)
         # host (CPU) parameters are refused unless a test of the state-dict / bookkeeping logic asks for them:
         # there is no CPU path in the product
         self.allow_host_params = allow_host_params
@@ -28,13 +31,19 @@ class FusedAdam(torch.optim.Optimizer):
         self._flat_v = None
         self._step = 0
 
+    @property
+    def runtime(self) -> Optional[EncoderRuntime]:
+        return self._runtime_owner.runtime if self._runtime_owner is not None else None
+
     # ---- flat state bound to the runtime's flat parameter buffer ------------------------------------
     def _bind_flat_state(self):
         rt = self.runtime
         if rt is None or rt.flat_params is None:
             return False
         n = rt.flat_params.numel()
-        if self._flat_m is None or self._flat_m.numel() != n or self._flat_m.device != rt.flat_params.device:
+        if (self._flat_m is None or self._flat_m.numel() != n or self._flat_m.device != rt.flat_params.device
+                or getattr(self, "_bound_to", None) is not rt):
+            self._bound_to = rt
             self._flat_m = torch.zeros(n, dtype=torch.float32, device=rt.flat_params.device)
             self._flat_v = torch.zeros(n, dtype=torch.float32, device=rt.flat_params.device)
             for (_, p), off in zip(rt._named, rt.offsets):
@@ -46,13 +55,17 @@ class FusedAdam(torch.optim.Optimizer):
                     v.copy_(st["exp_avg_sq"])
                     self._step = max(self._step, int(st["step"]))
                 st["exp_avg"], st["exp_avg_sq"] = m, v
-                st.setdefault("step", torch.tensor(float(self._step)))
+                st["step"] = self._step_t
+            self._step_t.fill_(float(self._step))
         return True
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._flat_m = None  # re-adopt loaded tensors into flat buffers at the next step
         self._flat_v = None
+        # the step count comes from the loaded state (or restarts at 0 for an empty one, as torch.optim.Adam does):
+        # keeping the old count would bias-correct fresh zero moments as if they were `_step` steps old
+        self._step = 0
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -76,8 +89,7 @@ class FusedAdam(torch.optim.Optimizer):
                     ops.adam_fused(rt.flat_params, rt.flat_grads, self._flat_m, self._flat_v, self._step, lr, b1, b2,
                                    eps, wd)
                 rt.mark_weights_dirty()
-                for p in in_flat:
-                    self.state[p]["step"] = torch.tensor(float(self._step))
+                self._step_t.fill_(float(self._step))  # one host tensor shared by every flat parameter's state
                 flat_ids = {id(p) for p in in_flat}
         for p in group["params"]:
             if id(p) in flat_ids or p.grad is None:

@@ -30,8 +30,7 @@ class WeatherBertTrainer(BaseTrainer):
         cfg["masking_function"], cfg["masking_prob"], cfg["n_masked_features"] = "weatherbert", masking_prob, n_masked_features
 
     def _loss(self, data, coords, year, interval, feature_mask) -> Dict[str, torch.Tensor]:
-        net = self._get_underlying_model()
-        y_pad = net.forward_raw(data, coords, year, interval, feature_mask)
+        y_pad = self.model.forward_raw(data, coords, year, interval, feature_mask)  # (the data-parallel wrapper forwards it)
         return {"total_loss": bert_masked_mse(y_pad, data, feature_mask)}
 
     def compute_train_loss(self, data, coords, year, interval, feature_mask) -> Dict[str, torch.Tensor]:

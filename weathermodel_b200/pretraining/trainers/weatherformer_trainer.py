@@ -46,13 +46,27 @@ class WeatherFormerTrainer(BaseTrainer):
             self.logger.info(f"KL Term: {out['kl_term'].item():.6f}")
         return out
 
-    def compute_train_loss(self, weather, coords, year, interval, feature_mask) -> Dict[str, torch.Tensor]:
+    def _fused_path(self) -> bool:
+        """The stock ELBO (standard-normal prior) on a stock WeatherFormer: loss straight from the raw head output, so
+        the (mu, var) tensors -- which the fused kernels never read -- are not materialised (no eager exp / clamp on
+        strided slices every step). Subclasses that override the prior or the ELBO take the generic path."""
+        cls = type(self)
+        return (cls.compute_kl_loss is WeatherFormerTrainer.compute_kl_loss
+                and cls.compute_elbo_loss is WeatherFormerTrainer.compute_elbo_loss
+                and type(self._get_underlying_model()) is WeatherFormer and not DRY_RUN)
+
+    def _loss(self, weather, coords, year, interval, feature_mask) -> Dict[str, torch.Tensor]:
+        if self._fused_path():
+            y_pad = self.model.forward_raw(weather, coords, year, interval, feature_mask)
+            return former_elbo(y_pad, weather, feature_mask, self.beta)
         outputs = self.model(weather, coords, year, interval, weather_feature_mask=feature_mask)
         return self.compute_elbo_loss(weather, feature_mask, *outputs)
 
+    def compute_train_loss(self, weather, coords, year, interval, feature_mask) -> Dict[str, torch.Tensor]:
+        return self._loss(weather, coords, year, interval, feature_mask)
+
     def compute_validation_loss(self, weather, coords, year, interval, feature_mask) -> Dict[str, torch.Tensor]:
-        outputs = self.model(weather, coords, year, interval, weather_feature_mask=feature_mask)
-        return self.compute_elbo_loss(weather, feature_mask, *outputs)
+        return self._loss(weather, coords, year, interval, feature_mask)
 
     def get_dataloaders(self, shuffle: bool = True) -> Tuple[DataLoader, DataLoader]:
         n_masked = self._get_n_masked_features(self.current_epoch, self.n_masked_features)
