@@ -61,6 +61,16 @@ def main():
     print(f"gaps > 20 us: {sum(1 for g, _, _ in gaps if g > 20)}; median gap {sorted(g for g, _, _ in gaps)[len(gaps) // 2]:.1f} us")
     for g, a_, b_ in sorted(gaps, reverse=True)[:15]:
         print(f"  {g:8.1f} us  after {a_}  before {b_}")
+    # per-kernel totals INSIDE the step (power-capped clocks, warm caches: what the step actually pays, unlike the
+    # serialised boost-clock figures of an ncu launch list)
+    agg = {}
+    for e in evs:
+        name = e.name.split("(")[0][:70]
+        n, t = agg.get(name, (0, 0.0))
+        agg[name] = (n + 1, t + (e.time_range.end - e.time_range.start))
+    print(f"{'kernel':72s} {'n':>5s} {'total ms':>9s} {'avg us':>8s} {'share':>6s}")
+    for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
+        print(f"{name:72s} {n:5d} {t / 1e3:9.3f} {t / n:8.1f} {100 * t / busy:5.1f}%")
 
 
 if __name__ == "__main__":

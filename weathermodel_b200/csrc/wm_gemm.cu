@@ -160,9 +160,12 @@ int g_gemm_diag = 0;  // copied into GemmEpilogue::diag by the launcher
 
 template <typename OutT>
 WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const float* sbias, const GemmEpilogue& ep,
-                             int row, int n0, int M, int N, bool wide, uint8_t* sdst) {
+                             int row, int n0, int M, int N, bool wide, uint8_t* sdst, int swz_chunk = -1) {
   // sdst (bf16 outputs only): this lane's 32 bytes of the chunk inside the warp's shared-memory staging tile; the
   // tile leaves through coalesced stores once all chunks are in (gemm_epilogue_tile). nullptr: direct stores.
+  // swz_chunk >= 0: sdst is the lane's 128-byte ROW of a 32 x 64 SWIZZLE_128B box (TMA-store epilogue) and the two
+  // 16-byte pieces go to chunks (swz_chunk ^ (row & 7)) and ((swz_chunk + 1) ^ (row & 7)) of it -- the layout
+  // cp.async.bulk.tensor expects, and conflict-free for lane = row (8 consecutive rows cover all 32 banks once).
   if (n0 >= N) return;  // warp-uniform
 #ifdef WM_DIAG
   const int diag = ep.diag;
@@ -258,8 +261,14 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
       if (!sdst && row >= M) return;
     }
     if (sdst) {
-      *reinterpret_cast<uint4*>(sdst) = o0;
-      *reinterpret_cast<uint4*>(sdst + 16) = o1;
+      if (swz_chunk >= 0) {
+        const uint32_t r7 = static_cast<uint32_t>(threadIdx.x) & 7u;  // row inside the box = lane
+        *reinterpret_cast<uint4*>(sdst + ((static_cast<uint32_t>(swz_chunk) ^ r7) << 4)) = o0;
+        *reinterpret_cast<uint4*>(sdst + ((static_cast<uint32_t>(swz_chunk + 1) ^ r7) << 4)) = o1;
+      } else {
+        *reinterpret_cast<uint4*>(sdst) = o0;
+        *reinterpret_cast<uint4*>(sdst + 16) = o1;
+      }
       return;
     }
 #ifdef WM_DIAG
@@ -295,7 +304,12 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
 template <typename OutT, int kAuxDepth>
 WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t* acc_full, uint32_t aph,
                                   uint32_t wait_code, uint32_t tbase, int row, int n_base, int cols_per, int M, int N,
-                                  bool wide, int lane, uint8_t* stage, uint64_t* acc_empty, uint32_t acc_empty_cluster) {
+                                  bool wide, int lane, uint8_t* stage, uint64_t* acc_empty, uint32_t acc_empty_cluster,
+                                  const CUtensorMap* tmC = nullptr) {
+  // tmC != nullptr (staged == 2, cols_per == 64): TMA-store epilogue. `stage` is this warp's 1024-byte aligned 4 KB
+  // box (32 rows x 64 bf16, SWIZZLE_128B); the lanes write their packed rows straight from the tcgen05.ld registers,
+  // one elected lane hands the box to cp.async.bulk.tensor (rows >= M / columns >= N are clipped by the tensor map)
+  // and the warp moves on: no read-back of the staging tile, no per-lane address arithmetic, no st.global.
   // acc_empty / acc_empty_cluster: the barrier that hands the accumulator stage back to the MMA warp (a local
   // barrier, or the leader CTA's as a shared::cluster address when acc_empty is nullptr). It is released as soon as
   // the last TMEM load has landed -- with staged stores that is before the tile is written out.
@@ -316,6 +330,10 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
 #pragma unroll
   for (int d = 0; d < kAuxDepth; ++d)
     if (d * 16 < cols_per) epi_load_aux(aux[d], ep, row, n_base + d * 16, M, N, wide);
+  if (tmC) {  // the previous tile's box must have been read by the TMA engine before it is overwritten
+    if (lane == 0) bulk_wait_group_read<0>();
+    __syncwarp();
+  }
   mbar_wait(acc_full, aph, wait_code);
   tc_fence_after();
   uint32_t va[16], vb[16];
@@ -331,12 +349,14 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
         tmem_ld_wait();
         if (d & 1) {
           if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, va);
-          epi_process16<OutT>(vb, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide,
-                              stage ? stage + lane * pitch + c0 * 2 : nullptr);
+          if (tmC) epi_process16<OutT>(vb, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3);
+          else epi_process16<OutT>(vb, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide,
+                                   stage ? stage + lane * pitch + c0 * 2 : nullptr);
         } else {
           if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, vb);
-          epi_process16<OutT>(va, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide,
-                              stage ? stage + lane * pitch + c0 * 2 : nullptr);
+          if (tmC) epi_process16<OutT>(va, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3);
+          else epi_process16<OutT>(va, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide,
+                                   stage ? stage + lane * pitch + c0 * 2 : nullptr);
         }
         if (c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
       }
@@ -352,7 +372,14 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
     else mbar_arrive_cluster(acc_empty_cluster);
   }
   if constexpr (sizeof(OutT) == 2) {
-    if (stage) {
+    if (tmC) {
+      fence_proxy_async_smem();  // the lanes' generic-proxy writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0 && n_base < N && row < M) {  // (row == first row of the box for lane 0)
+        tma_store_2d(tmC, stage, n_base, row);
+        bulk_commit_group();
+      }
+    } else if (stage) {
       __syncwarp();
       // 16-byte units of the tile in row-major order, 32 per instruction: unit i = lane + 32 k is piece i % u of
       // row i / u (u = units per row); consecutive lanes write consecutive global addresses within a row
@@ -381,16 +408,18 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
 template <typename OutT, int kEW>
 __global__ void __launch_bounds__(gemm_threads(kEW), 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               int M, int N, int K, int BN, int stages, int staged, GemmEpilogue ep) {
+               const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int BN, int stages, int staged,
+               GemmEpilogue ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024B-align the tile ring (SWIZZLE_128B atoms)
   uint8_t* smem = smem_align_up(smem_raw, 1024);
   const uint32_t a_bytes = kBM * kBK * 2;
   const uint32_t b_bytes = static_cast<uint32_t>(BN) * kBK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  // [tile ring][epilogue staging: kEW x 32 rows x (BN / (kEW / 4) * 2 + 16) bytes, if staged][tail]
+  // [tile ring][epilogue staging: kEW x 32 rows x (BN / (kEW / 4) * 2 + 16) bytes if staged == 1, kEW boxes of 4 KB
+  // (32 rows x 64 columns, SWIZZLE_128B, for the TMA-store epilogue) if staged == 2][tail]
   uint8_t* epi_stage = smem + static_cast<size_t>(stages) * stage_bytes;
-  const uint32_t epi_stage_warp = 32u * (static_cast<uint32_t>(BN / (kEW / 4)) * 2u + 16u);
+  const uint32_t epi_stage_warp = staged == 2 ? 4096u : 32u * (static_cast<uint32_t>(BN / (kEW / 4)) * 2u + 16u);
   GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(epi_stage + (staged ? kEW * epi_stage_warp : 0u));
 
   const int warp = warp_idx_uniform();
@@ -403,6 +432,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (staged == 2) tma_prefetch_desc(&tmC);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&tail->full[s], 1);
       mbar_init(&tail->empty[s], 1);
@@ -470,7 +500,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp - 2;              // 0..kEW-1
     const int half = ew >> 2;             // which slice of the tile's columns this warp owns
     const int cols_per = BN / (kEW / 4);  // a multiple of 16 (host-checked)
-    float* sbias = tail->bias + ew * (1024 / kEW);
+    float* sbias = tail->bias + ew * (kEW > 8 ? 64 : 128);  // 16-byte aligned slices, >= the warp's column count
     // 32-byte accesses need 32-byte aligned rows: every leading dimension a multiple of 16 bf16 elements
     const bool wide = ((ep.ld_out | (ep.residual ? ep.ld_res : 0) | (ep.gate ? ep.ld_gate : 0)) & 15) == 0 &&
                       ((reinterpret_cast<uintptr_t>(ep.out) | reinterpret_cast<uintptr_t>(ep.residual) |
@@ -484,8 +514,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       gemm_epilogue_tile<OutT, (kEW == 16 ? 2 : 4)>(ep, sbias, &tail->acc_full[as], aph, 14, tbase, m_blk * kBM + q * 32 + lane,
                                n_blk * BN + half * cols_per, cols_per, M, N, wide, lane,
                                staged ? epi_stage + static_cast<uint32_t>(ew) * epi_stage_warp : nullptr,
-                               &tail->acc_empty[as], 0u);
+                               &tail->acc_empty[as], 0u, staged == 2 ? &tmC : nullptr);
     }
+    if (staged == 2 && lane == 0) bulk_wait_group_read<0>();  // the last box must be read before the CTA's smem goes away
   }
   tc_fence_before();
   __syncthreads();
@@ -504,16 +535,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <typename OutT, int kEW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(kEW), 1)
 gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                int M, int N, int K, int BN, int stages, int staged, GemmEpilogue ep) {
+                const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int BN, int stages, int staged,
+                GemmEpilogue ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_align_up(smem_raw, 1024);
   const int BNH = BN >> 1;  // B rows staged by each CTA
   const uint32_t a_bytes = kBM * kBK * 2;
   const uint32_t b_bytes = static_cast<uint32_t>(BNH) * kBK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  // [tile ring][epilogue staging: kEW x 32 rows x (BN / (kEW / 4) * 2 + 16) bytes, if staged][tail]
+  // [tile ring][epilogue staging (see gemm_tn_kernel)][tail]
   uint8_t* epi_stage = smem + static_cast<size_t>(stages) * stage_bytes;
-  const uint32_t epi_stage_warp = 32u * (static_cast<uint32_t>(BN / (kEW / 4)) * 2u + 16u);
+  const uint32_t epi_stage_warp = staged == 2 ? 4096u : 32u * (static_cast<uint32_t>(BN / (kEW / 4)) * 2u + 16u);
   GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(epi_stage + (staged ? kEW * epi_stage_warp : 0u));
 
   const int warp = warp_idx_uniform();
@@ -594,7 +626,7 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int ew = warp - 2;
     const int half = ew >> 2;
     const int cols_per = BN / (kEW / 4);
-    float* sbias = tail->bias + ew * (1024 / kEW);
+    float* sbias = tail->bias + ew * (kEW > 8 ? 64 : 128);  // 16-byte aligned slices, >= the warp's column count
     const bool wide = ((ep.ld_out | (ep.residual ? ep.ld_res : 0) | (ep.gate ? ep.ld_gate : 0)) & 15) == 0 &&
                       ((reinterpret_cast<uintptr_t>(ep.out) | reinterpret_cast<uintptr_t>(ep.residual) |
                         reinterpret_cast<uintptr_t>(ep.gate)) & 31) == 0;
@@ -609,8 +641,9 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                m_blk * 2 * kBM + static_cast<int>(rank) * kBM + q * 32 + lane,
                                n_blk * BN + half * cols_per, cols_per, M, N, wide, lane,
                                staged ? epi_stage + static_cast<uint32_t>(ew) * epi_stage_warp : nullptr,
-                               nullptr, acc_empty_leader[as]);
+                               nullptr, acc_empty_leader[as], staged == 2 ? &tmC : nullptr);
     }
+    if (staged == 2 && lane == 0) bulk_wait_group_read<0>();
   }
   __syncwarp();  // reconverge the single-lane role warps: barrier.cluster.*.aligned needs whole warps
   tc_fence_before();
@@ -645,7 +678,7 @@ static int pick_bn(int N) {
 // Order of precedence: forced option (wm_set_option) > tuned table entry (wm_gemm_set_variant) > heuristic.
 int g_gemm_two_cta = -1;   // "gemm_two_cta": -1 auto, 0 single-CTA tiles, 1 CTA-pair tiles (M >= 1024)
 int g_gemm_epi_warps = 0;  // "gemm_epi_warps": 0 auto, 8 or 16 (16 needs a tile width that is a multiple of 64)
-int g_gemm_staged = -1;    // "gemm_staged": -1 auto, 0 thread-per-row stores, 1 stores staged through shared memory
+int g_gemm_staged = -1;    // "gemm_staged": -1 auto, 0 thread-per-row stores, 1 stores staged through shared memory, 2 TMA-store boxes
 
 struct GemmVariant { int M, N, K; uint32_t sig; int two_cta, epi_warps, staged; };
 constexpr int kMaxGemmVariants = 128;
@@ -660,7 +693,7 @@ uint32_t gemm_signature(const GemmEpilogue& ep, int out_fp32) {
          (ep.gate_bits ? 16u : 0u) | (ep.residual ? 32u : 0u) | (ep.sign_bits_out ? 64u : 0u) | (out_fp32 ? 128u : 0u);
 }
 int gemm_set_variant(int M, int N, int K, uint32_t sig, int two_cta, int epi_warps, int staged) {
-  if ((two_cta != 0 && two_cta != 1) || (epi_warps != 8 && epi_warps != 16) || (staged != 0 && staged != 1)) return WM_ERR_ARG;
+  if ((two_cta != 0 && two_cta != 1) || (epi_warps != 8 && epi_warps != 16) || staged < 0 || staged > 2) return WM_ERR_ARG;
   for (int i = 0; i < g_num_gemm_variants; ++i) {
     GemmVariant& v = g_gemm_variants[i];
     if (v.M == M && v.N == N && v.K == K && v.sig == sig) {
@@ -727,40 +760,55 @@ static int launch_gemm_tn_impl(const void* A, int lda, const void* B, int ldb, i
   if (rc) return rc;
   int want_two, want_ew, want_staged;
   gemm_pick_variant(M, N, K, gemm_signature(ep, out_fp32), &want_two, &want_ew, &want_staged);
-  const int ew = (want_ew >= 16 && (BN & 63) == 0) ? 16 : 8;
-  const int threads = gemm_threads(ew);
   const int fixed_smem = 2048 + static_cast<int>(sizeof(GemmSmemTail));
+  const bool aligned_out = !out_fp32 && (ep.ld_out & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0;
+  // staged == 2: TMA-store epilogue. Every epilogue warp owns one 32 x 64 box, so the warp count follows from the
+  // tile width: BN = 256 -> 16 warps, 192 -> 12, 128 -> 8.
+  const bool tma_out = want_staged == 2 && aligned_out && (BN & 63) == 0 && BN >= 128;
+  const int ew = tma_out ? BN / 16 : ((want_ew >= 16 && (BN & 63) == 0) ? 16 : 8);
+  const int threads = gemm_threads(ew);
   // staged stores: 16-byte aligned rows and at least three pipeline stages left next to the staging tiles
-  const int staging = ew * 32 * (BN / (ew / 4) * 2 + 16);
-  const bool can_stage = want_staged && !out_fp32 && (ep.ld_out & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0;
+  const int staging = tma_out ? ew * 4096 : ew * 32 * (BN / (ew / 4) * 2 + 16);
+  const bool can_stage = want_staged && aligned_out;
+  CUtensorMap tmC = tmA;  // (unused unless tma_out; a valid map keeps the __grid_constant__ copy well-defined)
+  if (tma_out) {
+    rc = make_tmap_bf16(&tmC, ep.out, M, N, ep.ld_out, 64, 32);
+    if (rc) return rc;
+  }
   if (want_two && !out_fp32 && M >= 1024 && (BN & 31) == 0 && bn_override >= 0) {
     // CTA-pair path: 256 x BN tiles, each CTA stages 128 rows of A and BN/2 rows of B per k-block
     rc = make_tmap_bf16(&tmB, B, b_rows, K, ldb, kBK, BN / 2);
     if (rc) return rc;
     const int stage2 = (kBM + BN / 2) * kBK * 2;
-    const int staged2 = (can_stage && (227 * 1024 - fixed_smem - staging) / stage2 >= 3) ? 1 : 0;
+    const int staged2 = (can_stage && (227 * 1024 - fixed_smem - staging) / stage2 >= 3) ? (tma_out ? 2 : 1) : 0;
     int st2 = (227 * 1024 - fixed_smem - (staged2 ? staging : 0)) / stage2;
     if (st2 > kMaxStages) st2 = kMaxStages;
     const int smem2 = st2 * stage2 + fixed_smem - 1024 + (staged2 ? staging : 0);
     const int tiles2 = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + BN - 1) / BN);
     const int pairs = min(tiles2, num_sms() / 2);
-    auto kern2 = ew == 16 ? gemm_tn2_kernel<__nv_bfloat16, 16> : gemm_tn2_kernel<__nv_bfloat16, 8>;
-    if (cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2) != cudaSuccess) return WM_ERR_CUDA;
-    kern2<<<2 * pairs, threads, smem2, stream>>>(tmA, tmB, M, N, K, BN, st2, staged2, ep);
-    WM_COUNT_LAUNCH();
-    return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+    if (!tma_out || staged2 == 2) {
+      auto kern2 = ew == 16 ? gemm_tn2_kernel<__nv_bfloat16, 16> : ew == 12 ? gemm_tn2_kernel<__nv_bfloat16, 12> : gemm_tn2_kernel<__nv_bfloat16, 8>;
+      if (cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2) != cudaSuccess) return WM_ERR_CUDA;
+      kern2<<<2 * pairs, threads, smem2, stream>>>(tmA, tmB, tmC, M, N, K, BN, st2, staged2, ep);
+      WM_COUNT_LAUNCH();
+      return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+    }
+    rc = make_tmap_bf16(&tmB, B, b_rows, K, ldb, kBK, BN);  // (no room for the boxes: fall through to single-CTA tiles)
+    if (rc) return rc;
   }
   const int stage_bytes = (kBM + BN) * kBK * 2;
-  const int staged1 = (can_stage && (227 * 1024 - fixed_smem - staging) / stage_bytes >= 3) ? 1 : 0;
+  const int staged1 = (can_stage && (227 * 1024 - fixed_smem - staging) / stage_bytes >= 3) ? (tma_out ? 2 : 1) : 0;
+  if (tma_out && staged1 != 2) return WM_ERR_SHAPE;  // cannot happen for BN <= 256 (3 x 48 KB + 64 KB + tail < 227 KB)
   int stages = (227 * 1024 - fixed_smem - (staged1 ? staging : 0)) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   const int smem = stages * stage_bytes + fixed_smem - 1024 + (staged1 ? staging : 0);
   const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + BN - 1) / BN;
   const int grid = min(m_tiles * n_tiles, num_sms());
   auto kern = out_fp32 ? (ew == 16 ? gemm_tn_kernel<float, 16> : gemm_tn_kernel<float, 8>)
-                       : (ew == 16 ? gemm_tn_kernel<__nv_bfloat16, 16> : gemm_tn_kernel<__nv_bfloat16, 8>);
+                       : (ew == 16 ? gemm_tn_kernel<__nv_bfloat16, 16>
+                                   : ew == 12 ? gemm_tn_kernel<__nv_bfloat16, 12> : gemm_tn_kernel<__nv_bfloat16, 8>);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
-  kern<<<grid, threads, smem, stream>>>(tmA, tmB, M, N, K, BN, stages, staged1, ep);
+  kern<<<grid, threads, smem, stream>>>(tmA, tmB, tmC, M, N, K, BN, stages, staged1, ep);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }

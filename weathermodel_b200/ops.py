@@ -133,7 +133,9 @@ def _gemm_epilogue(bias=None, relu=False, dropout_p=0.0, seed=0, stream_id=0, ga
 
 
 _TUNED_SITES = set()
-GEMM_VARIANTS = tuple((two, ew, st) for st in (0, 1) for two in (0, 1) for ew in (8, 16))  # (two_cta, epi_warps, staged stores); all bit-identical
+# (two_cta, epi_warps, staged): staged 0 = thread-per-row stores, 1 = smem-staged coalesced stores, 2 = TMA-store boxes
+# (the epilogue warp count then follows the tile width: 64 columns per warp). All bit-identical.
+GEMM_VARIANTS = tuple((two, ew, st) for st in (0, 1) for two in (0, 1) for ew in (8, 16)) + ((0, 16, 2), (1, 16, 2))
 
 
 def tune_gemm_sites(M, D, FF, dropout_p, device, min_tokens=8192, reps=5, margin=0.03):
