@@ -11,6 +11,13 @@ keeps activations and GEMM operands in bf16, 2^-9 per rounding):
   gradient norms  | ||g|| - ||g_ref|| | / ||g_ref|| <= 5e-3 per parameter tensor, 3e-3 for the global norm (measured: <= 2e-3)
   gradient field  ||g - g_ref||_F / ||g_ref||_F <= 3e-2 per tensor (bf16 operand rounding noise, unbiased)
   outputs         ||y - y_ref||_F / ||y_ref||_F <= 1e-2
+Second oracle (oracle/wm_oracle.py EncoderOracleBf16: the same algorithm with a bf16 rounding wherever the kernels
+STORE bf16, everything else exact): what is left is fp32 accumulation order, ex2.approx and values sitting on a bf16
+rounding boundary --
+  gradient field  ||g - g_bf16||_F / ||g_bf16||_F <= 4e-3 per tensor, <= 1.5e-3 global (measured: see profiles/r02_parity.txt)
+  loss            within 2e-4 relative
+i.e. the kernels implement the reference's math to ~1e-3; the remaining gap to the fp32 reference is the rounding of
+the bf16 operands north_star prescribes, and is the same size as torch.autocast(bfloat16)'s on the same GPU.
 """
 import os
 import sys
@@ -92,6 +99,21 @@ def _check_grads(model, ref_grads, tag):
     return worst
 
 
+def _check_grads_bf16_oracle(model, ref_grads, tag, per_tensor=4e-3, global_tol=1.5e-3):
+    """Against the bf16-storage oracle: only accumulation order / ex2.approx / rounding-boundary flips remain."""
+    tot_r, tot_d, worst = 0.0, 0.0, (0.0, "")
+    for name, p in model.named_parameters():
+        g = p.grad.detach().float().cpu().numpy().astype(np.float64)
+        r = np.asarray(ref_grads[name], dtype=np.float64)
+        tot_r += np.linalg.norm(r) ** 2
+        tot_d += np.linalg.norm(g - r) ** 2
+        worst = max(worst, (_rel(g, r), name))
+    gf = float(np.sqrt(tot_d / tot_r))
+    _record(f"{tag} vs bf16-storage oracle: gradient rel fro worst {worst[0]:.3e} ({worst[1]}), global rel fro {gf:.3e}")
+    assert worst[0] <= per_tensor, f"{tag}: {worst}"
+    assert gf <= global_tol, f"{tag}: global {gf}"
+
+
 def _load_golden(fname, cls):
     g = dict(np.load(os.path.join(GOLD, fname)))
     torch.manual_seed(1234)
@@ -120,6 +142,11 @@ def test_weatherbert_matches_reference_golden():
     assert abs(loss.item() - g["loss"][0]) <= 1e-3 * abs(g["loss"][0]), (loss.item(), g["loss"][0])
     worst = _check_grads(model, ref_grads, "bert")
     print("bert mini: loss", loss.item(), "ref", g["loss"][0], "worst grad rel", worst)
+    state = {k[len("param/"):]: v for k, v in g.items() if k.startswith("param/")}
+    lq, _, gq = O.train_step_grads(state, 4, "weatherbert", g["weather"], g["coords"], g["year"], g["interval"], g["mask"],
+                                   storage="bf16")
+    assert abs(loss.item() - lq["total_loss"]) <= 2e-4 * abs(lq["total_loss"]), (loss.item(), lq)
+    _check_grads_bf16_oracle(model, gq, "bert")
     # the public forward (sliced view) gives the same numbers and supports autograd through torch ops
     model.zero_grad()
     out = model(w, c, yr, iv, weather_feature_mask=mask)
@@ -140,6 +167,11 @@ def test_weatherformer_matches_reference_golden():
     losses["total_loss"].backward()
     _check_losses({k: v.item() for k, v in losses.items()}, dict(zip(("total_loss", "reconstruction", "kl_term"), g["loss"])))
     worst = _check_grads(model, ref_grads, "former")
+    state = {k[len("param/"):]: v for k, v in g.items() if k.startswith("param/")}
+    lq, _, gq = O.train_step_grads(state, 4, "weatherformer", g["weather"], g["coords"], g["year"], g["interval"],
+                                   g["mask"], beta=float(g["beta"][0]), storage="bf16")
+    assert abs(losses["total_loss"].item() - lq["total_loss"]) <= 2e-4 * abs(lq["total_loss"]), (losses, lq)
+    _check_grads_bf16_oracle(model, gq, "former")
     print("former mini: losses", {k: v.item() for k, v in losses.items()}, "ref", g["loss"], "worst", worst)
 
 
@@ -175,6 +207,10 @@ def test_model_matches_numpy_oracle(kind, size, B, S):
     _check_losses({k: v.item() for k, v in losses.items()}, losses_ref)
     worst = _check_grads(model, grads_ref, f"{kind}-{size}")
     print(kind, size, "loss", losses["total_loss"].item(), "oracle", losses_ref["total_loss"], "worst grad", worst)
+    lq, _, gq = O.train_step_grads(state, hp["num_heads"], kind, weather, coords, year, interval, mask, beta=0.5,
+                                   storage="bf16")
+    assert abs(losses["total_loss"].item() - lq["total_loss"]) <= 2e-4 * abs(lq["total_loss"]), (losses, lq)
+    _check_grads_bf16_oracle(model, gq, f"{kind}-{size}")
 
 
 def test_fused_adam_training_reduces_loss_and_matches_torch_adam():

@@ -92,6 +92,29 @@ def test_encoder_loss_and_grads_match_reference(fname, model):
         assert rel < 1e-3, f"{k}: relative error {rel}"  # fp32 reference vs fp64 oracle noise floor is ~4e-4
 
 
+def test_bf16_storage_oracle_is_the_same_algorithm():
+    """EncoderOracleBf16 with the rounding switched off IS EncoderOracle (so it inherits the golden pinning); with
+    it on, it predicts the size of the bf16 gap to the fp32 reference (what the B200 path is then measured against in
+    tests/test_gpu_model.py)."""
+    assert np.array_equal(O.bf16_round(np.array([1.0, 1.00390625, 1.001953125, 1.005859375, -3.14159, 0.0])),
+                          np.array([1.0, 1.0, 1.0, 1.0078125, -3.140625, 0.0]))  # ties to even; 2^-8 spacing at 1
+    g = _load("weatherformer_mini_b8.npz")
+    state = {k[len("param/"):]: v for k, v in g.items() if k.startswith("param/")}
+    args = (g["weather"], g["coords"], g["year"], g["interval"], g["mask"])
+    l0, Y0, g0 = O.train_step_grads(state, 4, "weatherformer", *args, beta=0.5)
+    enc = O.EncoderOracleBf16(state, 4, quant=False)
+    Y = enc.forward(*args)
+    _, dY = O.former_elbo(Y, g["weather"], g["mask"], 0.5, 31)
+    gi = enc.backward(dY)
+    assert np.allclose(Y, Y0, rtol=0, atol=1e-6)  # (year / coords are normalised in float32 as the kernel does)
+    for k, v in g0.items():
+        assert np.linalg.norm(gi[k] - v) <= 1e-6 * np.linalg.norm(v), k
+    lq, _, gq = O.train_step_grads(state, 4, "weatherformer", *args, beta=0.5, storage="bf16")
+    assert abs(lq["total_loss"] - l0["total_loss"]) < 1e-3 * l0["total_loss"]
+    rels = [np.linalg.norm(gq[k] - v) / np.linalg.norm(v) for k, v in g0.items()]
+    assert 2e-3 < max(rels) < 3e-2, max(rels)  # the bf16 operand-rounding gap: ~1e-2 on the worst tensor
+
+
 def test_known_answers_from_survey():
     """loss and gradient norms of the reference (CPU fp32) for the mini models."""
     g = _load("weatherbert_mini_b8.npz")

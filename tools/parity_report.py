@@ -89,7 +89,8 @@ def run_torch_autocast(kind, hp, state, batch, beta):
     return {k: v.item() for k, v in losses.items()}, grads
 
 
-def report(title, kind, losses, ref_losses, grads, ref_grads, y=None, y_ref=None, extra=None, out=None):
+def report(title, kind, losses, ref_losses, grads, ref_grads, y=None, y_ref=None, extra=None, out=None, bf16_grads=None,
+           bf16_losses=None):
     rows, glob = grad_table(grads, ref_grads)
     lines = [f"== {title}"]
     for k, r in ref_losses.items():
@@ -107,15 +108,28 @@ def report(title, kind, losses, ref_losses, grads, ref_grads, y=None, y_ref=None
         lines.append(f"   torch autocast(bf16) on the same GPU: rel fro max {fro2.max():.2e} median {np.median(fro2):.2e}; "
                      f"GLOBAL rel fro {glob2['fro']:.2e} norm {glob2['norm']:.2e}")
         extra_map = {t[0]: t[1] for t in rows2}
-    lines.append(f"   {'tensor':58s} {'rel fro':>9s} {'norm err':>9s} {'||ref||':>10s}" + ("  torch-bf16 fro" if extra is not None else ""))
+    q_map = None
+    if bf16_grads is not None:  # the same algorithm with a rounding wherever the kernels store bf16 (EncoderOracleBf16)
+        rows3, glob3 = grad_table(grads, bf16_grads)
+        fro3 = np.array([t[1] for t in rows3])
+        w3 = max(rows3, key=lambda t: t[1])
+        lines.append(f"   vs bf16-STORAGE oracle (same roundings as the kernels): rel fro max {fro3.max():.2e} ({w3[0]}) median "
+                     f"{np.median(fro3):.2e}; GLOBAL rel fro {glob3['fro']:.2e} norm {glob3['norm']:.2e}; loss rel "
+                     f"{abs(losses['total_loss'] - bf16_losses['total_loss']) / abs(bf16_losses['total_loss']):.2e}")
+        q_map = {t[0]: t[1] for t in rows3}
+    lines.append(f"   {'tensor':58s} {'rel fro':>9s} {'norm err':>9s} {'||ref||':>10s}" + ("  torch-bf16 fro" if extra is not None else "") + ("  vs bf16-oracle" if q_map else ""))
     for name, f, n, nr in rows:
-        lines.append(f"   {name:58s} {f:9.2e} {n:9.2e} {nr:10.3e}" + (f"  {extra_map[name]:9.2e}" if extra is not None else ""))
+        lines.append(f"   {name:58s} {f:9.2e} {n:9.2e} {nr:10.3e}" + (f"  {extra_map[name]:9.2e}" if extra is not None else "") +
+                     (f"      {q_map[name]:9.2e}" if q_map else ""))
     text = "\n".join(lines)
     print(text, flush=True)
     if out:
         out.write(text + "\n")
-    return {"fro_max": float(fro.max()), "fro_median": float(np.median(fro)), "norm_max": float(nrm.max()),
-            "global_fro": glob["fro"], "global_norm": glob["norm"]}
+    res = {"fro_max": float(fro.max()), "fro_median": float(np.median(fro)), "norm_max": float(nrm.max()),
+           "global_fro": glob["fro"], "global_norm": glob["norm"]}
+    if q_map:
+        res.update(bf16_oracle_fro_max=float(fro3.max()), bf16_oracle_global_fro=glob3["fro"])
+    return res
 
 
 def golden_case(fname, cls, kind, out):
@@ -136,8 +150,10 @@ def golden_case(fname, cls, kind, out):
     ref_losses = dict(zip(names, [float(v) for v in g["loss"]]))
     state = {k[len("param/"):]: v for k, v in g.items() if k.startswith("param/")}
     _, tgrads = run_torch_autocast(kind, hp, state, batch, beta)
+    lq, _, gq = O.train_step_grads(state, hp["num_heads"], kind, g["weather"], g["coords"], g["year"], g["interval"], g["mask"],
+                                   beta=beta, storage="bf16")
     return report(f"{kind} mini, B=8, golden vectors of the unmodified reference ({fname})", kind, losses, ref_losses, grads,
-                  ref_grads, extra=tgrads, out=out)
+                  ref_grads, extra=tgrads, out=out, bf16_grads=gq, bf16_losses=lq)
 
 
 def oracle_case(kind, size, B, S, out):
@@ -160,8 +176,9 @@ def oracle_case(kind, size, B, S, out):
     batch = tuple(torch.from_numpy(a).to(DEV) for a in (weather, coords, year, interval)) + (torch.from_numpy(mask).to(DEV),)
     losses, grads, y = run_ours(model, kind, batch, 0.5)
     _, tgrads = run_torch_autocast(kind, hp, state, batch, 0.5)
+    lq, _, gq = O.train_step_grads(state, hp["num_heads"], kind, weather, coords, year, interval, mask, beta=0.5, storage="bf16")
     return report(f"{kind} {size}, B={B}, S={S}, numpy fp64 oracle", kind, losses, ref_losses, grads, ref_grads,
-                  y[..., : y_ref.shape[-1]], y_ref, extra=tgrads, out=out)
+                  y[..., : y_ref.shape[-1]], y_ref, extra=tgrads, out=out, bf16_grads=gq, bf16_losses=lq)
 
 
 def main():
