@@ -194,6 +194,36 @@ def test_streaming_loader_reproduces_reference_sample_stream(tmp_path, monkeypat
     assert batches[0][4].dtype == torch.bool and batches[0][3].shape == (8, 1)
 
 
+@pytest.mark.parametrize("kind,shuffle", [("weatherbert", True), ("weatherformer", True), ("weatherformer", False)])
+def test_streaming_loader_matches_the_reference_loaders_own_stream(tmp_path, monkeypatch, kind, shuffle):
+    """tests/golden/loader_stream_*.npz was dumped from the UNMODIFIED reference `streaming_dataloader` iterating the
+    same synthetic chunk files (oracle/make_golden_loader.py): sample order, cutoff filtering, batch boundaries across
+    chunks, years, coords, intervals and every mask bit must be identical."""
+    import src.pretraining.dataloader.pretraining_dataloader as dl
+
+    gold = dict(np.load(os.path.join(os.path.dirname(__file__), "golden",
+                                     f"loader_stream_{kind}_{'shuffle' if shuffle else 'ordered'}.npz")))
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(dl, "DRY_RUN", True)
+    _write_chunks("data/nasa_power/processed/", [1, 34, 53, 72, 81], n=21, late_every=5)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: False)
+    random.seed(99)
+    torch.manual_seed(1234)
+    loader = dl.streaming_dataloader(8, split="train", shuffle=shuffle, masking_function=kind, masking_prob=0.3,
+                                     n_masked_features=7)
+    assert [int(p_.split("_")[-1].split(".")[0]) for p_ in loader.dataset.file_paths[1::3]] == gold["chunk_order"].tolist()
+    batches = list(loader)
+    assert [b[0].shape[0] for b in batches] == gold["batch_sizes"].tolist()
+    cat = [torch.cat([b[i] for b in batches]) for i in range(5)]
+    n = cat[0].shape[0]
+    assert np.array_equal(cat[0][:, 0, 0].numpy(), gold["key"])
+    assert np.array_equal(cat[0].double().sum((1, 2)).numpy(), gold["weather_sum"])
+    assert np.array_equal(cat[1].numpy(), gold["coords"])
+    assert np.array_equal(cat[2].numpy(), gold["year"])  # float32, same op order
+    assert np.array_equal(cat[3].numpy(), gold["interval"])
+    assert np.array_equal(np.packbits(cat[4].numpy().reshape(n, -1), axis=1), gold["mask_bits"])
+
+
 def test_fused_adam_host_path_matches_torch_adam():
     from weathermodel_b200.optim import FusedAdam
 
