@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- pretrain sequences/sec of the WeatherModel hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload large|medium|small|mini] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload large|medium|small|mini|yield]
+                    [--impl ours|reference|torch-gpu] [--no-trainer]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -10,7 +11,10 @@ synthetic batch of 365-day x 31-feature sequences, dropout 0.1 live as in the re
 WeatherFormer large (D=576, H=16, L=8), beta-KL ELBO, 512 sequences per GPU (BASELINE.json configs[3], weak
 scaling). Rank 0 prints ONE JSON line. `--impl reference` times the reference's CPU PyTorch path (torch-CPU
 port in oracle/torch_port.py; the reference is pure Python over torch and cannot be installed) on the host
-cores with a bounded batch of the same model.
+cores with a bounded batch of the same model. At N = 1 the line also carries `e2e_trainer`: the same metric through
+the drop-in trainer itself (WeatherFormerTrainer / WeatherBertTrainer._train_epoch over synthetic on-disk chunks read
+by streaming_dataloader) -- what a user of the CLI gets. `--impl torch-gpu` is informational only (never the reference
+arm): the torch port of the reference on the SAME B200 in fp32 eager and under bf16 autocast.
 """
 import argparse
 import json
@@ -126,6 +130,135 @@ def run_reference(args, rank):
         "loss": loss,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ informational
+def run_torch_gpu(args, rank):
+    """The reference's step in stock PyTorch on the same B200 (the honest same-box comparator): the
+    torch port of the reference (oracle/torch_port.py, stock nn.TransformerEncoder / Adam) in fp32 eager exactly as the
+    reference runs it, and under torch.autocast(bfloat16). Informational: `"impl": "torch-gpu"`, never the reference arm."""
+    if rank != 0:
+        return
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port
+
+    kind, size, B, _ = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    dev = torch.device("cuda:0")
+    out = {}
+    for mode in ("fp32", "bf16-autocast"):
+        torch.manual_seed(1234)
+        model = torch_port.PortModel(kind, **size_params(size)).to(dev).train()
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+        g = torch.Generator().manual_seed(0)
+        w = torch.randn(B, S, F, generator=g).to(dev)
+        c = torch.stack([torch.rand(B, generator=g) * 120 - 60, torch.rand(B, generator=g) * 360 - 180], 1).to(dev)
+        idx = torch.randint(0, 2, (B,), generator=g).float()
+        y = (1984.0 + ((idx[:, None] * 365 + torch.arange(S, dtype=torch.float32)[None]) * 7.0) / 365).to(dev)
+        iv = torch.full((B, 1), 7.0, device=dev)
+
+        def step():
+            if kind == "weatherformer":
+                mask = (torch.argsort(torch.rand(B, F, device=dev), dim=-1) < 10).unsqueeze(1).expand(-1, S, -1)
+            else:
+                mask = torch.rand(B, S, F, device=dev) < 0.15
+            opt.zero_grad()
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode != "fp32")):
+                loss = torch_port.port_loss(model, w, c, y, iv, mask, 0.5)["total_loss"]
+            loss.backward()
+            opt.step()
+            return loss
+
+        try:
+            for _ in range(max(2, args.warmup)):
+                step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.steps):
+                last = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            out[mode] = {"ms_per_step": ms, "sequences_per_s": B / (ms * 1e-3), "loss": last.item(),
+                         "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        except torch.cuda.OutOfMemoryError as e:  # pragma: no cover
+            out[mode] = {"error": f"out of memory: {str(e)[:80]}"}
+        del model, opt
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+    best = max((v.get("sequences_per_s", 0.0) for v in out.values()), default=0.0)
+    print(json.dumps({"impl": "torch-gpu", "metric": "pretrain sequences/sec (365d x 31 feat)", "value": best,
+                      "unit": "sequences/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "higher_is_better": True, "data": "synthetic",
+                      "config": {"workload": f"{kind}-{size} pretraining step, {B} sequences, stock PyTorch {torch.__version__} "
+                                             "modules (nn.TransformerEncoder, SDPA, optim.Adam), dropout 0.1"},
+                      "modes": out}), flush=True)
+
+
+def trainer_leg(kind, size, B, dev, steps_per_epoch=16, chunk=4096):
+    """Sequences/s through the drop-in trainer: <Model>Trainer._train_epoch over synthetic chunk files in the
+    reference's on-disk format, read by streaming_dataloader (torch.load -> mask -> randperm -> batches),
+    zero_grad / compute_train_loss / backward / FusedAdam.step exactly as the CLI runs them. One untimed epoch
+    (handles, tuner, page cache), then one timed epoch bracketed by CUDA events + synchronize."""
+    import tempfile
+
+    import torch
+
+    import weathermodel_b200.pretraining.dataloader.pretraining_dataloader as dl
+    from weathermodel_b200.pretraining.models.weatherbert import WeatherBERT
+    from weathermodel_b200.pretraining.models.weatherformer import WeatherFormer
+    from weathermodel_b200.pretraining.trainers.weatherbert_trainer import WeatherBertTrainer
+    from weathermodel_b200.pretraining.trainers.weatherformer_trainer import WeatherFormerTrainer
+
+    n_chunks = max(1, (steps_per_epoch * B + chunk - 1) // chunk)
+    ids = [1, 34, 53, 72, 81][:n_chunks]
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="wm_bench_chunks_")
+    try:
+        os.chdir(tmp)
+        base = "data/nasa_power/processed/"
+        os.makedirs(base)
+        g = torch.Generator().manual_seed(0)
+        for cid in ids:
+            w = torch.randn(chunk, S, F, generator=g)
+            coords = torch.stack([torch.rand(chunk, generator=g) * 120 - 60, torch.rand(chunk, generator=g) * 360 - 180], 1)
+            index = torch.stack([torch.randint(0, 2, (chunk,), generator=g).float(), torch.full((chunk,), 7.0)], 1)
+            torch.save(torch.utils.data.TensorDataset(w, coords, index), base + f"weather_dataset_weekly_{cid}.pt")
+        orig = dl.chunk_ids_for
+        dl.chunk_ids_for = lambda split, world_size=1, rank=0: list(ids) if split.lower() == "train" else list(ids[:1])
+        torch.manual_seed(1234)
+        common = dict(batch_size=B, num_epochs=4, init_lr=5e-4, num_warmup_epochs=0, decay_factor=0.99)
+        if kind == "weatherformer":
+            model = WeatherFormer(weather_dim=F, output_dim=F, device=dev, **size_params(size)).to(dev)
+            tr = WeatherFormerTrainer(model, masking_prob=0.15, n_masked_features=10, beta=0.5, **common)
+        else:
+            model = WeatherBERT(weather_dim=F, output_dim=F, device=dev, **size_params(size)).to(dev)
+            tr = WeatherBertTrainer(model, masking_prob=0.15, n_masked_features=1, **common)
+        tr.current_epoch = 0
+        tr._train_epoch(tr.get_dataloaders(shuffle=True)[0])  # untimed
+        loader = tr.get_dataloaders(shuffle=True)[0]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        loss = tr._train_epoch(loader)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        n = n_chunks * chunk
+        dl.chunk_ids_for = orig
+        return {"value": n / (ms * 1e-3), "unit": "sequences/s", "ms_per_step": ms / (n / B), "steps": n // B,
+                "epoch_loss": loss,
+                "what": f"{type(tr).__name__}._train_epoch over {n_chunks} chunk files of {chunk} sequences via "
+                        f"streaming_dataloader (disk -> pinned host -> device, masks, randperm, batches of {B}), FusedAdam"}
+    finally:
+        os.chdir(cwd)
+        import shutil
+
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -268,7 +401,9 @@ def run_ours(args, rank, world, local_rank):
         achieved = 2.0 * M * FF * D / (gemm_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tn_kernel<bf16> (linear1: M x 4D x D, bias+ReLU epilogue)",
                 "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((M, FF, D)), "peak_source": pk["source"] + " burst (kernel timed alone)",
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((M, FF, D)),
+                "traffic_source": "constant from the committed ncu --set full capture (profiles/), not measured in this run",
+                "peak_source": pk["source"] + " burst (kernel timed alone)",
                 "launch_ms": gemm_ms, "shape": [M, FF, D]}
         also["step_tensor_frac_of_sustained"] = (value / world) * flops_seq / (pk["tf_sustained"] * 1e12)
         also["algorithmic_gflop_per_seq"] = flops_seq / 1e9
@@ -285,6 +420,17 @@ def run_ours(args, rank, world, local_rank):
         sec = sum(times) / len(times)
         cpu = {"value": ref_batch / sec, "unit": "sequences/s", "cores": threads, "kind": "port",
                "sample": f"{kind}-{size}, {ref_batch} sequences/step x 2 steps (+1 warm-up), torch CPU fp32, dropout on"}
+        if args.workload != "mini":  # BASELINE configs[0], the reference's own CPU-runnable case: WeatherBERT mini, batch 64
+            t1, _ = torch_port.time_port_steps("weatherbert", size_params("mini"), 64, 3, 1, threads)
+            cpu["config1_weatherbert_mini_b64"] = {"value": 64 / (sum(t1) / len(t1)), "unit": "sequences/s",
+                                                   "sample": "64 sequences/step x 3 steps (+1 warm-up)"}
+
+    # ---- the same metric through the drop-in trainer and loader (N == 1 only: DRY_RUN-sized chunk lists do not split 8 ways)
+    trainer = None
+    if rank == 0 and world == 1 and not args.no_trainer:
+        del resident, staging
+        torch.cuda.empty_cache()
+        trainer = trainer_leg(kind, size, B, dev)
 
     if rank == 0:
         line = {
@@ -301,6 +447,7 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks.summary(),
             "roofline": roof,
             "cpu_baseline": cpu,
+            "e2e_trainer": trainer,
             "loss": loss_val, "loss_e2e": loss_e2e,
         }
         line.update(also)
@@ -320,8 +467,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-trainer", action="store_true", help="skip the trainer-level e2e leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", 0))
@@ -329,6 +477,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.impl == "torch-gpu":
+        run_torch_gpu(args, rank)
         return
     if world > 1:
         import torch

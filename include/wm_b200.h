@@ -147,6 +147,31 @@ int wm_loss_former_grad(const float* y, int ldy, const float* weather, const uin
                         int64_t mask_stride_s, int B, int S, int F, float beta, const float* scratch,
                         const float* grad_scale, void* dy_bf16, int lddy, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Crop-yield head (BASELINE configs[5]), one forward and one backward kernel on the raw encoder head output:
+ *   WeatherBERTYieldModel._impute_weather + yield_model  src/crop_yield/models/weatherbert_yield_model.py:40-67
+ *   WeatherFormerYieldModel.forward (z = mu + sqrt(var) eps)  src/crop_yield/models/weatherformer_yield_model.py:58-60
+ * y: fp32 [B*S, ldy] raw head output ([pred | pad] or [mu | logvar | pad]); eps: fp32 [B,S,F] standard-normal noise
+ * (WeatherFormer only; drawn by the caller so that the torch generator is consumed exactly as randn_like does);
+ * y_past [B, n_past]; the head's parameters as the reference modules hold them: att_w1 [16,F], att_b1 [16],
+ * att_w2 [1,16], att_b2 [1], mlp_w1 [HM, F + n_past], mlp_b1 [HM], mlp_w2 [1,HM], mlp_b2 [1].
+ * Forward: z_out fp32 [B,S,F] (imputed / sampled weather; also what backward needs), pred fp32 [B].
+ * Backward: dy fp32 [B*S, ldy] = dLoss/dy through the head (pad columns zeroed); grads: the parameter gradients
+ * flattened in the order above (wm_yield_head_param_count floats); partial: B * that many floats of workspace.
+ * Deterministic (fixed-order reductions): yield_main sets torch.use_deterministic_algorithms(True). S <= 384, F <= 32. */
+int wm_yield_head_param_count(int F, int n_past, int HM);
+int wm_yield_head_fwd(const float* y, int ldy, int is_former, const float* weather, const uint8_t* mask,
+                      int64_t mask_stride_b, int64_t mask_stride_s, const float* eps, const float* y_past, int n_past,
+                      const float* att_w1, const float* att_b1, const float* att_w2, const float* att_b2,
+                      const float* mlp_w1, const float* mlp_b1, const float* mlp_w2, const float* mlp_b2,
+                      float* z_out, float* pred, int B, int S, int F, int HM, void* stream);
+int wm_yield_head_bwd(const float* dpred, const float* y, int ldy, int is_former, const uint8_t* mask,
+                      int64_t mask_stride_b, int64_t mask_stride_s, const float* eps, const float* z_saved,
+                      const float* y_past, int n_past, const float* att_w1, const float* att_b1, const float* att_w2,
+                      const float* att_b2, const float* mlp_w1, const float* mlp_b1, const float* mlp_w2,
+                      const float* mlp_b2, float* dy, float* partial, float* grads, int B, int S, int F, int HM,
+                      void* stream);
+
 /* ---- optimiser: torch.optim.Adam as built at src/base_trainer/base_trainer.py:337 ------------------- */
 int wm_adam_fused(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                   void* shadow_bf16 /* optional */, int64_t n, float lr, float beta1, float beta2, float eps,

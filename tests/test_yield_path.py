@@ -171,3 +171,68 @@ def test_yield_model_matches_reference_golden(kind, monkeypatch):
         worst = max(worst, (rel, name))
         assert rel <= 3e-2, f"{kind} yield: grad {name} rel err {rel:.4g}"
     print(kind, "yield: loss", loss.item(), "ref", g["loss"][0], "worst grad", worst)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["weatherbert", "weatherformer"])
+def test_fused_yield_head_matches_the_torch_op_head(kind, monkeypatch):
+    """wm_yield_head_fwd / _bwd (one kernel each) against the reference's own torch-op head
+    (weatherbert_yield_model.py:40-67, weatherformer_yield_model.py:58-60) on the same encoder output: prediction,
+    z, every head-parameter gradient and the gradient handed back to the encoder (seen through in_proj.weight.grad),
+    fp32 on both sides -> 1e-5; twice the same result bit for bit (deterministic reductions)."""
+    from src.crop_yield.models.weatherbert_yield_model import WeatherBERTYieldModel
+    from src.crop_yield.models.weatherformer_yield_model import WeatherFormerYieldModel
+    from src.utils.utils import get_model_params
+
+    cls = WeatherBERTYieldModel if kind == "weatherbert" else WeatherFormerYieldModel
+    torch.manual_seed(5)
+    model = cls(name="y", device=torch.device("cuda"), weather_dim=31, n_past_years=6, **get_model_params("mini")).to("cuda").train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    B, S = 7, 364
+    g = torch.Generator(device="cuda").manual_seed(1)
+    w = torch.randn(B, S, 31, device="cuda", generator=g)
+    c = torch.rand(B, 2, device="cuda", generator=g) * 60
+    yr = 1990 + torch.arange(S, device="cuda").float()[None].repeat(B, 1) / 52
+    iv = torch.full((B, 1), 7.0, device="cuda")
+    mask = torch.ones(B, S, 31, dtype=torch.bool, device="cuda")
+    mask[:, :, [7, 8, 11, 1, 2, 29]] = False  # the yield loader's six observed features
+    y_past = torch.randn(B, 7, device="cuda", generator=g)
+    target = torch.randn(B, 1, device="cuda", generator=g)
+    eps = torch.randn(B, S, 31, device="cuda", generator=g)
+    monkeypatch.setattr(torch, "randn_like", lambda x, *a, **k: eps)
+
+    def run(fused):
+        monkeypatch.setattr(cls, "_fused_head_ok", (lambda self, *_: True) if fused else (lambda self, *_: False))
+        model.zero_grad()
+        out = model(w, c, yr, iv, mask, y_past)
+        pred = out if kind == "weatherbert" else out[0]
+        loss = torch.nn.functional.mse_loss(pred, target)
+        if kind == "weatherformer":
+            loss = loss + 1e-3 * (out[2] ** 2 + out[3]).mean()  # touches mu and var through torch ops as the KL term does
+        loss.backward()
+        return (pred.detach().clone(), None if kind == "weatherbert" else out[1].detach().clone(),
+                {n: p.grad.detach().clone() for n, p in model.named_parameters()})
+
+    pred_t, z_t, g_t = run(False)
+    pred_f, z_f, g_f = run(True)
+    pred_f2, _, g_f2 = run(True)
+    assert torch.equal(pred_f, pred_f2) and all(torch.equal(g_f[n], g_f2[n]) for n in g_f)
+    assert torch.allclose(pred_f, pred_t, rtol=1e-5, atol=1e-6), (pred_f.flatten(), pred_t.flatten())
+    if z_t is not None:
+        assert torch.allclose(z_f, z_t, rtol=1e-5, atol=1e-6)
+    for n in g_t:
+        ref = g_t[n]
+        err = (g_f[n] - ref).norm() / (ref.norm() + 1e-20)
+        if "weather_model" in n:
+            assert err < 2e-2, (n, err.item())  # encoder gradients pass through bf16 kernels on both paths
+        elif ref.norm() > 1e-7:
+            assert err < 2e-5, (n, err.item())
+        else:
+            assert g_f[n].norm() < 1e-6, n  # the bias in front of the softmax: mathematically zero

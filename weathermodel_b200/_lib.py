@@ -61,6 +61,10 @@ SIGNATURES = {
     "wm_loss_former": (_i, [_vp, _i, _vp, _vp, _i64, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "wm_loss_bert_grad": (_i, [_vp, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp]),
     "wm_loss_former_grad": (_i, [_vp, _i, _vp, _vp, _i64, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp]),
+    "wm_yield_head_param_count": (_i, [_i, _i, _i]),
+    "wm_yield_head_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i64, _vp, _vp, _i] + [_vp] * 8 + [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "wm_yield_head_bwd": (_i, [_vp, _vp, _i, _i, _vp, _i64, _i64, _vp, _vp, _vp, _i] + [_vp] * 8 +
+                          [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wm_adam_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "wm_encoder_param_count": (_i64, [C.POINTER(EncoderConfig)]),
     "wm_encoder_param_layout": (_i, [C.POINTER(EncoderConfig), C.POINTER(_i64), _i]),

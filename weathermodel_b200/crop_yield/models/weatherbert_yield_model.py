@@ -2,15 +2,18 @@
 (reference src/crop_yield/models/weatherbert_yield_model.py:11-132).
 
 The encoder call -- the only part that matters for time -- runs on the sm_100a kernels through
-WeatherBERT.forward (autograd flows back into the fused backward). The head is the reference's own tiny torch
-modules: masked-feature imputation, a 31->16->1 attention pooling over the sequence and a (31 + n_past_years + 1)
-->120->1 MLP (a few hundred FLOPs per sequence, "next" row f2 for a fused kernel)."""
+WeatherBERT.forward (autograd flows back into the fused backward). The head keeps the reference's own torch modules
+as PARAMETER CONTAINERS (same state_dict keys, same initialisation): masked-feature imputation, a 31->16->1 attention
+pooling over the sequence and a (31 + n_past_years + 1)->120->1 MLP. On CUDA with the stock head shapes the arithmetic
+runs as one forward and one backward kernel (engine.yield_head -> wm_yield_head_fwd / _bwd: ~40 eager launches per
+step otherwise, on a step that is launch-bound at B <= 64); anything else takes the torch-op path below."""
 from typing import Union
 
 import torch
 import torch.nn as nn
 
 from ...base_models.base_model import BaseModel
+from ...engine import yield_head
 from ...pretraining.models.weatherbert import WeatherBERT
 
 
@@ -45,7 +48,28 @@ class WeatherBERTYieldModel(BaseModel):
             raise ValueError(f"provided model class: {pretrained_model.__class__.__name__} is not supported")
         self.weather_model.load_pretrained(encoder, load_out_proj=True)
 
+    def _head_params(self):
+        a, m = self.weather_attention, self.yield_mlp
+        return (a[0].weight, a[0].bias, a[2].weight, a[2].bias, m[0].weight, m[0].bias, m[2].weight, m[2].bias)
+
+    def _fused_head_ok(self, weather, y_past) -> bool:
+        """Stock head shapes on a CUDA batch, and nobody overrode the head's pieces."""
+        cls = type(self)
+        a, m = self.weather_attention, self.yield_mlp
+        return (weather.is_cuda and weather.shape[1] <= 384 and weather.shape[2] <= 32
+                and cls.yield_model is WeatherBERTYieldModel.yield_model
+                and cls._impute_weather is WeatherBERTYieldModel._impute_weather
+                and isinstance(a, nn.Sequential) and len(a) == 3 and isinstance(a[0], nn.Linear) and a[0].out_features == 16
+                and isinstance(a[1], nn.GELU) and a[1].approximate == "none" and a[2].out_features == 1
+                and isinstance(m, nn.Sequential) and len(m) == 3 and m[0].out_features <= 128 and m[2].out_features == 1
+                and isinstance(m[1], nn.GELU) and m[1].approximate == "none"
+                and m[0].in_features == weather.shape[2] + y_past.shape[1] <= 64)
+
     def forward(self, weather, coord, year, interval, weather_feature_mask, y_past):
+        if self._fused_head_ok(weather, y_past):
+            y_pad = self.weather_model.forward_raw(weather, coord, year, interval, weather_feature_mask)
+            pred, _ = yield_head(y_pad, weather, weather_feature_mask, None, y_past, self._head_params(), is_former=False)
+            return pred
         predicted = self.weather_model(weather, coord, year, interval, weather_feature_mask=weather_feature_mask)
         filled = self._impute_weather(weather, predicted, weather_feature_mask)
         return self.yield_model(filled, coord, year, interval, weather_feature_mask=None, y_past=y_past)

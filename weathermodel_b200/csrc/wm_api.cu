@@ -220,4 +220,32 @@ int wm_adam_fused(float* param, const float* grad, float* exp_avg, float* exp_av
                      grad_scale, S_(stream));
 }
 
+int wm_yield_head_param_count(int F, int n_past, int HM) {
+  if (F <= 0 || F > 32 || n_past < 0 || HM <= 0 || HM > 128) return -1;
+  return yield_head_param_count(F, n_past, HM);
+}
+
+int wm_yield_head_fwd(const float* y, int ldy, int is_former, const float* weather, const uint8_t* mask,
+                      int64_t mask_stride_b, int64_t mask_stride_s, const float* eps, const float* y_past, int n_past,
+                      const float* att_w1, const float* att_b1, const float* att_w2, const float* att_b2,
+                      const float* mlp_w1, const float* mlp_b1, const float* mlp_w2, const float* mlp_b2,
+                      float* z_out, float* pred, int B, int S, int F, int HM, void* stream) {
+  if (!att_w1 || !att_b1 || !att_w2 || !att_b2 || !mlp_w1 || !mlp_b1 || !mlp_w2 || !mlp_b2) return WM_ERR_ARG;
+  const YieldHeadW W{att_w1, att_b1, att_w2, att_b2, mlp_w1, mlp_b1, mlp_w2, mlp_b2};
+  return launch_yield_head_fwd(y, ldy, is_former, weather, mask, mask_stride_b, mask_stride_s, eps, y_past, n_past, W,
+                               z_out, pred, B, S, F, HM, S_(stream));
+}
+
+int wm_yield_head_bwd(const float* dpred, const float* y, int ldy, int is_former, const uint8_t* mask,
+                      int64_t mask_stride_b, int64_t mask_stride_s, const float* eps, const float* z_saved,
+                      const float* y_past, int n_past, const float* att_w1, const float* att_b1, const float* att_w2,
+                      const float* att_b2, const float* mlp_w1, const float* mlp_b1, const float* mlp_w2,
+                      const float* mlp_b2, float* dy, float* partial, float* grads, int B, int S, int F, int HM,
+                      void* stream) {
+  if (!att_w1 || !att_b1 || !att_w2 || !att_b2 || !mlp_w1 || !mlp_b1 || !mlp_w2 || !mlp_b2) return WM_ERR_ARG;
+  const YieldHeadW W{att_w1, att_b1, att_w2, att_b2, mlp_w1, mlp_b1, mlp_w2, mlp_b2};
+  return launch_yield_head_bwd(dpred, y, ldy, is_former, mask, mask_stride_b, mask_stride_s, eps, z_saved, y_past, n_past,
+                               W, dy, partial, grads, B, S, F, HM, S_(stream));
+}
+
 }  // extern "C"

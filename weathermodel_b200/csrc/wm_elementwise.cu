@@ -93,100 +93,136 @@ int launch_mask_former(uint64_t seed, uint64_t philox_offset, int grid_x, int n_
 }
 
 // ------------------------------------------------------------------------------------------------
-// embed_fwd. CTA = 64 tokens x all D; rows of W_in staged in smem as [D][41] fp32.
+// embed_fwd: out[t, :] = bf16( ([w * ~m, year', lat', lon'] . W_in^T + b_in) + PE[t % S] ), fp32 FMA throughout.
+// Register-tiled like an SGEMM with K = 34: a CTA owns a strip of CT <= 320 output columns, keeps that strip of
+// W_in^T in shared memory for its whole life and walks over 64-token tiles (persistent: one launch wave, two CTAs
+// per SM so that one CTA's tile load overlaps the other's arithmetic). A thread computes 8 tokens x 8 columns with
+// packed fp32 FMAs (FFMA2: one issue slot per two multiply-adds): per input channel 4 + 2 shared-memory loads feed
+// 32 FFMA2 -- ~22 issued instructions per output element-pair... the first version (one column per thread, scalar
+// FMAs, 2-byte stores) needed 55 per element and ran at 0.64-0.76 ms for the large shape (5 % of the HBM roofline).
+// The input tile is stored DUPLICATED ((x, x) pairs) so that the broadcast operand of an FFMA2 needs no MOV.
 // ------------------------------------------------------------------------------------------------
-// tokens per CTA: the 34 x D weight matrix is staged once per CTA (94 KB at D = 576), so long CTAs amortise it
-// (256 tokens: 0.74 -> 0.64 ms at the large shape); short ones keep small batches spread over all SMs
-constexpr int kEmbTokLong = 256, kEmbTokShort = 64;
-constexpr int kXinLd = 64;  // padded bf16 copy of the 34-channel input row (wgrad operand)
+constexpr int kEmbTok = 64;   // tokens per tile
+constexpr int kXinLd = 64;    // padded bf16 copy of the 34-channel input row (wgrad operand)
+constexpr int kEmbMaxCT = 320;
 
-__global__ void __launch_bounds__(768)
+__global__ void __launch_bounds__(kEmbMaxCT, 2)
 embed_fwd_kernel(const float* __restrict__ weather, const uint8_t* __restrict__ mask, int64_t msb, int64_t mss,
                  const float* __restrict__ year, const float* __restrict__ coords,
                  const float* __restrict__ w_in, const float* __restrict__ b_in, const float* __restrict__ pe,
-                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ xin, int B, int S, int F, int D, int kEmbTok) {
-  extern __shared__ float smf[];
+                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ xin, int B, int S, int F, int D, int CT) {
+  extern __shared__ __align__(16) float smf[];
   const int Fin = F + 3;
-  const int FinP = (Fin + 3) & ~3;
-  constexpr int kWLd = 41;         // row pitch of the staged weight rows (odd: conflict-light column reads)
-  float* sW = smf;                 // [D][kWLd], row d = w_in[d, :]
-  float* sX = smf + D * kWLd;      // [kEmbTok][FinP]
-  const int64_t M = static_cast<int64_t>(B) * S;
-  const int64_t t0 = static_cast<int64_t>(blockIdx.x) * kEmbTok;
-  for (int i = threadIdx.x; i < Fin * D; i += blockDim.x) {  // coalesced global read, conflict-free smem write
-    const int d = i / Fin, c = i - d * Fin;
-    sW[d * kWLd + c] = w_in[i];
+  float* sW = smf;                       // [Fin][CT]      W_in^T strip
+  float* sX = smf + Fin * CT;            // [Fin][kEmbTok] input tile, channel-major
+  float* sRaw = sX + Fin * kEmbTok;      // [kEmbTok][F]   the tile's weather rows as they lie in memory
+  const int M = B * S;                   // (host-checked to fit 31 bits)
+  const int c_base = blockIdx.y * CT;    // first column of this CTA's strip
+  const int ncols = min(CT, D - c_base); // a multiple of 8
+  const int ntx = CT >> 3, half = CT >> 1;
+  const int tx = threadIdx.x % ntx, ty = threadIdx.x / ntx;  // column group / token group (8 x 8 outputs per thread)
+  // A thread's 8 columns are two runs of 4, half a strip apart: consecutive lanes then read consecutive 16-byte pieces
+  // of a W row (conflict-free LDS.128; 8 consecutive columns per lane made every such load a 2-way bank conflict)
+  const int colA = tx * 4, colB = half + tx * 4;
+  const bool active = ty < (kEmbTok >> 3);
+  const bool okA = active && colA < ncols, okB = active && colB < ncols;
+  for (int i = threadIdx.x; i < Fin * CT; i += blockDim.x) {  // coalesced over d within a channel row
+    const int c = i / CT, d = i - c * CT;
+    sW[i] = d < ncols ? w_in[static_cast<size_t>(c_base + d) * Fin + c] : 0.0f;
   }
-  for (int i = threadIdx.x; i < kEmbTok * FinP; i += blockDim.x) {
-    const int tt = i / FinP, c = i - tt * FinP;
-    const int64_t t = t0 + tt;
-    float v = 0.0f;
-    if (t < M && c < Fin) {
-      const int64_t b = t / S, s = t - b * S;
-      if (c < F) {
-        const float w = weather[t * F + c];
-        const uint8_t m = mask[b * msb + s * mss + c];
-        v = m ? w * 0.0f : w;  // weather * (~mask): keeps NaN/Inf semantics of the multiply
-      } else if (c == F) {
-        v = (year[t] - 1970.0f) / 100.0f;
-      } else if (c == F + 1) {
-        v = coords[b * 2] / 360.0f;
-      } else {
-        v = coords[b * 2 + 1] / 180.0f;
+  const int ntiles = (M + kEmbTok - 1) / kEmbTok;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int t0 = tile * kEmbTok;
+    const int nt = min(kEmbTok, M - t0);
+    __syncthreads();  // previous tile's readers are done with sX / sRaw (and, first time round, sW is complete)
+    {  // the tile's weather block is contiguous in memory: straight coalesced copy
+      const float* src = weather + static_cast<size_t>(t0) * F;
+      for (int i = threadIdx.x; i < nt * F; i += blockDim.x) sRaw[i] = src[i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kEmbTok * Fin; i += blockDim.x) {
+      const int c = i / kEmbTok, tt = i - c * kEmbTok;  // token fastest: conflict-free smem on both sides (F is odd)
+      const int t = t0 + tt;
+      float v = 0.0f;
+      if (t < M) {
+        const int b = t / S, sq = t - b * S;
+        if (c < F) {
+          const float w = sRaw[tt * F + c];
+          const uint8_t m = mask[b * msb + sq * mss + c];
+          v = m ? w * 0.0f : w;  // weather * (~mask): keeps NaN/Inf semantics of the multiply
+        } else if (c == F) {
+          v = (year[t] - 1970.0f) / 100.0f;
+        } else if (c == F + 1) {
+          v = coords[b * 2] / 360.0f;
+        } else {
+          v = coords[b * 2 + 1] / 180.0f;
+        }
+      }
+      sX[i] = v;
+    }
+    __syncthreads();
+    if (xin && blockIdx.y == 0) {  // bf16 copy of the input rows for the in_proj weight gradient
+      for (int i = threadIdx.x; i < kEmbTok * (kXinLd / 2); i += blockDim.x) {
+        const int tt = i / (kXinLd / 2), c2 = (i - tt * (kXinLd / 2)) * 2;
+        const int t = t0 + tt;
+        if (t < M) {
+          const float a = c2 < Fin ? sX[c2 * kEmbTok + tt] : 0.0f, b2 = c2 + 1 < Fin ? sX[(c2 + 1) * kEmbTok + tt] : 0.0f;
+          reinterpret_cast<uint32_t*>(xin)[(static_cast<size_t>(t) * kXinLd + c2) >> 1] = pack_bf16x2(a, b2);
+        }
       }
     }
-    sX[i] = v;
-  }
-  __syncthreads();
-  if (xin) {
-    for (int i = threadIdx.x; i < kEmbTok * kXinLd; i += blockDim.x) {
-      const int tt = i / kXinLd, c = i - tt * kXinLd;
-      const int64_t t = t0 + tt;
-      if (t < M) xin[t * kXinLd + c] = __float2bfloat16(c < Fin ? sX[tt * FinP + c] : 0.0f);
-    }
-  }
-  // One output column per thread (its 34 weights live in registers), two tokens in flight per step: with column
-  // PAIRS the kernel needed 118 registers and 112 KB of smem -- one 9-warp CTA per SM, 65 % of cycles without an
-  // eligible warp (ncu) and 1.27 ms for a 0.2 ms job.
-  const int s0 = static_cast<int>(t0 % S);
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float w0[40];
+    if (!okA) continue;
+    uint64_t acc[8][4];  // [token][column pair]: pairs 0, 1 = run A, pairs 2, 3 = run B
 #pragma unroll
-    for (int c = 0; c < 40; ++c) w0[c] = c < Fin ? sW[d * kWLd + c] : 0.0f;
-    const float bias0 = b_in[d];
-    int sidx = s0;                                              // position of token t0 + tb, kept incrementally: a
-    const float* pe_row = pe + static_cast<size_t>(s0) * D + d;  // `% S` per token cost ~80 of ~300 instructions per step
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[t][j] = 0ull;
+    const float* xrow = sX + ty * 8;
 #pragma unroll 1
-    for (int tb = 0; tb < kEmbTok; tb += 4) {
-      float pev[4];
+    for (int c = 0; c < Fin; ++c) {
+      const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(sW + c * CT + colA);
+      const ulonglong2 wb = *reinterpret_cast<const ulonglong2*>(sW + c * CT + (okB ? colB : colA));
+      const float4 x0 = *reinterpret_cast<const float4*>(xrow + c * kEmbTok);      // tokens 0-3 (warp broadcast)
+      const float4 x1 = *reinterpret_cast<const float4*>(xrow + c * kEmbTok + 4);  // tokens 4-7
+      const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {  // the four position-table loads of this batch are issued together
-        pev[u] = (t0 + tb + u < M) ? __ldg(pe_row) : 0.0f;
-        pe_row += D;
-        if (++sidx == S) {
-          sidx = 0;
-          pe_row = pe + d;
+      for (int t = 0; t < 8; ++t) {
+        const uint64_t xx = f2_pack(xs[t], xs[t]);
+        acc[t][0] = f2_fma(xx, wa.x, acc[t][0]);
+        acc[t][1] = f2_fma(xx, wa.y, acc[t][1]);
+        acc[t][2] = f2_fma(xx, wb.x, acc[t][2]);
+        acc[t][3] = f2_fma(xx, wb.y, acc[t][3]);
+      }
+    }
+    // epilogue: (acc + bias) + PE[position]; 4 bf16 = one 8-byte store per run and token; position kept incrementally
+    const int tfirst = t0 + ty * 8;
+    int sidx = tfirst % S;
+    const float4 bA = __ldg(reinterpret_cast<const float4*>(b_in + c_base + colA));
+    const float4 bB = okB ? __ldg(reinterpret_cast<const float4*>(b_in + c_base + colB)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int tok = tfirst + t;
+      if (tok < M) {
+        const float* prow = pe + static_cast<size_t>(sidx) * D + c_base;
+        __nv_bfloat16* orow = out + static_cast<size_t>(tok) * D + c_base;
+        float a0, a1, a2, a3;
+        f2_unpack(acc[t][0], a0, a1);
+        f2_unpack(acc[t][1], a2, a3);
+        const float4 pA = __ldg(reinterpret_cast<const float4*>(prow + colA));
+        uint2 o;
+        o.x = pack_bf16x2((a0 + bA.x) + pA.x, (a1 + bA.y) + pA.y);
+        o.y = pack_bf16x2((a2 + bA.z) + pA.z, (a3 + bA.w) + pA.w);
+        *reinterpret_cast<uint2*>(orow + colA) = o;
+        if (okB) {
+          f2_unpack(acc[t][2], a0, a1);
+          f2_unpack(acc[t][3], a2, a3);
+          const float4 pB = __ldg(reinterpret_cast<const float4*>(prow + colB));
+          o.x = pack_bf16x2((a0 + bB.x) + pB.x, (a1 + bB.y) + pB.y);
+          o.y = pack_bf16x2((a2 + bB.z) + pB.z, (a3 + bB.w) + pB.w);
+          *reinterpret_cast<uint2*>(orow + colB) = o;
         }
       }
-      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-      for (int c4 = 0; c4 < 10; ++c4) {
-        if (c4 * 4 < FinP) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float4 x = reinterpret_cast<const float4*>(sX + (tb + u) * FinP)[c4];
-            acc[u] = fmaf(x.x, w0[c4 * 4], acc[u]);
-            acc[u] = fmaf(x.y, w0[c4 * 4 + 1], acc[u]);
-            acc[u] = fmaf(x.z, w0[c4 * 4 + 2], acc[u]);
-            acc[u] = fmaf(x.w, w0[c4 * 4 + 3], acc[u]);
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t t = t0 + tb + u;
-        if (t < M) out[t * D + d] = __float2bfloat16((acc[u] + bias0) + pev[u]);
-      }
+      if (++sidx == S) sidx = 0;
     }
   }
 }
@@ -194,22 +230,29 @@ embed_fwd_kernel(const float* __restrict__ weather, const uint8_t* __restrict__ 
 int launch_embed_fwd(const float* weather, const uint8_t* mask, int64_t msb, int64_t mss, const float* year,
                      const float* coords, const float* w_in, const float* b_in, const float* pe,
                      __nv_bfloat16* out, __nv_bfloat16* xin, int B, int S, int F, int D, cudaStream_t stream) {
-  if (B <= 0 || S <= 0 || F <= 0 || F + 3 > 40 || (D & 1)) return WM_ERR_SHAPE;
+  if (B <= 0 || S <= 0 || F <= 0 || F + 3 > 40 || (D & 7)) return WM_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(pe) | reinterpret_cast<uintptr_t>(b_in)) & 15u) return WM_ERR_ALIGN;
   const int64_t M = static_cast<int64_t>(B) * S;
-  const int Fin = F + 3, FinP = (Fin + 3) & ~3;
+  if (M >= (1ll << 31) - kEmbTok) return WM_ERR_SHAPE;  // 32-bit token indices inside the kernel
+  const int Fin = F + 3;
   int sms = 0, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int tok = (M >= static_cast<int64_t>(kEmbTokLong) * 4 * (sms > 0 ? sms : 148)) ? kEmbTokLong : kEmbTokShort;
-  const int smem = (41 * D + tok * FinP) * 4;
+  if (sms <= 0) sms = 148;
+  const int strips = (D + kEmbMaxCT - 1) / kEmbMaxCT;
+  const int CT = ((D / 8 + strips - 1) / strips) * 8;   // columns per strip: a multiple of 8, <= 320
+  const int threads = ((CT + 31) / 32) * 32;            // CT/8 column groups x 8 token groups (+ idle lanes of the last warp)
+  const int smem = (Fin * CT + Fin * kEmbTok + kEmbTok * F) * 4;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return WM_ERR_CUDA;
-  const int blocks = static_cast<int>((M + tok - 1) / tok);
-  int threads = ((D + 31) / 32) * 32;  // one thread per output column
-  if (threads > 768) threads = 768;
-  embed_fwd_kernel<<<blocks, threads, smem, stream>>>(weather, mask, msb, mss, year, coords, w_in, b_in, pe, out,
-                                                      xin, B, S, F, D, tok);
+  const int64_t ntiles = (M + kEmbTok - 1) / kEmbTok;
+  // persistent: as many CTAs per strip as stay resident (registers: two 320-thread CTAs per SM; narrow strips: more)
+  const int per_sm = CT >= 160 ? 2 : (CT >= 64 ? 4 : 8);
+  const int gx = static_cast<int>(ntiles < static_cast<int64_t>(sms) * per_sm / strips ? ntiles : static_cast<int64_t>(sms) * per_sm / strips);
+  dim3 grid(gx > 0 ? gx : 1, strips);
+  embed_fwd_kernel<<<grid, threads, smem, stream>>>(weather, mask, msb, mss, year, coords, w_in, b_in, pe, out, xin, B,
+                                                    S, F, D, CT);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }

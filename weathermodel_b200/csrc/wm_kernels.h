@@ -108,4 +108,9 @@ int launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __
                     __nv_bfloat16* dqkv, const uint32_t* drop_words, void* workspace, int B, int S, int H, int dh,
                     uint32_t drop_thresh, cudaStream_t stream);
 
+
+// ---- crop-yield head (wm_yield.cu) -------------------------------------------------------------
+struct YieldHeadW;
+int yield_head_param_count(int F, int np, int HM);
+
 }  // namespace wm

@@ -3,5 +3,6 @@
 #include "wm_gemm.cu"
 #include "wm_elementwise.cu"
 #include "wm_attn.cu"
+#include "wm_yield.cu"
 #include "wm_encoder.cu"
 #include "wm_api.cu"

@@ -381,3 +381,32 @@ def former_elbo(y_pad, weather, mask, beta: float) -> Dict[str, torch.Tensor]:
     """ELBO of weatherformer_trainer.py:68-111 straight from the raw head output [mu | logvar | pad]."""
     total, allv = _FormerLossFn.apply(y_pad, weather.contiguous().float(), mask, float(beta), getattr(y_pad, "_wm_src", None))
     return {"total_loss": total, "reconstruction": allv[1], "kl_term": allv[2]}
+
+
+# ---------------------------------------------------------------------------------------------
+# fused crop-yield head on the raw (padded) encoder output
+# ---------------------------------------------------------------------------------------------
+class _YieldHeadFn(torch.autograd.Function):
+    """(pred, z) = head(y_pad, weather, mask, eps, y_past; 8 head parameters) -- one kernel forward, one backward
+    (+ a fixed-order fold of the per-sequence parameter gradients). z is returned for API parity only
+    (WeatherFormerYieldModel.forward returns it; no trainer differentiates through it)."""
+
+    @staticmethod
+    def forward(ctx, y_pad, weather, mask, eps, y_past, is_former, *params):
+        pred, z = ops.yield_head_fwd(y_pad, weather, mask, eps, y_past, params, is_former)
+        ctx.save_for_backward(y_pad, mask, eps if eps is not None else y_pad.new_empty(0), z, y_past, *params)
+        ctx.is_former = is_former
+        ctx.mark_non_differentiable(z)
+        return pred, z
+
+    @staticmethod
+    def backward(ctx, dpred, _dz):
+        y_pad, mask, eps, z, y_past, *params = ctx.saved_tensors
+        dy, grads = ops.yield_head_bwd(dpred, y_pad, mask, eps if ctx.is_former else None, z, y_past, params, ctx.is_former)
+        return (dy, None, None, None, None, None, *grads)
+
+
+def yield_head(y_pad, weather, mask, eps, y_past, params, is_former: bool):
+    """Imputation (+ reparameterisation), softmax pooling over the sequence and the yield MLP of the reference's
+    yield models (src/crop_yield/models/weatherbert_yield_model.py:40-67, weatherformer_yield_model.py:58-60)."""
+    return _YieldHeadFn.apply(y_pad, weather.contiguous().float(), mask, eps, y_past, bool(is_former), *params)

@@ -380,6 +380,63 @@ def loss_former_grad(y, weather, mask, beta, scratch, grad_scale=None, ld_grad=6
     return dy
 
 
+# ---------------------------------------------------------------------------------------------
+# crop-yield head (one forward / one backward kernel)
+# ---------------------------------------------------------------------------------------------
+def _head_params(params):
+    if len(params) != 8:
+        raise ValueError("yield head: expected (att_w1, att_b1, att_w2, att_b2, mlp_w1, mlp_b1, mlp_w2, mlp_b2)")
+    out = []
+    for t in params:
+        _cuda(t)
+        if t.dtype != torch.float32:
+            raise TypeError("yield head parameters must be float32")
+        out.append(t.contiguous())
+    return out
+
+
+def yield_head_fwd(y_pad, weather, mask, eps, y_past, params, is_former: bool):
+    """y_pad fp32 [B,S,P] raw head output -> (pred [B,1], z [B,S,F]); see include/wm_b200.h wm_yield_head_fwd."""
+    _cuda(y_pad, weather, mask, eps, y_past)
+    B, S, P = y_pad.shape
+    F = weather.shape[-1]
+    params = _head_params(params)
+    HM = params[4].shape[0]
+    mask, msb, mss = mask_strides(mask)
+    y_past = y_past.contiguous().float()
+    z = torch.empty((B, S, F), dtype=torch.float32, device=y_pad.device)
+    pred = torch.empty((B, 1), dtype=torch.float32, device=y_pad.device)
+    check(lib().wm_yield_head_fwd(_p(y_pad), P, int(is_former), _p(weather), _p(mask), msb, mss, _p(eps), _p(y_past),
+                                  y_past.shape[1], *[_p(t) for t in params], _p(z), _p(pred), B, S, F, HM, _stream()),
+          "wm_yield_head_fwd")
+    return pred, z
+
+
+def yield_head_bwd(dpred, y_pad, mask, eps, z, y_past, params, is_former: bool):
+    """-> (dy fp32 [B,S,P], [8 parameter gradients shaped like `params`])."""
+    _cuda(dpred, y_pad, mask, eps, z, y_past)
+    B, S, P = y_pad.shape
+    F = z.shape[-1]
+    params = _head_params(params)
+    HM = params[4].shape[0]
+    mask, msb, mss = mask_strides(mask)
+    y_past = y_past.contiguous().float()
+    n = lib().wm_yield_head_param_count(F, y_past.shape[1], HM)
+    if n != sum(t.numel() for t in params):
+        raise ValueError("yield head: parameter shapes do not match (F, n_past, hidden)")
+    dy = torch.empty((B, S, P), dtype=torch.float32, device=y_pad.device)
+    partial = torch.empty((B, n), dtype=torch.float32, device=y_pad.device)
+    grads = torch.empty(n, dtype=torch.float32, device=y_pad.device)
+    check(lib().wm_yield_head_bwd(_p(dpred.contiguous().float()), _p(y_pad), P, int(is_former), _p(mask), msb, mss, _p(eps),
+                                  _p(z), _p(y_past), y_past.shape[1], *[_p(t) for t in params], _p(dy), _p(partial),
+                                  _p(grads), B, S, F, HM, _stream()), "wm_yield_head_bwd")
+    out, off = [], 0
+    for t in params:
+        out.append(grads[off:off + t.numel()].view(t.shape))
+        off += t.numel()
+    return dy, out
+
+
 def adam_fused(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
                shadow=None, grad_scale=1.0):
     _cuda(param, grad, exp_avg, exp_avg_sq, shadow)

@@ -8,10 +8,13 @@ for the WHOLE chunk, then `randperm` shuffle, then the `< cutoff_year` filter, t
 `batch_size` that run across chunk boundaries; the RNG is consumed in the same order (mask, randperm), and
 the masks are bit-identical to the reference's torch.rand-based functions for the same generator state
 (CUDA: Philox replay kernels wm_mask_bert / wm_mask_former; CPU: torch.rand itself).
-What changed is the mechanics: no per-sample Python loop, no per-sample host sync, no per-sample collate.
+What changed is the mechanics: no per-sample Python loop, no per-sample host sync, no per-sample collate, and the
+NEXT chunk file is read, pinned and copied to the device by a helper thread on a side stream while the current
+chunk's batches train (the reference blocks the training loop for every torch.load).
 """
 import logging
 import random
+import threading
 from typing import Iterator, List, Optional, Tuple
 
 import torch
@@ -91,7 +94,11 @@ class StreamingDataset(torch.utils.data.IterableDataset):
 
     # ---- chunk -> tensors -------------------------------------------------------------------------
     def _load_chunk(self, path) -> Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
-        data = torch.load(path, weights_only=False, map_location=self.device)
+        """File -> (weather, coords, index) float32 on self.device. On CUDA the file is read to the host, pinned and
+        copied on a side stream; the returned tensors carry an event (`_ready`) the consumer stream waits on. No RNG
+        is touched here, so running it one chunk ahead in a helper thread leaves the mask / randperm order alone."""
+        on_cuda = torch.device(self.device).type == "cuda"
+        data = torch.load(path, weights_only=False, map_location="cpu" if on_cuda else self.device)
         if hasattr(data, "tensors"):
             weather, coords, index = data.tensors[:3]
         else:
@@ -102,13 +109,41 @@ class StreamingDataset(torch.utils.data.IterableDataset):
             index = torch.stack([s[2] for s in data])
         if weather.shape[0] == 0:
             return None
-        return weather.to(self.device).float(), coords.to(self.device).float(), index.to(self.device).float()
+        if not on_cuda:
+            return weather.to(self.device).float(), coords.to(self.device).float(), index.to(self.device).float()
+        with torch.cuda.device(self.device):
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            host = [t.float().contiguous().pin_memory() for t in (weather, coords, index)]
+            with torch.cuda.stream(self._copy_stream):
+                out = [t.to(self.device, non_blocking=True) for t in host]
+                ready = torch.cuda.Event()
+                ready.record(self._copy_stream)
+        return out[0], out[1], out[2], ready, host  # `host` keeps the pinned buffers alive until the copy is waited on
 
-    def _chunk_samples(self, path):
-        loaded = self._load_chunk(path)
+    def _start_prefetch(self, path):
+        box = {}
+
+        def work():
+            try:
+                box["v"] = self._load_chunk(path)
+            except BaseException as e:  # re-raised in the consumer
+                box["e"] = e
+
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+        return th, box
+
+    def _chunk_samples(self, path, loaded="load"):
+        if loaded == "load":
+            loaded = self._load_chunk(path)
         if loaded is None:
             return None
-        weather, coords, index = loaded
+        if len(loaded) == 5:  # CUDA: order this stream after the side-stream copy; the chunk then belongs to it
+            torch.cuda.current_stream(torch.device(self.device)).wait_event(loaded[3])
+            for t in loaded[:3]:
+                t.record_stream(torch.cuda.current_stream(torch.device(self.device)))
+        weather, coords, index = loaded[:3]
         n, seq_len, n_features = weather.shape
         interval = index[:, 1:2].contiguous()
         t = torch.arange(seq_len, dtype=torch.float32, device=self.device)
@@ -126,8 +161,15 @@ class StreamingDataset(torch.utils.data.IterableDataset):
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, ...]]:
         carry: Optional[List[torch.Tensor]] = None
         n_groups = len(self.file_paths) // 3
+        weekly = [self.file_paths[3 * gi + 1] for gi in range(n_groups)]  # the weekly file of each triple (:198)
+        pending = self._start_prefetch(weekly[0]) if n_groups else None
         for gi in range(n_groups):
-            parts = self._chunk_samples(self.file_paths[3 * gi + 1])  # the weekly file of each triple (:198)
+            th, box = pending
+            th.join()
+            if "e" in box:
+                raise box["e"]
+            pending = self._start_prefetch(weekly[gi + 1]) if gi + 1 < n_groups else None  # overlaps this chunk's batches
+            parts = self._chunk_samples(weekly[gi], loaded=box["v"])
             if parts is not None:
                 parts = list(parts)
                 if carry is not None:
