@@ -33,6 +33,9 @@ WORKLOADS = {
     "medium": ("weatherbert", "medium", 256, 8),
     "small": ("weatherformer", "small", 128, 16),
     "mini": ("weatherbert", "mini", 64, 64),
+    # BASELINE configs[5]: WeatherFormer mini crop-yield fine-tune step (n-past-years 6 => 364 weekly steps, 25 of 31
+    # features masked and imputed, MSE + beta * KL), batch 64 (yield_main.py default)
+    "yield": ("weatherformer-yield", "mini", 64, 64),
 }
 SIZES = {"mini": (4, 2, 12), "small": (10, 4, 20), "medium": (12, 6, 28), "large": (16, 8, 36)}
 S, F = 365, 31
@@ -199,7 +202,7 @@ def run_torch_gpu(args, rank):
                       "modes": out}), flush=True)
 
 
-def trainer_leg(kind, size, B, dev, steps_per_epoch=16, chunk=4096):
+def trainer_leg(kind, size, B, dev, steps_per_epoch=40, chunk=4096):
     """Sequences/s through the drop-in trainer: <Model>Trainer._train_epoch over synthetic chunk files in the
     reference's on-disk format, read by streaming_dataloader (torch.load -> mask -> randperm -> batches),
     zero_grad / compute_train_loss / backward / FusedAdam.step exactly as the CLI runs them. One untimed epoch
@@ -214,7 +217,7 @@ def trainer_leg(kind, size, B, dev, steps_per_epoch=16, chunk=4096):
     from weathermodel_b200.pretraining.trainers.weatherbert_trainer import WeatherBertTrainer
     from weathermodel_b200.pretraining.trainers.weatherformer_trainer import WeatherFormerTrainer
 
-    n_chunks = max(1, (steps_per_epoch * B + chunk - 1) // chunk)
+    n_chunks = max(3, (steps_per_epoch * B + chunk - 1) // chunk)  # >= 3 files: the one-ahead prefetch is exercised
     ids = [1, 34, 53, 72, 81][:n_chunks]
     cwd = os.getcwd()
     tmp = tempfile.mkdtemp(prefix="wm_bench_chunks_")
@@ -281,10 +284,19 @@ def run_ours(args, rank, world, local_rank):
     if args.batch:
         B = args.batch
     torch.manual_seed(1234)
-    cls = WeatherFormer if kind == "weatherformer" else WeatherBERT
-    model = cls(weather_dim=F, output_dim=F, device=dev, **size_params(size)).to(dev).train()
-    net = model
-    if world > 1:
+    is_yield = kind == "weatherformer-yield"
+    S = 364 if is_yield else globals()["S"]
+    if is_yield:
+        from weathermodel_b200.crop_yield.models.weatherformer_yield_model import WeatherFormerYieldModel
+        from weathermodel_b200.utils.losses import compute_gaussian_kl_divergence
+
+        model = WeatherFormerYieldModel(name="bench", device=dev, weather_dim=F, n_past_years=6, **size_params(size)).to(dev).train()
+        net = model.weather_model
+    else:
+        cls = WeatherFormer if kind == "weatherformer" else WeatherBERT
+        model = cls(weather_dim=F, output_dim=F, device=dev, **size_params(size)).to(dev).train()
+        net = model
+    if world > 1 and not is_yield:
         model = BucketedDataParallel(model)
     opt = FusedAdam(model.parameters(), lr=5e-4, runtime=net.runtime)
 
@@ -298,23 +310,45 @@ def run_ours(args, rank, world, local_rank):
         idx = torch.randint(0, 2, (B,), generator=g).float()
         y = (1984.0 + ((idx[:, None] * 365 + torch.arange(S, dtype=torch.float32)[None]) * 7.0) / 365).pin_memory()
         iv = torch.full((B, 1), 7.0).pin_memory()
-        host.append((w, c, y, iv))
+        if is_yield:
+            host.append((w, c, y, iv, torch.randn(B, 7, generator=g).pin_memory(), torch.randn(B, 1, generator=g).pin_memory()))
+        else:
+            host.append((w, c, y, iv))
     resident = [tuple(t.to(dev) for t in hb) for hb in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
     torch.cuda.manual_seed(1234 + rank)
 
-    def step(batch):
-        w, c, y, iv = batch
-        if kind == "weatherformer":
-            mask = ops.mask_former(S, F, B, 10, device=dev)
-        else:
-            mask = ops.mask_bert(S, F, B, 0.15, device=dev)
-        opt.zero_grad()
+    ymask = None
+    if is_yield:  # the yield loader's mask: six observed features, the other 25 imputed (yield_dataloader.py:157,266-279)
+        ymask = torch.ones(B, S, F, dtype=torch.bool, device=dev)
+        ymask[:, :, [7, 8, 11, 1, 2, 29]] = False
+
+    def loss_fn(*batch):
+        """The step's differentiable part (what BaseTrainer.compute_train_loss returns)."""
+        if is_yield:
+            w, c, y, iv, y_past, target = batch
+            pred, z, mu, var = model(w, c, y, iv, ymask, y_past)
+            kl = compute_gaussian_kl_divergence(ymask, mu, var, torch.zeros_like(mu), torch.ones_like(var)).mean()
+            return {"total_loss": torch.nn.functional.mse_loss(pred, target) + 1e-4 * kl}
+        w, c, y, iv, mask = batch
         y_pad = net.forward_raw(w, c, y, iv, mask)
         if kind == "weatherformer":
-            loss = engine.former_elbo(y_pad, w, mask, 0.5)["total_loss"]
-        else:
-            loss = engine.bert_masked_mse(y_pad, w, mask)
+            return {"total_loss": engine.former_elbo(y_pad, w, mask, 0.5)["total_loss"]}
+        return {"total_loss": engine.bert_masked_mse(y_pad, w, mask)}
+
+    # Launch-bound workloads (everything but WeatherFormer large): the step body is recorded once as a CUDA graph and
+    # replayed, exactly as BaseTrainer does for these shapes (graph_step.CapturedTrainStep). Masks are drawn outside.
+    captured = [None]
+    use_graph = world == 1 and (args.graph == "1" or (args.graph == "auto" and args.workload != "large"))
+
+    def step(batch):
+        if not is_yield:
+            mask = ops.mask_former(S, F, B, 10, device=dev) if kind == "weatherformer" else ops.mask_bert(S, F, B, 0.15, device=dev)
+            batch = tuple(batch) + (mask,)
+        if captured[0] is not None:
+            return captured[0](*batch)["total_loss"]
+        opt.zero_grad()
+        loss = loss_fn(*batch)["total_loss"]
         loss.backward()
         if world > 1:
             model.finish_gradient_sync()
@@ -361,32 +395,22 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         launches = lib().wm_launch_count() - l0
+        if captured[0] is not None:  # kernels replayed from the recorded step are not counted by the library's host counter
+            launches += captured[0].kernels_per_replay * n_steps
         return t.item(), launches, (last if from_host else last.item())
-
-    for i in range(args.warmup):
-        step(resident[i % n_ring])
-    with ClockSampler(local_rank) as clocks:
-        ms_total, launches, loss_val = timed(args.steps, from_host=False)
-        ms_e2e, _, loss_e2e = timed(args.steps, from_host=True)
-    code = ops.device_error()
-    if code:
-        raise SystemExit(f"device-side mbarrier timeout (site {code}) during the benchmark: numbers invalid")
-
-    pk = peaks()
-    seqs = B * world * args.steps
-    value = seqs / (ms_total * 1e-3)
-    e2e = seqs / (ms_e2e * 1e-3)
-    flops_seq = train_flops_per_seq(size, 62 if kind == "weatherformer" else 31)
 
     # ---- roofline of the dominant kernel (gemm_tn: FFN linear1 shape), timed alone with CUDA events
     roof = None
-    also = {}
+    pk = peaks()
     if rank == 0:
         h, l, f = SIZES[size]
         D, FF, M = h * f, 4 * h * f, B * S
         a = (torch.randn(M, D, device=dev) * 0.5).to(torch.bfloat16)
         bmat = (torch.randn(FF, D, device=dev) * D ** -0.5).to(torch.bfloat16)
         bias = torch.zeros(FF, device=dev)
+        # the library keeps one (bit-identical) kernel variant per call signature: pick it for this signature the way the
+        # encoder's own call sites are tuned at start-up (ops.tune_gemm_sites), then time that
+        variant, _ = ops.tune_gemm_call(a, bmat, bias=bias, relu=True)
         for _ in range(3):
             ops.gemm_tn(a, bmat, bias=bias, relu=True)
         reps = 20
@@ -399,19 +423,45 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         gemm_ms = e0.elapsed_time(e1) / reps
         achieved = 2.0 * M * FF * D / (gemm_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_tn_kernel<bf16> (linear1: M x 4D x D, bias+ReLU epilogue)",
+        roof = {"bound": "tensor", "kernel": f"gemm_tn{'2' if variant[0] else ''}_kernel<bf16> (linear1: M x 4D x D, bias+ReLU epilogue)",
                 "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((M, FF, D)),
                 "traffic_source": "constant from the committed ncu --set full capture (profiles/), not measured in this run",
                 "peak_source": pk["source"] + " burst (kernel timed alone)",
-                "launch_ms": gemm_ms, "shape": [M, FF, D]}
+                "launch_ms": gemm_ms, "shape": [M, FF, D],
+                "when": "before the step timing, on the launching stream, 20 launches between two CUDA events"}
+        roof["variant"] = {"two_cta": variant[0], "epilogue_warps": variant[1], "stores": ("direct", "staged", "tma")[variant[2]]}
+        del a, bmat
+
+    for i in range(args.warmup):
+        step(resident[i % n_ring])
+    if use_graph:
+        from weathermodel_b200.graph_step import CapturedTrainStep
+
+        ex = resident[0] if is_yield else tuple(resident[0]) + (ops.mask_former(S, F, B, 10, device=dev) if kind == "weatherformer"
+                                                                else ops.mask_bert(S, F, B, 0.15, device=dev),)
+        captured[0] = CapturedTrainStep(opt, loss_fn, ex)
+        for i in range(2):
+            step(resident[i % n_ring])
+    with ClockSampler(local_rank) as clocks:
+        ms_total, launches, loss_val = timed(args.steps, from_host=False)
+        ms_e2e, _, loss_e2e = timed(args.steps, from_host=True)
+    code = ops.device_error()
+    if code:
+        raise SystemExit(f"device-side mbarrier timeout (site {code}) during the benchmark: numbers invalid")
+
+    seqs = B * world * args.steps
+    value = seqs / (ms_total * 1e-3)
+    e2e = seqs / (ms_e2e * 1e-3)
+    flops_seq = train_flops_per_seq(size, 31 if kind == "weatherbert" else 62)
+    also = {}
+    if rank == 0:
         also["step_tensor_frac_of_sustained"] = (value / world) * flops_seq / (pk["tf_sustained"] * 1e12)
         also["algorithmic_gflop_per_seq"] = flops_seq / 1e9
-        del a, bmat
 
     # ---- CPU baseline (rank 0, N == 1 only): reference CPU PyTorch path, bounded sample
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not is_yield:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import torch_port
 
@@ -427,7 +477,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- the same metric through the drop-in trainer and loader (N == 1 only: DRY_RUN-sized chunk lists do not split 8 ways)
     trainer = None
-    if rank == 0 and world == 1 and not args.no_trainer:
+    if rank == 0 and world == 1 and not args.no_trainer and not is_yield:
         del resident, staging
         torch.cuda.empty_cache()
         trainer = trainer_leg(kind, size, B, dev)
@@ -437,9 +487,10 @@ def run_ours(args, rank, world, local_rank):
             "metric": "pretrain sequences/sec (365d x 31 feat)", "value": value, "unit": "sequences/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{kind}-{size} pretraining step, {B} sequences/GPU, seq 365 x 31 features, "
-                                   f"dropout 0.1, {'beta-KL ELBO' if kind == 'weatherformer' else 'masked MSE'}, Adam",
+            "config": {"workload": f"{kind}-{size} {'fine-tune' if is_yield else 'pretraining'} step, {B} sequences/GPU, seq {S} x 31 features, "
+                                   f"dropout 0.1, {'yield MSE + beta-KL, fused yield head' if is_yield else 'beta-KL ELBO' if kind == 'weatherformer' else 'masked MSE'}, Adam",
                        "global_batch": B * world, "seq_len": S, "parallelism": f"dp{world}",
+                       "step_issue": "one CUDA-graph replay per step (graph_step.CapturedTrainStep)" if use_graph else "eager launches",
                        "l2": "per-step working set (activations) >> 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
@@ -470,6 +521,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-trainer", action="store_true", help="skip the trainer-level e2e leg")
+    ap.add_argument("--graph", default="auto", choices=["auto", "0", "1"],
+                    help="replay the step as a CUDA graph (auto: every workload but large, single GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", 0))

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WM_B200_ABI_VERSION 2
+#define WM_B200_ABI_VERSION 3
 
 int wm_abi_version(void);
 const char* wm_strerror(int code);
@@ -173,9 +173,22 @@ int wm_yield_head_bwd(const float* dpred, const float* y, int ldy, int is_former
                       void* stream);
 
 /* ---- optimiser: torch.optim.Adam as built at src/base_trainer/base_trainer.py:337 ------------------- */
+/* beta1 / beta2 are doubles (ABI 3): torch.optim.Adam forms 1 - beta^step from Python floats, i.e. in double
+ * precision from the decimal value; bias corrections formed from the float-rounded betas are off by ~1e-5 relative. */
 int wm_adam_fused(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
-                  void* shadow_bf16 /* optional */, int64_t n, float lr, float beta1, float beta2, float eps,
+                  void* shadow_bf16 /* optional */, int64_t n, float lr, double beta1, double beta2, float eps,
                   float weight_decay, int step, float grad_scale, void* stream);
+/* The same update with the step-dependent scalars read from DEVICE memory: hyper_dev = {lr, 1 - beta1^t,
+ * sqrt(1 - beta2^t)} (3 floats). For a training step captured in a CUDA graph (the BaseTrainer step body,
+ * src/base_trainer/base_trainer.py:239-252, replayed without host work): the launch is replayed unchanged while the
+ * host refreshes the three numbers in a pinned buffer that a captured copy brings over. */
+int wm_adam_fused_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16 /* optional */,
+                      int64_t n, const float* hyper_dev, double beta1, double beta2, float eps, float weight_decay,
+                      float grad_scale, void* stream);
+/* Installs three per-replay words (device memory; NULL = zeros) that every dropout site of the kernels above folds
+ * into its keys: replays of a captured step then draw fresh masks although their launch parameters are frozen.
+ * Zero words (the initial state) reproduce the un-captured behaviour exactly. */
+int wm_step_params_apply(const void* dev_words /* 3 x uint32 */, void* stream);
 
 /* ---- the encoder as one object: WeatherBERT.forward / WeatherFormer.forward + autograd backward
  *      (src/pretraining/models/weatherbert.py:84-121; src/pretraining/models/weatherformer.py:60-94) ---- */

@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/wm_b200.h but not exported by libwm_b200.so"
     assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES and the header disagree"
-    assert lib.wm_abi_version() == 2
+    assert lib.wm_abi_version() == 3
     assert b"no fallback" in lib.wm_strerror(6)
 
 

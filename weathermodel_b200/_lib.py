@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("WM_B200_LIB") or os.path.join(_HERE, "libwm_b200.so")  # override: diagnostic builds (tools/)
 
-_vp, _i, _i64, _u64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
+_vp, _i, _i64, _u64, _f, _sz, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t, C.c_double
 
 
 class GemmEpilogue(C.Structure):
@@ -65,7 +65,9 @@ SIGNATURES = {
     "wm_yield_head_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i64, _vp, _vp, _i] + [_vp] * 8 + [_vp, _vp, _i, _i, _i, _i, _vp]),
     "wm_yield_head_bwd": (_i, [_vp, _vp, _i, _i, _vp, _i64, _i64, _vp, _vp, _vp, _i] + [_vp] * 8 +
                           [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "wm_adam_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp]),
+    "wm_adam_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _d, _d, _f, _f, _i, _f, _vp]),
+    "wm_adam_fused_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _d, _d, _f, _f, _f, _vp]),
+    "wm_step_params_apply": (_i, [_vp, _vp]),
     "wm_encoder_param_count": (_i64, [C.POINTER(EncoderConfig)]),
     "wm_encoder_param_layout": (_i, [C.POINTER(EncoderConfig), C.POINTER(_i64), _i]),
     "wm_encoder_workspace_bytes": (_sz, [C.POINTER(EncoderConfig)]),
@@ -95,7 +97,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.wm_abi_version() != 2:
+        if handle.wm_abi_version() != 3:
             raise RuntimeError("libwm_b200.so ABI version mismatch")
         # WM_OPTIONS="name=value,..." applies wm_set_option tuning switches at load time (A/B measurements)
         for item in filter(None, os.environ.get("WM_OPTIONS", "").split(",")):

@@ -26,6 +26,9 @@ from ..utils.constants import DATA_DIR, DRY_RUN
 
 
 class BaseTrainer(ABC):
+    # trainers whose compute_train_loss has no host round trip (.item(), boolean gathers) opt in to recorded steps
+    _graph_capturable = False
+
     def __init__(self, model: BaseModel, batch_size: int, num_epochs: int, init_lr: float = 1e-4,
                  num_warmup_epochs: int = 5, decay_factor: Optional[float] = None,
                  pretrained_model_path: Optional[str] = None, resume_from_checkpoint: Optional[str] = None,
@@ -143,18 +146,22 @@ class BaseTrainer(ABC):
         sums = torch.zeros(len(keys), dtype=torch.float64, device=self.device)
         steps, seqs = 0, 0
         t0 = time.perf_counter()
+        losses = None
         for batch in loader:
             batch = [t.to(self.device) for t in batch]
             if training:
-                self.optimizer.zero_grad()
-                losses = self.compute_train_loss(*batch)
-                loss = losses["total_loss"]
-                if self.rank == 0 and DRY_RUN:
-                    print(f"Train loss: {loss.item()}")
-                loss.backward()
-                if isinstance(self.model, BucketedDataParallel):
-                    self.model.finish_gradient_sync()
-                self.optimizer.step()
+                losses = None  # (drop the previous step's autograd graph before a step may be recorded)
+                losses = self._captured_step(batch)  # small shapes: the whole step body as one CUDA-graph replay
+                if losses is None:
+                    self.optimizer.zero_grad()
+                    losses = self.compute_train_loss(*batch)
+                    loss = losses["total_loss"]
+                    if self.rank == 0 and DRY_RUN:
+                        print(f"Train loss: {loss.item()}")
+                    loss.backward()
+                    if isinstance(self.model, BucketedDataParallel):
+                        self.model.finish_gradient_sync()
+                    self.optimizer.step()
             else:
                 with torch.no_grad():
                     losses = self.compute_validation_loss(*batch)
@@ -170,6 +177,58 @@ class BaseTrainer(ABC):
         if training and steps:
             self.last_epoch_seq_per_s = seqs / max(1e-9, time.perf_counter() - t0)
         return self._average_losses({k: v for k, v in zip(keys, totals)}, steps)
+
+    # ---------------------------------------------------------------- recorded steps (launch-bound shapes)
+    def _graph_eligible(self, batch) -> bool:
+        """WM_CUDA_GRAPH=0 never, =1 whenever possible, unset: when the step is launch-bound (batch tokens x model width
+        below ~2^25: WeatherBERT mini / WeatherFormer small / medium at their BASELINE batch sizes, the yield fine-tune;
+        WeatherFormer large at 512 sequences per GPU is 60 ms of kernels per step and gains nothing)."""
+        mode = os.environ.get("WM_CUDA_GRAPH", "auto")
+        if mode == "0" or not self._graph_capturable or self.is_distributed or DRY_RUN or self.device.type != "cuda":
+            return False
+        runtimes = [m.runtime for m in self._get_underlying_model().modules() if hasattr(m, "runtime")]
+        if len(runtimes) != 1 or getattr(self.optimizer, "runtime", None) is not runtimes[0]:
+            return False
+        if not all(p.requires_grad for _, p in runtimes[0].named_flat_params()):
+            return False  # frozen encoder phases of the yield trainers stay on the eager path
+        if mode == "1":
+            return True
+        D = runtimes[0]._dims()[0]
+        return batch[0].dim() == 3 and batch[0].shape[0] * batch[0].shape[1] * D <= (1 << 25)
+
+    def _captured_step(self, batch):
+        """Returns the step's loss dict after running it as a CUDA-graph replay, or None (caller runs the eager step).
+        The first two batches of every shape run eagerly (engine handles, GEMM tuning, optimiser state); the third is
+        recorded while it trains (graph_step.CapturedTrainStep); a failed recording disables the feature for this trainer."""
+        if getattr(self, "_graph_disabled", False) or not self._graph_eligible(batch):
+            return None
+        from ..graph_step import CapturedTrainStep
+
+        if not hasattr(self, "_graph_steps"):
+            self._graph_steps, self._graph_seen = {}, {}
+        key = tuple((tuple(t.shape), t.dtype) for t in batch)
+        step = self._graph_steps.get(key)
+        if step is not None:
+            return step(*batch)
+        seen = self._graph_seen.get(key, 0)
+        self._graph_seen[key] = seen + 1
+        if seen < 2 or len(self._graph_steps) >= 4:
+            return None
+        try:
+            step = CapturedTrainStep(self.optimizer, self.compute_train_loss, batch)
+        except Exception as e:  # noqa: BLE001 -- any failure: keep training eagerly
+            self._graph_disabled = True
+            if os.environ.get("WM_GRAPH_DEBUG"):
+                import traceback
+                traceback.print_exc()
+            from ..graph_step import repair_default_generator
+            repair_default_generator(self.device)
+            self.logger.warning(f"CUDA-graph recording of the training step failed ({type(e).__name__}: {e}); staying eager")
+            return None
+        self._graph_steps[key] = step
+        if self.rank == 0:
+            self.logger.info(f"training step recorded as a CUDA graph for batch shape {tuple(batch[0].shape)}")
+        return step.first_losses
 
     def _train_epoch(self, loader) -> float:
         self.model.train()

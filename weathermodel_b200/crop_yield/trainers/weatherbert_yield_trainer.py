@@ -35,6 +35,7 @@ def _reset_fold_index():
 
 
 class WeatherBERTYieldTrainer(BaseTrainer):
+    _graph_capturable = True  # MSE (+ beta * KL) in device-side torch ops; the fused head is one kernel each way
     def __init__(self, crop_df: pd.DataFrame, country: str, n_past_years: int, n_train_years: int, beta: float,
                  use_cropnet: bool, crop_type: str, test_year: Optional[int] = None, test_type: str = "extreme",
                  **kwargs):

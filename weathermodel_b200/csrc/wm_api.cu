@@ -213,11 +213,23 @@ int wm_loss_former_grad(const float* y, int ldy, const float* weather, const uin
 }
 
 int wm_adam_fused(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow, int64_t n,
-                  float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                  float lr, double beta1, double beta2, float eps, float weight_decay, int step, float grad_scale,
                   void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq) return WM_ERR_ARG;
   return launch_adam(param, grad, exp_avg, exp_avg_sq, MB(shadow), n, lr, beta1, beta2, eps, weight_decay, step,
                      grad_scale, S_(stream));
+}
+
+int wm_adam_fused_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow, int64_t n,
+                      const float* hyper_dev, double beta1, double beta2, float eps, float weight_decay, float grad_scale,
+                      void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper_dev) return WM_ERR_ARG;
+  return launch_adam_dev(param, grad, exp_avg, exp_avg_sq, MB(shadow), n, hyper_dev, beta1, beta2, eps, weight_decay,
+                         grad_scale, S_(stream));
+}
+
+int wm_step_params_apply(const void* dev_words, void* stream) {
+  return launch_step_params_apply(reinterpret_cast<const uint32_t*>(dev_words), S_(stream));
 }
 
 int wm_yield_head_param_count(int F, int n_past, int HM) {

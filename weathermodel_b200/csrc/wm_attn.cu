@@ -135,8 +135,9 @@ template <int NCH, bool DROP>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ ctx,
                 float* __restrict__ lse_out, uint32_t* __restrict__ drop_words, int nitems, int S, int H, int dh,
-                float scale, uint32_t thresh15, float drop_scale, DropKeys dkeys) {
+                float scale, uint32_t thresh15, float drop_scale, DropKeys dkeys_in) {
   using G = AttnFwdGeom<NCH>;
+  const DropKeys dkeys = DROP ? drop_keys_live(dkeys_in) : dkeys_in;  // (+ the per-replay words of a captured step)
   constexpr int DHP = G::DHP, KVB = G::KVB, KSTEPS = DHP / 16;
   constexpr bool kZeroTail = (NCH & 1) != 0;  // last k-step: second core-matrix column comes from the zero chunk
   extern __shared__ __align__(1024) uint8_t smem_raw[];

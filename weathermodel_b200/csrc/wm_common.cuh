@@ -470,6 +470,17 @@ __host__ __device__ inline DropKeys drop_keys(uint64_t seed, uint64_t stream) { 
   const uint32_t a = static_cast<uint32_t>(z), b = static_cast<uint32_t>(z >> 32);
   return DropKeys{a, b, (b ^ 0x68E31DA4u) + a * 0x2545F491u};
 }
+// Per-replay key mix for CUDA-graph replays of a training step: the kernels of a captured step carry the dropout keys
+// of the step that was captured as launch parameters; a captured 1-thread kernel (wm_step_params_apply) installs three
+// fresh words here at the head of every replay and every dropout site folds them into its keys, so replays draw new
+// masks (forward and backward of one replay see the same words). All zero -- the state outside graphs -- changes nothing.
+__device__ uint32_t g_wm_drop_mix[4] = {0u, 0u, 0u, 0u};
+WM_DEVICE DropKeys drop_keys_live(DropKeys k) {
+  k.k0 ^= g_wm_drop_mix[0];
+  k.k1 ^= g_wm_drop_mix[1];
+  k.k2 ^= g_wm_drop_mix[2];
+  return k;
+}
 struct DropWords {
   uint32_t a, b;  // a: elements 0 (bits 0-15) and 1 (bits 16-31) of the counter; b: elements 2 and 3
 };

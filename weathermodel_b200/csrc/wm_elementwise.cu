@@ -135,39 +135,71 @@ embed_fwd_kernel(const float* __restrict__ weather, const uint8_t* __restrict__ 
     const int t0 = tile * kEmbTok;
     const int nt = min(kEmbTok, M - t0);
     __syncthreads();  // previous tile's readers are done with sX / sRaw (and, first time round, sW is complete)
+    // Both staging loops keep EIGHT independent loads in flight per thread: one load per iteration exposed the full
+    // global-memory latency ~15 times per tile (0.40 ms for the large shape, 4x the arithmetic).
     {  // the tile's weather block is contiguous in memory: straight coalesced copy
       const float* src = weather + static_cast<size_t>(t0) * F;
-      for (int i = threadIdx.x; i < nt * F; i += blockDim.x) sRaw[i] = src[i];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kEmbTok * Fin; i += blockDim.x) {
-      const int c = i / kEmbTok, tt = i - c * kEmbTok;  // token fastest: conflict-free smem on both sides (F is odd)
-      const int t = t0 + tt;
-      float v = 0.0f;
-      if (t < M) {
-        const int b = t / S, sq = t - b * S;
-        if (c < F) {
-          const float w = sRaw[tt * F + c];
-          const uint8_t m = mask[b * msb + sq * mss + c];
-          v = m ? w * 0.0f : w;  // weather * (~mask): keeps NaN/Inf semantics of the multiply
-        } else if (c == F) {
-          v = (year[t] - 1970.0f) / 100.0f;
-        } else if (c == F + 1) {
-          v = coords[b * 2] / 360.0f;
-        } else {
-          v = coords[b * 2 + 1] / 180.0f;
+      const int n = nt * F;
+      for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
+        float r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * blockDim.x;
+          r[u] = i < n ? __ldg(src + i) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * blockDim.x;
+          if (i < n) sRaw[i] = r[u];
         }
       }
-      sX[i] = v;
+    }
+    __syncthreads();
+    for (int i0 = threadIdx.x; i0 < kEmbTok * Fin; i0 += 8 * blockDim.x) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        const int c = i / kEmbTok, tt = i - c * kEmbTok;  // token fastest: conflict-free smem on both sides (F is odd)
+        const int t = t0 + tt;
+        v[u] = 0.0f;
+        if (i < kEmbTok * Fin && t < M) {
+          const int b = t / S, sq = t - b * S;
+          if (c < F) {
+            const float w = sRaw[tt * F + c];
+            const uint8_t m = mask[b * msb + sq * mss + c];
+            v[u] = m ? w * 0.0f : w;  // weather * (~mask): keeps NaN/Inf semantics of the multiply
+          } else if (c == F) {
+            v[u] = (__ldg(year + t) - 1970.0f) / 100.0f;
+          } else if (c == F + 1) {
+            v[u] = __ldg(coords + b * 2) / 360.0f;
+          } else {
+            v[u] = __ldg(coords + b * 2 + 1) / 180.0f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < kEmbTok * Fin) sX[i] = v[u];
+      }
     }
     __syncthreads();
     if (xin && blockIdx.y == 0) {  // bf16 copy of the input rows for the in_proj weight gradient
-      for (int i = threadIdx.x; i < kEmbTok * (kXinLd / 2); i += blockDim.x) {
-        const int tt = i / (kXinLd / 2), c2 = (i - tt * (kXinLd / 2)) * 2;
+      // lanes run over tokens (conflict-free reads of the channel-major tile); a lane writes 16 bytes = 8 channels
+      for (int i = threadIdx.x; i < kEmbTok * (kXinLd / 8); i += blockDim.x) {
+        const int c8 = (i / kEmbTok) * 8, tt = i - (i / kEmbTok) * kEmbTok;
         const int t = t0 + tt;
         if (t < M) {
-          const float a = c2 < Fin ? sX[c2 * kEmbTok + tt] : 0.0f, b2 = c2 + 1 < Fin ? sX[(c2 + 1) * kEmbTok + tt] : 0.0f;
-          reinterpret_cast<uint32_t*>(xin)[(static_cast<size_t>(t) * kXinLd + c2) >> 1] = pack_bf16x2(a, b2);
+          float a[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = c8 + j < Fin ? sX[(c8 + j) * kEmbTok + tt] : 0.0f;
+          uint4 o;
+          o.x = pack_bf16x2(a[0], a[1]);
+          o.y = pack_bf16x2(a[2], a[3]);
+          o.z = pack_bf16x2(a[4], a[5]);
+          o.w = pack_bf16x2(a[6], a[7]);
+          *reinterpret_cast<uint4*>(xin + static_cast<size_t>(t) * kXinLd + c8) = o;
         }
       }
     }
@@ -382,7 +414,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      const float* __restrict__ gamma, const float* __restrict__ mean,
                      const float* __restrict__ rstd, __nv_bfloat16* __restrict__ dx,
                      __nv_bfloat16* __restrict__ dx_drop, int M, int D, uint32_t drop_thresh, float drop_scale,
-                     DropKeys dkeys, float* __restrict__ partial, int stages) {
+                     DropKeys dkeys_in, float* __restrict__ partial, int stages) {
+  const DropKeys dkeys = drop_keys_live(dkeys_in);  // (+ the per-replay words of a captured step; zero otherwise)
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const uint32_t row_bytes = static_cast<uint32_t>(D) * 2u;
   const uint32_t tens_bytes = static_cast<uint32_t>(kRows) * row_bytes;
@@ -898,8 +931,9 @@ int launch_loss_former(const float* y, int ldy, const float* weather, const uint
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            __nv_bfloat16* __restrict__ shadow, int64_t n, float lr, float beta1, float beta2, float eps,
+            __nv_bfloat16* __restrict__ shadow, int64_t n, float lr, float omb1, float beta2, float omb2, float eps,
             float weight_decay, float bc1, float bc2_sqrt, float grad_scale) {
+  // omb1 = float(1 - beta1), omb2 = float(1 - beta2) formed in double on the host, as torch forms its lerp / addcmul weights
   const float step_size = lr / bc1;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -907,8 +941,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     float pi = p[i];
     if (weight_decay != 0.0f) gi = fmaf(weight_decay, pi, gi);
     float mi = m[i], vi = v[i];
-    mi = mi + (1.0f - beta1) * (gi - mi);            // exp_avg.lerp_(grad, 1 - beta1), weight < 0.5
-    vi = vi * beta2 + (1.0f - beta2) * gi * gi;      // mul_(beta2).addcmul_(g, g, 1 - beta2)
+    mi = mi + omb1 * (gi - mi);                      // exp_avg.lerp_(grad, 1 - beta1), weight < 0.5
+    vi = vi * beta2 + omb2 * gi * gi;                // mul_(beta2).addcmul_(g, g, 1 - beta2)
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     pi = pi - step_size * (mi / denom);              // addcdiv_(exp_avg, denom, value=-step_size)
     p[i] = pi; m[i] = mi; v[i] = vi;
@@ -916,18 +950,63 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+// The same update with the step-dependent scalars read from DEVICE memory: hyper = {lr, 1 - beta1^t, sqrt(1 - beta2^t)}.
+// A captured training step (CUDA graph) replays this launch unchanged while the host refreshes the three numbers.
+__global__ void __launch_bounds__(256)
+adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                __nv_bfloat16* __restrict__ shadow, int64_t n, const float* __restrict__ hyper, float omb1, float beta2,
+                float omb2, float eps, float weight_decay, float grad_scale) {
+  const float lr = hyper[0], bc1 = hyper[1], bc2_sqrt = hyper[2];
+  const float step_size = lr / bc1;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    float pi = p[i];
+    if (weight_decay != 0.0f) gi = fmaf(weight_decay, pi, gi);
+    float mi = m[i], vi = v[i];
+    mi = mi + omb1 * (gi - mi);
+    vi = vi * beta2 + omb2 * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi = pi - step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (shadow) shadow[i] = __float2bfloat16(pi);
+  }
+}
+int launch_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, __nv_bfloat16* shadow, int64_t n,
+                    const float* hyper_dev, double beta1, double beta2, float eps, float weight_decay, float grad_scale,
+                    cudaStream_t stream) {
+  if (n <= 0) return WM_OK;
+  if (!hyper_dev) return WM_ERR_ARG;
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_dev_kernel<<<blocks, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, shadow, n, hyper_dev,
+                                              static_cast<float>(1.0 - beta1), static_cast<float>(beta2),
+                                              static_cast<float>(1.0 - beta2), eps, weight_decay, grad_scale);
+  WM_COUNT_LAUNCH();
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+__global__ void step_params_apply_kernel(const uint32_t* __restrict__ words) {
+  if (threadIdx.x < 3) g_wm_drop_mix[threadIdx.x] = words ? words[threadIdx.x] : 0u;
+}
+int launch_step_params_apply(const uint32_t* dev_words, cudaStream_t stream) {
+  step_params_apply_kernel<<<1, 32, 0, stream>>>(dev_words);
+  WM_COUNT_LAUNCH();
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
 int launch_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, __nv_bfloat16* shadow,
-                int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                int64_t n, float lr, double beta1, double beta2, float eps, float weight_decay, int step,
                 float grad_scale, cudaStream_t stream) {
   if (n <= 0) return WM_OK;
   if (step < 1) return WM_ERR_ARG;
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  const double bc1 = 1.0 - pow(beta1, step);
+  const double bc2 = 1.0 - pow(beta2, step);
   int blocks = static_cast<int>((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_kernel<<<blocks, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, shadow, n, lr, beta1, beta2, eps,
-                                          weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
-                                          grad_scale);
+  adam_kernel<<<blocks, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, shadow, n, lr, static_cast<float>(1.0 - beta1),
+                                          static_cast<float>(beta2), static_cast<float>(1.0 - beta2), eps, weight_decay,
+                                          static_cast<float>(bc1), static_cast<float>(sqrt(bc2)), grad_scale);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }

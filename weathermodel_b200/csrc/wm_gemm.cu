@@ -160,7 +160,7 @@ int g_gemm_diag = 0;  // copied into GemmEpilogue::diag by the launcher
 
 template <typename OutT>
 WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const float* sbias, const GemmEpilogue& ep,
-                             int row, int n0, int M, int N, bool wide, uint8_t* sdst, int swz_chunk = -1) {
+                             const DropKeys& dk, int row, int n0, int M, int N, bool wide, uint8_t* sdst, int swz_chunk = -1) {
   // sdst (bf16 outputs only): this lane's 32 bytes of the chunk inside the warp's shared-memory staging tile; the
   // tile leaves through coalesced stores once all chunks are in (gemm_epilogue_tile). nullptr: direct stores.
   // swz_chunk >= 0: sdst is the lane's 128-byte ROW of a 32 x 64 SWIZZLE_128B box (TMA-store epilogue) and the two
@@ -200,7 +200,7 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
     const uint32_t x0 = (static_cast<uint32_t>(row) * static_cast<uint32_t>((N + 15) >> 4) + static_cast<uint32_t>(n0 >> 4)) * 4u;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-      const DropWords fl = drop_flags4(x0 + w, ep.dkeys, add2);
+      const DropWords fl = drop_flags4(x0 + w, dk, add2);
       f[4 * w] = __uint_as_float(__float_as_uint(f[4 * w] * ep.drop_scale) & drop_mask32<0>(fl));
       f[4 * w + 1] = __uint_as_float(__float_as_uint(f[4 * w + 1] * ep.drop_scale) & drop_mask32<1>(fl));
       f[4 * w + 2] = __uint_as_float(__float_as_uint(f[4 * w + 2] * ep.drop_scale) & drop_mask32<2>(fl));
@@ -318,6 +318,7 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
   // not the MMAs, set the pace (tools/gemm_diag.py: linear1 0.505 ms with, 0.359 ms without the stores). Staged, a
   // warp-wide 16-byte store covers whole row segments: 4 - 5 lines per instruction instead of 32.
   const uint32_t pitch = static_cast<uint32_t>(cols_per) * 2u + 16u;  // odd number of 16-byte units: conflict-free
+  const DropKeys dk = ep.drop_thresh ? drop_keys_live(ep.dkeys) : ep.dkeys;  // (+ the per-replay words of a captured step)
   if (ep.bias) {
     __syncwarp();
     for (int j = lane; j < cols_per; j += 32) sbias[j] = (n_base + j < N) ? __ldg(ep.bias + n_base + j) : 0.0f;
@@ -349,13 +350,13 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
         tmem_ld_wait();
         if (d & 1) {
           if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, va);
-          if (tmC) epi_process16<OutT>(vb, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3);
-          else epi_process16<OutT>(vb, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide,
+          if (tmC) epi_process16<OutT>(vb, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3);
+          else epi_process16<OutT>(vb, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide,
                                    stage ? stage + lane * pitch + c0 * 2 : nullptr);
         } else {
           if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, vb);
-          if (tmC) epi_process16<OutT>(va, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3);
-          else epi_process16<OutT>(va, aux[d], sbias + c0, ep, row, n_base + c0, M, N, wide,
+          if (tmC) epi_process16<OutT>(va, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3);
+          else epi_process16<OutT>(va, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide,
                                    stage ? stage + lane * pitch + c0 * 2 : nullptr);
         }
         if (c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);

@@ -92,8 +92,12 @@ int launch_loss_former(const float* y, int ldy, const float* weather, const uint
                        float* scratch, float* loss_out, const float* grad_scale, __nv_bfloat16* dy, int lddy,
                        float* mu_out, float* var_out, cudaStream_t stream);
 int launch_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, __nv_bfloat16* shadow,
-                int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                int64_t n, float lr, double beta1, double beta2, float eps, float weight_decay, int step,
                 float grad_scale, cudaStream_t stream);
+int launch_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, __nv_bfloat16* shadow, int64_t n,
+                    const float* hyper_dev, double beta1, double beta2, float eps, float weight_decay, float grad_scale,
+                    cudaStream_t stream);
+int launch_step_params_apply(const uint32_t* dev_words, cudaStream_t stream);
 int launch_cast_transpose(const float* w, __nv_bfloat16* wt, int rows, int cols, int ld_out, cudaStream_t stream);
 int launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream);
 

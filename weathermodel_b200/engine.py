@@ -312,8 +312,11 @@ def encoder_apply(runtime: EncoderRuntime, weather, coords, year, mask, training
     coords = coords.contiguous().float()
     year = year.contiguous().float()
     runtime.ensure_flat(weather.device)
-    anchor = runtime._named[0][1]
     if torch.is_grad_enabled() and any(p.requires_grad for _, p in runtime._named):
+        # A fresh leaf per call makes autograd track the node. (A parameter in this role drags its AccumulateGrad node
+        # along: that node remembers the stream of the step it was created in for as long as any earlier graph is alive,
+        # and a backward recorded into a CUDA graph then fails on a dependency to that uncaptured stream.)
+        anchor = torch.empty((), dtype=torch.float32, device=weather.device).requires_grad_()
         y = _EncoderFn.apply(anchor, runtime, weather, coords, year, mask, training)
         y._wm_src = (runtime, runtime.step_counter)  # lets a fused loss park its bf16 gradient for this forward
         return y

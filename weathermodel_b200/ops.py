@@ -203,6 +203,39 @@ def tune_gemm_sites(M, D, FF, dropout_p, device, min_tokens=8192, reps=5, margin
     return chosen
 
 
+def tune_gemm_call(a, b, reps=5, margin=0.03, **kw):
+    """Pick the fastest (bit-identical) kernel variant for ONE gemm_tn call signature -- the (M, N, K, epilogue) of
+    `gemm_tn(a, b, **kw)` -- the same way tune_gemm_sites does for the encoder's eight sites. Returns (variant, {variant: ms})."""
+    _cuda(a, b)
+    M, K = a.shape
+    N = b.shape[0]
+    L = lib()
+    ep = _gemm_epilogue(**{k: v for k, v in kw.items() if k not in ("out_fp32", "tile_n")})
+    out = torch.empty((M, N), dtype=BF16, device=a.device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def launch():
+        check(L.wm_gemm_tn(_p(a), a.stride(0), _p(b), b.stride(0), M, N, K, C.byref(ep), _p(out), N, 0, 0, _stream()),
+              "wm_gemm_tn (tuning)")
+
+    times = {}
+    for _ in range(2):
+        for var in GEMM_VARIANTS:
+            check(L.wm_gemm_set_variant(M, N, K, C.byref(ep), 0, *var), "wm_gemm_set_variant")
+            launch()
+            e0.record()
+            for _ in range(reps):
+                launch()
+            e1.record()
+            e1.synchronize()
+            times[var] = min(times.get(var, float("inf")), e0.elapsed_time(e1) / reps)
+    best = min(times, key=times.get)
+    if times[best] > (1.0 - margin) * times[GEMM_VARIANTS[0]]:
+        best = GEMM_VARIANTS[0]
+    check(L.wm_gemm_set_variant(M, N, K, C.byref(ep), 0, *best), "wm_gemm_set_variant")
+    return best, times
+
+
 def gemm_wgrad(a, b, accumulate_into=None, want_bias_grad=False):
     """dW[Nout,Kout] = a[Mtok,Nout]^T @ b[Mtok,Kout] (fp32 out, deterministic split-K); optionally also
     db[Nout] = a.sum(0) from the same kernel."""
@@ -443,3 +476,17 @@ def adam_fused(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.99
     check(lib().wm_adam_fused(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(shadow), param.numel(), float(lr),
                               float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
                               float(grad_scale), _stream()), "wm_adam_fused")
+
+
+def adam_fused_dev(param, grad, exp_avg, exp_avg_sq, hyper_dev, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+                   shadow=None, grad_scale=1.0):
+    """adam_fused with {lr, 1 - beta1^t, sqrt(1 - beta2^t)} read from the device tensor `hyper_dev` (captured steps)."""
+    _cuda(param, grad, exp_avg, exp_avg_sq, shadow, hyper_dev)
+    check(lib().wm_adam_fused_dev(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(shadow), param.numel(), _p(hyper_dev),
+                                  float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale), _stream()),
+          "wm_adam_fused_dev")
+
+
+def step_params_apply(dev_words):
+    """Install the per-replay dropout words (device int32[>=3]; None = zeros) -- see include/wm_b200.h."""
+    check(lib().wm_step_params_apply(_p(dev_words), _stream()), "wm_step_params_apply")

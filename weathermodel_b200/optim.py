@@ -30,6 +30,9 @@ class FusedAdam(torch.optim.Optimizer):
         self._flat_m = None
         self._flat_v = None
         self._step = 0
+        # set by graph_step.CapturedTrainStep while it records a step: a device tensor {lr, 1 - b1^t, sqrt(1 - b2^t)} the
+        # update kernels read instead of taking the numbers as launch parameters; step counters are then kept by the caller
+        self._captured_hyper = None
 
     @property
     def runtime(self) -> Optional[EncoderRuntime]:
@@ -82,23 +85,39 @@ class FusedAdam(torch.optim.Optimizer):
             in_flat = [p for _, p in rt._named]
             # the flat launch is valid only if every flat parameter received its gradient as a view of
             # the flat gradient buffer in this step (frozen / unused tensors fall back to per-tensor)
+            if self._captured_hyper is not None and (self._flat_m is None or getattr(self, "_bound_to", None) is not rt):
+                raise RuntimeError("FusedAdam: record a step only after an eager step has bound the optimiser state")
             if all(p.grad is not None and p.grad.data_ptr() == rt.grad_view(i).data_ptr()
                    for i, p in enumerate(in_flat)) and self._bind_flat_state():
-                self._step += 1
                 with torch.cuda.device(rt.flat_params.device):
-                    ops.adam_fused(rt.flat_params, rt.flat_grads, self._flat_m, self._flat_v, self._step, lr, b1, b2,
-                                   eps, wd)
+                    if self._captured_hyper is not None:
+                        ops.adam_fused_dev(rt.flat_params, rt.flat_grads, self._flat_m, self._flat_v, self._captured_hyper,
+                                           b1, b2, eps, wd)
+                    else:
+                        self._step += 1
+                        ops.adam_fused(rt.flat_params, rt.flat_grads, self._flat_m, self._flat_v, self._step, lr, b1, b2,
+                                       eps, wd)
+                        self._step_t.fill_(float(self._step))  # one host tensor shared by every flat parameter's state
                 rt.mark_weights_dirty()
-                self._step_t.fill_(float(self._step))  # one host tensor shared by every flat parameter's state
                 flat_ids = {id(p) for p in in_flat}
         for p in group["params"]:
             if id(p) in flat_ids or p.grad is None:
                 continue
             st = self.state[p]
             if "exp_avg" not in st:
+                if self._captured_hyper is not None:
+                    raise RuntimeError("FusedAdam: record a step only after an eager step has created the optimiser state")
                 st["step"] = torch.tensor(0.0)
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            if self._captured_hyper is not None:  # recorded step: same device-side scalars as the flat bucket
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()):
+                    raise RuntimeError("FusedAdam: a captured step needs contiguous fp32 CUDA parameters")
+                with torch.cuda.device(p.device):
+                    ops.adam_fused_dev(p, p.grad, st["exp_avg"], st["exp_avg_sq"], self._captured_hyper, b1, b2, eps, wd)
+                if rt is not None:
+                    rt.mark_weights_dirty()
+                continue
             st["step"] += 1
             k = int(st["step"])
             if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous():

@@ -47,6 +47,14 @@ class StreamingDataset(torch.utils.data.IterableDataset):
         if masking_function not in table:
             raise ValueError(f"Masking function {masking_function} is not valid")
         self.masking_function = table[masking_function]
+        # The first chunk starts loading NOW (no RNG involved): BaseTrainer builds the train and validation loaders at
+        # the top of an epoch, so the validation loader's first file is read while the training epoch runs and the
+        # training loader's while the previous epoch's bookkeeping finishes.
+        self._first = None
+        if len(self.file_paths) >= 3 and torch.device(self.device).type == "cuda":
+            import os
+            if os.path.exists(self.file_paths[1]):
+                self._first = self._start_prefetch(self.file_paths[1])
 
     # ---- masks (reference :56-84) ------------------------------------------------------------------
     def weatherbert_masking_function(self, seq_len, n_features, batch_size):
@@ -98,7 +106,14 @@ class StreamingDataset(torch.utils.data.IterableDataset):
         copied on a side stream; the returned tensors carry an event (`_ready`) the consumer stream waits on. No RNG
         is touched here, so running it one chunk ahead in a helper thread leaves the mask / randperm order alone."""
         on_cuda = torch.device(self.device).type == "cuda"
-        data = torch.load(path, weights_only=False, map_location="cpu" if on_cuda else self.device)
+        data = None
+        if on_cuda:
+            try:  # map the file instead of reading it: the only copy of the payload is then the one to the device
+                data = torch.load(path, weights_only=False, map_location="cpu", mmap=True)
+            except Exception:  # noqa: BLE001 -- legacy (non-zip) files cannot be mapped
+                data = None
+        if data is None:
+            data = torch.load(path, weights_only=False, map_location="cpu" if on_cuda else self.device)
         if hasattr(data, "tensors"):
             weather, coords, index = data.tensors[:3]
         else:
@@ -111,15 +126,18 @@ class StreamingDataset(torch.utils.data.IterableDataset):
             return None
         if not on_cuda:
             return weather.to(self.device).float(), coords.to(self.device).float(), index.to(self.device).float()
-        with torch.cuda.device(self.device):
+        from ...graph_step import CAPTURE_LOCK  # no CUDA work of this helper thread while a training step is being recorded
+
+        with CAPTURE_LOCK, torch.cuda.device(self.device):
             if getattr(self, "_copy_stream", None) is None:
                 self._copy_stream = torch.cuda.Stream(device=self.device)
-            host = [t.float().contiguous().pin_memory() for t in (weather, coords, index)]
             with torch.cuda.stream(self._copy_stream):
-                out = [t.to(self.device, non_blocking=True) for t in host]
+                # pageable -> device on the side stream: the driver stages the copy itself (and blocks only this helper
+                # thread, with the GIL released); pinning 185 MB per chunk first cost more than the copy
+                out = [t.to(self.device).float() for t in (weather, coords, index)]
                 ready = torch.cuda.Event()
                 ready.record(self._copy_stream)
-        return out[0], out[1], out[2], ready, host  # `host` keeps the pinned buffers alive until the copy is waited on
+        return out[0], out[1], out[2], ready, None
 
     def _start_prefetch(self, path):
         box = {}
@@ -162,7 +180,7 @@ class StreamingDataset(torch.utils.data.IterableDataset):
         carry: Optional[List[torch.Tensor]] = None
         n_groups = len(self.file_paths) // 3
         weekly = [self.file_paths[3 * gi + 1] for gi in range(n_groups)]  # the weekly file of each triple (:198)
-        pending = self._start_prefetch(weekly[0]) if n_groups else None
+        pending, self._first = (self._first or self._start_prefetch(weekly[0])) if n_groups else None, None
         for gi in range(n_groups):
             th, box = pending
             th.join()

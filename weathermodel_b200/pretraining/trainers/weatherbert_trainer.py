@@ -21,6 +21,8 @@ torch.manual_seed(1234)
 
 
 class WeatherBertTrainer(BaseTrainer):
+    _graph_capturable = True  # loss stays on the device end to end
+
     def __init__(self, model: WeatherBERT, masking_prob: float, n_masked_features: int, **kwargs):
         super().__init__(model, **kwargs)
         self.masking_function = "weatherbert"

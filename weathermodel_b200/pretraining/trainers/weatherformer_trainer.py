@@ -16,6 +16,8 @@ from ..models.weatherformer import WeatherFormer
 
 
 class WeatherFormerTrainer(BaseTrainer):
+    _graph_capturable = True  # loss stays on the device end to end
+
     def __init__(self, model: WeatherFormer, masking_prob: float, n_masked_features: int, beta: float, **kwargs):
         super().__init__(model, **kwargs)
         self.masking_prob = masking_prob
