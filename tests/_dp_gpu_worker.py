@@ -45,7 +45,9 @@ def main():
             m.p = 0.0
         if isinstance(m, nn.MultiheadAttention):
             m.dropout = 0.0
-    ddp = BucketedDataParallel(model, bucket_cap_mb=2.0)  # several layer buckets at this size
+    # several layer buckets at this size; WM_DP_OVERLAP (set by the test) picks overlapped buckets or the single all-reduce
+    ddp = BucketedDataParallel(model, bucket_cap_mb=2.0)
+    report["overlap"] = ddp.overlap
     rt = model.runtime
     report["buckets"] = len(rt.bucket_schedule())
     # every rank can rebuild every rank's batch
@@ -105,8 +107,9 @@ def main():
             m.p = 0.1
         if isinstance(m, nn.MultiheadAttention):
             m.dropout = 0.1
-    seeds = [torch.tensor([rt.seed], dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(seeds, torch.tensor([rt.seed], dtype=torch.int64, device=dev))
+    seed63 = rt.seed & 0x7FFFFFFFFFFFFFFF  # (the seed is a uint64: int64 tensors take 63 bits of it)
+    seeds = [torch.tensor([seed63], dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(seeds, torch.tensor([seed63], dtype=torch.int64, device=dev))
     report["dropout_seeds_differ_per_rank"] = len({int(s.item()) for s in seeds}) == world
     for _ in range(2):
         opt.zero_grad()

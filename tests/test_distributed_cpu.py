@@ -30,7 +30,7 @@ def _worker(rank, world, port, out_dir):
 
         torch.manual_seed(100 + rank)  # different initial weights per rank: the wrapper must broadcast rank 0's
         model = WeatherFormer(31, 31, torch.device("cpu"), num_heads=4, num_layers=3, hidden_dim_factor=12)
-        ddp = BucketedDataParallel(model, bucket_cap_mb=0.2)
+        ddp = BucketedDataParallel(model, bucket_cap_mb=0.2, overlap=True)
         rt = model.runtime
         assert ddp.module is model and rt.grad_ready_hook is not None
         # (1) broadcast

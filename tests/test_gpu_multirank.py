@@ -23,20 +23,21 @@ def _free_port():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least two GPUs")
-def test_bucketed_data_parallel_equals_average_of_single_gpu_gradients(tmp_path):
+@pytest.mark.parametrize("overlap", ["0", "1"])  # one all-reduce after backward (default) / buckets overlapped with backward
+def test_bucketed_data_parallel_equals_average_of_single_gpu_gradients(tmp_path, overlap):
     world = 2
     out = tmp_path / "dp_report.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "_dp_gpu_worker.py"), str(out)]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, WM_DP_OVERLAP=overlap))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     rep = json.load(open(out))
     keep = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(keep):
-        json.dump(rep, open(os.path.join(keep, "r02_multirank_parity.json"), "w"), indent=1)
+        json.dump(rep, open(os.path.join(keep, f"r02_multirank_parity_overlap{overlap}.json"), "w"), indent=1)
     for r in rep["ranks"]:
-        assert r["world"] == world and r["buckets"] >= 3
+        assert r["world"] == world and r["buckets"] >= 3 and r["overlap"] == (overlap == "1")
         assert r["loss_matches_local"]
         # fp32 round-off only: the same deterministic kernels produced both sides, NCCL averages in fp32
         assert r["grad_rel_err_vs_average_of_single_gpu"] < 1e-6, r

@@ -8,6 +8,7 @@ kernels producing a bucket (one or more encoder layers, top first) are enqueued,
 with NCCL on its own stream (async_op) while the next layers' backward kernels run; all handles are waited
 once before the optimiser step. No per-parameter hooks, no gradient copies.
 """
+import os
 from typing import List
 
 import torch
@@ -16,10 +17,19 @@ import torch.nn as nn
 
 
 class BucketedDataParallel(nn.Module):
-    def __init__(self, module: nn.Module, process_group=None, bucket_cap_mb: float = 25.0):
+    def __init__(self, module: nn.Module, process_group=None, bucket_cap_mb: float = 25.0, overlap=None):
+        """overlap: True = all-reduce every bucket as soon as its gradients are enqueued (DDP's scheme); False = one
+        all-reduce over the whole flat gradient buffer when backward is done. Default from WM_DP_OVERLAP (unset: False).
+        Why the default is NOT to overlap on this path (profiles/r02_dp8_timeline.txt, 8 x B200): the payload is tiny --
+        128 MB per 60 ms step, ~0.5 ms at NVSwitch speed -- but every big kernel here is a persistent one-CTA-per-SM grid
+        with static tile striding. An NCCL kernel that holds even a few SMs while such a kernel starts pushes that
+        kernel's displaced CTAs into a second wave (gemm_tn2 311 -> 791 us, gemm_wgrad 239 -> 480 us when an all-reduce
+        was resident), and NCCL itself, starved of SMs, stays resident for 1-3 ms per 16 MB bucket. Overlapped buckets
+        cost +1.8 ms per step (+2.9 %) at 8 GPUs; one exposed all-reduce at the end costs less than a third of that."""
         super().__init__()
         self.module = module
         self.process_group = process_group
+        self.overlap = (os.environ.get("WM_DP_OVERLAP", "0") == "1") if overlap is None else bool(overlap)
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self._pending: List = []
         self.bucket_cap_mb = bucket_cap_mb
@@ -66,7 +76,7 @@ class BucketedDataParallel(nn.Module):
 
     def _make_hook(self, rt):
         def hook(lo: int, hi: int):
-            if self.world_size == 1:
+            if self.world_size == 1 or not self.overlap:
                 return
             sl = rt.flat_grads[lo:hi]
             if self._backend == "nccl":
@@ -84,6 +94,13 @@ class BucketedDataParallel(nn.Module):
             if self.world_size > 1 and getattr(rt, "_dp_owner", None) is not self:
                 raise RuntimeError("BucketedDataParallel: an encoder runtime was rebuilt after wrapping and ran its "
                                    "backward without the bucket hook (call the wrapper's forward, or re-wrap)")
+        if self.world_size > 1 and not self.overlap:  # one collective over the whole flat buffer, after backward
+            for rt in self._runtimes:
+                if self._backend == "nccl":
+                    dist.all_reduce(rt.flat_grads, op=dist.ReduceOp.AVG, group=self.process_group)
+                else:
+                    dist.all_reduce(rt.flat_grads, op=dist.ReduceOp.SUM, group=self.process_group)
+                    rt.flat_grads.div_(self.world_size)
         for work, sl in self._pending:
             work.wait()
             if sl is not None:
