@@ -506,9 +506,9 @@ def run_ours(args, rank, world, local_rank):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the one `ncu --set full`
-# capture kept under profiles/ (r01_gemm_lin1_full_v2.txt: gemm_tn_kernel<bf16, 16 epilogue warps>, staged stores);
+# capture kept under profiles/ (r02_gemm_lin1_full.txt: gemm_tn2_kernel<bf16, 16 epilogue warps>, CTA pairs, TMA-store epilogue);
 # keyed by the GEMM shape it was taken on, null for the others.
-NCU_DRAM_BYTES_PER_LAUNCH = {(186880, 2304, 576): 218038016 + 806161664}
+NCU_DRAM_BYTES_PER_LAUNCH = {(186880, 2304, 576): 218011648 + 803014144}
 
 
 def main():
