@@ -38,6 +38,9 @@ __host__ __device__ constexpr int attn_keep_bit(int k) { return (k >> 1) + 16 * 
 #ifndef WM_ATTN_INT_PACK
 #define WM_ATTN_INT_PACK 0
 #endif
+#ifndef WM_ATTN_INTERLEAVE
+#define WM_ATTN_INTERLEAVE 1  // dropout hash and exponentials of the same elements side by side (-5 % with dropout)
+#endif
 WM_DEVICE uint32_t attn_pack2(float lo, float hi) {
 #if WM_ATTN_INT_PACK
   uint32_t d;
@@ -86,6 +89,8 @@ WM_DEVICE float fast_exp2(float x) {
   return y;
 }
 
+// (A/B, profiles/r02_attn_variants.txt: taking a quarter or half of the exponentials from the FMA pipe -- Cody-Waite split +
+// degree-4 polynomial on packed fp32 -- made the forward kernel 1-5 % SLOWER: the SFU is not its limiter.)
 // ------------------------------------------------------------------------------------------------
 // forward: persistent, warp-specialised, TMA-fed; probabilities never leave tensor memory.
 //   warps 0-11  softmax: warp w reads TMEM lane quarter w%4 (query rows of the current 128-row tile) and owns
@@ -107,9 +112,20 @@ WM_DEVICE float fast_exp2(float x) {
 // (v5 staged P through shared memory: a fence.proxy.async per warp and chunk cost ~300 cycles each and a single
 // thread could not issue ~35 small MMAs per tile fast enough -- profiles/r01_attn_phase_ticks.txt.)
 // ------------------------------------------------------------------------------------------------
-constexpr int kFwdSoftmaxWarps = 12;
-constexpr int kFwdThreads = 32 * 15;
-constexpr int kKC = 96;  // keys per score chunk (3 slices of 32 columns)
+// WM_ATTN_FWD_SLICES = 32-column slices per score chunk = softmax warps per TMEM lane quarter: 3 (12 softmax warps, 96-key
+// chunks, TMEM loads double-buffered) or 4 (16 softmax warps, 128-key chunks, single-buffered loads to stay under 104
+// registers): both kernels are bound by dependent-issue latency, so a fourth warp per scheduler is worth more than the
+// prefetch (profiles/r02_attn_ncu_summary.txt; A/B in profiles/r02_attn_variants.txt).
+#ifndef WM_ATTN_FWD_SLICES
+#define WM_ATTN_FWD_SLICES 4
+#endif
+constexpr int kFwdSlices = WM_ATTN_FWD_SLICES;
+constexpr int kFwdSoftmaxWarps = 4 * kFwdSlices;
+constexpr int kFwdWarpMma = kFwdSoftmaxWarps, kFwdWarpProd = kFwdSoftmaxWarps + 1, kFwdWarpStore = kFwdSoftmaxWarps + 2;
+constexpr int kFwdThreads = 32 * (kFwdSoftmaxWarps + 3);
+constexpr int kKC = 32 * kFwdSlices;       // keys per score chunk
+constexpr int kFwdMaxChunks = 384 / kKC;   // chunks that cover kSP key columns
+constexpr bool kFwdPrefetch = kFwdSlices == 3;
 
 struct AttnFwdBars {
   uint64_t q_full[3], q_ready[3], q_free[3];
@@ -128,7 +144,7 @@ struct AttnFwdGeom {
   static constexpr uint32_t QT = NCH * CSQ, KT = NCH * CSK;
   static constexpr uint32_t OUTB = NCH * 8 * 2 * 128;  // output staging tile (>= 128 * dh * 2)
   // + one chunk of slack: an MN-major B descriptor with N = DHP > 8 * NCH reads one chunk past the last V buffer
-  static constexpr uint32_t kSmem = 3 * QT + 2 * KVB * KT + CSK + 2 * OUTB + 2048 + 2 * 3 * 128 * 4 + 128;
+  static constexpr uint32_t kSmem = 3 * QT + 2 * KVB * KT + CSK + 2 * OUTB + 2048 + 2 * kFwdSlices * 128 * 4 + 128;
 };
 
 template <int NCH, bool DROP>
@@ -148,7 +164,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   uint8_t* sOut = sV + KVB * G::KT + G::CSK;
   uint8_t* sZero = sOut + 2 * G::OUTB;
   float* sMax = reinterpret_cast<float*>(sZero + 2048);  // [3][128]
-  float* sSum = sMax + 3 * 128;                          // [3][128]
+  float* sSum = sMax + kFwdSlices * 128;                 // [kFwdSlices][128]
   __shared__ AttnFwdBars bars;
   __shared__ uint32_t tmem_slot;
 
@@ -181,7 +197,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
     fence_barrier_init();
   }
   for (int i = tid; i < 2048 / 16; i += kFwdThreads) reinterpret_cast<uint4*>(sZero)[i] = make_uint4(0u, 0u, 0u, 0u);
-  if (warp == 12) tmem_alloc<512>(&tmem_slot);
+  if (warp == kFwdWarpMma) tmem_alloc<512>(&tmem_slot);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -189,7 +205,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   const uint32_t tmem = tmem_slot;
   const uint32_t tS = tmem, tO = tmem + kSP;  // O buffers at +0 / +64
 
-  if (warp == 13) {
+  if (warp == kFwdWarpProd) {
     // ------------------------------------------------------------------ TMA producer (+ Q fix-up)
     if (lane == 0) tma_prefetch_desc(&tm_qkv);
     const bool need_fix = (dh & 7) != 0;
@@ -232,7 +248,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
         if (lane == 0) mbar_arrive(&bars.q_ready[i]);
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == kFwdWarpMma) {
     // ------------------------------------------------------------------ MMA issue
     // (all 32 lanes run this code convergently; umma_*_warp elect the issuing lane)
     const uint32_t idesc_o = umma_idesc_bf16(128, DHP, 0, 1);
@@ -303,7 +319,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
         }
       }
     }
-  } else if (warp == 14) {
+  } else if (warp == kFwdWarpStore) {
     // ------------------------------------------------------------------ ctx store
     const int pv = dh >> 2;  // 8-byte pieces per row
     uint32_t t = 0;
@@ -346,15 +362,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
         // three-input maxima: 16 instead of 32 issue slots per 32 columns
         float mloc = -INFINITY;
         {
-          uint32_t va[32], vb[32];
+          uint32_t va[32], vb[kFwdPrefetch ? 32 : 1];
           tmem_ld32(tS + lane_sel + sl * 32, va);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < kFwdMaxChunks; ++c) {
             if (c < nkc) {
-              uint32_t(&cur)[32] = (c & 1) ? vb : va;
-              uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+              uint32_t(&cur)[32] = (kFwdPrefetch && (c & 1)) ? reinterpret_cast<uint32_t(&)[32]>(vb) : va;
               tmem_ld_wait();
-              if (c + 1 < nkc) tmem_ld32(tS + lane_sel + (c + 1) * kKC + sl * 32, nxt);
+              if (kFwdPrefetch) {
+                uint32_t(&nxt)[32] = (c & 1) ? va : reinterpret_cast<uint32_t(&)[32]>(vb);
+                if (c + 1 < nkc) tmem_ld32(tS + lane_sel + (c + 1) * kKC + sl * 32, nxt);
+              }
               const int k0 = c * kKC + sl * 32;
               if (k0 + 32 <= S) {
 #pragma unroll
@@ -364,31 +382,61 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
                 for (int j = 0; j < 32; ++j)
                   if (k0 + j < S) mloc = fmaxf(mloc, __uint_as_float(cur[j]));
               }
+              if (!kFwdPrefetch && c + 1 < nkc) tmem_ld32(tS + lane_sel + (c + 1) * kKC + sl * 32, va);
             }
           }
         }
         sMax[sl * 128 + row] = mloc;
         WM_FTICK(3);
-        named_bar_sync(1 + lq, 96);
+        named_bar_sync(1 + lq, 32 * kFwdSlices);
         WM_FTICK(4);
-        const float mrow = fmaxf(fmaxf(sMax[row], sMax[128 + row]), sMax[256 + row]);
+        float mrow = sMax[row];
+#pragma unroll
+        for (int k = 1; k < kFwdSlices; ++k) mrow = fmaxf(mrow, sMax[k * 128 + row]);
         const float mneg = -mrow * c2;
         const uint64_t c2p = f2_pack(c2, c2), mnegp = f2_pack(mneg, mneg);
         // ---- pass 2: exp2, row sum, dropout; P (bf16 pairs) replaces the first 16 columns of the slice in TMEM.
         // Packed fp32 pairs: one FFMA2 scales and shifts two scores, one FADD2 adds two probabilities to the row sum.
         uint64_t lsum2 = f2_pack(0.0f, 0.0f);
         {
-          uint32_t va[32], vb[32];
+          uint32_t va[32], vb[kFwdPrefetch ? 32 : 1];
           tmem_ld32(tS + lane_sel + sl * 32, va);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < kFwdMaxChunks; ++c) {
             if (c < nkc) {
-              uint32_t(&cur)[32] = (c & 1) ? vb : va;
-              uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+              uint32_t(&cur)[32] = (kFwdPrefetch && (c & 1)) ? reinterpret_cast<uint32_t(&)[32]>(vb) : va;
               const int k0 = c * kKC + sl * 32;
               tmem_ld_wait();
-              if (c + 1 < nkc) tmem_ld32(tS + lane_sel + (c + 1) * kKC + sl * 32, nxt);
+              if (kFwdPrefetch) {
+                uint32_t(&nxt)[32] = (c & 1) ? va : reinterpret_cast<uint32_t(&)[32]>(vb);
+                if (c + 1 < nkc) tmem_ld32(tS + lane_sel + (c + 1) * kKC + sl * 32, nxt);
+              }
               uint32_t pk[16];
+#if WM_ATTN_INTERLEAVE
+              // Dropout and softmax of the SAME four elements side by side: the keep-bit hash is integer work, the
+              // exponentials sit on the SFU queue (8 cycles per warp instruction and scheduler). Written as two
+              // separate loops the three warps of a scheduler -- which run in step, chunk by chunk -- all hashed and
+              // then all queued on the SFU; interleaved, each pipe's work hides under the other's.
+              if (DROP && k0 + 32 <= S) {
+                const uint32_t x0 = (rowbase + static_cast<uint32_t>(k0 >> 4)) * 4u;
+                uint32_t bits = 0u;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                  const DropWords f = drop_flags4(x0 + w, dkeys, add2);
+                  float xa, xb, xc, xd;
+                  f2_unpack(f2_fma(f2_pack_u(cur[4 * w], cur[4 * w + 1]), c2p, mnegp), xa, xb);
+                  f2_unpack(f2_fma(f2_pack_u(cur[4 * w + 2], cur[4 * w + 3]), c2p, mnegp), xc, xd);
+                  const float ea = fast_exp2(xa), eb = fast_exp2(xb), ec = fast_exp2(xc), ed = fast_exp2(xd);
+                  lsum2 = f2_add(lsum2, f2_add(f2_pack(ea, eb), f2_pack(ec, ed)));
+                  const uint32_t ma = drop_pair_mask(f.a), mb = drop_pair_mask(f.b);
+                  pk[2 * w] = attn_pack2(ea, eb) & ma;
+                  pk[2 * w + 1] = attn_pack2(ec, ed) & mb;
+                  bits |= (ma & (0x00010001u << (2 * w))) | (mb & (0x00010001u << (2 * w + 1)));
+                }
+                if (drop_words) drop_words[attn_drop_word_index(item, k0 >> 7, q >> 6, (k0 >> 5) & 3, q & 63)] = bits;
+              } else
+#endif
+              {
               if (k0 + 32 <= S) {
 #pragma unroll
                 for (int w = 0; w < 16; ++w) {
@@ -423,6 +471,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
                 // the backward kernel reads these instead of re-deriving the hash in its transposed order
                 if (drop_words) drop_words[attn_drop_word_index(item, k0 >> 7, q >> 6, (k0 >> 5) & 3, q & 63)] = bits;
               }
+              }
+              if (!kFwdPrefetch && c + 1 < nkc) tmem_ld32(tS + lane_sel + (c + 1) * kKC + sl * 32, va);
               tmem_st16(tS + lane_sel + k0, pk);
               tmem_st_wait();
               tc_fence_before();
@@ -439,9 +489,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
           lsum = l0 + l1;
         }
         sSum[sl * 128 + row] = lsum;
-        named_bar_sync(1 + lq, 96);
+        named_bar_sync(1 + lq, 32 * kFwdSlices);
         WM_FTICK(9);
-        const float tot = sSum[row] + sSum[128 + row] + sSum[256 + row];
+        float tot = sSum[row];
+#pragma unroll
+        for (int k = 1; k < kFwdSlices; ++k) tot += sSum[k * 128 + row];
         // ---- epilogue: O / (row sum) -> bf16 staging tile (compact [128, dh]); slice sl takes columns [16 sl, 16 sl + 16)
         const uint32_t ob = t & 1u;
         mbar_wait(&bars.o_full[ob], (t >> 1) & 1, 74);
@@ -478,7 +530,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == kFwdWarpMma) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
