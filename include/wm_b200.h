@@ -212,6 +212,11 @@ size_t wm_encoder_workspace_bytes(const wm_encoder_config* cfg);
 int wm_encoder_create(const wm_encoder_config* cfg, void* workspace, size_t workspace_bytes, wm_encoder** out);
 int wm_encoder_destroy(wm_encoder* enc);
 int wm_encoder_refresh_weights(wm_encoder* enc, const float* params, void* stream);
+/* The bf16 shadow of the flat parameter buffer inside the workspace (same offsets as the fp32 buffer): pass it as
+ * shadow_bf16 to wm_adam_fused / wm_adam_fused_dev and the optimiser writes it while it updates the parameters; then only
+ * the transposed copies have to be rebuilt before the next forward: */
+void* wm_encoder_shadow(wm_encoder* enc);
+int wm_encoder_refresh_transposes(wm_encoder* enc, const float* params, void* stream);
 /* y_out: fp32 [B*S, 32 or 64] (columns >= out_dim are padding). training: dropout live (nn.Module.train()).
  * save_for_backward = 1 keeps every layer's activations for wm_encoder_backward_*; 0 is the lean schedule of a
  * forward that no backward follows (torch.no_grad()): all layers reuse one set of buffers and nothing that only the

@@ -74,6 +74,8 @@ SIGNATURES = {
     "wm_encoder_create": (_i, [C.POINTER(EncoderConfig), _vp, _sz, C.POINTER(_vp)]),
     "wm_encoder_destroy": (_i, [_vp]),
     "wm_encoder_refresh_weights": (_i, [_vp, _vp, _vp]),
+    "wm_encoder_shadow": (_vp, [_vp]),
+    "wm_encoder_refresh_transposes": (_i, [_vp, _vp, _vp]),
     "wm_encoder_forward": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i, _i, _u64, _u64, _vp]),
     "wm_encoder_backward_head": (_i, [_vp, _vp, _vp, _vp]),
     "wm_encoder_backward_layers": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

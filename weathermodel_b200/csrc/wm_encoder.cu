@@ -282,22 +282,43 @@ int wm_encoder_destroy(wm_encoder* e) {
 }
 
 // fp32 master -> bf16 shadow (same offsets) + transposed copies used as the B operand of dgrad GEMMs
-int wm_encoder_refresh_weights(wm_encoder* e, const float* params, void* stream_) {
-  if (!e || !params) return WM_ERR_ARG;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+static int refresh_impl(wm_encoder* e, const float* params, bool cast_shadow, cudaStream_t st) {
   const wm_encoder_config& c = e->cfg;
-  WM_TRY(launch_cast_bf16(params, e->shadow, e->lay.total, st));
+  if (cast_shadow) WM_TRY(launch_cast_bf16(params, e->shadow, e->lay.total, st));
+  if (cudaMemsetAsync(e->wout_t, 0, static_cast<size_t>(c.D) * e->outP * 2, st) != cudaSuccess) return WM_ERR_CUDA;
+  TransposeJobs jobs;
+  jobs.n = 0;
+  auto add = [&](const float* w, __nv_bfloat16* wt, int rows, int cols, int ld_out) {
+    jobs.job[jobs.n++] = TransposeJob{w, wt, rows, cols, ld_out, 0};
+  };
   for (int l = 0; l < c.L; ++l) {
     const LayerParams& q = e->lay.layers[l];
-    WM_TRY(launch_cast_transpose(params + q.w_qkv, e->wt[l].wqkv_t, 3 * c.D, c.D, 3 * c.D, st));
-    WM_TRY(launch_cast_transpose(params + q.w_o, e->wt[l].wo_t, c.D, c.D, c.D, st));
-    WM_TRY(launch_cast_transpose(params + q.w1, e->wt[l].w1_t, c.FF, c.D, c.FF, st));
-    WM_TRY(launch_cast_transpose(params + q.w2, e->wt[l].w2_t, c.D, c.FF, c.D, st));
+    if (jobs.n + 4 >= kMaxTransposeJobs) {  // (very deep models: flush in batches)
+      WM_TRY(launch_cast_transpose_multi(jobs, st));
+      jobs.n = 0;
+    }
+    add(params + q.w_qkv, e->wt[l].wqkv_t, 3 * c.D, c.D, 3 * c.D);
+    add(params + q.w_o, e->wt[l].wo_t, c.D, c.D, c.D);
+    add(params + q.w1, e->wt[l].w1_t, c.FF, c.D, c.FF);
+    add(params + q.w2, e->wt[l].w2_t, c.D, c.FF, c.D);
   }
-  if (cudaMemsetAsync(e->wout_t, 0, static_cast<size_t>(c.D) * e->outP * 2, st) != cudaSuccess) return WM_ERR_CUDA;
-  WM_TRY(launch_cast_transpose(params + e->lay.w_out, e->wout_t, c.out_dim, c.D, e->outP, st));
-  return WM_OK;
+  add(params + e->lay.w_out, e->wout_t, c.out_dim, c.D, e->outP);
+  return launch_cast_transpose_multi(jobs, st);
 }
+
+int wm_encoder_refresh_weights(wm_encoder* e, const float* params, void* stream_) {
+  if (!e || !params) return WM_ERR_ARG;
+  return refresh_impl(e, params, true, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+// The same when the bf16 shadow is already current (wm_adam_fused / _dev wrote it through shadow_bf16 =
+// wm_encoder_shadow()): only the transposed copies are rebuilt.
+int wm_encoder_refresh_transposes(wm_encoder* e, const float* params, void* stream_) {
+  if (!e || !params) return WM_ERR_ARG;
+  return refresh_impl(e, params, false, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+void* wm_encoder_shadow(wm_encoder* e) { return e ? e->shadow : nullptr; }
 
 int wm_encoder_forward(wm_encoder* e, const float* params, const float* weather, const uint8_t* mask,
                        int64_t mask_stride_b, int64_t mask_stride_s, const float* year, const float* coords,

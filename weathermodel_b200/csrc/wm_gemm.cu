@@ -988,8 +988,23 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // out[r, c] = (accumulate ? out[r, c] : 0) + sum_s partial[s][r, c] for r < rows_valid, c < cols_valid
 // (fixed summation order -> deterministic); out row pitch ld_out, partial tiles are [Nout, Kout].
+// The fused bias gradient's partials are folded by extra blocks of the SAME launch (blockIdx.x >= main_blocks): one
+// launch per weight gradient instead of two.
+WM_DEVICE void wgrad_bias_fold(const float* __restrict__ partial, float* __restrict__ out, int Nout, int rows_valid, int splits,
+                               int block) {
+  const int r = block * blockDim.x + threadIdx.x;
+  if (r >= rows_valid) return;
+  float acc = 0.0f;
+  for (int s = 0; s < splits; ++s) acc += partial[static_cast<size_t>(s) * Nout + r];
+  out[r] = acc;
+}
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int Nout, int Kout,
-                                    int rows_valid, int cols_valid, int ld_out, int splits, int accumulate) {
+                                    int rows_valid, int cols_valid, int ld_out, int splits, int accumulate, int main_blocks,
+                                    const float* __restrict__ bias_partial, float* __restrict__ dbias) {
+  if (static_cast<int>(blockIdx.x) >= main_blocks) {
+    wgrad_bias_fold(bias_partial, dbias, Nout, rows_valid, splits, blockIdx.x - main_blocks);
+    return;
+  }
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<int64_t>(rows_valid) * cols_valid) return;
   const int r = static_cast<int>(i / cols_valid), c = static_cast<int>(i - static_cast<int64_t>(r) * cols_valid);
@@ -1002,7 +1017,12 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 
 // the same for full-width outputs whose rows are 16-byte aligned: one float4 per thread and split
 __global__ void wgrad_reduce4_kernel(const float4* __restrict__ partial, float4* __restrict__ out, int64_t n4_per_split,
-                                     int64_t n4_valid, int splits, int accumulate) {
+                                     int64_t n4_valid, int splits, int accumulate, int main_blocks,
+                                     const float* __restrict__ bias_partial, float* __restrict__ dbias, int Nout, int rows_valid) {
+  if (static_cast<int>(blockIdx.x) >= main_blocks) {
+    wgrad_bias_fold(bias_partial, dbias, Nout, rows_valid, splits, blockIdx.x - main_blocks);
+    return;
+  }
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4_valid) return;
   float4 acc = accumulate ? out[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -1016,15 +1036,6 @@ __global__ void wgrad_reduce4_kernel(const float4* __restrict__ partial, float4*
 // Work items = output tiles x token splits, one per CTA, all the same size: pick the split count that fills whole
 // waves of SMs (the first plan used ceil(2 * SMs / tiles) and lost up to a third of the machine to a nearly empty
 // last wave: 300 items on 148 SMs = 3 waves at 68 %), with a mild preference for fewer partial tiles to reduce.
-__global__ void wgrad_bias_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int Nout,
-                                         int rows_valid, int splits) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows_valid) return;
-  float acc = 0.0f;
-  for (int s = 0; s < splits; ++s) acc += partial[static_cast<size_t>(s) * Nout + r];
-  out[r] = acc;
-}
-
 int wgrad_plan(int Mtok, int Nout, int Kout, int* BN, int* splits, int* tok_per_split) {
   int bn;
   if (Kout <= 64) bn = 64;
@@ -1099,33 +1110,30 @@ static int launch_gemm_wgrad_impl(const void* A, int lda, const void* B, int ldb
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
   const int64_t n = static_cast<int64_t>(rows_valid) * cols_valid;
   const int threads = 256;
+  const int bias_blocks = (dbias && fuse) ? (rows_valid + threads - 1) / threads : 0;  // folded by the same launch
   if (cols_valid == Kout && ld_dw == Kout && (Kout & 3) == 0 && (reinterpret_cast<uintptr_t>(dW) & 15u) == 0 &&
       (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0) {
     // contiguous [rows_valid, Kout] block: same element order and summation order, four columns per thread
     const int64_t n4 = n / 4;
-    wgrad_reduce4_kernel<<<static_cast<int>((n4 + threads - 1) / threads), threads, 0, stream>>>(
+    const int main_blocks = static_cast<int>((n4 + threads - 1) / threads);
+    wgrad_reduce4_kernel<<<main_blocks + bias_blocks, threads, 0, stream>>>(
         reinterpret_cast<const float4*>(workspace), reinterpret_cast<float4*>(dW),
-        static_cast<int64_t>(Nout) * Kout / 4, n4, splits, accumulate);
+        static_cast<int64_t>(Nout) * Kout / 4, n4, splits, accumulate, main_blocks, bias_partial, dbias, Nout, rows_valid);
   } else {
-    const int blocks = static_cast<int>((n + threads - 1) / threads);
-    wgrad_reduce_kernel<<<blocks, threads, 0, stream>>>(workspace, dW, Nout, Kout, rows_valid, cols_valid, ld_dw,
-                                                        splits, accumulate);
+    const int main_blocks = static_cast<int>((n + threads - 1) / threads);
+    wgrad_reduce_kernel<<<main_blocks + bias_blocks, threads, 0, stream>>>(workspace, dW, Nout, Kout, rows_valid, cols_valid, ld_dw,
+                                                                           splits, accumulate, main_blocks, bias_partial, dbias);
   }
   WM_COUNT_LAUNCH();
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
-  if (dbias) {
-    if (fuse) {
-      wgrad_bias_reduce_kernel<<<(rows_valid + 255) / 256, 256, 0, stream>>>(bias_partial, dbias, Nout, rows_valid, splits);
-      WM_COUNT_LAUNCH();
-    } else {  // 256-wide tiles leave no room for the ones chunk: separate column-sum pass (stream-ordered reuse of
-              // the workspace: the partials above have been consumed by wgrad_reduce)
-      float* tmp = workspace + colsum_workspace_bytes(Mtok, Nout) / sizeof(float);
-      const int rc2 = launch_colsum(reinterpret_cast<const __nv_bfloat16*>(A), lda, Mtok, Nout, tmp, workspace, stream);
-      if (rc2) return rc2;
-      if (cudaMemcpyAsync(dbias, tmp, static_cast<size_t>(rows_valid) * sizeof(float), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
-        return WM_ERR_CUDA;
-      return WM_OK;
-    }
+  if (dbias && !fuse) {  // 256-wide tiles leave no room for the ones chunk: separate column-sum pass (stream-ordered reuse
+                         // of the workspace: the partials above have been consumed by wgrad_reduce)
+    float* tmp = workspace + colsum_workspace_bytes(Mtok, Nout) / sizeof(float);
+    const int rc2 = launch_colsum(reinterpret_cast<const __nv_bfloat16*>(A), lda, Mtok, Nout, tmp, workspace, stream);
+    if (rc2) return rc2;
+    if (cudaMemcpyAsync(dbias, tmp, static_cast<size_t>(rows_valid) * sizeof(float), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+      return WM_ERR_CUDA;
+    return WM_OK;
   }
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }

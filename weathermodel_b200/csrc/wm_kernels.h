@@ -98,6 +98,17 @@ int launch_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_
                     const float* hyper_dev, double beta1, double beta2, float eps, float weight_decay, float grad_scale,
                     cudaStream_t stream);
 int launch_step_params_apply(const uint32_t* dev_words, cudaStream_t stream);
+constexpr int kMaxTransposeJobs = 72;  // 4 per layer + the head (kernel parameter space: 72 x 32 bytes)
+struct TransposeJob {
+  const float* w;      // [rows, cols] fp32
+  __nv_bfloat16* wt;   // [cols, ld_out] bf16, wt[c, r] = w[r, c]
+  int rows, cols, ld_out, tile0;
+};
+struct TransposeJobs {
+  int n;
+  TransposeJob job[kMaxTransposeJobs];
+};
+int launch_cast_transpose_multi(TransposeJobs& jobs, cudaStream_t stream);
 int launch_cast_transpose(const float* w, __nv_bfloat16* wt, int rows, int cols, int ld_out, cudaStream_t stream);
 int launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream);
 

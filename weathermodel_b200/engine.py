@@ -49,6 +49,7 @@ class EncoderRuntime:
         self._handles: Dict[Tuple[int, int, bool], int] = {}
         self._active: Optional[int] = None
         self._shadow_version = None
+        self._shadow_fresh_ver = None
         self.step_counter = 0
         self.base_seed = 0x5EED_2002
         self.seed = self.base_seed  # BucketedDataParallel folds the rank in
@@ -154,6 +155,7 @@ class EncoderRuntime:
             lib().wm_encoder_destroy(h)
         self._handles.clear()
         self._shadow_version = None
+        self._shadow_fresh_ver = None
 
     def __del__(self):
         try:
@@ -161,8 +163,19 @@ class EncoderRuntime:
         except Exception:
             pass
 
-    def mark_weights_dirty(self):
+    def mark_weights_dirty(self, shadow_written: bool = False):
+        """The fp32 parameters changed behind torch's back. shadow_written: the caller (FusedAdam) also wrote the bf16
+        shadow through shadow_ptr(), so the next refresh only has to rebuild the transposed copies -- valid as long as
+        nobody else touches the parameters in between (their version counters are remembered)."""
         self._shadow_version = None
+        self._shadow_fresh_ver = sum(p._version for _, p in self._named) if shadow_written else None
+
+    def shadow_ptr(self) -> Optional[int]:
+        """Device address of the bf16 parameter shadow (None before the first handle exists). All handles carve the same
+        workspace prefix, so any of them answers."""
+        for h in self._handles.values():
+            return lib().wm_encoder_shadow(h)
+        return None
 
     def _refresh_if_needed(self, handle: int):
         # all handles carve the same workspace, so the bf16 shadows written through one are valid for
@@ -171,9 +184,14 @@ class EncoderRuntime:
         # kernel writes behind torch's back and calls mark_weights_dirty() instead
         ver = sum(p._version for _, p in self._named)
         if self._shadow_version != ver:
-            check(lib().wm_encoder_refresh_weights(handle, self.flat_params.data_ptr(), ops._stream()),
-                  "wm_encoder_refresh_weights")
+            if getattr(self, "_shadow_fresh_ver", None) == ver:  # the optimiser wrote the bf16 shadow itself
+                check(lib().wm_encoder_refresh_transposes(handle, self.flat_params.data_ptr(), ops._stream()),
+                      "wm_encoder_refresh_transposes")
+            else:
+                check(lib().wm_encoder_refresh_weights(handle, self.flat_params.data_ptr(), ops._stream()),
+                      "wm_encoder_refresh_weights")
             self._shadow_version = ver
+            self._shadow_fresh_ver = None
 
     # ------------------------------------------------------------------ forward / backward
     def forward(self, weather, coords, year, mask, training: bool, save_for_backward: bool = True) -> torch.Tensor:

@@ -78,8 +78,10 @@ class CapturedTrainStep:
         self._dev_hyper = self._dev_words.view(torch.float32)[3:6]
         self.keys: Optional[List[str]] = None
         self.static_out: Optional[torch.Tensor] = None
-        if rt._shadow_version is not None:
-            rt.mark_weights_dirty()  # the recorded step must contain the weight refresh: every replay follows an update
+        # the recorded step must contain the FULL weight refresh (bf16 cast + transposes): every replay follows an update, and
+        # a parameter change from outside between replays (load_state_dict, ...) must not meet a stale shadow
+        rt._shadow_version = None
+        rt._shadow_fresh_ver = None
         self._load(example_batch)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
@@ -106,7 +108,7 @@ class CapturedTrainStep:
         self.kernels_per_replay = int(ops.lib().wm_launch_count() - launches0)  # libwm_b200 kernels inside one replay
         # the recording executes nothing: this replay IS the training step on example_batch
         self.graph.replay()
-        self.rt.mark_weights_dirty()
+        self.rt.mark_weights_dirty(shadow_written=self.rt.shadow_ptr() is not None)
         self.first_losses = {k: self.static_out[i] for i, k in enumerate(self.keys)}
 
     # ------------------------------------------------------------------ pieces
@@ -164,5 +166,6 @@ class CapturedTrainStep:
         self._load(batch)
         self._advance_host_state()
         self.graph.replay()
-        self.rt.mark_weights_dirty()  # Adam ran at the end of the replay: eager forwards (validation) must refresh
+        # Adam ran at the end of the replay (and wrote the bf16 shadow): eager forwards (validation) must rebuild the transposes
+        self.rt.mark_weights_dirty(shadow_written=self.rt.shadow_ptr() is not None)
         return {k: self.static_out[i] for i, k in enumerate(self.keys)}

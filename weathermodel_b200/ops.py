@@ -472,8 +472,9 @@ def yield_head_bwd(dpred, y_pad, mask, eps, z, y_past, params, is_former: bool):
 
 def adam_fused(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
                shadow=None, grad_scale=1.0):
-    _cuda(param, grad, exp_avg, exp_avg_sq, shadow)
-    check(lib().wm_adam_fused(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(shadow), param.numel(), float(lr),
+    """shadow: optional bf16 tensor (or raw device address) that receives the updated parameters in bf16."""
+    _cuda(param, grad, exp_avg, exp_avg_sq, None if isinstance(shadow, int) else shadow)
+    check(lib().wm_adam_fused(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), shadow if isinstance(shadow, int) else _p(shadow), param.numel(), float(lr),
                               float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
                               float(grad_scale), _stream()), "wm_adam_fused")
 
@@ -481,8 +482,8 @@ def adam_fused(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.99
 def adam_fused_dev(param, grad, exp_avg, exp_avg_sq, hyper_dev, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
                    shadow=None, grad_scale=1.0):
     """adam_fused with {lr, 1 - beta1^t, sqrt(1 - beta2^t)} read from the device tensor `hyper_dev` (captured steps)."""
-    _cuda(param, grad, exp_avg, exp_avg_sq, shadow, hyper_dev)
-    check(lib().wm_adam_fused_dev(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(shadow), param.numel(), _p(hyper_dev),
+    _cuda(param, grad, exp_avg, exp_avg_sq, None if isinstance(shadow, int) else shadow, hyper_dev)
+    check(lib().wm_adam_fused_dev(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), shadow if isinstance(shadow, int) else _p(shadow), param.numel(), _p(hyper_dev),
                                   float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale), _stream()),
           "wm_adam_fused_dev")
 

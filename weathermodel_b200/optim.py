@@ -89,16 +89,17 @@ class FusedAdam(torch.optim.Optimizer):
                 raise RuntimeError("FusedAdam: record a step only after an eager step has bound the optimiser state")
             if all(p.grad is not None and p.grad.data_ptr() == rt.grad_view(i).data_ptr()
                    for i, p in enumerate(in_flat)) and self._bind_flat_state():
+                shadow = rt.shadow_ptr()  # the kernel also writes the bf16 copy the GEMMs read (no separate cast pass)
                 with torch.cuda.device(rt.flat_params.device):
                     if self._captured_hyper is not None:
                         ops.adam_fused_dev(rt.flat_params, rt.flat_grads, self._flat_m, self._flat_v, self._captured_hyper,
-                                           b1, b2, eps, wd)
+                                           b1, b2, eps, wd, shadow=shadow)
                     else:
                         self._step += 1
                         ops.adam_fused(rt.flat_params, rt.flat_grads, self._flat_m, self._flat_v, self._step, lr, b1, b2,
-                                       eps, wd)
+                                       eps, wd, shadow=shadow)
                         self._step_t.fill_(float(self._step))  # one host tensor shared by every flat parameter's state
-                rt.mark_weights_dirty()
+                rt.mark_weights_dirty(shadow_written=shadow is not None)
                 flat_ids = {id(p) for p in in_flat}
         for p in group["params"]:
             if id(p) in flat_ids or p.grad is None:
