@@ -16,12 +16,13 @@ from weathermodel_b200.pretraining.models.weatherformer import WeatherFormer  # 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--size", default="large", choices=["mini", "small", "medium", "large"])
     a = ap.parse_args()
     dev = torch.device("cuda:0")
-    B, S, F = a.batch, 365, 31
+    B, S, F = a.batch or {"mini": 64, "small": 128, "medium": 256, "large": 512}[a.size], 365, 31
     torch.manual_seed(1234)
-    model = WeatherFormer(weather_dim=F, output_dim=F, device=dev, **bench.size_params("large")).to(dev).train()
+    model = WeatherFormer(weather_dim=F, output_dim=F, device=dev, **bench.size_params(a.size)).to(dev).train()
     opt = FusedAdam(model.parameters(), lr=5e-4, runtime=model.runtime)
     w = torch.randn(B, S, F, device=dev)
     c = torch.rand(B, 2, device=dev)

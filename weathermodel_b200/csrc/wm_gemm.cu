@@ -849,8 +849,10 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t b_bytes = static_cast<uint32_t>(BN) * kBK * 2;       // BN/64 boxes
   // Fused bias gradient (column sums of A over the tokens): an all-ones 64 x 64 chunk sits right behind the B
   // tile of every stage, so the k_blk == 0 CTAs simply run their MMAs 16 columns wider (N = BN + 16) and find
-  // sum_t A[t, n] in accumulator column BN -- no separate pass over the activation gradient.
+  // sum_t A[t, n] in accumulator column BN -- no separate pass over the activation gradient. With BN = 256 (the
+  // instruction's widest N) the ones chunk gets its own N = 16 MMA per k-step into columns [256, 272) instead.
   const bool fuse_bias = bias_partial != nullptr;
+  const bool wide_bias = fuse_bias && BN == 256;
   const uint32_t ones_bytes = fuse_bias ? 8192u : 0u;
   const uint32_t stage_bytes = a_bytes + b_bytes + ones_bytes;
   WgSmemTail* tail = reinterpret_cast<WgSmemTail*>(smem + static_cast<size_t>(kWgStages) * stage_bytes);
@@ -874,7 +876,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_init(&tail->acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<256>(&tail->tmem_base);
+  if (warp == 1) tmem_alloc<512>(&tail->tmem_base);
   if (fuse_bias && k_blk == 0) {
     const uint4 ones = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);  // bf16 1.0 x 8
     for (int i = threadIdx.x; i < kWgStages * 512; i += blockDim.x)
@@ -906,7 +908,9 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // MMA issue, whole warp convergent (see gemm_tn_kernel)
-    const uint32_t idesc = umma_idesc_bf16(kBM, static_cast<uint32_t>(BN + (fuse_bias && k_blk == 0 ? 16 : 0)), 1, 1);
+    const bool ones = fuse_bias && k_blk == 0;
+    const uint32_t idesc = umma_idesc_bf16(kBM, static_cast<uint32_t>(BN + (ones && !wide_bias ? 16 : 0)), 1, 1);
+    const uint32_t idesc_ones = umma_idesc_bf16(kBM, 16, 1, 1);
     // MN-major SW128: 64-wide MN chunks LBO = 8192 B apart, 8-token groups SBO = 1024 B apart
     const uint64_t desc_a0 = umma_smem_desc(smem_u32(smem), 8192, 1024, UMMA_SWZ_128B);
     int s = 0;
@@ -917,9 +921,13 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint64_t da_s = umma_desc_advance(desc_a0, static_cast<uint32_t>(s) * stage_bytes);
       const uint64_t db_s = umma_desc_advance(da_s, a_bytes);
 #pragma unroll
-      for (int k = 0; k < kBK / 16; ++k)
+      for (int k = 0; k < kBK / 16; ++k) {
         umma_ss_warp(tmem_base, umma_desc_advance(da_s, k * 2048), umma_desc_advance(db_s, k * 2048), idesc,
                      (kb | k) != 0 ? 1u : 0u);
+        if (ones && wide_bias)  // (warp-uniform) the all-ones chunk as a second, 16-column product
+          umma_ss_warp(tmem_base + 256, umma_desc_advance(da_s, k * 2048), umma_desc_advance(db_s, b_bytes + k * 2048), idesc_ones,
+                       (kb | k) != 0 ? 1u : 0u);
+      }
       umma_commit_warp(&tail->empty[s]);
       if (++s == kWgStages) { s = 0; ph ^= 1u; }
     }
@@ -982,7 +990,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -1037,11 +1045,21 @@ __global__ void wgrad_reduce4_kernel(const float4* __restrict__ partial, float4*
 // waves of SMs (the first plan used ceil(2 * SMs / tiles) and lost up to a third of the machine to a nearly empty
 // last wave: 300 items on 148 SMs = 3 waves at 68 %), with a mild preference for fewer partial tiles to reduce.
 int wgrad_plan(int Mtok, int Nout, int Kout, int* BN, int* splits, int* tok_per_split) {
-  int bn;
-  if (Kout <= 64) bn = 64;
-  else if (Kout <= 128) bn = 128;
-  else if (Kout % 192 == 0 || (Kout > 128 && Kout <= 192)) bn = 192;
-  else bn = 256;
+  // tile width over Kout (64-column TMA boxes): 192 where it divides Kout (the D = 576 shapes were tuned on it), otherwise
+  // the width that minimises tiles x (width + ~32 columns of per-tile overhead), the wider one on a tie
+  int bn = 64;
+  if (Kout % 192 == 0) {
+    bn = 192;
+  } else {
+    long best = -1;
+    for (int cand = 64; cand <= 256; cand += 64) {
+      const long cost = static_cast<long>((Kout + cand - 1) / cand) * (cand + 32);
+      if (best < 0 || cost <= best) {
+        best = cost;
+        bn = cand;
+      }
+    }
+  }
   const int tiles = ((Nout + kBM - 1) / kBM) * ((Kout + bn - 1) / bn);
   const int kb_total = (Mtok + kBK - 1) / kBK;
   const int sms = num_sms();
@@ -1073,7 +1091,8 @@ int wgrad_plan(int Mtok, int Nout, int Kout, int* BN, int* splits, int* tok_per_
 bool wgrad_fuses_bias(int Mtok, int Nout, int Kout) {
   int bn, sp, tps;
   wgrad_plan(Mtok, Nout, Kout, &bn, &sp, &tps);
-  return bn + 16 <= 256;
+  (void)bn;
+  return true;  // every tile width fuses it now (256-wide tiles through a second, 16-column MMA)
 }
 
 size_t wgrad_workspace_bytes(int Mtok, int Nout, int Kout) {
@@ -1098,7 +1117,7 @@ static int launch_gemm_wgrad_impl(const void* A, int lda, const void* B, int ldb
   if (rc) return rc;
   rc = make_tmap_bf16(&tmB, B, Mtok, Kout, ldb, 64, kBK);
   if (rc) return rc;
-  const bool fuse = dbias != nullptr && BN + 16 <= 256;
+  const bool fuse = dbias != nullptr;
   float* bias_partial = fuse ? workspace + static_cast<size_t>(splits) * Nout * Kout : nullptr;
   const int stage_bytes = (kBM + BN) * kBK * 2 + (fuse ? 8192 : 0);
   const int smem = kWgStages * stage_bytes + static_cast<int>(sizeof(WgSmemTail)) + 1024;
