@@ -116,6 +116,7 @@ struct GemmSmemTail {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
+  uint64_t res_full[16];           // per epilogue warp: the residual box of the current tile has landed (TMA-store epilogue)
   alignas(16) float bias[1024];    // per epilogue warp (kEW x 1024 / kEW floats): the bias slice of its columns of the current tile
 };
 
@@ -160,7 +161,8 @@ int g_gemm_diag = 0;  // copied into GemmEpilogue::diag by the launcher
 
 template <typename OutT>
 WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const float* sbias, const GemmEpilogue& ep,
-                             const DropKeys& dk, int row, int n0, int M, int N, bool wide, uint8_t* sdst, int swz_chunk = -1) {
+                             const DropKeys& dk, int row, int n0, int M, int N, bool wide, uint8_t* sdst, int swz_chunk = -1,
+                             bool res_in_box = false) {
   // sdst (bf16 outputs only): this lane's 32 bytes of the chunk inside the warp's shared-memory staging tile; the
   // tile leaves through coalesced stores once all chunks are in (gemm_epilogue_tile). nullptr: direct stores.
   // swz_chunk >= 0: sdst is the lane's 128-byte ROW of a 32 x 64 SWIZZLE_128B box (TMA-store epilogue) and the two
@@ -220,7 +222,11 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
   }
   if (ep.residual) {
     uint4 r0 = aux.a[0], r1 = aux.a[1];
-    if (ep.gate) {  // both operands given (not on the training schedule): the residual is loaded in place
+    if (res_in_box) {  // the residual tile was TMA-loaded into this warp's output box: same swizzled positions as the output
+      const uint32_t r7 = static_cast<uint32_t>(threadIdx.x) & 7u;
+      r0 = *reinterpret_cast<const uint4*>(sdst + ((static_cast<uint32_t>(swz_chunk) ^ r7) << 4));
+      r1 = *reinterpret_cast<const uint4*>(sdst + ((static_cast<uint32_t>(swz_chunk + 1) ^ r7) << 4));
+    } else if (ep.gate) {  // both operands given (not on the training schedule): the residual is loaded in place
       const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(row) * ep.ld_res + n0);
       r0 = row < M ? __ldg(rp) : make_uint4(0u, 0u, 0u, 0u);
       r1 = (row < M && n0 + 8 < N) ? __ldg(rp + 1) : make_uint4(0u, 0u, 0u, 0u);
@@ -305,7 +311,10 @@ template <typename OutT, int kAuxDepth>
 WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t* acc_full, uint32_t aph,
                                   uint32_t wait_code, uint32_t tbase, int row, int n_base, int cols_per, int M, int N,
                                   bool wide, int lane, uint8_t* stage, uint64_t* acc_empty, uint32_t acc_empty_cluster,
-                                  const CUtensorMap* tmC = nullptr) {
+                                  const CUtensorMap* tmC = nullptr, const CUtensorMap* tmR = nullptr,
+                                  uint64_t* res_full = nullptr, uint32_t* res_count = nullptr) {
+  // tmR != nullptr (with tmC): the residual operand arrives by TMA, too -- one box load per warp and tile into the output
+  // box itself (read-modify-write in place) instead of 32 row-strided 32-byte loads per lane and chunk.
   // tmC != nullptr (staged == 2, cols_per == 64): TMA-store epilogue. `stage` is this warp's 1024-byte aligned 4 KB
   // box (32 rows x 64 bf16, SWIZZLE_128B); the lanes write their packed rows straight from the tcgen05.ld registers,
   // one elected lane hands the box to cp.async.bulk.tensor (rows >= M / columns >= N are clipped by the tensor map)
@@ -328,15 +337,29 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
   // residual / gate rows in flight per SM
   static_assert(kAuxDepth == 2 || kAuxDepth == 4, "the TMEM double buffer alternates on the chunk parity");
   EpiAux aux[kAuxDepth];
+  const bool res_box = tmR != nullptr;
 #pragma unroll
-  for (int d = 0; d < kAuxDepth; ++d)
-    if (d * 16 < cols_per) epi_load_aux(aux[d], ep, row, n_base + d * 16, M, N, wide);
+  for (int d = 0; d < kAuxDepth; ++d) {
+    if (res_box) { aux[d].a[0] = aux[d].a[1] = make_uint4(0u, 0u, 0u, 0u); aux[d].bits = 0u; }
+    else if (d * 16 < cols_per) epi_load_aux(aux[d], ep, row, n_base + d * 16, M, N, wide);
+  }
   if (tmC) {  // the previous tile's box must have been read by the TMA engine before it is overwritten
-    if (lane == 0) bulk_wait_group_read<0>();
+    if (lane == 0) {
+      bulk_wait_group_read<0>();
+      if (res_box && n_base < N && row < M) {  // (lane 0's row is the first row of the box; skipped boxes are never waited for)
+        mbar_arrive_expect_tx(res_full, 4096u);
+        tma_load_2d(stage, tmR, res_full, n_base, row);
+      }
+    }
     __syncwarp();
   }
   mbar_wait(acc_full, aph, wait_code);
   tc_fence_after();
+  const bool box_live = res_box && n_base < N && (row - lane) < M;
+  if (box_live) {  // (warp-uniform) one completion of this warp's barrier per box actually loaded
+    mbar_wait(res_full, *res_count & 1u, wait_code + 100);
+    ++*res_count;
+  }
   uint32_t va[16], vb[16];
   tmem_ld16(tbase, va);
   for (int cb = 0; cb < cols_per; cb += 16 * kAuxDepth) {
@@ -350,16 +373,16 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
         tmem_ld_wait();
         if (d & 1) {
           if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, va);
-          if (tmC) epi_process16<OutT>(vb, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3);
+          if (tmC) epi_process16<OutT>(vb, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3, box_live);
           else epi_process16<OutT>(vb, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide,
                                    stage ? stage + lane * pitch + c0 * 2 : nullptr);
         } else {
           if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, vb);
-          if (tmC) epi_process16<OutT>(va, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3);
+          if (tmC) epi_process16<OutT>(va, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3, box_live);
           else epi_process16<OutT>(va, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide,
                                    stage ? stage + lane * pitch + c0 * 2 : nullptr);
         }
-        if (c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
+        if (!res_box && c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
       }
     }
   }
@@ -409,8 +432,8 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
 template <typename OutT, int kEW>
 __global__ void __launch_bounds__(gemm_threads(kEW), 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int BN, int stages, int staged,
-               GemmEpilogue ep) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int M, int N, int K, int BN,
+               int stages, int staged, int res_tma, GemmEpilogue ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024B-align the tile ring (SWIZZLE_128B atoms)
   uint8_t* smem = smem_align_up(smem_raw, 1024);
@@ -434,6 +457,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (staged == 2) tma_prefetch_desc(&tmC);
+    if (res_tma) tma_prefetch_desc(&tmR);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&tail->full[s], 1);
       mbar_init(&tail->empty[s], 1);
@@ -442,6 +466,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tail->acc_full[s], 1);
       mbar_init(&tail->acc_empty[s], kEW);  // one arrive per epilogue warp
     }
+    for (int s = 0; s < 16; ++s) mbar_init(&tail->res_full[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(&tail->tmem_base);
@@ -507,6 +532,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                       ((reinterpret_cast<uintptr_t>(ep.out) | reinterpret_cast<uintptr_t>(ep.residual) |
                         reinterpret_cast<uintptr_t>(ep.gate)) & 31) == 0;
     int it = 0;
+    uint32_t res_count = 0u;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int m_blk = t / n_tiles, n_blk = t % n_tiles;
       const int as = it & 1;
@@ -515,7 +541,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       gemm_epilogue_tile<OutT, (kEW == 16 ? 2 : 4)>(ep, sbias, &tail->acc_full[as], aph, 14, tbase, m_blk * kBM + q * 32 + lane,
                                n_blk * BN + half * cols_per, cols_per, M, N, wide, lane,
                                staged ? epi_stage + static_cast<uint32_t>(ew) * epi_stage_warp : nullptr,
-                               &tail->acc_empty[as], 0u, staged == 2 ? &tmC : nullptr);
+                               &tail->acc_empty[as], 0u, staged == 2 ? &tmC : nullptr, (staged == 2 && res_tma) ? &tmR : nullptr,
+                               &tail->res_full[ew], &res_count);
     }
     if (staged == 2 && lane == 0) bulk_wait_group_read<0>();  // the last box must be read before the CTA's smem goes away
   }
@@ -536,8 +563,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <typename OutT, int kEW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(kEW), 1)
 gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int BN, int stages, int staged,
-                GemmEpilogue ep) {
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int M, int N, int K, int BN,
+                int stages, int staged, int res_tma, GemmEpilogue ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_align_up(smem_raw, 1024);
   const int BNH = BN >> 1;  // B rows staged by each CTA
@@ -570,6 +597,8 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(&tail->acc_full[s], 1);
       mbar_init(&tail->acc_empty[s], 2 * kEW);  // the epilogue warps of both CTAs (the leader's copy is used)
     }
+    if (res_tma) tma_prefetch_desc(&tmR);
+    for (int s = 0; s < 16; ++s) mbar_init(&tail->res_full[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2cta<kTmemCols>(&tail->tmem_base);
@@ -633,6 +662,7 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         reinterpret_cast<uintptr_t>(ep.gate)) & 31) == 0;
     const uint32_t acc_empty_leader[2] = {mapa_u32(&tail->acc_empty[0], 0), mapa_u32(&tail->acc_empty[1], 0)};
     int it = 0;
+    uint32_t res_count = 0u;
     for (int t = pair; t < total_tiles; t += npairs, ++it) {
       const int m_blk = t / n_tiles, n_blk = t % n_tiles;
       const int as = it & 1;
@@ -642,7 +672,8 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                m_blk * 2 * kBM + static_cast<int>(rank) * kBM + q * 32 + lane,
                                n_blk * BN + half * cols_per, cols_per, M, N, wide, lane,
                                staged ? epi_stage + static_cast<uint32_t>(ew) * epi_stage_warp : nullptr,
-                               nullptr, acc_empty_leader[as], staged == 2 ? &tmC : nullptr);
+                               nullptr, acc_empty_leader[as], staged == 2 ? &tmC : nullptr, (staged == 2 && res_tma) ? &tmR : nullptr,
+                               &tail->res_full[ew], &res_count);
     }
     if (staged == 2 && lane == 0) bulk_wait_group_read<0>();
   }
@@ -772,9 +803,16 @@ static int launch_gemm_tn_impl(const void* A, int lda, const void* B, int ldb, i
   const int staging = tma_out ? ew * 4096 : ew * 32 * (BN / (ew / 4) * 2 + 16);
   const bool can_stage = want_staged && aligned_out;
   CUtensorMap tmC = tmA;  // (unused unless tma_out; a valid map keeps the __grid_constant__ copy well-defined)
+  CUtensorMap tmR = tmA;
+  // the residual rides the same boxes when it is a plain 16-byte aligned bf16 matrix (no gate operand in the way)
+  const bool res_tma = tma_out && ep.residual && !ep.gate && !ep.gate_bits && (ep.ld_res & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0;
   if (tma_out) {
     rc = make_tmap_bf16(&tmC, ep.out, M, N, ep.ld_out, 64, 32);
     if (rc) return rc;
+    if (res_tma) {
+      rc = make_tmap_bf16(&tmR, ep.residual, M, N, ep.ld_res, 64, 32);
+      if (rc) return rc;
+    }
   }
   if (want_two && !out_fp32 && M >= 1024 && (BN & 31) == 0 && bn_override >= 0) {
     // CTA-pair path: 256 x BN tiles, each CTA stages 128 rows of A and BN/2 rows of B per k-block
@@ -790,7 +828,7 @@ static int launch_gemm_tn_impl(const void* A, int lda, const void* B, int ldb, i
     if (!tma_out || staged2 == 2) {
       auto kern2 = ew == 16 ? gemm_tn2_kernel<__nv_bfloat16, 16> : ew == 12 ? gemm_tn2_kernel<__nv_bfloat16, 12> : gemm_tn2_kernel<__nv_bfloat16, 8>;
       if (cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2) != cudaSuccess) return WM_ERR_CUDA;
-      kern2<<<2 * pairs, threads, smem2, stream>>>(tmA, tmB, tmC, M, N, K, BN, st2, staged2, ep);
+      kern2<<<2 * pairs, threads, smem2, stream>>>(tmA, tmB, tmC, tmR, M, N, K, BN, st2, staged2, (staged2 == 2 && res_tma) ? 1 : 0, ep);
       WM_COUNT_LAUNCH();
       return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
     }
@@ -809,7 +847,7 @@ static int launch_gemm_tn_impl(const void* A, int lda, const void* B, int ldb, i
                        : (ew == 16 ? gemm_tn_kernel<__nv_bfloat16, 16>
                                    : ew == 12 ? gemm_tn_kernel<__nv_bfloat16, 12> : gemm_tn_kernel<__nv_bfloat16, 8>);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
-  kern<<<grid, threads, smem, stream>>>(tmA, tmB, tmC, M, N, K, BN, stages, staged1, ep);
+  kern<<<grid, threads, smem, stream>>>(tmA, tmB, tmC, tmR, M, N, K, BN, stages, staged1, (staged1 == 2 && res_tma) ? 1 : 0, ep);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
