@@ -332,28 +332,71 @@ WM_DEVICE void ln_unpack(const uint4 (&r)[kLnMaxChunks], float (&v)[kLnMaxChunks
   }
 }
 
+// Chunk width: a lane owns kW consecutive elements per pass. At D = 576 the 72 eight-element chunks need three passes of
+// which the last keeps 8 of 32 lanes busy (24 element slots per lane for 18 elements); 144 four-element chunks need
+// five passes = 20 slots: 17 % fewer issued instructions in kernels that are issue-bound (profiles/r01_ln_bwd_full.txt).
+template <int kW> struct LnVec;
+template <> struct LnVec<8> { using T = uint4; };
+template <> struct LnVec<4> { using T = uint2; };
+template <int kW>
+WM_DEVICE void ln_unpack_w(const typename LnVec<kW>::T& r, float (&v)[kW]) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
+#pragma unroll
+  for (int j = 0; j < kW / 2; ++j) {
+    v[2 * j] = bf16_lo(w[j]);
+    v[2 * j + 1] = bf16_hi(w[j]);
+  }
+}
+template <int kW>
+WM_DEVICE typename LnVec<kW>::T ln_pack_w(const float (&o)[kW]) {
+  typename LnVec<kW>::T pk;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+  for (int j = 0; j < kW / 2; ++j) w[j] = pack_bf16x2(o[2 * j], o[2 * j + 1]);
+  return pk;
+}
+// passes that hold an element of a row of D elements, and the chunk width that needs fewer element slots per lane
+static inline int ln_slots(int D, int w) { return ((D / w + 31) / 32) * w; }
+int g_ln_bwd_width = 0;  // 0 = default (8), 4 or 8 forced -- wm_set_option("ln_bwd_width", v)
+int g_ln_fwd_width = 0;  // 0 = auto (ln_pick_width), 4 or 8 forced -- wm_set_option("ln_fwd_width", v)
+static inline int ln_pick_width(int D) { return ln_slots(D, 4) < ln_slots(D, 8) ? 4 : 8; }
+
+template <int kW>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int M, int D, float eps) {
+  using Vec = typename LnVec<kW>::T;
+  constexpr int kIt = (kLnMaxChunks * 8) / kW;  // passes for the widest supported row
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  const int nchunks = D >> 3;
-  float v[kLnMaxChunks][8];
-  ln_load_row(x + static_cast<size_t>(row) * D, nchunks, lane, v);
+  const int nchunks = D / kW;
+  float v[kIt][kW];
+  const Vec* xr = reinterpret_cast<const Vec*>(x + static_cast<size_t>(row) * D);
+#pragma unroll
+  for (int i = 0; i < kIt; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+      const Vec r = __ldg(xr + c);
+      ln_unpack_w<kW>(r, v[i]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kW; ++j) v[i][j] = 0.0f;
+    }
+  }
   float s = 0.0f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxChunks; ++i)
+  for (int i = 0; i < kIt; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[i][j];
+    for (int j = 0; j < kW; ++j) s += v[i][j];
   const float mean = warp_sum(s) / static_cast<float>(D);
   float q = 0.0f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxChunks; ++i) {
+  for (int i = 0; i < kIt; ++i) {
     if (lane + 32 * i < nchunks) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < kW; ++j) {
         const float d = v[i][j] - mean;
         q = fmaf(d, d, q);
       }
@@ -365,24 +408,20 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
     if (rstd_out) rstd_out[row] = rstd;
   }
 #pragma unroll
-  for (int i = 0; i < kLnMaxChunks; ++i) {
+  for (int i = 0; i < kIt; ++i) {
     const int c = lane + 32 * i;
     if (c < nchunks) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c);
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c);
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + 1);
-      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o[8];
+      float g[kW], b[kW], o[kW];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, g[j], b[j]);
-      uint4 pk;
-      pk.x = pack_bf16x2(o[0], o[1]);
-      pk.y = pack_bf16x2(o[2], o[3]);
-      pk.z = pack_bf16x2(o[4], o[5]);
-      pk.w = pack_bf16x2(o[6], o[7]);
-      reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * D)[c] = pk;
+      for (int j4 = 0; j4 < kW / 4; ++j4) {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + c * kW) + j4);
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(beta + c * kW) + j4);
+        g[4 * j4] = gv.x; g[4 * j4 + 1] = gv.y; g[4 * j4 + 2] = gv.z; g[4 * j4 + 3] = gv.w;
+        b[4 * j4] = bv.x; b[4 * j4 + 1] = bv.y; b[4 * j4 + 2] = bv.z; b[4 * j4 + 3] = bv.w;
+      }
+#pragma unroll
+      for (int j = 0; j < kW; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, g[j], b[j]);
+      reinterpret_cast<Vec*>(y + static_cast<size_t>(row) * D)[c] = ln_pack_w<kW>(o);
     }
   }
 }
@@ -390,7 +429,8 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
 int launch_layernorm_fwd(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y,
                          float* mean, float* rstd, int M, int D, float eps, cudaStream_t stream) {
   if (M <= 0 || D <= 0 || (D & 7) || D > kLnMaxChunks * 256) return WM_ERR_SHAPE;
-  layernorm_fwd_kernel<<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, mean, rstd, M, D, eps);
+  if ((g_ln_fwd_width ? g_ln_fwd_width : ln_pick_width(D)) == 4) layernorm_fwd_kernel<4><<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, mean, rstd, M, D, eps);
+  else layernorm_fwd_kernel<8><<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, mean, rstd, M, D, eps);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
@@ -408,7 +448,7 @@ constexpr int kLnBwdMaxStages = 8;
 // kBias: also accumulate the bias gradient of the producing linear (column sums of the bf16-rounded dx / dx_drop).
 // The encoder takes that gradient from the wgrad GEMM instead (its fused all-ones chunk), which frees 24 registers
 // per thread: 15 consumer warps (rows per block) fit instead of 8 -- the kernel is issue/latency-bound, so warps count.
-template <bool kBias, int kRows>
+template <bool kBias, int kRows, int kW>
 __global__ void __launch_bounds__(32 * (kRows + 1), 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean,
@@ -426,7 +466,9 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   uint64_t* full = reinterpret_cast<uint64_t*>(sred + kRows * kSums * D);
   uint64_t* empty = full + stages;
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
-  const int nchunks = D >> 3;
+  using Vec = typename LnVec<kW>::T;
+  constexpr int kIt = (kLnMaxChunks * 8) / kW;  // lane passes for the widest supported row
+  const int nchunks = D / kW;
   const int nblk = (M + kRows - 1) / kRows;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -453,15 +495,16 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       }
     }
   } else {
-    float g[kLnMaxChunks][8];
-    float ag[kLnMaxChunks][8], ab[kLnMaxChunks][8], ad[kLnMaxChunks][8];
+    float g[kIt][kW];
+    float ag[kIt][kW], ab[kIt][kW], ad[kBias ? kIt : 1][kW];
 #pragma unroll
-    for (int i = 0; i < kLnMaxChunks; ++i) {
+    for (int i = 0; i < kIt; ++i) {
       const int c = lane + 32 * i;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        g[i][j] = c < nchunks ? gamma[c * 8 + j] : 0.0f;
-        ag[i][j] = 0.0f; ab[i][j] = 0.0f; ad[i][j] = 0.0f;
+      for (int j = 0; j < kW; ++j) {
+        g[i][j] = c < nchunks ? gamma[c * kW + j] : 0.0f;
+        ag[i][j] = 0.0f; ab[i][j] = 0.0f;
+        if constexpr (kBias) ad[i][j] = 0.0f;
       }
     }
     const float invD = 1.0f / static_cast<float>(D);
@@ -480,20 +523,23 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         if (rn < M) { mu_n = __ldg(mean + rn); rs_n = __ldg(rstd + rn); }
       }
       mbar_wait(&full[s], ph, 42);
-      float xv[kLnMaxChunks][8], dv[kLnMaxChunks][8];
+      float xv[kIt][kW], dv[kIt][kW];
       {
-        const uint4* sx = reinterpret_cast<const uint4*>(ring + static_cast<size_t>(s) * stage_bytes + warp * row_bytes);
-        const uint4* sd = reinterpret_cast<const uint4*>(ring + static_cast<size_t>(s) * stage_bytes + tens_bytes + warp * row_bytes);
-        uint4 xr[kLnMaxChunks], dr[kLnMaxChunks];
+        const Vec* sx = reinterpret_cast<const Vec*>(ring + static_cast<size_t>(s) * stage_bytes + warp * row_bytes);
+        const Vec* sd = reinterpret_cast<const Vec*>(ring + static_cast<size_t>(s) * stage_bytes + tens_bytes + warp * row_bytes);
+        Vec xr[kIt], dr[kIt];
 #pragma unroll
-        for (int i = 0; i < kLnMaxChunks; ++i) {
+        for (int i = 0; i < kIt; ++i) {
           const int c = lane + 32 * i;
           const bool ok = c < nchunks && row < M;
-          xr[i] = ok ? sx[c] : make_uint4(0u, 0u, 0u, 0u);
-          dr[i] = ok ? sd[c] : make_uint4(0u, 0u, 0u, 0u);
+          if (ok) { xr[i] = sx[c]; dr[i] = sd[c]; }
+          else { xr[i] = Vec{}; dr[i] = Vec{}; }
         }
-        ln_unpack(xr, xv);
-        ln_unpack(dr, dv);
+#pragma unroll
+        for (int i = 0; i < kIt; ++i) {
+          ln_unpack_w<kW>(xr[i], xv[i]);
+          ln_unpack_w<kW>(dr[i], dv[i]);
+        }
       }
       __syncwarp();  // every lane has its copy: hand the slot back to the producer
       if (lane == 0) mbar_arrive(&empty[s]);
@@ -501,10 +547,10 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       if (row >= M) continue;  // warp-uniform (tail block)
       float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
-      for (int i = 0; i < kLnMaxChunks; ++i) {
+      for (int i = 0; i < kIt; ++i) {
         if (lane + 32 * i < nchunks) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < kW; ++j) {
             const float xh = (xv[i][j] - mu) * rs;
             const float gd = dv[i][j] * g[i][j];
             s1 += gd;
@@ -518,37 +564,36 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       s1 = warp_sum(s1) * invD;
       s2 = warp_sum(s2) * invD;
 #pragma unroll
-      for (int i = 0; i < kLnMaxChunks; ++i) {
+      for (int i = 0; i < kIt; ++i) {
         const int c = lane + 32 * i;
         if (c < nchunks) {
-          float o[8];
+          float o[kW];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = rs * (dv[i][j] * g[i][j] - s1 - xv[i][j] * s2);
-          uint4 pk;
-          pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
-          pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
-          reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * D)[c] = pk;
-          if (drop_thresh) {  // the mask the GEMM epilogue drew for these 8 columns: two words of the 16-column group
+          for (int j = 0; j < kW; ++j) o[j] = rs * (dv[i][j] * g[i][j] - s1 - xv[i][j] * s2);
+          Vec pk = ln_pack_w<kW>(o);
+          reinterpret_cast<Vec*>(dx + static_cast<size_t>(row) * D)[c] = pk;
+          if (drop_thresh) {  // the mask the GEMM epilogue drew for these columns: counter = (row, 16-column group, 4-element word)
             const uint32_t add2 = drop_add2(drop_thresh);
-            const uint32_t x0 = (static_cast<uint32_t>(row) * static_cast<uint32_t>((D + 15) >> 4) + static_cast<uint32_t>(c >> 1)) * 4u + 2u * (c & 1);
+            const int col = c * kW;
+            const uint32_t x0 = (static_cast<uint32_t>(row) * static_cast<uint32_t>((D + 15) >> 4) + static_cast<uint32_t>(col >> 4)) * 4u +
+                                static_cast<uint32_t>((col & 15) >> 2);
 #pragma unroll
-            for (int w = 0; w < 2; ++w) {
+            for (int w = 0; w < kW / 4; ++w) {
               const DropWords fl = drop_flags4(x0 + w, dkeys, add2);
               o[4 * w] = __uint_as_float(__float_as_uint(o[4 * w] * drop_scale) & drop_mask32<0>(fl));
               o[4 * w + 1] = __uint_as_float(__float_as_uint(o[4 * w + 1] * drop_scale) & drop_mask32<1>(fl));
               o[4 * w + 2] = __uint_as_float(__float_as_uint(o[4 * w + 2] * drop_scale) & drop_mask32<2>(fl));
               o[4 * w + 3] = __uint_as_float(__float_as_uint(o[4 * w + 3] * drop_scale) & drop_mask32<3>(fl));
             }
-            pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
-            pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
-            reinterpret_cast<uint4*>(dx_drop + static_cast<size_t>(row) * D)[c] = pk;
+            pk = ln_pack_w<kW>(o);
+            reinterpret_cast<Vec*>(dx_drop + static_cast<size_t>(row) * D)[c] = pk;
           }
           // bias gradient of the producing linear sums what that linear's output actually received;
           // use the bf16-rounded values so it matches the wgrad operand exactly
           if constexpr (kBias) {
-            const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+            const uint32_t* pw = reinterpret_cast<const uint32_t*>(&pk);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < kW / 2; ++j) {
               ad[i][2 * j] += bf16_lo(pw[j]);
               ad[i][2 * j + 1] += bf16_hi(pw[j]);
             }
@@ -556,16 +601,16 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         }
       }
     }
-    // CTA reduce: warp w writes its registers, then the CTA folds 8 warps per column
+    // CTA reduce: warp w writes its registers, then the CTA folds the row warps per column
 #pragma unroll
-    for (int i = 0; i < kLnMaxChunks; ++i) {
+    for (int i = 0; i < kIt; ++i) {
       const int c = lane + 32 * i;
       if (c < nchunks) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          sred[(warp * kSums + 0) * D + c * 8 + j] = ag[i][j];
-          sred[(warp * kSums + 1) * D + c * 8 + j] = ab[i][j];
-          if constexpr (kBias) sred[(warp * kSums + 2) * D + c * 8 + j] = ad[i][j];
+        for (int j = 0; j < kW; ++j) {
+          sred[(warp * kSums + 0) * D + c * kW + j] = ag[i][j];
+          sred[(warp * kSums + 1) * D + c * kW + j] = ab[i][j];
+          if constexpr (kBias) sred[(warp * kSums + 2) * D + c * kW + j] = ad[i][j];
         }
       }
     }
@@ -635,7 +680,9 @@ int launch_layernorm_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const 
   if (stages < 2) return WM_ERR_SHAPE;
   const int smem = stages * stage_bytes + fixed;
   if (drop_thresh && static_cast<uint64_t>(M) * static_cast<uint64_t>((D + 15) / 16) * 4ull > 0xFFFFFFFFull) return WM_ERR_SHAPE;
-  auto kern = dbias ? layernorm_bwd_kernel<true, 8> : layernorm_bwd_kernel<false, 15>;
+  const bool w4 = g_ln_bwd_width ? g_ln_bwd_width == 4 : false;  // ("ln_bwd_width" option; A/B in profiles/r02_ln_width_ab.txt)
+  auto kern = dbias ? (w4 ? layernorm_bwd_kernel<true, 8, 4> : layernorm_bwd_kernel<true, 8, 8>)
+                    : (w4 ? layernorm_bwd_kernel<false, 15, 4> : layernorm_bwd_kernel<false, 15, 8>);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
   kern<<<ctas, 32 * (rows + 1), smem, stream>>>(dy, x, gamma, mean, rstd, dx, dx_drop, M, D, drop_thresh, drop_scale,
                                                 drop_keys(seed, stream_id), workspace, stages);
