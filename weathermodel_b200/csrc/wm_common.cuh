@@ -267,8 +267,12 @@ WM_DEVICE uint32_t mapa_u32(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(p)), "r"(rank));
   return a;
 }
+// Arrive on a barrier in another CTA of the cluster. Default semantics (.release at CTA scope), as CUTLASS'
+// ClusterBarrier::arrive uses: what this hands over is a TMEM accumulator stage, ordered by the tcgen05 fences around
+// it -- no global memory. The explicit `.release.cluster` form compiled to MEMBAR.ALL.GPU + ERRBAR in front of every
+// arrive: 46 % of the stall samples of the CTA-pair GEMM's epilogue warps (ncu source view, profiles/r02_gemm_membar.txt).
 WM_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
 template <uint32_t kCols>
 WM_DEVICE void tmem_alloc_2cta(uint32_t* smem_slot) {  // one warp in EACH CTA of the pair
