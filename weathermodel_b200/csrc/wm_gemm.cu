@@ -13,6 +13,8 @@
 //               fp32 partials reduced deterministically by wgrad_reduce.
 #include "wm_kernels.h"
 
+#include <type_traits>
+
 namespace wm {
 
 // ------------------------------------------------------------------------------------------------
@@ -109,6 +111,7 @@ constexpr int gemm_threads(int ew) { return 64 + 32 * ew; }
 constexpr int kWgradThreads = 192;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccStride = 256;
+constexpr int kBiasResident = 2560;
 
 struct GemmSmemTail {
   uint64_t full[kMaxStages];
@@ -117,7 +120,11 @@ struct GemmSmemTail {
   uint64_t acc_empty[2];
   uint32_t tmem_base;
   uint64_t res_full[16];           // per epilogue warp: the residual box of the current tile has landed (TMA-store epilogue)
-  alignas(16) float bias[1024];    // per epilogue warp (kEW x 1024 / kEW floats): the bias slice of its columns of the current tile
+  // the WHOLE bias vector (pre-scaled, zero-padded to whole tiles), staged once per CTA, when it fits (every layer of
+  // the model does: N <= 4 x 576); otherwise per epilogue warp (kEW x 1024 / kEW floats) the slice of the current tile,
+  // re-staged per tile -- a global-load latency per warp and tile with nothing to hide behind (ncu source view:
+  // long-scoreboard on that store was 26 % of the per-tile stall samples of the K = 576 epilogues)
+  alignas(16) float bias[kBiasResident];
 };
 
 // Epilogue of one 16-column group pair for one accumulator row. Auxiliary operands (residual / gate rows)
@@ -158,6 +165,125 @@ WM_DEVICE void epi_load_aux(EpiAux& x, const GemmEpilogue& ep, int row, int n0, 
 // arithmetic as well, bit 2 the TMEM loads, bit 3 stores the tile transposed-free into a compact per-CTA scratch.
 int g_gemm_diag = 0;  // copied into GemmEpilogue::diag by the launcher
 #endif
+
+// ---- straight-line epilogues for the flag sets of the training schedule -------------------------------------
+// The K = 576 GEMMs are bound by the ISSUE rate of their epilogue warps (ncu source view of the generic code below:
+// ~17 issued instructions per output element, stalls "not selected" / "math pipe throttle"): every option is a
+// run-time test there, and the compiler guards each with predicated register copies. For outputs in bf16 without a
+// second fp32 operand (no residual, no bf16 gate) the flag set becomes a template argument and the arithmetic runs
+// on register PAIRS: one FFMA2 / FADD2 / FMUL2 per two elements, ReLU and both kinds of mask on the packed bf16x2
+// word AFTER the conversion (max(., 0), a positive scale and an all-or-nothing mask commute with the rounding).
+constexpr int kEpiBias = 1, kEpiRelu = 2, kEpiDrop = 4, kEpiGateBits = 8, kEpiSignOut = 16;
+WM_DEVICE int epi_fast_flags(const GemmEpilogue& ep, int out_bytes) {
+  if (out_bytes != 2 || ep.gate || ep.residual) return -1;
+#ifdef WM_DIAG
+  if (ep.diag) return -1;
+#endif
+  const int f = (ep.bias ? kEpiBias : 0) | (ep.relu ? kEpiRelu : 0) | (ep.drop_thresh ? kEpiDrop : 0) |
+                (ep.gate_bits ? kEpiGateBits : 0) | (ep.sign_bits_out ? kEpiSignOut : 0);
+  switch (f) {  // qkv / plain dgrad / eval linear1 / training linear1 with and without dropout / linear2 dgrad
+    case 0: case kEpiBias: case kEpiBias | kEpiRelu: case kEpiBias | kEpiRelu | kEpiSignOut:
+    case kEpiBias | kEpiRelu | kEpiDrop | kEpiSignOut: case kEpiGateBits:
+      return f;
+  }
+  return -1;
+}
+// With dropout the bias slice in shared memory is PRE-SCALED by 1 / (1 - p): (acc + b) * s = fma(acc, s, b * s).
+WM_DEVICE float epi_bias_prescale(const GemmEpilogue& ep, int fast) { return (fast >= 0 && (fast & kEpiDrop)) ? ep.drop_scale : 1.0f; }
+WM_DEVICE void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int kF>
+WM_DEVICE void epi_fast16(const uint32_t (&v)[16], uint32_t gate_word, const float* sbias, const GemmEpilogue& ep,
+                          const DropKeys& dk, int row, int n0, int M, int N, bool wide, uint32_t sdst, int swz_chunk) {
+  // sdst: 32-bit shared address of this lane's row of the TMA box (swz_chunk >= 0) or of its 32 bytes of the staging
+  // tile (swz_chunk < 0); 0 = direct global stores. Same contract as epi_process16 otherwise.
+  if (n0 >= N) return;  // warp-uniform
+  const int m32 = (M + 31) & ~31;
+  if (!sdst && row >= M && (!(kF & kEpiSignOut) || row >= m32)) return;
+  uint32_t o[8];
+  const float4* b4 = reinterpret_cast<const float4*>(sbias);
+  const float sc = (kF & kEpiDrop) ? ep.drop_scale : ep.gate_scale;
+  const uint64_t sc2 = f2_pack(sc, sc);
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    uint64_t p0 = f2_pack_u(v[4 * j4], v[4 * j4 + 1]), p1 = f2_pack_u(v[4 * j4 + 2], v[4 * j4 + 3]);
+    if constexpr ((kF & kEpiBias) != 0) {
+      const float4 bv = b4[j4];
+      if constexpr ((kF & kEpiDrop) != 0) {
+        p0 = f2_fma(p0, sc2, f2_pack(bv.x, bv.y));
+        p1 = f2_fma(p1, sc2, f2_pack(bv.z, bv.w));
+      } else {
+        p0 = f2_add(p0, f2_pack(bv.x, bv.y));
+        p1 = f2_add(p1, f2_pack(bv.z, bv.w));
+      }
+    } else if constexpr ((kF & (kEpiDrop | kEpiGateBits)) != 0) {
+      p0 = f2_mul(p0, sc2);
+      p1 = f2_mul(p1, sc2);
+    }
+    float a0, a1, a2, a3;
+    f2_unpack(p0, a0, a1);
+    f2_unpack(p1, a2, a3);
+    o[2 * j4] = pack_bf16x2(a0, a1);
+    o[2 * j4 + 1] = pack_bf16x2(a2, a3);
+  }
+  if constexpr ((kF & kEpiRelu) != 0) {
+    const __nv_bfloat162 z = __floats2bfloat162_rn(0.0f, 0.0f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&o[j]), z);
+      o[j] = *reinterpret_cast<const uint32_t*>(&r);
+    }
+  }
+  if constexpr ((kF & kEpiDrop) != 0) {
+    const uint32_t add2 = drop_add2(ep.drop_thresh);
+    const uint32_t x0 = (static_cast<uint32_t>(row) * static_cast<uint32_t>((N + 15) >> 4) + static_cast<uint32_t>(n0 >> 4)) * 4u;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const DropWords fl = drop_flags4(x0 + w, dk, add2);
+      o[2 * w] &= drop_pair_mask(fl.a);
+      o[2 * w + 1] &= drop_pair_mask(fl.b);
+    }
+  }
+  if constexpr ((kF & kEpiGateBits) != 0) {  // bit j of the chunk's uint16 = even element of pair j, bit 8 + j = its odd one
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t m;  // the two bits go to the sign positions of bytes 0 and 1; PRMT replicates each over one half
+      asm("prmt.b32 %0, %1, %2, 0x9988;" : "=r"(m) : "r"(gate_word << (7 - j)), "r"(0u));
+      o[j] &= m;
+    }
+  }
+  const bool second = n0 + 8 < N;  // N % 8 == 0 (host-checked)
+  if constexpr ((kF & kEpiSignOut) != 0) {  // (outputs are >= 0 here: "positive" is "non-zero halfword")
+    uint32_t acc = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += __vminu2(o[i], 0x00010001u) << i;  // even elements at bit i, odd at 16 + i
+    uint32_t m = (acc & 0xFFu) | ((acc >> 8) & 0xFF00u);
+    if (!second) m &= 0x0F0Fu;
+    if (row < m32) ep.sign_bits_out[sign_bits_index(row, n0, N)] = static_cast<uint16_t>(row < M ? m : 0u);
+    if (!sdst && row >= M) return;
+  }
+  const uint4 o0 = make_uint4(o[0], o[1], o[2], o[3]), o1 = make_uint4(o[4], o[5], o[6], o[7]);
+  if (sdst) {
+    if (swz_chunk >= 0) {
+      const uint32_t r7 = static_cast<uint32_t>(threadIdx.x) & 7u;  // row inside the box = lane
+      sts128(sdst + ((static_cast<uint32_t>(swz_chunk) ^ r7) << 4), o0);
+      sts128(sdst + ((static_cast<uint32_t>(swz_chunk + 1) ^ r7) << 4), o1);
+    } else {
+      sts128(sdst, o0);
+      sts128(sdst + 16, o1);
+    }
+    return;
+  }
+  __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(row) * ep.ld_out + n0;
+  if (wide && second) {
+    stg256(op, o0, o1);
+  } else {
+    *reinterpret_cast<uint4*>(op) = o0;
+    if (second) *reinterpret_cast<uint4*>(op + 8) = o1;
+  }
+}
 
 template <typename OutT>
 WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const float* sbias, const GemmEpilogue& ep,
@@ -304,15 +430,65 @@ WM_DEVICE void epi_process16(const uint32_t (&v)[16], const EpiAux& aux, const f
   }
 }
 
+// The chunk loop of one epilogue warp and tile: TMEM loads run one 16-column chunk ahead of the arithmetic.
+// kF >= 0: one of the straight-line epilogues (epi_fast16<kF>); kF < 0: the generic one.
+template <typename OutT, int kAuxDepth, int kF>
+WM_DEVICE void epi_chunks(const GemmEpilogue& ep, const DropKeys& dk, EpiAux (&aux)[kAuxDepth], const float* sbias, uint32_t tbase,
+                          int row, int n_base, int cols_per, int M, int N, bool wide, int lane, uint8_t* stage, uint32_t stage_s,
+                          uint32_t pitch, bool box, bool res_box, bool box_live) {
+  uint32_t va[16], vb[16];
+  tmem_ld16(tbase, va);
+  for (int cb = 0; cb < cols_per; cb += 16 * kAuxDepth) {
+#pragma unroll
+    for (int d = 0; d < kAuxDepth; ++d) {
+      const int c0 = cb + d * 16;
+      if (c0 < cols_per) {
+#ifdef WM_DIAG
+        if (ep.diag & 4) continue;
+#endif
+        tmem_ld_wait();
+        if constexpr (kF >= 0) {
+          const uint32_t dst = box ? stage_s : (stage ? stage_s + static_cast<uint32_t>(c0) * 2u : 0u);
+          if (d & 1) {
+            if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, va);
+            epi_fast16<kF>(vb, aux[d].bits, sbias + c0, ep, dk, row, n_base + c0, M, N, wide, dst, box ? (c0 >> 3) : -1);
+          } else {
+            if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, vb);
+            epi_fast16<kF>(va, aux[d].bits, sbias + c0, ep, dk, row, n_base + c0, M, N, wide, dst, box ? (c0 >> 3) : -1);
+          }
+          if constexpr ((kF & kEpiGateBits) != 0) {
+            if (c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
+          }
+        } else {
+          if (d & 1) {
+            if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, va);
+            if (box) epi_process16<OutT>(vb, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3, box_live);
+            else epi_process16<OutT>(vb, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide,
+                                     stage ? stage + lane * pitch + c0 * 2 : nullptr);
+          } else {
+            if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, vb);
+            if (box) epi_process16<OutT>(va, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3, box_live);
+            else epi_process16<OutT>(va, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide,
+                                     stage ? stage + lane * pitch + c0 * 2 : nullptr);
+          }
+          if (!res_box && c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
+        }
+      }
+    }
+  }
+}
+
 // One epilogue warp's share of one accumulator tile: its 32 TMEM lanes (rows) x cols_per columns from n_base on.
 // Everything that does not depend on the accumulator (bias slice, first residual / gate chunks) is issued before
 // waiting for the MMAs; TMEM loads run one 16-column chunk ahead of the arithmetic.
-template <typename OutT, int kAuxDepth>
+template <typename OutT, int kAuxDepth, int kF>
 WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t* acc_full, uint32_t aph,
                                   uint32_t wait_code, uint32_t tbase, int row, int n_base, int cols_per, int M, int N,
                                   bool wide, int lane, uint8_t* stage, uint64_t* acc_empty, uint32_t acc_empty_cluster,
                                   const CUtensorMap* tmC = nullptr, const CUtensorMap* tmR = nullptr,
-                                  uint64_t* res_full = nullptr, uint32_t* res_count = nullptr) {
+                                  uint64_t* res_full = nullptr, uint32_t* res_count = nullptr, bool bias_resident = false) {
+  // kF: epi_fast_flags() of this launch (-1: the generic epilogue). bias_resident: sbias already points at this
+  // tile's columns of the whole (pre-scaled) bias vector, staged once per CTA.
   // tmR != nullptr (with tmC): the residual operand arrives by TMA, too -- one box load per warp and tile into the output
   // box itself (read-modify-write in place) instead of 32 row-strided 32-byte loads per lane and chunk.
   // tmC != nullptr (staged == 2, cols_per == 64): TMA-store epilogue. `stage` is this warp's 1024-byte aligned 4 KB
@@ -328,9 +504,10 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
   // warp-wide 16-byte store covers whole row segments: 4 - 5 lines per instruction instead of 32.
   const uint32_t pitch = static_cast<uint32_t>(cols_per) * 2u + 16u;  // odd number of 16-byte units: conflict-free
   const DropKeys dk = ep.drop_thresh ? drop_keys_live(ep.dkeys) : ep.dkeys;  // (+ the per-replay words of a captured step)
-  if (ep.bias) {
+  if (ep.bias && !bias_resident) {
+    const float bs = epi_bias_prescale(ep, kF);
     __syncwarp();
-    for (int j = lane; j < cols_per; j += 32) sbias[j] = (n_base + j < N) ? __ldg(ep.bias + n_base + j) : 0.0f;
+    for (int j = lane; j < cols_per; j += 32) sbias[j] = (n_base + j < N) ? __ldg(ep.bias + n_base + j) * bs : 0.0f;
     __syncwarp();
   }
   // ring of kAuxDepth prefetched 16-column chunks per thread (4 with 8 epilogue warps, 2 with 16): ~32 KB of
@@ -360,32 +537,9 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
     mbar_wait(res_full, *res_count & 1u, wait_code + 100);
     ++*res_count;
   }
-  uint32_t va[16], vb[16];
-  tmem_ld16(tbase, va);
-  for (int cb = 0; cb < cols_per; cb += 16 * kAuxDepth) {
-#pragma unroll
-    for (int d = 0; d < kAuxDepth; ++d) {
-      const int c0 = cb + d * 16;
-      if (c0 < cols_per) {
-#ifdef WM_DIAG
-        if (ep.diag & 4) continue;
-#endif
-        tmem_ld_wait();
-        if (d & 1) {
-          if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, va);
-          if (tmC) epi_process16<OutT>(vb, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3, box_live);
-          else epi_process16<OutT>(vb, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide,
-                                   stage ? stage + lane * pitch + c0 * 2 : nullptr);
-        } else {
-          if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, vb);
-          if (tmC) epi_process16<OutT>(va, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3, box_live);
-          else epi_process16<OutT>(va, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide,
-                                   stage ? stage + lane * pitch + c0 * 2 : nullptr);
-        }
-        if (!res_box && c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
-      }
-    }
-  }
+  const uint32_t stage_s = stage ? smem_u32(stage) + static_cast<uint32_t>(lane) * (tmC ? 128u : pitch) : 0u;
+epi_chunks<OutT, kAuxDepth, (sizeof(OutT) == 2 ? kF : -1)>(ep, dk, aux, sbias, tbase, row, n_base, cols_per, M, N, wide, lane, stage, stage_s, pitch,
+                                                              tmC != nullptr, res_box, box_live);
 #ifdef WM_DIAG
   tmem_ld_wait();
 #endif
@@ -429,6 +583,68 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
   }
 }
 
+// The persistent loop of one epilogue warp over its CTA's (or CTA pair's) tiles, for one epilogue flag set kF. The
+// dispatch over kF happens ONCE per kernel, outside this loop: with it inside, ptxas hoisted the loop invariants of all
+// seven bodies out of the tile loop together and spilled ~10 KB.
+struct EpiRole {
+  int t0, tstride, total_tiles, n_tiles, BN, M, N;
+  int row_tile, row_off;      // rows per tile index (128, or 256 for a CTA pair) and this CTA's offset inside it
+  uint32_t tmem_base, epi_stage_warp, wait_code;
+  uint8_t* epi_stage;
+  int staged, res_tma;
+  bool bias_resident, pair;
+};
+template <typename OutT, int kEW, int kF>
+WM_DEVICE void gemm_epilogue_role(const GemmEpilogue& ep, const EpiRole& r, GemmSmemTail* tail, const CUtensorMap* tmC,
+                                  const CUtensorMap* tmR, int warp, int lane) {
+  const int q = warp & 3;                 // TMEM lane quarter this warp may read
+  const int ew = warp - 2;                // 0..kEW-1
+  const int half = ew >> 2;               // which slice of the tile's columns this warp owns
+  const int cols_per = r.BN / (kEW / 4);  // a multiple of 16 (host-checked)
+  float* sbias = tail->bias + ew * (kEW > 8 ? 64 : 128);  // (not resident:) 16-byte aligned slices, >= the warp's column count
+  // 32-byte accesses need 32-byte aligned rows: every leading dimension a multiple of 16 bf16 elements
+  const bool wide = ((ep.ld_out | (ep.residual ? ep.ld_res : 0) | (ep.gate ? ep.ld_gate : 0)) & 15) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(ep.out) | reinterpret_cast<uintptr_t>(ep.residual) |
+                      reinterpret_cast<uintptr_t>(ep.gate)) & 31) == 0;
+  uint32_t acc_empty_leader[2] = {0u, 0u};
+  if (r.pair) {
+    acc_empty_leader[0] = mapa_u32(&tail->acc_empty[0], 0);
+    acc_empty_leader[1] = mapa_u32(&tail->acc_empty[1], 0);
+  }
+  int it = 0;
+  uint32_t res_count = 0u;
+  for (int t = r.t0; t < r.total_tiles; t += r.tstride, ++it) {
+    const int m_blk = t / r.n_tiles, n_blk = t % r.n_tiles;
+    const int as = it & 1;
+    const uint32_t aph = (it >> 1) & 1u;
+    const uint32_t tbase = r.tmem_base + as * kAccStride + half * cols_per + (static_cast<uint32_t>(q * 32) << 16);
+    gemm_epilogue_tile<OutT, (kEW == 16 ? 2 : 4), kF>(
+        ep, r.bias_resident ? tail->bias + n_blk * r.BN + half * cols_per : sbias, &tail->acc_full[as], aph, r.wait_code, tbase,
+        m_blk * r.row_tile + r.row_off + q * 32 + lane, n_blk * r.BN + half * cols_per, cols_per, r.M, r.N, wide, lane,
+        r.staged ? r.epi_stage + static_cast<uint32_t>(ew) * r.epi_stage_warp : nullptr, r.pair ? nullptr : &tail->acc_empty[as],
+        acc_empty_leader[as], r.staged == 2 ? tmC : nullptr, (r.staged == 2 && r.res_tma) ? tmR : nullptr, &tail->res_full[ew],
+        &res_count, r.bias_resident);
+  }
+  if (r.staged == 2 && lane == 0) bulk_wait_group_read<0>();  // the last box must be read before the CTA's smem goes away
+}
+template <typename OutT, int kEW>
+WM_DEVICE void gemm_epilogue_dispatch(int fast, const GemmEpilogue& ep, const EpiRole& r, GemmSmemTail* tail,
+                                      const CUtensorMap* tmC, const CUtensorMap* tmR, int warp, int lane) {
+#define WM_EPI_ROLE(F) gemm_epilogue_role<OutT, kEW, F>(ep, r, tail, tmC, tmR, warp, lane)
+  if constexpr (sizeof(OutT) == 2) {
+    if (fast == (kEpiBias | kEpiRelu | kEpiDrop | kEpiSignOut)) WM_EPI_ROLE(kEpiBias | kEpiRelu | kEpiDrop | kEpiSignOut);
+    else if (fast == kEpiGateBits) WM_EPI_ROLE(kEpiGateBits);
+    else if (fast == kEpiBias) WM_EPI_ROLE(kEpiBias);
+    else if (fast == 0) WM_EPI_ROLE(0);
+    else if (fast == (kEpiBias | kEpiRelu | kEpiSignOut)) WM_EPI_ROLE(kEpiBias | kEpiRelu | kEpiSignOut);
+    else if (fast == (kEpiBias | kEpiRelu)) WM_EPI_ROLE(kEpiBias | kEpiRelu);
+    else WM_EPI_ROLE(-1);
+  } else {
+    WM_EPI_ROLE(-1);
+  }
+#undef WM_EPI_ROLE
+}
+
 template <typename OutT, int kEW>
 __global__ void __launch_bounds__(gemm_threads(kEW), 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -470,6 +686,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(&tail->tmem_base);
+  const int fast = epi_fast_flags(ep, static_cast<int>(sizeof(OutT)));
+  const bool bias_resident = ep.bias && n_tiles * BN <= kBiasResident;
+  if (bias_resident) {
+    const float bs = epi_bias_prescale(ep, fast);
+    for (int j = threadIdx.x; j < n_tiles * BN; j += blockDim.x) tail->bias[j] = j < N ? __ldg(ep.bias + j) * bs : 0.0f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -522,29 +744,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit_warp(&tail->acc_full[as]);
     }
   } else {
-    const int q = warp & 3;          // TMEM lane quarter this warp may read
-    const int ew = warp - 2;              // 0..kEW-1
-    const int half = ew >> 2;             // which slice of the tile's columns this warp owns
-    const int cols_per = BN / (kEW / 4);  // a multiple of 16 (host-checked)
-    float* sbias = tail->bias + ew * (kEW > 8 ? 64 : 128);  // 16-byte aligned slices, >= the warp's column count
-    // 32-byte accesses need 32-byte aligned rows: every leading dimension a multiple of 16 bf16 elements
-    const bool wide = ((ep.ld_out | (ep.residual ? ep.ld_res : 0) | (ep.gate ? ep.ld_gate : 0)) & 15) == 0 &&
-                      ((reinterpret_cast<uintptr_t>(ep.out) | reinterpret_cast<uintptr_t>(ep.residual) |
-                        reinterpret_cast<uintptr_t>(ep.gate)) & 31) == 0;
-    int it = 0;
-    uint32_t res_count = 0u;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int m_blk = t / n_tiles, n_blk = t % n_tiles;
-      const int as = it & 1;
-      const uint32_t aph = (it >> 1) & 1u;
-      const uint32_t tbase = tmem_base + as * kAccStride + half * cols_per + (static_cast<uint32_t>(q * 32) << 16);
-      gemm_epilogue_tile<OutT, (kEW == 16 ? 2 : 4)>(ep, sbias, &tail->acc_full[as], aph, 14, tbase, m_blk * kBM + q * 32 + lane,
-                               n_blk * BN + half * cols_per, cols_per, M, N, wide, lane,
-                               staged ? epi_stage + static_cast<uint32_t>(ew) * epi_stage_warp : nullptr,
-                               &tail->acc_empty[as], 0u, staged == 2 ? &tmC : nullptr, (staged == 2 && res_tma) ? &tmR : nullptr,
-                               &tail->res_full[ew], &res_count);
-    }
-    if (staged == 2 && lane == 0) bulk_wait_group_read<0>();  // the last box must be read before the CTA's smem goes away
+    const EpiRole r{static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), total_tiles, n_tiles, BN, M, N, kBM, 0,
+                    tmem_base, epi_stage_warp, 14u, epi_stage, staged, res_tma, bias_resident, false};
+    gemm_epilogue_dispatch<OutT, kEW>(fast, ep, r, tail, &tmC, &tmR, warp, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -602,6 +804,12 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2cta<kTmemCols>(&tail->tmem_base);
+  const int fast = epi_fast_flags(ep, static_cast<int>(sizeof(OutT)));
+  const bool bias_resident = ep.bias && n_tiles * BN <= kBiasResident;
+  if (bias_resident) {
+    const float bs = epi_bias_prescale(ep, fast);
+    for (int j = threadIdx.x; j < n_tiles * BN; j += blockDim.x) tail->bias[j] = j < N ? __ldg(ep.bias + j) * bs : 0.0f;
+  }
   tc_fence_before();
   cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
   tc_fence_after();
@@ -652,30 +860,9 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    const int q = warp & 3;
-    const int ew = warp - 2;
-    const int half = ew >> 2;
-    const int cols_per = BN / (kEW / 4);
-    float* sbias = tail->bias + ew * (kEW > 8 ? 64 : 128);  // 16-byte aligned slices, >= the warp's column count
-    const bool wide = ((ep.ld_out | (ep.residual ? ep.ld_res : 0) | (ep.gate ? ep.ld_gate : 0)) & 15) == 0 &&
-                      ((reinterpret_cast<uintptr_t>(ep.out) | reinterpret_cast<uintptr_t>(ep.residual) |
-                        reinterpret_cast<uintptr_t>(ep.gate)) & 31) == 0;
-    const uint32_t acc_empty_leader[2] = {mapa_u32(&tail->acc_empty[0], 0), mapa_u32(&tail->acc_empty[1], 0)};
-    int it = 0;
-    uint32_t res_count = 0u;
-    for (int t = pair; t < total_tiles; t += npairs, ++it) {
-      const int m_blk = t / n_tiles, n_blk = t % n_tiles;
-      const int as = it & 1;
-      const uint32_t aph = (it >> 1) & 1u;
-      const uint32_t tbase = tmem_base + as * kAccStride + half * cols_per + (static_cast<uint32_t>(q * 32) << 16);
-      gemm_epilogue_tile<OutT, (kEW == 16 ? 2 : 4)>(ep, sbias, &tail->acc_full[as], aph, 64, tbase,
-                               m_blk * 2 * kBM + static_cast<int>(rank) * kBM + q * 32 + lane,
-                               n_blk * BN + half * cols_per, cols_per, M, N, wide, lane,
-                               staged ? epi_stage + static_cast<uint32_t>(ew) * epi_stage_warp : nullptr,
-                               nullptr, acc_empty_leader[as], staged == 2 ? &tmC : nullptr, (staged == 2 && res_tma) ? &tmR : nullptr,
-                               &tail->res_full[ew], &res_count);
-    }
-    if (staged == 2 && lane == 0) bulk_wait_group_read<0>();
+    const EpiRole r{pair, npairs, total_tiles, n_tiles, BN, M, N, 2 * kBM, static_cast<int>(rank) * kBM,
+                    tmem_base, epi_stage_warp, 64u, epi_stage, staged, res_tma, bias_resident, true};
+    gemm_epilogue_dispatch<OutT, kEW>(fast, ep, r, tail, &tmC, &tmR, warp, lane);
   }
   __syncwarp();  // reconverge the single-lane role warps: barrier.cluster.*.aligned needs whole warps
   tc_fence_before();
