@@ -170,20 +170,23 @@ int g_gemm_diag = 0;  // copied into GemmEpilogue::diag by the launcher
 // The K = 576 GEMMs are bound by the ISSUE rate of their epilogue warps (ncu source view of the generic code below:
 // ~17 issued instructions per output element, stalls "not selected" / "math pipe throttle"): every option is a
 // run-time test there, and the compiler guards each with predicated register copies. For outputs in bf16 without a
-// second fp32 operand (no residual, no bf16 gate) the flag set becomes a template argument and the arithmetic runs
-// on register PAIRS: one FFMA2 / FADD2 / FMUL2 per two elements, ReLU and both kinds of mask on the packed bf16x2
-// word AFTER the conversion (max(., 0), a positive scale and an all-or-nothing mask commute with the rounding).
-constexpr int kEpiBias = 1, kEpiRelu = 2, kEpiDrop = 4, kEpiGateBits = 8, kEpiSignOut = 16;
+// bf16 gate operand the flag set becomes a template argument and the arithmetic runs on register PAIRS: one FFMA2 /
+// FADD2 / FMUL2 per two elements. Without a residual, ReLU and both kinds of mask act on the packed bf16x2 word AFTER
+// the conversion (max(., 0), a positive scale and an all-or-nothing mask commute with the rounding); with one, the
+// dropout mask is applied per fp32 element so that the sum is rounded once.
+constexpr int kEpiBias = 1, kEpiRelu = 2, kEpiDrop = 4, kEpiGateBits = 8, kEpiSignOut = 16, kEpiResidual = 32;
 WM_DEVICE int epi_fast_flags(const GemmEpilogue& ep, int out_bytes) {
-  if (out_bytes != 2 || ep.gate || ep.residual) return -1;
+  if (out_bytes != 2 || ep.gate) return -1;
 #ifdef WM_DIAG
   if (ep.diag) return -1;
 #endif
   const int f = (ep.bias ? kEpiBias : 0) | (ep.relu ? kEpiRelu : 0) | (ep.drop_thresh ? kEpiDrop : 0) |
-                (ep.gate_bits ? kEpiGateBits : 0) | (ep.sign_bits_out ? kEpiSignOut : 0);
-  switch (f) {  // qkv / plain dgrad / eval linear1 / training linear1 with and without dropout / linear2 dgrad
+                (ep.gate_bits ? kEpiGateBits : 0) | (ep.sign_bits_out ? kEpiSignOut : 0) | (ep.residual ? kEpiResidual : 0);
+  switch (f) {  // qkv / plain dgrad / eval linear1 / training linear1 with and without dropout / linear2 dgrad /
+                // out-proj and linear2 with and without dropout / the dgrads that add the gradient of the residual branch
     case 0: case kEpiBias: case kEpiBias | kEpiRelu: case kEpiBias | kEpiRelu | kEpiSignOut:
     case kEpiBias | kEpiRelu | kEpiDrop | kEpiSignOut: case kEpiGateBits:
+    case kEpiBias | kEpiDrop | kEpiResidual: case kEpiBias | kEpiResidual: case kEpiResidual:
       return f;
   }
   return -1;
@@ -195,8 +198,9 @@ WM_DEVICE void sts128(uint32_t addr, const uint4& v) {
 }
 
 template <int kF>
-WM_DEVICE void epi_fast16(const uint32_t (&v)[16], uint32_t gate_word, const float* sbias, const GemmEpilogue& ep,
-                          const DropKeys& dk, int row, int n0, int M, int N, bool wide, uint32_t sdst, int swz_chunk) {
+WM_DEVICE void epi_fast16(const uint32_t (&v)[16], const EpiAux& aux, const float* sbias, const GemmEpilogue& ep,
+                          const DropKeys& dk, int row, int n0, int M, int N, bool wide, uint32_t sdst, int swz_chunk,
+                          bool res_in_box) {
   // sdst: 32-bit shared address of this lane's row of the TMA box (swz_chunk >= 0) or of its 32 bytes of the staging
   // tile (swz_chunk < 0); 0 = direct global stores. Same contract as epi_process16 otherwise.
   if (n0 >= N) return;  // warp-uniform
@@ -206,6 +210,21 @@ WM_DEVICE void epi_fast16(const uint32_t (&v)[16], uint32_t gate_word, const flo
   const float4* b4 = reinterpret_cast<const float4*>(sbias);
   const float sc = (kF & kEpiDrop) ? ep.drop_scale : ep.gate_scale;
   const uint64_t sc2 = f2_pack(sc, sc);
+  const uint32_t add2 = drop_add2(ep.drop_thresh);
+  const uint32_t x0 = (static_cast<uint32_t>(row) * static_cast<uint32_t>((N + 15) >> 4) + static_cast<uint32_t>(n0 >> 4)) * 4u;
+  const uint32_t r7 = static_cast<uint32_t>(threadIdx.x) & 7u;  // row inside a TMA box = lane
+  uint32_t rw[8];
+  if constexpr ((kF & kEpiResidual) != 0) {
+    uint4 r0 = aux.a[0], r1 = aux.a[1];
+    if (res_in_box) {  // the residual tile was TMA-loaded into this warp's output box: same swizzled positions as the output
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w)
+                   : "r"(sdst + ((static_cast<uint32_t>(swz_chunk) ^ r7) << 4)) : "memory");
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w)
+                   : "r"(sdst + ((static_cast<uint32_t>(swz_chunk + 1) ^ r7) << 4)) : "memory");
+    }
+    rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w;
+    rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
+  }
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) {
     uint64_t p0 = f2_pack_u(v[4 * j4], v[4 * j4 + 1]), p1 = f2_pack_u(v[4 * j4 + 2], v[4 * j4 + 3]);
@@ -225,6 +244,19 @@ WM_DEVICE void epi_fast16(const uint32_t (&v)[16], uint32_t gate_word, const flo
     float a0, a1, a2, a3;
     f2_unpack(p0, a0, a1);
     f2_unpack(p1, a2, a3);
+    if constexpr ((kF & kEpiResidual) != 0) {  // the sum with the residual is formed in fp32: masks per element, then FADD2
+      if constexpr ((kF & kEpiDrop) != 0) {
+        const DropWords fl = drop_flags4(x0 + j4, dk, add2);
+        a0 = __uint_as_float(__float_as_uint(a0) & drop_mask32<0>(fl));
+        a1 = __uint_as_float(__float_as_uint(a1) & drop_mask32<1>(fl));
+        a2 = __uint_as_float(__float_as_uint(a2) & drop_mask32<2>(fl));
+        a3 = __uint_as_float(__float_as_uint(a3) & drop_mask32<3>(fl));
+      }
+      p0 = f2_add(f2_pack(a0, a1), f2_pack(bf16_lo(rw[2 * j4]), bf16_hi(rw[2 * j4])));
+      p1 = f2_add(f2_pack(a2, a3), f2_pack(bf16_lo(rw[2 * j4 + 1]), bf16_hi(rw[2 * j4 + 1])));
+      f2_unpack(p0, a0, a1);
+      f2_unpack(p1, a2, a3);
+    }
     o[2 * j4] = pack_bf16x2(a0, a1);
     o[2 * j4 + 1] = pack_bf16x2(a2, a3);
   }
@@ -236,9 +268,7 @@ WM_DEVICE void epi_fast16(const uint32_t (&v)[16], uint32_t gate_word, const flo
       o[j] = *reinterpret_cast<const uint32_t*>(&r);
     }
   }
-  if constexpr ((kF & kEpiDrop) != 0) {
-    const uint32_t add2 = drop_add2(ep.drop_thresh);
-    const uint32_t x0 = (static_cast<uint32_t>(row) * static_cast<uint32_t>((N + 15) >> 4) + static_cast<uint32_t>(n0 >> 4)) * 4u;
+  if constexpr ((kF & kEpiDrop) != 0 && (kF & kEpiResidual) == 0) {
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const DropWords fl = drop_flags4(x0 + w, dk, add2);
@@ -250,7 +280,7 @@ WM_DEVICE void epi_fast16(const uint32_t (&v)[16], uint32_t gate_word, const flo
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       uint32_t m;  // the two bits go to the sign positions of bytes 0 and 1; PRMT replicates each over one half
-      asm("prmt.b32 %0, %1, %2, 0x9988;" : "=r"(m) : "r"(gate_word << (7 - j)), "r"(0u));
+      asm("prmt.b32 %0, %1, %2, 0x9988;" : "=r"(m) : "r"(aux.bits << (7 - j)), "r"(0u));
       o[j] &= m;
     }
   }
@@ -267,7 +297,6 @@ WM_DEVICE void epi_fast16(const uint32_t (&v)[16], uint32_t gate_word, const flo
   const uint4 o0 = make_uint4(o[0], o[1], o[2], o[3]), o1 = make_uint4(o[4], o[5], o[6], o[7]);
   if (sdst) {
     if (swz_chunk >= 0) {
-      const uint32_t r7 = static_cast<uint32_t>(threadIdx.x) & 7u;  // row inside the box = lane
       sts128(sdst + ((static_cast<uint32_t>(swz_chunk) ^ r7) << 4), o0);
       sts128(sdst + ((static_cast<uint32_t>(swz_chunk + 1) ^ r7) << 4), o1);
     } else {
@@ -451,13 +480,13 @@ WM_DEVICE void epi_chunks(const GemmEpilogue& ep, const DropKeys& dk, EpiAux (&a
           const uint32_t dst = box ? stage_s : (stage ? stage_s + static_cast<uint32_t>(c0) * 2u : 0u);
           if (d & 1) {
             if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, va);
-            epi_fast16<kF>(vb, aux[d].bits, sbias + c0, ep, dk, row, n_base + c0, M, N, wide, dst, box ? (c0 >> 3) : -1);
+            epi_fast16<kF>(vb, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, dst, box ? (c0 >> 3) : -1, box_live);
           } else {
             if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, vb);
-            epi_fast16<kF>(va, aux[d].bits, sbias + c0, ep, dk, row, n_base + c0, M, N, wide, dst, box ? (c0 >> 3) : -1);
+            epi_fast16<kF>(va, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, dst, box ? (c0 >> 3) : -1, box_live);
           }
-          if constexpr ((kF & kEpiGateBits) != 0) {
-            if (c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
+          if constexpr ((kF & (kEpiGateBits | kEpiResidual)) != 0) {
+            if (!res_box && c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
           }
         } else {
           if (d & 1) {
@@ -638,6 +667,9 @@ WM_DEVICE void gemm_epilogue_dispatch(int fast, const GemmEpilogue& ep, const Ep
     else if (fast == 0) WM_EPI_ROLE(0);
     else if (fast == (kEpiBias | kEpiRelu | kEpiSignOut)) WM_EPI_ROLE(kEpiBias | kEpiRelu | kEpiSignOut);
     else if (fast == (kEpiBias | kEpiRelu)) WM_EPI_ROLE(kEpiBias | kEpiRelu);
+    else if (fast == (kEpiBias | kEpiDrop | kEpiResidual)) WM_EPI_ROLE(kEpiBias | kEpiDrop | kEpiResidual);
+    else if (fast == kEpiResidual) WM_EPI_ROLE(kEpiResidual);
+    else if (fast == (kEpiBias | kEpiResidual)) WM_EPI_ROLE(kEpiBias | kEpiResidual);
     else WM_EPI_ROLE(-1);
   } else {
     WM_EPI_ROLE(-1);
