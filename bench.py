@@ -456,6 +456,8 @@ def run_ours(args, rank, world, local_rank):
     flops_seq = train_flops_per_seq(size, 31 if kind == "weatherbert" else 62)
     also = {}
     if rank == 0:
+        if ops.TUNED_GEMM_SITES:  # kernel variant per GEMM call site as tuned at start-up: (CTA pairs, epilogue warps, store path)
+            also["gemm_site_variants"] = {k: "/".join(str(v) for v in var) for k, var in next(iter(ops.TUNED_GEMM_SITES.values())).items()}
         also["step_tensor_frac_of_sustained"] = (value / world) * flops_seq / (pk["tf_sustained"] * 1e12)
         also["algorithmic_gflop_per_seq"] = flops_seq / 1e9
 
@@ -508,7 +510,7 @@ def run_ours(args, rank, world, local_rank):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the one `ncu --set full`
 # capture kept under profiles/ (r02_gemm_lin1_full.txt: gemm_tn2_kernel<bf16, 16 epilogue warps>, CTA pairs, TMA-store epilogue);
 # keyed by the GEMM shape it was taken on, null for the others.
-NCU_DRAM_BYTES_PER_LAUNCH = {(186880, 2304, 576): 218011648 + 803014144}
+NCU_DRAM_BYTES_PER_LAUNCH = {(186880, 2304, 576): 218562560 + 809818880}  # profiles/r02_gemm_roofline_ncu_v2.txt
 
 
 def main():

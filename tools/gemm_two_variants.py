@@ -8,7 +8,7 @@ a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
 w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
 bias = torch.zeros(N, device="cuda")
 bits = ops.gemm_sign_bits(M, N, "cuda")
-for two, ew, stg in ((1, 16, 2), (0, 16, 2)):
+for two, ew, stg in ((1, 8, 0), (1, 16, 2)):
     for name, v in (("gemm_two_cta", two), ("gemm_epi_warps", ew), ("gemm_staged", stg)):
         ops.lib().wm_set_option(name.encode(), v)
     for _ in range(3):

@@ -198,7 +198,7 @@ WM_DEVICE void sts128(uint32_t addr, const uint4& v) {
 }
 
 template <int kF>
-WM_DEVICE void epi_fast16(const uint32_t (&v)[16], const EpiAux& aux, const float* sbias, const GemmEpilogue& ep,
+WM_DEVICE void epi_fast16(const uint32_t (&v)[16], const EpiAux& aux, const float4 (&bias4)[4], const GemmEpilogue& ep,
                           const DropKeys& dk, int row, int n0, int M, int N, bool wide, uint32_t sdst, int swz_chunk,
                           bool res_in_box) {
   // sdst: 32-bit shared address of this lane's row of the TMA box (swz_chunk >= 0) or of its 32 bytes of the staging
@@ -207,7 +207,6 @@ WM_DEVICE void epi_fast16(const uint32_t (&v)[16], const EpiAux& aux, const floa
   const int m32 = (M + 31) & ~31;
   if (!sdst && row >= M && (!(kF & kEpiSignOut) || row >= m32)) return;
   uint32_t o[8];
-  const float4* b4 = reinterpret_cast<const float4*>(sbias);
   const float sc = (kF & kEpiDrop) ? ep.drop_scale : ep.gate_scale;
   const uint64_t sc2 = f2_pack(sc, sc);
   const uint32_t add2 = drop_add2(ep.drop_thresh);
@@ -229,7 +228,7 @@ WM_DEVICE void epi_fast16(const uint32_t (&v)[16], const EpiAux& aux, const floa
   for (int j4 = 0; j4 < 4; ++j4) {
     uint64_t p0 = f2_pack_u(v[4 * j4], v[4 * j4 + 1]), p1 = f2_pack_u(v[4 * j4 + 2], v[4 * j4 + 3]);
     if constexpr ((kF & kEpiBias) != 0) {
-      const float4 bv = b4[j4];
+      const float4 bv = bias4[j4];
       if constexpr ((kF & kEpiDrop) != 0) {
         p0 = f2_fma(p0, sc2, f2_pack(bv.x, bv.y));
         p1 = f2_fma(p1, sc2, f2_pack(bv.z, bv.w));
@@ -475,20 +474,28 @@ WM_DEVICE void epi_chunks(const GemmEpilogue& ep, const DropKeys& dk, EpiAux (&a
 #ifdef WM_DIAG
         if (ep.diag & 4) continue;
 #endif
-        tmem_ld_wait();
         if constexpr (kF >= 0) {
+          // (the bias values of the chunk are fetched BEFORE the wait: tcgen05.wait::ld is a compiler barrier for memory
+          // operations, and behind it the first FADD2 / FFMA2 stalled on this load)
+          float4 b4[4];
+          if constexpr ((kF & kEpiBias) != 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b4[j] = reinterpret_cast<const float4*>(sbias + c0)[j];
+          }
+          tmem_ld_wait();
           const uint32_t dst = box ? stage_s : (stage ? stage_s + static_cast<uint32_t>(c0) * 2u : 0u);
           if (d & 1) {
             if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, va);
-            epi_fast16<kF>(vb, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, dst, box ? (c0 >> 3) : -1, box_live);
+            epi_fast16<kF>(vb, aux[d], b4, ep, dk, row, n_base + c0, M, N, wide, dst, box ? (c0 >> 3) : -1, box_live);
           } else {
             if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, vb);
-            epi_fast16<kF>(va, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, dst, box ? (c0 >> 3) : -1, box_live);
+            epi_fast16<kF>(va, aux[d], b4, ep, dk, row, n_base + c0, M, N, wide, dst, box ? (c0 >> 3) : -1, box_live);
           }
           if constexpr ((kF & (kEpiGateBits | kEpiResidual)) != 0) {
             if (!res_box && c0 + 16 * kAuxDepth < cols_per) epi_load_aux(aux[d], ep, row, n_base + c0 + 16 * kAuxDepth, M, N, wide);
           }
         } else {
+          tmem_ld_wait();
           if (d & 1) {
             if (c0 + 16 < cols_per) tmem_ld16(tbase + c0 + 16, va);
             if (box) epi_process16<OutT>(vb, aux[d], sbias + c0, ep, dk, row, n_base + c0, M, N, wide, stage + lane * 128, c0 >> 3, box_live);
@@ -515,7 +522,8 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
                                   uint32_t wait_code, uint32_t tbase, int row, int n_base, int cols_per, int M, int N,
                                   bool wide, int lane, uint8_t* stage, uint64_t* acc_empty, uint32_t acc_empty_cluster,
                                   const CUtensorMap* tmC = nullptr, const CUtensorMap* tmR = nullptr,
-                                  uint64_t* res_full = nullptr, uint32_t* res_count = nullptr, bool bias_resident = false) {
+                                  uint64_t* res_full = nullptr, uint32_t* res_count = nullptr, bool bias_resident = false,
+                                  const DropKeys* live_keys = nullptr) {
   // kF: epi_fast_flags() of this launch (-1: the generic epilogue). bias_resident: sbias already points at this
   // tile's columns of the whole (pre-scaled) bias vector, staged once per CTA.
   // tmR != nullptr (with tmC): the residual operand arrives by TMA, too -- one box load per warp and tile into the output
@@ -532,7 +540,8 @@ WM_DEVICE void gemm_epilogue_tile(const GemmEpilogue& ep, float* sbias, uint64_t
   // not the MMAs, set the pace (tools/gemm_diag.py: linear1 0.505 ms with, 0.359 ms without the stores). Staged, a
   // warp-wide 16-byte store covers whole row segments: 4 - 5 lines per instruction instead of 32.
   const uint32_t pitch = static_cast<uint32_t>(cols_per) * 2u + 16u;  // odd number of 16-byte units: conflict-free
-  const DropKeys dk = ep.drop_thresh ? drop_keys_live(ep.dkeys) : ep.dkeys;  // (+ the per-replay words of a captured step)
+  // (+ the per-replay words of a captured step: device globals, read once per warp by the caller where it can)
+  const DropKeys dk = live_keys ? *live_keys : (ep.drop_thresh ? drop_keys_live(ep.dkeys) : ep.dkeys);
   if (ep.bias && !bias_resident) {
     const float bs = epi_bias_prescale(ep, kF);
     __syncwarp();
@@ -642,6 +651,7 @@ WM_DEVICE void gemm_epilogue_role(const GemmEpilogue& ep, const EpiRole& r, Gemm
   }
   int it = 0;
   uint32_t res_count = 0u;
+  const DropKeys dk = ep.drop_thresh ? drop_keys_live(ep.dkeys) : ep.dkeys;
   for (int t = r.t0; t < r.total_tiles; t += r.tstride, ++it) {
     const int m_blk = t / r.n_tiles, n_blk = t % r.n_tiles;
     const int as = it & 1;
@@ -652,7 +662,7 @@ WM_DEVICE void gemm_epilogue_role(const GemmEpilogue& ep, const EpiRole& r, Gemm
         m_blk * r.row_tile + r.row_off + q * 32 + lane, n_blk * r.BN + half * cols_per, cols_per, r.M, r.N, wide, lane,
         r.staged ? r.epi_stage + static_cast<uint32_t>(ew) * r.epi_stage_warp : nullptr, r.pair ? nullptr : &tail->acc_empty[as],
         acc_empty_leader[as], r.staged == 2 ? tmC : nullptr, (r.staged == 2 && r.res_tma) ? tmR : nullptr, &tail->res_full[ew],
-        &res_count, r.bias_resident);
+        &res_count, r.bias_resident, &dk);
   }
   if (r.staged == 2 && lane == 0) bulk_wait_group_read<0>();  // the last box must be read before the CTA's smem goes away
 }

@@ -133,12 +133,13 @@ def _gemm_epilogue(bias=None, relu=False, dropout_p=0.0, seed=0, stream_id=0, ga
 
 
 _TUNED_SITES = set()
+TUNED_GEMM_SITES = {}  # (M, D, FF, dropout, device) -> {site: (two_cta, epi_warps, staged)}: what the start-up tuner chose
 # (two_cta, epi_warps, staged): staged 0 = thread-per-row stores, 1 = smem-staged coalesced stores, 2 = TMA-store boxes
 # (the epilogue warp count then follows the tile width: 64 columns per warp). All bit-identical.
 GEMM_VARIANTS = tuple((two, ew, st) for st in (0, 1) for two in (0, 1) for ew in (8, 16)) + ((0, 16, 2), (1, 16, 2))
 
 
-def tune_gemm_sites(M, D, FF, dropout_p, device, min_tokens=8192, reps=5, margin=0.03):
+def tune_gemm_sites(M, D, FF, dropout_p, device, min_tokens=8192, reps=8, margin=0.03):
     """Time the (bit-identical) gemm_tn kernel variants on the eight GEMM call sites of one encoder layer --
     forward and dgrad, with the epilogues wm_encoder_forward / backward use -- on scratch operands of the real
     shapes, and record the fastest per site in the library (wm_gemm_set_variant). Runs once per (M, D, FF, dropout)
@@ -183,7 +184,7 @@ def tune_gemm_sites(M, D, FF, dropout_p, device, min_tokens=8192, reps=5, margin
                                    _stream()), "wm_gemm_tn (tuning)")
 
             times = {}
-            for _ in range(2):  # two passes over the variants: the first also warms clocks and caches
+            for _ in range(3):  # three passes over the variants (minimum kept): the first also warms clocks and caches
                 for var in GEMM_VARIANTS:
                     check(L.wm_gemm_set_variant(M, N, K, C.byref(ep), 0, *var), "wm_gemm_set_variant")
                     launch()
@@ -200,10 +201,11 @@ def tune_gemm_sites(M, D, FF, dropout_p, device, min_tokens=8192, reps=5, margin
                 best = GEMM_VARIANTS[0]
             check(L.wm_gemm_set_variant(M, N, K, C.byref(ep), 0, *best), "wm_gemm_set_variant")
             chosen[name] = best
+    TUNED_GEMM_SITES[key] = chosen
     return chosen
 
 
-def tune_gemm_call(a, b, reps=5, margin=0.03, **kw):
+def tune_gemm_call(a, b, reps=8, margin=0.03, **kw):
     """Pick the fastest (bit-identical) kernel variant for ONE gemm_tn call signature -- the (M, N, K, epilogue) of
     `gemm_tn(a, b, **kw)` -- the same way tune_gemm_sites does for the encoder's eight sites. Returns (variant, {variant: ms})."""
     _cuda(a, b)
@@ -219,7 +221,7 @@ def tune_gemm_call(a, b, reps=5, margin=0.03, **kw):
               "wm_gemm_tn (tuning)")
 
     times = {}
-    for _ in range(2):
+    for _ in range(3):
         for var in GEMM_VARIANTS:
             check(L.wm_gemm_set_variant(M, N, K, C.byref(ep), 0, *var), "wm_gemm_set_variant")
             launch()
