@@ -1311,11 +1311,15 @@ __global__ void wgrad_reduce4_kernel(const float4* __restrict__ partial, float4*
 // Work items = output tiles x token splits, one per CTA, all the same size: pick the split count that fills whole
 // waves of SMs (the first plan used ceil(2 * SMs / tiles) and lost up to a third of the machine to a nearly empty
 // last wave: 300 items on 148 SMs = 3 waves at 68 %), with a mild preference for fewer partial tiles to reduce.
+int g_wgrad_bn = 0;  // "wgrad_bn": 0 = the rule below, 64..256 = forced tile width (A/B runs)
 int wgrad_plan(int Mtok, int Nout, int Kout, int* BN, int* splits, int* tok_per_split) {
-  // tile width over Kout (64-column TMA boxes): 192 where it divides Kout (the D = 576 shapes were tuned on it), otherwise
+  // tile width over Kout (64-column TMA boxes): 256 for wide outputs it divides, 192 where that divides Kout (the D = 576
+  // shapes were tuned on it: 256-wide tiles there lose 15-25 % to the padded third tile), otherwise
   // the width that minimises tiles x (width + ~32 columns of per-tile overhead), the wider one on a tie
   int bn = 64;
-  if (Kout % 192 == 0) {
+  if (Kout % 256 == 0 && Kout >= 1024) {
+    bn = 256;  // (linear2's 576 x 2304 gradient: 0.484 ms against 0.510-0.516 with 192, tools/wgrad_bn_ab.py)
+  } else if (Kout % 192 == 0) {
     bn = 192;
   } else {
     long best = -1;
@@ -1327,6 +1331,7 @@ int wgrad_plan(int Mtok, int Nout, int Kout, int* BN, int* splits, int* tok_per_
       }
     }
   }
+  if (g_wgrad_bn >= 64 && g_wgrad_bn <= 256 && (g_wgrad_bn & 63) == 0) bn = g_wgrad_bn;
   const int tiles = ((Nout + kBM - 1) / kBM) * ((Kout + bn - 1) / bn);
   const int kb_total = (Mtok + kBK - 1) / kBK;
   const int sms = num_sms();
