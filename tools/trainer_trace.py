@@ -1,6 +1,6 @@
 """Where a trainer epoch spends host time: wraps the loader handed to <Model>Trainer._train_epoch and logs, per batch,
 how long the trainer waited for the loader (fetch) and how long it kept the batch (step issue). Diagnostic for the gap
-between bench.py's `value` and `e2e_trainer`.   python tools/trainer_trace.py [size] [batch]"""
+between bench.py's `value` and `e2e_trainer`.   python tools/trainer_trace.py [size] [batch] [weatherformer|weatherbert]"""
 import os
 import sys
 import time
@@ -53,7 +53,7 @@ def main():
         return out
 
     bt.BaseTrainer._train_epoch = traced_epoch
-    kind = "weatherformer"
+    kind = sys.argv[3] if len(sys.argv) > 3 else "weatherformer"
     print(bench.trainer_leg(kind, size, B, torch.device("cuda:0")))
 
 

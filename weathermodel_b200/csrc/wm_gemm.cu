@@ -968,11 +968,14 @@ int gemm_set_variant(int M, int N, int K, uint32_t sig, int two_cta, int epi_war
   g_gemm_variants[g_num_gemm_variants++] = GemmVariant{M, N, K, sig, two_cta, epi_warps, staged};
   return WM_OK;
 }
-static void gemm_pick_variant(int M, int N, int K, uint32_t sig, int* two_cta, int* epi_warps, int* staged) {
-  // untuned sites: CTA pairs where the main loop dominates, 16 epilogue warps + staged stores where the epilogue does
-  // (measured on the D = 576 shapes; narrower models gain nothing from either and keep the plain variant)
+static void gemm_pick_variant(int M, int N, int K, uint32_t sig, bool residual, int* two_cta, int* epi_warps, int* staged) {
+  // untuned sites of wide models: CTA pairs, 8 epilogue warps, direct stores -- except the short-K products that add a
+  // residual, where the TMA-store epilogue also TMA-loads the residual into the box (out-proj forward: 0.149 against
+  // 0.214 ms). Measured on the D = 576 shapes (profiles/r02_gemm_sites_variants_v3.txt); narrower models gain nothing
+  // from either and keep the plain variant.
   const bool wide_model = N >= 512 && K >= 512;
-  int two = (wide_model && K >= 1024) ? 1 : 0, ew = (wide_model && K < 1024) ? 16 : 8, stg = (wide_model && K < 1024) ? 1 : 0;
+  const bool box = wide_model && residual && K < 1024;
+  int two = wide_model ? 1 : 0, ew = box ? 16 : 8, stg = box ? 2 : 0;
   for (int i = 0; i < g_num_gemm_variants; ++i) {
     const GemmVariant& v = g_gemm_variants[i];
     if (v.M == M && v.N == N && v.K == K && v.sig == sig) {
@@ -1020,7 +1023,8 @@ static int launch_gemm_tn_impl(const void* A, int lda, const void* B, int ldb, i
   rc = make_tmap_bf16(&tmB, B, b_rows, K, ldb, kBK, BN);
   if (rc) return rc;
   int want_two, want_ew, want_staged;
-  gemm_pick_variant(M, N, K, gemm_signature(ep, out_fp32), &want_two, &want_ew, &want_staged);
+  gemm_pick_variant(M, N, K, gemm_signature(ep, out_fp32), ep.residual != nullptr && !ep.gate && !ep.gate_bits, &want_two, &want_ew,
+                    &want_staged);
   const int fixed_smem = 2048 + static_cast<int>(sizeof(GemmSmemTail));
   const bool aligned_out = !out_fp32 && (ep.ld_out & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0;
   // staged == 2: TMA-store epilogue. Every epilogue warp owns one 32 x 64 box, so the warp count follows from the
