@@ -187,6 +187,50 @@ def test_gemm_tn_epilogues():
     _cmp("dropout kept values", d1[kept], ((acc + bias) * scale)[kept], 2e-3, 2e-3)
 
 
+@pytest.mark.parametrize("M,N,K", [(777, 576, 576), (1030, 2304, 576), (515, 576, 2304)])
+def test_gemm_straight_line_epilogues_match_the_generic_body(M, N, K):
+    """bf16 outputs of the nine epilogue flag sets of the training / evaluation schedules run through straight-line
+    packed-math bodies (csrc/wm_gemm.cu epi_fast16); fp32 outputs run through the generic run-time-flag body. Same
+    masks (zero pattern bit for bit), same values up to the bf16 rounding of the output."""
+    a = _bf(M, K, seed=70)
+    b = _bf(N, K, scale=K ** -0.5, seed=71)
+    bias = torch.randn(N, device="cuda")
+    res = _bf(M, N, seed=72)
+    drop = dict(dropout_p=0.1, seed=21, stream_id=9)
+    bits = ops.gemm_sign_bits(M, N, "cuda")
+    bits32 = ops.gemm_sign_bits(M, N, "cuda")
+    cases = {
+        "plain": {}, "bias": dict(bias=bias), "bias+relu": dict(bias=bias, relu=True),
+        "bias+relu+bits": dict(bias=bias, relu=True, sign_bits_out=bits),
+        "bias+relu+drop+bits": dict(bias=bias, relu=True, sign_bits_out=bits, **drop),
+        "bias+drop+res": dict(bias=bias, residual=res, **drop), "bias+res": dict(bias=bias, residual=res),
+        "res": dict(residual=res),
+    }
+    for name, kw in cases.items():
+        kw32 = dict(kw)
+        if "sign_bits_out" in kw32:
+            kw32["sign_bits_out"] = bits32
+        fast = ops.gemm_tn(a, b, **kw)
+        slow = ops.gemm_tn(a, b, out_fp32=True, **kw32)
+        assert fast.dtype == torch.bfloat16 and slow.dtype == torch.float32
+        if "residual" not in kw:  # (with a residual a dropped element still carries the residual)
+            differ = (fast == 0) != (slow.to(torch.bfloat16) == 0)  # (only where acc + bias cancels to fp32 round-off)
+            assert bool((slow.abs()[differ] < 1e-5).all()) and int(differ.sum()) <= 4, f"{name}: zero pattern differs"
+        err = (fast.float() - slow).abs()
+        bound = slow.abs() * 2.0 ** -8 + 1e-6  # half an ulp of bf16 plus the fma-vs-(add, mul) difference
+        assert bool((err <= bound).all()), f"{name}: max excess {(err - bound).max().item():.3e}"
+        if "sign_bits_out" in kw:  # the sign side channel: bits of the bf16 output the next GEMM will see
+            g_fast = ops.gemm_tn(res, torch.eye(N, device="cuda", dtype=torch.bfloat16), gate_bits=bits, gate_scale=1.0)
+            assert torch.equal(g_fast != 0, (fast > 0) & (res != 0)), f"{name}: sign bits do not describe the output"
+    # gate bits (dgrad through dropout(relu(.))): straight-line body against the generic one
+    h = ops.gemm_tn(a, b, bias=bias, relu=True, sign_bits_out=bits, **drop)
+    g_fast = ops.gemm_tn(a, b, gate_bits=bits, gate_scale=1.0 / 0.9)
+    g_slow = ops.gemm_tn(a, b, gate_bits=bits, gate_scale=1.0 / 0.9, out_fp32=True)
+    assert torch.equal(g_fast != 0, (h > 0) & (g_slow.to(torch.bfloat16) != 0))
+    assert bool(((g_fast.float() - g_slow).abs() <= g_slow.abs() * 2.0 ** -8 + 1e-6).all())
+    assert ops.device_error() == 0
+
+
 # ------------------------------------------------------------------------------------------ gemm_wgrad
 @pytest.mark.parametrize("Mtok,Nout,Kout", [
     (64, 128, 64), (1000, 576, 576), (777, 64, 576), (3000, 200, 600), (4097, 1728, 576), (2048, 576, 2304),
