@@ -377,10 +377,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
               if (k0 + 32 <= S) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) mloc = fmax3(mloc, __uint_as_float(cur[j]), __uint_as_float(cur[j + 1]));
-              } else {
+              } else {  // the slice that holds key S - 1: only its valid columns (warp-uniform bounds)
+                const int nv = S - k0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (k0 + j < S) mloc = fmaxf(mloc, __uint_as_float(cur[j]));
+                for (int j = 0; j < 32; j += 2) {
+                  if (j + 2 <= nv) mloc = fmax3(mloc, __uint_as_float(cur[j]), __uint_as_float(cur[j + 1]));
+                  else if (j < nv) mloc = fmaxf(mloc, __uint_as_float(cur[j]));
+                }
               }
               if (!kFwdPrefetch && c + 1 < nkc) tmem_ld32(tS + lane_sel + (c + 1) * kKC + sl * 32, va);
             }
@@ -417,16 +420,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
               // exponentials sit on the SFU queue (8 cycles per warp instruction and scheduler). Written as two
               // separate loops the three warps of a scheduler -- which run in step, chunk by chunk -- all hashed and
               // then all queued on the SFU; interleaved, each pipe's work hides under the other's.
-              if (DROP && k0 + 32 <= S) {
+              // (The slice that holds key S - 1 takes the same loop with warp-uniform bounds: its invalid columns are
+              // skipped, not computed under per-element predicates -- the four warps that own it are otherwise the
+              // stragglers every other warp of the tile waits for at the next barrier.)
+              if (DROP) {
                 const uint32_t x0 = (rowbase + static_cast<uint32_t>(k0 >> 4)) * 4u;
+                const int nv = S - k0;  // >= 32 for a whole slice
                 uint32_t bits = 0u;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) {
+                  if (4 * w >= nv) {  // warp-uniform
+                    pk[2 * w] = 0u;
+                    pk[2 * w + 1] = 0u;
+                    continue;
+                  }
                   const DropWords f = drop_flags4(x0 + w, dkeys, add2);
                   float xa, xb, xc, xd;
                   f2_unpack(f2_fma(f2_pack_u(cur[4 * w], cur[4 * w + 1]), c2p, mnegp), xa, xb);
                   f2_unpack(f2_fma(f2_pack_u(cur[4 * w + 2], cur[4 * w + 3]), c2p, mnegp), xc, xd);
-                  const float ea = fast_exp2(xa), eb = fast_exp2(xb), ec = fast_exp2(xc), ed = fast_exp2(xd);
+                  float ea = fast_exp2(xa), eb = fast_exp2(xb), ec = fast_exp2(xc), ed = fast_exp2(xd);
+                  if (4 * w + 4 > nv) {  // the one word that straddles S
+                    if (4 * w + 1 >= nv) eb = 0.0f;
+                    if (4 * w + 2 >= nv) ec = 0.0f;
+                    if (4 * w + 3 >= nv) ed = 0.0f;
+                  }
                   lsum2 = f2_add(lsum2, f2_add(f2_pack(ea, eb), f2_pack(ec, ed)));
                   const uint32_t ma = drop_pair_mask(f.a), mb = drop_pair_mask(f.b);
                   pk[2 * w] = attn_pack2(ea, eb) & ma;
@@ -447,11 +464,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
                   pk[w] = attn_pack2(e0, e1);
                 }
               } else {
+                const int nv = S - k0;  // warp-uniform bounds: invalid columns are skipped, not predicated
 #pragma unroll
                 for (int w = 0; w < 16; ++w) {
-                  float e0 = 0.0f, e1 = 0.0f;
-                  if (k0 + 2 * w < S) e0 = fast_exp2(fmaf(__uint_as_float(cur[2 * w]), c2, mneg));
-                  if (k0 + 2 * w + 1 < S) e1 = fast_exp2(fmaf(__uint_as_float(cur[2 * w + 1]), c2, mneg));
+                  if (2 * w >= nv) {
+                    pk[w] = 0u;
+                    continue;
+                  }
+                  float x0f, x1f;
+                  f2_unpack(f2_fma(f2_pack_u(cur[2 * w], cur[2 * w + 1]), c2p, mnegp), x0f, x1f);
+                  const float e0 = fast_exp2(x0f), e1 = (2 * w + 1 < nv) ? fast_exp2(x1f) : 0.0f;
                   lsum2 = f2_add(lsum2, f2_pack(e0, e1));
                   pk[w] = attn_pack2(e0, e1);
                 }
