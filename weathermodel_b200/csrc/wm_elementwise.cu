@@ -358,6 +358,7 @@ WM_DEVICE typename LnVec<kW>::T ln_pack_w(const float (&o)[kW]) {
 // passes that hold an element of a row of D elements, and the chunk width that needs fewer element slots per lane
 static inline int ln_slots(int D, int w) { return ((D / w + 31) / 32) * w; }
 int g_ln_bwd_width = 0;  // 0 = default (8), 4 or 8 forced -- wm_set_option("ln_bwd_width", v)
+int g_ln_bwd_rows = 0;   // 0 = default, 14 or 15 row warps per CTA in the encoder form -- wm_set_option("ln_bwd_rows", v)
 int g_ln_fwd_width = 0;  // 0 = auto (ln_pick_width), 4 or 8 forced -- wm_set_option("ln_fwd_width", v)
 static inline int ln_pick_width(int D) { return ln_slots(D, 4) < ln_slots(D, 8) ? 4 : 8; }
 
@@ -463,7 +464,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   uint8_t* ring = ln_smem;
   constexpr int kSums = kBias ? 3 : 2;
   float* sred = reinterpret_cast<float*>(ring + static_cast<size_t>(stages) * stage_bytes);  // [kRows warps][kSums][D]
-  uint64_t* full = reinterpret_cast<uint64_t*>(sred + kRows * kSums * D);
+  float* sgam = sred + kRows * kSums * D;  // gamma (fp32): read per row from here instead of 24 registers per thread
+  uint64_t* full = reinterpret_cast<uint64_t*>(sgam + D);
   uint64_t* empty = full + stages;
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   using Vec = typename LnVec<kW>::T;
@@ -477,6 +479,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     }
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < D; i += blockDim.x) sgam[i] = gamma[i];
   __syncthreads();
 
   if (warp == kRows) {
@@ -500,14 +503,13 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     // the large shape, 4.1 TB/s), -3 % on the 8-row form -- so the kernel is NOT issue-bound; what remains is the
     // per-row dependency chain (barrier wait -> shared loads -> two warp reductions -> stores) at 15 rows per SM.
     constexpr int kP = kW / 2;
-    uint64_t g2[kIt][kP], ag2[kIt][kP], ab2[kIt][kP];
+    uint64_t ag2[kIt][kP], ab2[kIt][kP];
     float ad[kBias ? kIt : 1][kW];
 #pragma unroll
     for (int i = 0; i < kIt; ++i) {
       const int c = lane + 32 * i;
 #pragma unroll
       for (int j = 0; j < kP; ++j) {
-        g2[i][j] = c < nchunks ? f2_pack(gamma[c * kW + 2 * j], gamma[c * kW + 2 * j + 1]) : f2_pack(0.0f, 0.0f);
         ag2[i][j] = f2_pack(0.0f, 0.0f);
         ab2[i][j] = f2_pack(0.0f, 0.0f);
       }
@@ -534,44 +536,47 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         if (rn < M) { mu_n = __ldg(mean + rn); rs_n = __ldg(rstd + rn); }
       }
       mbar_wait(&full[s], ph, 42);
-      Vec xr[kIt], dr[kIt];
+      const bool live = row < M;  // warp-uniform (tail block)
+      uint64_t xh2[kIt][kP], gd2[kIt][kP];
+      uint64_t s1p = f2_pack(0.0f, 0.0f), s2p = f2_pack(0.0f, 0.0f);
+      const uint64_t nmu2 = f2_pack(-mu, -mu), rs2 = f2_pack(rs, rs);
       {
+        // (rows are read from the ring pass by pass, not all up front: the raw vectors of all passes next to the
+        // products built from them were the registers ptxas spilled -- the reloads showed up as long-scoreboard stalls)
         const Vec* sx = reinterpret_cast<const Vec*>(ring + static_cast<size_t>(s) * stage_bytes + warp * row_bytes);
         const Vec* sd = reinterpret_cast<const Vec*>(ring + static_cast<size_t>(s) * stage_bytes + tens_bytes + warp * row_bytes);
 #pragma unroll
         for (int i = 0; i < kIt; ++i) {
           const int c = lane + 32 * i;
-          const bool ok = c < nchunks && row < M;
-          if (ok) { xr[i] = sx[c]; dr[i] = sd[c]; }
-          else { xr[i] = Vec{}; dr[i] = Vec{}; }
-        }
-      }
-      __syncwarp();  // every lane has its copy: hand the slot back to the producer
-      if (lane == 0) mbar_arrive(&empty[s]);
-      if (++s == stages) { s = 0; ph ^= 1u; }
-      if (row >= M) continue;  // warp-uniform (tail block)
-      uint64_t xh2[kIt][kP], gd2[kIt][kP];
-      uint64_t s1p = f2_pack(0.0f, 0.0f), s2p = f2_pack(0.0f, 0.0f);
-      const uint64_t nmu2 = f2_pack(-mu, -mu), rs2 = f2_pack(rs, rs);
+          if (c < nchunks && live) {
+            const Vec xr = sx[c], dr = sd[c];
+            const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xr);
+            const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dr);
+            float gv[kW];
 #pragma unroll
-      for (int i = 0; i < kIt; ++i) {
-        if (lane + 32 * i < nchunks) {
-          const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xr[i]);
-          const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dr[i]);
+            for (int j4 = 0; j4 < kW / 4; ++j4) {
+              const float4 g4 = reinterpret_cast<const float4*>(sgam + c * kW)[j4];
+              gv[4 * j4] = g4.x; gv[4 * j4 + 1] = g4.y; gv[4 * j4 + 2] = g4.z; gv[4 * j4 + 3] = g4.w;
+            }
 #pragma unroll
-          for (int j = 0; j < kP; ++j) {
-            const uint64_t d2 = f2_pack(bf16_lo(dw[j]), bf16_hi(dw[j]));
-            const uint64_t xh = f2_mul(f2_add(f2_pack(bf16_lo(xw[j]), bf16_hi(xw[j])), nmu2), rs2);
-            const uint64_t gd = f2_mul(d2, g2[i][j]);
-            s1p = f2_add(s1p, gd);
-            s2p = f2_fma(gd, xh, s2p);
-            ag2[i][j] = f2_fma(d2, xh, ag2[i][j]);
-            ab2[i][j] = f2_add(ab2[i][j], d2);
-            xh2[i][j] = xh;
-            gd2[i][j] = gd;
+            for (int j = 0; j < kP; ++j) {
+              const uint64_t d2 = f2_pack(bf16_lo(dw[j]), bf16_hi(dw[j]));
+              const uint64_t xh = f2_mul(f2_add(f2_pack(bf16_lo(xw[j]), bf16_hi(xw[j])), nmu2), rs2);
+              const uint64_t gd = f2_mul(d2, f2_pack(gv[2 * j], gv[2 * j + 1]));
+              s1p = f2_add(s1p, gd);
+              s2p = f2_fma(gd, xh, s2p);
+              ag2[i][j] = f2_fma(d2, xh, ag2[i][j]);
+              ab2[i][j] = f2_add(ab2[i][j], d2);
+              xh2[i][j] = xh;
+              gd2[i][j] = gd;
+            }
           }
         }
       }
+      __syncwarp();  // every lane has read its part: hand the slot back to the producer
+      if (lane == 0) mbar_arrive(&empty[s]);
+      if (++s == stages) { s = 0; ph ^= 1u; }
+      if (!live) continue;
       float s1, s2;
       {
         float a0, a1, b0, b1;
@@ -698,13 +703,13 @@ int launch_layernorm_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  const int rows = dbias ? 8 : 15;
+  const int rows = dbias ? 8 : (g_ln_bwd_rows == 14 ? 14 : 15);  // (encoder form: 15 row warps at 122 registers, no spills)
   const int nsum = dbias ? 3 : 2;
   int ctas = (M + rows - 1) / rows;
   if (ctas > sms) ctas = sms;
   if (ctas > kLnBwdCtas) ctas = kLnBwdCtas;
   const int stage_bytes = 2 * rows * D * 2;
-  const int fixed = rows * nsum * D * 4 + 2 * kLnBwdMaxStages * 8 + 128;
+  const int fixed = rows * nsum * D * 4 + D * 4 + 2 * kLnBwdMaxStages * 8 + 128;
   int stages = (227 * 1024 - fixed) / stage_bytes;
   if (stages > kLnBwdMaxStages) stages = kLnBwdMaxStages;
   if (stages < 2) return WM_ERR_SHAPE;
@@ -712,7 +717,8 @@ int launch_layernorm_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const 
   if (drop_thresh && static_cast<uint64_t>(M) * static_cast<uint64_t>((D + 15) / 16) * 4ull > 0xFFFFFFFFull) return WM_ERR_SHAPE;
   const bool w4 = g_ln_bwd_width ? g_ln_bwd_width == 4 : false;  // ("ln_bwd_width" option; A/B in profiles/r02_ln_width_ab.txt)
   auto kern = dbias ? (w4 ? layernorm_bwd_kernel<true, 8, 4> : layernorm_bwd_kernel<true, 8, 8>)
-                    : (w4 ? layernorm_bwd_kernel<false, 15, 4> : layernorm_bwd_kernel<false, 15, 8>);
+                    : rows == 15 ? (w4 ? layernorm_bwd_kernel<false, 15, 4> : layernorm_bwd_kernel<false, 15, 8>)
+                                 : (w4 ? layernorm_bwd_kernel<false, 14, 4> : layernorm_bwd_kernel<false, 14, 8>);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return WM_ERR_CUDA;
   kern<<<ctas, 32 * (rows + 1), smem, stream>>>(dy, x, gamma, mean, rstd, dx, dx_drop, M, D, drop_thresh, drop_scale,
                                                 drop_keys(seed, stream_id), workspace, stages);
