@@ -499,9 +499,10 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     }
   } else {
     // Packed fp32 arithmetic throughout (FADD2 / FMUL2 / FFMA2 on register pairs: even element low, odd element high):
-    // ~11 instead of ~20 issued instructions per element. Measured effect: none on the 15-row form (0.207 -> 0.209 ms at
-    // the large shape, 4.1 TB/s), -3 % on the 8-row form -- so the kernel is NOT issue-bound; what remains is the
-    // per-row dependency chain (barrier wait -> shared loads -> two warp reductions -> stores) at 15 rows per SM.
+    // ~11 instead of ~20 issued instructions per element. By itself that changed nothing (0.207 -> 0.209 ms at the large
+    // shape): the ncu source view then showed what did hold the kernel back -- 18 spilled registers reloaded in the row
+    // loop, and the row statistics' global-load latency exposed on every row (see below). With both gone: 0.146 ms,
+    // 5.9 TB/s = 90 % of the measured copy bandwidth (profiles/r02_ln_bwd_v2.txt).
     constexpr int kP = kW / 2;
     uint64_t ag2[kIt][kP], ab2[kIt][kP];
     float ad[kBias ? kIt : 1][kW];
@@ -523,18 +524,20 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     const uint32_t add2 = drop_add2(drop_thresh);
     int s = 0;
     uint32_t ph = 0;
-    float mu_n = 0.0f, rs_n = 0.0f;  // row statistics one block ahead
-    {
-      const int r = blockIdx.x * kRows + warp;
-      if (blockIdx.x < nblk && r < M) { mu_n = __ldg(mean + r); rs_n = __ldg(rstd + r); }
-    }
-    for (int b = blockIdx.x; b < nblk; b += gridDim.x) {
+    // Row statistics: lane l holds those of this warp's row 32 * (it / 32) + l blocks ahead, one shuffle per row hands
+    // them out. (Loaded one block ahead as scalars they are warp-uniform, the compiler moves them to uniform registers
+    // right behind the load -- and that R2UR waited out the whole global-load latency on every row: 19 % of the
+    // kernel's stall samples in the ncu source view.)
+    float mu_v = 0.0f, rs_v = 0.0f;
+    int it = 0;
+    for (int b = blockIdx.x; b < nblk; b += gridDim.x, ++it) {
       const int row = b * kRows + warp;
-      const float mu = mu_n, rs = rs_n;
-      {
-        const int rn = (b + static_cast<int>(gridDim.x)) * kRows + warp;
-        if (rn < M) { mu_n = __ldg(mean + rn); rs_n = __ldg(rstd + rn); }
+      if ((it & 31) == 0) {
+        const long long r = (static_cast<long long>(b) + static_cast<long long>(lane) * gridDim.x) * kRows + warp;
+        mu_v = r < M ? __ldg(mean + r) : 0.0f;
+        rs_v = r < M ? __ldg(rstd + r) : 0.0f;
       }
+      const float mu = __shfl_sync(0xffffffffu, mu_v, it & 31), rs = __shfl_sync(0xffffffffu, rs_v, it & 31);
       mbar_wait(&full[s], ph, 42);
       const bool live = row < M;  // warp-uniform (tail block)
       uint64_t xh2[kIt][kP], gd2[kIt][kP];
