@@ -608,6 +608,25 @@ struct AttnBwdGeom {
 };
 
 // per (batch, head): two planes of kSP floats, x[q] = -lse * log2(e) + log2(drop_scale) and
+// sum over 4 * kN consecutive bf16 elements of o * d, same summation order as the run-time loop in the kernel below
+template <int kN>
+WM_DEVICE float attn_row_dot(const uint2* __restrict__ po, const uint2* __restrict__ pd) {
+  uint2 o[kN], d[kN];
+#pragma unroll
+  for (int p = 0; p < kN; ++p) {
+    o[p] = __ldg(po + p);
+    d[p] = __ldg(pd + p);
+  }
+  float acc = 0.0f;
+#pragma unroll
+  for (int p = 0; p < kN; ++p) {
+    acc = fmaf(bf16_lo(o[p].x), bf16_lo(d[p].x), acc);
+    acc = fmaf(bf16_hi(o[p].x), bf16_hi(d[p].x), acc);
+    acc = fmaf(bf16_lo(o[p].y), bf16_lo(d[p].y), acc);
+    acc = fmaf(bf16_hi(o[p].y), bf16_hi(d[p].y), acc);
+  }
+  return acc;
+}
 // y[q] = -(sum_d dO * O) * scale / drop_scale; rows >= S are zero. Planes (not interleaved pairs) so that one 16-byte
 // shared-memory load in the backward kernel yields four consecutive x (or y): aligned register pairs for the packed
 // fp32 instructions. One thread per (b, q, h); h runs fastest so a warp reads whole token rows.
@@ -625,13 +644,22 @@ __global__ void attn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ ctx, con
     const size_t off = (static_cast<size_t>(b) * S + q) * (static_cast<size_t>(H) * dh) + static_cast<size_t>(h) * dh;
     const uint2* po = reinterpret_cast<const uint2*>(ctx + off);
     const uint2* pd = reinterpret_cast<const uint2*>(dctx + off);
-    float acc = 0.0f;
-    for (int p = 0; p < dh / 4; ++p) {
-      const uint2 o = __ldg(po + p), d = __ldg(pd + p);
-      acc = fmaf(bf16_lo(o.x), bf16_lo(d.x), acc);
-      acc = fmaf(bf16_hi(o.x), bf16_hi(d.x), acc);
-      acc = fmaf(bf16_lo(o.y), bf16_lo(d.y), acc);
-      acc = fmaf(bf16_hi(o.y), bf16_hi(d.y), acc);
+    float acc;
+    switch (dh) {  // the head widths of the model table get all their loads in flight at once (a run-time trip count
+                   // serialises load -> fma: the kernel ran at 3.7 TB/s)
+      case 12: acc = attn_row_dot<3>(po, pd); break;
+      case 20: acc = attn_row_dot<5>(po, pd); break;
+      case 28: acc = attn_row_dot<7>(po, pd); break;
+      case 36: acc = attn_row_dot<9>(po, pd); break;
+      default:
+        acc = 0.0f;
+        for (int p = 0; p < dh / 4; ++p) {
+          const uint2 o = __ldg(po + p), d = __ldg(pd + p);
+          acc = fmaf(bf16_lo(o.x), bf16_lo(d.x), acc);
+          acc = fmaf(bf16_hi(o.x), bf16_hi(d.x), acc);
+          acc = fmaf(bf16_lo(o.y), bf16_lo(d.y), acc);
+          acc = fmaf(bf16_hi(o.y), bf16_hi(d.y), acc);
+        }
     }
     ox = -lse[(static_cast<size_t>(b) * H + h) * S + q] * 1.4426950408889634f + log2f(drop_scale);
     oy = -acc * scale / drop_scale;
