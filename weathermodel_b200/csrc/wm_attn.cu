@@ -669,6 +669,68 @@ __global__ void attn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ ctx, con
   base[kSP + q] = oy;
 }
 
+// The same statistics with whole-row accesses (dh % 4 == 0, D % 8 == 0, D <= 1024): a CTA takes 32 consecutive query rows
+// of one sequence; a warp reads a token row of ctx and dctx with coalesced 16-byte loads (the per-(b, q, h) kernel
+// above reads each row as 8-byte pieces 72 bytes apart: every load instruction touches 18 cache lines, nine times
+// over), forms the products, and leaves one partial sum per FOUR elements in shared memory -- a head is a whole number
+// of those; one thread per (query, head) then adds up its dh / 4 partials and writes x and y, 32 queries = 128 bytes
+// per head and plane.
+__global__ void __launch_bounds__(256)
+attn_bwd_stats_rows_kernel(const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
+                           const float* __restrict__ lse, float* __restrict__ stats, int S, int H, int dh, float scale,
+                           float drop_scale) {
+  extern __shared__ float hs[];  // [32 rows][D / 4 + 1]
+  const int D = H * dh, nq = D >> 2, pitch = nq + 1, nchunks = D >> 3;
+  const int b = blockIdx.y, q0 = blockIdx.x * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int ql = warp * 4 + r, q = q0 + ql;
+    if (q < S) {  // warp-uniform
+      const size_t off = (static_cast<size_t>(b) * S + q) * static_cast<size_t>(D);
+      const uint4* po = reinterpret_cast<const uint4*>(ctx + off);
+      const uint4* pd = reinterpret_cast<const uint4*>(dctx + off);
+      uint4 o[4], d[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunks) { o[i] = __ldg(po + c); d[i] = __ldg(pd + c); }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunks) {
+          float lo = bf16_lo(o[i].x) * bf16_lo(d[i].x);
+          lo = fmaf(bf16_hi(o[i].x), bf16_hi(d[i].x), lo);
+          lo = fmaf(bf16_lo(o[i].y), bf16_lo(d[i].y), lo);
+          lo = fmaf(bf16_hi(o[i].y), bf16_hi(d[i].y), lo);
+          float hi = bf16_lo(o[i].z) * bf16_lo(d[i].z);
+          hi = fmaf(bf16_hi(o[i].z), bf16_hi(d[i].z), hi);
+          hi = fmaf(bf16_lo(o[i].w), bf16_lo(d[i].w), hi);
+          hi = fmaf(bf16_hi(o[i].w), bf16_hi(d[i].w), hi);
+          hs[ql * pitch + 2 * c] = lo;
+          hs[ql * pitch + 2 * c + 1] = hi;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int per = dh >> 2;
+  for (int t = threadIdx.x; t < 32 * H; t += blockDim.x) {
+    const int ql = t & 31, h = t >> 5, q = q0 + ql;
+    float ox = 0.0f, oy = 0.0f;
+    if (q < S) {
+      float acc = 0.0f;
+      for (int j = 0; j < per; ++j) acc += hs[ql * pitch + h * per + j];
+      ox = -lse[(static_cast<size_t>(b) * H + h) * S + q] * 1.4426950408889634f + log2f(drop_scale);
+      oy = -acc * scale / drop_scale;
+    }
+    float* base = stats + (static_cast<size_t>(b) * H + h) * (2 * kSP);
+    base[q] = ox;
+    base[kSP + q] = oy;
+  }
+}
+
 template <int NCH, bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
@@ -1080,8 +1142,14 @@ static int launch_bwd_t(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, cons
   if (rc != WM_OK) return rc;
   {
     const long long total = static_cast<long long>(B) * kSP * H;
-    attn_bwd_stats_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(ctx, dctx, lse, stats, B, S, H, dh,
-                                                                                         scale, dscale);
+    if ((dh & 3) == 0 && (D & 7) == 0 && D <= 1024 && (reinterpret_cast<uintptr_t>(ctx) & 15u) == 0 &&
+        (reinterpret_cast<uintptr_t>(dctx) & 15u) == 0 && B <= 65535) {
+      const int smem_stats = 32 * (D / 4 + 1) * static_cast<int>(sizeof(float));
+      attn_bwd_stats_rows_kernel<<<dim3(kSP / 32, B), 256, smem_stats, stream>>>(ctx, dctx, lse, stats, S, H, dh, scale, dscale);
+    } else {
+      attn_bwd_stats_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(ctx, dctx, lse, stats, B, S, H, dh,
+                                                                                           scale, dscale);
+    }
     WM_COUNT_LAUNCH();
   }
   const int smem = AttnBwdGeom<NCH>::kSmem;

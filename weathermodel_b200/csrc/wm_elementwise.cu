@@ -362,6 +362,10 @@ int g_ln_bwd_rows = 0;   // 0 = default, 14 or 15 row warps per CTA in the encod
 int g_ln_fwd_width = 0;  // 0 = auto (ln_pick_width), 4 or 8 forced -- wm_set_option("ln_fwd_width", v)
 static inline int ln_pick_width(int D) { return ln_slots(D, 4) < ln_slots(D, 8) ? 4 : 8; }
 
+// kRows rows per warp: the loads of ALL its rows are issued before the first reduction, so a warp keeps kRows x 1152 B
+// (D = 576) in flight instead of one row's -- at one row per warp and 32 resident warps an SM had 36 KB of reads in
+// flight, short of what 6.5 TB/s at ~1 us latency asks for (the kernel ran at 4.7 TB/s).
+constexpr int kLnFwdRows = 2;
 template <int kW>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
@@ -369,60 +373,65 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
                      float* __restrict__ rstd_out, int M, int D, float eps) {
   using Vec = typename LnVec<kW>::T;
   constexpr int kIt = (kLnMaxChunks * 8) / kW;  // passes for the widest supported row
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kLnFwdRows;
   const int lane = threadIdx.x & 31;
-  if (row >= M) return;
+  if (row0 >= M) return;
   const int nchunks = D / kW;
-  float v[kIt][kW];
-  const Vec* xr = reinterpret_cast<const Vec*>(x + static_cast<size_t>(row) * D);
+  Vec raw[kLnFwdRows][kIt];
 #pragma unroll
-  for (int i = 0; i < kIt; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nchunks) {
-      const Vec r = __ldg(xr + c);
-      ln_unpack_w<kW>(r, v[i]);
-    } else {
+  for (int r = 0; r < kLnFwdRows; ++r) {
+    const Vec* xr = reinterpret_cast<const Vec*>(x + static_cast<size_t>(row0 + r) * D);
 #pragma unroll
-      for (int j = 0; j < kW; ++j) v[i][j] = 0.0f;
+    for (int i = 0; i < kIt; ++i) {
+      const int c = lane + 32 * i;
+      raw[r][i] = (c < nchunks && row0 + r < M) ? __ldg(xr + c) : Vec{};
     }
   }
-  float s = 0.0f;
 #pragma unroll
-  for (int i = 0; i < kIt; ++i)
+  for (int r = 0; r < kLnFwdRows; ++r) {
+    const int row = row0 + r;
+    if (row >= M) break;  // warp-uniform
+    float v[kIt][kW];
 #pragma unroll
-    for (int j = 0; j < kW; ++j) s += v[i][j];
-  const float mean = warp_sum(s) / static_cast<float>(D);
-  float q = 0.0f;
+    for (int i = 0; i < kIt; ++i) ln_unpack_w<kW>(raw[r][i], v[i]);  // (chunks past the row are zero)
+    float s = 0.0f;
 #pragma unroll
-  for (int i = 0; i < kIt; ++i) {
-    if (lane + 32 * i < nchunks) {
+    for (int i = 0; i < kIt; ++i)
 #pragma unroll
-      for (int j = 0; j < kW; ++j) {
-        const float d = v[i][j] - mean;
-        q = fmaf(d, d, q);
+      for (int j = 0; j < kW; ++j) s += v[i][j];
+    const float mean = warp_sum(s) / static_cast<float>(D);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kIt; ++i) {
+      if (lane + 32 * i < nchunks) {
+#pragma unroll
+        for (int j = 0; j < kW; ++j) {
+          const float d = v[i][j] - mean;
+          q = fmaf(d, d, q);
+        }
       }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + eps);
-  if (lane == 0) {
-    if (mean_out) mean_out[row] = mean;
-    if (rstd_out) rstd_out[row] = rstd;
-  }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
 #pragma unroll
-  for (int i = 0; i < kIt; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nchunks) {
-      float g[kW], b[kW], o[kW];
+    for (int i = 0; i < kIt; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        float g[kW], b[kW], o[kW];
 #pragma unroll
-      for (int j4 = 0; j4 < kW / 4; ++j4) {
-        const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + c * kW) + j4);
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(beta + c * kW) + j4);
-        g[4 * j4] = gv.x; g[4 * j4 + 1] = gv.y; g[4 * j4 + 2] = gv.z; g[4 * j4 + 3] = gv.w;
-        b[4 * j4] = bv.x; b[4 * j4 + 1] = bv.y; b[4 * j4 + 2] = bv.z; b[4 * j4 + 3] = bv.w;
+        for (int j4 = 0; j4 < kW / 4; ++j4) {
+          const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + c * kW) + j4);
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(beta + c * kW) + j4);
+          g[4 * j4] = gv.x; g[4 * j4 + 1] = gv.y; g[4 * j4 + 2] = gv.z; g[4 * j4 + 3] = gv.w;
+          b[4 * j4] = bv.x; b[4 * j4 + 1] = bv.y; b[4 * j4 + 2] = bv.z; b[4 * j4 + 3] = bv.w;
+        }
+#pragma unroll
+        for (int j = 0; j < kW; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, g[j], b[j]);
+        reinterpret_cast<Vec*>(y + static_cast<size_t>(row) * D)[c] = ln_pack_w<kW>(o);
       }
-#pragma unroll
-      for (int j = 0; j < kW; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, g[j], b[j]);
-      reinterpret_cast<Vec*>(y + static_cast<size_t>(row) * D)[c] = ln_pack_w<kW>(o);
     }
   }
 }
@@ -430,8 +439,8 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
 int launch_layernorm_fwd(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y,
                          float* mean, float* rstd, int M, int D, float eps, cudaStream_t stream) {
   if (M <= 0 || D <= 0 || (D & 7) || D > kLnMaxChunks * 256) return WM_ERR_SHAPE;
-  if ((g_ln_fwd_width ? g_ln_fwd_width : ln_pick_width(D)) == 4) layernorm_fwd_kernel<4><<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, mean, rstd, M, D, eps);
-  else layernorm_fwd_kernel<8><<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, mean, rstd, M, D, eps);
+  if ((g_ln_fwd_width ? g_ln_fwd_width : ln_pick_width(D)) == 4) layernorm_fwd_kernel<4><<<(M + 8 * kLnFwdRows - 1) / (8 * kLnFwdRows), 256, 0, stream>>>(x, gamma, beta, y, mean, rstd, M, D, eps);
+  else layernorm_fwd_kernel<8><<<(M + 8 * kLnFwdRows - 1) / (8 * kLnFwdRows), 256, 0, stream>>>(x, gamma, beta, y, mean, rstd, M, D, eps);
   WM_COUNT_LAUNCH();
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
