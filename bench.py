@@ -413,23 +413,27 @@ def run_ours(args, rank, world, local_rank):
         variant, _ = ops.tune_gemm_call(a, bmat, bias=bias, relu=True)
         for _ in range(3):
             ops.gemm_tn(a, bmat, bias=bias, relu=True)
-        reps = 20
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
-            ops.gemm_tn(a, bmat, bias=bias, relu=True)
-        e1.record()
-        torch.cuda.synchronize()
-        gemm_ms = e0.elapsed_time(e1) / reps
+        # five batches of 20 launches; the best batch average is reported, the way MEASURED_PEAKS.json's burst figure is the
+        # best of ten (kernel timed alone: the first batches after a cold start run below the clocks the later ones reach)
+        reps, batches = 20, []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                ops.gemm_tn(a, bmat, bias=bias, relu=True)
+            e1.record()
+            torch.cuda.synchronize()
+            batches.append(e0.elapsed_time(e1) / reps)
+        gemm_ms = min(batches)
         achieved = 2.0 * M * FF * D / (gemm_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": f"gemm_tn{'2' if variant[0] else ''}_kernel<bf16> (linear1: M x 4D x D, bias+ReLU epilogue)",
                 "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((M, FF, D)),
                 "traffic_source": "constant from the committed ncu --set full capture (profiles/), not measured in this run",
                 "peak_source": pk["source"] + " burst (kernel timed alone)",
-                "launch_ms": gemm_ms, "shape": [M, FF, D],
-                "when": "before the step timing, on the launching stream, 20 launches between two CUDA events"}
+                "launch_ms": gemm_ms, "launch_ms_batches": [round(v, 4) for v in batches], "shape": [M, FF, D],
+                "when": "before the step timing, on the launching stream: five batches of 20 launches between two CUDA events, best batch average"}
         roof["variant"] = {"two_cta": variant[0], "epilogue_warps": variant[1], "stores": ("direct", "staged", "tma")[variant[2]]}
         del a, bmat
 
