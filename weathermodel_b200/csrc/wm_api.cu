@@ -46,13 +46,13 @@ int wm_debug_ticks(long long* out_host, int n) {
   return cudaMemcpyFromSymbol(out_host, g_wm_ticks, sizeof(long long) * n) == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
-namespace wm { extern int g_gemm_two_cta, g_gemm_epi_warps, g_gemm_staged, g_ln_bwd_width, g_ln_fwd_width, g_wgrad_bn, g_ln_bwd_rows; }
+namespace wm { extern int g_gemm_two_cta, g_gemm_epi_warps, g_gemm_staged, g_ln_bwd_width, g_ln_fwd_width, g_wgrad_bn, g_ln_bwd_rows, g_wgrad_mh; }
 int wm_set_option(const char* name, int value) {
   if (!name) return WM_ERR_ARG;
   struct Opt { const char* name; int* slot; };
   const Opt opts[] = {{"gemm_two_cta", &wm::g_gemm_two_cta}, {"gemm_epi_warps", &wm::g_gemm_epi_warps},
                       {"gemm_staged", &wm::g_gemm_staged}, {"ln_bwd_width", &wm::g_ln_bwd_width},
-                      {"ln_fwd_width", &wm::g_ln_fwd_width}, {"wgrad_bn", &wm::g_wgrad_bn}, {"ln_bwd_rows", &wm::g_ln_bwd_rows}};
+                      {"ln_fwd_width", &wm::g_ln_fwd_width}, {"wgrad_bn", &wm::g_wgrad_bn}, {"ln_bwd_rows", &wm::g_ln_bwd_rows}, {"wgrad_mh", &wm::g_wgrad_mh}};
   for (const Opt& o : opts) {
     const char* a = name;
     const char* b = o.name;

@@ -1113,24 +1113,31 @@ struct WgSmemTail {
 __global__ void __launch_bounds__(kWgradThreads, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   int Mtok, int Nout, int Kout, int BN, int tok_per_split, float* __restrict__ partial,
-                  float* __restrict__ bias_partial) {
+                  float* __restrict__ bias_partial, int mh, int stages) {
+  // mh = 2: the CTA multiplies TWO 128-row tiles of A^T (rows 256 x and 256 x + 128 of Nout) with the same B tile, each into
+  // its own accumulator (TMEM columns [0, 256) and [256, 512)). What holds this kernel back is how much operand data an
+  // SM can take in per clock: one 128 x 192 tile needs 40 KB per 384 MMA cycles (104 B/clk; ncu: ~69 B/clk achieved, tensor
+  // pipe 71 % active, the MMA warp waiting for operands a third of its time) -- two tiles share the B half of that: 56 KB
+  // per 768 cycles = 73 B/clk. (A CTA-pair version saved less and an L2 prefetch made it worse: profiles/r02_wgrad_bn_ab.txt.)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_align_up(smem_raw, 1024);
-  const uint32_t a_bytes = kBM * kBK * 2;                             // 2 boxes of 64 tok x 64 n
+  const uint32_t a_half = kBM * kBK * 2;                              // 2 boxes of 64 tok x 64 n
+  const uint32_t a_bytes = static_cast<uint32_t>(mh) * a_half;
   const uint32_t b_bytes = static_cast<uint32_t>(BN) * kBK * 2;       // BN/64 boxes
   // Fused bias gradient (column sums of A over the tokens): an all-ones 64 x 64 chunk sits right behind the B
   // tile of every stage, so the k_blk == 0 CTAs simply run their MMAs 16 columns wider (N = BN + 16) and find
   // sum_t A[t, n] in accumulator column BN -- no separate pass over the activation gradient. With BN = 256 (the
   // instruction's widest N) the ones chunk gets its own N = 16 MMA per k-step into columns [256, 272) instead.
   const bool fuse_bias = bias_partial != nullptr;
-  const bool wide_bias = fuse_bias && BN == 256;
+  const bool wide_bias = fuse_bias && BN == 256;  // (host: mh == 1 then -- two 272-column accumulators do not fit)
   const uint32_t ones_bytes = fuse_bias ? 8192u : 0u;
   const uint32_t stage_bytes = a_bytes + b_bytes + ones_bytes;
-  WgSmemTail* tail = reinterpret_cast<WgSmemTail*>(smem + static_cast<size_t>(kWgStages) * stage_bytes);
+  WgSmemTail* tail = reinterpret_cast<WgSmemTail*>(smem + static_cast<size_t>(stages) * stage_bytes);
 
   const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
-  const int n_blk = blockIdx.x;  // tile over Nout (UMMA M side)
+  const int n_blk0 = blockIdx.x * mh;  // first 128-row tile over Nout (UMMA M side) of this CTA
+  const int nh = min(mh, (Nout + kBM - 1) / kBM - n_blk0);  // tiles it really has (the last CTA of an odd count: one)
   const int k_blk = blockIdx.y;  // tile over Kout (UMMA N side)
   const int split = blockIdx.z;
   const int tok0 = split * tok_per_split;
@@ -1140,7 +1147,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < kWgStages; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(&tail->full[s], 1);
       mbar_init(&tail->empty[s], 1);
     }
@@ -1150,7 +1157,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) tmem_alloc<512>(&tail->tmem_base);
   if (fuse_bias && k_blk == 0) {
     const uint4 ones = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);  // bf16 1.0 x 8
-    for (int i = threadIdx.x; i < kWgStages * 512; i += blockDim.x)
+    for (int i = threadIdx.x; i < stages * 512; i += blockDim.x)
       *reinterpret_cast<uint4*>(smem + static_cast<size_t>(i >> 9) * stage_bytes + a_bytes + b_bytes + (i & 511) * 16) = ones;
     fence_proxy_async_smem();
   }
@@ -1166,15 +1173,15 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&tail->empty[s], ph ^ 1u, 21);
         uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
-        mbar_arrive_expect_tx(&tail->full[s], a_bytes + b_bytes);
+        mbar_arrive_expect_tx(&tail->full[s], static_cast<uint32_t>(nh) * a_half + b_bytes);
         const int t = tok0 + kb * kBK;
         // NOTE: token rows past tok1 but < Mtok would belong to the next split; tok_per_split is a
         // multiple of 64 so a box never straddles a split boundary; rows >= Mtok are zero-filled.
-        for (int c = 0; c < kBM / 64; ++c)
-          tma_load_2d(sa + c * 8192, &tmA, &tail->full[s], n_blk * kBM + c * 64, t);
+        for (int c = 0; c < nh * (kBM / 64); ++c)
+          tma_load_2d(sa + c * 8192, &tmA, &tail->full[s], n_blk0 * kBM + c * 64, t);
         for (int c = 0; c < BN / 64; ++c)
           tma_load_2d(sa + a_bytes + c * 8192, &tmB, &tail->full[s], k_blk * BN + c * 64, t);
-        if (++s == kWgStages) { s = 0; ph ^= 1u; }
+        if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -1195,18 +1202,20 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int k = 0; k < kBK / 16; ++k) {
         umma_ss_warp(tmem_base, umma_desc_advance(da_s, k * 2048), umma_desc_advance(db_s, k * 2048), idesc,
                      (kb | k) != 0 ? 1u : 0u);
+        if (nh == 2)  // (warp-uniform) the second A^T tile against the same B tile
+          umma_ss_warp(tmem_base + 256, umma_desc_advance(da_s, a_half + k * 2048), umma_desc_advance(db_s, k * 2048), idesc,
+                       (kb | k) != 0 ? 1u : 0u);
         if (ones && wide_bias)  // (warp-uniform) the all-ones chunk as a second, 16-column product
           umma_ss_warp(tmem_base + 256, umma_desc_advance(da_s, k * 2048), umma_desc_advance(db_s, b_bytes + k * 2048), idesc_ones,
                        (kb | k) != 0 ? 1u : 0u);
       }
       umma_commit_warp(&tail->empty[s]);
-      if (++s == kWgStages) { s = 0; ph ^= 1u; }
+      if (++s == stages) { s = 0; ph ^= 1u; }
     }
     umma_commit_warp(&tail->acc_full);
   } else {
     const int q = warp & 3;
     float* out = partial + static_cast<size_t>(split) * Nout * Kout;
-    const int row0 = n_blk * kBM + q * 32;
     if (num_kb > 0) {
       mbar_wait(&tail->acc_full, 0, 24);
       tc_fence_after();
@@ -1217,44 +1226,49 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // for a 128 x 192 tile, against ~100k cycles of MMAs per work item.
     const uint32_t pitch = static_cast<uint32_t>(BN) * 4u + 16u;
     uint8_t* stage = smem + static_cast<uint32_t>(q) * 32u * pitch;
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      if (num_kb > 0) {
-        tmem_ld32(tmem_base + c0 + (static_cast<uint32_t>(q * 32) << 16), v);
-        tmem_ld_wait();
-      } else {
+    for (int h = 0; h < nh; ++h) {
+      const int row0 = (n_blk0 + h) * kBM + q * 32;
+      const uint32_t tcol = tmem_base + static_cast<uint32_t>(h) * 256u + (static_cast<uint32_t>(q * 32) << 16);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        if (num_kb > 0) {
+          tmem_ld32(tcol + c0, v);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
-      }
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
 #pragma unroll
-      for (int g = 0; g < 8; ++g)
-        *reinterpret_cast<uint4*>(stage + lane * pitch + (c0 + g * 4) * 4) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-    }
-    __syncwarp();
-    {
-      const int u = BN >> 2;  // 16-byte units per row
-      const int q32 = 32 / u, m32u = 32 - q32 * u;
-      int r = lane / u, piece = lane - r * u;
-      for (int k = 0; k < u; ++k) {
-        const int n = k_blk * BN + piece * 4;
-        const uint4 val = *reinterpret_cast<const uint4*>(stage + r * pitch + piece * 16);
-        if (row0 + r < Nout && n < Kout)  // Kout % 4 == 0 (host-checked)
-          *reinterpret_cast<uint4*>(out + static_cast<size_t>(row0 + r) * Kout + n) = val;
-        r += q32;
-        piece += m32u;
-        if (piece >= u) { piece -= u; ++r; }
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(stage + lane * pitch + (c0 + g * 4) * 4) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
       }
-    }
-    const int row = row0 + lane;
-    if (fuse_bias && k_blk == 0) {
-      uint32_t v[16];
-      if (num_kb > 0) {
-        tmem_ld16(tmem_base + BN + (static_cast<uint32_t>(q * 32) << 16), v);
-        tmem_ld_wait();
-      } else {
-        v[0] = 0u;
+      __syncwarp();
+      {
+        const int u = BN >> 2;  // 16-byte units per row
+        const int q32 = 32 / u, m32u = 32 - q32 * u;
+        int r = lane / u, piece = lane - r * u;
+        for (int k = 0; k < u; ++k) {
+          const int n = k_blk * BN + piece * 4;
+          const uint4 val = *reinterpret_cast<const uint4*>(stage + r * pitch + piece * 16);
+          if (row0 + r < Nout && n < Kout)  // Kout % 4 == 0 (host-checked)
+            *reinterpret_cast<uint4*>(out + static_cast<size_t>(row0 + r) * Kout + n) = val;
+          r += q32;
+          piece += m32u;
+          if (piece >= u) { piece -= u; ++r; }
+        }
       }
-      if (row < Nout) bias_partial[static_cast<size_t>(split) * Nout + row] = __uint_as_float(v[0]);
+      __syncwarp();  // the next half overwrites the staging block
+      const int row = row0 + lane;
+      if (fuse_bias && k_blk == 0) {
+        uint32_t v[16];
+        if (num_kb > 0) {
+          tmem_ld16(tcol + BN, v);
+          tmem_ld_wait();
+        } else {
+          v[0] = 0u;
+        }
+        if (row < Nout) bias_partial[static_cast<size_t>(split) * Nout + row] = __uint_as_float(v[0]);
+      }
     }
   }
   tc_fence_before();
@@ -1316,7 +1330,15 @@ __global__ void wgrad_reduce4_kernel(const float4* __restrict__ partial, float4*
 // waves of SMs (the first plan used ceil(2 * SMs / tiles) and lost up to a third of the machine to a nearly empty
 // last wave: 300 items on 148 SMs = 3 waves at 68 %), with a mild preference for fewer partial tiles to reduce.
 int g_wgrad_bn = 0;  // "wgrad_bn": 0 = the rule below, 64..256 = forced tile width (A/B runs)
-int wgrad_plan(int Mtok, int Nout, int Kout, int* BN, int* splits, int* tok_per_split) {
+int g_wgrad_mh = 0;  // "wgrad_mh": 0 = the rule below, 1 / 2 = A^T tiles per CTA forced
+// A^T tiles (128 rows of Nout) per CTA: two where both accumulators fit in TMEM (tile width <= 240 with the bias column)
+// and the problem is big enough to fill the machine with half as many CTAs per token split
+static int wgrad_pick_mh(int Mtok, int Nout, int bn) {
+  int mh = (bn <= 192 && Nout > kBM && Mtok >= 16384) ? 2 : 1;
+  if (g_wgrad_mh == 1 || g_wgrad_mh == 2) mh = (bn <= 192 && Nout > kBM) ? g_wgrad_mh : 1;
+  return mh;
+}
+int wgrad_plan(int Mtok, int Nout, int Kout, int* BN, int* splits, int* tok_per_split, int* mh_out = nullptr) {
   // tile width over Kout (64-column TMA boxes): 256 for wide outputs it divides, 192 where that divides Kout (the D = 576
   // shapes were tuned on it: 256-wide tiles there lose 15-25 % to the padded third tile), otherwise
   // the width that minimises tiles x (width + ~32 columns of per-tile overhead), the wider one on a tie
@@ -1336,7 +1358,9 @@ int wgrad_plan(int Mtok, int Nout, int Kout, int* BN, int* splits, int* tok_per_
     }
   }
   if (g_wgrad_bn >= 64 && g_wgrad_bn <= 256 && (g_wgrad_bn & 63) == 0) bn = g_wgrad_bn;
-  const int tiles = ((Nout + kBM - 1) / kBM) * ((Kout + bn - 1) / bn);
+  const int mh = wgrad_pick_mh(Mtok, Nout, bn);
+  if (mh_out) *mh_out = mh;
+  const int tiles = (((Nout + kBM - 1) / kBM + mh - 1) / mh) * ((Kout + bn - 1) / bn);
   const int kb_total = (Mtok + kBK - 1) / kBK;
   const int sms = num_sms();
   int best_sp = 1;
@@ -1386,8 +1410,8 @@ static int launch_gemm_wgrad_impl(const void* A, int lda, const void* B, int ldb
   if (Mtok <= 0 || Nout <= 0 || Kout <= 0) return WM_ERR_SHAPE;
   if (rows_valid > Nout || cols_valid > Kout || ld_dw < cols_valid) return WM_ERR_SHAPE;
   if ((Nout & 7) || (Kout & 7) || (lda & 7) || (ldb & 7)) return WM_ERR_ALIGN;
-  int BN, splits, tps;
-  wgrad_plan(Mtok, Nout, Kout, &BN, &splits, &tps);
+  int BN, splits, tps, mh;
+  wgrad_plan(Mtok, Nout, Kout, &BN, &splits, &tps, &mh);
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16(&tmA, A, Mtok, Nout, lda, 64, kBK);
   if (rc) return rc;
@@ -1395,12 +1419,15 @@ static int launch_gemm_wgrad_impl(const void* A, int lda, const void* B, int ldb
   if (rc) return rc;
   const bool fuse = dbias != nullptr;
   float* bias_partial = fuse ? workspace + static_cast<size_t>(splits) * Nout * Kout : nullptr;
-  const int stage_bytes = (kBM + BN) * kBK * 2 + (fuse ? 8192 : 0);
-  const int smem = kWgStages * stage_bytes + static_cast<int>(sizeof(WgSmemTail)) + 1024;
+  const int stage_bytes = (mh * kBM + BN) * kBK * 2 + (fuse ? 8192 : 0);
+  int stages = (227 * 1024 - static_cast<int>(sizeof(WgSmemTail)) - 1024) / stage_bytes;
+  if (stages > kWgStages) stages = kWgStages;
+  if (stages < 2) return WM_ERR_SHAPE;
+  const int smem = stages * stage_bytes + static_cast<int>(sizeof(WgSmemTail)) + 1024;
   if (cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return WM_ERR_CUDA;
-  dim3 grid((Nout + kBM - 1) / kBM, (Kout + BN - 1) / BN, splits);
-  gemm_wgrad_kernel<<<grid, kWgradThreads, smem, stream>>>(tmA, tmB, Mtok, Nout, Kout, BN, tps, workspace, bias_partial);
+  dim3 grid(((Nout + kBM - 1) / kBM + mh - 1) / mh, (Kout + BN - 1) / BN, splits);
+  gemm_wgrad_kernel<<<grid, kWgradThreads, smem, stream>>>(tmA, tmB, Mtok, Nout, Kout, BN, tps, workspace, bias_partial, mh, stages);
   WM_COUNT_LAUNCH();
   if (cudaGetLastError() != cudaSuccess) return WM_ERR_CUDA;
   const int64_t n = static_cast<int64_t>(rows_valid) * cols_valid;
