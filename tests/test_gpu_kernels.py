@@ -235,6 +235,8 @@ def test_gemm_straight_line_epilogues_match_the_generic_body(M, N, K):
 @pytest.mark.parametrize("Mtok,Nout,Kout", [
     (64, 128, 64), (1000, 576, 576), (777, 64, 576), (3000, 200, 600), (4097, 1728, 576), (2048, 576, 2304),
     (1500, 48, 192), (5000, 576, 64), (365 * 8, 336, 1344), (46720, 200, 200),
+    # big enough for two A^T tiles per CTA (wgrad_pick_mh): even / odd tile counts, a clipped last tile, narrow outputs
+    (16384 + 77, 1728, 576), (20000, 2304, 576), (17000, 640, 192), (16500, 200, 128), (18000, 576, 576),
 ])
 def test_gemm_wgrad(Mtok, Nout, Kout):
     a = _bf(Mtok, Nout, seed=9)
@@ -245,6 +247,18 @@ def test_gemm_wgrad(Mtok, Nout, Kout):
     out2, db = ops.gemm_wgrad(a, b, want_bias_grad=True)
     assert torch.equal(out, out2), "split-K wgrad is not deterministic"
     _cmp(f"wgrad bias {Mtok}x{Nout}", db, a.double().sum(0), 2e-3, 2e-3 * math.sqrt(Mtok))
+    # one and two A^T tiles per CTA (forced): the same product under another token-split plan
+    from weathermodel_b200._lib import lib
+    outs = {}
+    try:
+        for mh in (1, 2):
+            lib().wm_set_option(b"wgrad_mh", mh)
+            outs[mh] = ops.gemm_wgrad(a, b, want_bias_grad=True)
+    finally:
+        lib().wm_set_option(b"wgrad_mh", 0)
+    _cmp("wgrad: two tiles per CTA vs one", outs[2][0], outs[1][0], 1e-4, 1e-4 * math.sqrt(Mtok))
+    _cmp("wgrad bias: two tiles per CTA vs one", outs[2][1], outs[1][1], 1e-4, 1e-4 * math.sqrt(Mtok))
+    assert ops.device_error() == 0
 
 
 # ------------------------------------------------------------------------------------------ masks
