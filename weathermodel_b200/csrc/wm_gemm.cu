@@ -4,12 +4,14 @@
 // (reference: src/pretraining/models/weatherbert.py:34,45-56; torch/nn/modules/transformer.py:944-982)
 //
 //   gemm_tn   : C[M,N] = epilogue( A[M,K] . B[N,K]^T )   A,B bf16 row-major (K contiguous), fp32 acc.
-//               Persistent, warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (one thread),
-//               warps2-5 = epilogue (TMEM -> regs -> fused bias/ReLU/dropout/residual -> global).
-//               TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of i+1.
-//               Used for forward linears and for dgrad (with a transposed bf16 weight copy as B).
+//               Persistent, warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (whole warp, elected lane),
+//               8 / 12 / 16 epilogue warps (TMEM -> regs -> fused bias/ReLU/dropout/gate/residual -> global, shared-memory
+//               staging or TMA-store boxes). TMEM holds two accumulator stages so the epilogue of tile i overlaps the
+//               MMAs of i+1. Used for forward linears and for dgrad (with a transposed bf16 weight copy as B).
+//   gemm_tn2  : the same on CTA pairs (cta_group::2, 256 x BN tiles, each CTA stages half of B).
 //   gemm_wgrad: P[s][Nout,Kout] = A[Mtok,Nout]^T . B[Mtok,Kout] over token slice s (split-K),
-//               both operands MN-major straight from the token-major activations (no transposes),
+//               both operands MN-major straight from the token-major activations (no transposes), one or two
+//               128-row A^T tiles per CTA against the same B tile, bias gradient from an all-ones B chunk,
 //               fp32 partials reduced deterministically by wgrad_reduce.
 #include "wm_kernels.h"
 
@@ -103,10 +105,10 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxStages = 8;
 // warp0 TMA, warp1 MMA, then kEW epilogue warps: kEW / 4 per TMEM lane quarter, each owning BN / (kEW / 4) columns.
-// The epilogue is latency-bound per warp (ncu source view: ~1,070 cycles per 16-column chunk at ~130 issued
-// instructions -- fixed-latency waits, TMEM-load and smem scoreboards, instruction fetch), and with K = 576 it, not
-// the MMAs (4,608 cycles per 128 x 256 tile), set the pace (8,590 cycles per tile). 16 warps (4 per scheduler) halve
-// the per-tile epilogue time; 8 remain for tiles whose width is not a multiple of 64.
+// With K = 576 the epilogue, not the MMAs (4,608 cycles per 128 x 256 tile), sets the pace. Round 1 measured ~1,070
+// cycles per 16-column chunk at ~130 issued instructions with the run-time-flag body (hence 16 warps, 4 per
+// scheduler); the straight-line bodies below (epi_fast16: 62-165 instructions per chunk) made 8 and 16 warps
+// equivalent on most sites. 8 remain the only choice for tiles whose width is not a multiple of 64.
 constexpr int gemm_threads(int ew) { return 64 + 32 * ew; }
 constexpr int kWgradThreads = 192;
 constexpr uint32_t kTmemCols = 512;
