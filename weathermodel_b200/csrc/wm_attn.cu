@@ -423,9 +423,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
               // (The slice that holds key S - 1 takes the same loop with warp-uniform bounds: its invalid columns are
               // skipped, not computed under per-element predicates -- the four warps that own it are otherwise the
               // stragglers every other warp of the tile waits for at the next barrier.)
-              if (DROP) {
+              if (DROP && k0 + 32 <= S) {  // whole slice: no bounds at all in the loop
                 const uint32_t x0 = (rowbase + static_cast<uint32_t>(k0 >> 4)) * 4u;
-                const int nv = S - k0;  // >= 32 for a whole slice
+                uint32_t bits = 0u;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                  const DropWords f = drop_flags4(x0 + w, dkeys, add2);
+                  float xa, xb, xc, xd;
+                  f2_unpack(f2_fma(f2_pack_u(cur[4 * w], cur[4 * w + 1]), c2p, mnegp), xa, xb);
+                  f2_unpack(f2_fma(f2_pack_u(cur[4 * w + 2], cur[4 * w + 3]), c2p, mnegp), xc, xd);
+                  const float ea = fast_exp2(xa), eb = fast_exp2(xb), ec = fast_exp2(xc), ed = fast_exp2(xd);
+                  lsum2 = f2_add(lsum2, f2_add(f2_pack(ea, eb), f2_pack(ec, ed)));
+                  const uint32_t ma = drop_pair_mask(f.a), mb = drop_pair_mask(f.b);
+                  pk[2 * w] = attn_pack2(ea, eb) & ma;
+                  pk[2 * w + 1] = attn_pack2(ec, ed) & mb;
+                  bits |= (ma & (0x00010001u << (2 * w))) | (mb & (0x00010001u << (2 * w + 1)));
+                }
+                if (drop_words) drop_words[attn_drop_word_index(item, k0 >> 7, q >> 6, (k0 >> 5) & 3, q & 63)] = bits;
+              } else if (DROP) {  // the slice that holds key S - 1 (or lies behind it): warp-uniform bounds, invalid columns skipped
+                const uint32_t x0 = (rowbase + static_cast<uint32_t>(k0 >> 4)) * 4u;
+                const int nv = S - k0;
                 uint32_t bits = 0u;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) {
