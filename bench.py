@@ -339,7 +339,7 @@ def run_ours(args, rank, world, local_rank):
     # Launch-bound workloads (everything but WeatherFormer large): the step body is recorded once as a CUDA graph and
     # replayed, exactly as BaseTrainer does for these shapes (graph_step.CapturedTrainStep). Masks are drawn outside.
     captured = [None]
-    use_graph = world == 1 and (args.graph == "1" or (args.graph == "auto" and args.workload != "large"))
+    use_graph = world == 1 and args.graph in ("1", "auto")  # (the trainer's own rule: base_trainer._graph_eligible)
 
     def step(batch):
         if not is_yield:
@@ -528,7 +528,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-trainer", action="store_true", help="skip the trainer-level e2e leg")
     ap.add_argument("--graph", default="auto", choices=["auto", "0", "1"],
-                    help="replay the step as a CUDA graph (auto: every workload but large, single GPU)")
+                    help="replay the step as a CUDA graph (auto: single GPU, as the trainer does)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", 0))
