@@ -365,7 +365,10 @@ static inline int ln_pick_width(int D) { return ln_slots(D, 4) < ln_slots(D, 8) 
 // kRows rows per warp: the loads of ALL its rows are issued before the first reduction, so a warp keeps kRows x 1152 B
 // (D = 576) in flight instead of one row's -- at one row per warp and 32 resident warps an SM had 36 KB of reads in
 // flight, short of what 6.5 TB/s at ~1 us latency asks for (the kernel ran at 4.7 TB/s).
-constexpr int kLnFwdRows = 2;
+#ifndef WM_LN_FWD_ROWS
+#define WM_LN_FWD_ROWS 2
+#endif
+constexpr int kLnFwdRows = WM_LN_FWD_ROWS;
 template <int kW>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
