@@ -192,7 +192,18 @@ class StreamingDataset(torch.utils.data.IterableDataset):
                 ready.record(self._copy_stream)
                 if big is not None:
                     _PINNED.release(self._staging, ready)
-        return out[0], out[1], out[2], ready, None
+        # The cutoff-year filter almost never drops anything; whether it does is decided HERE, on the host copy of the
+        # index columns and with the same float32 operations in the same order as the device expression in
+        # _chunk_samples (IEEE mul / add / div on both sides: identical results), so that the training loop does not have
+        # to read a flag back from the GPU -- that read drained the launch queue once per chunk.
+        seq_len = weather.shape[1]
+        idx = index.float()
+        t = torch.arange(seq_len, dtype=torch.float32)
+        years_host = 1984.0 + ((idx[:, 0:1] * 365 + t) * idx[:, 1:2]) / 365
+        keep_all = bool((years_host.max(dim=1).values < self.cutoff_year).all())
+        if os.environ.get("WM_LOADER_HOST_CUTOFF", "1") == "0":  # (A/B switch: let the device decide, with its host sync)
+            keep_all = None
+        return out[0], out[1], out[2], ready, keep_all
 
     def _weather_via_pinned(self, path, weather) -> Optional[torch.Tensor]:
         """The weather tensor of a mapped chunk file, read with plain read() calls straight into a re-used page-locked
@@ -248,6 +259,7 @@ class StreamingDataset(torch.utils.data.IterableDataset):
             torch.cuda.current_stream(torch.device(self.device)).wait_event(loaded[3])
             for t in loaded[:3]:
                 t.record_stream(torch.cuda.current_stream(torch.device(self.device)))
+        keep_all = loaded[4] if len(loaded) == 5 else None  # (CUDA prefetch path: decided on the host, see _load_chunk)
         weather, coords, index = loaded[:3]
         n, seq_len, n_features = weather.shape
         interval = index[:, 1:2].contiguous()
@@ -258,9 +270,10 @@ class StreamingDataset(torch.utils.data.IterableDataset):
         if self.shuffle and n > 1:
             perm = torch.randperm(n, device=self.device)
             weather, coords, years, interval, mask = weather[perm], coords[perm], years[perm], interval[perm], mask[perm]
-        keep = years.max(dim=1).values < self.cutoff_year
-        if not bool(keep.all()):  # one host sync per chunk (the reference syncs once per sample)
-            weather, coords, years, interval, mask = weather[keep], coords[keep], years[keep], interval[keep], mask[keep]
+        if keep_all is not True:
+            keep = years.max(dim=1).values < self.cutoff_year
+            if not bool(keep.all()):  # one host sync per chunk (the reference syncs once per sample)
+                weather, coords, years, interval, mask = weather[keep], coords[keep], years[keep], interval[keep], mask[keep]
         return weather, coords, years, interval, mask
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, ...]]:
