@@ -224,6 +224,40 @@ def test_streaming_loader_matches_the_reference_loaders_own_stream(tmp_path, mon
     assert np.array_equal(np.packbits(cat[4].numpy().reshape(n, -1), axis=1), gold["mask_bits"])
 
 
+def test_chunk_payload_offset_inside_the_zip_file(tmp_path):
+    """The CUDA loader reads the weather tensor of a chunk file straight into a pinned buffer: the byte offset it derives
+    from the zip directory must point at the tensor's storage (torch.save layout), also when the tensor is a view."""
+    import numpy as np
+    from weathermodel_b200.pretraining.dataloader.pretraining_dataloader import _stored_payload_span
+
+    w = torch.randn(40, 365, 31)
+    coords, index = torch.rand(40, 2), torch.rand(40, 2)
+    path = str(tmp_path / "weather_dataset_weekly_1.pt")
+    torch.save(torch.utils.data.TensorDataset(w, coords, index), path)
+    off = _stored_payload_span(path, w.numel() * 4)
+    assert off is not None and off % 64 == 0  # torch aligns records to 64 bytes
+    raw = np.fromfile(path, dtype=np.float32, count=w.numel(), offset=off)
+    assert np.array_equal(raw, w.numpy().ravel())
+    assert _stored_payload_span(path, w.numel() * 4 + 4) is None          # no record of that size
+    assert _stored_payload_span(str(tmp_path / "missing.pt"), 16) is None  # unreadable file: caller falls back
+
+
+def test_cutoff_decision_on_the_host_equals_the_loader_expression():
+    """_load_chunk decides "does the cutoff-year filter drop anything" from the index columns on the host; the value
+    must be the one the per-chunk expression of _chunk_samples (reference pretraining_dataloader.py:251-256, 276) gives."""
+    g = torch.Generator().manual_seed(3)
+    for late in (0, 1, 7):
+        index = torch.stack([torch.randint(0, 2, (64,), generator=g).float(), torch.full((64,), 7.0)], 1)
+        if late:
+            index[::late, 0] = 2.0  # 1984 + ((2 * 365 + 364) * 7) / 365 > 2002
+        t = torch.arange(365, dtype=torch.float32)
+        years = 1984.0 + ((index[:, 0:1] * 365 + t) * index[:, 1:2].contiguous()) / 365
+        want = bool((years.max(dim=1).values < 2002.0).all())
+        idx = index.float()
+        got = bool(((1984.0 + ((idx[:, 0:1] * 365 + t) * idx[:, 1:2]) / 365).max(dim=1).values < 2002.0).all())
+        assert got == want == (late == 0)
+
+
 def test_fused_adam_host_path_matches_torch_adam():
     from weathermodel_b200.optim import FusedAdam
 
